@@ -1,0 +1,53 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE.  Builds the UNMODIFIED reference (yuansliu/minicom) from
+# the sources where they lie under /root/reference/src into oracle/_ref/, one
+# binary per (read length, mode), with link-time wrappers (mcref_wrap.cpp) for
+# phase timing and state dumps.  Nothing is copied from the reference; the only
+# generated file is config.h, which the reference's own wrapper script also
+# generates per run (minicom:56-91, :187-213).
+#
+# usage: build_ref.sh <readlen> <sg|order|pe>
+# output: oracle/_ref/minicom_ref_L<readlen>_<mode>   (+ build_L<..>/ objects)
+#         oracle/_ref/decompress                      (once)
+set -euo pipefail
+L=$1; MODE=$2
+HERE=$(cd "$(dirname "$0")" && pwd)
+REF=${MC_REFERENCE_SRC:-/root/reference/src}
+OUT=$HERE/../_ref
+B=$OUT/build_L${L}_${MODE}
+[ -d "$REF" ] || { echo "reference sources not found at $REF" >&2; exit 3; }
+mkdir -p "$B"
+{
+  echo "#pragma once"
+  echo "#include \"mcref_cfg.h\""
+  if [ "$MODE" = order ]; then echo "#define ORDER"; echo "int cmpcluster3(const void *a_, const void *b_);"; fi
+  if [ "$MODE" = pe ]; then echo "#define _PE"; echo "int cmpcluster3(const void *a_, const void *b_);"; fi
+  echo "#define readlen $L"
+  echo "#define num_thr mcref_cfg_int(\"MC_T\", 1)"
+  echo "#define uniqid mcref_cfg_str(\"MC_UNIQID\", \"umc\")"
+  echo "#define output mcref_cfg_str(\"MC_TMPDIR\", \"output_mc/\")"
+  echo "#define inik mcref_cfg_int(\"MC_K\", 0)"
+  echo "#define inithr mcref_cfg_int(\"MC_E\", 0)"
+  echo "#define inimaxthr mcref_cfg_int(\"MC_EMAX\", 0)"
+  echo "#define inistep mcref_cfg_int(\"MC_STEP\", 0)"
+  echo "#define ininumdict mcref_cfg_int(\"MC_S\", 0)"
+  echo "#define iniw mcref_cfg_int(\"MC_W\", 0)"
+  echo "#define inim mcref_cfg_int(\"MC_M\", 0)"
+  echo "#define inicbthr mcref_cfg_int(\"MC_CBTHR\", 0)"
+  echo "#define inimaxrounds mcref_cfg_int(\"MC_MAXROUNDS\", 0)"
+} > "$B/config.h"
+# -march=x86-64-v3 instead of the reference's -march=native so the binary also runs on the GPU box's host CPU
+CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$HERE -I$REF"
+OBJS="bseq misc preprocess sketch bbhashdict kthread_reads kthread_bucket kthread_idx kthread_cb kthread_dump kthread_hash_realign minicommain"
+[ "$MODE" = pe ] && OBJS="$OBJS kthread_dump_pe"
+pids=()
+for f in $OBJS; do g++ $CXXFLAGS -c "$REF/$f.c" -o "$B/$f.o" & pids+=($!); done
+g++ $CXXFLAGS -c "$HERE/mcref_wrap.cpp" -o "$B/mcref_wrap.o" & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+WRAP="-Wl,--wrap=_Z12kt_for_readsiP7reads_tl -Wl,--wrap=_Z13kt_for_bucketiP7reads_tl -Wl,--wrap=_Z17mm_idx_generationiP8mm_idx_t -Wl,--wrap=_Z15combine_clusteriP7reads_tPi -Wl,--wrap=_Z12realign_hashiP7reads_tii"
+ALL=""; for f in $OBJS; do ALL="$ALL $B/$f.o"; done
+g++ -O3 -fopenmp $ALL "$B/mcref_wrap.o" $WRAP -o "$OUT/minicom_ref_L${L}_${MODE}" -lm -lz -lpthread
+if [ ! -x "$OUT/decompress" ]; then
+  g++ -O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -include stdint.h -I$B -I$HERE -I$REF "$REF/decompress.c" -o "$OUT/decompress" -lm -lz -lpthread
+fi
+echo "built $OUT/minicom_ref_L${L}_${MODE}"
