@@ -1,0 +1,212 @@
+/* minicom_b200.h — C-ABI of the B200-native minicom front end.
+ *
+ * One shared library, libminicom_b200.so (hand-written sm_100a CUDA behind
+ * `extern "C"` entry points; plain pointers and sizes, no C++/torch types).
+ * Every entry point replaces one function of the reference's hot path
+ * (yuansliu/minicom, paths relative to /root/reference/src):
+ *
+ *   mcb_for_reads*      <- kt_for_reads        kthread_reads.c:247  (process_reads :40, mm_sketch_two sketch.c:238)
+ *   mcb_for_bucket      <- kt_for_bucket       kthread_bucket.c:562 (process_bucket :381, construct_ref :69,
+ *                                                                    mm_sketch_lh_ori sketch.c:116)
+ *   mcb_idx_build       <- mm_idx_generation   kthread_idx.c:170    (worker_post :116, radix_sort_128x ksort.h:108)
+ *   mcb_idx_get         <- mm_idx_get          kthread_idx.c:84
+ *   mcb_realign         <- realign_hash        kthread_hash_realign.c:569 (singleRead2bitset bbhashdict.c:127,
+ *                                               constructdictionary_realign :3, realign_hash_search :316)
+ *   mcb_sketch_lh_host  <- mm_sketch_lh_ori    sketch.c:116  (per-contig call made by the host contig merger,
+ *                                               kthread_cb.c:234,365,418 — a boundary helper, not the batched path)
+ *
+ * All functions return 0 on success and a negative MCB_E* code on failure;
+ * mcb_last_error() returns a human-readable message.  There is no CPU
+ * fallback: without a usable CUDA device mcb_create() fails.
+ *
+ * Result structs hold pointers into context-owned pinned host memory that
+ * stay valid until the next call of the same entry point or mcb_destroy().
+ */
+#ifndef MINICOM_B200_H
+#define MINICOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB_OK            0
+#define MCB_ECUDA        -1   /* CUDA runtime error (message has the call site) */
+#define MCB_EINVAL       -2   /* bad argument / unsupported option value */
+#define MCB_ESTATE       -3   /* call order violated (e.g. mcb_for_bucket before mcb_for_reads) */
+#define MCB_EINPUT       -4   /* input data outside the supported domain (see message) */
+#define MCB_ENOMEM       -5
+
+/* The reference's unit of exchange, mm128_t (breads.h:15-17):
+ *   x = hash64(canonical k-mer), y = id<<32 | last_pos<<1 | strand. */
+typedef struct { uint64_t x, y; } mcb_tuple;
+
+/* Run-time copy of the reference's compile-time options (minicommain.c:81-143,
+ * preprocess.c:87-107).  All fields are the *resolved* values (defaults applied
+ * by the caller, see mcb_resolve_params). */
+typedef struct {
+	int32_t readlen;         /* L, 1..256                      (config.h readlen; minicom:51) */
+	int32_t k;               /* -k, <= 31                      (minicommain.c:92-98) */
+	int32_t b;               /* bucket bits, 14                (minicommain.c:175) */
+	int32_t rw;              /* -w contig minimizer window     (preprocess.c:89-107) */
+	int32_t first_mininum;   /* -m minimizers indexed / contig (minicommain.c:117-119) */
+	int32_t diff_threshold;  /* -e                             (minicommain.c:100-102) */
+	int32_t max_rounds;      /* hidden -R, default 35          (minicommain.c:64,127) */
+	int32_t device;          /* CUDA device ordinal */
+} mcb_params;
+
+/* Fill *p from the reference's raw option macros (0 = "not given"), exactly as
+ * main()/pre_process() derive them: k=31 (17 if L<80); e=4; m=6; max_rounds=35
+ * (lowered only if 0<inimaxrounds<35); rw = L/2-k (L>=70) else 3, overridden by iniw>0. */
+void mcb_resolve_params(mcb_params *p, int readlen, int inik, int inithr, int iniw, int inim, int inimaxrounds);
+
+typedef struct mcb_ctx mcb_ctx;
+
+int  mcb_create(const mcb_params *p, mcb_ctx **out);
+void mcb_destroy(mcb_ctx *ctx);
+const char *mcb_last_error(void);
+const char *mcb_version(void);
+
+/* ------------------------------------------------------------------ */
+/* kt_for_reads (kthread_reads.c:247)                                   */
+/* ------------------------------------------------------------------ */
+
+/* Read classes in the order process_reads() tests them (kthread_reads.c:84-226). */
+enum {
+	MCB_CLS_SKETCHED = 0,  /* N-replaced (if any N), sketched, goes to the buckets   :182-218 */
+	MCB_CLS_ALLA     = 1,  /* sp->allA_id   :84  */
+	MCB_CLS_ALLT     = 2,  /* sp->allT_id   :95  */
+	MCB_CLS_ALLN     = 3,  /* sp->allN_id   :106 */
+	MCB_CLS_FPA      = 4,  /* reads->fpA_id :113 */
+	MCB_CLS_FPT      = 5,  /* reads->fpT_id :118 */
+	MCB_CLS_FPN      = 6,  /* reads->fpN_id :123 */
+	MCB_CLS_NFILE    = 7   /* reads->Nfile_id :219 (more than 0.4*L N) */
+};
+
+typedef struct {
+	uint64_t n_reads;
+	const uint8_t *cls;          /* [n_reads] MCB_CLS_* */
+	/* reads that contain at least one 'N', ascending rid (seq->n_pos, kthread_reads.c:69-80) */
+	uint64_t n_nreads;
+	const uint32_t *nread_rid;   /* [n_nreads] */
+	const uint8_t  *nread_repl;  /* [n_nreads] replacement base 'A'/'C'/'G'/'T' for sketched reads, 0 otherwise (:185-204) */
+	const uint64_t *nread_off;   /* [n_nreads+1] offsets into npos */
+	const uint32_t *npos;        /* N positions, ascending within a read */
+	uint64_t n_sketched;         /* reads that produced a tuple */
+} mcb_reads_result;
+
+/* rows: host memory, n*L bytes, read i at rows+i*L (no terminators), characters in {A,C,G,T,N}. */
+int mcb_for_reads(mcb_ctx *ctx, const char *rows, uint64_t n, mcb_reads_result *res);
+/* Same, gathering from scattered NUL-terminated strings: string i is *(const char**)((const char*)first_seq_ptr + i*stride)
+ * (for the reference: &reads->seq[0].seq with stride sizeof(bseq1_t), bseq.h:10-16).  n_threads host threads gather. */
+int mcb_for_reads_ptrs(mcb_ctx *ctx, const void *first_seq_ptr, size_t stride, uint64_t n, int n_threads, mcb_reads_result *res);
+/* Same with the rows already resident in device memory (d_rows: device pointer, n*L bytes). */
+int mcb_for_reads_device(mcb_ctx *ctx, const char *d_rows, uint64_t n, mcb_reads_result *res);
+
+/* Test/debug view of B[0] (kthread_reads.c:213-218): one tuple per read in rid order,
+ * {~0,~0} for reads that were not sketched.  out: host, n_reads tuples. */
+int mcb_debug_read_tuples(mcb_ctx *ctx, mcb_tuple *out);
+/* Batched mm_sketch_two (sketch.c:238) over reads already loaded, with an arbitrary k (used by rounds >= 2). */
+int mcb_debug_sketch_two(mcb_ctx *ctx, const uint32_t *rids, uint64_t n, int k, mcb_tuple *out);
+/* Copy the 2-bit packed, N-replaced reads back as ASCII rows (n_reads*L bytes). */
+int mcb_debug_unpack_reads(mcb_ctx *ctx, char *rows_out);
+
+/* ------------------------------------------------------------------ */
+/* kt_for_bucket (kthread_bucket.c:562)                                 */
+/* ------------------------------------------------------------------ */
+typedef struct {
+	/* seed contigs in the order the single-threaded reference creates them:
+	 * round, bucket, minimizer ascending (reads->clusters[0][0]) */
+	uint64_t n_clusters;
+	const uint32_t *cl_n;        /* [n_clusters] members per cluster (cluster_t.n) */
+	const uint64_t *cl_a_off;    /* [n_clusters+1] */
+	const uint64_t *cl_a;        /* members: rid<<32 | offset<<1 | dir (cluster_t.a, kthread_bucket.c:349) */
+	const uint64_t *cl_ref_off;  /* [n_clusters+1] */
+	const char     *cl_ref;      /* consensus strings, concatenated, no terminators (cluster_t.ref) */
+	/* reads->sg in push order (kthread_bucket.c:198-203,402-413,482-485) */
+	uint64_t n_sg;
+	const uint32_t *sg;
+	/* tuples pushed into reads->mi[0] (kthread_bucket.c:458-474): for cluster c, tuples mi[c*m .. c*m+mi_cnt[c]) */
+	const uint8_t  *mi_cnt;      /* [n_clusters] <= first_mininum */
+	const mcb_tuple *mi;         /* [n_clusters*first_mininum] */
+	int32_t rounds;              /* rounds executed (kmer = k-1 .. k-rounds) */
+	uint64_t n_sketched_total;   /* tuples sketched over all rounds (N_sk of the roofline formula) */
+	uint64_t n_grouped;          /* reads that sat in a group of >=2 (N_grp) */
+} mcb_bucket_result;
+
+int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res);
+
+/* ------------------------------------------------------------------ */
+/* mm_idx_generation / mm_idx_get (kthread_idx.c:170,84)                */
+/* ------------------------------------------------------------------ */
+typedef struct mcb_index mcb_index;
+
+/* tuples: host, bucket-major (bucket = x & (2^b-1)), inside a bucket in push order;
+ * bucket_off: [2^b+1].  The index reproduces the reference's posting order
+ * (radix_sort_128x is unstable above 64 elements; ksort.h:108-157). */
+int mcb_idx_build(mcb_ctx *ctx, const mcb_tuple *tuples, const uint64_t *bucket_off, mcb_index **out);
+/* Same as mcb_idx_build but the per-bucket arrays are still scattered: bucket i has
+ * cnt[i] tuples at ptrs[i] (the reference's mi->B[i].a.{a,n}). */
+int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptrs, const uint64_t *cnt, mcb_index **out);
+/* Host lookup; thread-safe; returns pointer to *n postings (y values) or NULL. */
+const uint64_t *mcb_idx_get(const mcb_index *idx, uint64_t minier, int *n);
+void mcb_idx_destroy(mcb_index *idx);
+/* Introspection for tests: number of distinct keys and postings. */
+void mcb_idx_stats(const mcb_index *idx, uint64_t *n_keys, uint64_t *n_post);
+
+/* ------------------------------------------------------------------ */
+/* realign_hash (kthread_hash_realign.c:569)                            */
+/* ------------------------------------------------------------------ */
+typedef struct {
+	/* reads claimed by contigs, in the exact order the single-threaded reference appends them
+	 * (contig, window jj, forward-then-reverse, dictionary l ascending, sg index descending) */
+	uint64_t n_claims;
+	const uint32_t *claim_contig; /* index into the contig list passed in */
+	const uint32_t *claim_sg;     /* index into sg (sg_flag[claim_sg]=true) */
+	const uint64_t *claim_y;      /* rid<<32 | jj<<1 | dir  (kthread_hash_realign.c:405,472) */
+	/* singles diverted to the near-poly-A / near-poly-T lists (bbhashdict.c:157-216), ascending sg index */
+	uint64_t n_fpA, n_fpT;
+	const uint32_t *fpA_sg, *fpT_sg;
+	/* work counters for the roofline formula */
+	uint64_t n_windows, n_probes, n_candidates, n_dict_keys;
+	int32_t numdict;              /* numdict_s actually used */
+} mcb_realign_result;
+
+/* sg: host, n_sg read ids (reads->sg after updateSingle); refs/ref_off: host, contig consensus strings
+ * concatenated (ref_off[n_contigs+1]); threshold: the current step of the -e/-S/-E schedule;
+ * maxsearch: the reference's global (500, or 2000 when sg.n<=5M, preprocess.c:169-172);
+ * ininumdict: raw -s value (0 = not given), resolved as setglobalarrays_realign does (:150-171). */
+int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off,
+                uint64_t n_contigs, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res);
+
+/* ------------------------------------------------------------------ */
+/* host-side boundary helpers                                           */
+/* ------------------------------------------------------------------ */
+/* mm_sketch_lh_ori (sketch.c:116): windowed (w,k)-minimizers of one string.  Writes at most cap tuples to out,
+ * returns the number the reference would have produced (may exceed cap). */
+int64_t mcb_sketch_lh_host(const char *str, int len, int w, int k, uint32_t rid, mcb_tuple *out, int64_t cap);
+/* mm_sketch_two (sketch.c:238) for one string (host; used by tests and by INTEGRATION examples). */
+void mcb_sketch_two_host(const char *str, int len, int k, uint32_t rid, mcb_tuple *out);
+/* hash64 (sketch.c:27) */
+uint64_t mcb_hash64(uint64_t key, uint64_t mask);
+
+/* ------------------------------------------------------------------ */
+/* measurement                                                          */
+/* ------------------------------------------------------------------ */
+/* Device-time accounting (CUDA events on the library's stream).  Timer names: "for_reads", "for_bucket",
+ * "idx_build", "realign" (whole entry point, device work only), "h2d", "d2h", and per-kernel names "k:<kernel>".
+ * mcb_timer_get returns accumulated milliseconds and the launch count; mcb_timers_reset zeroes everything. */
+void   mcb_timers_enable(mcb_ctx *ctx, int on);
+void   mcb_timers_reset(mcb_ctx *ctx);
+double mcb_timer_get(mcb_ctx *ctx, const char *name, uint64_t *count);
+/* Writes "name ms count\n" lines for every timer into buf (NUL-terminated, truncated to cap); returns needed size. */
+size_t mcb_timers_dump(mcb_ctx *ctx, char *buf, size_t cap);
+/* Total kernels launched by this context since creation / last reset. */
+uint64_t mcb_kernel_launches(mcb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINICOM_B200_H */

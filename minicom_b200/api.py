@@ -1,0 +1,334 @@
+"""ctypes binding of libminicom_b200.so (include/minicom_b200.h) for tests, bench.py and smoke().
+
+This is plumbing only: every function forwards to the C-ABI entry point of the same name and copies the
+context-owned result arrays into numpy arrays.  There is no Python or CPU implementation of the path here; if the
+library (or a CUDA device) is missing the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libminicom_b200.so")
+
+CLS_NAMES = ["sketched", "allA", "allT", "allN", "fpA", "fpT", "fpN", "Nfile"]
+
+
+class McbError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("readlen", C.c_int32), ("k", C.c_int32), ("b", C.c_int32), ("rw", C.c_int32),
+                ("first_mininum", C.c_int32), ("diff_threshold", C.c_int32), ("max_rounds", C.c_int32),
+                ("device", C.c_int32)]
+
+
+class _ReadsResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("cls", C.c_void_p), ("n_nreads", C.c_uint64), ("nread_rid", C.c_void_p),
+                ("nread_repl", C.c_void_p), ("nread_off", C.c_void_p), ("npos", C.c_void_p), ("n_sketched", C.c_uint64)]
+
+
+class _BucketResult(C.Structure):
+    _fields_ = [("n_clusters", C.c_uint64), ("cl_n", C.c_void_p), ("cl_a_off", C.c_void_p), ("cl_a", C.c_void_p),
+                ("cl_ref_off", C.c_void_p), ("cl_ref", C.c_void_p), ("n_sg", C.c_uint64), ("sg", C.c_void_p),
+                ("mi_cnt", C.c_void_p), ("mi", C.c_void_p), ("rounds", C.c_int32), ("n_sketched_total", C.c_uint64),
+                ("n_grouped", C.c_uint64)]
+
+
+class _RealignResult(C.Structure):
+    _fields_ = [("n_claims", C.c_uint64), ("claim_contig", C.c_void_p), ("claim_sg", C.c_void_p), ("claim_y", C.c_void_p),
+                ("n_fpA", C.c_uint64), ("n_fpT", C.c_uint64), ("fpA_sg", C.c_void_p), ("fpT_sg", C.c_void_p),
+                ("n_windows", C.c_uint64), ("n_probes", C.c_uint64), ("n_candidates", C.c_uint64),
+                ("n_dict_keys", C.c_uint64), ("numdict", C.c_int32)]
+
+
+EXPORTS = [
+    "mcb_resolve_params", "mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version",
+    "mcb_for_reads", "mcb_for_reads_ptrs", "mcb_for_reads_device",
+    "mcb_debug_read_tuples", "mcb_debug_sketch_two", "mcb_debug_unpack_reads",
+    "mcb_for_bucket", "mcb_idx_build", "mcb_idx_build_scattered", "mcb_idx_get", "mcb_idx_destroy", "mcb_idx_stats",
+    "mcb_realign", "mcb_sketch_lh_host", "mcb_sketch_two_host", "mcb_hash64",
+    "mcb_timers_enable", "mcb_timers_reset", "mcb_timer_get", "mcb_timers_dump", "mcb_kernel_launches",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA library.  Fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise McbError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(or `make -C minicom_b200/csrc`)")
+    lib = C.CDLL(LIB_PATH)
+    lib.mcb_last_error.restype = C.c_char_p
+    lib.mcb_version.restype = C.c_char_p
+    lib.mcb_resolve_params.argtypes = [C.POINTER(Params)] + [C.c_int] * 6
+    lib.mcb_resolve_params.restype = None
+    lib.mcb_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+    lib.mcb_destroy.argtypes = [C.c_void_p]
+    lib.mcb_destroy.restype = None
+    lib.mcb_for_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_ReadsResult)]
+    lib.mcb_for_reads_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_ReadsResult)]
+    lib.mcb_for_reads_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.POINTER(_ReadsResult)]
+    lib.mcb_debug_read_tuples.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mcb_debug_sketch_two.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    lib.mcb_debug_unpack_reads.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mcb_for_bucket.argtypes = [C.c_void_p, C.POINTER(_BucketResult)]
+    lib.mcb_idx_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mcb_idx_build_scattered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mcb_idx_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+    lib.mcb_idx_get.restype = C.c_void_p
+    lib.mcb_idx_destroy.argtypes = [C.c_void_p]
+    lib.mcb_idx_destroy.restype = None
+    lib.mcb_idx_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.mcb_idx_stats.restype = None
+    lib.mcb_realign.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                C.c_int, C.c_int, C.c_int, C.POINTER(_RealignResult)]
+    lib.mcb_sketch_lh_host.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int64]
+    lib.mcb_sketch_lh_host.restype = C.c_int64
+    lib.mcb_sketch_two_host.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+    lib.mcb_sketch_two_host.restype = None
+    lib.mcb_hash64.argtypes = [C.c_uint64, C.c_uint64]
+    lib.mcb_hash64.restype = C.c_uint64
+    lib.mcb_timers_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.mcb_timers_enable.restype = None
+    lib.mcb_timers_reset.argtypes = [C.c_void_p]
+    lib.mcb_timers_reset.restype = None
+    lib.mcb_timer_get.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64)]
+    lib.mcb_timer_get.restype = C.c_double
+    lib.mcb_timers_dump.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.mcb_timers_dump.restype = C.c_size_t
+    lib.mcb_kernel_launches.argtypes = [C.c_void_p]
+    lib.mcb_kernel_launches.restype = C.c_uint64
+    _lib = lib
+    return lib
+
+
+def _view(ptr, n, dtype):
+    if not n or not ptr:
+        return np.zeros(0, dtype=dtype)
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    buf = (C.c_char * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).copy()
+
+
+def resolve_params(readlen, k=0, e=0, w=0, m=0, max_rounds=0, device=0) -> Params:
+    p = Params()
+    load_library().mcb_resolve_params(C.byref(p), readlen, k, e, w, m, max_rounds)
+    p.device = device
+    return p
+
+
+def hash64(key: int, mask: int) -> int:
+    return int(load_library().mcb_hash64(key, mask))
+
+
+def sketch_two_host(seq: bytes, k: int, rid: int):
+    out = np.zeros(2, dtype=np.uint64)
+    load_library().mcb_sketch_two_host(seq, len(seq), k, rid, out.ctypes.data)
+    return int(out[0]), int(out[1])
+
+
+def sketch_lh_host(seq: bytes, w: int, k: int, rid: int) -> np.ndarray:
+    lib = load_library()
+    cap = max(16, len(seq))
+    out = np.zeros((cap, 2), dtype=np.uint64)
+    n = lib.mcb_sketch_lh_host(seq, len(seq), w, k, rid, out.ctypes.data, cap)
+    if n > cap:
+        out = np.zeros((n, 2), dtype=np.uint64)
+        n = lib.mcb_sketch_lh_host(seq, len(seq), w, k, rid, out.ctypes.data, n)
+    return out[:n].copy()
+
+
+@dataclass
+class ReadsResult:
+    cls: np.ndarray
+    nread_rid: np.ndarray
+    nread_repl: np.ndarray
+    nread_off: np.ndarray
+    npos: np.ndarray
+    n_sketched: int
+
+
+@dataclass
+class BucketResult:
+    cl_n: np.ndarray
+    cl_a_off: np.ndarray
+    cl_a: np.ndarray
+    cl_ref_off: np.ndarray
+    cl_ref: np.ndarray
+    sg: np.ndarray
+    mi_cnt: np.ndarray
+    mi: np.ndarray          # (n_clusters, m, 2)
+    rounds: int
+    n_sketched_total: int
+    n_grouped: int
+
+
+@dataclass
+class RealignResult:
+    claim_contig: np.ndarray
+    claim_sg: np.ndarray
+    claim_y: np.ndarray
+    fpA_sg: np.ndarray
+    fpT_sg: np.ndarray
+    n_windows: int
+    n_probes: int
+    n_candidates: int
+    n_dict_keys: int
+    numdict: int
+
+
+class Index:
+    def __init__(self, lib, handle):
+        self._lib, self._h = lib, handle
+
+    def get(self, x: int) -> np.ndarray:
+        n = C.c_int(0)
+        p = self._lib.mcb_idx_get(self._h, int(x), C.byref(n))
+        return _view(p, n.value, np.uint64)
+
+    def stats(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._lib.mcb_idx_stats(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def close(self):
+        if self._h:
+            self._lib.mcb_idx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Context:
+    """One device context = one run of the front end (mcb_ctx)."""
+
+    def __init__(self, params: Params):
+        self.lib = load_library()
+        self.params = params
+        h = C.c_void_p(0)
+        self._check(self.lib.mcb_create(C.byref(params), C.byref(h)))
+        self._h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise McbError(f"minicom_b200 error {rc}: {self.lib.mcb_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- kt_for_reads
+    def _reads_result(self, r: _ReadsResult) -> ReadsResult:
+        nn = r.n_nreads
+        off = _view(r.nread_off, nn + 1, np.uint64)
+        return ReadsResult(_view(r.cls, r.n_reads, np.uint8), _view(r.nread_rid, nn, np.uint32), _view(r.nread_repl, nn, np.uint8),
+                           off, _view(r.npos, int(off[-1]) if len(off) else 0, np.uint32), int(r.n_sketched))
+
+    def for_reads(self, rows: np.ndarray) -> ReadsResult:
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        assert rows.ndim == 2 and rows.shape[1] == self.params.readlen
+        r = _ReadsResult()
+        self._check(self.lib.mcb_for_reads(self._h, rows.ctypes.data, rows.shape[0], C.byref(r)))
+        return self._reads_result(r)
+
+    def for_reads_device(self, dptr: int, n: int) -> ReadsResult:
+        r = _ReadsResult()
+        self._check(self.lib.mcb_for_reads_device(self._h, dptr, n, C.byref(r)))
+        return self._reads_result(r)
+
+    def for_reads_ptrs(self, ptrs: np.ndarray, n_threads: int = 1) -> ReadsResult:
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.uint64)
+        r = _ReadsResult()
+        self._check(self.lib.mcb_for_reads_ptrs(self._h, ptrs.ctypes.data, 8, len(ptrs), n_threads, C.byref(r)))
+        return self._reads_result(r)
+
+    def debug_read_tuples(self, n: int) -> np.ndarray:
+        out = np.zeros((n, 2), dtype=np.uint64)
+        self._check(self.lib.mcb_debug_read_tuples(self._h, out.ctypes.data))
+        return out
+
+    def debug_sketch_two(self, rids: np.ndarray, k: int) -> np.ndarray:
+        rids = np.ascontiguousarray(rids, dtype=np.uint32)
+        out = np.zeros((len(rids), 2), dtype=np.uint64)
+        self._check(self.lib.mcb_debug_sketch_two(self._h, rids.ctypes.data, len(rids), k, out.ctypes.data))
+        return out
+
+    def debug_unpack_reads(self, n: int) -> np.ndarray:
+        out = np.zeros((n, self.params.readlen), dtype=np.uint8)
+        self._check(self.lib.mcb_debug_unpack_reads(self._h, out.ctypes.data))
+        return out
+
+    # -- kt_for_bucket
+    def for_bucket(self) -> BucketResult:
+        r = _BucketResult()
+        self._check(self.lib.mcb_for_bucket(self._h, C.byref(r)))
+        nc, m = r.n_clusters, self.params.first_mininum
+        a_off = _view(r.cl_a_off, nc + 1, np.uint64)
+        r_off = _view(r.cl_ref_off, nc + 1, np.uint64)
+        return BucketResult(_view(r.cl_n, nc, np.uint32), a_off, _view(r.cl_a, int(a_off[-1]) if nc else 0, np.uint64), r_off,
+                            _view(r.cl_ref, int(r_off[-1]) if nc else 0, np.uint8), _view(r.sg, r.n_sg, np.uint32),
+                            _view(r.mi_cnt, nc, np.uint8), _view(r.mi, nc * m * 2, np.uint64).reshape(nc, m, 2),
+                            int(r.rounds), int(r.n_sketched_total), int(r.n_grouped))
+
+    # -- mm_idx_generation
+    def idx_build(self, tuples: np.ndarray, bucket_off: np.ndarray) -> Index:
+        tuples = np.ascontiguousarray(tuples, dtype=np.uint64)
+        bucket_off = np.ascontiguousarray(bucket_off, dtype=np.uint64)
+        assert len(bucket_off) == (1 << self.params.b) + 1
+        h = C.c_void_p(0)
+        self._check(self.lib.mcb_idx_build(self._h, tuples.ctypes.data, bucket_off.ctypes.data, C.byref(h)))
+        return Index(self.lib, h)
+
+    # -- realign_hash
+    def realign(self, sg: np.ndarray, refs: np.ndarray, ref_off: np.ndarray, threshold: int, maxsearch: int, ininumdict: int = 0) -> RealignResult:
+        sg = np.ascontiguousarray(sg, dtype=np.uint32)
+        refs = np.ascontiguousarray(refs, dtype=np.uint8)
+        ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
+        r = _RealignResult()
+        self._check(self.lib.mcb_realign(self._h, sg.ctypes.data, len(sg), refs.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1,
+                                         threshold, maxsearch, ininumdict, C.byref(r)))
+        n = r.n_claims
+        return RealignResult(_view(r.claim_contig, n, np.uint32), _view(r.claim_sg, n, np.uint32), _view(r.claim_y, n, np.uint64),
+                             _view(r.fpA_sg, r.n_fpA, np.uint32), _view(r.fpT_sg, r.n_fpT, np.uint32),
+                             int(r.n_windows), int(r.n_probes), int(r.n_candidates), int(r.n_dict_keys), int(r.numdict))
+
+    # -- measurement
+    def timers_enable(self, on=True):
+        self.lib.mcb_timers_enable(self._h, 1 if on else 0)
+
+    def timers_reset(self):
+        self.lib.mcb_timers_reset(self._h)
+
+    def timers(self) -> dict:
+        need = self.lib.mcb_timers_dump(self._h, None, 0)
+        buf = C.create_string_buffer(need + 16)
+        self.lib.mcb_timers_dump(self._h, buf, need + 16)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.rsplit(" ", 2)
+            out[name] = (float(ms), int(cnt))
+        return out
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.mcb_kernel_launches(self._h))

@@ -1,0 +1,146 @@
+// mcb_api.cu — context lifetime, error reporting, timers and the host-side boundary helpers of the C-ABI.
+#include "mcb_common.cuh"
+#include "mcb_sketch_lh.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+
+static thread_local char g_err[1024] = "";
+
+void mcb_set_error(const char *fmt, ...)
+{
+	va_list ap; va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char *mcb_last_error(void) { return g_err; }
+extern "C" const char *mcb_version(void) { return "minicom_b200 0.1 (sm_100a)"; }
+
+// minicommain.c:92-127 and preprocess.c:89-107
+extern "C" void mcb_resolve_params(mcb_params *p, int readlen, int inik, int inithr, int iniw, int inim, int inimaxrounds)
+{
+	memset(p, 0, sizeof *p);
+	p->readlen = readlen;
+	p->k = readlen < 80 ? 17 : 31;
+	if (inik > 0) p->k = inik;
+	p->diff_threshold = inithr > 0 ? inithr : 4;
+	p->first_mininum = inim > 0 ? inim : 6;
+	p->max_rounds = 35;
+	if (inimaxrounds > 0 && inimaxrounds < p->max_rounds) p->max_rounds = inimaxrounds;
+	p->b = 14;
+	p->rw = readlen >= 70 ? readlen / 2 - p->k : 3;
+	if (iniw > 0) p->rw = iniw;
+	p->device = 0;
+}
+
+extern "C" int mcb_create(const mcb_params *p, mcb_ctx **out)
+{
+	if (!p || !out) { mcb_set_error("mcb_create: null argument"); return MCB_EINVAL; }
+	*out = nullptr;
+	if (p->readlen < 12 || p->readlen > 256) { mcb_set_error("readlen %d out of range [12,256] (minicom:51-54)", p->readlen); return MCB_EINVAL; }
+	if (p->k < 10 || p->k > 31 || p->k > p->readlen) { mcb_set_error("k=%d out of range [10,31]", p->k); return MCB_EINVAL; }
+	if (p->b != 14) { mcb_set_error("bucket bits b=%d unsupported (the reference fixes b=14, minicommain.c:175)", p->b); return MCB_EINVAL; }
+	if (p->rw < 1 || p->rw > MCB_LH_WMAX) { mcb_set_error("contig window rw=%d out of range [1,%d]", p->rw, MCB_LH_WMAX); return MCB_EINVAL; }
+	if (p->first_mininum < 1 || p->first_mininum > 255) { mcb_set_error("first_mininum=%d out of range [1,255]", p->first_mininum); return MCB_EINVAL; }
+	if (p->diff_threshold < 0 || p->max_rounds < 2 || p->max_rounds > 35) { mcb_set_error("bad diff_threshold/max_rounds"); return MCB_EINVAL; }
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev <= 0) {
+		mcb_set_error("no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+		cudaGetLastError();
+		return MCB_ECUDA;
+	}
+	if (p->device < 0 || p->device >= ndev) { mcb_set_error("device %d out of range (have %d)", p->device, ndev); return MCB_EINVAL; }
+	MCB_CUDA(cudaSetDevice(p->device));
+	mcb_ctx *ctx = new mcb_ctx();
+	ctx->prm = *p;
+	ctx->L = p->readlen; ctx->Wd = (p->readlen + 31) / 32; ctx->WS = (ctx->Wd + 1) & ~1;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; mcb_set_error("cudaStreamCreate failed"); return MCB_ECUDA; }
+	ctx->tm.stream = ctx->stream;
+	if (ctx->d_counters.ensure(64 * 8) != MCB_OK) { cudaStreamDestroy(ctx->stream); delete ctx; return MCB_ECUDA; }
+	cudaMemsetAsync(ctx->d_counters.p, 0, 64 * 8, ctx->stream);
+	*out = ctx;
+	return MCB_OK;
+}
+
+extern "C" void mcb_destroy(mcb_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->prm.device);
+	cudaStreamSynchronize(ctx->stream);
+	ctx->tm.collect();
+	for (auto e : ctx->tm.pool) cudaEventDestroy(e);
+	DBuf *db[] = { &ctx->d_ascii, &ctx->d_packed, &ctx->d_cls, &ctx->d_elemA, &ctx->d_elemB, &ctx->d_counters, &ctx->d_nread_rid, &ctx->d_nread_mask, &ctx->d_sort_hist };
+	for (auto b : db) b->release();
+	for (auto &b : ctx->d_scr) b.release();
+	for (auto &b : ctx->d_scan_tmp) b.release();
+	for (auto &b : ctx->d_x) b.release();
+	HBuf *hb[] = { &ctx->h_cls, &ctx->h_nrid, &ctx->h_nrepl, &ctx->h_noff, &ctx->h_npos, &ctx->h_nmask, &ctx->h_counters, &ctx->h_stage,
+	               &ctx->h_cl_n, &ctx->h_cl_a_off, &ctx->h_cl_a, &ctx->h_cl_ref_off, &ctx->h_cl_ref, &ctx->h_sg, &ctx->h_mi_cnt, &ctx->h_mi,
+	               &ctx->h_claim_c, &ctx->h_claim_s, &ctx->h_claim_y, &ctx->h_fpA, &ctx->h_fpT, &ctx->h_in0, &ctx->h_in1, &ctx->h_in2 };
+	for (auto b : hb) b->release();
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+// ---------------------------------------------------------------- timers
+extern "C" void mcb_timers_enable(mcb_ctx *ctx, int on) { if (ctx) ctx->tm.enabled = on != 0; }
+extern "C" void mcb_timers_reset(mcb_ctx *ctx) { if (ctx) { cudaStreamSynchronize(ctx->stream); ctx->tm.reset(); } }
+extern "C" double mcb_timer_get(mcb_ctx *ctx, const char *name, uint64_t *count)
+{
+	if (count) *count = 0;
+	if (!ctx || !name) return 0;
+	auto it = ctx->tm.idx.find(name);
+	if (it == ctx->tm.idx.end()) return 0;
+	if (count) *count = ctx->tm.cnt[it->second];
+	return ctx->tm.ms[it->second];
+}
+extern "C" size_t mcb_timers_dump(mcb_ctx *ctx, char *buf, size_t cap)
+{
+	std::string s;
+	if (ctx) for (size_t i = 0; i < ctx->tm.names.size(); ++i) {
+		char line[256];
+		snprintf(line, sizeof line, "%s %.6f %llu\n", ctx->tm.names[i].c_str(), ctx->tm.ms[i], (unsigned long long)ctx->tm.cnt[i]);
+		s += line;
+	}
+	if (buf && cap) { size_t n = s.size() < cap - 1 ? s.size() : cap - 1; memcpy(buf, s.data(), n); buf[n] = 0; }
+	return s.size() + 1;
+}
+extern "C" uint64_t mcb_kernel_launches(mcb_ctx *ctx) { return ctx ? ctx->tm.launches : 0; }
+
+// ---------------------------------------------------------------- host boundary helpers
+extern "C" uint64_t mcb_hash64(uint64_t key, uint64_t mask) { return mcb_hash64_hd(key, mask); }
+
+// mm_sketch_two (sketch.c:238-289) straight from ASCII; characters go through the same table as the reference
+// (seq_nt4_table: anything that is not ACGT/acgt has code 4 and is ORed in unmasked, sketch.c:257-261).
+extern "C" void mcb_sketch_two_host(const char *str, int len, int k, uint32_t rid, mcb_tuple *out)
+{
+	const uint64_t mask = (1ull << (2 * k)) - 1, shift1 = 2 * (k - 1);
+	uint64_t f = 0, r = 0;
+	mcb_tuple best; best.x = ~0ull; best.y = ~0ull;
+	int l = 0;
+	for (int i = 0; i < len; ++i) {
+		unsigned char ch = (unsigned char)str[i];
+		uint64_t c = (ch == 'A' || ch == 'a') ? 0 : (ch == 'C' || ch == 'c') ? 1 : (ch == 'G' || ch == 'g') ? 2 : (ch == 'T' || ch == 't') ? 3 : 4;
+		f = (f << 2 | c) & mask;
+		r = (r >> 2) | ((3ull ^ c) << shift1);
+		if (f == r) continue;
+		int z = f < r ? 0 : 1;
+		if (++l >= k) {
+			uint64_t h = mcb_hash64_hd(z ? r : f, mask);
+			if (h < best.x) { best.x = h; best.y = (uint64_t)rid << 32 | (uint64_t)(uint32_t)i << 1 | (uint64_t)z; }
+		}
+	}
+	*out = best;
+}
+
+extern "C" int64_t mcb_sketch_lh_host(const char *str, int len, int w, int k, uint32_t rid, mcb_tuple *out, int64_t cap)
+{
+	if (len <= 0 || w <= 0 || k <= 0 || k > 31) return 0;
+	std::vector<mcb_tuple> ring((size_t)w);
+	McbLhEmitArray em; em.out = out; em.cap = out ? cap : 0; em.n = 0;
+	mcb_sketch_lh_core(str, len, w, k, rid, ring.data(), em, (int64_t)-1);
+	return em.n;
+}

@@ -1,0 +1,243 @@
+// mcb_common.cuh — context, buffers, timers and the small integer helpers shared by all kernels.
+//
+// Data layout in HBM:
+//   packed reads   u64[N][WS]   2-bit codes A0 C1 G2 T3 (seq_nt4_table, sketch.c:8-25), base i in word i/32 at bits
+//                               2*(i%32); WS = round_up(ceil(L/32),2) so a row is a whole number of 16-byte vectors.
+//   sort elements  ulonglong2   .x = K1 = bucket<<50 | x>>14   (bucket = x & 0x3FFF, kthread_reads.c:213)
+//                               .y = K2 = posinv<<33 | rid<<1 | strand  (cmpcluster order, kthread_bucket.c:44-62)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/minicom_b200.h"
+
+#define MCB_HD __host__ __device__ __forceinline__
+
+// ---------------------------------------------------------------- errors
+void mcb_set_error(const char *fmt, ...);
+#define MCB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	mcb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+	return MCB_ECUDA; } } while (0)
+#define MCB_TRY(call) do { int r_ = (call); if (r_ != MCB_OK) return r_; } while (0)
+
+// ---------------------------------------------------------------- growable buffers
+struct DBuf {            // device
+	void *p = nullptr; size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return MCB_OK;
+		if (p) { cudaFree(p); p = nullptr; cap = 0; }
+		size_t want = bytes + (bytes >> 3) + 256;
+		MCB_CUDA(cudaMalloc(&p, want));
+		cap = want; return MCB_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <class T> T *as() const { return (T*)p; }
+};
+struct HBuf {            // pinned host
+	void *p = nullptr; size_t cap = 0;
+	int ensure(size_t bytes) {
+		if (bytes <= cap) return MCB_OK;
+		if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+		size_t want = bytes + (bytes >> 3) + 256;
+		MCB_CUDA(cudaMallocHost(&p, want));
+		cap = want; return MCB_OK;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+	template <class T> T *as() const { return (T*)p; }
+};
+
+// ---------------------------------------------------------------- timers (CUDA events on ctx->stream)
+struct McbTimers {
+	struct Rec { int name; cudaEvent_t a, b; };
+	bool enabled = false;
+	std::vector<std::string> names;
+	std::map<std::string, int> idx;
+	std::vector<double> ms;
+	std::vector<uint64_t> cnt;
+	std::vector<Rec> pending;
+	std::vector<cudaEvent_t> pool;
+	cudaStream_t stream = 0;
+	uint64_t launches = 0;
+	int id(const char *n) {
+		auto it = idx.find(n);
+		if (it != idx.end()) return it->second;
+		int i = (int)names.size(); names.push_back(n); idx[n] = i; ms.push_back(0); cnt.push_back(0); return i;
+	}
+	cudaEvent_t ev() {
+		if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+		cudaEvent_t e; cudaEventCreate(&e); return e;
+	}
+	int begin(const char *n) {
+		if (!enabled) return -1;
+		Rec r; r.name = id(n); r.a = ev(); r.b = ev();
+		cudaEventRecord(r.a, stream); pending.push_back(r); return (int)pending.size() - 1;
+	}
+	void end(int h) { if (h >= 0) cudaEventRecord(pending[h].b, stream); }
+	void collect() {  // caller has synchronized the stream
+		for (auto &r : pending) {
+			float t = 0;
+			if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) { cudaGetLastError(); t = 0; }   // span abandoned by an early return
+			ms[r.name] += t; cnt[r.name] += 1; pool.push_back(r.a); pool.push_back(r.b);
+		}
+		pending.clear();
+	}
+	void reset() { collect(); for (auto &v : ms) v = 0; for (auto &v : cnt) v = 0; launches = 0; }
+};
+
+// RAII span for whole-entry-point / copy timers
+struct McbSpan {
+	McbTimers &t; int h;
+	McbSpan(McbTimers &t_, const char *n) : t(t_), h(t_.begin(n)) {}
+	~McbSpan() { t.end(h); }
+};
+
+#define MCB_LAUNCH(ctx, kname, kernel, grid, block, smem, ...) do { \
+	int h_ = (ctx)->tm.begin("k:" kname); \
+	kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+	(ctx)->tm.end(h_); (ctx)->tm.launches++; \
+	cudaError_t le_ = cudaGetLastError(); if (le_ != cudaSuccess) { \
+		mcb_set_error("kernel launch %s failed at %s:%d: %s", kname, __FILE__, __LINE__, cudaGetErrorString(le_)); return MCB_ECUDA; } \
+	} while (0)
+
+// slots of the device scalar block ctx->d_counters (u64[64])
+enum { CT_SKETCHED = 0, CT_BADCHAR = 1, CT_DEGENERATE = 2, CT_NREADS = 3, CT_REFCURSOR = 4, CT_G = 5, CT_TOT_CL = 6, CT_TOT_MEM = 7,
+       CT_TOT_REF = 8, CT_TOT_SG = 9, CT_TOT_RESK = 10, CT_ERR = 11, CT_SCRATCH_IDX = 12,
+       CT_S2_U = 16, CT_S2_PROBES = 17, CT_S2_CAND = 18, CT_S2_NEEDEXACT = 19, CT_S2_CLAIMS = 20, CT_S2_FPA = 21, CT_S2_FPT = 22, CT_S2_ERR = 23 };
+
+// ---------------------------------------------------------------- context
+struct mcb_index;   // defined in mcb_index.cu
+
+struct mcb_ctx {
+	mcb_params prm;
+	cudaStream_t stream = 0;
+	int sm_count = 148;
+	McbTimers tm;
+	// geometry
+	int L = 0, Wd = 0, WS = 0;          // words per read (used / row stride)
+	// ---- persistent read state (mcb_for_reads)
+	uint64_t n_reads = 0;
+	bool reads_loaded = false, bucket_done = false;
+	DBuf d_ascii;                        // N*L bytes (kept until the N masks are extracted)
+	DBuf d_packed;                       // u64[N][WS]
+	DBuf d_cls;                          // u8[N]
+	DBuf d_elemA, d_elemB;               // ulonglong2[N] sort double buffer
+	DBuf d_counters;                     // u64[64] device scalars
+	uint64_t n_valid_round1 = 0;
+	// reads containing N: sorted rid list + N masks (1 bit per base, same 2-bit-field layout: bit 2*(i%32) of word i/32)
+	uint64_t n_nreads = 0;
+	DBuf d_nread_rid;                    // u32[n_nreads]
+	DBuf d_nread_mask;                   // u64[n_nreads][WS]
+	// scratch shared by the phases
+	DBuf d_scr[12];
+	DBuf d_sort_hist, d_scan_tmp[4];
+	DBuf d_x[4];                         // stage-2 extras
+	// host result buffers
+	HBuf h_cls, h_nrid, h_nrepl, h_noff, h_npos, h_nmask, h_counters, h_stage;
+	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref, h_sg, h_mi_cnt, h_mi;
+	HBuf h_claim_c, h_claim_s, h_claim_y, h_fpA, h_fpT, h_in0, h_in1, h_in2;
+	std::vector<uint64_t> tmp_off;
+};
+
+// ---------------------------------------------------------------- integer helpers (host + device)
+// Invertible integer mix restricted to 2k bits (sketch.c:27-37).
+MCB_HD uint64_t mcb_hash64_hd(uint64_t key, uint64_t mask)
+{
+	key = (~key + (key << 21)) & mask;
+	key ^= key >> 24;
+	key = (key + (key << 3) + (key << 8)) & mask;
+	key ^= key >> 14;
+	key = (key + (key << 2) + (key << 4)) & mask;
+	key ^= key >> 28;
+	key = (key + (key << 31)) & mask;
+	return key;
+}
+
+// base i (0..L-1) of a packed row
+MCB_HD unsigned mcb_base_at(const uint64_t *row, int i) { return (unsigned)(row[i >> 5] >> (2 * (i & 31))) & 3u; }
+
+// ASCII -> code: A0 C1 G2 T3 N4, anything else 5 (rejected; the reference's behaviour on such input is undefined:
+// process_reads counts only upper-case ACGTN, kthread_reads.c:56-73, and construct_ref indexes count_table[4] for 'N').
+MCB_HD unsigned mcb_code_of(unsigned char c)
+{
+	return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : c == 'N' ? 4u : 5u;
+}
+
+// reverse the order of the 32 two-bit fields of a word and complement them (A<->T, C<->G == 3-code)
+MCB_HD uint64_t mcb_rc_word(uint64_t w)
+{
+#ifdef __CUDA_ARCH__
+	uint64_t r = __brevll(w);
+#else
+	uint64_t r = w;
+	r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+	r = ((r >> 2) & 0x3333333333333333ull) | ((r & 0x3333333333333333ull) << 2);
+	r = ((r >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((r & 0x0F0F0F0F0F0F0F0Full) << 4);
+	r = ((r >> 8) & 0x00FF00FF00FF00FFull) | ((r & 0x00FF00FF00FF00FFull) << 8);
+	r = ((r >> 16) & 0x0000FFFF0000FFFFull) | ((r & 0x0000FFFF0000FFFFull) << 16);
+	r = (r >> 32) | (r << 32);
+#endif
+	r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);  // undo the swap inside each field
+	return ~r;
+}
+
+// Sort keys.  K1 orders by (bucket, minimizer); K2 by cmpcluster: strand-adjusted position descending, rid ascending.
+#define MCB_K1_INVALID 0xFFFFFFFFFFFFFFFFull
+MCB_HD uint64_t mcb_make_k1(uint64_t x) { return ((x & 0x3FFFull) << 50) | (x >> 14); }
+MCB_HD uint64_t mcb_k1_to_x(uint64_t k1) { return ((k1 & 0x3FFFFFFFFFFFFull) << 14) | (k1 >> 50); }
+#define MCB_POSINV_SHIFT 33
+#define MCB_POSINV_FIELD 0x1FFull   // 9 bits: posinv = pbase - pos', pbase = L + max_rounds <= 256 + 35; all ones = "not a tuple"
+// pos' (kthread_bucket.c:51-56): pos for strand 0, L - pos + k - 2 for strand 1 (k = reads->k, NOT the round's kmer)
+MCB_HD int mcb_adj_pos(int pos, int strand, int L, int k) { return strand ? L - pos + k - 2 : pos; }
+MCB_HD uint64_t mcb_make_k2(uint32_t rid, int pos, int strand, int L, int k, int pbase)
+{
+	int pa = mcb_adj_pos(pos, strand, L, k);
+	return ((uint64_t)(pbase - pa) << MCB_POSINV_SHIFT) | ((uint64_t)rid << 1) | (uint64_t)strand;
+}
+MCB_HD uint64_t mcb_make_k2_invalid(uint32_t rid) { return (MCB_POSINV_FIELD << MCB_POSINV_SHIFT) | ((uint64_t)rid << 1); }
+MCB_HD int mcb_k2_adjpos(uint64_t k2, int pbase) { return pbase - (int)(k2 >> MCB_POSINV_SHIFT); }
+MCB_HD uint32_t mcb_k2_rid(uint64_t k2) { return (uint32_t)(k2 >> 1); }
+MCB_HD int mcb_k2_strand(uint64_t k2) { return (int)(k2 & 1); }
+
+// mm_sketch_two (sketch.c:238-289) over a packed, N-free read.  Returns x (UINT64_MAX if no valid k-mer) and
+// the last position / strand of the chosen k-mer.
+MCB_HD uint64_t mcb_sketch_two_packed(const uint64_t *row, int L, int k, int *pos_out, int *strand_out)
+{
+	const uint64_t mask = (1ull << (2 * k)) - 1, shift1 = 2 * (k - 1);
+	uint64_t f = 0, r = 0, best = ~0ull;
+	int l = 0, bp = 0, bz = 0;
+	for (int w = 0; w * 32 < L; ++w) {
+		uint64_t word = row[w];
+		int lim = L - w * 32; if (lim > 32) lim = 32;
+		for (int j = 0; j < lim; ++j) {
+			uint64_t c = word & 3; word >>= 2;
+			f = (f << 2 | c) & mask;
+			r = (r >> 2) | ((3ull ^ c) << shift1);
+			if (f == r) continue;                  // symmetric k-mer: skipped and NOT counted (sketch.c:265)
+			int z = f < r ? 0 : 1;
+			if (++l >= k) {
+				uint64_t h = mcb_hash64_hd(z ? r : f, mask);
+				if (h < best) { best = h; bp = w * 32 + j; bz = z; }   // strict <: leftmost on ties (sketch.c:275)
+			}
+		}
+	}
+	*pos_out = bp; *strand_out = bz;
+	return best;
+}
+
+// ---------------------------------------------------------------- primitives (mcb_sort.cu)
+struct McbSortPass { int word; int shift; int bits; };  // word 0 = .x, 1 = .y
+int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const McbSortPass *passes, int n_passes,
+                   ulonglong2 **sorted_out);
+int mcb_add_bit_passes(std::vector<McbSortPass> &v, int word, int lo, int hi);  // digits covering bits [lo,hi)
+int mcb_exclusive_scan_u32(mcb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *d_total /* device u64, may be null */);
+int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t *d_total);
+
+static inline unsigned mcb_grid_for(uint64_t n, unsigned block, unsigned cap = 0x7FFFFFFFu)
+{
+	uint64_t g = (n + block - 1) / block; if (g < 1) g = 1; if (g > cap) g = cap; return (unsigned)g;
+}
+static inline int mcb_bits_for(uint64_t n) { int b = 0; while (b < 64 && (n >> b)) ++b; return b ? b : 1; }  // bits to hold values < n .. roughly

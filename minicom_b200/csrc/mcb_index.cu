@@ -1,0 +1,283 @@
+// mcb_index.cu — mm_idx_generation / mm_idx_get (kthread_idx.c:116-173, :84-101) on the device.
+//
+// The reference sorts every bucket with radix_sort_128x (misc.c:21-22, ksort.h:108-157): insertion sort up to 64
+// elements (stable), above that an in-place most-significant-digit "American flag" sort whose cycle-leader permutation
+// is NOT stable.  The order in which equal minimizers end up is observable: worker_post copies them into the posting
+// list in that order (kthread_idx.c:153-157) and the contig merger takes the first acceptable hit
+// (kthread_cb.c:267-343).  So the device index reproduces that permutation exactly: one warp per bucket, the
+// data-dependent cycle walk on one lane, histograms / small-segment sorts / CSR construction on all lanes.
+// The hash table of the reference (khash) is replaced by sorted distinct keys per bucket + CSR postings.
+#include "mcb_common.cuh"
+#include <stdlib.h>
+#include <thread>
+#include <algorithm>
+
+#define IX_WARPS 4
+#define IX_SMALL 64       // RS_MIN_SIZE (ksort.h:106)
+
+struct IxSeg { uint32_t b, e; int s; };
+
+// stable sort of a short segment by x: rank = #smaller + #equal-before.  Same result as the reference's insertion sort.
+__device__ void ix_small_sort_warp(mcb_tuple *a, uint32_t n, int lane)
+{
+	// n <= 64: each lane owns elements lane and lane+32
+	mcb_tuple e0, e1; bool h0 = lane < (int)n, h1 = lane + 32 < (int)n;
+	if (h0) e0 = a[lane];
+	if (h1) e1 = a[lane + 32];
+	uint32_t r0 = 0, r1 = 0;
+	for (uint32_t j = 0; j < n; ++j) {
+		uint64_t xj = a[j].x;
+		if (h0) r0 += (xj < e0.x) || (xj == e0.x && j < (uint32_t)lane);
+		if (h1) r1 += (xj < e1.x) || (xj == e1.x && j < (uint32_t)lane + 32);
+	}
+	__syncwarp();
+	if (h0) a[r0] = e0;
+	if (h1) a[r1] = e1;
+	__syncwarp();
+}
+__device__ void ix_insertion_sort(mcb_tuple *a, uint32_t n)
+{
+	for (uint32_t i = 1; i < n; ++i) {
+		mcb_tuple t = a[i];
+		if (t.x < a[i - 1].x) {
+			uint32_t j = i;
+			while (j > 0 && t.x < a[j - 1].x) { a[j] = a[j - 1]; --j; }
+			a[j] = t;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(IX_WARPS * 32)
+k_index_sort(mcb_tuple *__restrict__ t, const uint64_t *__restrict__ boff, int nb, IxSeg *__restrict__ stacks)
+{
+	__shared__ uint32_t s_cur[IX_WARPS][256], s_end[IX_WARPS][256];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	uint32_t *cur = s_cur[wib], *end = s_end[wib];
+	for (int bk = blockIdx.x * IX_WARPS + wib; bk < nb; bk += gridDim.x * IX_WARPS) {
+		const uint64_t B0 = boff[bk], B1 = boff[bk + 1];
+		const uint32_t n = (uint32_t)(B1 - B0);
+		mcb_tuple *a = t + B0;
+		if (n <= 1) continue;
+		if (n <= IX_SMALL) { ix_small_sort_warp(a, n, lane); continue; }
+		IxSeg *stk = stacks + (B0 / 65 + 8ull * bk);
+		int top = 0;
+		if (lane == 0) { stk[0].b = 0; stk[0].e = n; stk[0].s = 56; }
+		top = 1;
+		__syncwarp();
+		while (top > 0) {
+			--top;
+			const uint32_t sb = stk[top].b, se = stk[top].e; const int s = stk[top].s;
+			__syncwarp();
+			// digit histogram -> region [start,end) per digit
+			for (int d = lane; d < 256; d += 32) cur[d] = 0;
+			__syncwarp();
+			for (uint32_t i = sb + lane; i < se; i += 32) atomicAdd(&cur[(a[i].x >> s) & 255], 1u);
+			__syncwarp();
+			{
+				uint32_t v[8], sum = 0;
+#pragma unroll
+				for (int q = 0; q < 8; ++q) { v[q] = cur[lane * 8 + q]; sum += v[q]; }
+				uint32_t inc = sum;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
+				uint32_t run = sb + inc - sum;
+				__syncwarp();
+#pragma unroll
+				for (int q = 0; q < 8; ++q) { cur[lane * 8 + q] = run; run += v[q]; end[lane * 8 + q] = run; }
+			}
+			__syncwarp();
+			// cycle-leader permutation, exactly in the reference's visiting order (ksort.h:131-145)
+			if (lane == 0) {
+				for (int k = 0; k < 256;) {
+					if (cur[k] != end[k]) {
+						mcb_tuple tmp = a[cur[k]];
+						int l = (int)((tmp.x >> s) & 255);
+						if (l != k) {
+							do {
+								mcb_tuple sw = tmp;
+								uint32_t p = cur[l]++;
+								tmp = a[p]; a[p] = sw;
+								l = (int)((tmp.x >> s) & 255);
+							} while (l != k);
+							a[cur[k]++] = tmp;
+						} else ++cur[k];
+					} else ++k;
+				}
+			}
+			__syncwarp();
+			if (s > 0) {
+				const int s2 = s > 8 ? s - 8 : 0;
+				// region d spans [end[d-1], end[d])
+				for (int d0 = 0; d0 < 256; d0 += 32) {
+					int d = d0 + lane;
+					uint32_t rb = d == 0 ? sb : end[d - 1], re = end[d];
+					uint32_t sz = re - rb;
+					bool big = sz > IX_SMALL;
+					if (!big && sz > 1) ix_insertion_sort(a + rb, sz);
+					unsigned bm = __ballot_sync(0xFFFFFFFFu, big);
+					if (big) { int slot = top + __popc(bm & ((1u << lane) - 1u)); stk[slot].b = rb; stk[slot].e = re; stk[slot].s = s2; }
+					top += __popc(bm);
+				}
+			}
+			__syncwarp();
+		}
+	}
+}
+
+__global__ void k_ix_heads(const mcb_tuple *__restrict__ t, uint64_t n, uint32_t *__restrict__ flag)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) flag[i] = (i == 0 || t[i].x != t[i - 1].x) ? 1u : 0u;
+}
+__global__ void k_ix_keys(const mcb_tuple *__restrict__ t, uint64_t n, const uint32_t *__restrict__ hscan, const unsigned long long *__restrict__ U,
+                          uint64_t *__restrict__ keys, uint32_t *__restrict__ kstart, uint64_t *__restrict__ post)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	mcb_tuple e = t[i];
+	post[i] = e.y;
+	if (i == 0 || e.x != t[i - 1].x) { uint32_t u = hscan[i]; keys[u] = e.x; kstart[u] = (uint32_t)i; }
+	if (i == n - 1) kstart[*U] = (uint32_t)n;
+}
+__global__ void k_ix_bucket_ranges(const uint64_t *__restrict__ boff, int nb, uint64_t n, const uint32_t *__restrict__ hscan,
+                                   const unsigned long long *__restrict__ U, uint32_t *__restrict__ ub)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b > nb) return;
+	uint64_t p = boff[b];
+	ub[b] = p < n ? hscan[p] : (uint32_t)*U;
+}
+
+struct mcb_index {
+	int b = 14;
+	uint64_t n_keys = 0, n_post = 0;
+	uint64_t *keys = nullptr;      // [n_keys]   distinct minimizers, ascending inside each bucket
+	uint32_t *kstart = nullptr;    // [n_keys+1] posting offsets
+	uint64_t *post = nullptr;      // [n_post]   y values in the reference's order
+	uint32_t *ub = nullptr;        // [2^b+1]    key range of each bucket
+};
+
+extern "C" void mcb_idx_destroy(mcb_index *ix)
+{
+	if (!ix) return;
+	free(ix->keys); free(ix->kstart); free(ix->post); free(ix->ub);
+	delete ix;
+}
+
+extern "C" void mcb_idx_stats(const mcb_index *ix, uint64_t *n_keys, uint64_t *n_post)
+{
+	if (n_keys) *n_keys = ix ? ix->n_keys : 0;
+	if (n_post) *n_post = ix ? ix->n_post : 0;
+}
+
+extern "C" const uint64_t *mcb_idx_get(const mcb_index *ix, uint64_t minier, int *n)
+{
+	*n = 0;
+	if (!ix || !ix->n_keys) return nullptr;
+	const uint32_t bk = (uint32_t)(minier & ((1ull << ix->b) - 1));
+	uint32_t lo = ix->ub[bk], hi = ix->ub[bk + 1];
+	while (lo < hi) {
+		uint32_t mid = lo + ((hi - lo) >> 1);
+		uint64_t kx = ix->keys[mid];
+		if (kx < minier) lo = mid + 1; else if (kx > minier) hi = mid; else {
+			*n = (int)(ix->kstart[mid + 1] - ix->kstart[mid]);
+			return ix->post + ix->kstart[mid];
+		}
+	}
+	return nullptr;
+}
+
+static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mcb_index **out)
+{
+	// tuples are in d_scr[0] (device), bucket offsets on the host
+	const int b = ctx->prm.b, nb = 1 << b;
+	mcb_index *ix = new mcb_index(); ix->b = b; ix->n_post = n;
+	ix->ub = (uint32_t*)calloc((size_t)nb + 1, 4);
+	*out = ix;
+	if (n == 0) { ix->keys = (uint64_t*)calloc(1, 8); ix->kstart = (uint32_t*)calloc(2, 4); ix->post = (uint64_t*)calloc(1, 8); return MCB_OK; }
+	if (n >= 0xFFFFFFFFull) { mcb_set_error("index too large"); return MCB_EINVAL; }
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	MCB_TRY(ctx->d_scr[1].ensure(((size_t)nb + 1) * 8));
+	MCB_TRY(ctx->d_scr[2].ensure((n / 65 + 8ull * nb + 8) * sizeof(IxSeg)));
+	MCB_TRY(ctx->d_scr[3].ensure(n * 4 + 16));
+	MCB_TRY(ctx->d_scr[4].ensure(n * 8 + 16));           // keys (<= n)
+	MCB_TRY(ctx->d_scr[5].ensure((n + 2) * 4));          // kstart
+	MCB_TRY(ctx->d_scr[6].ensure(n * 8 + 16));           // postings
+	MCB_TRY(ctx->d_scr[7].ensure(((size_t)nb + 1) * 4)); // ub
+	mcb_tuple *dt = ctx->d_scr[0].as<mcb_tuple>();
+	{
+		McbSpan sp(ctx->tm, "h2d");
+		MCB_CUDA(cudaMemcpyAsync(ctx->d_scr[1].p, h_boff, ((size_t)nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	{
+		McbSpan sp(ctx->tm, "idx_build");
+		MCB_LAUNCH(ctx, "index_sort", k_index_sort, mcb_grid_for(nb, IX_WARPS), IX_WARPS * 32, 0, dt, ctx->d_scr[1].as<uint64_t>(), nb, ctx->d_scr[2].as<IxSeg>());
+		MCB_LAUNCH(ctx, "ix_heads", k_ix_heads, mcb_grid_for(n, 256), 256, 0, dt, n, ctx->d_scr[3].as<uint32_t>());
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, ctx->d_scr[3].as<uint32_t>(), n, (uint64_t*)&dc[CT_SCRATCH_IDX]));
+		MCB_LAUNCH(ctx, "ix_keys", k_ix_keys, mcb_grid_for(n, 256), 256, 0, dt, n, ctx->d_scr[3].as<uint32_t>(), &dc[CT_SCRATCH_IDX],
+		           ctx->d_scr[4].as<uint64_t>(), ctx->d_scr[5].as<uint32_t>(), ctx->d_scr[6].as<uint64_t>());
+		MCB_LAUNCH(ctx, "ix_bucket_ranges", k_ix_bucket_ranges, mcb_grid_for(nb + 1, 256), 256, 0, ctx->d_scr[1].as<uint64_t>(), nb, n,
+		           ctx->d_scr[3].as<uint32_t>(), &dc[CT_SCRATCH_IDX], ctx->d_scr[7].as<uint32_t>());
+	}
+	MCB_TRY(ctx->h_counters.ensure(64 * 8));
+	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	const uint64_t U = ctx->h_counters.as<unsigned long long>()[CT_SCRATCH_IDX];
+	ix->n_keys = U;
+	ix->keys = (uint64_t*)malloc(U * 8 + 8); ix->kstart = (uint32_t*)malloc((U + 1) * 4); ix->post = (uint64_t*)malloc(n * 8);
+	if (!ix->keys || !ix->kstart || !ix->post) { mcb_set_error("out of host memory"); return MCB_ENOMEM; }
+	{
+		McbSpan sp(ctx->tm, "d2h");
+		MCB_CUDA(cudaMemcpyAsync(ix->keys, ctx->d_scr[4].p, U * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaMemcpyAsync(ix->kstart, ctx->d_scr[5].p, (U + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaMemcpyAsync(ix->post, ctx->d_scr[6].p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaMemcpyAsync(ix->ub, ctx->d_scr[7].p, ((size_t)nb + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->tm.collect();
+	return MCB_OK;
+}
+
+extern "C" int mcb_idx_build(mcb_ctx *ctx, const mcb_tuple *tuples, const uint64_t *bucket_off, mcb_index **out)
+{
+	if (!ctx || !out || !bucket_off) { mcb_set_error("mcb_idx_build: null argument"); return MCB_EINVAL; }
+	MCB_CUDA(cudaSetDevice(ctx->prm.device));
+	*out = nullptr;
+	const int nb = 1 << ctx->prm.b;
+	const uint64_t n = bucket_off[nb];
+	if (n && !tuples) { mcb_set_error("mcb_idx_build: null tuples"); return MCB_EINVAL; }
+	MCB_TRY(ctx->d_counters.ensure(64 * 8));
+	MCB_TRY(ctx->d_scr[0].ensure(n * 16 + 16));
+	if (n) {
+		McbSpan sp(ctx->tm, "h2d");
+		MCB_CUDA(cudaMemcpyAsync(ctx->d_scr[0].p, tuples, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	int r = idx_build_device(ctx, n, bucket_off, out);
+	if (r != MCB_OK) { mcb_idx_destroy(*out); *out = nullptr; }
+	return r;
+}
+
+extern "C" int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptrs, const uint64_t *cnt, mcb_index **out)
+{
+	if (!ctx || !out || !ptrs || !cnt) { mcb_set_error("mcb_idx_build_scattered: null argument"); return MCB_EINVAL; }
+	MCB_CUDA(cudaSetDevice(ctx->prm.device));
+	*out = nullptr;
+	const int nb = 1 << ctx->prm.b;
+	MCB_TRY(ctx->h_in1.ensure(((size_t)nb + 1) * 8));
+	uint64_t *boff = ctx->h_in1.as<uint64_t>();
+	uint64_t n = 0;
+	for (int i = 0; i < nb; ++i) { boff[i] = n; n += cnt[i]; }
+	boff[nb] = n;
+	MCB_TRY(ctx->h_in0.ensure(n * 16 + 16));
+	mcb_tuple *flat = ctx->h_in0.as<mcb_tuple>();
+	for (int i = 0; i < nb; ++i) if (cnt[i]) memcpy(flat + boff[i], ptrs[i], cnt[i] * 16);
+	MCB_TRY(ctx->d_counters.ensure(64 * 8));
+	MCB_TRY(ctx->d_scr[0].ensure(n * 16 + 16));
+	if (n) {
+		McbSpan sp(ctx->tm, "h2d");
+		MCB_CUDA(cudaMemcpyAsync(ctx->d_scr[0].p, flat, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	int r = idx_build_device(ctx, n, boff, out);
+	if (r != MCB_OK) { mcb_idx_destroy(*out); *out = nullptr; }
+	return r;
+}

@@ -1,0 +1,196 @@
+// mcb_sort.cu — device primitives: stable LSD radix sort of 16-byte elements and exclusive scans.
+//
+// The reference sorts each of its 16384 buckets separately on the CPU (radix_sort_128x, ksort.h:108-157, called from
+// kthread_bucket.c:391) and then qsorts each group (cmpcluster, kthread_bucket.c:442).  Here ONE stable sort over all
+// tuples with the composite key (bucket, minimizer, adjusted position desc, rid) yields every bucket, every group and
+// the member order at once; CSR group boundaries fall out of a head-flag scan.
+//
+// Sort: 8-bit digits, three kernels per pass (per-tile histogram, scan of the digit-major histogram table, stable
+// scatter).  HBM-bound: each pass reads the elements twice (histogram + scatter) and writes them once, 48 B/element.
+// Tiles are 2048 elements (8 warps x 8 steps x 32 lanes); a warp owns a contiguous run of its tile so that ranks
+// computed with __match_any_sync are stable.
+#include "mcb_common.cuh"
+
+#define SORT_THREADS 256
+#define SORT_WARPS 8
+#define SORT_STEPS 8
+#define SORT_TILE (SORT_THREADS * SORT_STEPS)
+
+__device__ __forceinline__ unsigned digit_of(const ulonglong2 &e, int word, int shift, unsigned mask)
+{
+	unsigned long long v = word ? e.y : e.x;
+	return (unsigned)(v >> shift) & mask;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_hist(const ulonglong2 *__restrict__ in, uint64_t n, int word, int shift, unsigned mask, uint32_t *__restrict__ hist, unsigned nblocks)
+{
+	__shared__ unsigned h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	uint64_t base = (uint64_t)blockIdx.x * SORT_TILE;
+#pragma unroll
+	for (int s = 0; s < SORT_STEPS; ++s) {
+		uint64_t i = base + (uint64_t)s * SORT_THREADS + threadIdx.x;
+		if (i < n) atomicAdd(&h[digit_of(in[i], word, shift, mask)], 1u);
+	}
+	__syncthreads();
+	hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_scatter(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ out, uint64_t n, int word, int shift, unsigned mask,
+               const uint32_t *__restrict__ hist_scanned, unsigned nblocks)
+{
+	__shared__ unsigned wcnt[SORT_WARPS][256];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+	__syncthreads();
+	const uint64_t wbase = (uint64_t)blockIdx.x * SORT_TILE + (uint64_t)w * (32 * SORT_STEPS);
+	ulonglong2 e[SORT_STEPS];
+	unsigned dg[SORT_STEPS];
+#pragma unroll
+	for (int s = 0; s < SORT_STEPS; ++s) {
+		uint64_t i = wbase + s * 32 + lane;
+		if (i < n) {
+			e[s] = in[i];
+			dg[s] = digit_of(e[s], word, shift, mask);
+			atomicAdd(&wcnt[w][dg[s]], 1u);
+		} else dg[s] = 256u;
+	}
+	__syncthreads();
+	{   // per digit: turn per-warp counts into absolute output bases
+		unsigned d = threadIdx.x;
+		unsigned run = hist_scanned[(uint64_t)d * nblocks + blockIdx.x];
+#pragma unroll
+		for (int ww = 0; ww < SORT_WARPS; ++ww) { unsigned t = wcnt[ww][d]; wcnt[ww][d] = run; run += t; }
+	}
+	__syncthreads();
+	const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+	for (int s = 0; s < SORT_STEPS; ++s) {
+		unsigned peers = __match_any_sync(0xFFFFFFFFu, dg[s]);
+		bool valid = dg[s] < 256u;
+		unsigned base = 0;
+		if (valid) base = wcnt[w][dg[s]];
+		__syncwarp();
+		if (valid && lane == (__ffs(peers) - 1)) wcnt[w][dg[s]] = base + __popc(peers);
+		__syncwarp();
+		if (valid) out[(uint64_t)base + __popc(peers & lt)] = e[s];
+	}
+}
+
+// ---------------------------------------------------------------- scans
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+template <class T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T *total, T *smem /* [SCAN_THREADS/32] */)
+{
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	T inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+	if (lane == 31) smem[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		T s = lane < SCAN_THREADS / 32 ? smem[lane] : (T)0, si = s;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(0xFFFFFFFFu, si, o); if (lane >= o) si += t; }
+		if (lane < SCAN_THREADS / 32) smem[lane] = si - s;       // exclusive warp bases
+		if (lane == SCAN_THREADS / 32 - 1) *total = si;
+	}
+	__syncthreads();
+	T r = smem[w] + inc - v;
+	return r;
+}
+
+template <class T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const T *__restrict__ d, uint64_t n, T *__restrict__ sums)
+{
+	__shared__ T sm[SCAN_THREADS / 32];
+	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	T s = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) s += d[base + i];
+#pragma unroll
+	for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+	if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) { T t = 0; for (int i = 0; i < SCAN_THREADS / 32; ++i) t += sm[i]; sums[blockIdx.x] = t; }
+}
+
+// in-place exclusive scan of one tile per block, plus the block's base offset (sums may be null for the single-tile case)
+template <class T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(T *__restrict__ d, uint64_t n, const T *__restrict__ sums, uint64_t *total_out)
+{
+	__shared__ T sm[SCAN_THREADS / 32];
+	__shared__ T tot;
+	uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	T v[SCAN_ITEMS], s = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = base + i < n ? d[base + i] : (T)0; s += v[i]; }
+	T ex = block_exclusive_scan<T>(s, &tot, sm);
+	T off = sums ? sums[blockIdx.x] : (T)0;
+	T run = ex + off;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) d[base + i] = run; run += v[i]; }
+	if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && !sums) *total_out = (uint64_t)tot;
+}
+
+template <class T>
+static int scan_rec(mcb_ctx *ctx, T *d, uint64_t n, uint64_t *d_total, int level)
+{
+	if (n == 0) {
+		if (d_total) MCB_CUDA(cudaMemsetAsync(d_total, 0, 8, ctx->stream));
+		return MCB_OK;
+	}
+	uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+	if (nb == 1) {
+		MCB_LAUNCH(ctx, "scan_apply", k_scan_apply<T>, 1, SCAN_THREADS, 0, d, n, (const T*)nullptr, d_total);
+		return MCB_OK;
+	}
+	if (level >= 4) { mcb_set_error("scan too deep"); return MCB_EINVAL; }
+	MCB_TRY(ctx->d_scan_tmp[level].ensure(nb * sizeof(T)));
+	T *sums = ctx->d_scan_tmp[level].as<T>();
+	MCB_LAUNCH(ctx, "scan_reduce", k_scan_reduce<T>, (unsigned)nb, SCAN_THREADS, 0, d, n, sums);
+	MCB_TRY(scan_rec<T>(ctx, sums, nb, d_total, level + 1));
+	MCB_LAUNCH(ctx, "scan_apply", k_scan_apply<T>, (unsigned)nb, SCAN_THREADS, 0, d, n, (const T*)sums, (uint64_t*)nullptr);
+	return MCB_OK;
+}
+
+int mcb_exclusive_scan_u32(mcb_ctx *ctx, uint32_t *d, uint64_t n, uint64_t *d_total) { return scan_rec<uint32_t>(ctx, d, n, d_total, 0); }
+int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d, uint64_t n, uint64_t *d_total) { return scan_rec<unsigned long long>(ctx, (unsigned long long*)d, n, d_total, 0); }
+
+// ---------------------------------------------------------------- sort driver
+int mcb_add_bit_passes(std::vector<McbSortPass> &v, int word, int lo, int hi)
+{
+	while (lo < hi) {
+		int bits = hi - lo > 8 ? 8 : hi - lo;
+		McbSortPass p = { word, lo, bits };
+		v.push_back(p);
+		lo += bits;
+	}
+	return (int)v.size();
+}
+
+int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const McbSortPass *passes, int n_passes, ulonglong2 **sorted_out)
+{
+	*sorted_out = a;
+	if (n <= 1 || n_passes == 0) return MCB_OK;
+	uint64_t nb = (n + SORT_TILE - 1) / SORT_TILE;
+	if (nb > 0x7FFFFFFFull) { mcb_set_error("sort input too large"); return MCB_EINVAL; }
+	MCB_TRY(ctx->d_sort_hist.ensure(nb * 256 * sizeof(uint32_t)));
+	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>();
+	ulonglong2 *src = a, *dst = b;
+	for (int p = 0; p < n_passes; ++p) {
+		unsigned mask = (1u << passes[p].bits) - 1u;
+		MCB_LAUNCH(ctx, "sort_hist", k_sort_hist, (unsigned)nb, SORT_THREADS, 0, src, n, passes[p].word, passes[p].shift, mask, hist, (unsigned)nb);
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, hist, nb * 256, nullptr));
+		MCB_LAUNCH(ctx, "sort_scatter", k_sort_scatter, (unsigned)nb, SORT_THREADS, 0, src, dst, n, passes[p].word, passes[p].shift, mask, hist, (unsigned)nb);
+		ulonglong2 *t = src; src = dst; dst = t;
+	}
+	*sorted_out = src;
+	return MCB_OK;
+}

@@ -1,0 +1,805 @@
+// mcb_stage1.cu — kt_for_reads + kt_for_bucket on the device.
+//
+//   K01 k_pack_classify_sketch   process_reads (kthread_reads.c:40-230) + mm_sketch_two (sketch.c:238-289)
+//   K2  sort + head flags        radix_sort_128x + grouping + qsort(cmpcluster) (kthread_bucket.c:391-442)
+//   K3  k_consensus              construct_ref (kthread_bucket.c:69-377)
+//   K4  k_sketch_lh              mm_sketch_lh_ori (sketch.c:116-165), first `first_mininum` tuples per seed contig
+//   round loop                   kt_for_bucket (kthread_bucket.c:562-629)
+#include "mcb_common.cuh"
+#include "mcb_sketch_lh.cuh"
+#include <algorithm>
+#include <thread>
+
+// ---------------------------------------------------------------- classification (kthread_reads.c:84-226)
+struct McbCounts { int a, c, g, t, n; };
+MCB_HD int mcb_classify(const McbCounts &q, int L, int e, int *repl_code)
+{
+	*repl_code = -1;
+	if (q.a == L) return MCB_CLS_ALLA;
+	if (q.t == L) return MCB_CLS_ALLT;
+	if (q.n == L) return MCB_CLS_ALLN;
+	if (q.t + q.g + q.c + q.n <= e) return MCB_CLS_FPA;
+	if (q.a + q.g + q.c + q.n <= e) return MCB_CLS_FPT;
+	if (q.a + q.t + q.g + q.c <= e) return MCB_CLS_FPN;
+	if (5 * q.n > 2 * L) return MCB_CLS_NFILE;                 // cntN > 0.4*L  (kthread_reads.c:182)
+	if (q.n > 0) {                                             // most frequent base, ties in the order A,T,G,C (:185-201)
+		int mx = q.a; if (q.t > mx) mx = q.t; if (q.g > mx) mx = q.g; if (q.c > mx) mx = q.c;
+		*repl_code = mx == q.a ? 0 : mx == q.t ? 3 : mx == q.g ? 2 : 1;
+	}
+	return MCB_CLS_SKETCHED;
+}
+
+
+#define RD_THREADS 128
+#define HASN_BIT 0x80
+
+__global__ void __launch_bounds__(RD_THREADS)
+k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, int L, int Wd, int WS, int k, int e, int pbase,
+                       uint64_t *__restrict__ packed, uint8_t *__restrict__ cls, ulonglong2 *__restrict__ elem,
+                       unsigned long long *__restrict__ counters)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	uint64_t (*sp)[9] = (uint64_t (*)[9])smem;                                   // packed words per thread
+	unsigned char *rows = smem + RD_THREADS * 9 * sizeof(uint64_t);              // ASCII tile
+	const uint64_t first = (uint64_t)blockIdx.x * RD_THREADS;
+	const int nrow = (int)min((uint64_t)RD_THREADS, n - first);
+	const size_t nbytes = (size_t)nrow * L;
+	const uint8_t *src = ascii + first * L;
+	{   // coalesced 128-bit tile load (tile base is 16-byte aligned: 128*L is a multiple of 16)
+		const size_t nvec = nbytes >> 4;
+		const uint4 *s4 = (const uint4*)src; uint4 *d4 = (uint4*)rows;
+		for (size_t i = threadIdx.x; i < nvec; i += RD_THREADS) d4[i] = s4[i];
+		for (size_t i = (nvec << 4) + threadIdx.x; i < nbytes; i += RD_THREADS) rows[i] = src[i];
+	}
+	__syncthreads();
+	const int t = threadIdx.x;
+	const uint64_t rid = first + t;
+	bool sketched = false, bad = false, degenerate = false, hasn = false;
+	if (t < nrow) {
+		const unsigned char *row = rows + (size_t)t * L;
+		McbCounts q = {0, 0, 0, 0, 0};
+		uint64_t nmw[8];
+#pragma unroll
+		for (int w = 0; w < 8; ++w) {
+			uint64_t pw = 0, nw = 0;
+			if (w < Wd) {
+				int lim = L - w * 32; if (lim > 32) lim = 32;
+				for (int j = 0; j < lim; ++j) {
+					unsigned c = mcb_code_of(row[w * 32 + j]);
+					q.a += c == 0; q.c += c == 1; q.g += c == 2; q.t += c == 3; q.n += c == 4; bad |= c == 5;
+					if (c < 4) pw |= (uint64_t)c << (2 * j); else nw |= 1ull << (2 * j);
+				}
+				sp[t][w] = pw;
+			}
+			nmw[w] = nw;
+		}
+		int repl;
+		int c = mcb_classify(q, L, e, &repl);
+		hasn = q.n > 0;
+		if (c == MCB_CLS_SKETCHED && repl > 0) {
+#pragma unroll
+			for (int w = 0; w < 8; ++w) if (w < Wd) sp[t][w] |= nmw[w] * (uint64_t)repl;
+		}
+		cls[rid] = (uint8_t)(c | (hasn ? HASN_BIT : 0));
+		ulonglong2 el; el.x = MCB_K1_INVALID; el.y = mcb_make_k2_invalid((uint32_t)rid);
+		if (c == MCB_CLS_SKETCHED && !bad) {
+			int pos, z;
+			uint64_t x = mcb_sketch_two_packed(sp[t], L, k, &pos, &z);
+			if (x == ~0ull) degenerate = true;
+			else { el.x = mcb_make_k1(x); el.y = mcb_make_k2((uint32_t)rid, pos, z, L, k, pbase); sketched = true; }
+		}
+		elem[rid] = el;
+	}
+	__syncthreads();
+	{   // coalesced store of the packed rows of this tile
+		uint64_t *dst = packed + first * WS;
+		const int total = nrow * WS;
+		for (int i = threadIdx.x; i < total; i += RD_THREADS) { int r = i / WS, w = i - r * WS; dst[i] = w < Wd ? sp[r][w] : 0ull; }
+	}
+	unsigned m;
+	m = __ballot_sync(0xFFFFFFFFu, sketched);   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_SKETCHED], (unsigned long long)__popc(m));
+	m = __ballot_sync(0xFFFFFFFFu, bad);        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_BADCHAR], (unsigned long long)__popc(m));
+	m = __ballot_sync(0xFFFFFFFFu, degenerate); if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_DEGENERATE], (unsigned long long)__popc(m));
+	m = __ballot_sync(0xFFFFFFFFu, hasn);       if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_NREADS], (unsigned long long)__popc(m));
+}
+
+// reads with N: flag -> scan -> (rid, mask, replacement) side table
+__global__ void k_hasn_flags(const uint8_t *__restrict__ cls, uint64_t n, uint32_t *__restrict__ flag)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) flag[i] = (cls[i] & HASN_BIT) ? 1u : 0u;
+}
+__global__ void k_hasn_extract(const uint8_t *__restrict__ ascii, uint8_t *__restrict__ cls, uint64_t n, int L, int Wd, int WS, int e,
+                               const uint32_t *__restrict__ pos, uint32_t *__restrict__ nrid, uint64_t *__restrict__ nmask, uint8_t *__restrict__ nrepl)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint8_t c = cls[i];
+	if (!(c & HASN_BIT)) return;
+	cls[i] = c & ~HASN_BIT;
+	uint32_t o = pos[i];
+	nrid[o] = (uint32_t)i;
+	const uint8_t *row = ascii + i * L;
+	McbCounts q = {0, 0, 0, 0, 0};
+	for (int w = 0; w < WS; ++w) {
+		uint64_t nw = 0;
+		if (w < Wd) {
+			int lim = L - w * 32; if (lim > 32) lim = 32;
+			for (int j = 0; j < lim; ++j) {
+				unsigned cc = mcb_code_of(row[w * 32 + j]);
+				q.a += cc == 0; q.c += cc == 1; q.g += cc == 2; q.t += cc == 3; q.n += cc == 4;
+				if (cc == 4) nw |= 1ull << (2 * j);
+			}
+		}
+		nmask[(uint64_t)o * WS + w] = nw;
+	}
+	int repl; mcb_classify(q, L, e, &repl);
+	nrepl[o] = repl < 0 ? 0 : (uint8_t)"ACGT"[repl];
+}
+
+// batched mm_sketch_two over already packed reads (rounds >= 2: kthread_bucket.c:205,489)
+__global__ void k_resketch(const uint64_t *__restrict__ packed, int WS, int L, int k_orig, int kmer, int pbase,
+                           const uint32_t *__restrict__ rids, uint64_t n, ulonglong2 *__restrict__ elem, unsigned long long *__restrict__ counters)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t rid = rids[i];
+	uint64_t row[8];
+#pragma unroll
+	for (int w = 0; w < 8; ++w) row[w] = w < WS ? packed[(uint64_t)rid * WS + w] : 0ull;
+	int pos, z;
+	uint64_t x = mcb_sketch_two_packed(row, L, kmer, &pos, &z);
+	ulonglong2 el;
+	if (x == ~0ull) { atomicAdd(&counters[CT_DEGENERATE], 1ull); el.x = MCB_K1_INVALID; el.y = mcb_make_k2_invalid(rid); }
+	else { el.x = mcb_make_k1(x); el.y = mcb_make_k2(rid, pos, z, L, k_orig, pbase); }
+	elem[i] = el;
+}
+
+// raw tuples for tests: elem (rid order) -> (x,y)
+__global__ void k_elem_to_tuple(const ulonglong2 *__restrict__ elem, uint64_t n, int L, int k, int pbase, mcb_tuple *__restrict__ out, int by_rid)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	ulonglong2 e = elem[i];
+	mcb_tuple t;
+	if (e.x == MCB_K1_INVALID) { t.x = ~0ull; t.y = ~0ull; }
+	else {
+		int z = mcb_k2_strand(e.y), pa = mcb_k2_adjpos(e.y, pbase);
+		int pos = z ? L + k - 2 - pa : pa;
+		t.x = mcb_k1_to_x(e.x); t.y = (uint64_t)mcb_k2_rid(e.y) << 32 | (uint64_t)pos << 1 | (uint64_t)z;
+	}
+	out[by_rid ? (uint64_t)mcb_k2_rid(e.y) : i] = t;
+}
+
+__global__ void k_unpack(const uint64_t *__restrict__ packed, uint64_t n, int L, int WS, char *__restrict__ out)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n * (uint64_t)L) return;
+	uint64_t r = i / L; int p = (int)(i - r * L);
+	out[i] = "ACGT"[mcb_base_at(packed + r * WS, p)];
+}
+
+// ---------------------------------------------------------------- grouping
+__global__ void k_heads(const ulonglong2 *__restrict__ e, uint64_t n, uint32_t *__restrict__ flag)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) flag[i] = (i == 0 || e[i].x != e[i - 1].x) ? 1u : 0u;
+}
+__global__ void k_gstart(const ulonglong2 *__restrict__ e, uint64_t n, const uint32_t *__restrict__ hscan, const unsigned long long *__restrict__ G,
+                         uint32_t *__restrict__ gstart)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (i == 0 || e[i].x != e[i - 1].x) gstart[hscan[i]] = (uint32_t)i;
+	if (i == n - 1) gstart[*G] = (uint32_t)n;
+}
+
+// ---------------------------------------------------------------- K3 consensus (construct_ref, kthread_bucket.c:69-377)
+// One warp per group of >= 2 tuples.  Lane owns consensus columns lane, lane+32, ...; members are streamed in batches.
+#define CS_WARPS 4
+#define CS_MB 4          // members fetched per batch (CS_MB * 8 word slots = 32 lanes)
+
+struct ConsOut {
+	uint8_t *status;      // per element: 0 singleton, 1 kept member, 2 rejected, 3 lone survivor
+	uint32_t *erank;      // per element: rank inside its output list
+	uint64_t *newrec;     // per element: rid<<32 | offset<<1 | dir (kept members)
+	uint32_t *g_iscl, *g_kept, *g_sg, *g_resk;   // per group
+	unsigned long long *g_reflen;                // per group
+	unsigned long long *g_refoff;                // per group: offset into reftmp
+	char *reftmp;
+};
+
+__device__ __forceinline__ unsigned member_base(const uint64_t *mw, int dir, int p, int L)
+{
+	return dir ? 3u - mcb_base_at(mw, L - 1 - p) : mcb_base_at(mw, p);
+}
+
+__global__ void __launch_bounds__(CS_WARPS * 32)
+k_consensus(const ulonglong2 *__restrict__ el, const uint32_t *__restrict__ gstart, uint64_t G, const uint64_t *__restrict__ packed,
+            int WS, int L, int e_thr, int pbase, int NC, int last_round, ConsOut o, unsigned long long *__restrict__ counters, uint64_t reftmp_cap)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const size_t per_warp = (size_t)NC * 16 + NC + CS_MB * 8 * 8 + CS_MB * 16;
+	unsigned char *wsm = smem + (size_t)wib * ((per_warp + 15) & ~(size_t)15);
+	uint32_t *cnt = (uint32_t*)wsm;                                   // [4][NC]
+	uint64_t *mw = (uint64_t*)(wsm + (size_t)NC * 16);                // [CS_MB][8]
+	int *moff = (int*)(mw + CS_MB * 8);                               // [CS_MB]
+	int *mdir = moff + CS_MB;                                         // [CS_MB]
+	uint32_t *mrid = (uint32_t*)(mdir + CS_MB);                       // [CS_MB]
+	uint8_t *msel = (uint8_t*)(mrid + CS_MB);                         // [CS_MB] (padding inside the 16 B/member budget)
+	unsigned char *cons = wsm + (size_t)NC * 16 + CS_MB * 8 * 8 + CS_MB * 16;   // [NC]
+	const uint64_t nwarps = (uint64_t)gridDim.x * CS_WARPS;
+	for (uint64_t g = (uint64_t)blockIdx.x * CS_WARPS + wib; g < G; g += nwarps) {
+		const uint32_t s = gstart[g], cntm = gstart[g + 1] - s;
+		if (cntm < 2) {
+			if (lane == 0) {
+				o.status[s] = 0; o.erank[s] = 0;
+				o.g_iscl[g] = 0; o.g_kept[g] = 0; o.g_sg[g] = 1; o.g_resk[g] = 0; o.g_reflen[g] = 0; o.g_refoff[g] = 0;
+			}
+			continue;
+		}
+		const int posinv0 = (int)(el[s].y >> MCB_POSINV_SHIFT);
+		const int off_last = (int)(el[s + cntm - 1].y >> MCB_POSINV_SHIFT) - posinv0;
+		int ncol = off_last + L;
+		if (ncol > NC) { if (lane == 0) atomicAdd(&counters[CT_ERR], 1ull); ncol = NC; }
+		// ---- pass 1: column counts over all members, consensus (ties -> lowest code), stop at first empty column
+		for (int c = lane; c < 4 * NC; c += 32) cnt[c] = 0;
+		__syncwarp();
+		int kept = 0;
+		for (int pass = 0; pass < 3; ++pass) {
+			// pass 0: count all; pass 1: per-member mismatches vs consensus; pass 2: recount kept members
+			if (pass == 2) {
+				if (kept < 2) break;
+				for (int c = lane; c < 4 * NC; c += 32) cnt[c] = 0;
+				__syncwarp();
+			}
+			for (uint32_t b0 = 0; b0 < cntm; b0 += CS_MB) {
+				const int mb = min((uint32_t)CS_MB, cntm - b0);
+				{   // fetch a batch: lane = member*8 + word
+					int m = lane >> 3, w = lane & 7;
+					if (m < mb) {
+						unsigned long long k2 = el[s + b0 + m].y;
+						uint32_t rid = mcb_k2_rid(k2);
+						mw[m * 8 + w] = w < WS ? packed[(uint64_t)rid * WS + w] : 0ull;
+						if (w == 0) {
+							moff[m] = (int)(k2 >> MCB_POSINV_SHIFT) - posinv0; mdir[m] = (int)(k2 & 1); mrid[m] = rid;
+							msel[m] = pass == 2 ? (o.status[s + b0 + m] == 1) : 1;
+						}
+					}
+				}
+				__syncwarp();
+				for (int m = 0; m < mb; ++m) {
+					const int off = moff[m], dir = mdir[m];
+					const uint64_t *w64 = mw + m * 8;
+					if (pass != 1) {
+						if (msel[m]) {
+							for (int c = lane; c < ncol; c += 32) {
+								int p = c - off;
+								if ((unsigned)p < (unsigned)L) cnt[member_base(w64, dir, p, L) * NC + c]++;
+							}
+						}
+					} else {
+						int mism = 0;
+						for (int p = lane; p < L; p += 32) {
+							int c = off + p;
+							unsigned char rc = c < NC ? cons[c] : 0xFF;
+							mism += rc != member_base(w64, dir, p, L);
+						}
+						mism = __reduce_add_sync(0xFFFFFFFFu, mism);
+						const bool keep = mism <= e_thr;
+						kept += keep;
+						if (lane == 0) o.status[s + b0 + m] = keep ? 1 : 2;
+					}
+				}
+				__syncwarp();
+			}
+			if (pass == 0) {
+				// consensus over [0, ncol); a column with no coverage would end the string (kthread_bucket.c:117-120)
+				int reflen1 = ncol;
+				for (int c0 = 0; c0 < ncol; c0 += 32) {
+					int c = c0 + lane; bool empty = false;
+					if (c < ncol) {
+						uint32_t m0 = cnt[c], best = 0;
+						for (int b = 1; b < 4; ++b) { uint32_t v = cnt[b * NC + c]; if (v > m0) { m0 = v; best = b; } }
+						cons[c] = (unsigned char)best; empty = m0 == 0;
+					}
+					unsigned em = __ballot_sync(0xFFFFFFFFu, empty);
+					if (em) { reflen1 = c0 + __ffs(em) - 1; break; }
+				}
+				for (int c = reflen1 + lane; c < NC; c += 32) cons[c] = 0xFF;   // beyond the end nothing matches
+				__syncwarp();
+			}
+		}
+		// ---- finalize
+		const bool iscl = kept >= 2;
+		int sv = 0, rend = 0;
+		unsigned long long refoff = 0;
+		if (iscl) {
+			// sv = first covered column, rend = end of the right-most kept member (kthread_bucket.c:285-317)
+			int first_cov = ncol;
+			for (int c0 = 0; c0 < ncol; c0 += 32) {
+				int c = c0 + lane; bool cov = false;
+				if (c < ncol) cov = (cnt[c] | cnt[NC + c] | cnt[2 * NC + c] | cnt[3 * NC + c]) != 0;
+				unsigned cm = __ballot_sync(0xFFFFFFFFu, cov);
+				if (cm) { first_cov = c0 + __ffs(cm) - 1; break; }
+			}
+			sv = first_cov;
+			int last_cov = 0;
+			for (int c0 = ((ncol - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
+				int c = c0 + lane; bool cov = false;
+				if (c < ncol) cov = (cnt[c] | cnt[NC + c] | cnt[2 * NC + c] | cnt[3 * NC + c]) != 0;
+				unsigned cm = __ballot_sync(0xFFFFFFFFu, cov);
+				if (cm) { last_cov = c0 + 31 - __clz(cm); break; }
+			}
+			rend = last_cov + 1;    // == max(off)+L over kept members: a member covers every column of its span
+			const int reflen2 = rend - sv;
+			if (lane == 0) refoff = atomicAdd(&counters[CT_REFCURSOR], (unsigned long long)reflen2);
+			refoff = __shfl_sync(0xFFFFFFFFu, refoff, 0);
+			if (refoff + reflen2 > reftmp_cap) { if (lane == 0) atomicAdd(&counters[CT_ERR], 1ull); }
+			else for (int c = sv + lane; c < rend; c += 32) {
+				uint32_t m0 = cnt[c], best = 0;
+				for (int b = 1; b < 4; ++b) { uint32_t v = cnt[b * NC + c]; if (v > m0) { m0 = v; best = b; } }
+				o.reftmp[refoff + (c - sv)] = "ACGT"[best];
+			}
+			if (lane == 0) { o.g_reflen[g] = (unsigned long long)reflen2; o.g_refoff[g] = refoff; }
+		} else if (lane == 0) { o.g_reflen[g] = 0; o.g_refoff[g] = 0; }
+		// per-member ranks and records
+		int rk_keep = 0, rk_rej = 0;
+		const int nrej = (int)cntm - kept;
+		for (uint32_t j0 = 0; j0 < cntm; j0 += 32) {
+			uint32_t j = j0 + lane; bool valid = j < cntm; bool keep = false;
+			unsigned long long k2 = 0;
+			if (valid) { keep = o.status[s + j] == 1; k2 = el[s + j].y; }
+			unsigned km = __ballot_sync(0xFFFFFFFFu, valid && keep), rm = __ballot_sync(0xFFFFFFFFu, valid && !keep);
+			unsigned lt = (1u << lane) - 1u;
+			if (valid) {
+				if (keep) {
+					if (iscl) {
+						int off = (int)(k2 >> MCB_POSINV_SHIFT) - posinv0;
+						o.erank[s + j] = rk_keep + __popc(km & lt);
+						o.newrec[s + j] = ((unsigned long long)mcb_k2_rid(k2) << 32) | ((unsigned long long)(off - sv) << 1) | (k2 & 1);
+					} else { o.status[s + j] = 3; o.erank[s + j] = nrej; }     // lone survivor: after the rejects (:476-498)
+				} else o.erank[s + j] = rk_rej + __popc(rm & lt);
+			}
+			rk_keep += __popc(km); rk_rej += __popc(rm);
+		}
+		if (lane == 0) {
+			const uint32_t nout = iscl ? nrej : cntm;
+			o.g_iscl[g] = iscl; o.g_kept[g] = iscl ? kept : 0;
+			o.g_sg[g] = last_round ? nout : 0; o.g_resk[g] = last_round ? 0 : nout;
+		}
+		__syncwarp();
+	}
+}
+
+// scatter per element into the compact outputs (bases come from exclusive scans over the group arrays)
+struct ScatIn {
+	const uint8_t *status; const uint32_t *erank; const uint64_t *newrec; const uint32_t *hscan;
+	const uint32_t *g_iscl, *g_kept, *g_sg, *g_resk;     // exclusive-scanned
+};
+__global__ void k_scatter_members(const ulonglong2 *__restrict__ el, uint64_t n, ScatIn in, int last_round,
+                                  uint64_t mem_base, uint64_t sg_base, uint64_t *__restrict__ cl_a, uint32_t *__restrict__ sg, uint32_t *__restrict__ resk)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	bool head = i == 0 || el[i].x != el[i - 1].x;
+	uint32_t g = in.hscan[i] - (head ? 0u : 1u);
+	uint8_t st = in.status[i];
+	uint32_t rid = mcb_k2_rid(el[i].y);
+	if (st == 1) cl_a[mem_base + in.g_kept[g] + in.erank[i]] = in.newrec[i];
+	else if (st == 0 || last_round) sg[sg_base + in.g_sg[g] + in.erank[i]] = rid;
+	else resk[in.g_resk[g] + in.erank[i]] = rid;
+}
+// one warp per group: cluster table entries + consensus string copy
+__global__ void k_scatter_clusters(const uint32_t *__restrict__ gstart, uint64_t G, const uint32_t *__restrict__ g_iscl_scan, const uint32_t *__restrict__ g_kept_scan,
+                                   const unsigned long long *__restrict__ g_reflen_scan, const unsigned long long *__restrict__ g_refoff,
+                                   const unsigned long long *__restrict__ totals /* [CT_*] */, const char *__restrict__ reftmp,
+                                   uint64_t cl_base, uint64_t mem_base, uint64_t ref_base,
+                                   uint32_t *__restrict__ cl_n, uint64_t *__restrict__ cl_a_off, uint64_t *__restrict__ cl_ref_off, char *__restrict__ cl_ref)
+{
+	const int lane = threadIdx.x & 31;
+	uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (g >= G) return;
+	const uint32_t ci = g_iscl_scan[g];
+	const uint32_t ci_next = g + 1 < G ? g_iscl_scan[g + 1] : (uint32_t)totals[CT_TOT_CL];
+	if (ci_next == ci) return;                                    // not a cluster
+	const uint32_t kb = g_kept_scan[g];
+	const uint32_t kb_next = g + 1 < G ? g_kept_scan[g + 1] : (uint32_t)totals[CT_TOT_MEM];
+	const unsigned long long rb = g_reflen_scan[g];
+	const unsigned long long rb_next = g + 1 < G ? g_reflen_scan[g + 1] : totals[CT_TOT_REF];
+	if (lane == 0) {
+		cl_n[cl_base + ci] = kb_next - kb;
+		cl_a_off[cl_base + ci] = mem_base + kb;
+		cl_ref_off[cl_base + ci] = ref_base + rb;
+	}
+	const unsigned long long len = rb_next - rb, so = g_refoff[g];
+	for (unsigned long long c = lane; c < len; c += 32) cl_ref[ref_base + rb + c] = reftmp[so + c];
+}
+
+// ---------------------------------------------------------------- K4: first m windowed minimizers of each new seed contig
+__global__ void k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count,
+                            int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cl_count) return;
+	const uint64_t c = cl_first + i;
+	const uint64_t b = cl_ref_off[c], e = cl_ref_off[c + 1];
+	McbLhEmitArray em; em.out = mi + c * m; em.cap = m; em.n = 0;
+	mcb_tuple ring[MCB_LH_WMAX];
+	mcb_sketch_lh_core(cl_ref + b, (int)(e - b), w, k, (uint32_t)(c << 8), ring, em, (int64_t)m);
+	mi_cnt[c] = (uint8_t)(em.n < m ? em.n : m);
+}
+
+// ================================================================= host side
+static int sync_counters(mcb_ctx *ctx, unsigned long long **hc)
+{
+	MCB_TRY(ctx->h_counters.ensure(64 * 8));
+	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	*hc = ctx->h_counters.as<unsigned long long>();
+	return MCB_OK;
+}
+
+static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_reads_result *res)
+{
+	const int L = ctx->L, Wd = ctx->Wd, WS = ctx->WS;
+	const int pbase = L + ctx->prm.max_rounds;
+	ctx->n_reads = n; ctx->reads_loaded = false; ctx->bucket_done = false;
+	MCB_TRY(ctx->d_packed.ensure((size_t)n * WS * 8 + 16));
+	MCB_TRY(ctx->d_cls.ensure(n + 16));
+	MCB_TRY(ctx->d_elemA.ensure((size_t)n * 16 + 16));
+	MCB_TRY(ctx->d_elemB.ensure((size_t)n * 16 + 16));
+	MCB_TRY(ctx->d_counters.ensure(64 * 8));
+	MCB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64 * 8, ctx->stream));
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	unsigned long long *hc = nullptr;
+	{
+		McbSpan sp(ctx->tm, "for_reads");
+		if (n) {
+			size_t smem = RD_THREADS * 9 * sizeof(uint64_t) + (((size_t)RD_THREADS * L + 15) & ~(size_t)15);
+			MCB_LAUNCH(ctx, "pack_classify_sketch", k_pack_classify_sketch, mcb_grid_for(n, RD_THREADS), RD_THREADS, smem,
+			           d_rows, n, L, Wd, WS, ctx->prm.k, ctx->prm.diff_threshold, pbase,
+			           ctx->d_packed.as<uint64_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+		}
+	}
+	MCB_TRY(sync_counters(ctx, &hc));
+	if (hc[CT_BADCHAR]) { mcb_set_error("%llu reads contain characters other than A,C,G,T,N (unsupported; the reference's behaviour on them is undefined)", hc[CT_BADCHAR]); return MCB_EINPUT; }
+	if (hc[CT_DEGENERATE]) { mcb_set_error("%llu reads have no valid k-mer (reference would index read 0xFFFFFFFF)", hc[CT_DEGENERATE]); return MCB_EINPUT; }
+	const uint64_t n_sk = hc[CT_SKETCHED], nn = hc[CT_NREADS];
+	ctx->n_valid_round1 = n_sk; ctx->n_nreads = nn;
+	// ---- side table of reads with N
+	MCB_TRY(ctx->d_nread_rid.ensure(nn * 4 + 16));
+	MCB_TRY(ctx->d_nread_mask.ensure(nn * WS * 8 + 16));
+	MCB_TRY(ctx->d_scr[0].ensure(n * 4 + 16));
+	MCB_TRY(ctx->d_scr[1].ensure(nn + 16));
+	{
+		McbSpan sp(ctx->tm, "for_reads");
+		if (n && nn) {
+			MCB_LAUNCH(ctx, "hasn_flags", k_hasn_flags, mcb_grid_for(n, 256), 256, 0, ctx->d_cls.as<uint8_t>(), n, ctx->d_scr[0].as<uint32_t>());
+			MCB_TRY(mcb_exclusive_scan_u32(ctx, ctx->d_scr[0].as<uint32_t>(), n, nullptr));
+			MCB_LAUNCH(ctx, "hasn_extract", k_hasn_extract, mcb_grid_for(n, 256), 256, 0, d_rows, ctx->d_cls.as<uint8_t>(), n, L, Wd, WS,
+			           ctx->prm.diff_threshold, ctx->d_scr[0].as<uint32_t>(), ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->d_scr[1].as<uint8_t>());
+		}
+	}
+	// ---- results to the host
+	MCB_TRY(ctx->h_cls.ensure(n + 16));
+	MCB_TRY(ctx->h_nrid.ensure(nn * 4 + 16));
+	MCB_TRY(ctx->h_nrepl.ensure(nn + 16));
+	MCB_TRY(ctx->h_nmask.ensure(nn * WS * 8 + 16));
+	{
+		McbSpan sp(ctx->tm, "d2h");
+		if (n) MCB_CUDA(cudaMemcpyAsync(ctx->h_cls.p, ctx->d_cls.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+		if (nn) {
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_nrid.p, ctx->d_nread_rid.p, nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_nrepl.p, ctx->d_scr[1].p, nn, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_nmask.p, ctx->d_nread_mask.p, nn * WS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+	}
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->tm.collect();
+	// N positions from the masks
+	MCB_TRY(ctx->h_noff.ensure((nn + 1) * 8));
+	uint64_t *noff = ctx->h_noff.as<uint64_t>();
+	const uint64_t *nm = ctx->h_nmask.as<uint64_t>();
+	uint64_t tot = 0;
+	for (uint64_t i = 0; i < nn; ++i) { noff[i] = tot; for (int w = 0; w < Wd; ++w) tot += __builtin_popcountll(nm[i * WS + w]); }
+	noff[nn] = tot;
+	MCB_TRY(ctx->h_npos.ensure(tot * 4 + 16));
+	uint32_t *np = ctx->h_npos.as<uint32_t>();
+	for (uint64_t i = 0, o = 0; i < nn; ++i)
+		for (int w = 0; w < Wd; ++w) { uint64_t m = nm[i * WS + w]; while (m) { int bit = __builtin_ctzll(m); np[o++] = (uint32_t)(w * 32 + bit / 2); m &= m - 1; } }
+	res->n_reads = n; res->cls = ctx->h_cls.as<uint8_t>();
+	res->n_nreads = nn; res->nread_rid = ctx->h_nrid.as<uint32_t>(); res->nread_repl = ctx->h_nrepl.as<uint8_t>();
+	res->nread_off = noff; res->npos = np; res->n_sketched = n_sk;
+	ctx->reads_loaded = true;
+	return MCB_OK;
+}
+
+static int check_ctx(mcb_ctx *ctx) { if (!ctx) { mcb_set_error("null context"); return MCB_EINVAL; } MCB_CUDA(cudaSetDevice(ctx->prm.device)); return MCB_OK; }
+
+extern "C" int mcb_for_reads_device(mcb_ctx *ctx, const char *d_rows, uint64_t n, mcb_reads_result *res)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!res || (n && !d_rows)) { mcb_set_error("mcb_for_reads_device: null argument"); return MCB_EINVAL; }
+	if (((uintptr_t)d_rows & 15) != 0) { mcb_set_error("mcb_for_reads_device: rows must be 16-byte aligned"); return MCB_EINVAL; }
+	if (n >= (1ull << 31)) { mcb_set_error("too many reads (rid is a signed 32-bit int in the reference, kthread_bucket.c:48)"); return MCB_EINVAL; }
+	return for_reads_impl(ctx, (const uint8_t*)d_rows, n, res);
+}
+
+extern "C" int mcb_for_reads(mcb_ctx *ctx, const char *rows, uint64_t n, mcb_reads_result *res)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!res || (n && !rows)) { mcb_set_error("mcb_for_reads: null argument"); return MCB_EINVAL; }
+	const size_t bytes = (size_t)n * ctx->L;
+	MCB_TRY(ctx->d_ascii.ensure(bytes + 16));
+	{
+		McbSpan sp(ctx->tm, "h2d");
+		// pageable source: stage through pinned chunks so the copies are true async DMA
+		const size_t CH = 32u << 20;
+		MCB_TRY(ctx->h_stage.ensure(2 * CH));
+		cudaEvent_t ev[2]; cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+		int slot = 0;
+		for (size_t o = 0; o < bytes; o += CH, slot ^= 1) {
+			size_t len = std::min(CH, bytes - o);
+			char *st = ctx->h_stage.as<char>() + (size_t)slot * CH;
+			cudaEventSynchronize(ev[slot]);
+			memcpy(st, rows + o, len);
+			MCB_CUDA(cudaMemcpyAsync(ctx->d_ascii.as<char>() + o, st, len, cudaMemcpyHostToDevice, ctx->stream));
+			cudaEventRecord(ev[slot], ctx->stream);
+		}
+		cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+	}
+	return mcb_for_reads_device(ctx, ctx->d_ascii.as<char>(), n, res);
+}
+
+extern "C" int mcb_for_reads_ptrs(mcb_ctx *ctx, const void *first_seq_ptr, size_t stride, uint64_t n, int n_threads, mcb_reads_result *res)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!res || (n && !first_seq_ptr)) { mcb_set_error("mcb_for_reads_ptrs: null argument"); return MCB_EINVAL; }
+	const int L = ctx->L;
+	const size_t bytes = (size_t)n * L;
+	MCB_TRY(ctx->d_ascii.ensure(bytes + 16));
+	if (n_threads < 1) n_threads = 1;
+	{
+		McbSpan sp(ctx->tm, "h2d");
+		const uint64_t RCH = std::max<uint64_t>(1, (32u << 20) / L);          // reads per chunk
+		const size_t CH = (size_t)RCH * L;
+		MCB_TRY(ctx->h_stage.ensure(2 * CH));
+		cudaEvent_t ev[2]; cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+		int slot = 0; bool short_read = false;
+		for (uint64_t r0 = 0; r0 < n; r0 += RCH, slot ^= 1) {
+			uint64_t cnt = std::min(RCH, n - r0);
+			char *st = ctx->h_stage.as<char>() + (size_t)slot * CH;
+			cudaEventSynchronize(ev[slot]);
+			auto work = [&](uint64_t a, uint64_t b) {
+				for (uint64_t i = a; i < b; ++i) {
+					const char *s = *(const char *const *)((const char*)first_seq_ptr + (r0 + i) * stride);
+					if (memchr(s, 0, L)) short_read = true; else memcpy(st + i * L, s, L);
+				}
+			};
+			int T = (int)std::min<uint64_t>(n_threads, (cnt + 4095) / 4096);
+			if (T <= 1) work(0, cnt);
+			else {
+				std::vector<std::thread> th;
+				for (int t = 0; t < T; ++t) th.emplace_back(work, cnt * t / T, cnt * (t + 1) / T);
+				for (auto &x : th) x.join();
+			}
+			if (short_read) { cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); mcb_set_error("a read is shorter than readlen=%d", L); return MCB_EINPUT; }
+			MCB_CUDA(cudaMemcpyAsync(ctx->d_ascii.as<char>() + r0 * L, st, cnt * L, cudaMemcpyHostToDevice, ctx->stream));
+			cudaEventRecord(ev[slot], ctx->stream);
+		}
+		cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+	}
+	return mcb_for_reads_device(ctx, ctx->d_ascii.as<char>(), n, res);
+}
+
+extern "C" int mcb_debug_read_tuples(mcb_ctx *ctx, mcb_tuple *out)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!ctx->reads_loaded || ctx->bucket_done) { mcb_set_error("mcb_debug_read_tuples: call right after mcb_for_reads"); return MCB_ESTATE; }
+	const uint64_t n = ctx->n_reads;
+	if (!n) return MCB_OK;
+	MCB_TRY(ctx->d_scr[0].ensure(n * 16));
+	MCB_LAUNCH(ctx, "elem_to_tuple", k_elem_to_tuple, mcb_grid_for(n, 256), 256, 0, ctx->d_elemA.as<ulonglong2>(), n, ctx->L, ctx->prm.k,
+	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[0].as<mcb_tuple>(), 1);
+	MCB_CUDA(cudaMemcpyAsync(out, ctx->d_scr[0].p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MCB_OK;
+}
+
+extern "C" int mcb_debug_sketch_two(mcb_ctx *ctx, const uint32_t *rids, uint64_t n, int k, mcb_tuple *out)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!ctx->reads_loaded) { mcb_set_error("mcb_debug_sketch_two: no reads loaded"); return MCB_ESTATE; }
+	if (k < 1 || k > 31) { mcb_set_error("k out of range"); return MCB_EINVAL; }
+	if (!n) return MCB_OK;
+	for (uint64_t i = 0; i < n; ++i) if (rids[i] >= ctx->n_reads) { mcb_set_error("rid out of range"); return MCB_EINVAL; }
+	MCB_TRY(ctx->d_scr[0].ensure(n * 4)); MCB_TRY(ctx->d_scr[1].ensure(n * 16)); MCB_TRY(ctx->d_scr[2].ensure(n * 16));
+	MCB_CUDA(cudaMemcpyAsync(ctx->d_scr[0].p, rids, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	// note: positions are encoded against prm.k, decode with the same
+	MCB_LAUNCH(ctx, "resketch", k_resketch, mcb_grid_for(n, 128), 128, 0, ctx->d_packed.as<uint64_t>(), ctx->WS, ctx->L, ctx->prm.k, k,
+	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[0].as<uint32_t>(), n, ctx->d_scr[1].as<ulonglong2>(), ctx->d_counters.as<unsigned long long>());
+	MCB_LAUNCH(ctx, "elem_to_tuple", k_elem_to_tuple, mcb_grid_for(n, 256), 256, 0, ctx->d_scr[1].as<ulonglong2>(), n, ctx->L, ctx->prm.k,
+	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[2].as<mcb_tuple>(), 0);
+	MCB_CUDA(cudaMemcpyAsync(out, ctx->d_scr[2].p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MCB_OK;
+}
+
+extern "C" int mcb_debug_unpack_reads(mcb_ctx *ctx, char *rows_out)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!ctx->reads_loaded) { mcb_set_error("mcb_debug_unpack_reads: no reads loaded"); return MCB_ESTATE; }
+	const uint64_t tot = ctx->n_reads * (uint64_t)ctx->L;
+	if (!tot) return MCB_OK;
+	MCB_TRY(ctx->d_scr[0].ensure(tot));
+	MCB_LAUNCH(ctx, "unpack", k_unpack, mcb_grid_for(tot, 256), 256, 0, ctx->d_packed.as<uint64_t>(), ctx->n_reads, ctx->L, ctx->WS, ctx->d_scr[0].as<char>());
+	MCB_CUDA(cudaMemcpyAsync(rows_out, ctx->d_scr[0].p, tot, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MCB_OK;
+}
+
+// ---------------------------------------------------------------- kt_for_bucket
+// device accumulation buffers that must survive growth
+static int grow_preserve(mcb_ctx *ctx, DBuf &b, size_t used, size_t need)
+{
+	if (need <= b.cap) return MCB_OK;
+	DBuf nb; MCB_TRY(nb.ensure(need + need / 2));
+	if (used) MCB_CUDA(cudaMemcpyAsync(nb.p, b.p, used, cudaMemcpyDeviceToDevice, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	b.release(); b = nb;
+	return MCB_OK;
+}
+
+extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!res) { mcb_set_error("mcb_for_bucket: null result"); return MCB_EINVAL; }
+	if (!ctx->reads_loaded || ctx->bucket_done) { mcb_set_error("mcb_for_bucket: needs a fresh mcb_for_reads"); return MCB_ESTATE; }
+	const int L = ctx->L, WS = ctx->WS, k = ctx->prm.k, m = ctx->prm.first_mininum, max_rounds = ctx->prm.max_rounds;
+	const int pbase = L + max_rounds;
+	const uint64_t N = ctx->n_reads;
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	unsigned long long *hc = nullptr;
+	// d_scr roles: 0 head scan, 1 gstart, 2 status, 3 erank, 4 newrec, 5..9 group arrays, 10 refoff, 11 resk list
+	DBuf &b_hs = ctx->d_scr[0], &b_gs = ctx->d_scr[1], &b_st = ctx->d_scr[2], &b_er = ctx->d_scr[3], &b_nr = ctx->d_scr[4];
+	DBuf &b_gc = ctx->d_scr[5], &b_gk = ctx->d_scr[6], &b_gsg = ctx->d_scr[7], &b_grk = ctx->d_scr[8], &b_grl = ctx->d_scr[9], &b_gro = ctx->d_scr[10], &b_rk = ctx->d_scr[11];
+	// accumulated outputs (device): cluster tables + sg
+	DBuf d_cl_n, d_cl_aoff, d_cl_a, d_cl_roff, d_cl_ref, d_sg, d_mi, d_micnt;
+	struct Rel { DBuf *b[8]; ~Rel() { for (auto x : b) if (x) x->release(); } } rel = {{&d_cl_n, &d_cl_aoff, &d_cl_a, &d_cl_roff, &d_cl_ref, &d_sg, &d_mi, &d_micnt}};
+	uint64_t tot_cl = 0, tot_mem = 0, tot_ref = 0, tot_sg = 0, tot_sk = ctx->n_valid_round1;
+	const int NC = ((2 * L + 2 * max_rounds + 8 + 31) / 32) * 32;
+	const size_t cs_per_warp = (((size_t)NC * 16 + NC + CS_MB * 8 * 8 + CS_MB * 16) + 15) & ~(size_t)15;
+	const size_t cs_smem = cs_per_warp * CS_WARPS;
+	if (cs_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
+	// the ASCII buffer is dead after mcb_for_reads: reuse it for consensus strings before compaction
+	MCB_TRY(ctx->d_ascii.ensure((size_t)N * L + 16));
+	const uint64_t reftmp_cap = ctx->d_ascii.cap;
+
+	ulonglong2 *cur = ctx->d_elemA.as<ulonglong2>(), *alt = ctx->d_elemB.as<ulonglong2>();
+	uint64_t n_in = N;                 // elements handed to the sort (round 1: all reads, invalid ones sort last)
+	uint64_t n_valid = ctx->n_valid_round1;
+	int last_rounds = 0, rounds = 0;
+	long long pre_cluster_reads = 0;
+	MCB_TRY(d_sg.ensure(N * 4 + 16));
+	const int span_h = ctx->tm.begin("for_bucket");
+	for (int r = 1;; ++r) {
+		if (k - r <= 9) ++last_rounds;                       // kthread_bucket.c:584-585
+		if (r == max_rounds - 1) ++last_rounds;
+		const int is_last = last_rounds ? 1 : 0;
+		const int kmer = k - r;
+		rounds = r;
+		uint64_t n_cl_new = 0, n_mem_new = 0, n_resk = 0;
+		if (n_valid > 0) {
+			// ---- K2: one stable sort; key = (bucket, minimizer, adjusted pos desc, rid asc)
+			std::vector<McbSortPass> passes;
+			if (r > 1) mcb_add_bit_passes(passes, 1, 0, 1 + mcb_bits_for(N));          // strand + rid (round 1 arrives in rid order)
+			mcb_add_bit_passes(passes, 1, MCB_POSINV_SHIFT, MCB_POSINV_SHIFT + mcb_bits_for(pbase));
+			const int kbits = r == 1 ? 2 * k : 2 * (kmer + 1);                      // tuples of round r were hashed with k-(r-1) (r>=2) or k
+			mcb_add_bit_passes(passes, 0, 0, std::max(1, kbits - 14));
+			mcb_add_bit_passes(passes, 0, 50, 64);
+			ulonglong2 *sorted = nullptr;
+			MCB_TRY(mcb_radix_sort(ctx, cur, alt, n_in, passes.data(), (int)passes.size(), &sorted));
+			if (sorted != cur) { alt = cur; cur = sorted; }
+			const uint64_t n = n_valid;
+			// ---- groups
+			MCB_TRY(b_hs.ensure(n * 4 + 16)); MCB_TRY(b_gs.ensure((n + 2) * 4));
+			MCB_LAUNCH(ctx, "heads", k_heads, mcb_grid_for(n, 256), 256, 0, cur, n, b_hs.as<uint32_t>());
+			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_hs.as<uint32_t>(), n, (uint64_t*)&dc[CT_G]));
+			MCB_LAUNCH(ctx, "gstart", k_gstart, mcb_grid_for(n, 256), 256, 0, cur, n, b_hs.as<uint32_t>(), &dc[CT_G], b_gs.as<uint32_t>());
+			MCB_TRY(sync_counters(ctx, &hc));
+			const uint64_t G = hc[CT_G];
+			// ---- K3 consensus
+			MCB_TRY(b_st.ensure(n + 16)); MCB_TRY(b_er.ensure(n * 4 + 16)); MCB_TRY(b_nr.ensure(n * 8 + 16));
+			MCB_TRY(b_gc.ensure(G * 4 + 16)); MCB_TRY(b_gk.ensure(G * 4 + 16)); MCB_TRY(b_gsg.ensure(G * 4 + 16)); MCB_TRY(b_grk.ensure(G * 4 + 16));
+			MCB_TRY(b_grl.ensure(G * 8 + 16)); MCB_TRY(b_gro.ensure(G * 8 + 16));
+			MCB_CUDA(cudaMemsetAsync(&dc[CT_REFCURSOR], 0, 8, ctx->stream));
+			ConsOut co; co.status = b_st.as<uint8_t>(); co.erank = b_er.as<uint32_t>(); co.newrec = b_nr.as<uint64_t>();
+			co.g_iscl = b_gc.as<uint32_t>(); co.g_kept = b_gk.as<uint32_t>(); co.g_sg = b_gsg.as<uint32_t>(); co.g_resk = b_grk.as<uint32_t>();
+			co.g_reflen = b_grl.as<unsigned long long>(); co.g_refoff = b_gro.as<unsigned long long>(); co.reftmp = ctx->d_ascii.as<char>();
+			unsigned cgrid = mcb_grid_for(G, CS_WARPS, (unsigned)ctx->sm_count * 16);
+			MCB_LAUNCH(ctx, "consensus", k_consensus, cgrid, CS_WARPS * 32, cs_smem, cur, b_gs.as<uint32_t>(), G, ctx->d_packed.as<uint64_t>(), WS, L,
+			           ctx->prm.diff_threshold, pbase, NC, is_last, co, dc, reftmp_cap);
+			// ---- bases
+			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_gc.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_CL]));
+			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_gk.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_MEM]));
+			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_gsg.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_SG]));
+			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_grk.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_RESK]));
+			MCB_TRY(mcb_exclusive_scan_u64(ctx, b_grl.as<uint64_t>(), G, (uint64_t*)&dc[CT_TOT_REF]));
+			MCB_TRY(sync_counters(ctx, &hc));
+			if (hc[CT_ERR]) { mcb_set_error("internal: consensus table overflow (%llu groups)", hc[CT_ERR]); return MCB_EINVAL; }
+			n_cl_new = hc[CT_TOT_CL]; n_mem_new = hc[CT_TOT_MEM]; n_resk = hc[CT_TOT_RESK];
+			const uint64_t n_sg_new = hc[CT_TOT_SG], n_ref_new = hc[CT_TOT_REF];
+			MCB_TRY(grow_preserve(ctx, d_cl_n, tot_cl * 4, (tot_cl + n_cl_new) * 4 + 16));
+			MCB_TRY(grow_preserve(ctx, d_cl_aoff, tot_cl * 8, (tot_cl + n_cl_new + 1) * 8 + 16));
+			MCB_TRY(grow_preserve(ctx, d_cl_roff, tot_cl * 8, (tot_cl + n_cl_new + 1) * 8 + 16));
+			MCB_TRY(grow_preserve(ctx, d_cl_a, tot_mem * 8, (tot_mem + n_mem_new) * 8 + 16));
+			MCB_TRY(grow_preserve(ctx, d_cl_ref, tot_ref, tot_ref + n_ref_new + 16));
+			MCB_TRY(b_rk.ensure(n_resk * 4 + 16));
+			ScatIn si; si.status = b_st.as<uint8_t>(); si.erank = b_er.as<uint32_t>(); si.newrec = b_nr.as<uint64_t>(); si.hscan = b_hs.as<uint32_t>();
+			si.g_iscl = b_gc.as<uint32_t>(); si.g_kept = b_gk.as<uint32_t>(); si.g_sg = b_gsg.as<uint32_t>(); si.g_resk = b_grk.as<uint32_t>();
+			MCB_LAUNCH(ctx, "scatter_members", k_scatter_members, mcb_grid_for(n, 256), 256, 0, cur, n, si, is_last, tot_mem, tot_sg,
+			           d_cl_a.as<uint64_t>(), d_sg.as<uint32_t>(), b_rk.as<uint32_t>());
+			MCB_LAUNCH(ctx, "scatter_clusters", k_scatter_clusters, mcb_grid_for(G * 32, 256), 256, 0, b_gs.as<uint32_t>(), G, b_gc.as<uint32_t>(), b_gk.as<uint32_t>(),
+			           b_grl.as<unsigned long long>(), b_gro.as<unsigned long long>(), dc, ctx->d_ascii.as<char>(), tot_cl, tot_mem, tot_ref,
+			           d_cl_n.as<uint32_t>(), d_cl_aoff.as<uint64_t>(), d_cl_roff.as<uint64_t>(), d_cl_ref.as<char>());
+			// close the offset tables
+			{
+				uint64_t endv[2] = { tot_mem + n_mem_new, tot_ref + n_ref_new };
+				MCB_CUDA(cudaMemcpyAsync(d_cl_aoff.as<uint64_t>() + tot_cl + n_cl_new, &endv[0], 8, cudaMemcpyHostToDevice, ctx->stream));
+				MCB_CUDA(cudaMemcpyAsync(d_cl_roff.as<uint64_t>() + tot_cl + n_cl_new, &endv[1], 8, cudaMemcpyHostToDevice, ctx->stream));
+				MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+			}
+			// ---- K4: first m minimizers of each new seed contig (window rw, k = reads->k; kthread_bucket.c:458)
+			MCB_TRY(grow_preserve(ctx, d_mi, tot_cl * m * 16, (tot_cl + n_cl_new) * m * 16 + 16));
+			MCB_TRY(grow_preserve(ctx, d_micnt, tot_cl, tot_cl + n_cl_new + 16));
+			if (n_cl_new)
+				MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh, mcb_grid_for(n_cl_new, 64), 64, 0, d_cl_ref.as<char>(), d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new,
+				           ctx->prm.rw, k, m, d_mi.as<mcb_tuple>(), d_micnt.as<uint8_t>());
+			tot_cl += n_cl_new; tot_mem += n_mem_new; tot_ref += n_ref_new; tot_sg += n_sg_new;
+			// ---- rejected reads go to the next round with a shorter k-mer (kthread_bucket.c:205-212,488-496)
+			if (!is_last && n_resk) {
+				MCB_LAUNCH(ctx, "resketch", k_resketch, mcb_grid_for(n_resk, 128), 128, 0, ctx->d_packed.as<uint64_t>(), WS, L, k, kmer, pbase,
+				           b_rk.as<uint32_t>(), n_resk, alt, dc);
+				ulonglong2 *t = cur; cur = alt; alt = t;
+				tot_sk += n_resk;
+			}
+		}
+		n_in = n_valid = (is_last ? 0 : n_resk);
+		if (last_rounds) ++last_rounds;                      // kthread_bucket.c:594
+		const long long cluster_reads = (long long)tot_mem;  // sum of cluster sizes so far (:607-611)
+		if (cluster_reads - pre_cluster_reads < 100) ++last_rounds;
+		pre_cluster_reads = cluster_reads;
+		if (last_rounds > 1) break;
+	}
+	ctx->tm.end(span_h);
+	MCB_TRY(sync_counters(ctx, &hc));
+	if (hc[CT_DEGENERATE]) { mcb_set_error("%llu re-sketched reads have no valid k-mer", hc[CT_DEGENERATE]); return MCB_EINPUT; }
+	// ---- results to the host
+	MCB_TRY(ctx->h_cl_n.ensure(tot_cl * 4 + 16)); MCB_TRY(ctx->h_cl_a_off.ensure((tot_cl + 1) * 8)); MCB_TRY(ctx->h_cl_ref_off.ensure((tot_cl + 1) * 8));
+	MCB_TRY(ctx->h_cl_a.ensure(tot_mem * 8 + 16)); MCB_TRY(ctx->h_cl_ref.ensure(tot_ref + 16)); MCB_TRY(ctx->h_sg.ensure(tot_sg * 4 + 16));
+	MCB_TRY(ctx->h_mi.ensure(tot_cl * m * 16 + 16)); MCB_TRY(ctx->h_mi_cnt.ensure(tot_cl + 16));
+	{
+		McbSpan sp(ctx->tm, "d2h");
+		if (tot_cl) {
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_n.p, d_cl_n.p, tot_cl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_a_off.p, d_cl_aoff.p, (tot_cl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_ref_off.p, d_cl_roff.p, (tot_cl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_a.p, d_cl_a.p, tot_mem * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_ref.p, d_cl_ref.p, tot_ref, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_mi.p, d_mi.p, tot_cl * m * 16, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_mi_cnt.p, d_micnt.p, tot_cl, cudaMemcpyDeviceToHost, ctx->stream));
+		} else { ctx->h_cl_a_off.as<uint64_t>()[0] = 0; ctx->h_cl_ref_off.as<uint64_t>()[0] = 0; }
+		if (tot_sg) MCB_CUDA(cudaMemcpyAsync(ctx->h_sg.p, d_sg.p, tot_sg * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->tm.collect();
+	res->n_clusters = tot_cl; res->cl_n = ctx->h_cl_n.as<uint32_t>(); res->cl_a_off = ctx->h_cl_a_off.as<uint64_t>(); res->cl_a = ctx->h_cl_a.as<uint64_t>();
+	res->cl_ref_off = ctx->h_cl_ref_off.as<uint64_t>(); res->cl_ref = ctx->h_cl_ref.as<char>();
+	res->n_sg = tot_sg; res->sg = ctx->h_sg.as<uint32_t>();
+	res->mi_cnt = ctx->h_mi_cnt.as<uint8_t>(); res->mi = ctx->h_mi.as<mcb_tuple>();
+	res->rounds = rounds; res->n_sketched_total = tot_sk; res->n_grouped = tot_mem;
+	ctx->bucket_done = true;
+	return MCB_OK;
+}

@@ -1,0 +1,160 @@
+"""TEST INFRASTRUCTURE: run the reference binary built under oracle/_ref (oracle/ref/build_ref.sh) on a seeded
+synthetic read set and load the state dumps its link-time wrappers write (oracle/ref/mcref_wrap.cpp).
+
+Results are cached under tests/_cache/<key>/ (git-ignored; it travels to the GPU box with the snapshot, so a cache
+filled in the build container is reused there; when it is missing the binary is simply run again — it is a plain
+x86-64 executable and does not need /root/reference at run time).
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import resource
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from minicom_b200 import synth  # noqa: E402
+
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+CACHE = os.path.join(ROOT, "tests", "_cache")
+
+
+def ref_binary(L: int, mode: str = "sg") -> str:
+    return os.path.join(REF_DIR, f"minicom_ref_L{L}_{mode}")
+
+
+def have_reference(L: int, mode: str = "sg") -> bool:
+    return os.path.exists(ref_binary(L, mode))
+
+
+def _unlimit_stack():
+    try:
+        resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
+    except (ValueError, OSError):
+        pass
+
+
+def run_reference(reads: np.ndarray, workdir: str, mode: str = "sg", env_opts: dict | None = None, threads: int = 1,
+                  dump: bool = True, reads2: np.ndarray | None = None) -> dict:
+    """Runs the reference on `reads` inside workdir; returns {'timing': {...}, 'dump': dir, 'out': dir}."""
+    L = reads.shape[1]
+    exe = ref_binary(L, mode)
+    if not os.path.exists(exe):
+        raise FileNotFoundError(f"{exe} missing: run oracle/ref/build_ref.sh {L} {mode} where /root/reference exists")
+    os.makedirs(workdir, exist_ok=True)
+    fq = os.path.join(workdir, "in.fastq")
+    synth.write_fastq(fq, reads)
+    args = [exe, fq]
+    if reads2 is not None:
+        fq2 = os.path.join(workdir, "in2.fastq")
+        synth.write_fastq(fq2, reads2)
+        args.append(fq2)
+    out = os.path.join(workdir, "out")
+    dumpdir = os.path.join(workdir, "dump")
+    tmpd = os.path.join(workdir, "tmp") + "/"
+    for d in (out, dumpdir, tmpd):
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
+    args.append(out)
+    env = dict(os.environ)
+    env.update({"MC_T": str(threads), "MC_TMPDIR": tmpd, "MC_TIMING": os.path.join(workdir, "timing.json"), "OMP_NUM_THREADS": str(threads)})
+    if dump:
+        env.update({"MC_DUMP": dumpdir, "MC_DUMP_SEQS": "1"})
+    for k, v in (env_opts or {}).items():
+        env[k] = str(v)
+    p = subprocess.run(args, env=env, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, preexec_fn=_unlimit_stack)
+    if p.returncode != 0:
+        raise RuntimeError(f"reference failed ({p.returncode}): {p.stdout.decode()[-2000:]}")
+    with open(os.path.join(workdir, "timing.json")) as f:
+        timing = json.load(f)
+    os.remove(fq)
+    return {"timing": timing, "dump": dumpdir, "out": out, "log": p.stdout.decode()}
+
+
+def cached_reference(n_reads: int, L: int, G: int, seed: int, special: float = 0.0, mode: str = "sg", env_opts: dict | None = None):
+    """(reads, Dump) for a seeded synthetic set; the reference is run once per key."""
+    key = json.dumps([n_reads, L, G, seed, special, mode, sorted((env_opts or {}).items())])
+    h = hashlib.sha1(key.encode()).hexdigest()[:16]
+    wd = os.path.join(CACHE, h)
+    reads = synth.make_reads(n_reads, L, G, seed=seed, special=special)
+    if not os.path.exists(os.path.join(wd, "ok")):
+        shutil.rmtree(wd, ignore_errors=True)
+        run_reference(reads, wd, mode=mode, env_opts=env_opts)
+        with open(os.path.join(wd, "ok"), "w") as f:
+            f.write(key)
+    return reads, Dump(os.path.join(wd, "dump"))
+
+
+class Dump:
+    """Accessors over the flat little-endian arrays written by mcref_wrap.cpp."""
+
+    def __init__(self, path: str):
+        self.path = path
+
+    def has(self, name):
+        return os.path.exists(os.path.join(self.path, name))
+
+    def arr(self, name, dtype=None):
+        if dtype is None:
+            dtype = {"u64": np.uint64, "u32": np.uint32, "u8": np.uint8}[name.rsplit(".", 1)[1]]
+        return np.fromfile(os.path.join(self.path, name), dtype=dtype)
+
+    def buckets(self, prefix):
+        cnt = self.arr(prefix + "_counts.u64")
+        xy = self.arr(prefix + "_xy.u64").reshape(-1, 2)
+        off = np.zeros(len(cnt) + 1, dtype=np.uint64)
+        np.cumsum(cnt, out=off[1:])
+        return off, xy
+
+    def clusters(self, prefix):
+        n = self.arr(prefix + "_n.u64")
+        a = self.arr(prefix + "_a.u64")
+        rl = self.arr(prefix + "_reflen.u64")
+        ref = self.arr(prefix + "_ref.u8")
+        a_off = np.zeros(len(n) + 1, dtype=np.uint64)
+        np.cumsum(n, out=a_off[1:])
+        r_off = np.zeros(len(n) + 1, dtype=np.uint64)
+        np.cumsum(rl, out=r_off[1:])
+        return {"n": n, "a": a, "a_off": a_off, "ref": ref, "ref_off": r_off, "pert": self.arr(prefix + "_pert.u64")}
+
+    def postings(self, j):
+        """list of (x, ys) in dump order (bucket-major, keys ascending)."""
+        raw = self.arr(f"i{j}_post.u64")
+        out, i = [], 0
+        while i < len(raw):
+            x, n = int(raw[i]), int(raw[i + 1])
+            out.append((x, raw[i + 2:i + 2 + n]))
+            i += 2 + n
+        return out
+
+    def n_idx(self):
+        j = 0
+        while self.has(f"i{j}_post.u64"):
+            j += 1
+        return j
+
+    def n_realign(self):
+        j = 0
+        while self.has(f"h{j}_thr.u64"):
+            j += 1
+        return j
+
+    def seqs(self):
+        with open(os.path.join(self.path, "r_seqs.txt"), "rb") as f:
+            lines = f.read().split(b"\n")
+        return [l for l in lines if l]
+
+    def npos(self, n_reads):
+        raw = self.arr("r_npos.u32")
+        out, i = [], 0
+        for _ in range(n_reads):
+            c = int(raw[i])
+            out.append(raw[i + 1:i + 1 + c])
+            i += 1 + c
+        return out

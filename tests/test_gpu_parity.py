@@ -1,0 +1,184 @@
+"""GPU parity: every entry point of the C-ABI against the state dumps of the reference itself (oracle/_ref, num_thr=1).
+
+Bit-exact comparison of: bucket tuples after kt_for_reads, read classes, N bookkeeping, N-replaced reads, seed
+contigs / singles / index tuples after kt_for_bucket, every minimizer index the host merger builds (posting order
+included), and per threshold round of realign_hash the reads claimed by each contig in append order plus the
+near-poly-A/T diversions.
+"""
+import numpy as np
+import pytest
+
+import refdump
+from minicom_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+# (name, n_reads, L, genome, seed, special fraction, reference env options)
+CASES = [
+    ("20k_special", 20000, 100, 100000, 3, 0.01, {}),
+    ("60k_plain", 60000, 100, 300000, 5, 0.0, {}),
+    ("30k_k25_e6", 30000, 100, 150000, 7, 0.005, {"MC_K": 25, "MC_E": 6, "MC_M": 4, "MC_W": 12, "MC_S": 3, "MC_STEP": 3, "MC_EMAX": 30}),
+]
+
+
+def params_for(L, env):
+    return api.resolve_params(L, k=int(env.get("MC_K", 0)), e=int(env.get("MC_E", 0)), w=int(env.get("MC_W", 0)),
+                              m=int(env.get("MC_M", 0)), max_rounds=int(env.get("MC_MAXROUNDS", 0)))
+
+
+def bucket_major(tuples, b=14):
+    """stable partition of (n,2) tuples by bucket = x & (2^b-1): the order per-bucket pushes would give."""
+    bk = (tuples[:, 0] & np.uint64((1 << b) - 1)).astype(np.int64)
+    order = np.argsort(bk, kind="stable")
+    cnt = np.bincount(bk, minlength=1 << b).astype(np.uint64)
+    off = np.zeros((1 << b) + 1, dtype=np.uint64)
+    np.cumsum(cnt, out=off[1:])
+    return off, tuples[order]
+
+
+def check_reads(ctx, reads, dump, log):
+    n, L = reads.shape
+    rr = ctx.for_reads(reads)
+    for code, name in ((1, "r_allA.u32"), (2, "r_allT.u32"), (3, "r_allN.u32"), (4, "r_fpA.u32"), (5, "r_fpT.u32"), (6, "r_fpN.u32"), (7, "r_Nfile.u32")):
+        want = dump.arr(name)
+        got = np.nonzero(rr.cls == code)[0].astype(np.uint32)
+        assert np.array_equal(got, want), f"class list {name}: got {len(got)} want {len(want)}"
+    t = ctx.debug_read_tuples(n)
+    valid = t[:, 0] != np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert np.array_equal(valid, rr.cls == 0)
+    assert rr.n_sketched == int(valid.sum())
+    off, mine = bucket_major(t[valid])
+    roff, rxy = dump.buckets("r_B0")
+    assert np.array_equal(off, roff), "bucket sizes differ"
+    assert np.array_equal(mine, rxy), "bucket tuples differ"
+    # N bookkeeping
+    want_np = dump.npos(n)
+    has = np.array([len(x) > 0 for x in want_np])
+    assert np.array_equal(np.nonzero(has)[0].astype(np.uint32), rr.nread_rid)
+    for i, rid in enumerate(rr.nread_rid):
+        assert np.array_equal(rr.npos[int(rr.nread_off[i]):int(rr.nread_off[i + 1])], want_np[int(rid)])
+    # N-replaced sequences of the sketched reads
+    seqs = dump.seqs()
+    un = ctx.debug_unpack_reads(n)
+    sk = np.nonzero(rr.cls == 0)[0]
+    want = np.frombuffer(b"".join(seqs[i] for i in sk), dtype=np.uint8).reshape(len(sk), L)
+    assert np.array_equal(un[sk], want), "N-replaced reads differ"
+    for i, rid in enumerate(rr.nread_rid):
+        if rr.cls[rid] == 0:
+            assert rr.nread_repl[i] == seqs[int(rid)][int(rr.npos[int(rr.nread_off[i])])]
+    log.append(f"reads: {n} reads, {rr.n_sketched} sketched, {len(rr.nread_rid)} with N: OK")
+    return rr
+
+
+def check_bucket(ctx, dump, log):
+    br = ctx.for_bucket()
+    cl = dump.clusters("b_cl")
+    assert len(br.cl_n) == len(cl["n"]), f"cluster count {len(br.cl_n)} vs {len(cl['n'])}"
+    assert np.array_equal(br.cl_n.astype(np.uint64), cl["n"])
+    assert np.array_equal(br.cl_a, cl["a"]), "cluster members differ"
+    assert np.array_equal(br.cl_ref_off, cl["ref_off"]), "consensus lengths differ"
+    assert np.array_equal(br.cl_ref, cl["ref"]), "consensus strings differ"
+    assert np.array_equal(br.sg, dump.arr("b_sg.u32")), "singles (order) differ"
+    m = ctx.params.first_mininum
+    keep = np.arange(m)[None, :] < br.mi_cnt[:, None]
+    flat = br.mi[keep]
+    off, mine = bucket_major(flat)
+    roff, rxy = dump.buckets("b_mi")
+    assert np.array_equal(off, roff) and np.array_equal(mine, rxy), "mi[0] tuples differ"
+    log.append(f"bucket: {len(br.cl_n)} seed contigs, {len(br.sg)} singles, {len(flat)} index tuples, {br.rounds} rounds: OK")
+    return br
+
+
+def check_index(ctx, dump, log):
+    for j in range(dump.n_idx()):
+        off, xy = dump.buckets(f"i{j}_in")
+        ix = ctx.idx_build(xy, off)
+        post = dump.postings(j)
+        nk, npost = ix.stats()
+        assert nk == len(post) and npost == len(xy)
+        for x, ys in post:
+            got = ix.get(x)
+            assert np.array_equal(got, ys), f"index {j} key {x:#x}: {got} vs {ys}"
+        assert len(ix.get(0x123456789)) == 0 or any(x == 0x123456789 for x, _ in post)
+        ix.close()
+        log.append(f"index {j}: {len(xy)} tuples, {nk} keys: OK")
+
+
+def check_realign(ctx, dump, n_sg_stage1, env, log):
+    cl = dump.clusters("c_cl")
+    maxsearch = 2000 if n_sg_stage1 <= 5000000 else 500
+    for j in range(dump.n_realign()):
+        sg = dump.arr(f"h{j}_sg.u32")
+        thr = int(dump.arr(f"h{j}_thr.u64")[0])
+        rr = ctx.realign(sg, cl["ref"], cl["ref_off"], thr, maxsearch, int(env.get("MC_S", 0)))
+        want_cnt = dump.arr(f"h{j}_app_cnt.u64")
+        want_y = dump.arr(f"h{j}_app_y.u64")
+        got_cnt = np.bincount(rr.claim_contig, minlength=len(want_cnt)).astype(np.uint64)
+        assert len(rr.claim_y) == len(want_y), f"round {j} thr {thr}: {len(rr.claim_y)} claims vs {len(want_y)}"
+        assert np.array_equal(got_cnt, want_cnt), f"round {j}: per-contig claim counts differ"
+        assert np.all(np.diff(rr.claim_contig.astype(np.int64)) >= 0)
+        assert np.array_equal(rr.claim_y, want_y), f"round {j}: claims / append order differ"
+        assert np.array_equal(sg[rr.claim_sg], (rr.claim_y >> np.uint64(32)).astype(np.uint32))
+        assert np.array_equal(sg[rr.fpA_sg], dump.arr(f"h{j}_fpA.u32")), "near-poly-A list differs"
+        assert np.array_equal(sg[rr.fpT_sg], dump.arr(f"h{j}_fpT.u32")), "near-poly-T list differs"
+        flag = np.zeros(len(sg), dtype=np.uint8)
+        flag[rr.claim_sg] = 1
+        flag[rr.fpA_sg] = 1
+        flag[rr.fpT_sg] = 1
+        assert np.array_equal(flag, dump.arr(f"h{j}_flag.u8")), "sg_flag differs"
+        log.append(f"realign {j}: thr {thr}, {len(sg)} singles, {rr.n_windows} windows, {rr.n_probes} probes, {rr.n_candidates} candidates, "
+                   f"{len(rr.claim_y)} claims, {len(rr.fpA_sg)}+{len(rr.fpT_sg)} polyA/T: OK")
+
+
+def run_case(case, log):
+    name, n, L, G, seed, special, env = case
+    reads, dump = refdump.cached_reference(n, L, G, seed, special, "sg", env)
+    with api.Context(params_for(L, env)) as ctx:
+        check_reads(ctx, reads, dump, log)
+        br = check_bucket(ctx, dump, log)
+        check_index(ctx, dump, log)
+        check_realign(ctx, dump, len(br.sg), env, log)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_front_end_matches_reference(case):
+    log = []
+    try:
+        run_case(case, log)
+    finally:
+        print("\n".join(log))
+
+
+def test_host_buffer_variants_agree():
+    """mcb_for_reads (contiguous rows), mcb_for_reads_ptrs (scattered strings) give identical tuples."""
+    name, n, L, G, seed, special, env = CASES[0]
+    reads, _ = refdump.cached_reference(n, L, G, seed, special, "sg", env)
+    with api.Context(params_for(L, env)) as ctx:
+        ctx.for_reads(reads)
+        t0 = ctx.debug_read_tuples(n)
+    bufs = [np.frombuffer(reads[i].tobytes() + b"\0", dtype=np.uint8).copy() for i in range(n)]
+    ptrs = np.array([b.ctypes.data for b in bufs], dtype=np.uint64)
+    with api.Context(params_for(L, env)) as ctx:
+        ctx.for_reads_ptrs(ptrs, n_threads=4)
+        t1 = ctx.debug_read_tuples(n)
+    assert np.array_equal(t0, t1)
+
+
+if __name__ == "__main__":
+    import sys
+    import traceback
+    sel = sys.argv[1:] or [c[0] for c in CASES]
+    rc = 0
+    for case in CASES:
+        if case[0] not in sel:
+            continue
+        log = []
+        try:
+            run_case(case, log)
+            print(f"[{case[0]}] PASS")
+        except Exception:
+            rc = 1
+            print(f"[{case[0]}] FAIL")
+            traceback.print_exc()
+        print("\n".join("   " + l for l in log))
+    sys.exit(rc)
