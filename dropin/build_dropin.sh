@@ -1,0 +1,47 @@
+#!/bin/bash
+# Builds the drop-in executable: the reference's KEPT host objects, compiled from the sources where they lie under
+# /root/reference/src (nothing is copied), linked with dropin/mcb_dropin.cpp and libminicom_b200.so in place of
+# sketch.o kthread_reads.o kthread_bucket.o kthread_idx.o kthread_hash_realign.o bbhashdict.o.
+#
+# usage: build_dropin.sh <readlen> <sg|order|pe> [wrap]
+#   output: dropin/_build/minicom_b200_L<readlen>_<mode>
+#   with `wrap`: additionally links oracle/ref/mcref_wrap.cpp (state dumps for the parity tests) ->
+#           oracle/_ref/minicom_b200_L<readlen>_<mode>_wrapped      (test infrastructure)
+set -euo pipefail
+L=$1; MODE=$2; WRAPPED=${3:-}
+HERE=$(cd "$(dirname "$0")" && pwd)
+ROOT=$(cd "$HERE/.." && pwd)
+REF=${MC_REFERENCE_SRC:-/root/reference/src}
+[ -d "$REF" ] || { echo "reference sources not found at $REF" >&2; exit 3; }
+B=$HERE/_build/L${L}_${MODE}
+mkdir -p "$B"
+{
+  echo "#pragma once"
+  echo "#include \"mcref_cfg.h\""
+  if [ "$MODE" = order ]; then echo "#define ORDER"; echo "int cmpcluster3(const void *a_, const void *b_);"; fi
+  if [ "$MODE" = pe ]; then echo "#define _PE"; echo "int cmpcluster3(const void *a_, const void *b_);"; fi
+  echo "#define readlen $L"
+  for kv in "num_thr MC_T 1" "inik MC_K 0" "inithr MC_E 0" "inimaxthr MC_EMAX 0" "inistep MC_STEP 0" "ininumdict MC_S 0" "iniw MC_W 0" "inim MC_M 0" "inicbthr MC_CBTHR 0" "inimaxrounds MC_MAXROUNDS 0"; do
+    set -- $kv; echo "#define $1 mcref_cfg_int(\"$2\", $3)"
+  done
+  echo "#define uniqid mcref_cfg_str(\"MC_UNIQID\", \"umc\")"
+  echo "#define output mcref_cfg_str(\"MC_TMPDIR\", \"output_mc/\")"
+} > "$B/config.h"
+CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$ROOT/oracle/ref -I$REF -I$ROOT/include"
+KEPT="bseq misc preprocess kthread_cb kthread_dump minicommain"
+[ "$MODE" = pe ] && KEPT="$KEPT kthread_dump_pe"
+pids=()
+for f in $KEPT; do g++ $CXXFLAGS -c "$REF/$f.c" -o "$B/$f.o" & pids+=($!); done
+g++ $CXXFLAGS -c "$HERE/mcb_dropin.cpp" -o "$B/mcb_dropin.o" & pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+ALL=""; for f in $KEPT; do ALL="$ALL $B/$f.o"; done
+LIBDIR=$ROOT/minicom_b200
+g++ -O3 -fopenmp $ALL "$B/mcb_dropin.o" -L"$LIBDIR" -lminicom_b200 -Wl,-rpath,'$ORIGIN/../../minicom_b200' -o "$HERE/_build/minicom_b200_L${L}_${MODE}" -lm -lz -lpthread
+echo "built $HERE/_build/minicom_b200_L${L}_${MODE}"
+if [ "$WRAPPED" = wrap ]; then
+  g++ $CXXFLAGS -c "$ROOT/oracle/ref/mcref_wrap.cpp" -o "$B/mcref_wrap.o"
+  WRAP="-Wl,--wrap=_Z12kt_for_readsiP7reads_tl -Wl,--wrap=_Z13kt_for_bucketiP7reads_tl -Wl,--wrap=_Z17mm_idx_generationiP8mm_idx_t -Wl,--wrap=_Z15combine_clusteriP7reads_tPi -Wl,--wrap=_Z12realign_hashiP7reads_tii"
+  mkdir -p "$ROOT/oracle/_ref"
+  g++ -O3 -fopenmp $ALL "$B/mcb_dropin.o" "$B/mcref_wrap.o" $WRAP -L"$LIBDIR" -lminicom_b200 -Wl,-rpath,'$ORIGIN/../../minicom_b200' -o "$ROOT/oracle/_ref/minicom_b200_L${L}_${MODE}_wrapped" -lm -lz -lpthread
+  echo "built $ROOT/oracle/_ref/minicom_b200_L${L}_${MODE}_wrapped"
+fi

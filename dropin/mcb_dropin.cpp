@@ -1,0 +1,244 @@
+// mcb_dropin.cpp — the reference-side binding of libminicom_b200.so.
+//
+// Defines, with the reference's own (C++-mangled) signatures, exactly the ten symbols that the KEPT objects of
+// yuansliu/minicom (minicommain.o preprocess.o kthread_cb.o kthread_dump[_pe].o bseq.o misc.o) import from the
+// objects this project replaces (sketch.o kthread_reads.o kthread_bucket.o kthread_idx.o kthread_hash_realign.o
+// bbhashdict.o) — SURVEY.md §8b:
+//     kt_for_reads  kt_for_bucket  mm_idx_init  mm_idx_generation  mm_idx_get  mm_idx_destroy  realign_hash
+//     mm_sketch_lh_ori  seq_nt4_table  invert_code_rule
+// It is compiled inside the reference tree against the reference's headers (breads.h, kvec.h and the generated
+// config.h), the way a maintainer would add it; it contains marshalling only — every computation is
+// a call into the C-ABI (include/minicom_b200.h).  Cluster placement equals the num_thr=1 layout of the reference
+// (all contigs in clusters[idx][0], ids idx<<8), which is the only deterministic configuration of the reference.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "minicom_b200.h"
+// config.h defines `readlen` and `ininumdict` as macros: everything that spells those identifiers comes before it
+static inline void set_readlen(mcb_params *p, int v) { p->readlen = v; }
+#include "breads.h"
+#include "kvec.h"
+#include "config.h"
+
+// ---- data symbols (sketch.c:8-25, kthread_bucket.c:64)
+unsigned char seq_nt4_table[256] = {
+#define R4 4, 4, 4, 4
+#define R16 R4, R4, R4, R4
+	0, 1, 2, 3, R4, R4, R4, R16, R16, R16,
+	4, 0, 4, 1, 4, 4, 4, 2, R4, R4, 4, 4, 4, 4, 3, 4, 4, 4, R4, R4,
+	4, 0, 4, 1, 4, 4, 4, 2, R4, R4, 4, 4, 4, 4, 3, 4, 4, 4, R4, R4,
+	R16, R16, R16, R16, R16, R16, R16, R16
+};
+const char invert_code_rule[4] = {'A', 'C', 'G', 'T'};
+
+static mcb_ctx *g_ctx = 0;
+static double g_wall[4];      // for_reads, for_bucket, idx_build, realign (host wall seconds inside the entry points)
+static int g_calls[4];
+static std::string g_realign_detail;
+
+static void die(const char *where, int rc)
+{
+	fprintf(stderr, "minicom_b200: %s failed (%d): %s\n", where, rc, mcb_last_error());
+	exit(1);
+}
+
+struct McbAtExit {
+	~McbAtExit()
+	{
+		const char *p = getenv("MCB_TIMING");
+		if (p && *p) {
+			FILE *f = fopen(p, "w");
+			if (f) {
+				static char buf[1 << 16];
+				buf[0] = 0;
+				if (g_ctx) mcb_timers_dump(g_ctx, buf, sizeof buf);
+				std::string dev = "{";
+				for (char *line = strtok(buf, "\n"); line; line = strtok(0, "\n")) {
+					char name[128]; double ms; unsigned long long cnt;
+					if (sscanf(line, "%127s %lf %llu", name, &ms, &cnt) == 3) {
+						char e[256]; snprintf(e, sizeof e, "%s\"%s\": [%.6f, %llu]", dev.size() > 1 ? ", " : "", name, ms, cnt);
+						dev += e;
+					}
+				}
+				dev += "}";
+				fprintf(f, "{\"n_reads\": %d, \"readlen\": %d, \"threads\": %d, \"kt_for_reads\": %.6f, \"kt_for_bucket\": %.6f, "
+				        "\"mm_idx_generation\": %.6f, \"n_idx\": %d, \"realign_hash\": %.6f, \"n_realign\": %d, \"realign_rounds\": [%s], "
+				        "\"kernel_launches\": %llu, \"device_ms\": %s}\n",
+				        reads ? reads->n_seq : 0, reads ? reads->seq_len : 0, n_threads, g_wall[0], g_wall[1], g_wall[2], g_calls[2], g_wall[3], g_calls[3],
+				        g_realign_detail.c_str(), g_ctx ? (unsigned long long)mcb_kernel_launches(g_ctx) : 0ull, dev.c_str());
+				fclose(f);
+			}
+		}
+		if (g_ctx) { mcb_destroy(g_ctx); g_ctx = 0; }
+	}
+};
+static McbAtExit g_at_exit;
+
+static mcb_ctx *ctx_for(reads_t *r)
+{
+	if (g_ctx) return g_ctx;
+	mcb_params p;
+	memset(&p, 0, sizeof p);
+	set_readlen(&p, r->seq_len); p.k = r->k; p.b = r->b; p.rw = r->rw;            // resolved by main()/pre_process()
+	p.first_mininum = first_mininum; p.diff_threshold = diff_threshold; p.max_rounds = max_rounds;
+	const char *dev = getenv("MCB_DEVICE");
+	p.device = dev ? atoi(dev) : 0;
+	int rc = mcb_create(&p, &g_ctx);
+	if (rc) die("mcb_create", rc);
+	if (getenv("MCB_TIMING")) mcb_timers_enable(g_ctx, 1);
+	return g_ctx;
+}
+
+// ---- kt_for_reads (kthread_reads.c:247)
+void kt_for_reads(int n_threads_, reads_t *r, long n)
+{
+	double t0 = realtime();
+	mcb_ctx *ctx = ctx_for(r);
+	mcb_reads_result res;
+	int rc = mcb_for_reads_ptrs(ctx, &r->seq[0].seq, sizeof(bseq1_t), (uint64_t)n, n_threads_, &res);
+	if (rc) die("kt_for_reads", rc);
+	sp_reads_t *s = r->sp;
+	for (long i = 0; i < n; ++i) {
+		r->seq[i].n_pos = NULL;
+		switch (res.cls[i]) {
+		case MCB_CLS_ALLA: s->allA++; kv_push(uint32_t, s->allA_id, (uint32_t)i); break;
+		case MCB_CLS_ALLT: s->allT++; kv_push(uint32_t, s->allT_id, (uint32_t)i); break;
+		case MCB_CLS_ALLN: s->allN++; kv_push(uint32_t, s->allN_id, (uint32_t)i); break;
+		case MCB_CLS_FPA: kv_push(uint32_t, r->fpA_id, (uint32_t)i); break;
+		case MCB_CLS_FPT: kv_push(uint32_t, r->fpT_id, (uint32_t)i); break;
+		case MCB_CLS_FPN: kv_push(uint32_t, r->fpN_id, (uint32_t)i); break;
+		case MCB_CLS_NFILE: kv_push(uint32_t, r->Nfile_id, (uint32_t)i); break;
+		default: break;
+		}
+	}
+	for (uint64_t j = 0; j < res.n_nreads; ++j) {
+		uint32_t rid = res.nread_rid[j];
+		uint32_v *np = (uint32_v*)calloc(1, sizeof(uint32_v));
+		for (uint64_t q = res.nread_off[j]; q < res.nread_off[j + 1]; ++q) {
+			kv_push(uint32_t, *np, res.npos[q]);
+			if (res.nread_repl[j]) r->seq[rid].seq[res.npos[q]] = (char)res.nread_repl[j];   // kthread_reads.c:202-204
+		}
+		r->seq[rid].n_pos = np;
+	}
+	g_wall[0] += realtime() - t0; g_calls[0]++;
+}
+
+// ---- kt_for_bucket (kthread_bucket.c:562)
+void kt_for_bucket(int n_threads_, reads_t *r, long n)
+{
+	double t0 = realtime();
+	mcb_ctx *ctx = ctx_for(r);
+	mcb_bucket_result res;
+	int rc = mcb_for_bucket(ctx, &res);
+	if (rc) die("kt_for_bucket", rc);
+	cluster_v *cv = &r->clusters[0][0];
+	for (uint64_t c = 0; c < res.n_clusters; ++c) {
+		cluster_t *p;
+		kv_pushp(cluster_t, *cv, &p);
+		kv_init(*p);
+		size_t nm = res.cl_n[c], len = (size_t)(res.cl_ref_off[c + 1] - res.cl_ref_off[c]);
+		kv_resize(uint64_t, *p, nm);
+		memcpy(p->a, res.cl_a + res.cl_a_off[c], nm * sizeof(uint64_t));
+		p->n = nm;
+		p->ref = (char*)calloc(len + 1, 1);
+		memcpy(p->ref, res.cl_ref + res.cl_ref_off[c], len);
+		p->ennum = 0;
+	}
+	for (uint64_t i = 0; i < res.n_sg; ++i) kv_push(uint32_t, r->sg, res.sg[i]);
+	const int mask = (1 << r->b) - 1, m = first_mininum;
+	for (uint64_t c = 0; c < res.n_clusters; ++c)
+		for (int j = 0; j < res.mi_cnt[c]; ++j) {
+			const mcb_tuple *t = &res.mi[c * m + j];
+			mm128_t v; v.x = t->x; v.y = t->y;
+			mm128_v *pp = &r->mi[0]->B[v.x & mask].a;
+			kv_push(mm128_t, *pp, v);
+		}
+	g_wall[1] += realtime() - t0; g_calls[1]++;
+}
+
+// ---- minimizer index (kthread_idx.c:77-173).  mm_idx_t keeps the reference's layout; the device-built index hangs off B[0].h.
+mm_idx_t *mm_idx_init(int b)
+{
+	mm_idx_t *mi = (mm_idx_t*)calloc(1, sizeof(mm_idx_t));
+	mi->B = (mm_idx_bucket_t*)calloc((size_t)1 << b, sizeof(mm_idx_bucket_t));
+	return mi;
+}
+
+void mm_idx_generation(int n_threads_, mm_idx_t *mi)
+{
+	double t0 = realtime();
+	mcb_ctx *ctx = ctx_for(reads);
+	const int nb = 1 << reads->b;
+	std::vector<const mcb_tuple*> ptrs(nb);
+	std::vector<uint64_t> cnt(nb);
+	for (int i = 0; i < nb; ++i) { ptrs[i] = (const mcb_tuple*)mi->B[i].a.a; cnt[i] = mi->B[i].a.n; }
+	mcb_index *ix = 0;
+	int rc = mcb_idx_build_scattered(ctx, ptrs.data(), cnt.data(), &ix);
+	if (rc) die("mm_idx_generation", rc);
+	for (int i = 0; i < nb; ++i) { free(mi->B[i].a.a); mi->B[i].a.a = 0; mi->B[i].a.n = mi->B[i].a.m = 0; }   // kthread_idx.c:166-167
+	if (mi->B[0].h) mcb_idx_destroy((mcb_index*)mi->B[0].h);
+	mi->B[0].h = ix;
+	g_wall[2] += realtime() - t0; g_calls[2]++;
+}
+
+const uint64_t *mm_idx_get(const mm_idx_t *mi, uint64_t minier, int *n)
+{
+	return mcb_idx_get((const mcb_index*)mi->B[0].h, minier, n);
+}
+
+void mm_idx_destroy(mm_idx_t *mi)
+{
+	if (mi == 0) return;
+	mcb_idx_destroy((mcb_index*)mi->B[0].h);
+	for (int i = 0; i < 1 << reads->b; ++i) free(mi->B[i].a.a);
+	free(mi->B);
+	free(mi);
+}
+
+// ---- mm_sketch_lh_ori (sketch.c:116): per-contig call from the host merger (kthread_cb.c:234,365,418)
+void mm_sketch_lh_ori(const char *str, int len, int w, int k, uint32_t rid, mm128_v *p)
+{
+	mcb_tuple stackbuf[512];
+	int64_t n = mcb_sketch_lh_host(str, len, w, k, rid, stackbuf, 512);
+	const mcb_tuple *src = stackbuf;
+	std::vector<mcb_tuple> big;
+	if (n > 512) { big.resize((size_t)n); mcb_sketch_lh_host(str, len, w, k, rid, big.data(), n); src = big.data(); }
+	for (int64_t i = 0; i < n; ++i) { mm128_t v; v.x = src[i].x; v.y = src[i].y; kv_push(mm128_t, *p, v); }
+}
+
+// ---- realign_hash (kthread_hash_realign.c:569)
+void realign_hash(int n_threads_, reads_t *r, int index, int max_threshold)
+{
+	double t0 = realtime();
+	mcb_ctx *ctx = ctx_for(r);
+	std::vector<cluster_t*> contigs;
+	std::vector<uint64_t> off;
+	std::string refs;
+	for (int t = 0; t < n_threads_; ++t)
+		for (size_t i = 0; i < r->clusters[index][t].n; ++i) {
+			cluster_t *p = &r->clusters[index][t].a[i];
+			qsort(p->a, p->n, sizeof(uint64_t), cmpcluster2);          // kthread_hash_realign.c:318
+			contigs.push_back(p);
+			off.push_back(refs.size());
+			refs.append(p->ref);
+		}
+	off.push_back(refs.size());
+	mcb_realign_result res;
+	int rc = mcb_realign(ctx, r->sg.a, r->sg.n, refs.data(), off.data(), contigs.size(), max_threshold, maxsearch, ininumdict, &res);
+	if (rc) die("realign_hash", rc);
+	for (uint64_t i = 0; i < res.n_fpA; ++i) { r->sg_flag[res.fpA_sg[i]] = true; kv_push(uint32_t, r->fpA_id, r->sg.a[res.fpA_sg[i]]); }
+	for (uint64_t i = 0; i < res.n_fpT; ++i) { r->sg_flag[res.fpT_sg[i]] = true; kv_push(uint32_t, r->fpT_id, r->sg.a[res.fpT_sg[i]]); }
+	for (uint64_t i = 0; i < res.n_claims; ++i) {
+		cluster_t *p = contigs[res.claim_contig[i]];
+		kv_push(uint64_t, *p, res.claim_y[i]);
+		r->sg_flag[res.claim_sg[i]] = true;
+	}
+	double dt = realtime() - t0;
+	char buf[160];
+	snprintf(buf, sizeof buf, "%s{\"thr\": %d, \"singles\": %zu, \"sec\": %.6f, \"claims\": %llu}", g_calls[3] ? ", " : "", max_threshold, (size_t)r->sg.n, dt,
+	         (unsigned long long)res.n_claims);
+	g_realign_detail += buf;
+	g_wall[3] += dt; g_calls[3]++;
+}

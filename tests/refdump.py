@@ -40,11 +40,16 @@ def _unlimit_stack():
         pass
 
 
+def dropin_binary(L: int, mode: str = "sg") -> str:
+    return os.path.join(ROOT, "dropin", "_build", f"minicom_b200_L{L}_{mode}")
+
+
 def run_reference(reads: np.ndarray, workdir: str, mode: str = "sg", env_opts: dict | None = None, threads: int = 1,
-                  dump: bool = True, reads2: np.ndarray | None = None) -> dict:
-    """Runs the reference on `reads` inside workdir; returns {'timing': {...}, 'dump': dir, 'out': dir}."""
+                  dump: bool = True, reads2: np.ndarray | None = None, exe: str | None = None) -> dict:
+    """Runs the reference (or, with `exe`, the drop-in executable) on `reads` inside workdir;
+    returns {'timing': {...}, 'dump': dir, 'out': dir}."""
     L = reads.shape[1]
-    exe = ref_binary(L, mode)
+    exe = exe or ref_binary(L, mode)
     if not os.path.exists(exe):
         raise FileNotFoundError(f"{exe} missing: run oracle/ref/build_ref.sh {L} {mode} where /root/reference exists")
     os.makedirs(workdir, exist_ok=True)
@@ -63,7 +68,8 @@ def run_reference(reads: np.ndarray, workdir: str, mode: str = "sg", env_opts: d
         os.makedirs(d)
     args.append(out)
     env = dict(os.environ)
-    env.update({"MC_T": str(threads), "MC_TMPDIR": tmpd, "MC_TIMING": os.path.join(workdir, "timing.json"), "OMP_NUM_THREADS": str(threads)})
+    env.update({"MC_T": str(threads), "MC_TMPDIR": tmpd, "MC_TIMING": os.path.join(workdir, "timing.json"), "OMP_NUM_THREADS": str(threads),
+                "MCB_TIMING": os.path.join(workdir, "timing.json")})
     if dump:
         env.update({"MC_DUMP": dumpdir, "MC_DUMP_SEQS": "1"})
     for k, v in (env_opts or {}).items():
@@ -77,17 +83,21 @@ def run_reference(reads: np.ndarray, workdir: str, mode: str = "sg", env_opts: d
     return {"timing": timing, "dump": dumpdir, "out": out, "log": p.stdout.decode()}
 
 
-def cached_reference(n_reads: int, L: int, G: int, seed: int, special: float = 0.0, mode: str = "sg", env_opts: dict | None = None):
-    """(reads, Dump) for a seeded synthetic set; the reference is run once per key."""
-    key = json.dumps([n_reads, L, G, seed, special, mode, sorted((env_opts or {}).items())])
+def cached_reference(n_reads: int, L: int, G: int, seed: int, special: float = 0.0, mode: str = "sg", env_opts: dict | None = None,
+                     dump: bool = True):
+    """(reads, Dump) for a seeded synthetic set; the reference is run once per key.  With dump=False only the
+    output directory is kept (for the large cases) and (reads, out_dir) is returned."""
+    key = json.dumps([n_reads, L, G, seed, special, mode, sorted((env_opts or {}).items())] + ([] if dump else ["nodump"]))
     h = hashlib.sha1(key.encode()).hexdigest()[:16]
     wd = os.path.join(CACHE, h)
     reads = synth.make_reads(n_reads, L, G, seed=seed, special=special)
     if not os.path.exists(os.path.join(wd, "ok")):
         shutil.rmtree(wd, ignore_errors=True)
-        run_reference(reads, wd, mode=mode, env_opts=env_opts)
+        run_reference(reads, wd, mode=mode, env_opts=env_opts, dump=dump)
         with open(os.path.join(wd, "ok"), "w") as f:
             f.write(key)
+    if not dump:
+        return reads, os.path.join(wd, "out")
     return reads, Dump(os.path.join(wd, "dump"))
 
 
