@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — reads/s of the sketch + index + overlap stage (BASELINE.json metric) on N B200s.
+
+One "step" = one pass of the hot path over one batch of synthetic reads: every call the reference's host code makes
+into the replaced functions during one compression run — kt_for_reads, kt_for_bucket, each mm_idx_generation, each
+realign_hash of the -e/-S/-E schedule — issued through the C-ABI of libminicom_b200.so.
+
+The host stages that sit BETWEEN those calls (contig merge, kthread_cb.c) are not part of the path; their outputs are
+needed as inputs, so the workload is prepared once, untimed, by running the drop-in executable (reference host objects +
+this library) with MCB_RECORD: it writes the host-side inputs of every index build / realign call, and each timed step
+replays exactly that call sequence.
+
+Two timed regions per run:
+  value : device time (CUDA events inside the library, on its stream) of the four entry points with the reads resident
+          in HBM; host<->device copies excluded.
+  e2e   : wall clock of the same calls through the host-buffer C-ABI (pinned host rows in, results copied back to host
+          memory every step).
+`--impl reference` times the reference's own multithreaded CPU implementation (oracle/_ref, built from the unmodified
+sources) on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# name -> (reads per GPU, read length, genome length, mode, reference options)
+WORKLOADS = {
+    "C1": (1_000_000, 100, 5_000_000, "sg", {}),
+    "C2": (10_000_000, 100, 50_000_000, "order", {}),
+    "tiny": (100_000, 100, 500_000, "order", {}),
+}
+# bounded sample of the workload for the CPU arm: same shape and coverage, fewer reads
+CPU_SAMPLE = {"C2": (1_000_000, 100, 5_000_000), "C1": (1_000_000, 100, 5_000_000), "tiny": (100_000, 100, 500_000)}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def unlimit_stack():
+    import resource
+    try:
+        resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
+    except (ValueError, OSError):
+        pass
+
+
+def run_binary(exe, fastq, workdir, env_extra, threads):
+    out, tmpd = os.path.join(workdir, "out"), os.path.join(workdir, "tmp") + "/"
+    for d in (out, tmpd):
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
+    timing = os.path.join(workdir, "timing.json")
+    env = dict(os.environ)
+    env.update({"MC_T": str(threads), "OMP_NUM_THREADS": str(threads), "MC_TMPDIR": tmpd, "MC_TIMING": timing, "MCB_TIMING": timing})
+    env.update({k: str(v) for k, v in env_extra.items()})
+    t0 = time.time()
+    p = subprocess.run([exe, fastq, out], env=env, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, preexec_fn=unlimit_stack)
+    if p.returncode != 0:
+        raise RuntimeError(f"{exe} failed ({p.returncode}): {p.stdout.decode()[-3000:]}")
+    with open(timing) as f:
+        t = json.load(f)
+    t["wall_total"] = time.time() - t0
+    shutil.rmtree(out, ignore_errors=True)
+    return t
+
+
+def front_end_seconds(t):
+    return t["kt_for_reads"] + t["kt_for_bucket"] + t["mm_idx_generation"] + t["realign_hash"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.stop_flag, self.gpu = [], False, gpu_index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(kernel, c):
+    """SURVEY.md 8(d) per-unit figures x the units of one step (DESIGN.md 'roofline accounting')."""
+    L4 = (c["L"] + 3) // 4
+    if kernel == "k:s2_probe":          # per launch: one threshold round
+        return sum(8 * (2 * r["nd"] - 1) * r["W"] + L4 * r["C"] + (r["R"] + 3) // 4 for r in c["rounds"]) / max(1, len(c["rounds"])), len(c["rounds"])
+    if kernel == "k:pack_classify_sketch":
+        return c["N"] * (L4 + 16), 1
+    if kernel in ("k:sort_scatter", "k:sort_hist"):
+        return None, None                # filled by caller: 32 B x elements per pass
+    if kernel == "k:consensus":
+        return 2 * L4 * c["N_grp"] / max(1, c["bucket_rounds"]), c["bucket_rounds"]
+    return None, None
+
+
+def bench_ours(args):
+    import torch
+    import torch.distributed as dist
+    from minicom_b200 import api, synth
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, L, G, mode, ref_env = WORKLOADS[args.workload]
+    if args.reads:
+        n, G = args.reads, max(1000, args.reads * 5)
+    threads = args.host_threads or min(os.cpu_count() or 1, 32) // max(1, world) or 1
+    exe = os.path.join(ROOT, "dropin", "_build", f"minicom_b200_L{L}_{mode}")
+    if not os.path.exists(exe):
+        raise SystemExit(f"{exe} missing: run __graft_entry__.build() where /root/reference exists (no CPU fallback)")
+    # ---- prepare (untimed): synthetic reads, one drop-in run that records the call sequence
+    t0 = time.time()
+    reads = synth.make_reads(n, L, G, seed=1 + rank)          # every rank owns an independent read set (weak scaling)
+    wd = tempfile.mkdtemp(prefix=f"mcb_bench_r{rank}_")
+    rec = os.path.join(wd, "rec")
+    os.makedirs(rec)
+    fq = os.path.join(wd, "in.fastq")
+    synth.write_fastq(fq, reads)
+    log(f"[rank {rank}] workload {args.workload}: {n} x {L} bp synthesized in {time.time() - t0:.1f}s; running the drop-in executable once to record the call sequence")
+    dt = run_binary(exe, fq, wd, dict(ref_env, MCB_RECORD=rec, MCB_DEVICE=local), threads)
+    os.remove(fq)
+    log(f"[rank {rank}] drop-in run: front end {front_end_seconds(dt):.3f}s wall inside the entry points (first call includes CUDA context creation); whole program {dt['wall_total']:.1f}s")
+    idx_calls, realign_calls = [], []
+    j = 0
+    while os.path.exists(os.path.join(rec, f"idx_{j}.off.u64")):
+        idx_calls.append((np.fromfile(os.path.join(rec, f"idx_{j}.xy.u64"), dtype=np.uint64), np.fromfile(os.path.join(rec, f"idx_{j}.off.u64"), dtype=np.uint64)))
+        j += 1
+    j = 0
+    while os.path.exists(os.path.join(rec, f"realign_{j}.meta.u64")):
+        meta = np.fromfile(os.path.join(rec, f"realign_{j}.meta.u64"), dtype=np.uint64)
+        realign_calls.append((np.fromfile(os.path.join(rec, f"realign_{j}.sg.u32"), dtype=np.uint32), np.fromfile(os.path.join(rec, f"realign_{j}.refs.u8"), dtype=np.uint8),
+                              np.fromfile(os.path.join(rec, f"realign_{j}.off.u64"), dtype=np.uint64), int(meta[0]), int(meta[1]), int(meta[2])))
+        j += 1
+    shutil.rmtree(wd, ignore_errors=True)
+    # pinned host rows (e2e arm) and device-resident rows (value arm)
+    rows_pinned = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
+    rows_pinned.numpy()[:] = reads
+    rows_dev = rows_pinned.to("cuda", non_blocking=False)
+    del reads
+    params = api.resolve_params(L, device=local, **{k: int(ref_env[e]) for k, e in (("k", "MC_K"), ("e", "MC_E"), ("w", "MC_W"), ("m", "MC_M")) if e in ref_env})
+    ctx = api.Context(params)
+    ctx.timers_enable(True)
+    counters = {}
+
+    def step(device_resident):
+        C = api.C
+        rr = api._ReadsResult()
+        if device_resident:
+            ctx._check(ctx.lib.mcb_for_reads_device(ctx._h, rows_dev.data_ptr(), n, C.byref(rr)))
+        else:
+            ctx._check(ctx.lib.mcb_for_reads(ctx._h, rows_pinned.data_ptr(), n, C.byref(rr)))
+        br = api._BucketResult()
+        ctx._check(ctx.lib.mcb_for_bucket(ctx._h, C.byref(br)))
+        nc = int(br.n_clusters)
+        ref_bytes = int(C.cast(br.cl_ref_off, C.POINTER(C.c_uint64))[nc]) if nc else 0
+        mem = int(C.cast(br.cl_a_off, C.POINTER(C.c_uint64))[nc]) if nc else 0
+        idx_d2h = 0
+        for xy, off in idx_calls:
+            h = C.c_void_p(0)
+            ctx._check(ctx.lib.mcb_idx_build(ctx._h, xy.ctypes.data, off.ctypes.data, C.byref(h)))
+            nk, npost = C.c_uint64(0), C.c_uint64(0)
+            ctx.lib.mcb_idx_stats(h, C.byref(nk), C.byref(npost))
+            idx_d2h += nk.value * 12 + npost.value * 8 + len(off) * 4
+            ctx.lib.mcb_idx_destroy(h)
+        rounds = []
+        for sg, refs, off, thr, ms, nd in realign_calls:
+            r = api._RealignResult()
+            ctx._check(ctx.lib.mcb_realign(ctx._h, sg.ctypes.data, len(sg), refs.ctypes.data, off.ctypes.data, len(off) - 1, thr, ms, nd, C.byref(r)))
+            rounds.append({"S": len(sg), "R": int(len(refs)), "W": int(r.n_windows), "C": int(r.n_candidates), "nd": int(r.numdict), "claims": int(r.n_claims),
+                           "probes": int(r.n_probes), "polyAT": int(r.n_fpA + r.n_fpT)})
+        counters.update({"N": n, "L": L, "N_sk": int(br.n_sketched_total), "N_grp": int(br.n_grouped), "bucket_rounds": int(br.rounds), "clusters": nc,
+                         "singles_stage1": int(br.n_sg), "T_cb": int(sum(len(x[0]) // 2 for x in idx_calls)), "rounds": rounds})
+        # bytes crossing PCIe in this step, counted from the arrays the library copies (inputs in, results out)
+        h2d = (0 if device_resident else n * L) + sum(x[0].nbytes + x[1].nbytes for x in idx_calls) + sum(c[0].nbytes + c[1].nbytes + 3 * c[2].nbytes for c in realign_calls)
+        nn = int(rr.n_nreads)
+        d2h = n + nn * (5 + params_ws * 8)                                                        # classes, N side table
+        d2h += nc * (4 + 16 + 1 + 16 * params.first_mininum) + mem * 8 + ref_bytes + int(br.n_sg) * 4   # seed contigs, singles, index tuples
+        d2h += idx_d2h + sum(r["claims"] * 16 + r["polyAT"] * 4 for r in rounds)
+        return h2d, d2h
+
+    params_ws = (((L + 31) // 32) + 1) & ~1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_ms(tm):
+        return sum(tm.get(k, (0.0, 0))[0] for k in ("for_reads", "for_bucket", "idx_build", "realign"))
+
+    for _ in range(args.warmup):
+        step(True)
+        step(False)
+    # ---- timed region 1: device-resident ("value")
+    ctx.timers_reset()
+    barrier()
+    with ClockSampler(local) as clk:
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(True)
+        barrier()
+        wall_dev_arm = time.perf_counter() - w0
+        tm = ctx.timers()
+        launches = ctx.kernel_launches()
+        # ---- timed region 2: host buffers in, host results out ("e2e")
+        ctx.timers_reset()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            h2d, d2h = step(False)
+        barrier()
+        wall_e2e = time.perf_counter() - w0
+        tm_e2e = ctx.timers()
+    ms_dev = dev_ms(tm) / args.steps
+    vals = torch.tensor([ms_dev, wall_e2e / args.steps * 1e3, wall_dev_arm / args.steps * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_dev_max, ms_e2e_max, ms_wall_dev_max = (float(x) for x in vals.cpu())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (live CUDA-event times of the value arm)
+    peak, peak_src = measured_peaks()
+    kern = {k: v for k, v in tm.items() if k.startswith("k:")}
+    dom = max(kern, key=lambda k: kern[k][0])
+    dom_ms, dom_cnt = kern[dom]
+    ab, per_step_launches = algorithmic_bytes(dom, counters)
+    if ab is None and dom in ("k:sort_scatter", "k:sort_hist"):
+        ab = 32.0 * (counters["N_sk"] + counters["T_cb"]) / max(1, dom_cnt / args.steps)
+    avg_launch_s = dom_ms / max(1, dom_cnt) / 1e3
+    achieved = (ab / avg_launch_s / 1e9) if ab else None
+    roof = {"bound": "hbm", "kernel": dom[2:], "achieved": round(achieved, 2) if achieved else None, "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 5) if achieved else None, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ab, "avg_launch_ms": dom_ms / max(1, dom_cnt), "share_of_device_time": round(dom_ms / max(1e-9, dev_ms(tm)), 4)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            roof["traffic"] = json.load(f).get(dom[2:])
+    cpu = cpu_baseline(args.workload, 1, quiet=True) if not args.no_cpu_baseline else None
+    value = n * world / (ms_dev_max / 1e3)
+    line = {
+        "metric": "reads/sec for sketch+index+overlap stage", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_dev_max, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n} x {L} bp reads per GPU, {G} bp random genome, 1% substitutions, mode {mode}, defaults k=31 m=6 e=4" + ("" if world == 1 else "; independent read set per GPU, no exchange"),
+                   "l2": "inputs larger than L2 (reads %.0f MB per step)" % (n * L / 1e6), "timing": "value = CUDA-event device time of the four entry points (reads resident in HBM); e2e = wall clock through the host-buffer C-ABI",
+                   "bases_per_s": round(value * L, 1), "wall_ms_per_step_device_arm": round(ms_wall_dev_max, 3),
+                   "counters": {k: v for k, v in counters.items() if k != "rounds"}, "realign_rounds": counters["rounds"],
+                   "device_ms_by_entry_point": {k: round(tm[k][0] / args.steps, 4) for k in ("for_reads", "for_bucket", "idx_build", "realign") if k in tm},
+                   "kernel_ms_per_step": {k[2:]: round(v[0] / args.steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])},
+                   "dropin_first_run_front_end_s": round(front_end_seconds(dt), 4), "host_threads": threads},
+        "e2e": {"value": round(n * world / (ms_e2e_max / 1e3), 1), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e_max, 3),
+                "copy_ms_per_step": {k: round(tm_e2e[k][0] / args.steps, 3) for k in ("h2d", "d2h") if k in tm_e2e}},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(workload, steps, quiet=False, warmup=0):
+    """The reference's own CPU implementation (oracle/_ref, unmodified sources) on a bounded sample, all host threads."""
+    from minicom_b200 import synth
+    n, L, G = CPU_SAMPLE[workload]
+    mode = WORKLOADS[workload][3]
+    exe = os.path.join(ROOT, "oracle", "_ref", f"minicom_ref_L{L}_{mode}")
+    if not os.path.exists(exe):
+        return {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {exe} not built"}
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    wd = tempfile.mkdtemp(prefix="mcb_cpu_")
+    reads = synth.make_reads(n, L, G, seed=1)
+    fq = os.path.join(wd, "in.fastq")
+    synth.write_fastq(fq, reads)
+    secs = []
+    for i in range(warmup + steps):
+        t = run_binary(exe, fq, wd, WORKLOADS[workload][4], threads)
+        if i >= warmup:
+            secs.append(front_end_seconds(t))
+        if not quiet:
+            log(f"[reference] step {i}: front end {front_end_seconds(t):.2f}s (reads {t['kt_for_reads']:.2f} bucket {t['kt_for_bucket']:.2f} idx {t['mm_idx_generation']:.2f} realign {t['realign_hash']:.2f}), host merge {t.get('host_combine', 0):.2f}s")
+    shutil.rmtree(wd, ignore_errors=True)
+    s = sum(secs) / len(secs)
+    return {"value": round(n / s, 1), "unit": "reads/s", "cores": threads, "kind": "reference",
+            "sample": f"{n} x {L} bp reads over a {G} bp genome (same shape and 20x coverage as the workload, -t {threads}), wall time inside kt_for_reads+kt_for_bucket+mm_idx_generation+realign_hash = {s:.2f}s",
+            "seconds": round(s, 3)}
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    cpu = cpu_baseline(args.workload, args.steps, warmup=min(args.warmup, 1))
+    n, L, G = CPU_SAMPLE[args.workload]
+    wn, wL, wG, mode, _ = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "reads/sec for sketch+index+overlap stage", "value": cpu["value"], "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": cpu["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wn} x {wL} bp reads per GPU, {wG} bp random genome, 1% substitutions, mode {mode}, defaults k=31 m=6 e=4",
+                       "note": "CPU arm timed on a bounded sample of the workload (see cpu_baseline.sample); the reference is a single-process CPU program, so its value does not grow with n_gpus"},
+            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="override reads per GPU (debug)")
+    ap.add_argument("--host-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,18 @@ static double g_wall[4];      // for_reads, for_bucket, idx_build, realign (host
 static int g_calls[4];
 static std::string g_realign_detail;
 
+// MCB_RECORD=<dir>: write the host-side inputs of every mm_idx_generation / realign_hash call as flat little-endian
+// files, so bench.py can replay the exact sequence of C-ABI calls of this run without the host stages in between.
+static const char *record_dir() { const char *s = getenv("MCB_RECORD"); return (s && *s) ? s : 0; }
+static void record(const char *name, int idx, const char *suffix, const void *data, size_t bytes)
+{
+	char path[4096];
+	snprintf(path, sizeof path, "%s/%s_%d.%s", record_dir(), name, idx, suffix);
+	FILE *f = fopen(path, "wb");
+	if (!f || (bytes && fwrite(data, 1, bytes, f) != bytes)) { fprintf(stderr, "minicom_b200: cannot write %s\n", path); exit(1); }
+	fclose(f);
+}
+
 static void die(const char *where, int rc)
 {
 	fprintf(stderr, "minicom_b200: %s failed (%d): %s\n", where, rc, mcb_last_error());
@@ -174,6 +186,14 @@ void mm_idx_generation(int n_threads_, mm_idx_t *mi)
 	std::vector<const mcb_tuple*> ptrs(nb);
 	std::vector<uint64_t> cnt(nb);
 	for (int i = 0; i < nb; ++i) { ptrs[i] = (const mcb_tuple*)mi->B[i].a.a; cnt[i] = mi->B[i].a.n; }
+	if (record_dir()) {
+		std::vector<uint64_t> off(nb + 1, 0);
+		for (int i = 0; i < nb; ++i) off[i + 1] = off[i] + cnt[i];
+		std::vector<mcb_tuple> flat(off[nb]);
+		for (int i = 0; i < nb; ++i) if (cnt[i]) memcpy(&flat[off[i]], ptrs[i], cnt[i] * sizeof(mcb_tuple));
+		record("idx", g_calls[2], "off.u64", off.data(), off.size() * 8);
+		record("idx", g_calls[2], "xy.u64", flat.data(), flat.size() * sizeof(mcb_tuple));
+	}
 	mcb_index *ix = 0;
 	int rc = mcb_idx_build_scattered(ctx, ptrs.data(), cnt.data(), &ix);
 	if (rc) die("mm_idx_generation", rc);
@@ -225,6 +245,13 @@ void realign_hash(int n_threads_, reads_t *r, int index, int max_threshold)
 			refs.append(p->ref);
 		}
 	off.push_back(refs.size());
+	if (record_dir()) {
+		uint64_t meta[3] = { (uint64_t)max_threshold, (uint64_t)maxsearch, (uint64_t)ininumdict };
+		record("realign", g_calls[3], "meta.u64", meta, sizeof meta);
+		record("realign", g_calls[3], "sg.u32", r->sg.a, r->sg.n * 4);
+		record("realign", g_calls[3], "off.u64", off.data(), off.size() * 8);
+		record("realign", g_calls[3], "refs.u8", refs.data(), refs.size());
+	}
 	mcb_realign_result res;
 	int rc = mcb_realign(ctx, r->sg.a, r->sg.n, refs.data(), off.data(), contigs.size(), max_threshold, maxsearch, ininumdict, &res);
 	if (rc) die("realign_hash", rc);

@@ -533,7 +533,13 @@ extern "C" int mcb_for_reads(mcb_ctx *ctx, const char *rows, uint64_t n, mcb_rea
 	if (!res || (n && !rows)) { mcb_set_error("mcb_for_reads: null argument"); return MCB_EINVAL; }
 	const size_t bytes = (size_t)n * ctx->L;
 	MCB_TRY(ctx->d_ascii.ensure(bytes + 16));
-	{
+	cudaPointerAttributes pa;
+	const bool pinned = cudaPointerGetAttributes(&pa, rows) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (pinned) {   // page-locked source: one DMA, no staging
+		McbSpan sp(ctx->tm, "h2d");
+		MCB_CUDA(cudaMemcpyAsync(ctx->d_ascii.p, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	} else {
 		McbSpan sp(ctx->tm, "h2d");
 		// pageable source: stage through pinned chunks so the copies are true async DMA
 		const size_t CH = 32u << 20;

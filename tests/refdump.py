@@ -83,13 +83,20 @@ def run_reference(reads: np.ndarray, workdir: str, mode: str = "sg", env_opts: d
     return {"timing": timing, "dump": dumpdir, "out": out, "log": p.stdout.decode()}
 
 
+def _cache_dir(n_reads, L, G, seed, special, mode, env_opts, dump):
+    key = json.dumps([n_reads, L, G, seed, special, mode, sorted((env_opts or {}).items())] + ([] if dump else ["nodump"]))
+    return key, os.path.join(CACHE, hashlib.sha1(key.encode()).hexdigest()[:16])
+
+
+def have_cached(n_reads, L, G, seed, special=0.0, mode="sg", env_opts=None, dump=True) -> bool:
+    return os.path.exists(os.path.join(_cache_dir(n_reads, L, G, seed, special, mode, env_opts, dump)[1], "ok"))
+
+
 def cached_reference(n_reads: int, L: int, G: int, seed: int, special: float = 0.0, mode: str = "sg", env_opts: dict | None = None,
                      dump: bool = True):
     """(reads, Dump) for a seeded synthetic set; the reference is run once per key.  With dump=False only the
     output directory is kept (for the large cases) and (reads, out_dir) is returned."""
-    key = json.dumps([n_reads, L, G, seed, special, mode, sorted((env_opts or {}).items())] + ([] if dump else ["nodump"]))
-    h = hashlib.sha1(key.encode()).hexdigest()[:16]
-    wd = os.path.join(CACHE, h)
+    key, wd = _cache_dir(n_reads, L, G, seed, special, mode, env_opts, dump)
     reads = synth.make_reads(n_reads, L, G, seed=seed, special=special)
     if not os.path.exists(os.path.join(wd, "ok")):
         shutil.rmtree(wd, ignore_errors=True)
