@@ -187,15 +187,23 @@ def bench_ours(args):
     ctx.timers_enable(True)
     counters = {}
 
+    wall = {}
+
     def step(device_resident):
         C = api.C
+        w = wall.setdefault("device" if device_resident else "host", {"for_reads": 0.0, "for_bucket": 0.0, "idx_build": 0.0, "realign": 0.0})
+        t = time.perf_counter()
         rr = api._ReadsResult()
         if device_resident:
             ctx._check(ctx.lib.mcb_for_reads_device(ctx._h, rows_dev.data_ptr(), n, C.byref(rr)))
         else:
             ctx._check(ctx.lib.mcb_for_reads(ctx._h, rows_pinned.data_ptr(), n, C.byref(rr)))
+        w["for_reads"] += time.perf_counter() - t
+        t = time.perf_counter()
         br = api._BucketResult()
         ctx._check(ctx.lib.mcb_for_bucket(ctx._h, C.byref(br)))
+        w["for_bucket"] += time.perf_counter() - t
+        t = time.perf_counter()
         nc = int(br.n_clusters)
         ref_bytes = int(C.cast(br.cl_ref_off, C.POINTER(C.c_uint64))[nc]) if nc else 0
         mem = int(C.cast(br.cl_a_off, C.POINTER(C.c_uint64))[nc]) if nc else 0
@@ -207,12 +215,15 @@ def bench_ours(args):
             ctx.lib.mcb_idx_stats(h, C.byref(nk), C.byref(npost))
             idx_d2h += nk.value * 12 + npost.value * 8 + len(off) * 4
             ctx.lib.mcb_idx_destroy(h)
+        w["idx_build"] += time.perf_counter() - t
+        t = time.perf_counter()
         rounds = []
         for sg, refs, off, thr, ms, nd in realign_calls:
             r = api._RealignResult()
             ctx._check(ctx.lib.mcb_realign(ctx._h, sg.ctypes.data, len(sg), refs.ctypes.data, off.ctypes.data, len(off) - 1, thr, ms, nd, C.byref(r)))
             rounds.append({"S": len(sg), "R": int(len(refs)), "W": int(r.n_windows), "C": int(r.n_candidates), "nd": int(r.numdict), "claims": int(r.n_claims),
                            "probes": int(r.n_probes), "polyAT": int(r.n_fpA + r.n_fpT)})
+        w["realign"] += time.perf_counter() - t
         counters.update({"N": n, "L": L, "N_sk": int(br.n_sketched_total), "N_grp": int(br.n_grouped), "bucket_rounds": int(br.rounds), "clusters": nc,
                          "singles_stage1": int(br.n_sg), "T_cb": int(sum(len(x[0]) // 2 for x in idx_calls)), "rounds": rounds})
         # bytes crossing PCIe in this step, counted from the arrays the library copies (inputs in, results out)
@@ -238,6 +249,7 @@ def bench_ours(args):
         step(True)
         step(False)
     # ---- timed region 1: device-resident ("value")
+    wall.clear()
     ctx.timers_reset()
     barrier()
     with ClockSampler(local) as clk:
@@ -294,6 +306,7 @@ def bench_ours(args):
                    "counters": {k: v for k, v in counters.items() if k != "rounds"}, "realign_rounds": counters["rounds"],
                    "device_ms_by_entry_point": {k: round(tm[k][0] / args.steps, 4) for k in ("for_reads", "for_bucket", "idx_build", "realign") if k in tm},
                    "kernel_ms_per_step": {k[2:]: round(v[0] / args.steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])},
+                   "host_wall_ms_per_step": {a: {k: round(v / args.steps * 1e3, 3) for k, v in d.items()} for a, d in wall.items()},
                    "dropin_first_run_front_end_s": round(front_end_seconds(dt), 4), "host_threads": threads},
         "e2e": {"value": round(n * world / (ms_e2e_max / 1e3), 1), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e_max, 3),
                 "copy_ms_per_step": {k: round(tm_e2e[k][0] / args.steps, 3) for k in ("h2d", "d2h") if k in tm_e2e}},

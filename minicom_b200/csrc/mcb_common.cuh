@@ -135,6 +135,7 @@ struct mcb_ctx {
 	DBuf d_scr[12];
 	DBuf d_sort_hist, d_scan_tmp[4];
 	DBuf d_x[4];                         // stage-2 extras
+	DBuf d_out[8];                       // kt_for_bucket outputs accumulated over the rounds
 	// host result buffers
 	HBuf h_cls, h_nrid, h_nrepl, h_noff, h_npos, h_nmask, h_counters, h_stage;
 	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref, h_sg, h_mi_cnt, h_mi;

@@ -47,79 +47,97 @@ __device__ void ix_insertion_sort(mcb_tuple *a, uint32_t n)
 	}
 }
 
+// sorts a[0..n) (n > IX_SMALL) exactly like the reference; `a` may point to shared or global memory
+__device__ void ix_flag_sort(mcb_tuple *a, uint32_t n, IxSeg *stk, uint32_t *cur, uint32_t *end, int lane)
+{
+	int top = 1;
+	if (lane == 0) { stk[0].b = 0; stk[0].e = n; stk[0].s = 56; }
+	__syncwarp();
+	while (top > 0) {
+		--top;
+		const uint32_t sb = stk[top].b, se = stk[top].e; const int s = stk[top].s;
+		__syncwarp();
+		// digit histogram -> region [start,end) per digit
+		for (int d = lane; d < 256; d += 32) cur[d] = 0;
+		__syncwarp();
+		for (uint32_t i = sb + lane; i < se; i += 32) atomicAdd(&cur[(a[i].x >> s) & 255], 1u);
+		__syncwarp();
+		{
+			uint32_t v[8], sum = 0;
+#pragma unroll
+			for (int q = 0; q < 8; ++q) { v[q] = cur[lane * 8 + q]; sum += v[q]; }
+			uint32_t inc = sum;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
+			uint32_t run = sb + inc - sum;
+			__syncwarp();
+#pragma unroll
+			for (int q = 0; q < 8; ++q) { cur[lane * 8 + q] = run; run += v[q]; end[lane * 8 + q] = run; }
+		}
+		__syncwarp();
+		// cycle-leader permutation, exactly in the reference's visiting order (ksort.h:131-145)
+		if (lane == 0) {
+			for (int k = 0; k < 256;) {
+				if (cur[k] != end[k]) {
+					mcb_tuple tmp = a[cur[k]];
+					int l = (int)((tmp.x >> s) & 255);
+					if (l != k) {
+						do {
+							mcb_tuple sw = tmp;
+							uint32_t p = cur[l]++;
+							tmp = a[p]; a[p] = sw;
+							l = (int)((tmp.x >> s) & 255);
+						} while (l != k);
+						a[cur[k]++] = tmp;
+					} else ++cur[k];
+				} else ++k;
+			}
+		}
+		__syncwarp();
+		if (s > 0) {
+			const int s2 = s > 8 ? s - 8 : 0;
+			// region d spans [end[d-1], end[d]): small ones are insertion-sorted by one lane each, big ones recurse
+			for (int d0 = 0; d0 < 256; d0 += 32) {
+				int d = d0 + lane;
+				uint32_t rb = d == 0 ? sb : end[d - 1], re = end[d];
+				uint32_t sz = re - rb;
+				bool big = sz > IX_SMALL;
+				if (!big && sz > 1) ix_insertion_sort(a + rb, sz);
+				unsigned bm = __ballot_sync(0xFFFFFFFFu, big);
+				if (big) { int slot = top + __popc(bm & ((1u << lane) - 1u)); stk[slot].b = rb; stk[slot].e = re; stk[slot].s = s2; }
+				top += __popc(bm);
+			}
+		}
+		__syncwarp();
+	}
+}
+
+#define IX_SMEM_CAP 1024       // tuples of one bucket staged in shared memory (16 KB per warp)
+#define IX_SMEM_STK 32
+
 __global__ void __launch_bounds__(IX_WARPS * 32)
 k_index_sort(mcb_tuple *__restrict__ t, const uint64_t *__restrict__ boff, int nb, IxSeg *__restrict__ stacks)
 {
-	__shared__ uint32_t s_cur[IX_WARPS][256], s_end[IX_WARPS][256];
+	extern __shared__ __align__(16) unsigned char ix_smem[];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	uint32_t *cur = s_cur[wib], *end = s_end[wib];
+	uint32_t *cur = (uint32_t*)ix_smem + wib * 512, *end = cur + 256;
+	IxSeg *sstk = (IxSeg*)(ix_smem + IX_WARPS * 2048) + wib * IX_SMEM_STK;
+	mcb_tuple *stage = (mcb_tuple*)(ix_smem + IX_WARPS * 2048 + IX_WARPS * IX_SMEM_STK * sizeof(IxSeg)) + (size_t)wib * IX_SMEM_CAP;
 	for (int bk = blockIdx.x * IX_WARPS + wib; bk < nb; bk += gridDim.x * IX_WARPS) {
 		const uint64_t B0 = boff[bk], B1 = boff[bk + 1];
 		const uint32_t n = (uint32_t)(B1 - B0);
 		mcb_tuple *a = t + B0;
 		if (n <= 1) continue;
 		if (n <= IX_SMALL) { ix_small_sort_warp(a, n, lane); continue; }
-		IxSeg *stk = stacks + (B0 / 65 + 8ull * bk);
-		int top = 0;
-		if (lane == 0) { stk[0].b = 0; stk[0].e = n; stk[0].s = 56; }
-		top = 1;
-		__syncwarp();
-		while (top > 0) {
-			--top;
-			const uint32_t sb = stk[top].b, se = stk[top].e; const int s = stk[top].s;
+		if (n <= IX_SMEM_CAP) {
+			// alive segments are disjoint and > 64 tuples each: at most n/65 <= 15 stack entries
+			for (uint32_t i = lane; i < n; i += 32) stage[i] = a[i];
 			__syncwarp();
-			// digit histogram -> region [start,end) per digit
-			for (int d = lane; d < 256; d += 32) cur[d] = 0;
+			ix_flag_sort(stage, n, sstk, cur, end, lane);
+			for (uint32_t i = lane; i < n; i += 32) a[i] = stage[i];
 			__syncwarp();
-			for (uint32_t i = sb + lane; i < se; i += 32) atomicAdd(&cur[(a[i].x >> s) & 255], 1u);
-			__syncwarp();
-			{
-				uint32_t v[8], sum = 0;
-#pragma unroll
-				for (int q = 0; q < 8; ++q) { v[q] = cur[lane * 8 + q]; sum += v[q]; }
-				uint32_t inc = sum;
-#pragma unroll
-				for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
-				uint32_t run = sb + inc - sum;
-				__syncwarp();
-#pragma unroll
-				for (int q = 0; q < 8; ++q) { cur[lane * 8 + q] = run; run += v[q]; end[lane * 8 + q] = run; }
-			}
-			__syncwarp();
-			// cycle-leader permutation, exactly in the reference's visiting order (ksort.h:131-145)
-			if (lane == 0) {
-				for (int k = 0; k < 256;) {
-					if (cur[k] != end[k]) {
-						mcb_tuple tmp = a[cur[k]];
-						int l = (int)((tmp.x >> s) & 255);
-						if (l != k) {
-							do {
-								mcb_tuple sw = tmp;
-								uint32_t p = cur[l]++;
-								tmp = a[p]; a[p] = sw;
-								l = (int)((tmp.x >> s) & 255);
-							} while (l != k);
-							a[cur[k]++] = tmp;
-						} else ++cur[k];
-					} else ++k;
-				}
-			}
-			__syncwarp();
-			if (s > 0) {
-				const int s2 = s > 8 ? s - 8 : 0;
-				// region d spans [end[d-1], end[d])
-				for (int d0 = 0; d0 < 256; d0 += 32) {
-					int d = d0 + lane;
-					uint32_t rb = d == 0 ? sb : end[d - 1], re = end[d];
-					uint32_t sz = re - rb;
-					bool big = sz > IX_SMALL;
-					if (!big && sz > 1) ix_insertion_sort(a + rb, sz);
-					unsigned bm = __ballot_sync(0xFFFFFFFFu, big);
-					if (big) { int slot = top + __popc(bm & ((1u << lane) - 1u)); stk[slot].b = rb; stk[slot].e = re; stk[slot].s = s2; }
-					top += __popc(bm);
-				}
-			}
-			__syncwarp();
+		} else {
+			ix_flag_sort(a, n, stacks + (B0 / 65 + 8ull * bk), cur, end, lane);
 		}
 	}
 }
@@ -211,7 +229,9 @@ static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mc
 	}
 	{
 		McbSpan sp(ctx->tm, "idx_build");
-		MCB_LAUNCH(ctx, "index_sort", k_index_sort, mcb_grid_for(nb, IX_WARPS), IX_WARPS * 32, 0, dt, ctx->d_scr[1].as<uint64_t>(), nb, ctx->d_scr[2].as<IxSeg>());
+		const size_t ix_smem = IX_WARPS * 2048 + IX_WARPS * IX_SMEM_STK * sizeof(IxSeg) + (size_t)IX_WARPS * IX_SMEM_CAP * sizeof(mcb_tuple);
+		MCB_CUDA(cudaFuncSetAttribute(k_index_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix_smem));
+		MCB_LAUNCH(ctx, "index_sort", k_index_sort, mcb_grid_for(nb, IX_WARPS), IX_WARPS * 32, ix_smem, dt, ctx->d_scr[1].as<uint64_t>(), nb, ctx->d_scr[2].as<IxSeg>());
 		MCB_LAUNCH(ctx, "ix_heads", k_ix_heads, mcb_grid_for(n, 256), 256, 0, dt, n, ctx->d_scr[3].as<uint32_t>());
 		MCB_TRY(mcb_exclusive_scan_u32(ctx, ctx->d_scr[3].as<uint32_t>(), n, (uint64_t*)&dc[CT_SCRATCH_IDX]));
 		MCB_LAUNCH(ctx, "ix_keys", k_ix_keys, mcb_grid_for(n, 256), 256, 0, dt, n, ctx->d_scr[3].as<uint32_t>(), &dc[CT_SCRATCH_IDX],

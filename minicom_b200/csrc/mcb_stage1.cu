@@ -672,8 +672,9 @@ extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)
 	DBuf &b_hs = ctx->d_scr[0], &b_gs = ctx->d_scr[1], &b_st = ctx->d_scr[2], &b_er = ctx->d_scr[3], &b_nr = ctx->d_scr[4];
 	DBuf &b_gc = ctx->d_scr[5], &b_gk = ctx->d_scr[6], &b_gsg = ctx->d_scr[7], &b_grk = ctx->d_scr[8], &b_grl = ctx->d_scr[9], &b_gro = ctx->d_scr[10], &b_rk = ctx->d_scr[11];
 	// accumulated outputs (device): cluster tables + sg
-	DBuf d_cl_n, d_cl_aoff, d_cl_a, d_cl_roff, d_cl_ref, d_sg, d_mi, d_micnt;
-	struct Rel { DBuf *b[8]; ~Rel() { for (auto x : b) if (x) x->release(); } } rel = {{&d_cl_n, &d_cl_aoff, &d_cl_a, &d_cl_roff, &d_cl_ref, &d_sg, &d_mi, &d_micnt}};
+	// (kept in the context: allocating them per call costs more than all the kernels of this entry point together)
+	DBuf &d_cl_n = ctx->d_out[0], &d_cl_aoff = ctx->d_out[1], &d_cl_a = ctx->d_out[2], &d_cl_roff = ctx->d_out[3], &d_cl_ref = ctx->d_out[4],
+	     &d_sg = ctx->d_out[5], &d_mi = ctx->d_out[6], &d_micnt = ctx->d_out[7];
 	uint64_t tot_cl = 0, tot_mem = 0, tot_ref = 0, tot_sg = 0, tot_sk = ctx->n_valid_round1;
 	const int NC = ((2 * L + 2 * max_rounds + 8 + 31) / 32) * 32;
 	const size_t cs_per_warp = (((size_t)NC * 16 + NC + CS_MB * 8 * 8 + CS_MB * 16) + 15) & ~(size_t)15;
