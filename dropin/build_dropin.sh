@@ -29,7 +29,8 @@ mkdir -p "$B"
 } > "$B/config.h"
 CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$ROOT/oracle/ref -I$REF -I$ROOT/include"
 KEPT="bseq misc preprocess kthread_cb kthread_dump minicommain"
-[ "$MODE" = pe ] && KEPT="$KEPT kthread_dump_pe"
+# minicompe links from an archive (src/Makefile:24-25,33-34): kthread_dump.o is never pulled in and clashes with kthread_dump_pe.o
+[ "$MODE" = pe ] && KEPT="${KEPT/kthread_dump /kthread_dump_pe }"
 pids=()
 for f in $KEPT; do g++ $CXXFLAGS -c "$REF/$f.c" -o "$B/$f.o" & pids+=($!); done
 g++ $CXXFLAGS -c "$HERE/mcb_dropin.cpp" -o "$B/mcb_dropin.o" & pids+=($!)

@@ -39,7 +39,9 @@ mkdir -p "$B"
 # -march=x86-64-v3 instead of the reference's -march=native so the binary also runs on the GPU box's host CPU
 CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$HERE -I$REF"
 OBJS="bseq misc preprocess sketch bbhashdict kthread_reads kthread_bucket kthread_idx kthread_cb kthread_dump kthread_hash_realign minicommain"
-[ "$MODE" = pe ] && OBJS="$OBJS kthread_dump_pe"
+# the reference links minicompe from an archive (src/Makefile:24-25,33-34): kthread_dump.o is never pulled in there and
+# defines the same cmp() as kthread_dump_pe.o
+[ "$MODE" = pe ] && OBJS="${OBJS/kthread_dump /kthread_dump_pe }"
 pids=()
 for f in $OBJS; do g++ $CXXFLAGS -c "$REF/$f.c" -o "$B/$f.o" & pids+=($!); done
 g++ $CXXFLAGS -c "$HERE/mcref_wrap.cpp" -o "$B/mcref_wrap.o" & pids+=($!)

@@ -162,10 +162,12 @@ class Dump:
             j += 1
         return j
 
+    def raw(self, name) -> bytes:
+        with open(os.path.join(self.path, name), "rb") as f:
+            return f.read()
+
     def seqs(self):
-        with open(os.path.join(self.path, "r_seqs.txt"), "rb") as f:
-            lines = f.read().split(b"\n")
-        return [l for l in lines if l]
+        return [l for l in self.raw("r_seqs.txt").split(b"\n") if l]
 
     def npos(self, n_reads):
         raw = self.arr("r_npos.u32")
@@ -175,3 +177,37 @@ class Dump:
             out.append(raw[i + 1:i + 1 + c])
             i += 1 + c
         return out
+
+
+class GoldenDump(Dump):
+    """Same accessors over a committed fixture tests/golden/<name>.npz (written by tests/golden/make_golden.py)."""
+
+    def __init__(self, npz):
+        self.npz = npz
+        self.path = None
+
+    def has(self, name):
+        return "dump/" + name in self.npz.files
+
+    def arr(self, name, dtype=None):
+        if dtype is None:
+            dtype = {"u64": np.uint64, "u32": np.uint32, "u8": np.uint8}[name.rsplit(".", 1)[1]]
+        return np.frombuffer(self.npz["dump/" + name].tobytes(), dtype=dtype)
+
+    def raw(self, name) -> bytes:
+        return self.npz["dump/" + name].tobytes()
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+
+def load_golden(name):
+    """(reads, meta dict, GoldenDump, {output file name: bytes})"""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = eval(z["meta"].tobytes().decode(), {"__builtins__": {}})
+    out = {k[4:]: z[k].tobytes() for k in z.files if k.startswith("out/")}
+    return z["reads"], meta, GoldenDump(z), out
