@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import refdump
-from minicom_b200 import api
+from minicom_b200 import api, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -149,10 +149,104 @@ def test_front_end_matches_reference(case):
         print("\n".join(log))
 
 
+@pytest.mark.parametrize("name", refdump.golden_names())
+def test_front_end_matches_golden_fixture(name):
+    """Same state-by-state comparison against the committed fixtures (tests/golden/*.npz: dumps of the unmodified
+    reference) — needs neither /root/reference nor a cache."""
+    reads, meta, dump, _ = refdump.load_golden(name)
+    env, log = meta["env"], []
+    try:
+        with api.Context(params_for(meta["L"], env)) as ctx:
+            check_reads(ctx, reads, dump, log)
+            br = check_bucket(ctx, dump, log)
+            check_index(ctx, dump, log)
+            check_realign(ctx, dump, len(br.sg), env, log)
+    finally:
+        print("\n".join(log))
+
+
+# shapes without a reference build: the oracle restatement (oracle/mc_oracle.c, itself pinned against the reference) is the checker
+ORACLE_CASES = [
+    # (name, n_reads, L, genome, seed, special, options)
+    ("L36_min_k", 6000, 36, 20000, 31, 0.01, {"k": 12}),
+    ("L64", 6000, 64, 30000, 32, 0.01, {}),
+    ("L125", 5000, 125, 30000, 33, 0.01, {}),
+    ("L200_w30", 4000, 200, 40000, 34, 0.01, {"w": 30, "m": 3}),
+    ("L256_max", 3000, 256, 40000, 35, 0.01, {"e": 8}),
+    ("n1", 1, 100, 1000, 36, 0.0, {}),
+    ("n127", 127, 100, 600, 37, 0.02, {}),
+    ("n129", 129, 100, 600, 38, 0.02, {}),
+    ("dup_heavy", 8000, 100, 4000, 39, 0.0, {}),          # 200x coverage: big groups, long contigs, buckets above 64 tuples
+    ("rounds_many", 8000, 100, 40000, 40, 0.0, {"k": 14, "e": 2}),
+]
+
+
+@pytest.mark.parametrize("case", ORACLE_CASES, ids=[c[0] for c in ORACLE_CASES])
+def test_front_end_matches_oracle(case):
+    import oracle_lib as O
+    name, n, L, G, seed, special, opt = case
+    reads = synth.make_reads(n, L, G, seed=seed, special=special)
+    S = O.Stage1(O.resolve_params(L, **opt), reads)
+    with api.Context(api.resolve_params(L, **opt)) as ctx:
+        rr = ctx.for_reads(reads)
+        assert np.array_equal(rr.cls, S.cls)
+        t = ctx.debug_read_tuples(n)
+        assert np.array_equal(t, S.tuples)
+        sk = np.nonzero(S.cls == 0)[0]
+        assert np.array_equal(ctx.debug_unpack_reads(n)[sk], S.rows[sk])
+        br = ctx.for_bucket()
+        assert br.rounds == S.rounds
+        assert np.array_equal(br.cl_n, S.cl_n) and np.array_equal(br.cl_a, S.cl_a)
+        assert np.array_equal(br.cl_ref_off, S.cl_ref_off) and np.array_equal(br.cl_ref, S.cl_ref)
+        assert np.array_equal(br.sg, S.sg)
+        m = ctx.params.first_mininum
+        flat = br.mi[np.arange(m)[None, :] < br.mi_cnt[:, None]]
+        assert np.array_equal(flat, S.mi)
+        assert br.n_sketched_total == S.n_sketched_total
+        # index over the seed-contig tuples (the first mm_idx_generation of the host merge)
+        off, xy = O.bucket_major(S.mi)
+        ix, ox = ctx.idx_build(xy, off), O.Index(xy, off)
+        keys, st, post = ox.flat()
+        assert ix.stats() == (ox.n_keys, ox.n_post)
+        for i, x in enumerate(keys):
+            assert np.array_equal(ix.get(int(x)), post[int(st[i]):int(st[i + 1])])
+        ix.close()
+        # the threshold schedule over the seed contigs (no host merge in between: contigs = seed contigs)
+        sg = S.sg.copy()
+        e = ctx.params.diff_threshold
+        for thr in (e, 2 * e, 3 * e, 28):
+            if len(sg) == 0 or len(S.cl_n) == 0:
+                break
+            want = S.realign(sg, S.cl_ref, S.cl_ref_off, thr, 2000)
+            got = ctx.realign(sg, S.cl_ref, S.cl_ref_off, thr, 2000)
+            assert np.array_equal(got.claim_y, want["claim_y"]), f"thr {thr}: claims / append order differ"
+            assert np.array_equal(got.claim_contig, want["claim_contig"]) and np.array_equal(got.claim_sg, want["claim_sg"])
+            assert np.array_equal(got.fpA_sg, want["fpA_sg"]) and np.array_equal(got.fpT_sg, want["fpT_sg"])
+            assert (got.n_windows, got.n_probes, got.numdict) == (want["n_windows"], want["n_probes"], want["numdict"])
+            sg = sg[want["flag"] == 0]
+    S.close()
+
+
+def test_empty_input():
+    with api.Context(api.resolve_params(100)) as ctx:
+        rr = ctx.for_reads(np.zeros((0, 100), dtype=np.uint8))
+        assert rr.n_sketched == 0 and len(rr.cls) == 0
+        br = ctx.for_bucket()
+        assert len(br.cl_n) == 0 and len(br.sg) == 0
+
+
+def test_bad_characters_are_rejected_loudly():
+    reads = synth.make_reads(1000, 100, 5000, seed=1)
+    reads[17, 5] = ord("x")
+    with api.Context(api.resolve_params(100)) as ctx:
+        with pytest.raises(api.McbError):
+            ctx.for_reads(reads)
+
+
 def test_host_buffer_variants_agree():
     """mcb_for_reads (contiguous rows), mcb_for_reads_ptrs (scattered strings) give identical tuples."""
     name, n, L, G, seed, special, env = CASES[0]
-    reads, _ = refdump.cached_reference(n, L, G, seed, special, "sg", env)
+    reads = synth.make_reads(n, L, G, seed=seed, special=special)
     with api.Context(params_for(L, env)) as ctx:
         ctx.for_reads(reads)
         t0 = ctx.debug_read_tuples(n)
