@@ -252,8 +252,16 @@ void realign_hash(int n_threads_, reads_t *r, int index, int max_threshold)
 		record("realign", g_calls[3], "off.u64", off.data(), off.size() * 8);
 		record("realign", g_calls[3], "refs.u8", refs.data(), refs.size());
 	}
+	// Between two realign_hash calls of one run only updateSingle() executes (preprocess.c:197-232): the consensus strings are
+	// the ones of the previous round, so only the first round ships them; later rounds reuse the device-side contig table.
+	static std::vector<const char*> sent_refs;
+	std::vector<const char*> cur_refs(contigs.size());
+	for (size_t i = 0; i < contigs.size(); ++i) cur_refs[i] = contigs[i]->ref;
+	const bool same = g_calls[3] > 0 && cur_refs == sent_refs && !getenv("MCB_RESEND_CONTIGS");
 	mcb_realign_result res;
-	int rc = mcb_realign(ctx, r->sg.a, r->sg.n, refs.data(), off.data(), contigs.size(), max_threshold, maxsearch, ininumdict, &res);
+	int rc = same ? mcb_realign(ctx, r->sg.a, r->sg.n, NULL, NULL, contigs.size(), max_threshold, maxsearch, ininumdict, &res)
+	              : mcb_realign(ctx, r->sg.a, r->sg.n, refs.data(), off.data(), contigs.size(), max_threshold, maxsearch, ininumdict, &res);
+	sent_refs.swap(cur_refs);
 	if (rc) die("realign_hash", rc);
 	for (uint64_t i = 0; i < res.n_fpA; ++i) { r->sg_flag[res.fpA_sg[i]] = true; kv_push(uint32_t, r->fpA_id, r->sg.a[res.fpA_sg[i]]); }
 	for (uint64_t i = 0; i < res.n_fpT; ++i) { r->sg_flag[res.fpT_sg[i]] = true; kv_push(uint32_t, r->fpT_id, r->sg.a[res.fpT_sg[i]]); }

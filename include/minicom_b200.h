@@ -169,7 +169,9 @@ typedef struct {
 	/* singles diverted to the near-poly-A / near-poly-T lists (bbhashdict.c:157-216), ascending sg index */
 	uint64_t n_fpA, n_fpT;
 	const uint32_t *fpA_sg, *fpT_sg;
-	/* work counters for the roofline formula */
+	/* work counters for the roofline formula: contig windows; dictionary probes the reference's window loop
+	 * would issue for them (kthread_hash_realign.c:355-504); (window, single) pairs with equal dictionary keys that were
+	 * verified; n_dict_keys is reserved (0) */
 	uint64_t n_windows, n_probes, n_candidates, n_dict_keys;
 	int32_t numdict;              /* numdict_s actually used */
 } mcb_realign_result;
@@ -177,7 +179,11 @@ typedef struct {
 /* sg: host, n_sg read ids (reads->sg after updateSingle); refs/ref_off: host, contig consensus strings
  * concatenated (ref_off[n_contigs+1]); threshold: the current step of the -e/-S/-E schedule;
  * maxsearch: the reference's global (500, or 2000 when sg.n<=5M, preprocess.c:169-172);
- * ininumdict: raw -s value (0 = not given), resolved as setglobalarrays_realign does (:150-171). */
+ * ininumdict: raw -s value (0 = not given), resolved as setglobalarrays_realign does (:150-171).
+ * The contigs do not change between the rounds of one -e/-S/-E schedule (preprocess.c:197-232: only updateSingle() runs
+ * between two realign_hash calls), and the library keeps the device-side k-mer table it built over them: passing
+ * refs == NULL and ref_off == NULL reuses the contigs of the previous call (n_contigs must be 0 or the same count).
+ * When refs is given, the table is rebuilt only if the strings differ from the cached ones. */
 int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off,
                 uint64_t n_contigs, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res);
 

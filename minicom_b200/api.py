@@ -303,11 +303,14 @@ class Context:
     # -- realign_hash
     def realign(self, sg: np.ndarray, refs: np.ndarray, ref_off: np.ndarray, threshold: int, maxsearch: int, ininumdict: int = 0) -> RealignResult:
         sg = np.ascontiguousarray(sg, dtype=np.uint32)
-        refs = np.ascontiguousarray(refs, dtype=np.uint8)
-        ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
         r = _RealignResult()
-        self._check(self.lib.mcb_realign(self._h, sg.ctypes.data, len(sg), refs.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1,
-                                         threshold, maxsearch, ininumdict, C.byref(r)))
+        if refs is None:      # reuse the contigs of the previous call (see include/minicom_b200.h)
+            self._check(self.lib.mcb_realign(self._h, sg.ctypes.data, len(sg), None, None, 0, threshold, maxsearch, ininumdict, C.byref(r)))
+        else:
+            refs = np.ascontiguousarray(refs, dtype=np.uint8)
+            ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
+            self._check(self.lib.mcb_realign(self._h, sg.ctypes.data, len(sg), refs.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1,
+                                             threshold, maxsearch, ininumdict, C.byref(r)))
         n = r.n_claims
         return RealignResult(_view(r.claim_contig, n, np.uint32), _view(r.claim_sg, n, np.uint32), _view(r.claim_y, n, np.uint64),
                              _view(r.fpA_sg, r.n_fpA, np.uint32), _view(r.fpT_sg, r.n_fpT, np.uint32),

@@ -106,10 +106,27 @@ struct McbSpan {
 // slots of the device scalar block ctx->d_counters (u64[64])
 enum { CT_SKETCHED = 0, CT_BADCHAR = 1, CT_DEGENERATE = 2, CT_NREADS = 3, CT_REFCURSOR = 4, CT_G = 5, CT_TOT_CL = 6, CT_TOT_MEM = 7,
        CT_TOT_REF = 8, CT_TOT_SG = 9, CT_TOT_RESK = 10, CT_ERR = 11, CT_SCRATCH_IDX = 12,
-       CT_S2_U = 16, CT_S2_PROBES = 17, CT_S2_CAND = 18, CT_S2_NEEDEXACT = 19, CT_S2_CLAIMS = 20, CT_S2_FPA = 21, CT_S2_FPT = 22, CT_S2_ERR = 23 };
+       CT_S2_U = 16, CT_S2_PROBES = 17, CT_S2_CAND = 18, CT_S2_NEEDEXACT = 19, CT_S2_CLAIMS = 20, CT_S2_FPA = 21, CT_S2_FPT = 22, CT_S2_ERR = 23,
+       CT_S2_MAXBIN = 24, CT_S2_DIFF = 25 };
 
 // ---------------------------------------------------------------- context
 struct mcb_index;   // defined in mcb_index.cu
+
+// Stage 2: the contigs of the last mcb_realign call and the k-mer index built over them (mcb_stage2.cu).  The contigs do
+// not change between the rounds of the -e/-S/-E schedule (preprocess.c:197-232), so the index is built once per run.
+struct McbContigIndex {
+	bool valid = false;
+	uint64_t n_contigs = 0, ref_bytes = 0, total_words = 0, n_windows = 0, n_entries = 0;
+	int L = 0, lt = 0, pbits = 0;
+	DBuf refs;      // ASCII consensus strings, concatenated (kept to recognise an identical contig set)
+	DBuf roff;      // u64[n_contigs+1] offsets into refs
+	DBuf cwo;       // u64[n_contigs+1] word offsets of the packed contigs
+	DBuf wo;        // u64[n_contigs+1] window offsets (prefix sums of len-L+1)
+	DBuf cw;        // packed contigs, 2 bits per base, each contig padded to whole words + 1
+	DBuf pblk;      // u32[ref_bytes/512+1] contig holding base 512*i
+	DBuf ptab;      // u32[2^pbits+1] bucket ends of the k-mer table
+	DBuf ents;      // u64[n_entries] key<<30 | global base position, bucketed by a hash of the key
+};
 
 struct mcb_ctx {
 	mcb_params prm;
@@ -136,6 +153,7 @@ struct mcb_ctx {
 	DBuf d_sort_hist, d_scan_tmp[4];
 	DBuf d_x[4];                         // stage-2 extras
 	DBuf d_out[8];                       // kt_for_bucket outputs accumulated over the rounds
+	McbContigIndex cix;                  // stage-2 contig k-mer index (cached across threshold rounds)
 	// host result buffers
 	HBuf h_cls, h_nrid, h_nrepl, h_noff, h_npos, h_nmask, h_counters, h_stage;
 	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref, h_sg, h_mi_cnt, h_mi;

@@ -1,15 +1,27 @@
 // mcb_stage2.cu — realign_hash (kthread_hash_realign.c:569-594) on the device.
 //
-//   K5 k_s2_singles   singleRead2bitset (bbhashdict.c:127-227): gather the 2-bit reads of the singletons, their reverse
-//                     complements, the near-poly-A / near-poly-T diversion, and the per-dictionary substring keys
-//   K6 sort + table   constructdictionary_realign (kthread_hash_realign.c:3-140): one stable radix sort of (dict, key) ->
-//                     CSR bins with ascending sg index; an open-addressing table replaces the BooPHF minimal perfect hash
-//                     (its value only selects a bin; the `ull == ull1` re-check at :385 makes the lookup an exact match)
-//   K7 k_s2_probe     realign_hash_search (:316-508): one thread per contig window; forward probes l=0..nd-1, reverse
-//                     probes for dictionaries with dict_start>0; XOR/popcount verification, encode_byte gate (:283-314)
-//   K8 claims         the single-threaded reference lets the FIRST probe step that matches a read claim it.  Here every
-//                     matching step proposes priority P=(window, phase, l); atomicMin keeps the first; claims are then
-//                     sorted by (P, sg index descending) = the reference's append order.
+// The reference builds, per threshold round, `numdict` dictionaries over substrings of the leftover reads ("singles",
+// constructdictionary_realign :3-140) and slides every contig window over them (realign_hash_search :316-508):
+// W windows x (2*numdict-1) random dictionary probes, of which ~98 % miss.  The join is symmetric, and the contigs do not
+// change between rounds (preprocess.c:197-232), so this implementation turns it around:
+//
+//   once per contig set   K5a k_s2_pack_refs    2-bit packed contigs
+//                         K5b k_s2_kmer_hist/fill  every lt-mer of every contig (lt = 17, or 11 for L <= 80) -> a bucketed
+//                                               table (counting sort on a hash of the lt-mer): entry = lt-mer<<30 | position
+//   every round           K6  k_s2_singles      singleRead2bitset (bbhashdict.c:127-227): 2-bit singles, near-poly-A/T
+//                                               diversion, and a count-min sketch of the dictionary bins (bin sizes matter:
+//                                               the reference scans only the last `maxsearch` entries of a bin, :388)
+//                         K7  k_s2_join         one thread per (single, dictionary): its substring key, and the reverse
+//                                               complement of the key, are looked up in the contig table; each hit is a
+//                                               (window, single) candidate = exactly the pairs the reference's probes
+//                                               meet; XOR/popcount verification and the encode_byte gate (:283-314) follow
+//                         K8  claims            the single-threaded reference lets the FIRST probe step that matches a read
+//                                               claim it.  Every verified pair proposes priority P=(window, phase, l);
+//                                               atomicMin keeps the first; claims are then sorted by (P, sg index
+//                                               descending) = the reference's append order.
+//
+// Probes per round drop from 9 per window (4.7e8 at 10 M reads) to 2 per (single, dictionary) (3e7 in the first round,
+// 3e6 later), and only true key matches touch the contigs.
 //
 // Distance is the popcount of the XOR of 2-bit codes (bbhashdict.c:247-254), not a base count: A<->T and C<->G cost 2.
 // The reference's code A=00,G=01,C=10,T=11 (kthread_hash_realign.c:251-258) and ours (A0 C1 G2 T3) differ only by
@@ -18,6 +30,9 @@
 #include <algorithm>
 
 #define S2_MAXD 16
+#define S2_POS_BITS 30
+#define S2_POS_MASK ((1ull << S2_POS_BITS) - 1)
+#define S2_BLK_SHIFT 9
 struct S2Geom {
 	int L, Wd, WS, nd, lt;
 	int dstart[S2_MAXD];
@@ -41,6 +56,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t k)
 	k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
 	return k;
 }
+__device__ __forceinline__ uint32_t kmer_bucket(uint64_t key, int pbits) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - pbits)); }
 
 // encode_byte (kthread_hash_realign.c:283-314) on a mismatch pattern given as XOR words, positions ascending.
 // Reproduces the missing `eq_char_num = 0` of the literal branch (:301-305).
@@ -59,104 +75,7 @@ __device__ bool enc_ok(const uint64_t *x, int L, int limit)
 	return len <= limit;
 }
 
-// ---------------------------------------------------------------- K5
-__global__ void k_s2_singles(const uint32_t *__restrict__ sg, uint64_t S, const uint64_t *__restrict__ packed, S2Geom gm,
-                             const uint32_t *__restrict__ nread_rid, const uint64_t *__restrict__ nread_mask, uint64_t n_nreads, uint64_t n_reads,
-                             uint64_t *__restrict__ rd, uint64_t *__restrict__ rdrc, uint8_t *__restrict__ flagged, ulonglong2 *__restrict__ kv,
-                             unsigned long long *__restrict__ counters)
-{
-	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= S) return;
-	const uint32_t rid = sg[s];
-	if (rid >= n_reads) { atomicAdd(&counters[CT_S2_ERR], 1ull); return; }
-	const int L = gm.L, Wd = gm.Wd, WS = gm.WS;
-	uint64_t w[9], r[9];
-#pragma unroll
-	for (int i = 0; i < 9; ++i) { w[i] = i < Wd ? packed[(uint64_t)rid * WS + i] : 0ull; }
-	// reverse complement: reverse fields over Wd words, then drop the pad fields that moved to the bottom
-#pragma unroll
-	for (int i = 0; i < 9; ++i) r[i] = 0;
-	const int pad = Wd * 32 - L;
-	for (int i = 0; i < Wd; ++i) {
-		uint64_t a = mcb_rc_word(w[Wd - 1 - i]);
-		uint64_t b = i + 1 < Wd ? mcb_rc_word(w[Wd - 2 - i]) : 0ull;
-		r[i] = pad ? (a >> (2 * pad)) | (b << (64 - 2 * pad)) : a;
-	}
-	if (L & 31) r[Wd - 1] &= (1ull << (2 * (L & 31))) - 1;
-	int pcA = 0, pcT = 0;
-	for (int i = 0; i < Wd; ++i) {
-		uint64_t valid = (i == Wd - 1 && (L & 31)) ? (1ull << (2 * (L & 31))) - 1 : ~0ull;
-		pcA += __popcll(w[i]); pcT += __popcll(~w[i] & valid);
-	}
-	for (int i = 0; i < WS; ++i) { rd[s * WS + i] = w[i]; rdrc[s * WS + i] = r[i]; }
-	// near-poly-A / near-poly-T (bbhashdict.c:157-216); the run-length code is measured on the ORIGINAL characters (N restored)
-	uint8_t fl = 0;
-	const bool nearA = pcA <= gm.thr, nearT = !nearA && pcT <= gm.thr;
-	if (nearA || nearT) {
-		const uint64_t *nm = nullptr;
-		{   // binary search the side table of reads that contained N
-			uint64_t lo = 0, hi = n_nreads;
-			while (lo < hi) { uint64_t mid = (lo + hi) >> 1; uint32_t v = nread_rid[mid]; if (v < rid) lo = mid + 1; else hi = mid; }
-			if (lo < n_nreads && nread_rid[lo] == rid) nm = nread_mask + lo * WS;
-		}
-		const unsigned want = nearA ? 0u : 3u;
-		int len = 0, eq = 0;
-		for (int i = 0; i < L; ++i) {
-			bool isn = nm ? ((nm[i >> 5] >> (2 * (i & 31))) & 1) != 0 : false;
-			bool same = !isn && (((w[i >> 5] >> (2 * (i & 31))) & 3) == want);
-			if (!same) { if (eq > 0) { len += ndigits(eq); eq = 0; } ++len; } else ++eq;
-		}
-		if (len == 0) len = 1;
-		if (len <= gm.enc_limit) fl = nearA ? 1 : 2;
-	}
-	flagged[s] = fl;
-	for (int l = 0; l < gm.nd; ++l) {
-		ulonglong2 e; e.x = ((unsigned long long)l << 34) | extract_bases(w, gm.dstart[l], gm.lt); e.y = s;
-		kv[(uint64_t)l * S + s] = e;
-	}
-}
-
-__global__ void k_s2_heads(const ulonglong2 *__restrict__ e, uint64_t n, uint32_t *__restrict__ flag)
-{
-	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) flag[i] = (i == 0 || e[i].x != e[i - 1].x) ? 1u : 0u;
-}
-// distinct keys -> bin start; also flatten the sorted values into the bin array
-__global__ void k_s2_bins(const ulonglong2 *__restrict__ e, uint64_t n, const uint32_t *__restrict__ hscan, const unsigned long long *__restrict__ U,
-                          uint64_t *__restrict__ ukey, uint32_t *__restrict__ bstart, uint32_t *__restrict__ bin_sg)
-{
-	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	ulonglong2 v = e[i];
-	bin_sg[i] = (uint32_t)v.y;
-	if (i == 0 || v.x != e[i - 1].x) { uint32_t u = hscan[i]; ukey[u] = v.x; bstart[u] = (uint32_t)i; }
-	if (i == n - 1) bstart[*U] = (uint32_t)n;
-}
-#define S2_EMPTY 0xFFFFFFFFFFFFFFFFull
-__global__ void k_s2_table_insert(const uint64_t *__restrict__ ukey, uint64_t U, unsigned long long *__restrict__ tkey, uint32_t *__restrict__ tval, uint64_t hmask)
-{
-	uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (u >= U) return;
-	const unsigned long long key = ukey[u];
-	uint64_t h = mix64(key) & hmask;
-	for (;;) {
-		unsigned long long old = atomicCAS(&tkey[h], S2_EMPTY, key);
-		if (old == S2_EMPTY || old == key) { tval[h] = (uint32_t)u; return; }
-		h = (h + 1) & hmask;
-	}
-}
-__device__ __forceinline__ bool table_find(const unsigned long long *__restrict__ tkey, const uint32_t *__restrict__ tval, uint64_t hmask, unsigned long long key, uint32_t *u)
-{
-	uint64_t h = mix64(key) & hmask;
-	for (;;) {
-		unsigned long long k = tkey[h];
-		if (k == key) { *u = tval[h]; return true; }
-		if (k == S2_EMPTY) return false;
-		h = (h + 1) & hmask;
-	}
-}
-
-// ---------------------------------------------------------------- contig packing
+// ---------------------------------------------------------------- K5a contig packing
 // contig c occupies words [cw_off[c], cw_off[c+1]) (ceil(len/32)+1 words, zero padded)
 __global__ void k_s2_pack_refs(const char *__restrict__ refs, const uint64_t *__restrict__ ref_off, const uint64_t *__restrict__ cw_off, uint64_t n_contigs,
                                uint64_t total_words, uint64_t *__restrict__ cw, unsigned long long *__restrict__ counters)
@@ -176,15 +95,147 @@ __global__ void k_s2_pack_refs(const char *__restrict__ refs, const uint64_t *__
 	cw[q] = v;
 }
 
+// contig that holds base 512*i of the concatenated consensus strings
+__global__ void k_s2_pos_blocks(const uint64_t *__restrict__ ref_off, uint64_t n_contigs, uint64_t n_blocks, uint32_t *__restrict__ pblk)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_blocks) return;
+	const uint64_t P = i << S2_BLK_SHIFT;
+	uint64_t lo = 0, hi = n_contigs;          // last c with ref_off[c] <= P
+	while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (ref_off[mid] <= P) lo = mid; else hi = mid; }
+	pblk[i] = (uint32_t)lo;
+}
+
+// were the contigs of this call the ones the cached index was built from?
+__global__ void k_s2_same(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, uint64_t nwords, unsigned long long *__restrict__ counters)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	bool diff = i < nwords && a[i] != b[i];
+	if (__any_sync(0xFFFFFFFFu, diff) && (threadIdx.x & 31) == 0) atomicAdd(&counters[CT_S2_DIFF], 1ull);
+}
+
+// ---------------------------------------------------------------- K5b contig lt-mer table
+// One thread per packed word: the 32 lt-mers that START in it.  FILL=false counts bucket sizes, FILL=true places entries
+// (tab holds bucket starts on entry and bucket ends on exit).
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_s2_kmers(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_off, const uint64_t *__restrict__ ref_off, uint64_t n_contigs, uint64_t total_words,
+           int L, int lt, int pbits, uint32_t *__restrict__ tab, unsigned long long *__restrict__ ents)
+{
+	uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= total_words) return;
+	uint64_t lo = 0, hi = n_contigs;
+	while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (cw_off[mid] <= q) lo = mid; else hi = mid; }
+	const uint64_t c = lo, wq = q - cw_off[c];
+	const uint64_t base = ref_off[c], len = ref_off[c + 1] - base;
+	if (len < (uint64_t)L || wq * 32 + lt > len) return;            // contigs shorter than a read have no windows
+	const uint64_t w0 = cw[q], w1 = cw[q + 1];
+	const uint64_t kmask = (1ull << (2 * lt)) - 1;
+	const int nstart = (int)min((uint64_t)32, len - lt + 1 - wq * 32);
+	for (int j = 0; j < nstart; ++j) {
+		uint64_t key = ((w0 >> (2 * j)) | (j ? w1 << (64 - 2 * j) : 0ull)) & kmask;
+		uint32_t b = kmer_bucket(key, pbits);
+		if (!FILL) atomicAdd(&tab[b], 1u);
+		else {
+			uint32_t slot = atomicAdd(&tab[b], 1u);
+			ents[slot] = (key << S2_POS_BITS) | (base + wq * 32 + j);
+		}
+	}
+}
+
+// ---------------------------------------------------------------- K6
+__global__ void k_s2_singles(const uint32_t *__restrict__ sg, uint64_t S, const uint64_t *__restrict__ packed, S2Geom gm,
+                             const uint32_t *__restrict__ nread_rid, const uint64_t *__restrict__ nread_mask, uint64_t n_nreads, uint64_t n_reads,
+                             uint64_t *__restrict__ rd, uint8_t *__restrict__ flagged, uint32_t *__restrict__ cm, uint64_t cm_mask,
+                             unsigned long long *__restrict__ counters)
+{
+	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned maxbin = 0;
+	if (s < S) {
+		const uint32_t rid = sg[s];
+		if (rid >= n_reads) atomicAdd(&counters[CT_S2_ERR], 1ull);
+		else {
+			const int L = gm.L, Wd = gm.Wd, WS = gm.WS;
+			uint64_t w[9];
+#pragma unroll
+			for (int i = 0; i < 9; ++i) w[i] = i < Wd ? packed[(uint64_t)rid * WS + i] : 0ull;
+			int pcA = 0, pcT = 0;
+			for (int i = 0; i < Wd; ++i) {
+				uint64_t valid = (i == Wd - 1 && (L & 31)) ? (1ull << (2 * (L & 31))) - 1 : ~0ull;
+				pcA += __popcll(w[i]); pcT += __popcll(~w[i] & valid);
+			}
+			for (int i = 0; i < WS; ++i) rd[s * WS + i] = w[i];
+			// near-poly-A / near-poly-T (bbhashdict.c:157-216); the run-length code is measured on the ORIGINAL characters (N restored)
+			uint8_t fl = 0;
+			const bool nearA = pcA <= gm.thr, nearT = !nearA && pcT <= gm.thr;
+			if (nearA || nearT) {
+				const uint64_t *nm = nullptr;
+				{   // binary search the side table of reads that contained N
+					uint64_t lo = 0, hi = n_nreads;
+					while (lo < hi) { uint64_t mid = (lo + hi) >> 1; uint32_t v = nread_rid[mid]; if (v < rid) lo = mid + 1; else hi = mid; }
+					if (lo < n_nreads && nread_rid[lo] == rid) nm = nread_mask + lo * WS;
+				}
+				const unsigned want = nearA ? 0u : 3u;
+				int len = 0, eq = 0;
+				for (int i = 0; i < L; ++i) {
+					bool isn = nm ? ((nm[i >> 5] >> (2 * (i & 31))) & 1) != 0 : false;
+					bool same = !isn && (((w[i >> 5] >> (2 * (i & 31))) & 3) == want);
+					if (!same) { if (eq > 0) { len += ndigits(eq); eq = 0; } ++len; } else ++eq;
+				}
+				if (len == 0) len = 1;
+				if (len <= gm.enc_limit) fl = nearA ? 1 : 2;
+			}
+			flagged[s] = fl;
+			// count-min sketch of the dictionary bins: an upper bound of every bin size (a bin = singles sharing a key in dictionary l)
+			for (int l = 0; l < gm.nd; ++l) {
+				unsigned long long key = ((unsigned long long)l << 34) | extract_bases(w, gm.dstart[l], gm.lt);
+				unsigned v = atomicAdd(&cm[mix64(key) & cm_mask], 1u) + 1u;
+				maxbin = max(maxbin, v);
+			}
+		}
+	}
+	maxbin = __reduce_max_sync(0xFFFFFFFFu, maxbin);
+	if ((threadIdx.x & 31) == 0 && maxbin) atomicMax(&counters[CT_S2_MAXBIN], (unsigned long long)maxbin);
+}
+
+// exact bin sizes (only when the sketch reports a possible bin above maxsearch): open addressing (l,key) -> count
+#define S2_EMPTY 0xFFFFFFFFFFFFFFFFull
+__global__ void k_s2_bins_exact(const uint64_t *__restrict__ rd, uint64_t S, S2Geom gm, unsigned long long *__restrict__ tkey, uint32_t *__restrict__ tcnt, uint64_t hmask)
+{
+	uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= S * (uint64_t)gm.nd) return;
+	const int l = (int)(idx / S); const uint64_t s = idx - (uint64_t)l * S;
+	uint64_t w[9];
+#pragma unroll
+	for (int i = 0; i < 9; ++i) w[i] = i < gm.Wd ? rd[s * gm.WS + i] : 0ull;
+	const unsigned long long key = ((unsigned long long)l << 34) | extract_bases(w, gm.dstart[l], gm.lt);
+	uint64_t h = mix64(key) & hmask;
+	for (;;) {
+		unsigned long long old = atomicCAS(&tkey[h], S2_EMPTY, key);
+		if (old == S2_EMPTY || old == key) { atomicAdd(&tcnt[h], 1u); return; }
+		h = (h + 1) & hmask;
+	}
+}
+__device__ __forceinline__ uint32_t bins_exact_count(const unsigned long long *__restrict__ tkey, const uint32_t *__restrict__ tcnt, uint64_t hmask, unsigned long long key)
+{
+	uint64_t h = mix64(key) & hmask;
+	for (;;) {
+		unsigned long long k = tkey[h];
+		if (k == key) return tcnt[h];
+		if (k == S2_EMPTY) return 0;
+		h = (h + 1) & hmask;
+	}
+}
+
 // ---------------------------------------------------------------- K7
-struct S2Probe {
-	const uint64_t *cw, *cw_off, *woff;   // packed contigs, word offsets, window offsets (prefix sums)
-	uint64_t n_contigs, n_windows;
-	const unsigned long long *tkey; const uint32_t *tval; uint64_t hmask;
-	const uint32_t *bstart, *bin_sg;
-	const uint64_t *rd, *rdrc; const uint8_t *flagged;
+struct S2Join {
+	uint64_t S;
+	const uint64_t *rd; const uint8_t *flagged;
+	const uint32_t *ptab; const unsigned long long *ents; int pbits;
+	const uint32_t *pblk; const uint64_t *ref_off, *cw, *cw_off, *woff;
 	unsigned long long *claim;            // [S] min priority
 	unsigned long long *counters;
+	const unsigned long long *xkey; const uint32_t *xcnt; uint64_t xmask;   // exact bin sizes (null: trust the sketch)
 };
 
 __device__ __forceinline__ uint64_t rev_fields(uint64_t v, int nbases)
@@ -194,62 +245,84 @@ __device__ __forceinline__ uint64_t rev_fields(uint64_t v, int nbases)
 	return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
 }
 
-__global__ void __launch_bounds__(128) k_s2_probe(S2Probe p, S2Geom gm)
+__global__ void __launch_bounds__(128) k_s2_join(S2Join p, S2Geom gm)
 {
-	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned long long n_probe = 0, n_cand = 0;
-	if (g < p.n_windows) {
-	uint64_t lo = 0, hi = p.n_contigs;        // last c with woff[c] <= g (contigs without windows have equal offsets: take the last)
-	while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (p.woff[mid] <= g) lo = mid; else hi = mid; }
-	const uint64_t c = lo;
-	const uint64_t jj = g - p.woff[c];
-	const int L = gm.L, Wd = gm.Wd, WS = gm.WS;
-	// window bits
-	uint64_t W[9];
-	{
-		const uint64_t *src = p.cw + p.cw_off[c] + (jj >> 5);
-		const int sh = 2 * (int)(jj & 31);
+	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long n_cand = 0;
+	if (idx < p.S * (uint64_t)gm.nd) {
+		const int l = (int)(idx / p.S); const uint64_t s = idx - (uint64_t)l * p.S;
+		if (!p.flagged[s]) {                  // sg_flag already set by the poly-A/T diversion: can never be claimed
+			const int L = gm.L, Wd = gm.Wd, WS = gm.WS, lt = gm.lt, ds = gm.dstart[l];
+			uint64_t R[9], RC[9];
 #pragma unroll
-		for (int i = 0; i < 9; ++i) {
-			if (i < Wd) { uint64_t a = src[i]; W[i] = sh ? (a >> sh) | (src[i + 1] << (64 - sh)) : a; } else W[i] = 0;
-		}
-		if (L & 31) W[Wd - 1] &= (1ull << (2 * (L & 31))) - 1;
-	}
-	for (int phase = 0; phase < 2; ++phase) {
-		for (int l = 0; l < gm.nd; ++l) {
-			unsigned long long key;
-			if (phase == 0) key = extract_bases(W, gm.dstart[l], gm.lt);
-			else {
-				if (gm.dstart[l] <= 0) continue;                                  // kthread_hash_realign.c:440 (j = 0)
-				// key of the reverse-complemented window: complement and reverse the bases [L-dstart-lt, L-dstart)
-				uint64_t v = extract_bases(W, L - gm.dstart[l] - gm.lt, gm.lt);
-				key = rev_fields(~v & ((1ull << (2 * gm.lt)) - 1), gm.lt);
-			}
-			key |= (unsigned long long)l << 34;
-			++n_probe;
-			uint32_t u;
-			if (!table_find(p.tkey, p.tval, p.hmask, key, &u)) continue;
-			const uint32_t bs = p.bstart[u], be = p.bstart[u + 1];
-			const unsigned long long prio = (g << 5) | ((unsigned long long)phase << 4) | (unsigned long long)l;
-			for (uint32_t i = be; i-- > bs;) {
-				const uint32_t s = p.bin_sg[i];
-				const uint64_t *r = (phase ? p.rdrc : p.rd) + (uint64_t)s * WS;
-				uint64_t X[9]; int pc = 0;
+			for (int i = 0; i < 9; ++i) R[i] = i < Wd ? p.rd[s * WS + i] : 0ull;
+			bool have_rc = false;
+			const uint64_t key_f = extract_bases(R, ds, lt);
+			const uint64_t kmask = (1ull << (2 * lt)) - 1;
+			const bool sketch_big = p.counters[CT_S2_MAXBIN] > (unsigned long long)gm.maxsearch;
+			for (int phase = 0; phase < 2; ++phase) {
+				if (phase && ds <= 0) break;                                         // kthread_hash_realign.c:440 (j = 0)
+				// forward: the window holds the key at [ds, ds+lt).  reverse: the reverse-complemented window holds it there,
+				// i.e. the window itself holds the key's reverse complement at [L-ds-lt, L-ds).
+				const uint64_t key = phase ? rev_fields(~key_f & kmask, lt) : key_f;
+				const int koff = phase ? L - ds - lt : ds;
+				const uint32_t b = kmer_bucket(key, p.pbits);
+				const uint32_t i0 = b ? p.ptab[b - 1] : 0u, i1 = p.ptab[b];
+				for (uint32_t i = i0; i < i1; ++i) {
+					const unsigned long long e = p.ents[i];
+					if ((e >> S2_POS_BITS) != key) continue;
+					const uint64_t P = e & S2_POS_MASK;
+					uint32_t c = p.pblk[P >> S2_BLK_SHIFT];
+					while (p.ref_off[c + 1] <= P) ++c;
+					const uint64_t cb = p.ref_off[c], len = p.ref_off[c + 1] - cb;
+					const long long jj = (long long)(P - cb) - koff;
+					if (jj < 0 || (uint64_t)jj + L > len) continue;
+					++n_cand;
+					// window bits
+					uint64_t X[9]; int pc = 0;
+					{
+						const uint64_t *src = p.cw + p.cw_off[c] + ((uint64_t)jj >> 5);
+						const int sh = 2 * (int)(jj & 31);
+						if (phase && !have_rc) {
+							// reverse complement of the single: reverse fields over Wd words, then drop the pad fields that moved to the bottom
+							const int pad = Wd * 32 - L;
 #pragma unroll
-				for (int q = 0; q < 9; ++q) { X[q] = q < Wd ? (W[q] ^ r[q]) : 0ull; pc += __popcll(X[q]); }
-				++n_cand;
-				if (pc > gm.thr) continue;
-				if ((phase == 0 || gm.thr > 24) && !enc_ok(X, L, gm.enc_limit)) continue;   // :393 / :461
-				if (p.flagged[s]) continue;                                                // sg_flag already set by the poly-A/T diversion
-				if (be - 1 - i >= (uint32_t)gm.maxsearch) atomicAdd(&p.counters[CT_S2_NEEDEXACT], 1ull);   // beyond the static scan window (:388)
-				atomicMin(&p.claim[s], prio);
+							for (int q = 0; q < 9; ++q) RC[q] = 0;
+							for (int q = 0; q < Wd; ++q) {
+								uint64_t a = mcb_rc_word(R[Wd - 1 - q]);
+								uint64_t bb = q + 1 < Wd ? mcb_rc_word(R[Wd - 2 - q]) : 0ull;
+								RC[q] = pad ? (a >> (2 * pad)) | (bb << (64 - 2 * pad)) : a;
+							}
+							if (L & 31) RC[Wd - 1] &= (1ull << (2 * (L & 31))) - 1;
+							have_rc = true;
+						}
+#pragma unroll
+						for (int q = 0; q < 9; ++q) {
+							if (q < Wd) {
+								uint64_t a = src[q], w = sh ? (a >> sh) | (src[q + 1] << (64 - sh)) : a;
+								if (q == Wd - 1 && (L & 31)) w &= (1ull << (2 * (L & 31))) - 1;
+								X[q] = w ^ (phase ? RC[q] : R[q]);
+								pc += __popcll(X[q]);
+							} else X[q] = 0;
+						}
+					}
+					if (pc > gm.thr) continue;
+					if ((phase == 0 || gm.thr > 24) && !enc_ok(X, L, gm.enc_limit)) continue;   // :393 / :461
+					if (sketch_big) {
+						// The reference scans only the last `maxsearch` live entries of a bin (:388); with every bin at most that
+						// large the scan sees everything and "all matches, first one wins" is exact.
+						bool big = true;
+						if (p.xkey) big = bins_exact_count(p.xkey, p.xcnt, p.xmask, ((unsigned long long)l << 34) | key_f) > (uint32_t)gm.maxsearch;
+						if (big) atomicAdd(&p.counters[CT_S2_NEEDEXACT], 1ull);
+					}
+					const unsigned long long g = p.woff[c] + (unsigned long long)jj;
+					atomicMin(&p.claim[s], (g << 5) | ((unsigned long long)phase << 4) | (unsigned long long)l);
+				}
 			}
 		}
 	}
-	}
-	// warp-aggregated statistics
-	for (int o = 16; o; o >>= 1) { n_probe += __shfl_xor_sync(0xFFFFFFFFu, n_probe, o); n_cand += __shfl_xor_sync(0xFFFFFFFFu, n_cand, o); }
-	if ((threadIdx.x & 31) == 0) { atomicAdd(&p.counters[CT_S2_PROBES], n_probe); atomicAdd(&p.counters[CT_S2_CAND], n_cand); }
+	for (int o = 16; o; o >>= 1) n_cand += __shfl_xor_sync(0xFFFFFFFFu, n_cand, o);
+	if ((threadIdx.x & 31) == 0 && n_cand) atomicAdd(&p.counters[CT_S2_CAND], n_cand);
 }
 
 // ---------------------------------------------------------------- K8
@@ -286,13 +359,85 @@ __global__ void k_s2_claim_emit(const ulonglong2 *__restrict__ el, uint64_t n, c
 }
 
 // ================================================================= host
+// Upload the contigs and (re)build the lt-mer table unless the cached one was built from identical contigs.
+static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int lt)
+{
+	McbContigIndex &cx = ctx->cix;
+	const int L = ctx->L;
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	const uint64_t ref_bytes = n_contigs ? ref_off[n_contigs] : 0;
+	if (ref_bytes >= (1ull << S2_POS_BITS)) { mcb_set_error("mcb_realign: %llu contig bases exceed the 2^%d positions of one call", (unsigned long long)ref_bytes, S2_POS_BITS); return MCB_EINVAL; }
+	// ---- host-side offsets
+	uint64_t total_words = 0, n_windows = 0, n_entries = 0;
+	MCB_TRY(ctx->h_in0.ensure((n_contigs + 1) * 8)); MCB_TRY(ctx->h_in1.ensure((n_contigs + 1) * 8));
+	uint64_t *cwo = ctx->h_in0.as<uint64_t>(), *wo = ctx->h_in1.as<uint64_t>();
+	for (uint64_t c = 0; c < n_contigs; ++c) {
+		if (ref_off[c + 1] < ref_off[c]) { mcb_set_error("mcb_realign: ref_off is not monotonic"); return MCB_EINVAL; }
+		const uint64_t len = ref_off[c + 1] - ref_off[c];
+		cwo[c] = total_words; wo[c] = n_windows;
+		total_words += (len + 31) / 32 + 1;
+		if (len >= (uint64_t)L) { n_windows += len - L + 1; n_entries += len - lt + 1; }
+	}
+	cwo[n_contigs] = total_words + 1; wo[n_contigs] = n_windows;   // +1 guard word: loaders read one word ahead
+	if (n_windows >= (1ull << 58)) { mcb_set_error("too many windows"); return MCB_EINVAL; }
+	// ---- same contigs as last time?  (compare on the device: the strings have to be uploaded to find out)
+	const bool maybe_same = cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L;
+	DBuf &stage_refs = maybe_same ? ctx->d_scr[1] : cx.refs, &stage_off = maybe_same ? ctx->d_scr[2] : cx.roff;
+	const size_t refs_pad = (ref_bytes + 7) & ~(size_t)7;
+	MCB_TRY(stage_refs.ensure(refs_pad + 16)); MCB_TRY(stage_off.ensure((n_contigs + 1) * 8));
+	cx.valid = cx.valid && maybe_same;
+	{
+		McbSpan sp(ctx->tm, "h2d");
+		if (refs_pad > ref_bytes) MCB_CUDA(cudaMemsetAsync(stage_refs.as<char>() + (refs_pad - 8), 0, 8, ctx->stream));
+		MCB_CUDA(cudaMemcpyAsync(stage_refs.p, refs, ref_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		MCB_CUDA(cudaMemcpyAsync(stage_off.p, ref_off, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	if (maybe_same) {
+		McbSpan sp(ctx->tm, "realign");
+		MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_DIFF], 0, 8, ctx->stream));
+		if (refs_pad) MCB_LAUNCH(ctx, "s2_same", k_s2_same, mcb_grid_for(refs_pad / 8, 256), 256, 0, stage_refs.as<uint64_t>(), cx.refs.as<uint64_t>(), refs_pad / 8, dc);
+		MCB_LAUNCH(ctx, "s2_same", k_s2_same, mcb_grid_for(n_contigs + 1, 256), 256, 0, stage_off.as<uint64_t>(), cx.roff.as<uint64_t>(), n_contigs + 1, dc);
+		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (ctx->h_counters.as<unsigned long long>()[CT_S2_DIFF] == 0) return MCB_OK;      // identical: keep the table
+		cx.valid = false;
+		std::swap(cx.refs, ctx->d_scr[1]); std::swap(cx.roff, ctx->d_scr[2]);
+	}
+	// ---- build
+	cx.n_contigs = n_contigs; cx.ref_bytes = ref_bytes; cx.total_words = total_words; cx.n_windows = n_windows; cx.n_entries = n_entries; cx.L = L; cx.lt = lt;
+	int pbits = 10; while (pbits < 26 && pbits < 2 * lt && (2ull << pbits) < n_entries) ++pbits;                 // about 1..2 entries per bucket
+	cx.pbits = pbits;
+	const uint64_t nbk = 1ull << pbits, n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
+	MCB_TRY(cx.cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.wo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.cw.ensure((total_words + 2) * 8));
+	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16)); MCB_TRY(cx.ptab.ensure((nbk + 1) * 4)); MCB_TRY(cx.ents.ensure(n_entries * 8 + 16));
+	{
+		McbSpan sp(ctx->tm, "h2d");
+		MCB_CUDA(cudaMemcpyAsync(cx.cwo.p, cwo, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+		MCB_CUDA(cudaMemcpyAsync(cx.wo.p, wo, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	if (n_contigs == 0 || n_windows == 0) { cx.valid = true; return MCB_OK; }
+	McbSpan sp(ctx->tm, "realign");
+	MCB_CUDA(cudaMemsetAsync(cx.cw.as<uint64_t>() + total_words, 0, 16, ctx->stream));
+	MCB_LAUNCH(ctx, "s2_pack_refs", k_s2_pack_refs, mcb_grid_for(total_words, 256), 256, 0, cx.refs.as<char>(), cx.roff.as<uint64_t>(), cx.cwo.as<uint64_t>(),
+	           n_contigs, total_words, cx.cw.as<uint64_t>(), dc);
+	MCB_LAUNCH(ctx, "s2_pos_blocks", k_s2_pos_blocks, mcb_grid_for(n_blocks, 256), 256, 0, cx.roff.as<uint64_t>(), n_contigs, n_blocks, cx.pblk.as<uint32_t>());
+	MCB_CUDA(cudaMemsetAsync(cx.ptab.p, 0, (nbk + 1) * 4, ctx->stream));
+	MCB_LAUNCH(ctx, "s2_kmer_hist", k_s2_kmers<false>, mcb_grid_for(total_words, 256), 256, 0, cx.cw.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.roff.as<uint64_t>(),
+	           n_contigs, total_words, L, lt, pbits, cx.ptab.as<uint32_t>(), cx.ents.as<unsigned long long>());
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, cx.ptab.as<uint32_t>(), nbk + 1, nullptr));
+	MCB_LAUNCH(ctx, "s2_kmer_fill", k_s2_kmers<true>, mcb_grid_for(total_words, 256), 256, 0, cx.cw.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.roff.as<uint64_t>(),
+	           n_contigs, total_words, L, lt, pbits, cx.ptab.as<uint32_t>(), cx.ents.as<unsigned long long>());
+	cx.valid = true;
+	return MCB_OK;
+}
+
 extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
                            int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
 {
 	if (!ctx || !res) { mcb_set_error("mcb_realign: null argument"); return MCB_EINVAL; }
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
 	if (!ctx->reads_loaded) { mcb_set_error("mcb_realign: no reads loaded"); return MCB_ESTATE; }
-	if ((S && !sg) || (n_contigs && (!refs || !ref_off))) { mcb_set_error("mcb_realign: null input"); return MCB_EINVAL; }
+	if (S && !sg) { mcb_set_error("mcb_realign: null input"); return MCB_EINVAL; }
 	if (S >= 0xFFFFFFFFull) { mcb_set_error("mcb_realign: too many singles"); return MCB_EINVAL; }
 	memset(res, 0, sizeof(*res));
 	const int L = ctx->L, Wd = ctx->Wd, WS = ctx->WS;
@@ -307,115 +452,93 @@ extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const c
 	for (int i = 0; i < gm.nd; ++i) gm.dstart[i] = st0 + i * gm.lt;
 	gm.enc_limit = (int)((double)L * 0.4);
 	res->numdict = gm.nd;
-	MCB_TRY(ctx->d_counters.ensure(64 * 8));
+	MCB_TRY(ctx->d_counters.ensure(64 * 8)); MCB_TRY(ctx->h_counters.ensure(64 * 8));
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
 	MCB_CUDA(cudaMemsetAsync(dc + 16, 0, 16 * 8, ctx->stream));
-	// ---- host-side offsets
-	uint64_t total_words = 0, n_windows = 0, ref_bytes = n_contigs ? ref_off[n_contigs] : 0;
-	MCB_TRY(ctx->h_in0.ensure((n_contigs + 1) * 8)); MCB_TRY(ctx->h_in1.ensure((n_contigs + 1) * 8));
-	uint64_t *cwo = ctx->h_in0.as<uint64_t>(), *wo = ctx->h_in1.as<uint64_t>();
-	for (uint64_t c = 0; c < n_contigs; ++c) {
-		uint64_t len = ref_off[c + 1] - ref_off[c];
-		cwo[c] = total_words; wo[c] = n_windows;
-		total_words += (len + 31) / 32 + 1;
-		if (len >= (uint64_t)L) n_windows += len - L + 1;
+	// ---- contigs: refs == NULL reuses the contigs (and their table) of the previous call
+	McbContigIndex &cx = ctx->cix;
+	if (refs || ref_off) {
+		if (n_contigs && (!refs || !ref_off)) { mcb_set_error("mcb_realign: refs and ref_off must be given together"); return MCB_EINVAL; }
+		MCB_TRY(contig_index_update(ctx, refs, ref_off, n_contigs, gm.lt));
+	} else {
+		if (!cx.valid || cx.L != L || cx.lt != gm.lt) { mcb_set_error("mcb_realign: refs == NULL but no contigs from a previous call are cached"); return MCB_ESTATE; }
+		if (n_contigs && n_contigs != cx.n_contigs) { mcb_set_error("mcb_realign: refs == NULL with a different contig count (%llu, cached %llu)", (unsigned long long)n_contigs, (unsigned long long)cx.n_contigs); return MCB_EINVAL; }
 	}
-	cwo[n_contigs] = total_words + 1; wo[n_contigs] = n_windows;   // +1 guard word: the window loader reads one word ahead
-	if (n_windows >= (1ull << 58)) { mcb_set_error("too many windows"); return MCB_EINVAL; }
+	n_contigs = cx.n_contigs;
+	const uint64_t n_windows = cx.n_windows;
 	res->n_windows = n_windows;
+	{
+		int nrev = 0; for (int l = 0; l < gm.nd; ++l) nrev += gm.dstart[l] > 0;
+		res->n_probes = n_windows * (uint64_t)(gm.nd + nrev);                 // what the reference's window loop would issue (:355-504)
+	}
 	const uint64_t nkv = S * (uint64_t)gm.nd;
 	if (S == 0 || n_windows == 0 || gm.nd == 0) return MCB_OK;
 	if (nkv >= 0xFFFFFFFFull) { mcb_set_error("dictionary too large"); return MCB_EINVAL; }
-	// d_scr roles: 0 sg, 1 refs ascii, 2 ref_off, 3 cw_off, 4 woff, 5 cw, 6 rd, 7 rdrc, 8 flagged, 9 kv A, 10 kv B, 11 misc
-	DBuf &b_sg = ctx->d_scr[0], &b_refs = ctx->d_scr[1], &b_roff = ctx->d_scr[2], &b_cwo = ctx->d_scr[3], &b_wo = ctx->d_scr[4], &b_cw = ctx->d_scr[5];
-	DBuf &b_rd = ctx->d_scr[6], &b_rc = ctx->d_scr[7], &b_fl = ctx->d_scr[8], &b_kva = ctx->d_scr[9], &b_kvb = ctx->d_scr[10], &b_misc = ctx->d_scr[11];
-	MCB_TRY(b_sg.ensure(S * 4 + 16)); MCB_TRY(b_refs.ensure(ref_bytes + 16)); MCB_TRY(b_roff.ensure((n_contigs + 1) * 8));
-	MCB_TRY(b_cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(b_wo.ensure((n_contigs + 1) * 8)); MCB_TRY(b_cw.ensure((total_words + 2) * 8));
-	MCB_TRY(b_rd.ensure(S * WS * 8 + 16)); MCB_TRY(b_rc.ensure(S * WS * 8 + 16)); MCB_TRY(b_fl.ensure(S + 16));
-	MCB_TRY(b_kva.ensure(nkv * 16 + 16)); MCB_TRY(b_kvb.ensure(nkv * 16 + 16));
+	// d_scr roles: 0 sg, 3 flags (K8), 4 fpA|fpT, 5 count-min sketch / exact bins, 6 rd, 8 flagged, 9/10 claim elements, 11 claim outputs
+	DBuf &b_sg = ctx->d_scr[0], &b_fl3 = ctx->d_scr[3], &b_fp = ctx->d_scr[4], &b_cm = ctx->d_scr[5], &b_rd = ctx->d_scr[6], &b_fl = ctx->d_scr[8];
+	DBuf &b_elA = ctx->d_scr[9], &b_elB = ctx->d_scr[10], &b_out = ctx->d_scr[11];
+	uint64_t CM = 1024; while (CM < 2 * nkv && CM < (1ull << 28)) CM <<= 1;
+	MCB_TRY(b_sg.ensure(S * 4 + 16)); MCB_TRY(b_rd.ensure(S * WS * 8 + 16)); MCB_TRY(b_fl.ensure(S + 16)); MCB_TRY(b_cm.ensure(CM * 4));
+	MCB_TRY(ctx->d_x[0].ensure(S * 8 + 16));                   // claim priorities
+	unsigned long long *claim = ctx->d_x[0].as<unsigned long long>();
 	{
 		McbSpan sp(ctx->tm, "h2d");
 		MCB_CUDA(cudaMemcpyAsync(b_sg.p, sg, S * 4, cudaMemcpyHostToDevice, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(b_refs.p, refs, ref_bytes, cudaMemcpyHostToDevice, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(b_roff.p, ref_off, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(b_cwo.p, cwo, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(b_wo.p, wo, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
 	}
 	const int span_h = ctx->tm.begin("realign");
-	MCB_CUDA(cudaMemsetAsync(b_cw.as<uint64_t>() + total_words, 0, 16, ctx->stream));
-	MCB_LAUNCH(ctx, "s2_pack_refs", k_s2_pack_refs, mcb_grid_for(total_words, 256), 256, 0, b_refs.as<char>(), b_roff.as<uint64_t>(), b_cwo.as<uint64_t>(),
-	           n_contigs, total_words, b_cw.as<uint64_t>(), dc);
+	MCB_CUDA(cudaMemsetAsync(b_cm.p, 0, CM * 4, ctx->stream));
 	MCB_LAUNCH(ctx, "s2_singles", k_s2_singles, mcb_grid_for(S, 128), 128, 0, b_sg.as<uint32_t>(), S, ctx->d_packed.as<uint64_t>(), gm,
 	           ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->n_nreads, ctx->n_reads,
-	           b_rd.as<uint64_t>(), b_rc.as<uint64_t>(), b_fl.as<uint8_t>(), b_kva.as<ulonglong2>(), dc);
-	// ---- K6: dictionaries
-	std::vector<McbSortPass> passes;
-	mcb_add_bit_passes(passes, 0, 0, 2 * gm.lt);
-	if (gm.nd > 1) mcb_add_bit_passes(passes, 0, 34, 34 + mcb_bits_for(gm.nd - 1));
-	ulonglong2 *kvs = nullptr;
-	MCB_TRY(mcb_radix_sort(ctx, b_kva.as<ulonglong2>(), b_kvb.as<ulonglong2>(), nkv, passes.data(), (int)passes.size(), &kvs));
-	ulonglong2 *kvfree = kvs == b_kva.as<ulonglong2>() ? b_kvb.as<ulonglong2>() : b_kva.as<ulonglong2>();
-	// misc layout: hscan u32[nkv] | ukey u64[nkv] | bstart u32[nkv+1] | bin_sg u32[nkv]
-	size_t o_h = 0, o_uk = (nkv * 4 + 15) & ~(size_t)15, o_bs = o_uk + nkv * 8, o_bn = (o_bs + (nkv + 1) * 4 + 15) & ~(size_t)15, o_end = o_bn + nkv * 4;
-	MCB_TRY(b_misc.ensure(o_end + 16));
-	uint32_t *hscan = (uint32_t*)(b_misc.as<char>() + o_h); uint64_t *ukey = (uint64_t*)(b_misc.as<char>() + o_uk);
-	uint32_t *bstart = (uint32_t*)(b_misc.as<char>() + o_bs), *bin_sg = (uint32_t*)(b_misc.as<char>() + o_bn);
-	MCB_LAUNCH(ctx, "s2_heads", k_s2_heads, mcb_grid_for(nkv, 256), 256, 0, kvs, nkv, hscan);
-	MCB_TRY(mcb_exclusive_scan_u32(ctx, hscan, nkv, (uint64_t*)&dc[CT_S2_U]));
-	MCB_LAUNCH(ctx, "s2_bins", k_s2_bins, mcb_grid_for(nkv, 256), 256, 0, kvs, nkv, hscan, &dc[CT_S2_U], ukey, bstart, bin_sg);
-	MCB_TRY(ctx->h_counters.ensure(64 * 8));
-	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
-	if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }
-	const uint64_t U = hc[CT_S2_U];
-	res->n_dict_keys = U;
-	uint64_t H = 1024; while (H < 2 * U) H <<= 1;
-	// the free half of the kv double buffer holds the table (keys u64[H] | vals u32[H]); grow it if needed
-	DBuf &b_tab = (kvfree == b_kva.as<ulonglong2>()) ? b_kva : b_kvb;
-	MCB_TRY(b_tab.ensure(H * 12 + 16));
-	unsigned long long *tkey = b_tab.as<unsigned long long>(); uint32_t *tval = (uint32_t*)(b_tab.as<char>() + H * 8);
-	MCB_CUDA(cudaMemsetAsync(tkey, 0xFF, H * 8, ctx->stream));
-	MCB_LAUNCH(ctx, "s2_table_insert", k_s2_table_insert, mcb_grid_for(U, 256), 256, 0, ukey, U, tkey, tval, H - 1);
-	// ---- K7
-	MCB_TRY(ctx->d_x[0].ensure(S * 8 + 16));                   // claim priorities
-	unsigned long long *claim = ctx->d_x[0].as<unsigned long long>();
+	           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, dc);
+	S2Join jn; memset(&jn, 0, sizeof jn);
+	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents.as<unsigned long long>(); jn.pbits = cx.pbits;
+	jn.pblk = cx.pblk.as<uint32_t>(); jn.ref_off = cx.roff.as<uint64_t>(); jn.cw = cx.cw.as<uint64_t>(); jn.cw_off = cx.cwo.as<uint64_t>(); jn.woff = cx.wo.as<uint64_t>();
+	jn.claim = claim; jn.counters = dc;
 	MCB_CUDA(cudaMemsetAsync(claim, 0xFF, S * 8, ctx->stream));
-	S2Probe pr; pr.cw = b_cw.as<uint64_t>(); pr.cw_off = b_cwo.as<uint64_t>(); pr.woff = b_wo.as<uint64_t>(); pr.n_contigs = n_contigs; pr.n_windows = n_windows;
-	pr.tkey = tkey; pr.tval = tval; pr.hmask = H - 1; pr.bstart = bstart; pr.bin_sg = bin_sg; pr.rd = b_rd.as<uint64_t>(); pr.rdrc = b_rc.as<uint64_t>();
-	pr.flagged = b_fl.as<uint8_t>(); pr.claim = claim; pr.counters = dc;
-	MCB_LAUNCH(ctx, "s2_probe", k_s2_probe, mcb_grid_for(n_windows, 128), 128, 0, pr, gm);
+	MCB_LAUNCH(ctx, "s2_join", k_s2_join, mcb_grid_for(nkv, 128), 128, 0, jn, gm);
 	// ---- K8
-	// reuse: refs ascii buffer is dead -> flags; sized S*12
-	MCB_TRY(b_refs.ensure(S * 12 + 64));
-	uint32_t *f_c = b_refs.as<uint32_t>(), *f_a = f_c + S, *f_t = f_a + S;
-	MCB_LAUNCH(ctx, "s2_claim_flags", k_s2_claim_flags, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, f_c, f_a, f_t);
-	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_c, S, (uint64_t*)&dc[CT_S2_CLAIMS]));
-	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_a, S, (uint64_t*)&dc[CT_S2_FPA]));
-	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_t, S, (uint64_t*)&dc[CT_S2_FPT]));
-	// claim elements go to the kv buffer that held the sorted pairs (dead now: bins were flattened)
-	DBuf &b_el = (kvs == b_kva.as<ulonglong2>()) ? b_kva : b_kvb;
-	MCB_TRY(ctx->d_x[1].ensure(S * 16 + 16));
-	ulonglong2 *elA = b_el.as<ulonglong2>(), *elB = ctx->d_x[1].as<ulonglong2>();
-	MCB_TRY(b_cw.ensure(S * 8 + 64));                           // packed contigs are dead after the probe: fpA | fpT lists
-	uint32_t *d_fpa = b_cw.as<uint32_t>(), *d_fpt = d_fpa + S;
-	MCB_LAUNCH(ctx, "s2_claim_compact", k_s2_claim_compact, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, f_c, f_a, f_t, elA, d_fpa, d_fpt);
-	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-	const uint64_t ncl = hc[CT_S2_CLAIMS], nfa = hc[CT_S2_FPA], nft = hc[CT_S2_FPT];
-	if (hc[CT_S2_NEEDEXACT]) {
-		mcb_set_error("mcb_realign: %llu matches lie beyond the maxsearch=%d scan window of their bin; the sequential bin-window emulation is not implemented",
-		              hc[CT_S2_NEEDEXACT], maxsearch);
-		return MCB_EINPUT;
+	MCB_TRY(b_fl3.ensure(S * 12 + 64));
+	uint32_t *f_c = b_fl3.as<uint32_t>(), *f_a = f_c + S, *f_t = f_a + S;
+	MCB_TRY(b_elA.ensure(S * 16 + 16)); MCB_TRY(b_elB.ensure(S * 16 + 16)); MCB_TRY(b_fp.ensure(S * 8 + 64));
+	ulonglong2 *elA = b_elA.as<ulonglong2>(), *elB = b_elB.as<ulonglong2>();
+	uint32_t *d_fpa = b_fp.as<uint32_t>(), *d_fpt = d_fpa + S;
+	for (int attempt = 0;; ++attempt) {
+		MCB_LAUNCH(ctx, "s2_claim_flags", k_s2_claim_flags, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, f_c, f_a, f_t);
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, f_c, S, (uint64_t*)&dc[CT_S2_CLAIMS]));
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, f_a, S, (uint64_t*)&dc[CT_S2_FPA]));
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, f_t, S, (uint64_t*)&dc[CT_S2_FPT]));
+		MCB_LAUNCH(ctx, "s2_claim_compact", k_s2_claim_compact, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, f_c, f_a, f_t, elA, d_fpa, d_fpt);
+		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }
+		if (!hc[CT_S2_NEEDEXACT]) break;
+		if (attempt == 1) {
+			mcb_set_error("mcb_realign: %llu matches fall into dictionary bins with more than maxsearch=%d singles; the sequential bin-window emulation "
+			              "(kthread_hash_realign.c:388, bbhashdict.c:33-67) is not implemented", hc[CT_S2_NEEDEXACT], maxsearch);
+			return MCB_EINPUT;
+		}
+		// the sketch only bounds bin sizes from above: count them exactly and join again
+		uint64_t H = 1024; while (H < 2 * nkv) H <<= 1;
+		MCB_TRY(b_cm.ensure(H * 12 + 16));
+		unsigned long long *tkey = b_cm.as<unsigned long long>(); uint32_t *tcnt = (uint32_t*)(b_cm.as<char>() + H * 8);
+		MCB_CUDA(cudaMemsetAsync(tkey, 0xFF, H * 8, ctx->stream)); MCB_CUDA(cudaMemsetAsync(tcnt, 0, H * 4, ctx->stream));
+		MCB_LAUNCH(ctx, "s2_bins_exact", k_s2_bins_exact, mcb_grid_for(nkv, 256), 256, 0, b_rd.as<uint64_t>(), S, gm, tkey, tcnt, H - 1);
+		jn.xkey = tkey; jn.xcnt = tcnt; jn.xmask = H - 1;
+		MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_CAND], 0, 8, ctx->stream)); MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NEEDEXACT], 0, 8, ctx->stream));
+		MCB_CUDA(cudaMemsetAsync(claim, 0xFF, S * 8, ctx->stream));
+		MCB_LAUNCH(ctx, "s2_join", k_s2_join, mcb_grid_for(nkv, 128), 128, 0, jn, gm);
 	}
-	passes.clear();
+	const uint64_t ncl = hc[CT_S2_CLAIMS], nfa = hc[CT_S2_FPA], nft = hc[CT_S2_FPT];
+	res->n_candidates = hc[CT_S2_CAND];
+	std::vector<McbSortPass> passes;
 	mcb_add_bit_passes(passes, 1, 0, mcb_bits_for(S));                                // 0xFFFFFFFF-s: only the low bits vary
 	mcb_add_bit_passes(passes, 0, 0, 5 + mcb_bits_for(n_windows));
 	ulonglong2 *els = nullptr;
 	MCB_TRY(mcb_radix_sort(ctx, elA, elB, ncl, passes.data(), (int)passes.size(), &els));
-	MCB_TRY(b_rd.ensure(ncl * 16 + 64));                                                // rd is dead: claim outputs c | s | y
-	uint64_t *o_y = b_rd.as<uint64_t>(); uint32_t *o_c = (uint32_t*)(o_y + ncl), *o_s = o_c + ncl;
-	if (ncl) MCB_LAUNCH(ctx, "s2_claim_emit", k_s2_claim_emit, mcb_grid_for(ncl, 256), 256, 0, els, ncl, b_wo.as<uint64_t>(), n_contigs, b_sg.as<uint32_t>(), o_c, o_s, o_y);
+	MCB_TRY(b_out.ensure(ncl * 16 + 64));
+	uint64_t *o_y = b_out.as<uint64_t>(); uint32_t *o_c = (uint32_t*)(o_y + ncl), *o_s = o_c + ncl;
+	if (ncl) MCB_LAUNCH(ctx, "s2_claim_emit", k_s2_claim_emit, mcb_grid_for(ncl, 256), 256, 0, els, ncl, cx.wo.as<uint64_t>(), n_contigs, b_sg.as<uint32_t>(), o_c, o_s, o_y);
 	ctx->tm.end(span_h);
 	MCB_TRY(ctx->h_claim_c.ensure(ncl * 4 + 16)); MCB_TRY(ctx->h_claim_s.ensure(ncl * 4 + 16)); MCB_TRY(ctx->h_claim_y.ensure(ncl * 8 + 16));
 	MCB_TRY(ctx->h_fpA.ensure(nfa * 4 + 16)); MCB_TRY(ctx->h_fpT.ensure(nft * 4 + 16));
@@ -428,12 +551,10 @@ extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const c
 		}
 		if (nfa) MCB_CUDA(cudaMemcpyAsync(ctx->h_fpA.p, d_fpa, nfa * 4, cudaMemcpyDeviceToHost, ctx->stream));
 		if (nft) MCB_CUDA(cudaMemcpyAsync(ctx->h_fpT.p, d_fpt, nft * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->tm.collect();
 	res->n_claims = ncl; res->claim_contig = ctx->h_claim_c.as<uint32_t>(); res->claim_sg = ctx->h_claim_s.as<uint32_t>(); res->claim_y = ctx->h_claim_y.as<uint64_t>();
 	res->n_fpA = nfa; res->n_fpT = nft; res->fpA_sg = ctx->h_fpA.as<uint32_t>(); res->fpT_sg = ctx->h_fpT.as<uint32_t>();
-	res->n_probes = hc[CT_S2_PROBES]; res->n_candidates = hc[CT_S2_CAND];
 	return MCB_OK;
 }

@@ -214,16 +214,63 @@ def test_front_end_matches_oracle(case):
         # the threshold schedule over the seed contigs (no host merge in between: contigs = seed contigs)
         sg = S.sg.copy()
         e = ctx.params.diff_threshold
-        for thr in (e, 2 * e, 3 * e, 28):
+        for rnd, thr in enumerate((e, 2 * e, 3 * e, 28)):
             if len(sg) == 0 or len(S.cl_n) == 0:
                 break
             want = S.realign(sg, S.cl_ref, S.cl_ref_off, thr, 2000)
-            got = ctx.realign(sg, S.cl_ref, S.cl_ref_off, thr, 2000)
+            # later rounds reuse the contigs of the first call (refs=None), as the drop-in shim does
+            got = ctx.realign(sg, S.cl_ref, S.cl_ref_off, thr, 2000) if rnd == 0 else ctx.realign(sg, None, None, thr, 2000)
             assert np.array_equal(got.claim_y, want["claim_y"]), f"thr {thr}: claims / append order differ"
             assert np.array_equal(got.claim_contig, want["claim_contig"]) and np.array_equal(got.claim_sg, want["claim_sg"])
             assert np.array_equal(got.fpA_sg, want["fpA_sg"]) and np.array_equal(got.fpT_sg, want["fpT_sg"])
             assert (got.n_windows, got.n_probes, got.numdict) == (want["n_windows"], want["n_probes"], want["numdict"])
             sg = sg[want["flag"] == 0]
+    S.close()
+
+
+def test_realign_contig_cache_is_invalidated_by_content():
+    """Two contig sets of identical shape but different bases: the cached device table must not survive the second call."""
+    import oracle_lib as O
+    L = 100
+    genome = synth.make_genome(6000, 41)
+    reads = synth.make_reads(1500, L, 6000, seed=41, genome=genome)
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    contigs_a = genome.copy()
+    contigs_b = comp[genome[::-1]].copy()                  # same length, reverse complement
+    off = np.array([0, 2500, 2560, 6000], dtype=np.uint64)   # includes a contig shorter than a read
+    sg = np.arange(len(reads), dtype=np.uint32)
+    S = O.Stage1(O.resolve_params(L), reads)
+    with api.Context(api.resolve_params(L)) as ctx:
+        ctx.for_reads(reads)
+        for refs in (contigs_a, contigs_b, contigs_b, contigs_a):
+            want = S.realign(sg, refs, off, 8, 2000)
+            got = ctx.realign(sg, refs, off, 8, 2000)
+            assert len(want["claim_y"]) > 500
+            assert np.array_equal(got.claim_y, want["claim_y"]) and np.array_equal(got.claim_contig, want["claim_contig"])
+    S.close()
+
+
+def test_realign_bins_above_maxsearch():
+    """20 identical singles share every dictionary bin.  maxsearch >= 20: identical to the sequential scan.  maxsearch 4:
+    the reference would scan only the last 4 live entries per probe; the library refuses loudly instead of guessing."""
+    import oracle_lib as O
+    rng = np.random.default_rng(9)
+    L = 100
+    read = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=L)]
+    reads = np.tile(read, (20, 1))
+    contig = np.concatenate([read, read])
+    off = np.array([0, 2 * L], dtype=np.uint64)
+    sg = np.arange(20, dtype=np.uint32)
+    S = O.Stage1(O.resolve_params(L), reads)
+    with api.Context(api.resolve_params(L)) as ctx:
+        ctx.for_reads(reads)
+        want = S.realign(sg, contig, off, 4, 2000)
+        got = ctx.realign(sg, contig, off, 4, 2000)
+        assert np.array_equal(got.claim_y, want["claim_y"]) and len(got.claim_y) == 20
+        with pytest.raises(api.McbError):
+            ctx.realign(sg, contig, off, 4, 4)
     S.close()
 
 
