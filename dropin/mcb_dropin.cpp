@@ -195,7 +195,7 @@ void mm_idx_generation(int n_threads_, mm_idx_t *mi)
 		record("idx", g_calls[2], "xy.u64", flat.data(), flat.size() * sizeof(mcb_tuple));
 	}
 	mcb_index *ix = 0;
-	int rc = mcb_idx_build_scattered(ctx, ptrs.data(), cnt.data(), &ix);
+	int rc = mcb_idx_build_scattered(ctx, ptrs.data(), cnt.data(), n_threads_, &ix);
 	if (rc) die("mm_idx_generation", rc);
 	for (int i = 0; i < nb; ++i) { free(mi->B[i].a.a); mi->B[i].a.a = 0; mi->B[i].a.n = mi->B[i].a.m = 0; }   // kthread_idx.c:166-167
 	if (mi->B[0].h) mcb_idx_destroy((mcb_index*)mi->B[0].h);

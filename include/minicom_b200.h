@@ -148,8 +148,8 @@ typedef struct mcb_index mcb_index;
  * (radix_sort_128x is unstable above 64 elements; ksort.h:108-157). */
 int mcb_idx_build(mcb_ctx *ctx, const mcb_tuple *tuples, const uint64_t *bucket_off, mcb_index **out);
 /* Same as mcb_idx_build but the per-bucket arrays are still scattered: bucket i has
- * cnt[i] tuples at ptrs[i] (the reference's mi->B[i].a.{a,n}). */
-int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptrs, const uint64_t *cnt, mcb_index **out);
+ * cnt[i] tuples at ptrs[i] (the reference's mi->B[i].a.{a,n}); n_threads host threads gather them (mm_idx_generation's n_threads). */
+int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptrs, const uint64_t *cnt, int n_threads, mcb_index **out);
 /* Host lookup; thread-safe; returns pointer to *n postings (y values) or NULL. */
 const uint64_t *mcb_idx_get(const mcb_index *idx, uint64_t minier, int *n);
 void mcb_idx_destroy(mcb_index *idx);

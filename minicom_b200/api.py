@@ -83,7 +83,7 @@ def load_library() -> C.CDLL:
     lib.mcb_debug_unpack_reads.argtypes = [C.c_void_p, C.c_void_p]
     lib.mcb_for_bucket.argtypes = [C.c_void_p, C.POINTER(_BucketResult)]
     lib.mcb_idx_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
-    lib.mcb_idx_build_scattered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mcb_idx_build_scattered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.mcb_idx_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
     lib.mcb_idx_get.restype = C.c_void_p
     lib.mcb_idx_destroy.argtypes = [C.c_void_p]

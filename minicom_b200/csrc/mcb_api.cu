@@ -3,6 +3,7 @@
 #include "mcb_sketch_lh.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
+#include <algorithm>
 
 static thread_local char g_err[1024] = "";
 
@@ -59,6 +60,7 @@ extern "C" int mcb_create(const mcb_params *p, mcb_ctx **out)
 	if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; mcb_set_error("cudaStreamCreate failed"); return MCB_ECUDA; }
 	ctx->tm.stream = ctx->stream;
+	ctx->pool = new McbPinnedPool();
 	if (ctx->d_counters.ensure(64 * 8) != MCB_OK) { cudaStreamDestroy(ctx->stream); delete ctx; return MCB_ECUDA; }
 	cudaMemsetAsync(ctx->d_counters.p, 0, 64 * 8, ctx->stream);
 	*out = ctx;
@@ -84,7 +86,47 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 	               &ctx->h_claim_c, &ctx->h_claim_s, &ctx->h_claim_y, &ctx->h_fpA, &ctx->h_fpT, &ctx->h_in0, &ctx->h_in1, &ctx->h_in2 };
 	for (auto b : hb) b->release();
 	cudaStreamDestroy(ctx->stream);
+	if (ctx->pool && ctx->pool->close()) delete ctx->pool;
 	delete ctx;
+}
+
+// ---------------------------------------------------------------- host -> device staging
+#include <thread>
+static void par_memcpy(char *dst, const char *src, size_t bytes, int n_threads)
+{
+	int T = (int)std::min<size_t>((size_t)std::max(1, n_threads), (bytes + (4u << 20) - 1) / (4u << 20));
+	if (T <= 1) { memcpy(dst, src, bytes); return; }
+	std::vector<std::thread> th;
+	for (int t = 0; t < T; ++t) {
+		size_t a = bytes * t / T, b = bytes * (t + 1) / T;
+		th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
+	}
+	for (auto &x : th) x.join();
+}
+
+int mcb_h2d(mcb_ctx *ctx, void *dst, const void *src, size_t bytes, int n_threads)
+{
+	if (!bytes) return MCB_OK;
+	cudaPointerAttributes pa;
+	const bool pinned = cudaPointerGetAttributes(&pa, src) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (pinned) { MCB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return MCB_OK; }
+	const size_t CH = 16u << 20;
+	MCB_TRY(ctx->h_stage.ensure(2 * CH));
+	cudaEvent_t ev[2];
+	cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+	int slot = 0, rc = MCB_OK;
+	for (size_t o = 0; o < bytes; o += CH, slot ^= 1) {
+		const size_t len = std::min(CH, bytes - o);
+		char *st = ctx->h_stage.as<char>() + (size_t)slot * CH;
+		cudaEventSynchronize(ev[slot]);
+		par_memcpy(st, (const char*)src + o, len, n_threads);
+		if (cudaMemcpyAsync((char*)dst + o, st, len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { mcb_set_error("h2d staging copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = MCB_ECUDA; break; }
+		cudaEventRecord(ev[slot], ctx->stream);
+	}
+	cudaEventSynchronize(ev[0]); cudaEventSynchronize(ev[1]);
+	cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+	return rc;
 }
 
 // ---------------------------------------------------------------- timers

@@ -50,6 +50,40 @@ struct HBuf {            // pinned host
 	template <class T> T *as() const { return (T*)p; }
 };
 
+// Pool of pinned host slabs that outlive single calls (the arrays of an mcb_index are handed to the caller and read by the
+// host for as long as the index lives).  cudaMallocHost costs ~0.2 ms per MiB, so slabs are recycled; the pool is
+// reference-counted because an index may be destroyed after its context.
+#include <mutex>
+struct McbPinnedPool {
+	std::mutex mu;
+	std::vector<HBuf> free_slabs;
+	int refs = 1;               // the context + every live index
+	bool ctx_alive = true;
+	HBuf take(size_t bytes) {
+		std::lock_guard<std::mutex> g(mu);
+		int best = -1;
+		for (size_t i = 0; i < free_slabs.size(); ++i)
+			if (free_slabs[i].cap >= bytes && (best < 0 || free_slabs[i].cap < free_slabs[best].cap)) best = (int)i;
+		HBuf b;
+		if (best >= 0) { b = free_slabs[best]; free_slabs.erase(free_slabs.begin() + best); }
+		++refs;
+		return b;                 // caller ensure()s the size (no-op when recycled)
+	}
+	// returns true when the pool itself must be deleted by the caller
+	bool give(HBuf b) {
+		std::lock_guard<std::mutex> g(mu);
+		if (ctx_alive && free_slabs.size() < 8) free_slabs.push_back(b); else b.release();
+		return --refs == 0;
+	}
+	bool close() {                // context is going away
+		std::lock_guard<std::mutex> g(mu);
+		ctx_alive = false;
+		for (auto &b : free_slabs) b.release();
+		free_slabs.clear();
+		return --refs == 0;
+	}
+};
+
 // ---------------------------------------------------------------- timers (CUDA events on ctx->stream)
 struct McbTimers {
 	struct Rec { int name; cudaEvent_t a, b; };
@@ -154,6 +188,7 @@ struct mcb_ctx {
 	DBuf d_x[4];                         // stage-2 extras
 	DBuf d_out[8];                       // kt_for_bucket outputs accumulated over the rounds
 	McbContigIndex cix;                  // stage-2 contig k-mer index (cached across threshold rounds)
+	McbPinnedPool *pool = nullptr;       // pinned slabs of the minimizer indexes
 	// host result buffers
 	HBuf h_cls, h_nrid, h_nrepl, h_noff, h_npos, h_nmask, h_counters, h_stage;
 	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref, h_sg, h_mi_cnt, h_mi;
@@ -254,6 +289,10 @@ int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const
 int mcb_add_bit_passes(std::vector<McbSortPass> &v, int word, int lo, int hi);  // digits covering bits [lo,hi)
 int mcb_exclusive_scan_u32(mcb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *d_total /* device u64, may be null */);
 int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t *d_total);
+
+// host -> device copy that is a true DMA whatever the source: page-locked sources go in one piece, pageable ones are staged
+// through pinned chunks filled by n_threads host threads while the previous chunk is in flight (mcb_api.cu)
+int mcb_h2d(mcb_ctx *ctx, void *dst, const void *src, size_t bytes, int n_threads);
 
 static inline unsigned mcb_grid_for(uint64_t n, unsigned block, unsigned cap = 0x7FFFFFFFu)
 {

@@ -173,12 +173,15 @@ struct mcb_index {
 	uint32_t *kstart = nullptr;    // [n_keys+1] posting offsets
 	uint64_t *post = nullptr;      // [n_post]   y values in the reference's order
 	uint32_t *ub = nullptr;        // [2^b+1]    key range of each bucket
+	HBuf slab;                     // one pinned allocation behind the four arrays (recycled through the context's pool)
+	McbPinnedPool *pool = nullptr;
 };
 
 extern "C" void mcb_idx_destroy(mcb_index *ix)
 {
 	if (!ix) return;
-	free(ix->keys); free(ix->kstart); free(ix->post); free(ix->ub);
+	if (ix->pool) { if (ix->pool->give(ix->slab)) delete ix->pool; }
+	else ix->slab.release();
 	delete ix;
 }
 
@@ -205,14 +208,29 @@ extern "C" const uint64_t *mcb_idx_get(const mcb_index *ix, uint64_t minier, int
 	return nullptr;
 }
 
+// carve the four host arrays out of one pinned slab
+static int idx_alloc_host(mcb_ctx *ctx, mcb_index *ix, uint64_t U, uint64_t n, int nb)
+{
+	const size_t o_keys = 0, o_post = o_keys + (U + 1) * 8, o_ks = o_post + (n + 1) * 8, o_ub = (o_ks + (U + 2) * 4 + 7) & ~(size_t)7, tot = o_ub + ((size_t)nb + 2) * 4;
+	ix->pool = ctx->pool;
+	ix->slab = ctx->pool->take(tot);
+	MCB_TRY(ix->slab.ensure(tot));
+	char *base = ix->slab.as<char>();
+	ix->keys = (uint64_t*)(base + o_keys); ix->post = (uint64_t*)(base + o_post); ix->kstart = (uint32_t*)(base + o_ks); ix->ub = (uint32_t*)(base + o_ub);
+	return MCB_OK;
+}
+
 static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mcb_index **out)
 {
 	// tuples are in d_scr[0] (device), bucket offsets on the host
 	const int b = ctx->prm.b, nb = 1 << b;
 	mcb_index *ix = new mcb_index(); ix->b = b; ix->n_post = n;
-	ix->ub = (uint32_t*)calloc((size_t)nb + 1, 4);
 	*out = ix;
-	if (n == 0) { ix->keys = (uint64_t*)calloc(1, 8); ix->kstart = (uint32_t*)calloc(2, 4); ix->post = (uint64_t*)calloc(1, 8); return MCB_OK; }
+	if (n == 0) {
+		MCB_TRY(idx_alloc_host(ctx, ix, 0, 0, nb));
+		memset(ix->ub, 0, ((size_t)nb + 1) * 4); ix->kstart[0] = 0;
+		return MCB_OK;
+	}
 	if (n >= 0xFFFFFFFFull) { mcb_set_error("index too large"); return MCB_EINVAL; }
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
 	MCB_TRY(ctx->d_scr[1].ensure(((size_t)nb + 1) * 8));
@@ -225,7 +243,7 @@ static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mc
 	mcb_tuple *dt = ctx->d_scr[0].as<mcb_tuple>();
 	{
 		McbSpan sp(ctx->tm, "h2d");
-		MCB_CUDA(cudaMemcpyAsync(ctx->d_scr[1].p, h_boff, ((size_t)nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+		MCB_TRY(mcb_h2d(ctx, ctx->d_scr[1].p, h_boff, ((size_t)nb + 1) * 8, 1));
 	}
 	{
 		McbSpan sp(ctx->tm, "idx_build");
@@ -244,8 +262,7 @@ static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mc
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	const uint64_t U = ctx->h_counters.as<unsigned long long>()[CT_SCRATCH_IDX];
 	ix->n_keys = U;
-	ix->keys = (uint64_t*)malloc(U * 8 + 8); ix->kstart = (uint32_t*)malloc((U + 1) * 4); ix->post = (uint64_t*)malloc(n * 8);
-	if (!ix->keys || !ix->kstart || !ix->post) { mcb_set_error("out of host memory"); return MCB_ENOMEM; }
+	MCB_TRY(idx_alloc_host(ctx, ix, U, n, nb));
 	{
 		McbSpan sp(ctx->tm, "d2h");
 		MCB_CUDA(cudaMemcpyAsync(ix->keys, ctx->d_scr[4].p, U * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -270,14 +287,14 @@ extern "C" int mcb_idx_build(mcb_ctx *ctx, const mcb_tuple *tuples, const uint64
 	MCB_TRY(ctx->d_scr[0].ensure(n * 16 + 16));
 	if (n) {
 		McbSpan sp(ctx->tm, "h2d");
-		MCB_CUDA(cudaMemcpyAsync(ctx->d_scr[0].p, tuples, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+		MCB_TRY(mcb_h2d(ctx, ctx->d_scr[0].p, tuples, n * 16, 4));
 	}
 	int r = idx_build_device(ctx, n, bucket_off, out);
 	if (r != MCB_OK) { mcb_idx_destroy(*out); *out = nullptr; }
 	return r;
 }
 
-extern "C" int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptrs, const uint64_t *cnt, mcb_index **out)
+extern "C" int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptrs, const uint64_t *cnt, int n_threads, mcb_index **out)
 {
 	if (!ctx || !out || !ptrs || !cnt) { mcb_set_error("mcb_idx_build_scattered: null argument"); return MCB_EINVAL; }
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
@@ -290,7 +307,16 @@ extern "C" int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptr
 	boff[nb] = n;
 	MCB_TRY(ctx->h_in0.ensure(n * 16 + 16));
 	mcb_tuple *flat = ctx->h_in0.as<mcb_tuple>();
-	for (int i = 0; i < nb; ++i) if (cnt[i]) memcpy(flat + boff[i], ptrs[i], cnt[i] * 16);
+	{   // gather the bucket arrays into one pinned block, n_threads host threads over contiguous bucket ranges
+		const int T = std::max(1, std::min(n_threads, (int)(n / 65536) + 1));
+		auto work = [&](int b0, int b1) { for (int i = b0; i < b1; ++i) if (cnt[i]) memcpy(flat + boff[i], ptrs[i], cnt[i] * 16); };
+		if (T == 1) work(0, nb);
+		else {
+			std::vector<std::thread> th;
+			for (int t = 0; t < T; ++t) th.emplace_back(work, (int)((int64_t)nb * t / T), (int)((int64_t)nb * (t + 1) / T));
+			for (auto &x : th) x.join();
+		}
+	}
 	MCB_TRY(ctx->d_counters.ensure(64 * 8));
 	MCB_TRY(ctx->d_scr[0].ensure(n * 16 + 16));
 	if (n) {

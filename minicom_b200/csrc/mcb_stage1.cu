@@ -446,6 +446,7 @@ static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_r
 	const int L = ctx->L, Wd = ctx->Wd, WS = ctx->WS;
 	const int pbase = L + ctx->prm.max_rounds;
 	ctx->n_reads = n; ctx->reads_loaded = false; ctx->bucket_done = false;
+	ctx->cix.valid = false;              // a new read set starts a new run: contigs of the previous one are never reused
 	MCB_TRY(ctx->d_packed.ensure((size_t)n * WS * 8 + 16));
 	MCB_TRY(ctx->d_cls.ensure(n + 16));
 	MCB_TRY(ctx->d_elemA.ensure((size_t)n * 16 + 16));
@@ -533,28 +534,9 @@ extern "C" int mcb_for_reads(mcb_ctx *ctx, const char *rows, uint64_t n, mcb_rea
 	if (!res || (n && !rows)) { mcb_set_error("mcb_for_reads: null argument"); return MCB_EINVAL; }
 	const size_t bytes = (size_t)n * ctx->L;
 	MCB_TRY(ctx->d_ascii.ensure(bytes + 16));
-	cudaPointerAttributes pa;
-	const bool pinned = cudaPointerGetAttributes(&pa, rows) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-	cudaGetLastError();
-	if (pinned) {   // page-locked source: one DMA, no staging
+	{
 		McbSpan sp(ctx->tm, "h2d");
-		MCB_CUDA(cudaMemcpyAsync(ctx->d_ascii.p, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
-	} else {
-		McbSpan sp(ctx->tm, "h2d");
-		// pageable source: stage through pinned chunks so the copies are true async DMA
-		const size_t CH = 32u << 20;
-		MCB_TRY(ctx->h_stage.ensure(2 * CH));
-		cudaEvent_t ev[2]; cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
-		int slot = 0;
-		for (size_t o = 0; o < bytes; o += CH, slot ^= 1) {
-			size_t len = std::min(CH, bytes - o);
-			char *st = ctx->h_stage.as<char>() + (size_t)slot * CH;
-			cudaEventSynchronize(ev[slot]);
-			memcpy(st, rows + o, len);
-			MCB_CUDA(cudaMemcpyAsync(ctx->d_ascii.as<char>() + o, st, len, cudaMemcpyHostToDevice, ctx->stream));
-			cudaEventRecord(ev[slot], ctx->stream);
-		}
-		cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+		MCB_TRY(mcb_h2d(ctx, ctx->d_ascii.p, rows, bytes, 4));
 	}
 	return mcb_for_reads_device(ctx, ctx->d_ascii.as<char>(), n, res);
 }
