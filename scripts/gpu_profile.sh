@@ -19,9 +19,9 @@ if [[ $STEPS == *launches* ]]; then
   echo "ncu launches rc=$?"
 fi
 if [[ $STEPS == *full* ]]; then
-  KREGEX=${KREGEX:-'regex:k_s2_|k_index_sort|k_consensus|k_pack_classify|k_sketch_lh|k_sort_scatter|k_sort_hist'}
+  KREGEX=${KREGEX:-'regex:k_s2_|k_index_sort|k_consensus|k_pack_classify|k_sketch_lh'}
   $CMD > $O/plain2_$TAG.log 2>&1 &&
-  ncu --target-processes application-only --set full --clock-control none --import-source on -k "$KREGEX" -c ${KCOUNT:-40} -o $O/prof_${WL}_$TAG -f $CMD > $O/ncu_full_$TAG.log 2>&1
+  ncu --target-processes application-only --set full --clock-control none -k "$KREGEX" -c ${KCOUNT:-40} -o $O/prof_${WL}_$TAG -f $CMD > $O/ncu_full_$TAG.log 2>&1
   echo "ncu full rc=$?"
   ncu -i $O/prof_${WL}_$TAG.ncu-rep --page raw --csv > $O/prof_${WL}_${TAG}_raw.csv 2> /dev/null
   ncu -i $O/prof_${WL}_$TAG.ncu-rep --page details --csv > $O/prof_${WL}_${TAG}_details.csv 2> /dev/null
