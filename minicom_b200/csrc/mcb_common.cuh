@@ -159,7 +159,9 @@ struct McbContigIndex {
 	DBuf cw;        // packed contigs, 2 bits per base, each contig padded to whole words + 1
 	DBuf pblk;      // u32[ref_bytes/512+1] contig holding base 512*i
 	DBuf ptab;      // u32[2^pbits+1] bucket ends of the k-mer table
-	DBuf ents;      // u64[n_entries] key<<30 | global base position, bucketed by a hash of the key
+	DBuf ents, ents2; // u64[n_entries] key<<30 | global base position, ordered by a hash of the key (double buffer of the sort)
+	unsigned long long *ents_sorted = nullptr;
+	DBuf eoff;      // u64[n_contigs+1] entry offsets (prefix sums of len-lt+1 over contigs with windows)
 };
 
 struct mcb_ctx {
@@ -198,15 +200,18 @@ struct mcb_ctx {
 
 // ---------------------------------------------------------------- integer helpers (host + device)
 // Invertible integer mix restricted to 2k bits (sketch.c:27-37).
+// The shift-add forms of the reference are multiplications modulo 2^64 (the mask is applied afterwards in both):
+//   ~key + (key<<21) = key*(2^21-1) - 1,  key + (key<<3) + (key<<8) = key*265,  key + (key<<2) + (key<<4) = key*21,
+//   key + (key<<31) = key*(2^31+1).  A 64x32-bit multiply is 2-3 instructions on the device, each shift-add chain 6-8.
 MCB_HD uint64_t mcb_hash64_hd(uint64_t key, uint64_t mask)
 {
-	key = (~key + (key << 21)) & mask;
+	key = (key * 0x1FFFFFull - 1ull) & mask;
 	key ^= key >> 24;
-	key = (key + (key << 3) + (key << 8)) & mask;
+	key = (key * 265ull) & mask;
 	key ^= key >> 14;
-	key = (key + (key << 2) + (key << 4)) & mask;
+	key = (key * 21ull) & mask;
 	key ^= key >> 28;
-	key = (key + (key << 31)) & mask;
+	key = (key * 0x80000001ull) & mask;
 	return key;
 }
 
@@ -282,10 +287,15 @@ MCB_HD uint64_t mcb_sketch_two_packed(const uint64_t *row, int L, int k, int *po
 	return best;
 }
 
+// Stage-2 contig table entries: lt-mer << 30 | global base position; buckets by a multiplicative hash of the lt-mer
+#define MCB_S2_POS_BITS 30
+MCB_HD uint32_t mcb_kmer_bucket(uint64_t key, int pbits) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - pbits)); }
+
 // ---------------------------------------------------------------- primitives (mcb_sort.cu)
 struct McbSortPass { int word; int shift; int bits; };  // word 0 = .x, 1 = .y
 int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const McbSortPass *passes, int n_passes,
                    ulonglong2 **sorted_out);
+int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long *b, uint64_t n, int pbits, unsigned long long **sorted_out);
 int mcb_add_bit_passes(std::vector<McbSortPass> &v, int word, int lo, int hi);  // digits covering bits [lo,hi)
 int mcb_exclusive_scan_u32(mcb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *d_total /* device u64, may be null */);
 int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t *d_total);

@@ -16,14 +16,20 @@
 #define SORT_STEPS 8
 #define SORT_TILE (SORT_THREADS * SORT_STEPS)
 
-__device__ __forceinline__ unsigned digit_of(const ulonglong2 &e, int word, int shift, unsigned mask)
-{
-	unsigned long long v = word ? e.y : e.x;
-	return (unsigned)(v >> shift) & mask;
-}
+// digit extractors: (a) a bit field of one word of a 16-byte element, (b) a bit field of the bucket hash of a Stage-2
+// contig-table entry (lt-mer<<30 | position)
+struct DigitPair {
+	int word, shift; unsigned mask;
+	__device__ __forceinline__ unsigned operator()(const ulonglong2 &e) const { unsigned long long v = word ? e.y : e.x; return (unsigned)(v >> shift) & mask; }
+};
+struct DigitKmer {
+	int pbits, shift; unsigned mask;
+	__device__ __forceinline__ unsigned operator()(const unsigned long long &e) const { return (mcb_kmer_bucket(e >> MCB_S2_POS_BITS, pbits) >> shift) & mask; }
+};
 
+template <class E, class D>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_hist(const ulonglong2 *__restrict__ in, uint64_t n, int word, int shift, unsigned mask, uint32_t *__restrict__ hist, unsigned nblocks)
+k_sort_hist(const E *__restrict__ in, uint64_t n, D digit, uint32_t *__restrict__ hist, unsigned nblocks)
 {
 	__shared__ unsigned h[256];
 	h[threadIdx.x] = 0;
@@ -32,29 +38,29 @@ k_sort_hist(const ulonglong2 *__restrict__ in, uint64_t n, int word, int shift, 
 #pragma unroll
 	for (int s = 0; s < SORT_STEPS; ++s) {
 		uint64_t i = base + (uint64_t)s * SORT_THREADS + threadIdx.x;
-		if (i < n) atomicAdd(&h[digit_of(in[i], word, shift, mask)], 1u);
+		if (i < n) atomicAdd(&h[digit(in[i])], 1u);
 	}
 	__syncthreads();
 	hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
+template <class E, class D>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_scatter(const ulonglong2 *__restrict__ in, ulonglong2 *__restrict__ out, uint64_t n, int word, int shift, unsigned mask,
-               const uint32_t *__restrict__ hist_scanned, unsigned nblocks)
+k_sort_scatter(const E *__restrict__ in, E *__restrict__ out, uint64_t n, D digit, const uint32_t *__restrict__ hist_scanned, unsigned nblocks)
 {
 	__shared__ unsigned wcnt[SORT_WARPS][256];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
 	__syncthreads();
 	const uint64_t wbase = (uint64_t)blockIdx.x * SORT_TILE + (uint64_t)w * (32 * SORT_STEPS);
-	ulonglong2 e[SORT_STEPS];
+	E e[SORT_STEPS];
 	unsigned dg[SORT_STEPS];
 #pragma unroll
 	for (int s = 0; s < SORT_STEPS; ++s) {
 		uint64_t i = wbase + s * 32 + lane;
 		if (i < n) {
 			e[s] = in[i];
-			dg[s] = digit_of(e[s], word, shift, mask);
+			dg[s] = digit(e[s]);
 			atomicAdd(&wcnt[w][dg[s]], 1u);
 		} else dg[s] = 256u;
 	}
@@ -185,11 +191,35 @@ int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const
 	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>();
 	ulonglong2 *src = a, *dst = b;
 	for (int p = 0; p < n_passes; ++p) {
-		unsigned mask = (1u << passes[p].bits) - 1u;
-		MCB_LAUNCH(ctx, "sort_hist", k_sort_hist, (unsigned)nb, SORT_THREADS, 0, src, n, passes[p].word, passes[p].shift, mask, hist, (unsigned)nb);
+		DigitPair dg = { passes[p].word, passes[p].shift, (1u << passes[p].bits) - 1u };
+		MCB_LAUNCH(ctx, "sort_hist", (k_sort_hist<ulonglong2, DigitPair>), (unsigned)nb, SORT_THREADS, 0, src, n, dg, hist, (unsigned)nb);
 		MCB_TRY(mcb_exclusive_scan_u32(ctx, hist, nb * 256, nullptr));
-		MCB_LAUNCH(ctx, "sort_scatter", k_sort_scatter, (unsigned)nb, SORT_THREADS, 0, src, dst, n, passes[p].word, passes[p].shift, mask, hist, (unsigned)nb);
+		MCB_LAUNCH(ctx, "sort_scatter", (k_sort_scatter<ulonglong2, DigitPair>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb);
 		ulonglong2 *t = src; src = dst; dst = t;
+	}
+	*sorted_out = src;
+	return MCB_OK;
+}
+
+// Stage-2 contig table: order the 8-byte entries by the `pbits`-bit bucket hash of their lt-mer (order inside a bucket is free)
+int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long *b, uint64_t n, int pbits, unsigned long long **sorted_out)
+{
+	*sorted_out = a;
+	if (n <= 1) return MCB_OK;
+	uint64_t nb = (n + SORT_TILE - 1) / SORT_TILE;
+	if (nb > 0x7FFFFFFFull) { mcb_set_error("sort input too large"); return MCB_EINVAL; }
+	MCB_TRY(ctx->d_sort_hist.ensure(nb * 256 * sizeof(uint32_t)));
+	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>();
+	unsigned long long *src = a, *dst = b;
+	const int n_passes = (pbits + 7) / 8;
+	for (int p = 0, lo = 0; p < n_passes; ++p) {
+		const int bits = (pbits - lo + (n_passes - p) - 1) / (n_passes - p);      // spread the bits evenly over the passes
+		DigitKmer dg = { pbits, lo, (1u << bits) - 1u };
+		MCB_LAUNCH(ctx, "s2_kmer_sort_hist", (k_sort_hist<unsigned long long, DigitKmer>), (unsigned)nb, SORT_THREADS, 0, src, n, dg, hist, (unsigned)nb);
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, hist, nb * 256, nullptr));
+		MCB_LAUNCH(ctx, "s2_kmer_sort_scatter", (k_sort_scatter<unsigned long long, DigitKmer>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb);
+		unsigned long long *t = src; src = dst; dst = t;
+		lo += bits;
 	}
 	*sorted_out = src;
 	return MCB_OK;

@@ -56,23 +56,52 @@ k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, int L, int
 	const uint64_t rid = first + t;
 	bool sketched = false, bad = false, degenerate = false, hasn = false;
 	if (t < nrow) {
-		const unsigned char *row = rows + (size_t)t * L;
+		// Four characters per step, SIMD inside a 32-bit register.  (c>>1)&3 maps A,C,T,G (0x41,0x43,0x54,0x47) to 0,1,2,3;
+		// x ^ (x>>1) turns that into the reference's codes A0 C1 G2 T3 (seq_nt4_table).  A character is accepted iff it
+		// is 'N' or equals "ACGT"[code]; everything else is rejected (see mcb_code_of).
+		const uint32_t *rows32 = (const uint32_t*)rows;
+		const unsigned rowb = (unsigned)t * (unsigned)L;
 		McbCounts q = {0, 0, 0, 0, 0};
 		uint64_t nmw[8];
+		unsigned badacc = 0;
 #pragma unroll
 		for (int w = 0; w < 8; ++w) {
 			uint64_t pw = 0, nw = 0;
 			if (w < Wd) {
-				int lim = L - w * 32; if (lim > 32) lim = 32;
-				for (int j = 0; j < lim; ++j) {
-					unsigned c = mcb_code_of(row[w * 32 + j]);
-					q.a += c == 0; q.c += c == 1; q.g += c == 2; q.t += c == 3; q.n += c == 4; bad |= c == 5;
-					if (c < 4) pw |= (uint64_t)c << (2 * j); else nw |= 1ull << (2 * j);
+				const int lim = min(32, L - w * 32);
+#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					if (j * 4 < lim) {
+						const unsigned a = rowb + (unsigned)(w * 32 + j * 4);
+						const unsigned ai = a >> 2, sh = (a & 3u) * 8u;
+						unsigned v = __funnelshift_r(rows32[ai], rows32[ai + 1], sh);          // staging buffer is padded by 8 bytes
+						const int nb = lim - j * 4;                                            // bytes of this word that belong to the read
+						if (nb < 4) v = (v & (0xFFFFFFFFu >> (8 * (4 - nb)))) | (0x41414141u << (8 * nb));   // pad with 'A': code 0, valid
+						const unsigned x = (v >> 1) & 0x03030303u;
+						unsigned code = x ^ ((x >> 1) & 0x01010101u);
+						const unsigned tn = v ^ 0x4E4E4E4Eu;
+						const unsigned isn = ~(((tn & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | tn | 0x7F7F7F7Fu);            // 0x80 in every byte that is 'N'
+						const unsigned sel = (code & 0x3u) | ((code >> 4) & 0x30u) | ((code >> 8) & 0x300u) | ((code >> 12) & 0x3000u);
+						const unsigned df = __byte_perm(0x54474341u, 0u, sel) ^ v;
+						badacc |= (((df & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | df) & 0x80808080u & ~isn;
+						const unsigned n1 = isn >> 7;
+						code &= ~(n1 * 3u);
+						unsigned pc = code | (code >> 6); pc = (pc | (pc >> 12)) & 0xFFu;
+						unsigned pn = n1 | (n1 >> 6); pn = (pn | (pn >> 12)) & 0xFFu;
+						if (nb < 4) pn &= (1u << (2 * nb)) - 1u;
+						pw |= (uint64_t)pc << (8 * j); nw |= (uint64_t)pn << (8 * j);
+					}
 				}
+				const uint64_t valid = lim == 32 ? 0x5555555555555555ull : (0x5555555555555555ull & ((1ull << (2 * lim)) - 1ull));
+				const uint64_t lo = pw & 0x5555555555555555ull, hi = (pw >> 1) & 0x5555555555555555ull;
+				const int nn = __popcll(nw), nt = __popcll(lo & hi), ng = __popcll(hi & ~lo), nc = __popcll(lo & ~hi);
+				q.n += nn; q.t += nt; q.g += ng; q.c += nc; q.a += lim - nn - nt - ng - nc;
+				(void)valid;
 				sp[t][w] = pw;
 			}
 			nmw[w] = nw;
 		}
+		bad = badacc != 0;
 		int repl;
 		int c = mcb_classify(q, L, e, &repl);
 		hasn = q.n > 0;
@@ -418,8 +447,83 @@ __global__ void k_scatter_clusters(const uint32_t *__restrict__ gstart, uint64_t
 }
 
 // ---------------------------------------------------------------- K4: first m windowed minimizers of each new seed contig
-__global__ void k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count,
-                            int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
+// mm_sketch_lh_ori (sketch.c:116-165) is a sequential scan with data-dependent tie rules, so one thread walks one contig;
+// the 64 contigs of a CTA are adjacent in cl_ref, so their characters are staged into shared memory with coalesced loads,
+// and the w-slot ring buffer (hash + position/strand per slot) lives in shared memory too, slot-major so that the lanes
+// of a warp hit different banks.  The walk stops after m outputs (kthread_bucket.c:463).
+#define LH_THREADS 64
+struct LhRingSmem {
+	uint64_t *x; uint32_t *ps; int tid;
+	__device__ __forceinline__ void set(int j, uint64_t hx, uint32_t p) { x[j * LH_THREADS + tid] = hx; ps[j * LH_THREADS + tid] = p; }
+	__device__ __forceinline__ uint64_t hx(int j) const { return x[j * LH_THREADS + tid]; }
+	__device__ __forceinline__ uint32_t p(int j) const { return ps[j * LH_THREADS + tid]; }
+};
+
+__global__ void __launch_bounds__(LH_THREADS)
+k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count,
+            int w, int k, int m, int span_cap, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
+{
+	extern __shared__ __align__(16) unsigned char lh_smem[];
+	uint64_t *rx = (uint64_t*)lh_smem;                                        // [w][LH_THREADS]
+	uint32_t *rp = (uint32_t*)(rx + (size_t)w * LH_THREADS);                  // [w][LH_THREADS]
+	char *chars = (char*)(rp + (size_t)w * LH_THREADS);                       // [span_cap]
+	const uint64_t i0 = (uint64_t)blockIdx.x * LH_THREADS;
+	const int nloc = (int)min((uint64_t)LH_THREADS, cl_count - i0);
+	const uint64_t span0 = cl_ref_off[cl_first + i0], span1 = cl_ref_off[cl_first + i0 + nloc];
+	const bool staged = span1 - span0 <= (uint64_t)span_cap;
+	if (staged) for (uint64_t q = threadIdx.x; q < span1 - span0; q += LH_THREADS) chars[q] = cl_ref[span0 + q];
+	__syncthreads();
+	if ((int)threadIdx.x >= nloc) return;
+	const uint64_t c = cl_first + i0 + threadIdx.x;
+	const uint64_t b = cl_ref_off[c], e = cl_ref_off[c + 1];
+	const char *str = staged ? chars + (b - span0) : cl_ref + b;
+	const int len = (int)(e - b);
+	const uint32_t rid = (uint32_t)(c << 8);
+	LhRingSmem ring; ring.x = rx; ring.ps = rp; ring.tid = threadIdx.x;
+	mcb_tuple *out = mi + c * m;
+	int n_out = 0;
+	const uint64_t mask = (1ull << (2 * k)) - 1, shift1 = 2 * (k - 1);
+	uint64_t fw = 0, rv = 0, mn_x = ~0ull; uint32_t mn_p = ~0u;
+	int l = 0, bp = 0, mp = 0;
+#define LH_EMIT(hx_, p_) do { if (n_out < m) { mcb_tuple t_; t_.x = (hx_); t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } while (0)
+	for (int j = 0; j < w; ++j) ring.set(j, ~0ull, ~0u);
+	for (int i = 0; i < len && n_out < m; ++i) {
+		const unsigned cc = mcb_code_of((unsigned char)str[i]);           // consensus strings are upper-case ACGT (invert_code_rule)
+		uint64_t ix = ~0ull; uint32_t ip = ~0u;
+		if (cc < 4) {
+			fw = (fw << 2 | cc) & mask;
+			rv = (rv >> 2) | ((3ull ^ cc) << shift1);
+			if (fw == rv) continue;
+			const int z = fw < rv ? 0 : 1;
+			if (++l >= k) { ix = mcb_hash64_hd(z ? rv : fw, mask); ip = (uint32_t)i << 1 | (uint32_t)z; }
+		} else l = 0;
+		ring.set(bp, ix, ip);
+		if (l == w + k - 1) {
+			for (int j = bp + 1; j < w; ++j) if (mn_x == ring.hx(j) && ring.p(j) != mn_p) LH_EMIT(ring.hx(j), ring.p(j));
+			for (int j = 0; j < bp; ++j) if (mn_x == ring.hx(j) && ring.p(j) != mn_p) LH_EMIT(ring.hx(j), ring.p(j));
+		}
+		if (ix <= mn_x) {
+			if (l >= w + k) LH_EMIT(mn_x, mn_p);
+			mn_x = ix; mn_p = ip; mp = bp;
+		} else if (bp == mp) {
+			if (l >= w + k - 1) LH_EMIT(mn_x, mn_p);
+			mn_x = ~0ull;
+			for (int j = bp + 1; j < w; ++j) { uint64_t v = ring.hx(j); if (mn_x >= v) { mn_x = v; mn_p = ring.p(j); mp = j; } }
+			for (int j = 0; j <= bp; ++j) { uint64_t v = ring.hx(j); if (mn_x >= v) { mn_x = v; mn_p = ring.p(j); mp = j; } }
+			if (l >= w + k - 1) {
+				for (int j = bp + 1; j < w; ++j) if (mn_x == ring.hx(j) && mn_p != ring.p(j)) LH_EMIT(ring.hx(j), ring.p(j));
+				for (int j = 0; j <= bp; ++j) if (mn_x == ring.hx(j) && mn_p != ring.p(j)) LH_EMIT(ring.hx(j), ring.p(j));
+			}
+		}
+		if (++bp == w) bp = 0;
+	}
+	if (n_out < m && mn_x != ~0ull) LH_EMIT(mn_x, mn_p);
+#undef LH_EMIT
+	mi_cnt[c] = (uint8_t)(n_out < m ? n_out : m);
+}
+// fallback for windows too wide for shared memory: ring buffer in local memory
+__global__ void k_sketch_lh_local(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count,
+                                  int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
 {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= cl_count) return;
@@ -458,7 +562,7 @@ static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_r
 	{
 		McbSpan sp(ctx->tm, "for_reads");
 		if (n) {
-			size_t smem = RD_THREADS * 9 * sizeof(uint64_t) + (((size_t)RD_THREADS * L + 15) & ~(size_t)15);
+			size_t smem = RD_THREADS * 9 * sizeof(uint64_t) + (((size_t)RD_THREADS * L + 15) & ~(size_t)15) + 16;
 			MCB_LAUNCH(ctx, "pack_classify_sketch", k_pack_classify_sketch, mcb_grid_for(n, RD_THREADS), RD_THREADS, smem,
 			           d_rows, n, L, Wd, WS, ctx->prm.k, ctx->prm.diff_threshold, pbase,
 			           ctx->d_packed.as<uint64_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
@@ -743,9 +847,18 @@ extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)
 			// ---- K4: first m minimizers of each new seed contig (window rw, k = reads->k; kthread_bucket.c:458)
 			MCB_TRY(grow_preserve(ctx, d_mi, tot_cl * m * 16, (tot_cl + n_cl_new) * m * 16 + 16));
 			MCB_TRY(grow_preserve(ctx, d_micnt, tot_cl, tot_cl + n_cl_new + 16));
-			if (n_cl_new)
-				MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh, mcb_grid_for(n_cl_new, 64), 64, 0, d_cl_ref.as<char>(), d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new,
-				           ctx->prm.rw, k, m, d_mi.as<mcb_tuple>(), d_micnt.as<uint8_t>());
+			if (n_cl_new) {
+				const int rw = ctx->prm.rw;
+				const int span_cap = ((LH_THREADS * (2 * L + 2 * max_rounds + 8)) + 15) & ~15;
+				const size_t lh_smem = (size_t)rw * LH_THREADS * 12 + span_cap;
+				if (lh_smem <= 160 * 1024) {
+					if (lh_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_sketch_lh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh_smem));
+					MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh_smem, d_cl_ref.as<char>(), d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new,
+					           rw, k, m, span_cap, d_mi.as<mcb_tuple>(), d_micnt.as<uint8_t>());
+				} else
+					MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh_local, mcb_grid_for(n_cl_new, 64), 64, 0, d_cl_ref.as<char>(), d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new,
+					           rw, k, m, d_mi.as<mcb_tuple>(), d_micnt.as<uint8_t>());
+			}
 			tot_cl += n_cl_new; tot_mem += n_mem_new; tot_ref += n_ref_new; tot_sg += n_sg_new;
 			// ---- rejected reads go to the next round with a shorter k-mer (kthread_bucket.c:205-212,488-496)
 			if (!is_last && n_resk) {

@@ -6,8 +6,9 @@
 // change between rounds (preprocess.c:197-232), so this implementation turns it around:
 //
 //   once per contig set   K5a k_s2_pack_refs    2-bit packed contigs
-//                         K5b k_s2_kmer_hist/fill  every lt-mer of every contig (lt = 17, or 11 for L <= 80) -> a bucketed
-//                                               table (counting sort on a hash of the lt-mer): entry = lt-mer<<30 | position
+//                         K5b k_s2_kmer_emit    every lt-mer of every contig (lt = 17, or 11 for L <= 80) as an 8-byte entry
+//                                               lt-mer<<30 | position, radix-sorted by a hash of the lt-mer into 2^p buckets
+//                                               (mcb_radix_sort_kmers) + k_s2_bucket_ends
 //   every round           K6  k_s2_singles      singleRead2bitset (bbhashdict.c:127-227): 2-bit singles, near-poly-A/T
 //                                               diversion, and a count-min sketch of the dictionary bins (bin sizes matter:
 //                                               the reference scans only the last `maxsearch` entries of a bin, :388)
@@ -30,7 +31,7 @@
 #include <algorithm>
 
 #define S2_MAXD 16
-#define S2_POS_BITS 30
+#define S2_POS_BITS MCB_S2_POS_BITS
 #define S2_POS_MASK ((1ull << S2_POS_BITS) - 1)
 #define S2_BLK_SHIFT 9
 struct S2Geom {
@@ -56,7 +57,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t k)
 	k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
 	return k;
 }
-__device__ __forceinline__ uint32_t kmer_bucket(uint64_t key, int pbits) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - pbits)); }
+__device__ __forceinline__ uint32_t kmer_bucket(uint64_t key, int pbits) { return mcb_kmer_bucket(key, pbits); }
 
 // encode_byte (kthread_hash_realign.c:283-314) on a mismatch pattern given as XOR words, positions ascending.
 // Reproduces the missing `eq_char_num = 0` of the literal branch (:301-305).
@@ -115,32 +116,47 @@ __global__ void k_s2_same(const uint64_t *__restrict__ a, const uint64_t *__rest
 }
 
 // ---------------------------------------------------------------- K5b contig lt-mer table
-// One thread per packed word: the 32 lt-mers that START in it.  FILL=false counts bucket sizes, FILL=true places entries
-// (tab holds bucket starts on entry and bucket ends on exit).
-template <bool FILL>
+// One thread per packed word finds its contig; the warp then walks its 32 words together, lane j writing the lt-mer that
+// starts at base j of the word, so every store instruction covers 32 consecutive entries.
 __global__ void __launch_bounds__(256)
-k_s2_kmers(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_off, const uint64_t *__restrict__ ref_off, uint64_t n_contigs, uint64_t total_words,
-           int L, int lt, int pbits, uint32_t *__restrict__ tab, unsigned long long *__restrict__ ents)
+k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_off, const uint64_t *__restrict__ ref_off, const uint64_t *__restrict__ ent_off,
+               uint64_t n_contigs, uint64_t total_words, int L, int lt, unsigned long long *__restrict__ ents)
 {
-	uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= total_words) return;
-	uint64_t lo = 0, hi = n_contigs;
-	while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (cw_off[mid] <= q) lo = mid; else hi = mid; }
-	const uint64_t c = lo, wq = q - cw_off[c];
-	const uint64_t base = ref_off[c], len = ref_off[c + 1] - base;
-	if (len < (uint64_t)L || wq * 32 + lt > len) return;            // contigs shorter than a read have no windows
-	const uint64_t w0 = cw[q], w1 = cw[q + 1];
-	const uint64_t kmask = (1ull << (2 * lt)) - 1;
-	const int nstart = (int)min((uint64_t)32, len - lt + 1 - wq * 32);
-	for (int j = 0; j < nstart; ++j) {
-		uint64_t key = ((w0 >> (2 * j)) | (j ? w1 << (64 - 2 * j) : 0ull)) & kmask;
-		uint32_t b = kmer_bucket(key, pbits);
-		if (!FILL) atomicAdd(&tab[b], 1u);
-		else {
-			uint32_t slot = atomicAdd(&tab[b], 1u);
-			ents[slot] = (key << S2_POS_BITS) | (base + wq * 32 + j);
+	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	uint64_t w0 = 0, w1 = 0, dst = 0, pos0 = 0; int nstart = 0;
+	if (q < total_words) {
+		uint64_t lo = 0, hi = n_contigs;
+		while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (cw_off[mid] <= q) lo = mid; else hi = mid; }
+		const uint64_t c = lo, wq = q - cw_off[c];
+		const uint64_t base = ref_off[c], len = ref_off[c + 1] - base;
+		if (len >= (uint64_t)L && wq * 32 + lt <= len) {                 // contigs shorter than a read have no windows
+			w0 = cw[q]; w1 = cw[q + 1];
+			nstart = (int)min((uint64_t)32, len - lt + 1 - wq * 32);
+			dst = ent_off[c] + wq * 32; pos0 = base + wq * 32;
 		}
 	}
+	const uint64_t kmask = (1ull << (2 * lt)) - 1;
+	for (int t = 0; t < 32; ++t) {
+		const int cnt = __shfl_sync(0xFFFFFFFFu, nstart, t);
+		if (cnt == 0) continue;
+		const uint64_t a = __shfl_sync(0xFFFFFFFFu, w0, t), b = __shfl_sync(0xFFFFFFFFu, w1, t);
+		const uint64_t d = __shfl_sync(0xFFFFFFFFu, dst, t), p = __shfl_sync(0xFFFFFFFFu, pos0, t);
+		if (lane < cnt) {
+			const uint64_t key = ((a >> (2 * lane)) | (lane ? b << (64 - 2 * lane) : 0ull)) & kmask;
+			ents[d + lane] = (key << S2_POS_BITS) | (p + lane);
+		}
+	}
+}
+// entries are ordered by bucket: ptab[b] = end of bucket b (= start of bucket b+1)
+__global__ void k_s2_bucket_ends(const unsigned long long *__restrict__ ents, uint64_t n, int pbits, uint32_t *__restrict__ ptab)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t b = kmer_bucket(ents[i] >> S2_POS_BITS, pbits);
+	const uint32_t bn = i + 1 < n ? kmer_bucket(ents[i + 1] >> S2_POS_BITS, pbits) : (1u << pbits);
+	if (i == 0) for (uint32_t q = 0; q < b; ++q) ptab[q] = 0;
+	for (uint32_t q = b; q < bn; ++q) ptab[q] = (uint32_t)(i + 1);
 }
 
 // ---------------------------------------------------------------- K6
@@ -370,15 +386,16 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	// ---- host-side offsets
 	uint64_t total_words = 0, n_windows = 0, n_entries = 0;
 	MCB_TRY(ctx->h_in0.ensure((n_contigs + 1) * 8)); MCB_TRY(ctx->h_in1.ensure((n_contigs + 1) * 8));
-	uint64_t *cwo = ctx->h_in0.as<uint64_t>(), *wo = ctx->h_in1.as<uint64_t>();
+	MCB_TRY(ctx->h_in2.ensure((n_contigs + 1) * 8));
+	uint64_t *cwo = ctx->h_in0.as<uint64_t>(), *wo = ctx->h_in1.as<uint64_t>(), *eo = ctx->h_in2.as<uint64_t>();
 	for (uint64_t c = 0; c < n_contigs; ++c) {
 		if (ref_off[c + 1] < ref_off[c]) { mcb_set_error("mcb_realign: ref_off is not monotonic"); return MCB_EINVAL; }
 		const uint64_t len = ref_off[c + 1] - ref_off[c];
-		cwo[c] = total_words; wo[c] = n_windows;
+		cwo[c] = total_words; wo[c] = n_windows; eo[c] = n_entries;
 		total_words += (len + 31) / 32 + 1;
 		if (len >= (uint64_t)L) { n_windows += len - L + 1; n_entries += len - lt + 1; }
 	}
-	cwo[n_contigs] = total_words + 1; wo[n_contigs] = n_windows;   // +1 guard word: loaders read one word ahead
+	cwo[n_contigs] = total_words + 1; wo[n_contigs] = n_windows; eo[n_contigs] = n_entries;   // +1 guard word: loaders read one word ahead
 	if (n_windows >= (1ull << 58)) { mcb_set_error("too many windows"); return MCB_EINVAL; }
 	// ---- same contigs as last time?  (compare on the device: the strings have to be uploaded to find out)
 	const bool maybe_same = cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L;
@@ -405,15 +422,17 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	}
 	// ---- build
 	cx.n_contigs = n_contigs; cx.ref_bytes = ref_bytes; cx.total_words = total_words; cx.n_windows = n_windows; cx.n_entries = n_entries; cx.L = L; cx.lt = lt;
-	int pbits = 10; while (pbits < 26 && pbits < 2 * lt && (2ull << pbits) < n_entries) ++pbits;                 // about 1..2 entries per bucket
+	int pbits = 10; while (pbits < 24 && pbits < 2 * lt && (8ull << pbits) < n_entries) ++pbits;                 // 4..8 entries (1-2 sectors) per bucket
 	cx.pbits = pbits;
 	const uint64_t nbk = 1ull << pbits, n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
 	MCB_TRY(cx.cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.wo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.cw.ensure((total_words + 2) * 8));
-	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16)); MCB_TRY(cx.ptab.ensure((nbk + 1) * 4)); MCB_TRY(cx.ents.ensure(n_entries * 8 + 16));
+	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16)); MCB_TRY(cx.ptab.ensure((nbk + 1) * 4)); MCB_TRY(cx.ents.ensure(n_entries * 8 + 16)); MCB_TRY(cx.ents2.ensure(n_entries * 8 + 16));
+	MCB_TRY(cx.eoff.ensure((n_contigs + 1) * 8));
 	{
 		McbSpan sp(ctx->tm, "h2d");
 		MCB_CUDA(cudaMemcpyAsync(cx.cwo.p, cwo, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
 		MCB_CUDA(cudaMemcpyAsync(cx.wo.p, wo, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+		MCB_CUDA(cudaMemcpyAsync(cx.eoff.p, eo, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
 	}
 	if (n_contigs == 0 || n_windows == 0) { cx.valid = true; return MCB_OK; }
 	McbSpan sp(ctx->tm, "realign");
@@ -421,12 +440,11 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	MCB_LAUNCH(ctx, "s2_pack_refs", k_s2_pack_refs, mcb_grid_for(total_words, 256), 256, 0, cx.refs.as<char>(), cx.roff.as<uint64_t>(), cx.cwo.as<uint64_t>(),
 	           n_contigs, total_words, cx.cw.as<uint64_t>(), dc);
 	MCB_LAUNCH(ctx, "s2_pos_blocks", k_s2_pos_blocks, mcb_grid_for(n_blocks, 256), 256, 0, cx.roff.as<uint64_t>(), n_contigs, n_blocks, cx.pblk.as<uint32_t>());
+	MCB_LAUNCH(ctx, "s2_kmer_emit", k_s2_kmer_emit, mcb_grid_for(total_words, 256), 256, 0, cx.cw.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.roff.as<uint64_t>(),
+	           cx.eoff.as<uint64_t>(), n_contigs, total_words, L, lt, cx.ents.as<unsigned long long>());
+	MCB_TRY(mcb_radix_sort_kmers(ctx, cx.ents.as<unsigned long long>(), cx.ents2.as<unsigned long long>(), n_entries, pbits, &cx.ents_sorted));
 	MCB_CUDA(cudaMemsetAsync(cx.ptab.p, 0, (nbk + 1) * 4, ctx->stream));
-	MCB_LAUNCH(ctx, "s2_kmer_hist", k_s2_kmers<false>, mcb_grid_for(total_words, 256), 256, 0, cx.cw.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.roff.as<uint64_t>(),
-	           n_contigs, total_words, L, lt, pbits, cx.ptab.as<uint32_t>(), cx.ents.as<unsigned long long>());
-	MCB_TRY(mcb_exclusive_scan_u32(ctx, cx.ptab.as<uint32_t>(), nbk + 1, nullptr));
-	MCB_LAUNCH(ctx, "s2_kmer_fill", k_s2_kmers<true>, mcb_grid_for(total_words, 256), 256, 0, cx.cw.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.roff.as<uint64_t>(),
-	           n_contigs, total_words, L, lt, pbits, cx.ptab.as<uint32_t>(), cx.ents.as<unsigned long long>());
+	if (n_entries) MCB_LAUNCH(ctx, "s2_bucket_ends", k_s2_bucket_ends, mcb_grid_for(n_entries, 256), 256, 0, cx.ents_sorted, n_entries, pbits, cx.ptab.as<uint32_t>());
 	cx.valid = true;
 	return MCB_OK;
 }
@@ -492,7 +510,7 @@ extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const c
 	           ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->n_nreads, ctx->n_reads,
 	           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, dc);
 	S2Join jn; memset(&jn, 0, sizeof jn);
-	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents.as<unsigned long long>(); jn.pbits = cx.pbits;
+	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents_sorted; jn.pbits = cx.pbits;
 	jn.pblk = cx.pblk.as<uint32_t>(); jn.ref_off = cx.roff.as<uint64_t>(); jn.cw = cx.cw.as<uint64_t>(); jn.cw_off = cx.cwo.as<uint64_t>(); jn.woff = cx.wo.as<uint64_t>();
 	jn.claim = claim; jn.counters = dc;
 	MCB_CUDA(cudaMemsetAsync(claim, 0xFF, S * 8, ctx->stream));
