@@ -44,15 +44,22 @@ k_sort_hist(const E *__restrict__ in, uint64_t n, D digit, uint32_t *__restrict_
 	hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
+// Stable scatter of one tile.  Elements are first ranked inside the tile (warp-private digit counters +
+// __match_any_sync), parked in shared memory in digit order, and then written out so that consecutive threads write
+// consecutive addresses of a digit's run: global stores are whole sectors instead of 32 scattered 8/16-byte pieces.
 template <class E, class D>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_scatter(const E *__restrict__ in, E *__restrict__ out, uint64_t n, D digit, const uint32_t *__restrict__ hist_scanned, unsigned nblocks)
 {
 	__shared__ unsigned wcnt[SORT_WARPS][256];
+	__shared__ unsigned gbase[256];
+	__shared__ unsigned wsum[SORT_WARPS];
+	__shared__ E stage[SORT_TILE];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
 	__syncthreads();
-	const uint64_t wbase = (uint64_t)blockIdx.x * SORT_TILE + (uint64_t)w * (32 * SORT_STEPS);
+	const uint64_t tbase = (uint64_t)blockIdx.x * SORT_TILE;
+	const uint64_t wbase = tbase + (uint64_t)w * (32 * SORT_STEPS);
 	E e[SORT_STEPS];
 	unsigned dg[SORT_STEPS];
 #pragma unroll
@@ -65,11 +72,23 @@ k_sort_scatter(const E *__restrict__ in, E *__restrict__ out, uint64_t n, D digi
 		} else dg[s] = 256u;
 	}
 	__syncthreads();
-	{   // per digit: turn per-warp counts into absolute output bases
-		unsigned d = threadIdx.x;
-		unsigned run = hist_scanned[(uint64_t)d * nblocks + blockIdx.x];
+	{   // thread d owns digit d: tile-local start of the digit (exclusive scan over the 256 digit totals), per-warp starts, global base
+		const unsigned d = threadIdx.x;
+		unsigned c[SORT_WARPS], tot = 0;
 #pragma unroll
-		for (int ww = 0; ww < SORT_WARPS; ++ww) { unsigned t = wcnt[ww][d]; wcnt[ww][d] = run; run += t; }
+		for (int ww = 0; ww < SORT_WARPS; ++ww) { c[ww] = wcnt[ww][d]; tot += c[ww]; }
+		unsigned inc = tot;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+		if (lane == 31) wsum[w] = inc;
+		__syncthreads();
+		unsigned wb = 0;
+#pragma unroll
+		for (int ww = 0; ww < SORT_WARPS; ++ww) if (ww < w) wb += wsum[ww];
+		unsigned run = wb + inc - tot;                           // tile-local start of digit d
+		gbase[d] = hist_scanned[(uint64_t)d * nblocks + blockIdx.x] - run;
+#pragma unroll
+		for (int ww = 0; ww < SORT_WARPS; ++ww) { wcnt[ww][d] = run; run += c[ww]; }
 	}
 	__syncthreads();
 	const unsigned lt = (1u << lane) - 1u;
@@ -82,7 +101,13 @@ k_sort_scatter(const E *__restrict__ in, E *__restrict__ out, uint64_t n, D digi
 		__syncwarp();
 		if (valid && lane == (__ffs(peers) - 1)) wcnt[w][dg[s]] = base + __popc(peers);
 		__syncwarp();
-		if (valid) out[(uint64_t)base + __popc(peers & lt)] = e[s];
+		if (valid) stage[base + __popc(peers & lt)] = e[s];
+	}
+	__syncthreads();
+	const unsigned cnt = (unsigned)min((uint64_t)SORT_TILE, n - tbase);
+	for (unsigned i = threadIdx.x; i < cnt; i += SORT_THREADS) {
+		const E v = stage[i];
+		out[(uint32_t)(gbase[digit(v)] + i)] = v;          // 32-bit wrap-around arithmetic: gbase may be "negative"
 	}
 }
 

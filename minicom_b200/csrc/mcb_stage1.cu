@@ -448,9 +448,8 @@ __global__ void k_scatter_clusters(const uint32_t *__restrict__ gstart, uint64_t
 
 // ---------------------------------------------------------------- K4: first m windowed minimizers of each new seed contig
 // mm_sketch_lh_ori (sketch.c:116-165) is a sequential scan with data-dependent tie rules, so one thread walks one contig;
-// the 64 contigs of a CTA are adjacent in cl_ref, so their characters are staged into shared memory with coalesced loads,
-// and the w-slot ring buffer (hash + position/strand per slot) lives in shared memory too, slot-major so that the lanes
-// of a warp hit different banks.  The walk stops after m outputs (kthread_bucket.c:463).
+// its characters arrive through aligned 64-bit loads, and the w-slot ring buffer (hash + position/strand per slot) lives in
+// shared memory, slot-major so that the lanes of a warp hit different banks.  The walk stops after m outputs (kthread_bucket.c:463).
 #define LH_THREADS 64
 struct LhRingSmem {
 	uint64_t *x; uint32_t *ps; int tid;
@@ -461,24 +460,21 @@ struct LhRingSmem {
 
 __global__ void __launch_bounds__(LH_THREADS)
 k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count,
-            int w, int k, int m, int span_cap, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
+            int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
 {
 	extern __shared__ __align__(16) unsigned char lh_smem[];
 	uint64_t *rx = (uint64_t*)lh_smem;                                        // [w][LH_THREADS]
 	uint32_t *rp = (uint32_t*)(rx + (size_t)w * LH_THREADS);                  // [w][LH_THREADS]
-	char *chars = (char*)(rp + (size_t)w * LH_THREADS);                       // [span_cap]
-	const uint64_t i0 = (uint64_t)blockIdx.x * LH_THREADS;
-	const int nloc = (int)min((uint64_t)LH_THREADS, cl_count - i0);
-	const uint64_t span0 = cl_ref_off[cl_first + i0], span1 = cl_ref_off[cl_first + i0 + nloc];
-	const bool staged = span1 - span0 <= (uint64_t)span_cap;
-	if (staged) for (uint64_t q = threadIdx.x; q < span1 - span0; q += LH_THREADS) chars[q] = cl_ref[span0 + q];
-	__syncthreads();
-	if ((int)threadIdx.x >= nloc) return;
-	const uint64_t c = cl_first + i0 + threadIdx.x;
+	const uint64_t ci = (uint64_t)blockIdx.x * LH_THREADS + threadIdx.x;
+	if (ci >= cl_count) return;
+	const uint64_t c = cl_first + ci;
 	const uint64_t b = cl_ref_off[c], e = cl_ref_off[c + 1];
-	const char *str = staged ? chars + (b - span0) : cl_ref + b;
 	const int len = (int)(e - b);
 	const uint32_t rid = (uint32_t)(c << 8);
+	// characters come eight at a time from aligned 64-bit loads (the buffer is padded past its end)
+	const uint64_t *str8 = (const uint64_t*)(cl_ref + (b & ~(uint64_t)7));
+	const int skew = (int)(b & 7);
+	uint64_t chunk = 0;
 	LhRingSmem ring; ring.x = rx; ring.ps = rp; ring.tid = threadIdx.x;
 	mcb_tuple *out = mi + c * m;
 	int n_out = 0;
@@ -488,7 +484,9 @@ k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref
 #define LH_EMIT(hx_, p_) do { if (n_out < m) { mcb_tuple t_; t_.x = (hx_); t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } while (0)
 	for (int j = 0; j < w; ++j) ring.set(j, ~0ull, ~0u);
 	for (int i = 0; i < len && n_out < m; ++i) {
-		const unsigned cc = mcb_code_of((unsigned char)str[i]);           // consensus strings are upper-case ACGT (invert_code_rule)
+		const int ai = i + skew;
+		if (i == 0 || (ai & 7) == 0) chunk = str8[ai >> 3];
+		const unsigned cc = mcb_code_of((unsigned char)(chunk >> (8 * (ai & 7))));   // consensus strings are upper-case ACGT (invert_code_rule)
 		uint64_t ix = ~0ull; uint32_t ip = ~0u;
 		if (cc < 4) {
 			fw = (fw << 2 | cc) & mask;
@@ -849,12 +847,11 @@ extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)
 			MCB_TRY(grow_preserve(ctx, d_micnt, tot_cl, tot_cl + n_cl_new + 16));
 			if (n_cl_new) {
 				const int rw = ctx->prm.rw;
-				const int span_cap = ((LH_THREADS * (2 * L + 2 * max_rounds + 8)) + 15) & ~15;
-				const size_t lh_smem = (size_t)rw * LH_THREADS * 12 + span_cap;
+				const size_t lh_smem = (size_t)rw * LH_THREADS * 12;
 				if (lh_smem <= 160 * 1024) {
 					if (lh_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_sketch_lh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh_smem));
 					MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh_smem, d_cl_ref.as<char>(), d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new,
-					           rw, k, m, span_cap, d_mi.as<mcb_tuple>(), d_micnt.as<uint8_t>());
+					           rw, k, m, d_mi.as<mcb_tuple>(), d_micnt.as<uint8_t>());
 				} else
 					MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh_local, mcb_grid_for(n_cl_new, 64), 64, 0, d_cl_ref.as<char>(), d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new,
 					           rw, k, m, d_mi.as<mcb_tuple>(), d_micnt.as<uint8_t>());

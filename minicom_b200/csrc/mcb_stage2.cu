@@ -268,13 +268,18 @@ __global__ void __launch_bounds__(128) k_s2_join(S2Join p, S2Geom gm)
 	if (idx < p.S * (uint64_t)gm.nd) {
 		const int l = (int)(idx / p.S); const uint64_t s = idx - (uint64_t)l * p.S;
 		if (!p.flagged[s]) {                  // sg_flag already set by the poly-A/T diversion: can never be claimed
-			const int L = gm.L, Wd = gm.Wd, WS = gm.WS, lt = gm.lt, ds = gm.dstart[l];
-			uint64_t R[9], RC[9];
-#pragma unroll
-			for (int i = 0; i < 9; ++i) R[i] = i < Wd ? p.rd[s * WS + i] : 0ull;
-			bool have_rc = false;
-			const uint64_t key_f = extract_bases(R, ds, lt);
+			const int L = gm.L, Wd = gm.Wd, lt = gm.lt, ds = gm.dstart[l];
+			const uint64_t *__restrict__ row = p.rd + s * gm.WS;       // 2-bit single, re-read from L1 where needed: no per-thread arrays
 			const uint64_t kmask = (1ull << (2 * lt)) - 1;
+			const uint64_t tailmask = (L & 31) ? (1ull << (2 * (L & 31))) - 1 : ~0ull;
+			const int pad = Wd * 32 - L;
+			uint64_t key_f;
+			{
+				const int bit = 2 * ds, wi = bit >> 6, sh = bit & 63;
+				uint64_t v = row[wi] >> sh;
+				if (sh + 2 * lt > 64) v |= row[wi + 1] << (64 - sh);
+				key_f = v & kmask;
+			}
 			const bool sketch_big = p.counters[CT_S2_MAXBIN] > (unsigned long long)gm.maxsearch;
 			for (int phase = 0; phase < 2; ++phase) {
 				if (phase && ds <= 0) break;                                         // kthread_hash_realign.c:440 (j = 0)
@@ -294,36 +299,44 @@ __global__ void __launch_bounds__(128) k_s2_join(S2Join p, S2Geom gm)
 					const long long jj = (long long)(P - cb) - koff;
 					if (jj < 0 || (uint64_t)jj + L > len) continue;
 					++n_cand;
-					// window bits
-					uint64_t X[9]; int pc = 0;
-					{
-						const uint64_t *src = p.cw + p.cw_off[c] + ((uint64_t)jj >> 5);
-						const int sh = 2 * (int)(jj & 31);
-						if (phase && !have_rc) {
-							// reverse complement of the single: reverse fields over Wd words, then drop the pad fields that moved to the bottom
-							const int pad = Wd * 32 - L;
-#pragma unroll
-							for (int q = 0; q < 9; ++q) RC[q] = 0;
-							for (int q = 0; q < Wd; ++q) {
-								uint64_t a = mcb_rc_word(R[Wd - 1 - q]);
-								uint64_t bb = q + 1 < Wd ? mcb_rc_word(R[Wd - 2 - q]) : 0ull;
-								RC[q] = pad ? (a >> (2 * pad)) | (bb << (64 - 2 * pad)) : a;
-							}
-							if (L & 31) RC[Wd - 1] &= (1ull << (2 * (L & 31))) - 1;
-							have_rc = true;
+					const uint64_t *__restrict__ src = p.cw + p.cw_off[c] + ((uint64_t)jj >> 5);
+					const int sh = 2 * (int)(jj & 31);
+					// word q of (window XOR single); for the reverse phase the single is reverse-complemented on the fly:
+					// reverse the fields over Wd words, then drop the pad fields that moved to the bottom
+					auto xword = [&](int q) -> uint64_t {
+						const uint64_t a = src[q];
+						uint64_t w = sh ? (a >> sh) | (src[q + 1] << (64 - sh)) : a;
+						uint64_t r;
+						if (!phase) r = row[q];
+						else {
+							const uint64_t hi = mcb_rc_word(row[Wd - 1 - q]);
+							const uint64_t lo = q + 1 < Wd ? mcb_rc_word(row[Wd - 2 - q]) : 0ull;
+							r = pad ? (hi >> (2 * pad)) | (lo << (64 - 2 * pad)) : hi;
 						}
+						if (q == Wd - 1) { w &= tailmask; r &= tailmask; }
+						return w ^ r;
+					};
+					int pc = 0;
 #pragma unroll
-						for (int q = 0; q < 9; ++q) {
-							if (q < Wd) {
-								uint64_t a = src[q], w = sh ? (a >> sh) | (src[q + 1] << (64 - sh)) : a;
-								if (q == Wd - 1 && (L & 31)) w &= (1ull << (2 * (L & 31))) - 1;
-								X[q] = w ^ (phase ? RC[q] : R[q]);
-								pc += __popcll(X[q]);
-							} else X[q] = 0;
-						}
-					}
+					for (int q = 0; q < 8; ++q) if (q < Wd) pc += __popcll(xword(q));
 					if (pc > gm.thr) continue;
-					if ((phase == 0 || gm.thr > 24) && !enc_ok(X, L, gm.enc_limit)) continue;   // :393 / :461
+					if (phase == 0 || gm.thr > 24) {                                             // encode_byte gate, :393 / :461
+						int len_e = 0, eq = 0;
+#pragma unroll 1
+						for (int q = 0; q < Wd; ++q) {
+							uint64_t x = xword(q);
+							const int lim = min(32, L - q * 32);
+							for (int j = 0; j < lim; ++j, x >>= 2) {
+								if (x & 3) {
+									if (eq > 1) { len_e += ndigits(eq); eq = 0; }
+									else len_e += eq;                                                   // stale-counter quirk of :301-305
+									++len_e;
+								} else ++eq;
+							}
+						}
+						if (len_e == 0) len_e = 1;
+						if (len_e > gm.enc_limit) continue;
+					}
 					if (sketch_big) {
 						// The reference scans only the last `maxsearch` live entries of a bin (:388); with every bin at most that
 						// large the scan sees everything and "all matches, first one wins" is exact.
@@ -422,7 +435,7 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	}
 	// ---- build
 	cx.n_contigs = n_contigs; cx.ref_bytes = ref_bytes; cx.total_words = total_words; cx.n_windows = n_windows; cx.n_entries = n_entries; cx.L = L; cx.lt = lt;
-	int pbits = 10; while (pbits < 24 && pbits < 2 * lt && (8ull << pbits) < n_entries) ++pbits;                 // 4..8 entries (1-2 sectors) per bucket
+	int pbits = 10; while (pbits < 26 && pbits < 2 * lt && (4ull << pbits) < n_entries) ++pbits;                 // 2..4 entries per bucket
 	cx.pbits = pbits;
 	const uint64_t nbk = 1ull << pbits, n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
 	MCB_TRY(cx.cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.wo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.cw.ensure((total_words + 2) * 8));
