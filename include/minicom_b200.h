@@ -138,6 +138,40 @@ typedef struct {
 
 int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res);
 
+/* kt_for_bucket's loop control (kthread_bucket.c:584-585,594,607-622), for callers that drive the rounds themselves:
+ *   is_last = mcb_round_control_begin(&rc, k, max_rounds);  ... one round ...;  stop = mcb_round_control_end(&rc, members so far) */
+typedef struct { int32_t round, last_rounds; int64_t pre_members; } mcb_round_control;
+void mcb_round_control_init(mcb_round_control *rc);
+int  mcb_round_control_begin(mcb_round_control *rc, int k, int max_rounds);
+int  mcb_round_control_end(mcb_round_control *rc, uint64_t members_total);
+
+/* ------------------------------------------------------------------ */
+/* sharding across the GPUs of one box                   */
+/* ------------------------------------------------------------------ */
+/* One context per GPU (one process per GPU).  Reads are split into contiguous read-id ranges; every minimizer bucket
+ * (16384 of them) is owned by one rank: owner = bucket * n_ranks >> 14.  The library does the device work and exposes
+ * device pointers; the caller moves data between ranks (NCCL all-to-all / all-gather, see minicom_b200/shard.py):
+ *
+ *   mcb_shard_begin(rank, n_ranks, n_total, rid_base)      then mcb_for_reads*() on the slice: read ids are global
+ *   all-gather of the packed reads   mcb_shard_packed() -> [n_total][row_bytes], this rank's rows already in place
+ *   all-gather of the N side table   mcb_shard_get_nreads() / mcb_shard_set_nreads()
+ *   per round r = 1, 2, ... (loop control: mcb_round_control on the GLOBAL member count)
+ *     mcb_shard_partition()  -> tuples grouped by owner + counts; all-to-all into mcb_shard_recv_buffer(); mcb_shard_set_tuples()
+ *     mcb_bucket_round_a()   -> sort, group, consensus; reports the new seed contigs / members / singles / rejects of this rank
+ *     mcb_bucket_round_b(cid_first)  cid_first = global index of this rank's first new contig in the single-GPU order
+ *                                    (contigs of earlier rounds on all ranks + this round's contigs on lower ranks)
+ *   mcb_bucket_finish()      -> this rank's contigs / singles in round order + what each round contributed
+ * Concatenating, round by round, the ranks' contributions in rank order reproduces the single-GPU result exactly. */
+int mcb_shard_begin(mcb_ctx *ctx, int rank, int n_ranks, uint64_t n_total, uint64_t rid_base);
+int mcb_shard_partition(mcb_ctx *ctx, uint64_t *counts /* [n_ranks] */, void **d_tuples /* 16-byte elements, grouped by owner */);
+int mcb_shard_recv_buffer(mcb_ctx *ctx, uint64_t n_tuples, void **d_recv, void **d_send /* current address of the partitioned tuples */);
+int mcb_shard_set_tuples(mcb_ctx *ctx, uint64_t n_tuples);
+int mcb_shard_packed(mcb_ctx *ctx, void **d_packed, uint64_t *row_bytes);
+int mcb_shard_get_nreads(mcb_ctx *ctx, const uint32_t **rid, const uint64_t **mask /* [n][row_bytes/8] */, uint64_t *n);
+int mcb_shard_set_nreads(mcb_ctx *ctx, const uint32_t *rid, const uint64_t *mask, uint64_t n);
+int mcb_bucket_round_a(mcb_ctx *ctx, int round, int is_last, uint64_t *out4 /* new contigs, members, singles, rejects */);
+int mcb_bucket_round_b(mcb_ctx *ctx, uint64_t cid_first);
+int mcb_bucket_finish(mcb_ctx *ctx, mcb_bucket_result *res, uint64_t *round_counts /* [4*cap_rounds]: contigs, members, consensus bytes, singles */, int cap_rounds);
 /* ------------------------------------------------------------------ */
 /* mm_idx_generation / mm_idx_get (kthread_idx.c:170,84)                */
 /* ------------------------------------------------------------------ */
@@ -186,6 +220,15 @@ typedef struct {
  * When refs is given, the table is rebuilt only if the strings differ from the cached ones. */
 int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off,
                 uint64_t n_contigs, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res);
+
+/* Stage 2 sharded: every rank holds all singles and a contiguous range of the contigs.  window_base = number of contig
+ * windows on lower ranks.  mcb_realign_begin runs the search and exposes the per-single claim priorities (u64[n_sg], all
+ * ones = unclaimed); the caller min-reduces them over the ranks in place; mcb_realign_finish then emits the claims that
+ * fall on this rank's contigs.  Rank-order concatenation of the claim lists is the single-GPU list. */
+#define MCB_CLAIM_NONE 0x7F7F7F7F7F7F7F7Fll
+int mcb_realign_begin(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
+                      uint64_t window_base, int threshold, int maxsearch, int ininumdict, void **d_claim);
+int mcb_realign_finish(mcb_ctx *ctx, mcb_realign_result *res);
 
 /* ------------------------------------------------------------------ */
 /* host-side boundary helpers                                           */

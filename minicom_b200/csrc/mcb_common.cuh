@@ -164,6 +164,25 @@ struct McbContigIndex {
 	DBuf eoff;      // u64[n_contigs+1] entry offsets (prefix sums of len-lt+1 over contigs with windows)
 };
 
+// kt_for_bucket as a resumable round loop (the sharded driver exchanges tuples between the rounds)
+struct McbBucketState {
+	bool active = false;
+	int r = 0, is_last = 0;
+	ulonglong2 *cur = nullptr, *alt = nullptr;
+	uint64_t n_in = 0, n_valid = 0;                       // elements handed to the sort / valid tuples among them
+	uint64_t tot_cl = 0, tot_mem = 0, tot_ref = 0, tot_sg = 0, tot_sk = 0;
+	uint64_t n = 0, G = 0, n_cl_new = 0, n_mem_new = 0, n_sg_new = 0, n_ref_new = 0, n_resk = 0;   // current round
+	bool half = false;                                    // round_a done, round_b pending
+	std::vector<uint64_t> round_cl, round_mem, round_ref, round_sg;   // what each round appended (sharded merge order)
+};
+
+// mcb_realign between its two halves (search / claim emission)
+struct McbRealignState {
+	bool pending = false;
+	uint64_t S = 0, window_base = 0;
+	int nd = 0;
+};
+
 struct mcb_ctx {
 	mcb_params prm;
 	cudaStream_t stream = 0;
@@ -172,8 +191,13 @@ struct mcb_ctx {
 	// geometry
 	int L = 0, Wd = 0, WS = 0;          // words per read (used / row stride)
 	// ---- persistent read state (mcb_for_reads)
-	uint64_t n_reads = 0;
+	uint64_t n_reads = 0;                // size of the read-id space (all reads of the job; == n_local unless sharded)
+	uint64_t n_local = 0, rid_base = 0;  // this context's slice [rid_base, rid_base + n_local)
+	int shard_rank = 0, shard_n = 1;
+	uint64_t elem_cap = 0;               // capacity (elements) of d_elemA / d_elemB
 	bool reads_loaded = false, bucket_done = false;
+	McbBucketState bs;
+	McbRealignState rs;
 	DBuf d_ascii;                        // N*L bytes (kept until the N masks are extracted)
 	DBuf d_packed;                       // u64[N][WS]
 	DBuf d_cls;                          // u8[N]

@@ -249,3 +249,39 @@ int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long
 	*sorted_out = src;
 	return MCB_OK;
 }
+
+// ---------------------------------------------------------------- sharding: group tuples by owning rank (stable)
+// owner of a tuple = owner of its bucket: contiguous bucket ranges, rank = bucket * n_ranks >> 14;
+// elements that are not tuples (reads that were not sketched) go last and are not counted
+struct DigitOwner {
+	int n_ranks;
+	__device__ __forceinline__ unsigned operator()(const ulonglong2 &e) const
+	{ return e.x == MCB_K1_INVALID ? (unsigned)n_ranks : (unsigned)(((e.x >> 50) * (unsigned long long)n_ranks) >> 14); }
+};
+int mcb_partition_by_owner(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, int n_ranks, uint64_t *counts)
+{
+	for (int i = 0; i <= n_ranks; ++i) counts[i] = 0;
+	if (n == 0) return MCB_OK;
+	if (n == 1) {    // nothing to move; classify the single element on the host side of a tiny copy
+		ulonglong2 e;
+		MCB_CUDA(cudaMemcpyAsync(&e, a, 16, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		counts[e.x == MCB_K1_INVALID ? n_ranks : (int)(((e.x >> 50) * (unsigned long long)n_ranks) >> 14)] = 1;
+		return MCB_OK;
+	}
+	uint64_t nb = (n + SORT_TILE - 1) / SORT_TILE;
+	if (nb > 0x7FFFFFFFull) { mcb_set_error("sort input too large"); return MCB_EINVAL; }
+	MCB_TRY(ctx->d_sort_hist.ensure(nb * 256 * sizeof(uint32_t)));
+	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>();
+	DigitOwner dg = { n_ranks };
+	MCB_LAUNCH(ctx, "shard_hist", (k_sort_hist<ulonglong2, DigitOwner>), (unsigned)nb, SORT_THREADS, 0, a, n, dg, hist, (unsigned)nb);
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, hist, nb * 256, nullptr));
+	MCB_LAUNCH(ctx, "shard_scatter", (k_sort_scatter<ulonglong2, DigitOwner>), (unsigned)nb, SORT_THREADS, 0, a, b, n, dg, hist, (unsigned)nb);
+	// start offset of digit d = first entry of its row of the digit-major table
+	uint32_t starts[257];
+	MCB_CUDA(cudaMemcpy2DAsync(starts, 4, hist, nb * 4, 4, 256, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	starts[256] = (uint32_t)n;
+	for (int i = 0; i <= n_ranks; ++i) counts[i] = starts[i + 1] - starts[i];
+	return MCB_OK;
+}

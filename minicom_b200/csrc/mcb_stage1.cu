@@ -34,7 +34,7 @@ MCB_HD int mcb_classify(const McbCounts &q, int L, int e, int *repl_code)
 #define HASN_BIT 0x80
 
 __global__ void __launch_bounds__(RD_THREADS)
-k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, int L, int Wd, int WS, int k, int e, int pbase,
+k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, uint64_t rid_base, int L, int Wd, int WS, int k, int e, int pbase,
                        uint64_t *__restrict__ packed, uint8_t *__restrict__ cls, ulonglong2 *__restrict__ elem,
                        unsigned long long *__restrict__ counters)
 {
@@ -53,7 +53,7 @@ k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, int L, int
 	}
 	__syncthreads();
 	const int t = threadIdx.x;
-	const uint64_t rid = first + t;
+	const uint64_t lid = first + t, rid = rid_base + lid;       // index inside this slice / global read id
 	bool sketched = false, bad = false, degenerate = false, hasn = false;
 	if (t < nrow) {
 		// Four characters per step, SIMD inside a 32-bit register.  (c>>1)&3 maps A,C,T,G (0x41,0x43,0x54,0x47) to 0,1,2,3;
@@ -109,7 +109,7 @@ k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, int L, int
 #pragma unroll
 			for (int w = 0; w < 8; ++w) if (w < Wd) sp[t][w] |= nmw[w] * (uint64_t)repl;
 		}
-		cls[rid] = (uint8_t)(c | (hasn ? HASN_BIT : 0));
+		cls[lid] = (uint8_t)(c | (hasn ? HASN_BIT : 0));
 		ulonglong2 el; el.x = MCB_K1_INVALID; el.y = mcb_make_k2_invalid((uint32_t)rid);
 		if (c == MCB_CLS_SKETCHED && !bad) {
 			int pos, z;
@@ -117,11 +117,11 @@ k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, int L, int
 			if (x == ~0ull) degenerate = true;
 			else { el.x = mcb_make_k1(x); el.y = mcb_make_k2((uint32_t)rid, pos, z, L, k, pbase); sketched = true; }
 		}
-		elem[rid] = el;
+		elem[lid] = el;
 	}
 	__syncthreads();
 	{   // coalesced store of the packed rows of this tile
-		uint64_t *dst = packed + first * WS;
+		uint64_t *dst = packed + (rid_base + first) * WS;
 		const int total = nrow * WS;
 		for (int i = threadIdx.x; i < total; i += RD_THREADS) { int r = i / WS, w = i - r * WS; dst[i] = w < Wd ? sp[r][w] : 0ull; }
 	}
@@ -138,7 +138,7 @@ __global__ void k_hasn_flags(const uint8_t *__restrict__ cls, uint64_t n, uint32
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) flag[i] = (cls[i] & HASN_BIT) ? 1u : 0u;
 }
-__global__ void k_hasn_extract(const uint8_t *__restrict__ ascii, uint8_t *__restrict__ cls, uint64_t n, int L, int Wd, int WS, int e,
+__global__ void k_hasn_extract(const uint8_t *__restrict__ ascii, uint8_t *__restrict__ cls, uint64_t n, uint64_t rid_base, int L, int Wd, int WS, int e,
                                const uint32_t *__restrict__ pos, uint32_t *__restrict__ nrid, uint64_t *__restrict__ nmask, uint8_t *__restrict__ nrepl)
 {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,7 +147,7 @@ __global__ void k_hasn_extract(const uint8_t *__restrict__ ascii, uint8_t *__res
 	if (!(c & HASN_BIT)) return;
 	cls[i] = c & ~HASN_BIT;
 	uint32_t o = pos[i];
-	nrid[o] = (uint32_t)i;
+	nrid[o] = (uint32_t)(rid_base + i);
 	const uint8_t *row = ascii + i * L;
 	McbCounts q = {0, 0, 0, 0, 0};
 	for (int w = 0; w < WS; ++w) {
@@ -185,7 +185,7 @@ __global__ void k_resketch(const uint64_t *__restrict__ packed, int WS, int L, i
 }
 
 // raw tuples for tests: elem (rid order) -> (x,y)
-__global__ void k_elem_to_tuple(const ulonglong2 *__restrict__ elem, uint64_t n, int L, int k, int pbase, mcb_tuple *__restrict__ out, int by_rid)
+__global__ void k_elem_to_tuple(const ulonglong2 *__restrict__ elem, uint64_t n, int L, int k, int pbase, mcb_tuple *__restrict__ out, int by_rid, uint64_t rid_base)
 {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -197,7 +197,7 @@ __global__ void k_elem_to_tuple(const ulonglong2 *__restrict__ elem, uint64_t n,
 		int pos = z ? L + k - 2 - pa : pa;
 		t.x = mcb_k1_to_x(e.x); t.y = (uint64_t)mcb_k2_rid(e.y) << 32 | (uint64_t)pos << 1 | (uint64_t)z;
 	}
-	out[by_rid ? (uint64_t)mcb_k2_rid(e.y) : i] = t;
+	out[by_rid ? (uint64_t)mcb_k2_rid(e.y) - rid_base : i] = t;
 }
 
 __global__ void k_unpack(const uint64_t *__restrict__ packed, uint64_t n, int L, int WS, char *__restrict__ out)
@@ -459,7 +459,7 @@ struct LhRingSmem {
 };
 
 __global__ void __launch_bounds__(LH_THREADS)
-k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count,
+k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count, uint64_t cid_first,
             int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
 {
 	extern __shared__ __align__(16) unsigned char lh_smem[];
@@ -470,7 +470,7 @@ k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref
 	const uint64_t c = cl_first + ci;
 	const uint64_t b = cl_ref_off[c], e = cl_ref_off[c + 1];
 	const int len = (int)(e - b);
-	const uint32_t rid = (uint32_t)(c << 8);
+	const uint32_t rid = (uint32_t)((cid_first + ci) << 8);          // ((clusters.n-1)<<8)+tid, tid 0 (kthread_bucket.c:458)
 	// characters come eight at a time from aligned 64-bit loads (the buffer is padded past its end)
 	const uint64_t *str8 = (const uint64_t*)(cl_ref + (b & ~(uint64_t)7));
 	const int skew = (int)(b & 7);
@@ -520,7 +520,7 @@ k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref
 	mi_cnt[c] = (uint8_t)(n_out < m ? n_out : m);
 }
 // fallback for windows too wide for shared memory: ring buffer in local memory
-__global__ void k_sketch_lh_local(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count,
+__global__ void k_sketch_lh_local(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count, uint64_t cid_first,
                                   int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
 {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -529,7 +529,7 @@ __global__ void k_sketch_lh_local(const char *__restrict__ cl_ref, const uint64_
 	const uint64_t b = cl_ref_off[c], e = cl_ref_off[c + 1];
 	McbLhEmitArray em; em.out = mi + c * m; em.cap = m; em.n = 0;
 	mcb_tuple ring[MCB_LH_WMAX];
-	mcb_sketch_lh_core(cl_ref + b, (int)(e - b), w, k, (uint32_t)(c << 8), ring, em, (int64_t)m);
+	mcb_sketch_lh_core(cl_ref + b, (int)(e - b), w, k, (uint32_t)((cid_first + i) << 8), ring, em, (int64_t)m);
 	mi_cnt[c] = (uint8_t)(em.n < m ? em.n : m);
 }
 
@@ -543,16 +543,30 @@ static int sync_counters(mcb_ctx *ctx, unsigned long long **hc)
 	return MCB_OK;
 }
 
+static int ensure_elems(mcb_ctx *ctx, uint64_t n, bool keep_cur)
+{
+	if (n <= ctx->elem_cap) return MCB_OK;
+	(void)keep_cur;
+	MCB_TRY(ctx->d_elemA.ensure((size_t)n * 16 + 16));
+	MCB_TRY(ctx->d_elemB.ensure((size_t)n * 16 + 16));
+	ctx->elem_cap = std::min(ctx->d_elemA.cap, ctx->d_elemB.cap) / 16;
+	return MCB_OK;
+}
+
 static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_reads_result *res)
 {
 	const int L = ctx->L, Wd = ctx->Wd, WS = ctx->WS;
 	const int pbase = L + ctx->prm.max_rounds;
-	ctx->n_reads = n; ctx->reads_loaded = false; ctx->bucket_done = false;
+	if (ctx->shard_n > 1) {
+		if (ctx->rid_base + n > ctx->n_reads) { mcb_set_error("mcb_for_reads: slice [%llu,+%llu) exceeds the %llu reads declared by mcb_shard_begin", (unsigned long long)ctx->rid_base, (unsigned long long)n, (unsigned long long)ctx->n_reads); return MCB_EINVAL; }
+	} else { ctx->n_reads = n; ctx->rid_base = 0; }
+	ctx->n_local = n; ctx->reads_loaded = false; ctx->bucket_done = false; ctx->bs.active = false;
 	ctx->cix.valid = false;              // a new read set starts a new run: contigs of the previous one are never reused
-	MCB_TRY(ctx->d_packed.ensure((size_t)n * WS * 8 + 16));
+	const uint64_t rid_base = ctx->rid_base;
+	MCB_TRY(ctx->d_packed.ensure((size_t)(ctx->n_reads + ctx->shard_n) * WS * 8 + 16));   // slack: equal-sized all-gather chunks may overhang by < n_ranks rows
 	MCB_TRY(ctx->d_cls.ensure(n + 16));
-	MCB_TRY(ctx->d_elemA.ensure((size_t)n * 16 + 16));
-	MCB_TRY(ctx->d_elemB.ensure((size_t)n * 16 + 16));
+	ctx->elem_cap = std::min(ctx->d_elemA.cap, ctx->d_elemB.cap) / 16;
+	MCB_TRY(ensure_elems(ctx, n + 1, false));
 	MCB_TRY(ctx->d_counters.ensure(64 * 8));
 	MCB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64 * 8, ctx->stream));
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
@@ -562,7 +576,7 @@ static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_r
 		if (n) {
 			size_t smem = RD_THREADS * 9 * sizeof(uint64_t) + (((size_t)RD_THREADS * L + 15) & ~(size_t)15) + 16;
 			MCB_LAUNCH(ctx, "pack_classify_sketch", k_pack_classify_sketch, mcb_grid_for(n, RD_THREADS), RD_THREADS, smem,
-			           d_rows, n, L, Wd, WS, ctx->prm.k, ctx->prm.diff_threshold, pbase,
+			           d_rows, n, rid_base, L, Wd, WS, ctx->prm.k, ctx->prm.diff_threshold, pbase,
 			           ctx->d_packed.as<uint64_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
 		}
 	}
@@ -581,7 +595,7 @@ static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_r
 		if (n && nn) {
 			MCB_LAUNCH(ctx, "hasn_flags", k_hasn_flags, mcb_grid_for(n, 256), 256, 0, ctx->d_cls.as<uint8_t>(), n, ctx->d_scr[0].as<uint32_t>());
 			MCB_TRY(mcb_exclusive_scan_u32(ctx, ctx->d_scr[0].as<uint32_t>(), n, nullptr));
-			MCB_LAUNCH(ctx, "hasn_extract", k_hasn_extract, mcb_grid_for(n, 256), 256, 0, d_rows, ctx->d_cls.as<uint8_t>(), n, L, Wd, WS,
+			MCB_LAUNCH(ctx, "hasn_extract", k_hasn_extract, mcb_grid_for(n, 256), 256, 0, d_rows, ctx->d_cls.as<uint8_t>(), n, rid_base, L, Wd, WS,
 			           ctx->prm.diff_threshold, ctx->d_scr[0].as<uint32_t>(), ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->d_scr[1].as<uint8_t>());
 		}
 	}
@@ -687,12 +701,12 @@ extern "C" int mcb_for_reads_ptrs(mcb_ctx *ctx, const void *first_seq_ptr, size_
 extern "C" int mcb_debug_read_tuples(mcb_ctx *ctx, mcb_tuple *out)
 {
 	MCB_TRY(check_ctx(ctx));
-	if (!ctx->reads_loaded || ctx->bucket_done) { mcb_set_error("mcb_debug_read_tuples: call right after mcb_for_reads"); return MCB_ESTATE; }
-	const uint64_t n = ctx->n_reads;
+	if (!ctx->reads_loaded || ctx->bucket_done || ctx->bs.active) { mcb_set_error("mcb_debug_read_tuples: call right after mcb_for_reads"); return MCB_ESTATE; }
+	const uint64_t n = ctx->n_local;
 	if (!n) return MCB_OK;
 	MCB_TRY(ctx->d_scr[0].ensure(n * 16));
 	MCB_LAUNCH(ctx, "elem_to_tuple", k_elem_to_tuple, mcb_grid_for(n, 256), 256, 0, ctx->d_elemA.as<ulonglong2>(), n, ctx->L, ctx->prm.k,
-	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[0].as<mcb_tuple>(), 1);
+	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[0].as<mcb_tuple>(), 1, ctx->rid_base);
 	MCB_CUDA(cudaMemcpyAsync(out, ctx->d_scr[0].p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return MCB_OK;
@@ -711,7 +725,7 @@ extern "C" int mcb_debug_sketch_two(mcb_ctx *ctx, const uint32_t *rids, uint64_t
 	MCB_LAUNCH(ctx, "resketch", k_resketch, mcb_grid_for(n, 128), 128, 0, ctx->d_packed.as<uint64_t>(), ctx->WS, ctx->L, ctx->prm.k, k,
 	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[0].as<uint32_t>(), n, ctx->d_scr[1].as<ulonglong2>(), ctx->d_counters.as<unsigned long long>());
 	MCB_LAUNCH(ctx, "elem_to_tuple", k_elem_to_tuple, mcb_grid_for(n, 256), 256, 0, ctx->d_scr[1].as<ulonglong2>(), n, ctx->L, ctx->prm.k,
-	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[2].as<mcb_tuple>(), 0);
+	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[2].as<mcb_tuple>(), 0, (uint64_t)0);
 	MCB_CUDA(cudaMemcpyAsync(out, ctx->d_scr[2].p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return MCB_OK;
@@ -742,139 +756,175 @@ static int grow_preserve(mcb_ctx *ctx, DBuf &b, size_t used, size_t need)
 	return MCB_OK;
 }
 
-extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)
+// ---- the round loop of kt_for_bucket (kthread_bucket.c:562-629) as begin / round_a / round_b / finish, so that the sharded
+// driver can exchange tuples and cluster counts between the halves; mcb_for_bucket below is the single-GPU loop over them.
+struct BucketBufs {
+	DBuf &b_hs, &b_gs, &b_st, &b_er, &b_nr, &b_gc, &b_gk, &b_gsg, &b_grk, &b_grl, &b_gro, &b_rk;
+	DBuf &d_cl_n, &d_cl_aoff, &d_cl_a, &d_cl_roff, &d_cl_ref, &d_sg, &d_mi, &d_micnt;
+	// d_scr roles: 0 head scan, 1 gstart, 2 status, 3 erank, 4 newrec, 5..9 group arrays, 10 refoff, 11 resk list
+	// d_out: accumulated outputs (kept in the context: allocating them per call costs more than all the kernels of this entry point together)
+	explicit BucketBufs(mcb_ctx *c) : b_hs(c->d_scr[0]), b_gs(c->d_scr[1]), b_st(c->d_scr[2]), b_er(c->d_scr[3]), b_nr(c->d_scr[4]), b_gc(c->d_scr[5]), b_gk(c->d_scr[6]),
+		b_gsg(c->d_scr[7]), b_grk(c->d_scr[8]), b_grl(c->d_scr[9]), b_gro(c->d_scr[10]), b_rk(c->d_scr[11]),
+		d_cl_n(c->d_out[0]), d_cl_aoff(c->d_out[1]), d_cl_a(c->d_out[2]), d_cl_roff(c->d_out[3]), d_cl_ref(c->d_out[4]), d_sg(c->d_out[5]), d_mi(c->d_out[6]), d_micnt(c->d_out[7]) {}
+};
+static inline int consensus_cols(const mcb_ctx *ctx) { return ((2 * ctx->L + 2 * ctx->prm.max_rounds + 8 + 31) / 32) * 32; }
+
+static int bucket_begin(mcb_ctx *ctx)
 {
-	MCB_TRY(check_ctx(ctx));
-	if (!res) { mcb_set_error("mcb_for_bucket: null result"); return MCB_EINVAL; }
-	if (!ctx->reads_loaded || ctx->bucket_done) { mcb_set_error("mcb_for_bucket: needs a fresh mcb_for_reads"); return MCB_ESTATE; }
-	const int L = ctx->L, WS = ctx->WS, k = ctx->prm.k, m = ctx->prm.first_mininum, max_rounds = ctx->prm.max_rounds;
-	const int pbase = L + max_rounds;
+	if (!ctx->reads_loaded || ctx->bucket_done) { mcb_set_error("kt_for_bucket: needs a fresh mcb_for_reads"); return MCB_ESTATE; }
+	McbBucketState &bs = ctx->bs;
+	bs = McbBucketState();
+	bs.active = true;
+	bs.cur = ctx->d_elemA.as<ulonglong2>(); bs.alt = ctx->d_elemB.as<ulonglong2>();
+	bs.n_in = ctx->n_local;            // round 1: every read of the slice, invalid ones sort last
+	bs.n_valid = ctx->n_valid_round1;
+	bs.tot_sk = ctx->n_valid_round1;
+	return MCB_OK;
+}
+
+// sort + group + consensus of the current tuples; leaves the per-round totals in bs (n_cl_new, n_mem_new, n_sg_new, n_resk)
+static int bucket_round_a(mcb_ctx *ctx, int r, int is_last)
+{
+	McbBucketState &bs = ctx->bs;
+	if (!bs.active || bs.half) { mcb_set_error("bucket round: call order violated"); return MCB_ESTATE; }
+	BucketBufs B(ctx);
+	const int L = ctx->L, WS = ctx->WS, k = ctx->prm.k, max_rounds = ctx->prm.max_rounds;
+	const int pbase = L + max_rounds, kmer = k - r;
 	const uint64_t N = ctx->n_reads;
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
 	unsigned long long *hc = nullptr;
-	// d_scr roles: 0 head scan, 1 gstart, 2 status, 3 erank, 4 newrec, 5..9 group arrays, 10 refoff, 11 resk list
-	DBuf &b_hs = ctx->d_scr[0], &b_gs = ctx->d_scr[1], &b_st = ctx->d_scr[2], &b_er = ctx->d_scr[3], &b_nr = ctx->d_scr[4];
-	DBuf &b_gc = ctx->d_scr[5], &b_gk = ctx->d_scr[6], &b_gsg = ctx->d_scr[7], &b_grk = ctx->d_scr[8], &b_grl = ctx->d_scr[9], &b_gro = ctx->d_scr[10], &b_rk = ctx->d_scr[11];
-	// accumulated outputs (device): cluster tables + sg
-	// (kept in the context: allocating them per call costs more than all the kernels of this entry point together)
-	DBuf &d_cl_n = ctx->d_out[0], &d_cl_aoff = ctx->d_out[1], &d_cl_a = ctx->d_out[2], &d_cl_roff = ctx->d_out[3], &d_cl_ref = ctx->d_out[4],
-	     &d_sg = ctx->d_out[5], &d_mi = ctx->d_out[6], &d_micnt = ctx->d_out[7];
-	uint64_t tot_cl = 0, tot_mem = 0, tot_ref = 0, tot_sg = 0, tot_sk = ctx->n_valid_round1;
-	const int NC = ((2 * L + 2 * max_rounds + 8 + 31) / 32) * 32;
+	bs.r = r; bs.is_last = is_last;
+	bs.n = bs.G = bs.n_cl_new = bs.n_mem_new = bs.n_sg_new = bs.n_ref_new = bs.n_resk = 0;
+	bs.half = true;
+	if (bs.n_valid == 0) return MCB_OK;
+	const int NC = consensus_cols(ctx);
 	const size_t cs_per_warp = (((size_t)NC * 16 + NC + CS_MB * 8 * 8 + CS_MB * 16) + 15) & ~(size_t)15;
 	const size_t cs_smem = cs_per_warp * CS_WARPS;
 	if (cs_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
 	// the ASCII buffer is dead after mcb_for_reads: reuse it for consensus strings before compaction
-	MCB_TRY(ctx->d_ascii.ensure((size_t)N * L + 16));
+	MCB_TRY(ctx->d_ascii.ensure((size_t)std::max<uint64_t>(bs.n_valid, ctx->n_local) * L + 16));
 	const uint64_t reftmp_cap = ctx->d_ascii.cap;
+	McbSpan sp(ctx->tm, "for_bucket");
+	// ---- K2: one stable sort; key = (bucket, minimizer, adjusted pos desc, rid asc)
+	std::vector<McbSortPass> passes;
+	if (r > 1 || ctx->shard_n > 1) mcb_add_bit_passes(passes, 1, 0, 1 + mcb_bits_for(N));      // strand + rid (a single GPU's round 1 arrives in rid order)
+	mcb_add_bit_passes(passes, 1, MCB_POSINV_SHIFT, MCB_POSINV_SHIFT + mcb_bits_for(pbase));
+	const int kbits = r == 1 ? 2 * k : 2 * (kmer + 1);                      // tuples of round r were hashed with k-(r-1) (r>=2) or k
+	mcb_add_bit_passes(passes, 0, 0, std::max(1, kbits - 14));
+	mcb_add_bit_passes(passes, 0, 50, 64);
+	ulonglong2 *sorted = nullptr;
+	MCB_TRY(mcb_radix_sort(ctx, bs.cur, bs.alt, bs.n_in, passes.data(), (int)passes.size(), &sorted));
+	if (sorted != bs.cur) { bs.alt = bs.cur; bs.cur = sorted; }
+	ulonglong2 *cur = bs.cur;
+	const uint64_t n = bs.n_valid;
+	bs.n = n;
+	// ---- groups
+	MCB_TRY(B.b_hs.ensure(n * 4 + 16)); MCB_TRY(B.b_gs.ensure((n + 2) * 4));
+	MCB_LAUNCH(ctx, "heads", k_heads, mcb_grid_for(n, 256), 256, 0, cur, n, B.b_hs.as<uint32_t>());
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_hs.as<uint32_t>(), n, (uint64_t*)&dc[CT_G]));
+	MCB_LAUNCH(ctx, "gstart", k_gstart, mcb_grid_for(n, 256), 256, 0, cur, n, B.b_hs.as<uint32_t>(), &dc[CT_G], B.b_gs.as<uint32_t>());
+	MCB_TRY(sync_counters(ctx, &hc));
+	const uint64_t G = hc[CT_G];
+	bs.G = G;
+	// ---- K3 consensus
+	MCB_TRY(B.b_st.ensure(n + 16)); MCB_TRY(B.b_er.ensure(n * 4 + 16)); MCB_TRY(B.b_nr.ensure(n * 8 + 16));
+	MCB_TRY(B.b_gc.ensure(G * 4 + 16)); MCB_TRY(B.b_gk.ensure(G * 4 + 16)); MCB_TRY(B.b_gsg.ensure(G * 4 + 16)); MCB_TRY(B.b_grk.ensure(G * 4 + 16));
+	MCB_TRY(B.b_grl.ensure(G * 8 + 16)); MCB_TRY(B.b_gro.ensure(G * 8 + 16));
+	MCB_CUDA(cudaMemsetAsync(&dc[CT_REFCURSOR], 0, 8, ctx->stream));
+	ConsOut co; co.status = B.b_st.as<uint8_t>(); co.erank = B.b_er.as<uint32_t>(); co.newrec = B.b_nr.as<uint64_t>();
+	co.g_iscl = B.b_gc.as<uint32_t>(); co.g_kept = B.b_gk.as<uint32_t>(); co.g_sg = B.b_gsg.as<uint32_t>(); co.g_resk = B.b_grk.as<uint32_t>();
+	co.g_reflen = B.b_grl.as<unsigned long long>(); co.g_refoff = B.b_gro.as<unsigned long long>(); co.reftmp = ctx->d_ascii.as<char>();
+	unsigned cgrid = mcb_grid_for(G, CS_WARPS, (unsigned)ctx->sm_count * 16);
+	MCB_LAUNCH(ctx, "consensus", k_consensus, cgrid, CS_WARPS * 32, cs_smem, cur, B.b_gs.as<uint32_t>(), G, ctx->d_packed.as<uint64_t>(), WS, L,
+	           ctx->prm.diff_threshold, pbase, NC, is_last, co, dc, reftmp_cap);
+	// ---- bases
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_gc.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_CL]));
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_gk.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_MEM]));
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_gsg.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_SG]));
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_grk.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_RESK]));
+	MCB_TRY(mcb_exclusive_scan_u64(ctx, B.b_grl.as<uint64_t>(), G, (uint64_t*)&dc[CT_TOT_REF]));
+	MCB_TRY(sync_counters(ctx, &hc));
+	if (hc[CT_ERR]) { mcb_set_error("internal: consensus table overflow (%llu groups)", hc[CT_ERR]); return MCB_EINVAL; }
+	bs.n_cl_new = hc[CT_TOT_CL]; bs.n_mem_new = hc[CT_TOT_MEM]; bs.n_resk = hc[CT_TOT_RESK];
+	bs.n_sg_new = hc[CT_TOT_SG]; bs.n_ref_new = hc[CT_TOT_REF];
+	return MCB_OK;
+}
 
-	ulonglong2 *cur = ctx->d_elemA.as<ulonglong2>(), *alt = ctx->d_elemB.as<ulonglong2>();
-	uint64_t n_in = N;                 // elements handed to the sort (round 1: all reads, invalid ones sort last)
-	uint64_t n_valid = ctx->n_valid_round1;
-	int last_rounds = 0, rounds = 0;
-	long long pre_cluster_reads = 0;
-	MCB_TRY(d_sg.ensure(N * 4 + 16));
-	const int span_h = ctx->tm.begin("for_bucket");
-	for (int r = 1;; ++r) {
-		if (k - r <= 9) ++last_rounds;                       // kthread_bucket.c:584-585
-		if (r == max_rounds - 1) ++last_rounds;
-		const int is_last = last_rounds ? 1 : 0;
-		const int kmer = k - r;
-		rounds = r;
-		uint64_t n_cl_new = 0, n_mem_new = 0, n_resk = 0;
-		if (n_valid > 0) {
-			// ---- K2: one stable sort; key = (bucket, minimizer, adjusted pos desc, rid asc)
-			std::vector<McbSortPass> passes;
-			if (r > 1) mcb_add_bit_passes(passes, 1, 0, 1 + mcb_bits_for(N));          // strand + rid (round 1 arrives in rid order)
-			mcb_add_bit_passes(passes, 1, MCB_POSINV_SHIFT, MCB_POSINV_SHIFT + mcb_bits_for(pbase));
-			const int kbits = r == 1 ? 2 * k : 2 * (kmer + 1);                      // tuples of round r were hashed with k-(r-1) (r>=2) or k
-			mcb_add_bit_passes(passes, 0, 0, std::max(1, kbits - 14));
-			mcb_add_bit_passes(passes, 0, 50, 64);
-			ulonglong2 *sorted = nullptr;
-			MCB_TRY(mcb_radix_sort(ctx, cur, alt, n_in, passes.data(), (int)passes.size(), &sorted));
-			if (sorted != cur) { alt = cur; cur = sorted; }
-			const uint64_t n = n_valid;
-			// ---- groups
-			MCB_TRY(b_hs.ensure(n * 4 + 16)); MCB_TRY(b_gs.ensure((n + 2) * 4));
-			MCB_LAUNCH(ctx, "heads", k_heads, mcb_grid_for(n, 256), 256, 0, cur, n, b_hs.as<uint32_t>());
-			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_hs.as<uint32_t>(), n, (uint64_t*)&dc[CT_G]));
-			MCB_LAUNCH(ctx, "gstart", k_gstart, mcb_grid_for(n, 256), 256, 0, cur, n, b_hs.as<uint32_t>(), &dc[CT_G], b_gs.as<uint32_t>());
-			MCB_TRY(sync_counters(ctx, &hc));
-			const uint64_t G = hc[CT_G];
-			// ---- K3 consensus
-			MCB_TRY(b_st.ensure(n + 16)); MCB_TRY(b_er.ensure(n * 4 + 16)); MCB_TRY(b_nr.ensure(n * 8 + 16));
-			MCB_TRY(b_gc.ensure(G * 4 + 16)); MCB_TRY(b_gk.ensure(G * 4 + 16)); MCB_TRY(b_gsg.ensure(G * 4 + 16)); MCB_TRY(b_grk.ensure(G * 4 + 16));
-			MCB_TRY(b_grl.ensure(G * 8 + 16)); MCB_TRY(b_gro.ensure(G * 8 + 16));
-			MCB_CUDA(cudaMemsetAsync(&dc[CT_REFCURSOR], 0, 8, ctx->stream));
-			ConsOut co; co.status = b_st.as<uint8_t>(); co.erank = b_er.as<uint32_t>(); co.newrec = b_nr.as<uint64_t>();
-			co.g_iscl = b_gc.as<uint32_t>(); co.g_kept = b_gk.as<uint32_t>(); co.g_sg = b_gsg.as<uint32_t>(); co.g_resk = b_grk.as<uint32_t>();
-			co.g_reflen = b_grl.as<unsigned long long>(); co.g_refoff = b_gro.as<unsigned long long>(); co.reftmp = ctx->d_ascii.as<char>();
-			unsigned cgrid = mcb_grid_for(G, CS_WARPS, (unsigned)ctx->sm_count * 16);
-			MCB_LAUNCH(ctx, "consensus", k_consensus, cgrid, CS_WARPS * 32, cs_smem, cur, b_gs.as<uint32_t>(), G, ctx->d_packed.as<uint64_t>(), WS, L,
-			           ctx->prm.diff_threshold, pbase, NC, is_last, co, dc, reftmp_cap);
-			// ---- bases
-			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_gc.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_CL]));
-			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_gk.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_MEM]));
-			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_gsg.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_SG]));
-			MCB_TRY(mcb_exclusive_scan_u32(ctx, b_grk.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_RESK]));
-			MCB_TRY(mcb_exclusive_scan_u64(ctx, b_grl.as<uint64_t>(), G, (uint64_t*)&dc[CT_TOT_REF]));
-			MCB_TRY(sync_counters(ctx, &hc));
-			if (hc[CT_ERR]) { mcb_set_error("internal: consensus table overflow (%llu groups)", hc[CT_ERR]); return MCB_EINVAL; }
-			n_cl_new = hc[CT_TOT_CL]; n_mem_new = hc[CT_TOT_MEM]; n_resk = hc[CT_TOT_RESK];
-			const uint64_t n_sg_new = hc[CT_TOT_SG], n_ref_new = hc[CT_TOT_REF];
-			MCB_TRY(grow_preserve(ctx, d_cl_n, tot_cl * 4, (tot_cl + n_cl_new) * 4 + 16));
-			MCB_TRY(grow_preserve(ctx, d_cl_aoff, tot_cl * 8, (tot_cl + n_cl_new + 1) * 8 + 16));
-			MCB_TRY(grow_preserve(ctx, d_cl_roff, tot_cl * 8, (tot_cl + n_cl_new + 1) * 8 + 16));
-			MCB_TRY(grow_preserve(ctx, d_cl_a, tot_mem * 8, (tot_mem + n_mem_new) * 8 + 16));
-			MCB_TRY(grow_preserve(ctx, d_cl_ref, tot_ref, tot_ref + n_ref_new + 16));
-			MCB_TRY(b_rk.ensure(n_resk * 4 + 16));
-			ScatIn si; si.status = b_st.as<uint8_t>(); si.erank = b_er.as<uint32_t>(); si.newrec = b_nr.as<uint64_t>(); si.hscan = b_hs.as<uint32_t>();
-			si.g_iscl = b_gc.as<uint32_t>(); si.g_kept = b_gk.as<uint32_t>(); si.g_sg = b_gsg.as<uint32_t>(); si.g_resk = b_grk.as<uint32_t>();
-			MCB_LAUNCH(ctx, "scatter_members", k_scatter_members, mcb_grid_for(n, 256), 256, 0, cur, n, si, is_last, tot_mem, tot_sg,
-			           d_cl_a.as<uint64_t>(), d_sg.as<uint32_t>(), b_rk.as<uint32_t>());
-			MCB_LAUNCH(ctx, "scatter_clusters", k_scatter_clusters, mcb_grid_for(G * 32, 256), 256, 0, b_gs.as<uint32_t>(), G, b_gc.as<uint32_t>(), b_gk.as<uint32_t>(),
-			           b_grl.as<unsigned long long>(), b_gro.as<unsigned long long>(), dc, ctx->d_ascii.as<char>(), tot_cl, tot_mem, tot_ref,
-			           d_cl_n.as<uint32_t>(), d_cl_aoff.as<uint64_t>(), d_cl_roff.as<uint64_t>(), d_cl_ref.as<char>());
-			// close the offset tables
-			{
-				uint64_t endv[2] = { tot_mem + n_mem_new, tot_ref + n_ref_new };
-				MCB_CUDA(cudaMemcpyAsync(d_cl_aoff.as<uint64_t>() + tot_cl + n_cl_new, &endv[0], 8, cudaMemcpyHostToDevice, ctx->stream));
-				MCB_CUDA(cudaMemcpyAsync(d_cl_roff.as<uint64_t>() + tot_cl + n_cl_new, &endv[1], 8, cudaMemcpyHostToDevice, ctx->stream));
-				MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-			}
-			// ---- K4: first m minimizers of each new seed contig (window rw, k = reads->k; kthread_bucket.c:458)
-			MCB_TRY(grow_preserve(ctx, d_mi, tot_cl * m * 16, (tot_cl + n_cl_new) * m * 16 + 16));
-			MCB_TRY(grow_preserve(ctx, d_micnt, tot_cl, tot_cl + n_cl_new + 16));
-			if (n_cl_new) {
-				const int rw = ctx->prm.rw;
-				const size_t lh_smem = (size_t)rw * LH_THREADS * 12;
-				if (lh_smem <= 160 * 1024) {
-					if (lh_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_sketch_lh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh_smem));
-					MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh_smem, d_cl_ref.as<char>(), d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new,
-					           rw, k, m, d_mi.as<mcb_tuple>(), d_micnt.as<uint8_t>());
-				} else
-					MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh_local, mcb_grid_for(n_cl_new, 64), 64, 0, d_cl_ref.as<char>(), d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new,
-					           rw, k, m, d_mi.as<mcb_tuple>(), d_micnt.as<uint8_t>());
-			}
-			tot_cl += n_cl_new; tot_mem += n_mem_new; tot_ref += n_ref_new; tot_sg += n_sg_new;
-			// ---- rejected reads go to the next round with a shorter k-mer (kthread_bucket.c:205-212,488-496)
-			if (!is_last && n_resk) {
-				MCB_LAUNCH(ctx, "resketch", k_resketch, mcb_grid_for(n_resk, 128), 128, 0, ctx->d_packed.as<uint64_t>(), WS, L, k, kmer, pbase,
-				           b_rk.as<uint32_t>(), n_resk, alt, dc);
-				ulonglong2 *t = cur; cur = alt; alt = t;
-				tot_sk += n_resk;
-			}
+// scatter into the accumulated outputs, index tuples of the new seed contigs (ids cid_first, cid_first+1, ...), re-sketch of the rejects
+static int bucket_round_b(mcb_ctx *ctx, uint64_t cid_first)
+{
+	McbBucketState &bs = ctx->bs;
+	if (!bs.active || !bs.half) { mcb_set_error("bucket round: call order violated"); return MCB_ESTATE; }
+	bs.half = false;
+	BucketBufs B(ctx);
+	const int L = ctx->L, WS = ctx->WS, k = ctx->prm.k, m = ctx->prm.first_mininum, max_rounds = ctx->prm.max_rounds;
+	const int pbase = L + max_rounds, kmer = k - bs.r, is_last = bs.is_last;
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	const uint64_t n = bs.n, G = bs.G, n_cl_new = bs.n_cl_new, n_mem_new = bs.n_mem_new, n_resk = bs.n_resk, n_sg_new = bs.n_sg_new, n_ref_new = bs.n_ref_new;
+	const uint64_t tot_cl = bs.tot_cl, tot_mem = bs.tot_mem, tot_ref = bs.tot_ref, tot_sg = bs.tot_sg;
+	bs.round_cl.push_back(n_cl_new); bs.round_mem.push_back(n_mem_new); bs.round_ref.push_back(n_ref_new); bs.round_sg.push_back(n_sg_new);
+	if (n == 0) { bs.n_in = bs.n_valid = 0; return MCB_OK; }
+	ulonglong2 *cur = bs.cur;
+	{
+		McbSpan sp(ctx->tm, "for_bucket");
+		MCB_TRY(grow_preserve(ctx, B.d_sg, tot_sg * 4, (tot_sg + n_sg_new) * 4 + 16));
+		MCB_TRY(grow_preserve(ctx, B.d_cl_n, tot_cl * 4, (tot_cl + n_cl_new) * 4 + 16));
+		MCB_TRY(grow_preserve(ctx, B.d_cl_aoff, tot_cl * 8, (tot_cl + n_cl_new + 1) * 8 + 16));
+		MCB_TRY(grow_preserve(ctx, B.d_cl_roff, tot_cl * 8, (tot_cl + n_cl_new + 1) * 8 + 16));
+		MCB_TRY(grow_preserve(ctx, B.d_cl_a, tot_mem * 8, (tot_mem + n_mem_new) * 8 + 16));
+		MCB_TRY(grow_preserve(ctx, B.d_cl_ref, tot_ref, tot_ref + n_ref_new + 16));
+		MCB_TRY(B.b_rk.ensure(n_resk * 4 + 16));
+		ScatIn si; si.status = B.b_st.as<uint8_t>(); si.erank = B.b_er.as<uint32_t>(); si.newrec = B.b_nr.as<uint64_t>(); si.hscan = B.b_hs.as<uint32_t>();
+		si.g_iscl = B.b_gc.as<uint32_t>(); si.g_kept = B.b_gk.as<uint32_t>(); si.g_sg = B.b_gsg.as<uint32_t>(); si.g_resk = B.b_grk.as<uint32_t>();
+		MCB_LAUNCH(ctx, "scatter_members", k_scatter_members, mcb_grid_for(n, 256), 256, 0, cur, n, si, is_last, tot_mem, tot_sg,
+		           B.d_cl_a.as<uint64_t>(), B.d_sg.as<uint32_t>(), B.b_rk.as<uint32_t>());
+		MCB_LAUNCH(ctx, "scatter_clusters", k_scatter_clusters, mcb_grid_for(G * 32, 256), 256, 0, B.b_gs.as<uint32_t>(), G, B.b_gc.as<uint32_t>(), B.b_gk.as<uint32_t>(),
+		           B.b_grl.as<unsigned long long>(), B.b_gro.as<unsigned long long>(), dc, ctx->d_ascii.as<char>(), tot_cl, tot_mem, tot_ref,
+		           B.d_cl_n.as<uint32_t>(), B.d_cl_aoff.as<uint64_t>(), B.d_cl_roff.as<uint64_t>(), B.d_cl_ref.as<char>());
+		// close the offset tables
+		{
+			uint64_t endv[2] = { tot_mem + n_mem_new, tot_ref + n_ref_new };
+			MCB_CUDA(cudaMemcpyAsync(B.d_cl_aoff.as<uint64_t>() + tot_cl + n_cl_new, &endv[0], 8, cudaMemcpyHostToDevice, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(B.d_cl_roff.as<uint64_t>() + tot_cl + n_cl_new, &endv[1], 8, cudaMemcpyHostToDevice, ctx->stream));
+			MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 		}
-		n_in = n_valid = (is_last ? 0 : n_resk);
-		if (last_rounds) ++last_rounds;                      // kthread_bucket.c:594
-		const long long cluster_reads = (long long)tot_mem;  // sum of cluster sizes so far (:607-611)
-		if (cluster_reads - pre_cluster_reads < 100) ++last_rounds;
-		pre_cluster_reads = cluster_reads;
-		if (last_rounds > 1) break;
+		// ---- K4: first m minimizers of each new seed contig (window rw, k = reads->k; kthread_bucket.c:458)
+		MCB_TRY(grow_preserve(ctx, B.d_mi, tot_cl * m * 16, (tot_cl + n_cl_new) * m * 16 + 16));
+		MCB_TRY(grow_preserve(ctx, B.d_micnt, tot_cl, tot_cl + n_cl_new + 16));
+		if (n_cl_new) {
+			const int rw = ctx->prm.rw;
+			const size_t lh_smem = (size_t)rw * LH_THREADS * 12;
+			if (lh_smem <= 160 * 1024) {
+				if (lh_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_sketch_lh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh_smem));
+				MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh_smem, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
+				           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>());
+			} else
+				MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh_local, mcb_grid_for(n_cl_new, 64), 64, 0, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
+				           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>());
+		}
+		bs.tot_cl += n_cl_new; bs.tot_mem += n_mem_new; bs.tot_ref += n_ref_new; bs.tot_sg += n_sg_new;
+		// ---- rejected reads go to the next round with a shorter k-mer (kthread_bucket.c:205-212,488-496)
+		if (!is_last && n_resk) {
+			MCB_LAUNCH(ctx, "resketch", k_resketch, mcb_grid_for(n_resk, 128), 128, 0, ctx->d_packed.as<uint64_t>(), WS, L, k, kmer, pbase,
+			           B.b_rk.as<uint32_t>(), n_resk, bs.alt, dc);
+			ulonglong2 *t = bs.cur; bs.cur = bs.alt; bs.alt = t;
+			bs.tot_sk += n_resk;
+		}
 	}
-	ctx->tm.end(span_h);
+	bs.n_in = bs.n_valid = (is_last ? 0 : n_resk);
+	return MCB_OK;
+}
+
+static int bucket_finish(mcb_ctx *ctx, mcb_bucket_result *res)
+{
+	McbBucketState &bs = ctx->bs;
+	if (!bs.active || bs.half) { mcb_set_error("bucket finish: call order violated"); return MCB_ESTATE; }
+	BucketBufs B(ctx);
+	const int m = ctx->prm.first_mininum;
+	unsigned long long *hc = nullptr;
 	MCB_TRY(sync_counters(ctx, &hc));
 	if (hc[CT_DEGENERATE]) { mcb_set_error("%llu re-sketched reads have no valid k-mer", hc[CT_DEGENERATE]); return MCB_EINPUT; }
+	const uint64_t tot_cl = bs.tot_cl, tot_mem = bs.tot_mem, tot_ref = bs.tot_ref, tot_sg = bs.tot_sg;
 	// ---- results to the host
 	MCB_TRY(ctx->h_cl_n.ensure(tot_cl * 4 + 16)); MCB_TRY(ctx->h_cl_a_off.ensure((tot_cl + 1) * 8)); MCB_TRY(ctx->h_cl_ref_off.ensure((tot_cl + 1) * 8));
 	MCB_TRY(ctx->h_cl_a.ensure(tot_mem * 8 + 16)); MCB_TRY(ctx->h_cl_ref.ensure(tot_ref + 16)); MCB_TRY(ctx->h_sg.ensure(tot_sg * 4 + 16));
@@ -882,15 +932,15 @@ extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)
 	{
 		McbSpan sp(ctx->tm, "d2h");
 		if (tot_cl) {
-			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_n.p, d_cl_n.p, tot_cl * 4, cudaMemcpyDeviceToHost, ctx->stream));
-			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_a_off.p, d_cl_aoff.p, (tot_cl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_ref_off.p, d_cl_roff.p, (tot_cl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_a.p, d_cl_a.p, tot_mem * 8, cudaMemcpyDeviceToHost, ctx->stream));
-			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_ref.p, d_cl_ref.p, tot_ref, cudaMemcpyDeviceToHost, ctx->stream));
-			MCB_CUDA(cudaMemcpyAsync(ctx->h_mi.p, d_mi.p, tot_cl * m * 16, cudaMemcpyDeviceToHost, ctx->stream));
-			MCB_CUDA(cudaMemcpyAsync(ctx->h_mi_cnt.p, d_micnt.p, tot_cl, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_n.p, B.d_cl_n.p, tot_cl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_a_off.p, B.d_cl_aoff.p, (tot_cl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_ref_off.p, B.d_cl_roff.p, (tot_cl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_a.p, B.d_cl_a.p, tot_mem * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_ref.p, B.d_cl_ref.p, tot_ref, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_mi.p, B.d_mi.p, tot_cl * m * 16, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_mi_cnt.p, B.d_micnt.p, tot_cl, cudaMemcpyDeviceToHost, ctx->stream));
 		} else { ctx->h_cl_a_off.as<uint64_t>()[0] = 0; ctx->h_cl_ref_off.as<uint64_t>()[0] = 0; }
-		if (tot_sg) MCB_CUDA(cudaMemcpyAsync(ctx->h_sg.p, d_sg.p, tot_sg * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		if (tot_sg) MCB_CUDA(cudaMemcpyAsync(ctx->h_sg.p, B.d_sg.p, tot_sg * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	}
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->tm.collect();
@@ -898,7 +948,154 @@ extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)
 	res->cl_ref_off = ctx->h_cl_ref_off.as<uint64_t>(); res->cl_ref = ctx->h_cl_ref.as<char>();
 	res->n_sg = tot_sg; res->sg = ctx->h_sg.as<uint32_t>();
 	res->mi_cnt = ctx->h_mi_cnt.as<uint8_t>(); res->mi = ctx->h_mi.as<mcb_tuple>();
-	res->rounds = rounds; res->n_sketched_total = tot_sk; res->n_grouped = tot_mem;
+	res->rounds = bs.r; res->n_sketched_total = bs.tot_sk; res->n_grouped = tot_mem;
+	bs.active = false;
 	ctx->bucket_done = true;
 	return MCB_OK;
+}
+
+// loop control of kt_for_bucket (kthread_bucket.c:584-585,594,607-622): feed it the members gained in the round
+extern "C" void mcb_round_control_init(mcb_round_control *rc) { memset(rc, 0, sizeof *rc); }
+extern "C" int mcb_round_control_begin(mcb_round_control *rc, int k, int max_rounds)
+{
+	rc->round += 1;
+	if (k - rc->round <= 9) ++rc->last_rounds;
+	if (rc->round == max_rounds - 1) ++rc->last_rounds;
+	return rc->last_rounds ? 1 : 0;                    // is_last for this round
+}
+extern "C" int mcb_round_control_end(mcb_round_control *rc, uint64_t members_total)
+{
+	if (rc->last_rounds) ++rc->last_rounds;
+	if ((long long)members_total - rc->pre_members < 100) ++rc->last_rounds;
+	rc->pre_members = (long long)members_total;
+	return rc->last_rounds > 1 ? 1 : 0;                // stop
+}
+
+extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!res) { mcb_set_error("mcb_for_bucket: null result"); return MCB_EINVAL; }
+	if (ctx->shard_n > 1) { mcb_set_error("mcb_for_bucket: context is sharded, drive the rounds with mcb_bucket_round_a/_b"); return MCB_ESTATE; }
+	MCB_TRY(bucket_begin(ctx));
+	mcb_round_control rc; mcb_round_control_init(&rc);
+	for (;;) {
+		const int is_last = mcb_round_control_begin(&rc, ctx->prm.k, ctx->prm.max_rounds);
+		MCB_TRY(bucket_round_a(ctx, rc.round, is_last));
+		MCB_TRY(bucket_round_b(ctx, ctx->bs.tot_cl));
+		if (mcb_round_control_end(&rc, ctx->bs.tot_mem)) break;
+	}
+	return bucket_finish(ctx, res);
+}
+
+// ---------------------------------------------------------------- sharding (one context per GPU, see include/minicom_b200.h)
+extern "C" int mcb_shard_begin(mcb_ctx *ctx, int rank, int n_ranks, uint64_t n_total, uint64_t rid_base)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (n_ranks < 1 || n_ranks > 255 || rank < 0 || rank >= n_ranks || rid_base > n_total) { mcb_set_error("mcb_shard_begin: bad arguments"); return MCB_EINVAL; }
+	if (n_total >= (1ull << 31)) { mcb_set_error("too many reads (rid is a signed 32-bit int in the reference, kthread_bucket.c:48)"); return MCB_EINVAL; }
+	ctx->shard_rank = rank; ctx->shard_n = n_ranks; ctx->n_reads = n_total; ctx->rid_base = rid_base;
+	ctx->reads_loaded = false; ctx->bucket_done = false; ctx->bs.active = false;
+	return MCB_OK;
+}
+
+int mcb_partition_by_owner(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, int n_ranks, uint64_t *counts /* host [n_ranks+1] */);   // mcb_sort.cu
+
+extern "C" int mcb_shard_partition(mcb_ctx *ctx, uint64_t *counts, void **d_tuples)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!counts || !d_tuples) { mcb_set_error("mcb_shard_partition: null argument"); return MCB_EINVAL; }
+	McbBucketState &bs = ctx->bs;
+	if (!ctx->reads_loaded) { mcb_set_error("mcb_shard_partition: no reads loaded"); return MCB_ESTATE; }
+	if (!bs.active) MCB_TRY(bucket_begin(ctx));
+	if (bs.half) { mcb_set_error("mcb_shard_partition: round in progress"); return MCB_ESTATE; }
+	std::vector<uint64_t> c((size_t)ctx->shard_n + 1, 0);
+	MCB_TRY(mcb_partition_by_owner(ctx, bs.cur, bs.alt, bs.n_in, ctx->shard_n, c.data()));
+	if (bs.n_in > 1) { ulonglong2 *t = bs.cur; bs.cur = bs.alt; bs.alt = t; }
+	for (int i = 0; i < ctx->shard_n; ++i) counts[i] = c[i];
+	*d_tuples = bs.cur;
+	return MCB_OK;
+}
+
+extern "C" int mcb_shard_recv_buffer(mcb_ctx *ctx, uint64_t n_tuples, void **d_recv, void **d_send)
+{
+	MCB_TRY(check_ctx(ctx));
+	McbBucketState &bs = ctx->bs;
+	if (!bs.active || bs.half || !d_recv || !d_send) { mcb_set_error("mcb_shard_recv_buffer: call order violated"); return MCB_ESTATE; }
+	if (n_tuples + 1 > ctx->elem_cap) {
+		// grow both halves of the sort double buffer; the send side (bs.cur) must survive
+		const bool cur_is_A = bs.cur == ctx->d_elemA.as<ulonglong2>();
+		DBuf &keep = cur_is_A ? ctx->d_elemA : ctx->d_elemB, &other = cur_is_A ? ctx->d_elemB : ctx->d_elemA;
+		MCB_TRY(other.ensure((n_tuples + 1) * 16 + 16));
+		MCB_TRY(grow_preserve(ctx, keep, bs.n_in * 16, (n_tuples + 1) * 16 + 16));
+		ctx->elem_cap = std::min(ctx->d_elemA.cap, ctx->d_elemB.cap) / 16;
+		bs.cur = keep.as<ulonglong2>(); bs.alt = other.as<ulonglong2>();
+	}
+	*d_recv = bs.alt; *d_send = bs.cur;     // growing the buffers may have moved the partitioned tuples
+	return MCB_OK;
+}
+
+extern "C" int mcb_shard_set_tuples(mcb_ctx *ctx, uint64_t n_tuples)
+{
+	MCB_TRY(check_ctx(ctx));
+	McbBucketState &bs = ctx->bs;
+	if (!bs.active || bs.half) { mcb_set_error("mcb_shard_set_tuples: call order violated"); return MCB_ESTATE; }
+	if (n_tuples > ctx->elem_cap) { mcb_set_error("mcb_shard_set_tuples: more tuples than mcb_shard_recv_buffer reserved"); return MCB_EINVAL; }
+	ulonglong2 *t = bs.cur; bs.cur = bs.alt; bs.alt = t;      // the receive buffer becomes the input of the next round
+	bs.n_in = bs.n_valid = n_tuples;
+	return MCB_OK;
+}
+
+extern "C" int mcb_shard_packed(mcb_ctx *ctx, void **d_packed, uint64_t *row_bytes)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!ctx->reads_loaded) { mcb_set_error("mcb_shard_packed: no reads loaded"); return MCB_ESTATE; }
+	*d_packed = ctx->d_packed.p; *row_bytes = (uint64_t)ctx->WS * 8;
+	return MCB_OK;
+}
+
+// the side table of reads that contained N, for all reads of the job (ascending rid); replaces the slice-local one
+extern "C" int mcb_shard_set_nreads(mcb_ctx *ctx, const uint32_t *rid, const uint64_t *mask, uint64_t n)
+{
+	MCB_TRY(check_ctx(ctx));
+	const int WS = ctx->WS;
+	MCB_TRY(ctx->d_nread_rid.ensure(n * 4 + 16)); MCB_TRY(ctx->d_nread_mask.ensure(n * WS * 8 + 16));
+	if (n) {
+		MCB_CUDA(cudaMemcpyAsync(ctx->d_nread_rid.p, rid, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+		MCB_CUDA(cudaMemcpyAsync(ctx->d_nread_mask.p, mask, n * WS * 8, cudaMemcpyHostToDevice, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	ctx->n_nreads = n;
+	return MCB_OK;
+}
+extern "C" int mcb_shard_get_nreads(mcb_ctx *ctx, const uint32_t **rid, const uint64_t **mask, uint64_t *n)
+{
+	MCB_TRY(check_ctx(ctx));
+	*rid = ctx->h_nrid.as<uint32_t>(); *mask = ctx->h_nmask.as<uint64_t>(); *n = ctx->n_nreads;
+	return MCB_OK;
+}
+
+extern "C" int mcb_bucket_round_a(mcb_ctx *ctx, int round, int is_last, uint64_t *out4)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!ctx->bs.active) MCB_TRY(bucket_begin(ctx));
+	MCB_TRY(bucket_round_a(ctx, round, is_last));
+	if (out4) { out4[0] = ctx->bs.n_cl_new; out4[1] = ctx->bs.n_mem_new; out4[2] = ctx->bs.n_sg_new; out4[3] = ctx->bs.n_resk; }
+	return MCB_OK;
+}
+extern "C" int mcb_bucket_round_b(mcb_ctx *ctx, uint64_t cid_first)
+{
+	MCB_TRY(check_ctx(ctx));
+	return bucket_round_b(ctx, cid_first);
+}
+extern "C" int mcb_bucket_finish(mcb_ctx *ctx, mcb_bucket_result *res, uint64_t *round_counts /* [4*rounds]: clusters, members, ref bytes, singles per round */, int cap_rounds)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!res) { mcb_set_error("mcb_bucket_finish: null result"); return MCB_EINVAL; }
+	const McbBucketState &bs = ctx->bs;
+	const int nr = (int)bs.round_cl.size();
+	if (round_counts) {
+		if (cap_rounds < nr) { mcb_set_error("mcb_bucket_finish: %d rounds, room for %d", nr, cap_rounds); return MCB_EINVAL; }
+		for (int i = 0; i < nr; ++i) { round_counts[4 * i] = bs.round_cl[i]; round_counts[4 * i + 1] = bs.round_mem[i]; round_counts[4 * i + 2] = bs.round_ref[i]; round_counts[4 * i + 3] = bs.round_sg[i]; }
+	}
+	return bucket_finish(ctx, res);
 }

@@ -250,6 +250,7 @@ struct S2Join {
 	const uint32_t *ptab; const unsigned long long *ents; int pbits;
 	const uint32_t *pblk; const uint64_t *ref_off, *cw, *cw_off, *woff;
 	unsigned long long *claim;            // [S] min priority
+	unsigned long long window_base;       // windows on lower ranks (0 on a single GPU)
 	unsigned long long *counters;
 	const unsigned long long *xkey; const uint32_t *xcnt; uint64_t xmask;   // exact bin sizes (null: trust the sketch)
 };
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(128) k_s2_join(S2Join p, S2Geom gm)
 						if (p.xkey) big = bins_exact_count(p.xkey, p.xcnt, p.xmask, ((unsigned long long)l << 34) | key_f) > (uint32_t)gm.maxsearch;
 						if (big) atomicAdd(&p.counters[CT_S2_NEEDEXACT], 1ull);
 					}
-					const unsigned long long g = p.woff[c] + (unsigned long long)jj;
+					const unsigned long long g = p.window_base + p.woff[c] + (unsigned long long)jj;
 					atomicMin(&p.claim[s], (g << 5) | ((unsigned long long)phase << 4) | (unsigned long long)l);
 				}
 			}
@@ -355,21 +356,24 @@ __global__ void __launch_bounds__(128) k_s2_join(S2Join p, S2Geom gm)
 }
 
 // ---------------------------------------------------------------- K8
-__global__ void k_s2_claim_flags(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S,
+// a claim belongs to this rank when its window lies in [g_lo, g_hi) (all of them on a single GPU)
+#define S2_NOCLAIM ((unsigned long long)MCB_CLAIM_NONE)
+__device__ __forceinline__ bool claim_mine(unsigned long long c, uint64_t g_lo, uint64_t g_hi) { return c != S2_NOCLAIM && (c >> 5) >= g_lo && (c >> 5) < g_hi; }
+__global__ void k_s2_claim_flags(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S, uint64_t g_lo, uint64_t g_hi,
                                  uint32_t *__restrict__ f_claim, uint32_t *__restrict__ f_a, uint32_t *__restrict__ f_t)
 {
 	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= S) return;
-	f_claim[s] = claim[s] != S2_EMPTY; f_a[s] = flagged[s] == 1; f_t[s] = flagged[s] == 2;
+	f_claim[s] = claim_mine(claim[s], g_lo, g_hi); f_a[s] = flagged[s] == 1; f_t[s] = flagged[s] == 2;
 }
-__global__ void k_s2_claim_compact(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S,
+__global__ void k_s2_claim_compact(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S, uint64_t g_lo, uint64_t g_hi,
                                    const uint32_t *__restrict__ p_claim, const uint32_t *__restrict__ p_a, const uint32_t *__restrict__ p_t,
                                    ulonglong2 *__restrict__ el, uint32_t *__restrict__ fpa, uint32_t *__restrict__ fpt)
 {
 	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= S) return;
 	unsigned long long c = claim[s];
-	if (c != S2_EMPTY) { ulonglong2 e; e.x = c; e.y = 0xFFFFFFFFull - s; el[p_claim[s]] = e; }   // ascending y == descending sg index
+	if (claim_mine(c, g_lo, g_hi)) { ulonglong2 e; e.x = c - (g_lo << 5); e.y = 0xFFFFFFFFull - s; el[p_claim[s]] = e; }   // local window index; ascending y == descending sg index
 	if (flagged[s] == 1) fpa[p_a[s]] = (uint32_t)s;
 	if (flagged[s] == 2) fpt[p_t[s]] = (uint32_t)s;
 }
@@ -462,19 +466,12 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	return MCB_OK;
 }
 
-extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
-                           int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
+// d_scr roles of one mcb_realign: 0 sg, 3 flags (K8), 4 fpA|fpT, 5 count-min sketch / exact bins, 6 rd, 8 flagged, 9/10 claim elements, 11 claim outputs
+static int realign_geometry(mcb_ctx *ctx, int threshold, int maxsearch, int ininumdict, S2Geom *out)
 {
-	if (!ctx || !res) { mcb_set_error("mcb_realign: null argument"); return MCB_EINVAL; }
-	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	if (!ctx->reads_loaded) { mcb_set_error("mcb_realign: no reads loaded"); return MCB_ESTATE; }
-	if (S && !sg) { mcb_set_error("mcb_realign: null input"); return MCB_EINVAL; }
-	if (S >= 0xFFFFFFFFull) { mcb_set_error("mcb_realign: too many singles"); return MCB_EINVAL; }
-	memset(res, 0, sizeof(*res));
-	const int L = ctx->L, Wd = ctx->Wd, WS = ctx->WS;
-	// ---- geometry (setglobalarrays_realign, kthread_hash_realign.c:150-207)
+	const int L = ctx->L;
 	S2Geom gm; memset(&gm, 0, sizeof gm);
-	gm.L = L; gm.Wd = Wd; gm.WS = WS; gm.thr = threshold; gm.maxsearch = maxsearch;
+	gm.L = L; gm.Wd = ctx->Wd; gm.WS = ctx->WS; gm.thr = threshold; gm.maxsearch = maxsearch;
 	gm.lt = L <= 80 ? 11 : 17;
 	gm.nd = L / gm.lt;
 	if (ininumdict > 1 && ininumdict < gm.nd) gm.nd = ininumdict;
@@ -482,6 +479,21 @@ extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const c
 	int st0 = (ininumdict > 0 && ininumdict < gm.nd) ? L / 2 - (gm.lt * gm.nd) / 2 : 0;
 	for (int i = 0; i < gm.nd; ++i) gm.dstart[i] = st0 + i * gm.lt;
 	gm.enc_limit = (int)((double)L * 0.4);
+	*out = gm;
+	return MCB_OK;
+}
+
+// first half: contigs, singles, join.  Leaves the claim priorities in ctx->d_x[0] (u64[S]).
+static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
+                          uint64_t window_base, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
+{
+	if (!ctx->reads_loaded) { mcb_set_error("mcb_realign: no reads loaded"); return MCB_ESTATE; }
+	if (S && !sg) { mcb_set_error("mcb_realign: null input"); return MCB_EINVAL; }
+	if (S >= 0xFFFFFFFFull) { mcb_set_error("mcb_realign: too many singles"); return MCB_EINVAL; }
+	memset(res, 0, sizeof(*res));
+	const int L = ctx->L, WS = ctx->WS;
+	S2Geom gm;
+	MCB_TRY(realign_geometry(ctx, threshold, maxsearch, ininumdict, &gm));       // setglobalarrays_realign, kthread_hash_realign.c:150-207
 	res->numdict = gm.nd;
 	MCB_TRY(ctx->d_counters.ensure(64 * 8)); MCB_TRY(ctx->h_counters.ensure(64 * 8));
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
@@ -496,50 +508,45 @@ extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const c
 		if (!cx.valid || cx.L != L || cx.lt != gm.lt) { mcb_set_error("mcb_realign: refs == NULL but no contigs from a previous call are cached"); return MCB_ESTATE; }
 		if (n_contigs && n_contigs != cx.n_contigs) { mcb_set_error("mcb_realign: refs == NULL with a different contig count (%llu, cached %llu)", (unsigned long long)n_contigs, (unsigned long long)cx.n_contigs); return MCB_EINVAL; }
 	}
-	n_contigs = cx.n_contigs;
 	const uint64_t n_windows = cx.n_windows;
+	if (window_base + n_windows >= (1ull << 57)) { mcb_set_error("too many windows"); return MCB_EINVAL; }
 	res->n_windows = n_windows;
 	{
 		int nrev = 0; for (int l = 0; l < gm.nd; ++l) nrev += gm.dstart[l] > 0;
 		res->n_probes = n_windows * (uint64_t)(gm.nd + nrev);                 // what the reference's window loop would issue (:355-504)
 	}
 	const uint64_t nkv = S * (uint64_t)gm.nd;
-	if (S == 0 || n_windows == 0 || gm.nd == 0) return MCB_OK;
-	if (nkv >= 0xFFFFFFFFull) { mcb_set_error("dictionary too large"); return MCB_EINVAL; }
-	// d_scr roles: 0 sg, 3 flags (K8), 4 fpA|fpT, 5 count-min sketch / exact bins, 6 rd, 8 flagged, 9/10 claim elements, 11 claim outputs
-	DBuf &b_sg = ctx->d_scr[0], &b_fl3 = ctx->d_scr[3], &b_fp = ctx->d_scr[4], &b_cm = ctx->d_scr[5], &b_rd = ctx->d_scr[6], &b_fl = ctx->d_scr[8];
-	DBuf &b_elA = ctx->d_scr[9], &b_elB = ctx->d_scr[10], &b_out = ctx->d_scr[11];
-	uint64_t CM = 1024; while (CM < 2 * nkv && CM < (1ull << 28)) CM <<= 1;
-	MCB_TRY(b_sg.ensure(S * 4 + 16)); MCB_TRY(b_rd.ensure(S * WS * 8 + 16)); MCB_TRY(b_fl.ensure(S + 16)); MCB_TRY(b_cm.ensure(CM * 4));
+	ctx->rs.pending = true; ctx->rs.S = S; ctx->rs.window_base = window_base; ctx->rs.nd = gm.nd;
 	MCB_TRY(ctx->d_x[0].ensure(S * 8 + 16));                   // claim priorities
 	unsigned long long *claim = ctx->d_x[0].as<unsigned long long>();
+	if (S) MCB_CUDA(cudaMemsetAsync(claim, 0x7F, S * 8, ctx->stream));          // MCB_CLAIM_NONE
+	DBuf &b_sg = ctx->d_scr[0], &b_cm = ctx->d_scr[5], &b_rd = ctx->d_scr[6], &b_fl = ctx->d_scr[8];
+	MCB_TRY(b_sg.ensure(S * 4 + 16)); MCB_TRY(b_rd.ensure(S * WS * 8 + 16)); MCB_TRY(b_fl.ensure(S + 16));
+	if (S == 0 || gm.nd == 0) return MCB_OK;
+	if (nkv >= 0xFFFFFFFFull) { mcb_set_error("dictionary too large"); return MCB_EINVAL; }
+	uint64_t CM = 1024; while (CM < 2 * nkv && CM < (1ull << 28)) CM <<= 1;
+	MCB_TRY(b_cm.ensure(CM * 4));
 	{
 		McbSpan sp(ctx->tm, "h2d");
 		MCB_CUDA(cudaMemcpyAsync(b_sg.p, sg, S * 4, cudaMemcpyHostToDevice, ctx->stream));
 	}
-	const int span_h = ctx->tm.begin("realign");
+	McbSpan span(ctx->tm, "realign");
 	MCB_CUDA(cudaMemsetAsync(b_cm.p, 0, CM * 4, ctx->stream));
 	MCB_LAUNCH(ctx, "s2_singles", k_s2_singles, mcb_grid_for(S, 128), 128, 0, b_sg.as<uint32_t>(), S, ctx->d_packed.as<uint64_t>(), gm,
 	           ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->n_nreads, ctx->n_reads,
 	           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, dc);
+	if (n_windows == 0) {          // no contig long enough on this rank: the diversion lists are still needed
+		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }
+		return MCB_OK;
+	}
 	S2Join jn; memset(&jn, 0, sizeof jn);
 	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents_sorted; jn.pbits = cx.pbits;
 	jn.pblk = cx.pblk.as<uint32_t>(); jn.ref_off = cx.roff.as<uint64_t>(); jn.cw = cx.cw.as<uint64_t>(); jn.cw_off = cx.cwo.as<uint64_t>(); jn.woff = cx.wo.as<uint64_t>();
-	jn.claim = claim; jn.counters = dc;
-	MCB_CUDA(cudaMemsetAsync(claim, 0xFF, S * 8, ctx->stream));
-	MCB_LAUNCH(ctx, "s2_join", k_s2_join, mcb_grid_for(nkv, 128), 128, 0, jn, gm);
-	// ---- K8
-	MCB_TRY(b_fl3.ensure(S * 12 + 64));
-	uint32_t *f_c = b_fl3.as<uint32_t>(), *f_a = f_c + S, *f_t = f_a + S;
-	MCB_TRY(b_elA.ensure(S * 16 + 16)); MCB_TRY(b_elB.ensure(S * 16 + 16)); MCB_TRY(b_fp.ensure(S * 8 + 64));
-	ulonglong2 *elA = b_elA.as<ulonglong2>(), *elB = b_elB.as<ulonglong2>();
-	uint32_t *d_fpa = b_fp.as<uint32_t>(), *d_fpt = d_fpa + S;
+	jn.claim = claim; jn.window_base = window_base; jn.counters = dc;
 	for (int attempt = 0;; ++attempt) {
-		MCB_LAUNCH(ctx, "s2_claim_flags", k_s2_claim_flags, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, f_c, f_a, f_t);
-		MCB_TRY(mcb_exclusive_scan_u32(ctx, f_c, S, (uint64_t*)&dc[CT_S2_CLAIMS]));
-		MCB_TRY(mcb_exclusive_scan_u32(ctx, f_a, S, (uint64_t*)&dc[CT_S2_FPA]));
-		MCB_TRY(mcb_exclusive_scan_u32(ctx, f_t, S, (uint64_t*)&dc[CT_S2_FPT]));
-		MCB_LAUNCH(ctx, "s2_claim_compact", k_s2_claim_compact, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, f_c, f_a, f_t, elA, d_fpa, d_fpt);
+		MCB_LAUNCH(ctx, "s2_join", k_s2_join, mcb_grid_for(nkv, 128), 128, 0, jn, gm);
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 		if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }
@@ -557,11 +564,39 @@ extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const c
 		MCB_LAUNCH(ctx, "s2_bins_exact", k_s2_bins_exact, mcb_grid_for(nkv, 256), 256, 0, b_rd.as<uint64_t>(), S, gm, tkey, tcnt, H - 1);
 		jn.xkey = tkey; jn.xcnt = tcnt; jn.xmask = H - 1;
 		MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_CAND], 0, 8, ctx->stream)); MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NEEDEXACT], 0, 8, ctx->stream));
-		MCB_CUDA(cudaMemsetAsync(claim, 0xFF, S * 8, ctx->stream));
-		MCB_LAUNCH(ctx, "s2_join", k_s2_join, mcb_grid_for(nkv, 128), 128, 0, jn, gm);
+		MCB_CUDA(cudaMemsetAsync(claim, 0x7F, S * 8, ctx->stream));
 	}
-	const uint64_t ncl = hc[CT_S2_CLAIMS], nfa = hc[CT_S2_FPA], nft = hc[CT_S2_FPT];
 	res->n_candidates = hc[CT_S2_CAND];
+	return MCB_OK;
+}
+
+// second half (K8): compact the claims that lie on this context's contigs, order them, copy the lists to the host
+static int realign_claims(mcb_ctx *ctx, mcb_realign_result *res)
+{
+	if (!ctx->rs.pending) { mcb_set_error("mcb_realign_finish: no search pending"); return MCB_ESTATE; }
+	ctx->rs.pending = false;
+	const uint64_t S = ctx->rs.S, window_base = ctx->rs.window_base;
+	McbContigIndex &cx = ctx->cix;
+	const uint64_t n_windows = cx.n_windows, n_contigs = cx.n_contigs;
+	if (S == 0 || ctx->rs.nd == 0) return MCB_OK;
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
+	unsigned long long *claim = ctx->d_x[0].as<unsigned long long>();
+	DBuf &b_sg = ctx->d_scr[0], &b_fl3 = ctx->d_scr[3], &b_fp = ctx->d_scr[4], &b_fl = ctx->d_scr[8], &b_elA = ctx->d_scr[9], &b_elB = ctx->d_scr[10], &b_out = ctx->d_scr[11];
+	MCB_TRY(b_fl3.ensure(S * 12 + 64));
+	uint32_t *f_c = b_fl3.as<uint32_t>(), *f_a = f_c + S, *f_t = f_a + S;
+	MCB_TRY(b_elA.ensure(S * 16 + 16)); MCB_TRY(b_elB.ensure(S * 16 + 16)); MCB_TRY(b_fp.ensure(S * 8 + 64));
+	ulonglong2 *elA = b_elA.as<ulonglong2>(), *elB = b_elB.as<ulonglong2>();
+	uint32_t *d_fpa = b_fp.as<uint32_t>(), *d_fpt = d_fpa + S;
+	const int span_h = ctx->tm.begin("realign");
+	MCB_LAUNCH(ctx, "s2_claim_flags", k_s2_claim_flags, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, window_base, window_base + n_windows, f_c, f_a, f_t);
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_c, S, (uint64_t*)&dc[CT_S2_CLAIMS]));
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_a, S, (uint64_t*)&dc[CT_S2_FPA]));
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_t, S, (uint64_t*)&dc[CT_S2_FPT]));
+	MCB_LAUNCH(ctx, "s2_claim_compact", k_s2_claim_compact, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, window_base, window_base + n_windows, f_c, f_a, f_t, elA, d_fpa, d_fpt);
+	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	const uint64_t ncl = hc[CT_S2_CLAIMS], nfa = hc[CT_S2_FPA], nft = hc[CT_S2_FPT];
 	std::vector<McbSortPass> passes;
 	mcb_add_bit_passes(passes, 1, 0, mcb_bits_for(S));                                // 0xFFFFFFFF-s: only the low bits vary
 	mcb_add_bit_passes(passes, 0, 0, 5 + mcb_bits_for(n_windows));
@@ -588,4 +623,34 @@ extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const c
 	res->n_claims = ncl; res->claim_contig = ctx->h_claim_c.as<uint32_t>(); res->claim_sg = ctx->h_claim_s.as<uint32_t>(); res->claim_y = ctx->h_claim_y.as<uint64_t>();
 	res->n_fpA = nfa; res->n_fpT = nft; res->fpA_sg = ctx->h_fpA.as<uint32_t>(); res->fpT_sg = ctx->h_fpT.as<uint32_t>();
 	return MCB_OK;
+}
+
+static mcb_realign_result g_pending_result;   // counters of the search half, carried to mcb_realign_finish (one pending search per process is enough for the sharded driver)
+
+extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
+                           int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
+{
+	if (!ctx || !res) { mcb_set_error("mcb_realign: null argument"); return MCB_EINVAL; }
+	MCB_CUDA(cudaSetDevice(ctx->prm.device));
+	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, 0, threshold, maxsearch, ininumdict, res));
+	return realign_claims(ctx, res);
+}
+
+extern "C" int mcb_realign_begin(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
+                                 uint64_t window_base, int threshold, int maxsearch, int ininumdict, void **d_claim)
+{
+	if (!ctx || !d_claim) { mcb_set_error("mcb_realign_begin: null argument"); return MCB_EINVAL; }
+	MCB_CUDA(cudaSetDevice(ctx->prm.device));
+	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, window_base, threshold, maxsearch, ininumdict, &g_pending_result));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));        // the caller reduces the array on its own stream
+	*d_claim = ctx->d_x[0].p;
+	return MCB_OK;
+}
+
+extern "C" int mcb_realign_finish(mcb_ctx *ctx, mcb_realign_result *res)
+{
+	if (!ctx || !res) { mcb_set_error("mcb_realign_finish: null argument"); return MCB_EINVAL; }
+	MCB_CUDA(cudaSetDevice(ctx->prm.device));
+	*res = g_pending_result;
+	return realign_claims(ctx, res);
 }
