@@ -334,6 +334,184 @@ def bench_ours(args):
         dist.destroy_process_group()
 
 
+def load_recorded(rec, pin):
+    idx_calls, realign_calls = [], []
+    j = 0
+    while os.path.exists(os.path.join(rec, f"idx_{j}.off.u64")):
+        idx_calls.append((np.fromfile(os.path.join(rec, f"idx_{j}.xy.u64"), dtype=np.uint64), np.fromfile(os.path.join(rec, f"idx_{j}.off.u64"), dtype=np.uint64)))
+        j += 1
+    j = 0
+    while os.path.exists(os.path.join(rec, f"realign_{j}.meta.u64")):
+        meta = np.fromfile(os.path.join(rec, f"realign_{j}.meta.u64"), dtype=np.uint64)
+        realign_calls.append((np.fromfile(os.path.join(rec, f"realign_{j}.sg.u32"), dtype=np.uint32), np.fromfile(os.path.join(rec, f"realign_{j}.refs.u8"), dtype=np.uint8),
+                              np.fromfile(os.path.join(rec, f"realign_{j}.off.u64"), dtype=np.uint64), int(meta[0]), int(meta[1]), int(meta[2])))
+        j += 1
+    return idx_calls, realign_calls
+
+
+def bench_sharded(args):
+    """N > 1: ONE job over N x n reads, sharded as SURVEY.md 8e says (minicom_b200/shard.py): reads by read-id range, tuples
+    all-to-all by bucket owner, packed reads all-gathered, index builds by bucket range, contigs partitioned for Stage 2 with a
+    min-reduce of the claim priorities.  The host-side inputs (what the contig merger hands to mm_idx_generation / realign_hash)
+    come from one untimed drop-in run of the whole job on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from minicom_b200 import api, shard, synth
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n, L, G, mode, ref_env = WORKLOADS[args.workload]
+    if args.reads:
+        n, G = args.reads, max(1000, args.reads * 5)
+    n_total, G_total = n * world, G * world
+    threads = args.host_threads or min(os.cpu_count() or 1, 32)
+    exe = os.path.join(ROOT, "dropin", "_build", f"minicom_b200_L{L}_{mode}")
+    if not os.path.exists(exe):
+        raise SystemExit(f"{exe} missing: run __graft_entry__.build() where /root/reference exists (no CPU fallback)")
+    # ---- prepare (untimed)
+    t0 = time.time()
+    genome = synth.make_genome(G_total, seed=1)
+    reads = synth.make_reads(n, L, G_total, seed=101 + rank, genome=genome)      # rank r holds read ids [r*n, (r+1)*n) of the job
+    del genome
+    box = [tempfile.mkdtemp(prefix="mcb_bench_shard_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    wd = box[0]
+    synth.write_fastq(os.path.join(wd, f"part_{rank}.fastq"), reads)
+    dist.barrier()
+    rec = os.path.join(wd, "rec")
+    if rank == 0:
+        os.makedirs(rec)
+        fq = os.path.join(wd, "in.fastq")
+        with open(fq, "wb") as out:
+            for q in range(world):
+                with open(os.path.join(wd, f"part_{q}.fastq"), "rb") as f:
+                    shutil.copyfileobj(f, out, 64 << 20)
+                os.remove(os.path.join(wd, f"part_{q}.fastq"))
+        log(f"[rank 0] job: {n_total} x {L} bp over {world} GPUs, inputs ready in {time.time() - t0:.1f}s; one untimed drop-in run records the call sequence")
+        dt = run_binary(exe, fq, wd, dict(ref_env, MCB_RECORD=rec, MCB_DEVICE=local), threads)
+        os.remove(fq)
+        log(f"[rank 0] drop-in run: front end {front_end_seconds(dt):.3f}s inside the entry points; whole program {dt['wall_total']:.1f}s")
+    dist.barrier()
+    idx_calls, realign_calls = load_recorded(rec, None)
+    dist.barrier()
+    if rank == 0:
+        shutil.rmtree(wd, ignore_errors=True)
+    keep = []
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep.append(t)
+        return t.numpy()
+
+    # this rank's share of every recorded call
+    b0, b1 = shard.bucket_range(rank, world)
+    my_idx = []
+    for xy, off in idx_calls:
+        lo, hi = int(off[b0]), int(off[b1])
+        mine = np.full(shard.NB + 1, hi - lo, dtype=np.uint64)
+        mine[:b0] = 0
+        mine[b0:b1 + 1] = off[b0:b1 + 1] - np.uint64(lo)
+        my_idx.append((pin(xy.reshape(-1, 2)[lo:hi]), mine))
+    my_realign = []
+    for j, (sg, refs, off, thr, ms, nd) in enumerate(realign_calls):
+        same = j > 0 and np.array_equal(refs, realign_calls[j - 1][1]) and np.array_equal(off, realign_calls[j - 1][2])
+        cuts, wbase = shard.contig_partition(off, world, L)
+        c0, c1 = int(cuts[rank]), int(cuts[rank + 1])
+        my_realign.append((pin(sg), None if same else pin(refs[int(off[c0]):int(off[c1])]), None if same else (off[c0:c1 + 1] - off[c0]), int(wbase[rank]), thr, ms, nd))
+    T_cb = int(sum(len(x[0]) // 2 for x in idx_calls))
+    R_total = int(len(realign_calls[0][1])) if realign_calls else 0
+    del idx_calls, realign_calls
+    rows_pinned = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
+    rows_pinned.numpy()[:] = reads
+    rows_dev = rows_pinned.to(dev)
+    del reads
+    params = api.resolve_params(L, device=local, **{k: int(ref_env[e]) for k, e in (("k", "MC_K"), ("e", "MC_E"), ("w", "MC_W"), ("m", "MC_M")) if e in ref_env})
+    ctx = api.Context(params)
+    ctx.timers_enable(True)
+    fe = shard.ShardedFrontEnd(ctx, dist, dev)
+    fe.time_collectives = True
+    stats = {}
+
+    def step(device_resident):
+        rr, part = fe.stage1(rows_dev if device_resident else rows_pinned.numpy(), n_total, device_resident)
+        for xy, off in my_idx:
+            ctx.idx_build(xy, off).close()
+        claims = 0
+        for sg, refs, off, wb, thr, ms, nd in my_realign:
+            r = fe.realign(sg, refs, off, wb, thr, ms, nd)
+            claims += len(r.claim_y)
+        stats.update({"seed_contigs_rank0": int(len(part.cl_n)), "singles_rank0": int(len(part.sg)), "claims_rank0": claims, "bucket_rounds": int(len(part.rounds))})
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_ms(tm):
+        return sum(tm.get(k, (0.0, 0))[0] for k in ("for_reads", "for_bucket", "idx_build", "realign"))
+
+    for _ in range(args.warmup):
+        step(True)
+        step(False)
+    ctx.timers_reset()
+    fe.collective_ms()
+    fe.bytes_exchanged = 0
+    barrier()
+    with ClockSampler(local) as clk:
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(True)
+        barrier()
+        wall_dev_arm = time.perf_counter() - w0
+        tm = ctx.timers()
+        launches = ctx.kernel_launches()
+        coll_ms = fe.collective_ms()
+        sent = fe.bytes_exchanged
+        ctx.timers_reset()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(False)
+        barrier()
+        wall_e2e = time.perf_counter() - w0
+        tm_e2e = ctx.timers()
+    ms_dev = (dev_ms(tm) + coll_ms) / args.steps
+    vals = torch.tensor([ms_dev, wall_e2e / args.steps * 1e3, wall_dev_arm / args.steps * 1e3, coll_ms / args.steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_dev_max, ms_e2e_max, ms_wall_dev_max, coll_max = (float(x) for x in vals.cpu())
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kern = {k: v for k, v in tm.items() if k.startswith("k:")}
+        dom = max(kern, key=lambda k: kern[k][0])
+        value = n_total / (ms_dev_max / 1e3)
+        line = {
+            "metric": "reads/sec for sketch+index+overlap stage", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_dev_max, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{args.workload} x {world}: ONE job of {n_total} x {L} bp reads ({n} per GPU), {G_total} bp random genome, 1% substitutions, mode {mode}, defaults k=31 m=6 e=4",
+                       "sharding": "reads by read-id range; tuples all-to-all by bucket owner (bucket*G>>14) every round; packed reads all-gather; index builds by bucket range; "
+                                   "Stage 2 contigs partitioned, claim priorities all-reduce(MIN); results bit-identical to one GPU (tests/test_gpu_shard.py)",
+                       "l2": "inputs larger than L2 (reads %.0f MB per GPU per step)" % (n * L / 1e6),
+                       "timing": "value = max over ranks of (CUDA-event time of the library entry points + CUDA-event time of the NCCL collectives), reads resident in HBM; e2e = max over ranks of the wall clock with pinned host inputs and results copied back",
+                       "bases_per_s": round(value * L, 1), "wall_ms_per_step_device_arm": round(ms_wall_dev_max, 3), "collective_ms_per_step": round(coll_max, 3),
+                       "nccl_bytes_sent_per_step_rank0": int(sent // max(1, args.steps)), "T_cb": T_cb, "contig_bases": R_total, "rank0": stats,
+                       "device_ms_by_entry_point_rank0": {k: round(tm[k][0] / args.steps, 4) for k in ("for_reads", "for_bucket", "idx_build", "realign") if k in tm},
+                       "kernel_ms_per_step_rank0": {k[2:]: round(v[0] / args.steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:12]}, "host_threads": threads},
+            "e2e": {"value": round(n_total / (ms_e2e_max / 1e3), 1), "unit": "reads/s", "h2d_bytes_per_step": int(n * L + sum(x[0].nbytes + x[1].nbytes for x in my_idx) + sum(c[0].nbytes + (c[1].nbytes if c[1] is not None else 0) for c in my_realign)),
+                    "d2h_bytes_per_step": None, "ms_per_step": round(ms_e2e_max, 3), "copy_ms_per_step_rank0": {k: round(tm_e2e[k][0] / args.steps, 3) for k in ("h2d", "d2h") if k in tm_e2e},
+                    "note": "byte counts are rank 0's"},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": dom[2:], "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                         "note": "per-kernel roofline is reported by the N=1 run; this line is about scaling"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def cpu_baseline(workload, steps, quiet=False, warmup=0):
     """The reference's own CPU implementation (oracle/_ref, unmodified sources) on a bounded sample, all host threads."""
     from minicom_b200 import synth
@@ -388,9 +566,12 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="override reads per GPU (debug)")
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent single-GPU jobs instead of one sharded job")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)
+    elif int(os.environ.get("WORLD_SIZE", 1)) > 1 and not args.replicas:
+        bench_sharded(args)
     else:
         bench_ours(args)
 

@@ -151,6 +151,26 @@ class ShardedFrontEnd:
         self.ctx, self.dist, self.device, self.torch = ctx, dist, device, torch
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.bytes_exchanged = 0
+        self.time_collectives = False
+        self._events = []
+
+    def _coll(self, fn, *a, **kw):
+        """run a collective; when asked, bracket it with CUDA events on the stream it is enqueued on"""
+        if not self.time_collectives:
+            return fn(*a, **kw)
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **kw)
+        e1.record()
+        self._events.append((e0, e1))
+        return r
+
+    def collective_ms(self, reset=True):
+        self.torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._events)
+        if reset:
+            self._events = []
+        return ms
 
     # ---- Stage 1: kt_for_reads + kt_for_bucket over the whole read set
     def stage1(self, rows_local, n_total: int, device_resident: bool = False):
@@ -166,7 +186,7 @@ class ShardedFrontEnd:
         cap = (n_total + self.world - 1) // self.world
         whole = dev_view(ptr, self.world * cap * rb, self.device)
         mine = whole[self.rank * cap * rb:(self.rank + 1) * cap * rb].clone()
-        dist.all_gather_into_tensor(whole, mine)
+        self._coll(dist.all_gather_into_tensor, whole, mine)
         self.bytes_exchanged += whole.numel()
         # the (rare) reads that contained N: every rank needs all of them for the near-poly-A/T test of Stage 2
         nrid, nmask = ctx.shard_get_nreads()
@@ -184,20 +204,20 @@ class ShardedFrontEnd:
             counts, _ = ctx.shard_partition(self.world)
             sc = torch.as_tensor(counts.astype(np.int64), device=self.device)
             rcnt = torch.empty(self.world, dtype=torch.int64, device=self.device)
-            dist.all_to_all_single(rcnt, sc)
+            self._coll(dist.all_to_all_single, rcnt, sc)
             recv_counts = rcnt.cpu().numpy()
             n_send, n_recv = int(counts.sum()), int(recv_counts.sum())
             rptr, sptr = ctx.shard_recv_buffer(n_recv)
             send = dev_view(sptr, n_send * 16, self.device).view(torch.int64).view(-1, 2)
             recv = dev_view(rptr, n_recv * 16, self.device).view(torch.int64).view(-1, 2)
-            dist.all_to_all_single(recv, send, output_split_sizes=[int(x) for x in recv_counts], input_split_sizes=[int(x) for x in counts])
+            self._coll(dist.all_to_all_single, recv, send, output_split_sizes=[int(x) for x in recv_counts], input_split_sizes=[int(x) for x in counts])
             torch.cuda.synchronize()
             self.bytes_exchanged += n_send * 16
             ctx.shard_set_tuples(n_recv)
             n_cl_new, n_mem_new, _, _ = ctx.bucket_round_a(int(rc.round), int(is_last))
             mine2 = torch.tensor([n_cl_new, n_mem_new], dtype=torch.int64, device=self.device)
             allc = torch.empty((self.world, 2), dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(allc, mine2)
+            self._coll(dist.all_gather_into_tensor, allc, mine2)
             allc = allc.cpu().numpy()
             ctx.bucket_round_b(tot_cl + int(allc[:self.rank, 0].sum()))
             tot_cl += int(allc[:, 0].sum())
@@ -222,7 +242,7 @@ class ShardedFrontEnd:
             raise err or RuntimeError("mcb_realign_begin failed on another rank")
         claim = dev_view(ptr, len(sg) * 8, self.device).view(torch.int64)
         if len(sg):
-            dist.all_reduce(claim, op=dist.ReduceOp.MIN)
+            self._coll(dist.all_reduce, claim, op=dist.ReduceOp.MIN)
             self.bytes_exchanged += len(sg) * 8
         torch.cuda.synchronize()
         return ctx.realign_finish()
