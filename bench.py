@@ -47,6 +47,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Native libraries (NCCL's version banner, the reference binary) also write to
+# file descriptor 1, so the real stdout is set aside and everything else is sent to stderr.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def unlimit_stack():
     import resource
     try:
@@ -328,7 +350,7 @@ def bench_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -431,6 +453,7 @@ def bench_sharded(args):
     ctx.timers_enable(True)
     fe = shard.ShardedFrontEnd(ctx, dist, dev)
     fe.time_collectives = True
+    api.VIEW_COPY = False          # results are consumed (counted) before the next call: no second copy on the host
     stats = {}
 
     def step(device_resident):
@@ -506,7 +529,7 @@ def bench_sharded(args):
                          "note": "per-kernel roofline is reported by the N=1 run; this line is about scaling"},
             "cpu_baseline": None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -553,7 +576,7 @@ def bench_reference(args):
             "config": {"workload": f"{args.workload}: {wn} x {wL} bp reads per GPU, {wG} bp random genome, 1% substitutions, mode {mode}, defaults k=31 m=6 e=4",
                        "note": "CPU arm timed on a bounded sample of the workload (see cpu_baseline.sample); the reference is a single-process CPU program, so its value does not grow with n_gpus"},
             "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -568,6 +591,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent single-GPU jobs instead of one sharded job")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         bench_reference(args)
     elif int(os.environ.get("WORLD_SIZE", 1)) > 1 and not args.replicas:

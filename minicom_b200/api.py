@@ -137,12 +137,18 @@ def load_library() -> C.CDLL:
     return lib
 
 
+# Result arrays live in context-owned pinned memory that the next call of the same entry point overwrites, so the wrappers
+# copy them out by default.  Callers that consume a result before the next call (bench.py) can switch the copies off.
+VIEW_COPY = True
+
+
 def _view(ptr, n, dtype):
     if not n or not ptr:
         return np.zeros(0, dtype=dtype)
     nbytes = int(n) * np.dtype(dtype).itemsize
     buf = (C.c_char * nbytes).from_address(ptr)
-    return np.frombuffer(buf, dtype=dtype).copy()
+    a = np.frombuffer(buf, dtype=dtype)
+    return a.copy() if VIEW_COPY else a
 
 
 def resolve_params(readlen, k=0, e=0, w=0, m=0, max_rounds=0, device=0) -> Params:

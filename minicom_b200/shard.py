@@ -190,9 +190,12 @@ class ShardedFrontEnd:
         self.bytes_exchanged += whole.numel()
         # the (rare) reads that contained N: every rank needs all of them for the near-poly-A/T test of Stage 2
         nrid, nmask = ctx.shard_get_nreads()
-        gathered = [None] * self.world
-        dist.all_gather_object(gathered, (nrid, nmask))
-        if sum(len(g[0]) for g in gathered):
+        ncnt = torch.tensor([len(nrid)], dtype=torch.int64, device=self.device)
+        nall = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        self._coll(dist.all_gather_into_tensor, nall, ncnt)
+        if int(nall.sum().item()):
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (np.array(nrid), np.array(nmask)))
             ctx.shard_set_nreads(np.concatenate([g[0] for g in gathered]), np.concatenate([g[1] for g in gathered]))
         torch.cuda.synchronize()
         # rounds
