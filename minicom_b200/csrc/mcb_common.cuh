@@ -161,6 +161,7 @@ struct McbContigIndex {
 	DBuf ptab;      // u32[2^pbits+1] bucket ends of the k-mer table
 	DBuf ents, ents2; // u64[n_entries] key<<30 | global base position, ordered by a hash of the key (double buffer of the sort)
 	unsigned long long *ents_sorted = nullptr;
+	DBuf meta;      // S2ContigMeta[n_contigs+1]: {ref_off, cw_off, woff, len} per contig, 32 bytes
 	DBuf eoff;      // u64[n_contigs+1] entry offsets (prefix sums of len-lt+1 over contigs with windows)
 };
 

@@ -44,16 +44,51 @@ k_sort_hist(const E *__restrict__ in, uint64_t n, D digit, uint32_t *__restrict_
 	hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
+// Exclusive scan of every digit's row of the digit-major tile histogram (row d = counts of digit d per tile), one CTA per
+// digit; the row totals go to rowsum[256].  Together with a 256-value scan inside the scatter kernel this replaces a
+// general multi-level scan (3-5 launches per pass) by one launch.
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_rowscan(uint32_t *__restrict__ hist, unsigned nblocks, uint32_t *__restrict__ rowsum)
+{
+	__shared__ unsigned wsum[SORT_WARPS];
+	__shared__ unsigned carry_s;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t *row = hist + (uint64_t)blockIdx.x * nblocks;
+	if (threadIdx.x == 0) carry_s = 0;
+	__syncthreads();
+	for (unsigned base = 0; base < nblocks; base += SORT_THREADS * 4) {
+		unsigned v[4], tot = 0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) { unsigned i = base + threadIdx.x * 4 + j; v[j] = i < nblocks ? row[i] : 0u; tot += v[j]; }
+		unsigned inc = tot;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+		if (lane == 31) wsum[w] = inc;
+		__syncthreads();
+		unsigned wb = 0, all = 0;
+#pragma unroll
+		for (int ww = 0; ww < SORT_WARPS; ++ww) { unsigned t = wsum[ww]; if (ww < w) wb += t; all += t; }
+		unsigned run = carry_s + wb + inc - tot;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) { unsigned i = base + threadIdx.x * 4 + j; if (i < nblocks) row[i] = run; run += v[j]; }
+		__syncthreads();
+		if (threadIdx.x == 0) carry_s += all;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) rowsum[blockIdx.x] = carry_s;
+}
+
 // Stable scatter of one tile.  Elements are first ranked inside the tile (warp-private digit counters +
 // __match_any_sync), parked in shared memory in digit order, and then written out so that consecutive threads write
 // consecutive addresses of a digit's run: global stores are whole sectors instead of 32 scattered 8/16-byte pieces.
 template <class E, class D>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_scatter(const E *__restrict__ in, E *__restrict__ out, uint64_t n, D digit, const uint32_t *__restrict__ hist_scanned, unsigned nblocks)
+k_sort_scatter(const E *__restrict__ in, E *__restrict__ out, uint64_t n, D digit, const uint32_t *__restrict__ hist_scanned, unsigned nblocks,
+               const uint32_t *__restrict__ rowsum)
 {
 	__shared__ unsigned wcnt[SORT_WARPS][256];
 	__shared__ unsigned gbase[256];
-	__shared__ unsigned wsum[SORT_WARPS];
+	__shared__ unsigned wsum[SORT_WARPS], rsum[SORT_WARPS];
 	__shared__ E stage[SORT_TILE];
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
@@ -77,16 +112,21 @@ k_sort_scatter(const E *__restrict__ in, E *__restrict__ out, uint64_t n, D digi
 		unsigned c[SORT_WARPS], tot = 0;
 #pragma unroll
 		for (int ww = 0; ww < SORT_WARPS; ++ww) { c[ww] = wcnt[ww][d]; tot += c[ww]; }
-		unsigned inc = tot;
+		const unsigned rs = rowsum[d];                           // elements with digit d in the whole input
+		unsigned inc = tot, rinc = rs;
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
-		if (lane == 31) wsum[w] = inc;
+		for (int o = 1; o < 32; o <<= 1) {
+			unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o), u = __shfl_up_sync(0xFFFFFFFFu, rinc, o);
+			if (lane >= o) { inc += t; rinc += u; }
+		}
+		if (lane == 31) { wsum[w] = inc; rsum[w] = rinc; }
 		__syncthreads();
-		unsigned wb = 0;
+		unsigned wb = 0, rb = 0;
 #pragma unroll
-		for (int ww = 0; ww < SORT_WARPS; ++ww) if (ww < w) wb += wsum[ww];
+		for (int ww = 0; ww < SORT_WARPS; ++ww) if (ww < w) { wb += wsum[ww]; rb += rsum[ww]; }
 		unsigned run = wb + inc - tot;                           // tile-local start of digit d
-		gbase[d] = hist_scanned[(uint64_t)d * nblocks + blockIdx.x] - run;
+		const unsigned dstart = rb + rinc - rs;                  // global start of digit d
+		gbase[d] = dstart + hist_scanned[(uint64_t)d * nblocks + blockIdx.x] - run;
 #pragma unroll
 		for (int ww = 0; ww < SORT_WARPS; ++ww) { wcnt[ww][d] = run; run += c[ww]; }
 	}
@@ -212,14 +252,14 @@ int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const
 	if (n <= 1 || n_passes == 0) return MCB_OK;
 	uint64_t nb = (n + SORT_TILE - 1) / SORT_TILE;
 	if (nb > 0x7FFFFFFFull) { mcb_set_error("sort input too large"); return MCB_EINVAL; }
-	MCB_TRY(ctx->d_sort_hist.ensure(nb * 256 * sizeof(uint32_t)));
-	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>();
+	MCB_TRY(ctx->d_sort_hist.ensure((nb + 1) * 256 * sizeof(uint32_t)));
+	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>(), *rowsum = hist + nb * 256;
 	ulonglong2 *src = a, *dst = b;
 	for (int p = 0; p < n_passes; ++p) {
 		DigitPair dg = { passes[p].word, passes[p].shift, (1u << passes[p].bits) - 1u };
 		MCB_LAUNCH(ctx, "sort_hist", (k_sort_hist<ulonglong2, DigitPair>), (unsigned)nb, SORT_THREADS, 0, src, n, dg, hist, (unsigned)nb);
-		MCB_TRY(mcb_exclusive_scan_u32(ctx, hist, nb * 256, nullptr));
-		MCB_LAUNCH(ctx, "sort_scatter", (k_sort_scatter<ulonglong2, DigitPair>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb);
+		MCB_LAUNCH(ctx, "sort_rowscan", k_sort_rowscan, 256, SORT_THREADS, 0, hist, (unsigned)nb, rowsum);
+		MCB_LAUNCH(ctx, "sort_scatter", (k_sort_scatter<ulonglong2, DigitPair>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb, rowsum);
 		ulonglong2 *t = src; src = dst; dst = t;
 	}
 	*sorted_out = src;
@@ -233,16 +273,16 @@ int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long
 	if (n <= 1) return MCB_OK;
 	uint64_t nb = (n + SORT_TILE - 1) / SORT_TILE;
 	if (nb > 0x7FFFFFFFull) { mcb_set_error("sort input too large"); return MCB_EINVAL; }
-	MCB_TRY(ctx->d_sort_hist.ensure(nb * 256 * sizeof(uint32_t)));
-	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>();
+	MCB_TRY(ctx->d_sort_hist.ensure((nb + 1) * 256 * sizeof(uint32_t)));
+	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>(), *rowsum = hist + nb * 256;
 	unsigned long long *src = a, *dst = b;
 	const int n_passes = (pbits + 7) / 8;
 	for (int p = 0, lo = 0; p < n_passes; ++p) {
 		const int bits = (pbits - lo + (n_passes - p) - 1) / (n_passes - p);      // spread the bits evenly over the passes
 		DigitKmer dg = { pbits, lo, (1u << bits) - 1u };
 		MCB_LAUNCH(ctx, "s2_kmer_sort_hist", (k_sort_hist<unsigned long long, DigitKmer>), (unsigned)nb, SORT_THREADS, 0, src, n, dg, hist, (unsigned)nb);
-		MCB_TRY(mcb_exclusive_scan_u32(ctx, hist, nb * 256, nullptr));
-		MCB_LAUNCH(ctx, "s2_kmer_sort_scatter", (k_sort_scatter<unsigned long long, DigitKmer>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb);
+		MCB_LAUNCH(ctx, "sort_rowscan", k_sort_rowscan, 256, SORT_THREADS, 0, hist, (unsigned)nb, rowsum);
+		MCB_LAUNCH(ctx, "s2_kmer_sort_scatter", (k_sort_scatter<unsigned long long, DigitKmer>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb, rowsum);
 		unsigned long long *t = src; src = dst; dst = t;
 		lo += bits;
 	}
@@ -271,17 +311,15 @@ int mcb_partition_by_owner(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t 
 	}
 	uint64_t nb = (n + SORT_TILE - 1) / SORT_TILE;
 	if (nb > 0x7FFFFFFFull) { mcb_set_error("sort input too large"); return MCB_EINVAL; }
-	MCB_TRY(ctx->d_sort_hist.ensure(nb * 256 * sizeof(uint32_t)));
-	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>();
+	MCB_TRY(ctx->d_sort_hist.ensure((nb + 1) * 256 * sizeof(uint32_t)));
+	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>(), *rowsum = hist + nb * 256;
 	DigitOwner dg = { n_ranks };
 	MCB_LAUNCH(ctx, "shard_hist", (k_sort_hist<ulonglong2, DigitOwner>), (unsigned)nb, SORT_THREADS, 0, a, n, dg, hist, (unsigned)nb);
-	MCB_TRY(mcb_exclusive_scan_u32(ctx, hist, nb * 256, nullptr));
-	MCB_LAUNCH(ctx, "shard_scatter", (k_sort_scatter<ulonglong2, DigitOwner>), (unsigned)nb, SORT_THREADS, 0, a, b, n, dg, hist, (unsigned)nb);
-	// start offset of digit d = first entry of its row of the digit-major table
-	uint32_t starts[257];
-	MCB_CUDA(cudaMemcpy2DAsync(starts, 4, hist, nb * 4, 4, 256, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_LAUNCH(ctx, "sort_rowscan", k_sort_rowscan, 256, SORT_THREADS, 0, hist, (unsigned)nb, rowsum);
+	MCB_LAUNCH(ctx, "shard_scatter", (k_sort_scatter<ulonglong2, DigitOwner>), (unsigned)nb, SORT_THREADS, 0, a, b, n, dg, hist, (unsigned)nb, rowsum);
+	uint32_t sums[256];          // elements per digit = per owner
+	MCB_CUDA(cudaMemcpyAsync(sums, rowsum, sizeof sums, cudaMemcpyDeviceToHost, ctx->stream));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-	starts[256] = (uint32_t)n;
-	for (int i = 0; i <= n_ranks; ++i) counts[i] = starts[i + 1] - starts[i];
+	for (int i = 0; i <= n_ranks; ++i) counts[i] = sums[i];
 	return MCB_OK;
 }

@@ -107,6 +107,18 @@ __global__ void k_s2_pos_blocks(const uint64_t *__restrict__ ref_off, uint64_t n
 	pblk[i] = (uint32_t)lo;
 }
 
+// one 32-byte record per contig, so that a candidate costs one sector for all its contig coordinates
+struct __align__(32) S2ContigMeta { uint64_t ref_off, cw_off, woff, len; };
+__global__ void k_s2_contig_meta(const uint64_t *__restrict__ ref_off, const uint64_t *__restrict__ cw_off, const uint64_t *__restrict__ woff, uint64_t n_contigs,
+                                 S2ContigMeta *__restrict__ meta)
+{
+	uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c > n_contigs) return;
+	S2ContigMeta m;
+	m.ref_off = ref_off[c]; m.cw_off = cw_off[c]; m.woff = woff[c]; m.len = c < n_contigs ? ref_off[c + 1] - ref_off[c] : ~0ull >> 1;   // sentinel ends every walk
+	meta[c] = m;
+}
+
 // were the contigs of this call the ones the cached index was built from?
 __global__ void k_s2_same(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, uint64_t nwords, unsigned long long *__restrict__ counters)
 {
@@ -248,7 +260,7 @@ struct S2Join {
 	uint64_t S;
 	const uint64_t *rd; const uint8_t *flagged;
 	const uint32_t *ptab; const unsigned long long *ents; int pbits;
-	const uint32_t *pblk; const uint64_t *ref_off, *cw, *cw_off, *woff;
+	const uint32_t *pblk; const S2ContigMeta *meta; const uint64_t *cw;
 	unsigned long long *claim;            // [S] min priority
 	unsigned long long window_base;       // windows on lower ranks (0 on a single GPU)
 	unsigned long long *counters;
@@ -282,25 +294,34 @@ __global__ void __launch_bounds__(128) k_s2_join(S2Join p, S2Geom gm)
 				key_f = v & kmask;
 			}
 			const bool sketch_big = p.counters[CT_S2_MAXBIN] > (unsigned long long)gm.maxsearch;
+			// both probes are set up before either is followed, so that their table look-ups are in flight together
+			const int nphase = ds > 0 ? 2 : 1;                                       // kthread_hash_realign.c:440 (j = 0): no reverse probe for a dictionary at 0
+			// forward: the window holds the key at [ds, ds+lt).  reverse: the reverse-complemented window holds it there,
+			// i.e. the window itself holds the key's reverse complement at [L-ds-lt, L-ds).
+			const uint64_t key2[2] = { key_f, rev_fields(~key_f & kmask, lt) };
+			uint32_t lo2[2], hi2[2];
+#pragma unroll
 			for (int phase = 0; phase < 2; ++phase) {
-				if (phase && ds <= 0) break;                                         // kthread_hash_realign.c:440 (j = 0)
-				// forward: the window holds the key at [ds, ds+lt).  reverse: the reverse-complemented window holds it there,
-				// i.e. the window itself holds the key's reverse complement at [L-ds-lt, L-ds).
-				const uint64_t key = phase ? rev_fields(~key_f & kmask, lt) : key_f;
+				const uint32_t b = kmer_bucket(key2[phase], p.pbits);
+				lo2[phase] = (phase < nphase && b) ? p.ptab[b - 1] : 0u;
+				hi2[phase] = phase < nphase ? p.ptab[b] : 0u;
+			}
+#pragma unroll
+			for (int phase = 0; phase < 2; ++phase) {
+				const uint64_t key = key2[phase];
 				const int koff = phase ? L - ds - lt : ds;
-				const uint32_t b = kmer_bucket(key, p.pbits);
-				const uint32_t i0 = b ? p.ptab[b - 1] : 0u, i1 = p.ptab[b];
-				for (uint32_t i = i0; i < i1; ++i) {
+				for (uint32_t i = lo2[phase]; i < hi2[phase]; ++i) {
 					const unsigned long long e = p.ents[i];
 					if ((e >> S2_POS_BITS) != key) continue;
 					const uint64_t P = e & S2_POS_MASK;
 					uint32_t c = p.pblk[P >> S2_BLK_SHIFT];
-					while (p.ref_off[c + 1] <= P) ++c;
-					const uint64_t cb = p.ref_off[c], len = p.ref_off[c + 1] - cb;
-					const long long jj = (long long)(P - cb) - koff;
+					S2ContigMeta cm = p.meta[c];
+					while (cm.ref_off + cm.len <= P) cm = p.meta[++c];
+					const uint64_t len = cm.len;
+					const long long jj = (long long)(P - cm.ref_off) - koff;
 					if (jj < 0 || (uint64_t)jj + L > len) continue;
 					++n_cand;
-					const uint64_t *__restrict__ src = p.cw + p.cw_off[c] + ((uint64_t)jj >> 5);
+					const uint64_t *__restrict__ src = p.cw + cm.cw_off + ((uint64_t)jj >> 5);
 					const int sh = 2 * (int)(jj & 31);
 					// word q of (window XOR single); for the reverse phase the single is reverse-complemented on the fly:
 					// reverse the fields over Wd words, then drop the pad fields that moved to the bottom
@@ -345,7 +366,7 @@ __global__ void __launch_bounds__(128) k_s2_join(S2Join p, S2Geom gm)
 						if (p.xkey) big = bins_exact_count(p.xkey, p.xcnt, p.xmask, ((unsigned long long)l << 34) | key_f) > (uint32_t)gm.maxsearch;
 						if (big) atomicAdd(&p.counters[CT_S2_NEEDEXACT], 1ull);
 					}
-					const unsigned long long g = p.window_base + p.woff[c] + (unsigned long long)jj;
+					const unsigned long long g = p.window_base + cm.woff + (unsigned long long)jj;
 					atomicMin(&p.claim[s], (g << 5) | ((unsigned long long)phase << 4) | (unsigned long long)l);
 				}
 			}
@@ -444,7 +465,7 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	const uint64_t nbk = 1ull << pbits, n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
 	MCB_TRY(cx.cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.wo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.cw.ensure((total_words + 2) * 8));
 	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16)); MCB_TRY(cx.ptab.ensure((nbk + 1) * 4)); MCB_TRY(cx.ents.ensure(n_entries * 8 + 16)); MCB_TRY(cx.ents2.ensure(n_entries * 8 + 16));
-	MCB_TRY(cx.eoff.ensure((n_contigs + 1) * 8));
+	MCB_TRY(cx.eoff.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.meta.ensure((n_contigs + 2) * 32));
 	{
 		McbSpan sp(ctx->tm, "h2d");
 		MCB_CUDA(cudaMemcpyAsync(cx.cwo.p, cwo, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -453,6 +474,8 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	}
 	if (n_contigs == 0 || n_windows == 0) { cx.valid = true; return MCB_OK; }
 	McbSpan sp(ctx->tm, "realign");
+	MCB_LAUNCH(ctx, "s2_contig_meta", k_s2_contig_meta, mcb_grid_for(n_contigs + 1, 256), 256, 0, cx.roff.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.wo.as<uint64_t>(), n_contigs,
+	           cx.meta.as<S2ContigMeta>());
 	MCB_CUDA(cudaMemsetAsync(cx.cw.as<uint64_t>() + total_words, 0, 16, ctx->stream));
 	MCB_LAUNCH(ctx, "s2_pack_refs", k_s2_pack_refs, mcb_grid_for(total_words, 256), 256, 0, cx.refs.as<char>(), cx.roff.as<uint64_t>(), cx.cwo.as<uint64_t>(),
 	           n_contigs, total_words, cx.cw.as<uint64_t>(), dc);
@@ -543,7 +566,7 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	}
 	S2Join jn; memset(&jn, 0, sizeof jn);
 	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents_sorted; jn.pbits = cx.pbits;
-	jn.pblk = cx.pblk.as<uint32_t>(); jn.ref_off = cx.roff.as<uint64_t>(); jn.cw = cx.cw.as<uint64_t>(); jn.cw_off = cx.cwo.as<uint64_t>(); jn.woff = cx.wo.as<uint64_t>();
+	jn.pblk = cx.pblk.as<uint32_t>(); jn.meta = cx.meta.as<S2ContigMeta>(); jn.cw = cx.cw.as<uint64_t>();
 	jn.claim = claim; jn.window_base = window_base; jn.counters = dc;
 	for (int attempt = 0;; ++attempt) {
 		MCB_LAUNCH(ctx, "s2_join", k_s2_join, mcb_grid_for(nkv, 128), 128, 0, jn, gm);

@@ -63,3 +63,39 @@ def test_dropin_directory_is_byte_identical(case):
         r = refdump.run_reference(reads, wd, mode="sg", env_opts=env, dump=False, exe=exe)
         files = compare_dirs(ref_out, r["out"])
         print(name, "identical files:", len(files), "timing:", r["timing"])
+
+
+@pytest.mark.parametrize("name", refdump.golden_names())
+def test_dropin_matches_golden_output_directory(name):
+    """The committed fixtures hold the reference's output directory (file name -> bytes): sg mode at L=75/100/150, an option
+    sweep and ORDER mode.  Needs neither /root/reference nor the reference binary."""
+    reads, meta, _, want = refdump.load_golden(name)
+    exe = refdump.dropin_binary(meta["L"], meta["mode"])
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} not built (dropin/build_dropin.sh {meta['L']} {meta['mode']})")
+    with tempfile.TemporaryDirectory() as wd:
+        r = refdump.run_reference(reads, wd, mode=meta["mode"], env_opts=meta["env"], dump=False, exe=exe)
+        got = {f: open(os.path.join(r["out"], f), "rb").read() for f in os.listdir(r["out"])}
+    assert sorted(got) == sorted(want), f"file sets differ: {set(got) ^ set(want)}"
+    bad = [f for f in want if got[f] != want[f]]
+    assert not bad, f"files differ: {bad}"
+
+
+def test_dropin_paired_end_mode():
+    """-1/-2: two files, _PE build (kthread_dump_pe.c on the host side).  The reference binary is run here (it is a plain
+    x86-64 executable that travels with the snapshot); skipped when it was never built."""
+    L, n = 101, 12000
+    ref, exe = refdump.ref_binary(L, "pe"), refdump.dropin_binary(L, "pe")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/minicom_ref_L101_pe not built")
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} not built")
+    from minicom_b200 import synth
+    genome = synth.make_genome(60000, 51)
+    r1 = synth.make_reads(n, L, 60000, seed=51, special=0.01, genome=genome)
+    r2 = synth.make_reads(n, L, 60000, seed=52, special=0.01, genome=genome)
+    with tempfile.TemporaryDirectory() as wa, tempfile.TemporaryDirectory() as wb:
+        a = refdump.run_reference(r1, wa, mode="pe", dump=False, reads2=r2)
+        b = refdump.run_reference(r1, wb, mode="pe", dump=False, reads2=r2, exe=exe)
+        files = compare_dirs(a["out"], b["out"])
+        print("PE identical files:", len(files))
