@@ -245,7 +245,7 @@ __device__ __forceinline__ unsigned member_base(const uint64_t *mw, int dir, int
 
 __global__ void __launch_bounds__(CS_WARPS * 32)
 k_consensus(const ulonglong2 *__restrict__ el, const uint32_t *__restrict__ gstart, uint64_t G, const uint64_t *__restrict__ packed,
-            int WS, int L, int e_thr, int pbase, int NC, int last_round, ConsOut o, unsigned long long *__restrict__ counters, uint64_t reftmp_cap)
+            int WS, int L, int e_thr, int pbase, int NC, int last_round, ConsOut o, unsigned long long *__restrict__ counters, uint64_t reftmp_cap, uint32_t min_members)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -261,6 +261,7 @@ k_consensus(const ulonglong2 *__restrict__ el, const uint32_t *__restrict__ gsta
 	const uint64_t nwarps = (uint64_t)gridDim.x * CS_WARPS;
 	for (uint64_t g = (uint64_t)blockIdx.x * CS_WARPS + wib; g < G; g += nwarps) {
 		const uint32_t s = gstart[g], cntm = gstart[g + 1] - s;
+		if (cntm < min_members) continue;                 // smaller groups: k_cons_worklist / k_consensus_bs
 		if (cntm < 2) {
 			if (lane == 0) {
 				o.status[s] = 0; o.erank[s] = 0;
@@ -399,6 +400,249 @@ k_consensus(const ulonglong2 *__restrict__ el, const uint32_t *__restrict__ gsta
 			o.g_sg[g] = last_round ? nout : 0; o.g_resk[g] = last_round ? 0 : nout;
 		}
 		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------- K3, bit-sliced formulation
+// The same construct_ref, reorganised around 32-column words.  A group is handled by GW lanes (GW = 8, 16 or 32, the
+// smallest that covers the widest possible pile-up of the round); lane j owns columns [32j, 32j+32).  Per column and
+// base, the coverage counters are bit-sliced: plane q of a counter word holds bit q of the 32 columns' counts, so adding
+// one member is a ripple-carry over K planes (K = bits needed for the group size) on whole words.  A member's bases are
+// split into a low-bit and a high-bit plane (32 bases per word), reverse-complemented at plane level when on the
+// reverse strand, and shifted to the member's offset with two shuffles per plane.  Majority, first empty column,
+// mismatch counts (XOR against the consensus planes + popcount) and the final trim all work on these words; rejected
+// members are subtracted from the counters as soon as they are found, which is pass 3 of the reference (recount over
+// the kept members) without touching the kept ones again.  Several groups share a warp (32/GW), walking their members
+// in lockstep.
+__device__ __forceinline__ uint32_t compress_even(uint64_t w)
+{
+	uint64_t x = w & 0x5555555555555555ull;
+	x = (x | (x >> 1)) & 0x3333333333333333ull;
+	x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+	x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+	x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+	x = x | (x >> 16);
+	return (uint32_t)x;
+}
+template <int K> __device__ __forceinline__ void bs_add(uint32_t (&c)[K], uint32_t m)
+{
+	uint32_t carry = m;
+#pragma unroll
+	for (int q = 0; q < K; ++q) { const uint32_t t = c[q] & carry; c[q] ^= carry; carry = t; }
+}
+template <int K> __device__ __forceinline__ void bs_sub(uint32_t (&c)[K], uint32_t m)
+{
+	uint32_t borrow = m;
+#pragma unroll
+	for (int q = 0; q < K; ++q) { const uint32_t t = ~c[q] & borrow; c[q] ^= borrow; borrow = t; }
+}
+template <int K> __device__ __forceinline__ uint32_t bs_gt(const uint32_t (&x)[K], const uint32_t (&y)[K])
+{
+	uint32_t gt = 0, eq = ~0u;
+#pragma unroll
+	for (int q = K - 1; q >= 0; --q) { gt |= eq & x[q] & ~y[q]; eq &= ~(x[q] ^ y[q]); }
+	return gt;
+}
+// per column: the most frequent base, ties to the lowest code (strict > at kthread_bucket.c:111); cov = some base seen
+template <int K> __device__ __forceinline__ void bs_majority(const uint32_t (&cA)[K], const uint32_t (&cC)[K], const uint32_t (&cG)[K], const uint32_t (&cT)[K],
+                                                            uint32_t &lo, uint32_t &hi, uint32_t &cov)
+{
+	uint32_t best[K];
+#pragma unroll
+	for (int q = 0; q < K; ++q) best[q] = cA[q];
+	lo = 0; hi = 0;
+	uint32_t g = bs_gt<K>(cC, best);
+	lo = g;
+#pragma unroll
+	for (int q = 0; q < K; ++q) best[q] = (cC[q] & g) | (best[q] & ~g);
+	g = bs_gt<K>(cG, best);
+	lo &= ~g; hi = g;
+#pragma unroll
+	for (int q = 0; q < K; ++q) best[q] = (cG[q] & g) | (best[q] & ~g);
+	g = bs_gt<K>(cT, best);
+	lo |= g; hi |= g;
+	cov = 0;
+#pragma unroll
+	for (int q = 0; q < K; ++q) cov |= (cT[q] & g) | (best[q] & ~g);
+}
+
+struct BsMember { uint32_t lo, hi, valid; };
+// 32-column chunk (word wq) of member `k2` of the sub-group, oriented and shifted to its offset
+template <int GW>
+__device__ __forceinline__ BsMember bs_member_chunk(const uint64_t *__restrict__ packed, int WS, int Wd, int L, unsigned long long k2, int posinv0, int wq, unsigned sgmask, bool active)
+{
+	const int dir = (int)(k2 & 1), off = (int)(k2 >> MCB_POSINV_SHIFT) - posinv0;
+	uint32_t plo = 0, phi = 0;
+	if (active && wq < Wd) {       // this lane holds plane word wq of the oriented read
+		const uint64_t *row = packed + (uint64_t)mcb_k2_rid(k2) * WS;
+		uint64_t w;
+		if (!dir) w = row[wq];
+		else {
+			const int pad = Wd * 32 - L;
+			const uint64_t a = mcb_rc_word(row[Wd - 1 - wq]);
+			const uint64_t b = wq + 1 < Wd ? mcb_rc_word(row[Wd - 2 - wq]) : 0ull;
+			w = pad ? (a >> (2 * pad)) | (b << (64 - 2 * pad)) : a;
+		}
+		if (wq == Wd - 1 && (L & 31)) w &= (1ull << (2 * (L & 31))) - 1;
+		plo = compress_even(w); phi = compress_even(w >> 1);
+	}
+	// columns [32wq, 32wq+32) are read positions [32wq-off, ...): plane words i0, i0+1 shifted by sh
+	const int b0 = 32 * wq - off, i0 = b0 >> 5, sh = b0 & 31;
+	const int base = (threadIdx.x & 31) & ~(GW - 1);
+	const int s0 = (i0 >= 0 && i0 < GW) ? i0 : 0, s1 = (i0 + 1 >= 0 && i0 + 1 < GW) ? i0 + 1 : 0;
+	uint32_t l0 = __shfl_sync(sgmask, plo, base + s0), l1 = __shfl_sync(sgmask, plo, base + s1);
+	uint32_t h0 = __shfl_sync(sgmask, phi, base + s0), h1 = __shfl_sync(sgmask, phi, base + s1);
+	if (i0 < 0 || i0 >= GW) { l0 = 0; h0 = 0; }
+	if (i0 + 1 < 0 || i0 + 1 >= GW) { l1 = 0; h1 = 0; }
+	BsMember m;
+	m.lo = sh ? (l0 >> sh) | (l1 << (32 - sh)) : l0;
+	m.hi = sh ? (h0 >> sh) | (h1 << (32 - sh)) : h0;
+	const int vb0 = max(0, off - 32 * wq), vb1 = min(32, off + L - 32 * wq);     // valid bits: columns off .. off+L-1
+	m.valid = (active && vb1 > vb0) ? ((vb1 >= 32 ? ~0u : (1u << vb1) - 1u) & ~((1u << vb0) - 1u)) : 0u;
+	m.lo &= m.valid; m.hi &= m.valid;
+	return m;
+}
+
+template <int GW> __device__ __forceinline__ int sg_min(int v, unsigned m) { for (int o = GW / 2; o; o >>= 1) v = min(v, __shfl_xor_sync(m, v, o)); return v; }
+template <int GW> __device__ __forceinline__ int sg_max(int v, unsigned m) { for (int o = GW / 2; o; o >>= 1) v = max(v, __shfl_xor_sync(m, v, o)); return v; }
+template <int GW> __device__ __forceinline__ int sg_sum(int v, unsigned m) { for (int o = GW / 2; o; o >>= 1) v += __shfl_xor_sync(m, v, o); return v; }
+
+// one batch of 32/GW groups (one per sub-group) whose sizes all fit K counter planes
+template <int GW, int K>
+__device__ void cons_groups_bs(const ulonglong2 *__restrict__ el, uint32_t s, uint32_t cntm, uint64_t g, bool have, const uint64_t *__restrict__ packed,
+                               int WS, int Wd, int L, int e_thr, int last_round, const ConsOut &o, unsigned long long *__restrict__ counters, uint64_t reftmp_cap)
+{
+	const unsigned FULL = 0xFFFFFFFFu;
+	const int lane = threadIdx.x & 31, wq = lane & (GW - 1);
+	const bool lead = wq == 0;
+	uint32_t cA[K], cC[K], cG[K], cT[K];
+#pragma unroll
+	for (int q = 0; q < K; ++q) { cA[q] = 0; cC[q] = 0; cG[q] = 0; cT[q] = 0; }
+	const int posinv0 = have ? (int)(el[s].y >> MCB_POSINV_SHIFT) : 0;
+	const int ncol = have ? (int)(el[s + cntm - 1].y >> MCB_POSINV_SHIFT) - posinv0 + L : 0;
+	if (have && ncol > 32 * GW && lead) atomicAdd(&counters[CT_ERR], 1ull);
+	const uint32_t colmask = ncol >= 32 * (wq + 1) ? ~0u : (ncol > 32 * wq ? (1u << (ncol - 32 * wq)) - 1u : 0u);
+	uint32_t maxm = cntm;
+	for (int ofs = 16; ofs; ofs >>= 1) maxm = max(maxm, __shfl_xor_sync(FULL, maxm, ofs));
+	// ---- pass 1: pile-up of all members
+	for (uint32_t m = 0; m < maxm; ++m) {
+		const bool act = have && m < cntm;
+		const unsigned long long k2 = act ? el[s + m].y : 0ull;
+		const BsMember mb = bs_member_chunk<GW>(packed, WS, Wd, L, k2, posinv0, wq, FULL, act);
+		bs_add<K>(cA, ~mb.lo & ~mb.hi & mb.valid); bs_add<K>(cC, mb.lo & ~mb.hi); bs_add<K>(cG, ~mb.lo & mb.hi); bs_add<K>(cT, mb.lo & mb.hi);
+	}
+	uint32_t conlo, conhi, cov;
+	bs_majority<K>(cA, cC, cG, cT, conlo, conhi, cov);
+	// the consensus string ends at the first column nobody covers (kthread_bucket.c:117-120); beyond it nothing matches
+	const uint32_t empty = ~cov & colmask;
+	const int reflen1 = sg_min<GW>(empty ? 32 * wq + __ffs(empty) - 1 : ncol, FULL);
+	const uint32_t inref = reflen1 >= 32 * (wq + 1) ? ~0u : (reflen1 > 32 * wq ? (1u << (reflen1 - 32 * wq)) - 1u : 0u);
+	// ---- pass 2: mismatches of every member against the consensus; rejected members leave the counters (= pass 3's recount)
+	int kept = 0, nrej = 0;
+	for (uint32_t m = 0; m < maxm; ++m) {
+		const bool act = have && m < cntm;
+		const unsigned long long k2 = act ? el[s + m].y : 0ull;
+		const BsMember mb = bs_member_chunk<GW>(packed, WS, Wd, L, k2, posinv0, wq, FULL, act);
+		const uint32_t diff = (((mb.lo ^ conlo) | (mb.hi ^ conhi)) | ~inref) & mb.valid;
+		const int mism = sg_sum<GW>(__popc(diff), FULL);
+		const bool keep = mism <= e_thr;
+		if (act) {
+			if (lead) { o.status[s + m] = keep ? 1 : 2; o.erank[s + m] = keep ? kept : nrej; }
+			if (keep) ++kept;
+			else {
+				++nrej;
+				bs_sub<K>(cA, ~mb.lo & ~mb.hi & mb.valid); bs_sub<K>(cC, mb.lo & ~mb.hi); bs_sub<K>(cG, ~mb.lo & mb.hi); bs_sub<K>(cT, mb.lo & mb.hi);
+			}
+		}
+	}
+	// ---- finalize: trim to the covered span of the kept members and write the consensus
+	const bool iscl = have && kept >= 2;
+	int sv = 0;
+	if (have) {
+		bs_majority<K>(cA, cC, cG, cT, conlo, conhi, cov);
+		cov &= colmask;
+	} else cov = 0;
+	{
+		const int first_cov = sg_min<GW>(cov ? 32 * wq + __ffs(cov) - 1 : 1 << 30, FULL);
+		const int last_cov = sg_max<GW>(cov ? 32 * wq + 31 - __clz(cov) : -1, FULL);
+		unsigned long long refoff = 0;
+		int reflen2 = 0;
+		if (iscl) { sv = first_cov; reflen2 = last_cov + 1 - sv; }
+		if (iscl && lead) refoff = atomicAdd(&counters[CT_REFCURSOR], (unsigned long long)reflen2);
+		refoff = __shfl_sync(FULL, refoff, lane & ~(GW - 1));
+		if (iscl) {
+			if (refoff + reflen2 > reftmp_cap) { if (lead) atomicAdd(&counters[CT_ERR], 1ull); }
+			else {
+				const int c0 = max(sv, 32 * wq), c1 = min(sv + reflen2, 32 * wq + 32);
+				for (int c = c0; c < c1; ++c) {
+					const int b = c - 32 * wq;
+					o.reftmp[refoff + (c - sv)] = "ACGT"[((conlo >> b) & 1u) | (((conhi >> b) & 1u) << 1)];
+				}
+			}
+		}
+		if (have && lead) {
+			const uint32_t nout = iscl ? (uint32_t)nrej : cntm;
+			o.g_iscl[g] = iscl; o.g_kept[g] = iscl ? kept : 0;
+			o.g_sg[g] = last_round ? nout : 0; o.g_resk[g] = last_round ? 0 : nout;
+			o.g_reflen[g] = (unsigned long long)reflen2; o.g_refoff[g] = iscl ? refoff : 0ull;
+		}
+	}
+	__syncwarp();
+	// ---- member records (need sv) / lone survivor placement
+	for (uint32_t j0 = 0; j0 < maxm; j0 += GW) {
+		const uint32_t j = j0 + wq;
+		if (have && j < cntm) {
+			const unsigned long long k2 = el[s + j].y;
+			if (o.status[s + j] == 1) {
+				if (iscl) o.newrec[s + j] = ((unsigned long long)mcb_k2_rid(k2) << 32) | ((unsigned long long)((int)(k2 >> MCB_POSINV_SHIFT) - posinv0 - sv) << 1) | (k2 & 1);
+				else { o.status[s + j] = 3; o.erank[s + j] = nrej; }            // lone survivor: after the rejects (:476-498)
+			}
+		}
+	}
+	__syncwarp();
+}
+
+// groups taken from a work list of one size class (K counter planes hold sizes below 2^K); singletons never get here
+template <int GW, int K>
+__global__ void __launch_bounds__(128)
+k_consensus_bs(const ulonglong2 *__restrict__ el, const uint32_t *__restrict__ gstart, const uint32_t *__restrict__ worklist, const unsigned long long *__restrict__ n_work_ptr,
+               const uint64_t *__restrict__ packed, int WS, int Wd, int L, int e_thr, int last_round, ConsOut o, unsigned long long *__restrict__ counters, uint64_t reftmp_cap)
+{
+	constexpr int SGW = 32 / GW;                                   // sub-groups per warp
+	const uint64_t n_work = *n_work_ptr;
+	const int lane = threadIdx.x & 31;
+	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for (uint64_t w0 = warp * SGW; w0 < n_work; w0 += nwarps * SGW) {
+		const uint64_t wi = w0 + lane / GW;
+		const bool have = wi < n_work;
+		uint64_t g = 0; uint32_t s = 0, cntm = 0;
+		if (have) { g = worklist[wi]; s = gstart[g]; cntm = gstart[g + 1] - s; }
+		cons_groups_bs<GW, K>(el, s, cntm, g, have, packed, WS, Wd, L, e_thr, last_round, o, counters, reftmp_cap);
+	}
+}
+
+#define CONS_BS_MAX_MEMBERS 60000u
+// singletons are settled here; groups of 2..15 / 16..255 / 256..CONS_BS_MAX_MEMBERS members go to the three work lists of
+// k_consensus_bs (4, 8, 16 counter planes), larger ones to k_consensus
+__global__ void k_cons_worklist(const uint32_t *__restrict__ gstart, uint64_t G, ConsOut o, uint32_t *__restrict__ worklist, unsigned long long *__restrict__ counters)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	int cls = -1;
+	if (g < G) {
+		const uint32_t s = gstart[g], cntm = gstart[g + 1] - s;
+		if (cntm < 2) {
+			o.status[s] = 0; o.erank[s] = 0;
+			o.g_iscl[g] = 0; o.g_kept[g] = 0; o.g_sg[g] = 1; o.g_resk[g] = 0; o.g_reflen[g] = 0; o.g_refoff[g] = 0;
+		} else if (cntm <= CONS_BS_MAX_MEMBERS) cls = cntm < 16 ? 0 : cntm < 256 ? 1 : 2;
+	}
+	const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		const unsigned bal = __ballot_sync(0xFFFFFFFFu, cls == c);
+		unsigned long long base = 0;
+		if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(&counters[CT_WORK0 + c], (unsigned long long)__popc(bal));
+		base = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if (cls == c) worklist[(uint64_t)c * G + base + __popc(bal & lt)] = (uint32_t)g;
 	}
 }
 
@@ -834,9 +1078,27 @@ static int bucket_round_a(mcb_ctx *ctx, int r, int is_last)
 	ConsOut co; co.status = B.b_st.as<uint8_t>(); co.erank = B.b_er.as<uint32_t>(); co.newrec = B.b_nr.as<uint64_t>();
 	co.g_iscl = B.b_gc.as<uint32_t>(); co.g_kept = B.b_gk.as<uint32_t>(); co.g_sg = B.b_gsg.as<uint32_t>(); co.g_resk = B.b_grk.as<uint32_t>();
 	co.g_reflen = B.b_grl.as<unsigned long long>(); co.g_refoff = B.b_gro.as<unsigned long long>(); co.reftmp = ctx->d_ascii.as<char>();
-	unsigned cgrid = mcb_grid_for(G, CS_WARPS, (unsigned)ctx->sm_count * 16);
-	MCB_LAUNCH(ctx, "consensus", k_consensus, cgrid, CS_WARPS * 32, cs_smem, cur, B.b_gs.as<uint32_t>(), G, ctx->d_packed.as<uint64_t>(), WS, L,
-	           ctx->prm.diff_threshold, pbase, NC, is_last, co, dc, reftmp_cap);
+	{
+		// widest pile-up a group of this round can have: offsets are differences of strand-adjusted positions in [kmer', L+r-2]
+		// (kmer' = length of the k-mers these tuples were sketched with), so columns <= 2L + 2r - 2 - k  (+ margin)
+		const int max_cols = 2 * L + 2 * r - k + 2;
+		const int ncw = (max_cols + 31) / 32;
+		MCB_TRY(ctx->d_x[2].ensure(3 * G * 4 + 16));
+		uint32_t *worklist = ctx->d_x[2].as<uint32_t>();
+		MCB_CUDA(cudaMemsetAsync(&dc[CT_WORK0], 0, 3 * 8, ctx->stream));
+		MCB_LAUNCH(ctx, "cons_worklist", k_cons_worklist, mcb_grid_for(G, 256), 256, 0, B.b_gs.as<uint32_t>(), G, co, worklist, dc);
+		const unsigned bgrid = (unsigned)ctx->sm_count * 16;
+#define CONS_BS_LAUNCH(GWv, Kv, cls) MCB_LAUNCH(ctx, "consensus", (k_consensus_bs<GWv, Kv>), bgrid, 128, 0, cur, B.b_gs.as<uint32_t>(), worklist + (uint64_t)(cls) * G, \
+		&dc[CT_WORK0 + (cls)], ctx->d_packed.as<uint64_t>(), WS, ctx->Wd, L, ctx->prm.diff_threshold, is_last, co, dc, reftmp_cap)
+		if (ncw <= 8) { CONS_BS_LAUNCH(8, 4, 0); CONS_BS_LAUNCH(8, 8, 1); CONS_BS_LAUNCH(8, 16, 2); }
+		else if (ncw <= 16) { CONS_BS_LAUNCH(16, 4, 0); CONS_BS_LAUNCH(16, 8, 1); CONS_BS_LAUNCH(16, 16, 2); }
+		else { CONS_BS_LAUNCH(32, 4, 0); CONS_BS_LAUNCH(32, 8, 1); CONS_BS_LAUNCH(32, 16, 2); }
+#undef CONS_BS_LAUNCH
+		// groups too large for the bit-sliced counters (more than CONS_BS_MAX_MEMBERS members): the column-count kernel
+		unsigned cgrid = mcb_grid_for(G, CS_WARPS, (unsigned)ctx->sm_count * 16);
+		MCB_LAUNCH(ctx, "consensus_huge", k_consensus, cgrid, CS_WARPS * 32, cs_smem, cur, B.b_gs.as<uint32_t>(), G, ctx->d_packed.as<uint64_t>(), WS, L,
+		           ctx->prm.diff_threshold, pbase, NC, is_last, co, dc, reftmp_cap, CONS_BS_MAX_MEMBERS + 1);
+	}
 	// ---- bases
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_gc.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_CL]));
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_gk.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_MEM]));
