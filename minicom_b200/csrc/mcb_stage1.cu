@@ -245,7 +245,8 @@ __device__ __forceinline__ unsigned member_base(const uint64_t *mw, int dir, int
 
 __global__ void __launch_bounds__(CS_WARPS * 32)
 k_consensus(const ulonglong2 *__restrict__ el, const uint32_t *__restrict__ gstart, uint64_t G, const uint64_t *__restrict__ packed,
-            int WS, int L, int e_thr, int pbase, int NC, int last_round, ConsOut o, unsigned long long *__restrict__ counters, uint64_t reftmp_cap, uint32_t min_members)
+            int WS, int L, int e_thr, int pbase, int NC, int last_round, ConsOut o, unsigned long long *__restrict__ counters, uint64_t reftmp_cap,
+            const uint32_t *__restrict__ worklist, const unsigned long long *__restrict__ n_work_ptr)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -259,9 +260,10 @@ k_consensus(const ulonglong2 *__restrict__ el, const uint32_t *__restrict__ gsta
 	uint8_t *msel = (uint8_t*)(mrid + CS_MB);                         // [CS_MB] (padding inside the 16 B/member budget)
 	unsigned char *cons = wsm + (size_t)NC * 16 + CS_MB * 8 * 8 + CS_MB * 16;   // [NC]
 	const uint64_t nwarps = (uint64_t)gridDim.x * CS_WARPS;
-	for (uint64_t g = (uint64_t)blockIdx.x * CS_WARPS + wib; g < G; g += nwarps) {
+	const uint64_t n_work = *n_work_ptr;                  // only the groups too large for k_consensus_bs come here
+	for (uint64_t wi = (uint64_t)blockIdx.x * CS_WARPS + wib; wi < n_work; wi += nwarps) {
+		const uint64_t g = worklist[wi];
 		const uint32_t s = gstart[g], cntm = gstart[g + 1] - s;
-		if (cntm < min_members) continue;                 // smaller groups: k_cons_worklist / k_consensus_bs
 		if (cntm < 2) {
 			if (lane == 0) {
 				o.status[s] = 0; o.erank[s] = 0;
@@ -623,7 +625,7 @@ k_consensus_bs(const ulonglong2 *__restrict__ el, const uint32_t *__restrict__ g
 
 #define CONS_BS_MAX_MEMBERS 60000u
 // singletons are settled here; groups of 2..15 / 16..255 / 256..CONS_BS_MAX_MEMBERS members go to the three work lists of
-// k_consensus_bs (4, 8, 16 counter planes), larger ones to k_consensus
+// k_consensus_bs (4, 8, 16 counter planes), larger ones to the fourth list, for k_consensus
 __global__ void k_cons_worklist(const uint32_t *__restrict__ gstart, uint64_t G, ConsOut o, uint32_t *__restrict__ worklist, unsigned long long *__restrict__ counters)
 {
 	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -633,11 +635,11 @@ __global__ void k_cons_worklist(const uint32_t *__restrict__ gstart, uint64_t G,
 		if (cntm < 2) {
 			o.status[s] = 0; o.erank[s] = 0;
 			o.g_iscl[g] = 0; o.g_kept[g] = 0; o.g_sg[g] = 1; o.g_resk[g] = 0; o.g_reflen[g] = 0; o.g_refoff[g] = 0;
-		} else if (cntm <= CONS_BS_MAX_MEMBERS) cls = cntm < 16 ? 0 : cntm < 256 ? 1 : 2;
+		} else cls = cntm < 16 ? 0 : cntm < 256 ? 1 : cntm <= CONS_BS_MAX_MEMBERS ? 2 : 3;
 	}
 	const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
 #pragma unroll
-	for (int c = 0; c < 3; ++c) {
+	for (int c = 0; c < 4; ++c) {
 		const unsigned bal = __ballot_sync(0xFFFFFFFFu, cls == c);
 		unsigned long long base = 0;
 		if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(&counters[CT_WORK0 + c], (unsigned long long)__popc(bal));
@@ -1083,9 +1085,9 @@ static int bucket_round_a(mcb_ctx *ctx, int r, int is_last)
 		// (kmer' = length of the k-mers these tuples were sketched with), so columns <= 2L + 2r - 2 - k  (+ margin)
 		const int max_cols = 2 * L + 2 * r - k + 2;
 		const int ncw = (max_cols + 31) / 32;
-		MCB_TRY(ctx->d_x[2].ensure(3 * G * 4 + 16));
+		MCB_TRY(ctx->d_x[2].ensure(4 * G * 4 + 16));
 		uint32_t *worklist = ctx->d_x[2].as<uint32_t>();
-		MCB_CUDA(cudaMemsetAsync(&dc[CT_WORK0], 0, 3 * 8, ctx->stream));
+		MCB_CUDA(cudaMemsetAsync(&dc[CT_WORK0], 0, 4 * 8, ctx->stream));
 		MCB_LAUNCH(ctx, "cons_worklist", k_cons_worklist, mcb_grid_for(G, 256), 256, 0, B.b_gs.as<uint32_t>(), G, co, worklist, dc);
 		const unsigned bgrid = (unsigned)ctx->sm_count * 16;
 #define CONS_BS_LAUNCH(GWv, Kv, cls) MCB_LAUNCH(ctx, "consensus", (k_consensus_bs<GWv, Kv>), bgrid, 128, 0, cur, B.b_gs.as<uint32_t>(), worklist + (uint64_t)(cls) * G, \
@@ -1095,9 +1097,8 @@ static int bucket_round_a(mcb_ctx *ctx, int r, int is_last)
 		else { CONS_BS_LAUNCH(32, 4, 0); CONS_BS_LAUNCH(32, 8, 1); CONS_BS_LAUNCH(32, 16, 2); }
 #undef CONS_BS_LAUNCH
 		// groups too large for the bit-sliced counters (more than CONS_BS_MAX_MEMBERS members): the column-count kernel
-		unsigned cgrid = mcb_grid_for(G, CS_WARPS, (unsigned)ctx->sm_count * 16);
-		MCB_LAUNCH(ctx, "consensus_huge", k_consensus, cgrid, CS_WARPS * 32, cs_smem, cur, B.b_gs.as<uint32_t>(), G, ctx->d_packed.as<uint64_t>(), WS, L,
-		           ctx->prm.diff_threshold, pbase, NC, is_last, co, dc, reftmp_cap, CONS_BS_MAX_MEMBERS + 1);
+		MCB_LAUNCH(ctx, "consensus_huge", k_consensus, (unsigned)ctx->sm_count, CS_WARPS * 32, cs_smem, cur, B.b_gs.as<uint32_t>(), G, ctx->d_packed.as<uint64_t>(), WS, L,
+		           ctx->prm.diff_threshold, pbase, NC, is_last, co, dc, reftmp_cap, worklist + 3ull * G, &dc[CT_WORK0 + 3]);
 	}
 	// ---- bases
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_gc.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_CL]));

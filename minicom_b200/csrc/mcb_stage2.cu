@@ -274,106 +274,139 @@ __device__ __forceinline__ uint64_t rev_fields(uint64_t v, int nbases)
 	return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
 }
 
-__global__ void __launch_bounds__(128) k_s2_join(S2Join p, S2Geom gm)
+// K7a: probe.  One thread per (single, dictionary): the key and its reverse complement are looked up in the contig table;
+// every entry with an equal lt-mer becomes a candidate record (pair index | phase | contig position), appended with one
+// atomic per warp and loop step.  No verification here: key matches are sparse (a fraction of a match per thread), and
+// verifying them inside this loop left 31 lanes idle around each one.
+#define S2_CAND_PHASE_BIT 30
+__global__ void __launch_bounds__(256) k_s2_probe_table(S2Join p, S2Geom gm, unsigned long long *__restrict__ cand, unsigned long long cand_cap)
 {
 	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned long long n_cand = 0;
+	const int lane = threadIdx.x & 31;
+	uint64_t key2[2] = { 0, 0 };
+	uint32_t lo2[2] = { 0, 0 }, hi2[2] = { 0, 0 };
 	if (idx < p.S * (uint64_t)gm.nd) {
 		const int l = (int)(idx / p.S); const uint64_t s = idx - (uint64_t)l * p.S;
 		if (!p.flagged[s]) {                  // sg_flag already set by the poly-A/T diversion: can never be claimed
-			const int L = gm.L, Wd = gm.Wd, lt = gm.lt, ds = gm.dstart[l];
-			const uint64_t *__restrict__ row = p.rd + s * gm.WS;       // 2-bit single, re-read from L1 where needed: no per-thread arrays
+			const int lt = gm.lt, ds = gm.dstart[l];
+			const uint64_t *__restrict__ row = p.rd + s * gm.WS;
 			const uint64_t kmask = (1ull << (2 * lt)) - 1;
-			const uint64_t tailmask = (L & 31) ? (1ull << (2 * (L & 31))) - 1 : ~0ull;
-			const int pad = Wd * 32 - L;
-			uint64_t key_f;
-			{
-				const int bit = 2 * ds, wi = bit >> 6, sh = bit & 63;
-				uint64_t v = row[wi] >> sh;
-				if (sh + 2 * lt > 64) v |= row[wi + 1] << (64 - sh);
-				key_f = v & kmask;
-			}
-			const bool sketch_big = p.counters[CT_S2_MAXBIN] > (unsigned long long)gm.maxsearch;
-			// both probes are set up before either is followed, so that their table look-ups are in flight together
-			const int nphase = ds > 0 ? 2 : 1;                                       // kthread_hash_realign.c:440 (j = 0): no reverse probe for a dictionary at 0
+			const int bit = 2 * ds, wi = bit >> 6, sh = bit & 63;
+			uint64_t v = row[wi] >> sh;
+			if (sh + 2 * lt > 64) v |= row[wi + 1] << (64 - sh);
 			// forward: the window holds the key at [ds, ds+lt).  reverse: the reverse-complemented window holds it there,
 			// i.e. the window itself holds the key's reverse complement at [L-ds-lt, L-ds).
-			const uint64_t key2[2] = { key_f, rev_fields(~key_f & kmask, lt) };
-			uint32_t lo2[2], hi2[2];
+			key2[0] = v & kmask; key2[1] = rev_fields(~key2[0] & kmask, lt);
+			const int nphase = ds > 0 ? 2 : 1;                      // kthread_hash_realign.c:440 (j = 0): no reverse probe for a dictionary at 0
 #pragma unroll
 			for (int phase = 0; phase < 2; ++phase) {
-				const uint32_t b = kmer_bucket(key2[phase], p.pbits);
-				lo2[phase] = (phase < nphase && b) ? p.ptab[b - 1] : 0u;
-				hi2[phase] = phase < nphase ? p.ptab[b] : 0u;
-			}
-#pragma unroll
-			for (int phase = 0; phase < 2; ++phase) {
-				const uint64_t key = key2[phase];
-				const int koff = phase ? L - ds - lt : ds;
-				for (uint32_t i = lo2[phase]; i < hi2[phase]; ++i) {
-					const unsigned long long e = p.ents[i];
-					if ((e >> S2_POS_BITS) != key) continue;
-					const uint64_t P = e & S2_POS_MASK;
-					uint32_t c = p.pblk[P >> S2_BLK_SHIFT];
-					S2ContigMeta cm = p.meta[c];
-					while (cm.ref_off + cm.len <= P) cm = p.meta[++c];
-					const uint64_t len = cm.len;
-					const long long jj = (long long)(P - cm.ref_off) - koff;
-					if (jj < 0 || (uint64_t)jj + L > len) continue;
-					++n_cand;
-					const uint64_t *__restrict__ src = p.cw + cm.cw_off + ((uint64_t)jj >> 5);
-					const int sh = 2 * (int)(jj & 31);
-					// word q of (window XOR single); for the reverse phase the single is reverse-complemented on the fly:
-					// reverse the fields over Wd words, then drop the pad fields that moved to the bottom
-					auto xword = [&](int q) -> uint64_t {
-						const uint64_t a = src[q];
-						uint64_t w = sh ? (a >> sh) | (src[q + 1] << (64 - sh)) : a;
-						uint64_t r;
-						if (!phase) r = row[q];
-						else {
-							const uint64_t hi = mcb_rc_word(row[Wd - 1 - q]);
-							const uint64_t lo = q + 1 < Wd ? mcb_rc_word(row[Wd - 2 - q]) : 0ull;
-							r = pad ? (hi >> (2 * pad)) | (lo << (64 - 2 * pad)) : hi;
-						}
-						if (q == Wd - 1) { w &= tailmask; r &= tailmask; }
-						return w ^ r;
-					};
-					int pc = 0;
-#pragma unroll
-					for (int q = 0; q < 8; ++q) if (q < Wd) pc += __popcll(xword(q));
-					if (pc > gm.thr) continue;
-					if (phase == 0 || gm.thr > 24) {                                             // encode_byte gate, :393 / :461
-						int len_e = 0, eq = 0;
-#pragma unroll 1
-						for (int q = 0; q < Wd; ++q) {
-							uint64_t x = xword(q);
-							const int lim = min(32, L - q * 32);
-							for (int j = 0; j < lim; ++j, x >>= 2) {
-								if (x & 3) {
-									if (eq > 1) { len_e += ndigits(eq); eq = 0; }
-									else len_e += eq;                                                   // stale-counter quirk of :301-305
-									++len_e;
-								} else ++eq;
-							}
-						}
-						if (len_e == 0) len_e = 1;
-						if (len_e > gm.enc_limit) continue;
-					}
-					if (sketch_big) {
-						// The reference scans only the last `maxsearch` live entries of a bin (:388); with every bin at most that
-						// large the scan sees everything and "all matches, first one wins" is exact.
-						bool big = true;
-						if (p.xkey) big = bins_exact_count(p.xkey, p.xcnt, p.xmask, ((unsigned long long)l << 34) | key_f) > (uint32_t)gm.maxsearch;
-						if (big) atomicAdd(&p.counters[CT_S2_NEEDEXACT], 1ull);
-					}
-					const unsigned long long g = p.window_base + cm.woff + (unsigned long long)jj;
-					atomicMin(&p.claim[s], (g << 5) | ((unsigned long long)phase << 4) | (unsigned long long)l);
+				if (phase < nphase) {
+					const uint32_t b = kmer_bucket(key2[phase], p.pbits);
+					lo2[phase] = b ? p.ptab[b - 1] : 0u;
+					hi2[phase] = p.ptab[b];
 				}
 			}
 		}
 	}
-	for (int o = 16; o; o >>= 1) n_cand += __shfl_xor_sync(0xFFFFFFFFu, n_cand, o);
-	if ((threadIdx.x & 31) == 0 && n_cand) atomicAdd(&p.counters[CT_S2_CAND], n_cand);
+#pragma unroll
+	for (int phase = 0; phase < 2; ++phase) {
+		const uint32_t n_it = hi2[phase] - lo2[phase];
+		uint32_t max_it = n_it;
+		for (int o = 16; o; o >>= 1) max_it = max(max_it, __shfl_xor_sync(0xFFFFFFFFu, max_it, o));
+		for (uint32_t it = 0; it < max_it; ++it) {
+			unsigned long long e = 0; bool hit = false;
+			if (it < n_it) { e = p.ents[lo2[phase] + it]; hit = (e >> S2_POS_BITS) == key2[phase]; }
+			const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+			if (!bal) continue;
+			unsigned long long base = 0;
+			if (lane == 0) base = atomicAdd(&p.counters[CT_S2_NCAND], (unsigned long long)__popc(bal));
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			const unsigned long long at = base + __popc(bal & ((1u << lane) - 1u));
+			if (hit && at < cand_cap) cand[at] = (idx << 31) | ((unsigned long long)phase << S2_CAND_PHASE_BIT) | (e & S2_POS_MASK);
+		}
+	}
+}
+
+// K7b: verify.  One thread per candidate: contig coordinates, window validity, XOR/popcount against the single (or its
+// reverse complement), the encode_byte gate, and the claim.
+__global__ void __launch_bounds__(128) k_s2_verify(S2Join p, S2Geom gm, const unsigned long long *__restrict__ cand, uint64_t n_cand_listed)
+{
+	const uint64_t ci = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long n_valid = 0;
+	if (ci < n_cand_listed) {
+		const unsigned long long cr = cand[ci];
+		const uint64_t idx = cr >> 31, P = cr & S2_POS_MASK;
+		const int phase = (int)((cr >> S2_CAND_PHASE_BIT) & 1);
+		const int l = (int)(idx / p.S); const uint64_t s = idx - (uint64_t)l * p.S;
+		const int L = gm.L, Wd = gm.Wd, lt = gm.lt, ds = gm.dstart[l];
+		const int koff = phase ? L - ds - lt : ds;
+		uint32_t c = p.pblk[P >> S2_BLK_SHIFT];
+		S2ContigMeta cm = p.meta[c];
+		while (cm.ref_off + cm.len <= P) cm = p.meta[++c];
+		const long long jj = (long long)(P - cm.ref_off) - koff;
+		if (jj >= 0 && (uint64_t)jj + L <= cm.len) {
+			n_valid = 1;
+			const uint64_t *__restrict__ row = p.rd + s * gm.WS;
+			const uint64_t tailmask = (L & 31) ? (1ull << (2 * (L & 31))) - 1 : ~0ull;
+			const int pad = Wd * 32 - L;
+			const uint64_t *__restrict__ src = p.cw + cm.cw_off + ((uint64_t)jj >> 5);
+			const int sh = 2 * (int)(jj & 31);
+			// word q of (window XOR single); for the reverse phase the single is reverse-complemented on the fly:
+			// reverse the fields over Wd words, then drop the pad fields that moved to the bottom
+			auto xword = [&](int q) -> uint64_t {
+				const uint64_t a = src[q];
+				uint64_t w = sh ? (a >> sh) | (src[q + 1] << (64 - sh)) : a;
+				uint64_t r;
+				if (!phase) r = row[q];
+				else {
+					const uint64_t hi = mcb_rc_word(row[Wd - 1 - q]);
+					const uint64_t lo = q + 1 < Wd ? mcb_rc_word(row[Wd - 2 - q]) : 0ull;
+					r = pad ? (hi >> (2 * pad)) | (lo << (64 - 2 * pad)) : hi;
+				}
+				if (q == Wd - 1) { w &= tailmask; r &= tailmask; }
+				return w ^ r;
+			};
+			int pc = 0;
+#pragma unroll
+			for (int q = 0; q < 8; ++q) if (q < Wd) pc += __popcll(xword(q));
+			bool ok = pc <= gm.thr;
+			if (ok && (phase == 0 || gm.thr > 24)) {                                             // encode_byte gate, :393 / :461
+				int len_e = 0, eq = 0;
+#pragma unroll 1
+				for (int q = 0; q < Wd; ++q) {
+					uint64_t x = xword(q);
+					const int lim = min(32, L - q * 32);
+					for (int j = 0; j < lim; ++j, x >>= 2) {
+						if (x & 3) {
+							if (eq > 1) { len_e += ndigits(eq); eq = 0; }
+							else len_e += eq;                                                   // stale-counter quirk of :301-305
+							++len_e;
+						} else ++eq;
+					}
+				}
+				if (len_e == 0) len_e = 1;
+				ok = len_e <= gm.enc_limit;
+			}
+			if (ok) {
+				if (p.counters[CT_S2_MAXBIN] > (unsigned long long)gm.maxsearch) {
+					// The reference scans only the last `maxsearch` live entries of a bin (:388); with every bin at most that
+					// large the scan sees everything and "all matches, first one wins" is exact.
+					bool big = true;
+					if (p.xkey) {
+						const int bit = 2 * ds, wi = bit >> 6, shk = bit & 63;
+						uint64_t v = row[wi] >> shk;
+						if (shk + 2 * lt > 64) v |= row[wi + 1] << (64 - shk);
+						big = bins_exact_count(p.xkey, p.xcnt, p.xmask, ((unsigned long long)l << 34) | (v & ((1ull << (2 * lt)) - 1))) > (uint32_t)gm.maxsearch;
+					}
+					if (big) atomicAdd(&p.counters[CT_S2_NEEDEXACT], 1ull);
+				}
+				const unsigned long long g = p.window_base + cm.woff + (unsigned long long)jj;
+				atomicMin(&p.claim[s], (g << 5) | ((unsigned long long)phase << 4) | (unsigned long long)l);
+			}
+		}
+	}
+	for (int o = 16; o; o >>= 1) n_valid += __shfl_xor_sync(0xFFFFFFFFu, n_valid, o);
+	if ((threadIdx.x & 31) == 0 && n_valid) atomicAdd(&p.counters[CT_S2_CAND], n_valid);
 }
 
 // ---------------------------------------------------------------- K8
@@ -568,8 +601,23 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents_sorted; jn.pbits = cx.pbits;
 	jn.pblk = cx.pblk.as<uint32_t>(); jn.meta = cx.meta.as<S2ContigMeta>(); jn.cw = cx.cw.as<uint64_t>();
 	jn.claim = claim; jn.window_base = window_base; jn.counters = dc;
+	// candidate list: sized from the previous call's count, grown (and the probe repeated) when it overflows
+	DBuf &b_cand = ctx->d_x[3];
+	if (b_cand.cap < (nkv / 2 + 1024) * 8) MCB_TRY(b_cand.ensure((nkv / 2 + 1024) * 8));
+	uint64_t n_listed = 0;
+	for (int tries = 0;; ++tries) {
+		const uint64_t cap = b_cand.cap / 8;
+		MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NCAND], 0, 8, ctx->stream));
+		MCB_LAUNCH(ctx, "s2_probe_table", k_s2_probe_table, mcb_grid_for(nkv, 256), 256, 0, jn, gm, b_cand.as<unsigned long long>(), (unsigned long long)cap);
+		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		n_listed = hc[CT_S2_NCAND];
+		if (n_listed <= cap) break;
+		if (tries) { mcb_set_error("mcb_realign: candidate list overflow"); return MCB_EINVAL; }
+		MCB_TRY(b_cand.ensure(n_listed * 8 + 1024));
+	}
 	for (int attempt = 0;; ++attempt) {
-		MCB_LAUNCH(ctx, "s2_join", k_s2_join, mcb_grid_for(nkv, 128), 128, 0, jn, gm);
+		if (n_listed) MCB_LAUNCH(ctx, "s2_verify", k_s2_verify, mcb_grid_for(n_listed, 128), 128, 0, jn, gm, b_cand.as<unsigned long long>(), n_listed);
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 		if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }

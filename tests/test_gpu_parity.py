@@ -178,6 +178,7 @@ ORACLE_CASES = [
     ("n129", 129, 100, 600, 38, 0.02, {}),
     ("dup_heavy", 8000, 100, 4000, 39, 0.0, {}),          # 200x coverage: big groups, long contigs, buckets above 64 tuples
     ("rounds_many", 8000, 100, 40000, 40, 0.0, {"k": 14, "e": 2}),
+    ("huge_groups", 150000, 100, 130, 42, 0.0, {}),        # 31 start positions: groups beyond the bit-sliced counters (> 60000 members) and of every size class
 ]
 
 
