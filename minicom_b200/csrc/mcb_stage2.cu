@@ -276,7 +276,7 @@ __device__ __forceinline__ uint64_t rev_fields(uint64_t v, int nbases)
 
 // K7a: probe.  One thread per (single, dictionary): the key and its reverse complement are looked up in the contig table;
 // every entry with an equal lt-mer becomes a candidate record (pair index | phase | contig position), appended with one
-// atomic per warp and loop step.  No verification here: key matches are sparse (a fraction of a match per thread), and
+// atomic per warp.  No verification here: key matches are sparse (a fraction of a match per thread), and
 // verifying them inside this loop left 31 lanes idle around each one.
 #define S2_CAND_PHASE_BIT 30
 __global__ void __launch_bounds__(256) k_s2_probe_table(S2Join p, S2Geom gm, unsigned long long *__restrict__ cand, unsigned long long cand_cap)
@@ -308,22 +308,31 @@ __global__ void __launch_bounds__(256) k_s2_probe_table(S2Join p, S2Geom gm, uns
 			}
 		}
 	}
+	// count this lane's key matches, reserve room for the whole warp with ONE atomic, then write them (the second sweep over
+	// the few table entries hits L1)
+	unsigned mine = 0;
 #pragma unroll
-	for (int phase = 0; phase < 2; ++phase) {
-		const uint32_t n_it = hi2[phase] - lo2[phase];
-		uint32_t max_it = n_it;
-		for (int o = 16; o; o >>= 1) max_it = max(max_it, __shfl_xor_sync(0xFFFFFFFFu, max_it, o));
-		for (uint32_t it = 0; it < max_it; ++it) {
-			unsigned long long e = 0; bool hit = false;
-			if (it < n_it) { e = p.ents[lo2[phase] + it]; hit = (e >> S2_POS_BITS) == key2[phase]; }
-			const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
-			if (!bal) continue;
-			unsigned long long base = 0;
-			if (lane == 0) base = atomicAdd(&p.counters[CT_S2_NCAND], (unsigned long long)__popc(bal));
-			base = __shfl_sync(0xFFFFFFFFu, base, 0);
-			const unsigned long long at = base + __popc(bal & ((1u << lane) - 1u));
-			if (hit && at < cand_cap) cand[at] = (idx << 31) | ((unsigned long long)phase << S2_CAND_PHASE_BIT) | (e & S2_POS_MASK);
-		}
+	for (int phase = 0; phase < 2; ++phase)
+		for (uint32_t i = lo2[phase]; i < hi2[phase]; ++i) mine += (p.ents[i] >> S2_POS_BITS) == key2[phase];
+	unsigned inc = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+	const unsigned total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+	if (total == 0) return;
+	unsigned long long base = 0;
+	if (lane == 0) base = atomicAdd(&p.counters[CT_S2_NCAND], (unsigned long long)total);
+	base = __shfl_sync(0xFFFFFFFFu, base, 0);
+	unsigned long long at = base + (inc - mine);
+	if (mine) {
+#pragma unroll
+		for (int phase = 0; phase < 2; ++phase)
+			for (uint32_t i = lo2[phase]; i < hi2[phase]; ++i) {
+				const unsigned long long e = p.ents[i];
+				if ((e >> S2_POS_BITS) == key2[phase]) {
+					if (at < cand_cap) cand[at] = (idx << 31) | ((unsigned long long)phase << S2_CAND_PHASE_BIT) | (e & S2_POS_MASK);
+					++at;
+				}
+			}
 	}
 }
 
