@@ -147,16 +147,30 @@ def measured_peaks():
 
 
 def algorithmic_bytes(kernel, c):
-    """SURVEY.md 8(d) per-unit figures x the units of one step (DESIGN.md 'roofline accounting')."""
+    """(algorithmic bytes per launch, launches per step) of one kernel: SURVEY.md 8(d) per-unit figures x the units one
+    launch processes ("roofline accounting").  Kernels the survey has no term for get the bytes they cannot
+    avoid moving (inputs read once + outputs written once)."""
     L4 = (c["L"] + 3) // 4
-    if kernel == "k:s2_probe":          # per launch: one threshold round
-        return sum(8 * (2 * r["nd"] - 1) * r["W"] + L4 * r["C"] + (r["R"] + 3) // 4 for r in c["rounds"]) / max(1, len(c["rounds"])), len(c["rounds"])
-    if kernel == "k:pack_classify_sketch":
+    rounds = c["rounds"]
+    nr = max(1, len(rounds))
+    if kernel == "k:pack_classify_sketch":        # packed read + tuple per read
         return c["N"] * (L4 + 16), 1
     if kernel in ("k:sort_scatter", "k:sort_hist"):
-        return None, None                # filled by caller: 32 B x elements per pass
-    if kernel == "k:consensus":
+        return None, None                          # filled by the caller: 32 B x tuples, spread over the passes
+    if kernel == "k:consensus":                   # count + verify: 2 x packed read per grouped read
         return 2 * L4 * c["N_grp"] / max(1, c["bucket_rounds"]), c["bucket_rounds"]
+    if kernel == "k:index_sort":                  # one read + one write of every 16-byte tuple
+        return 32 * c["T_cb"] / max(1, c["n_idx"]), c["n_idx"]
+    if kernel == "k:sketch_lh":                   # consensus characters in, first m tuples out
+        return (c["seed_ref_bytes"] + 16 * c["m"] * c["clusters"]) / max(1, c["bucket_rounds"]), c["bucket_rounds"]
+    if kernel in ("k:s2_kmer_sort_scatter", "k:s2_kmer_sort_hist"):   # 8-byte table entries, read + written once per pass
+        return 16 * rounds[0]["R"] if rounds else None, None
+    if kernel == "k:s2_probe_table":              # per single: packed read + 12 B per dictionary (key + bin slot)
+        return sum(r["S"] * (L4 + 12 * r["nd"]) for r in rounds) / nr, nr
+    if kernel == "k:s2_verify":                   # per candidate: the window and the single
+        return sum(2 * L4 * r["C"] for r in rounds) / nr, nr
+    if kernel == "k:s2_singles":
+        return sum(r["S"] * 2 * L4 for r in rounds) / nr, nr
     return None, None
 
 
@@ -259,7 +273,8 @@ def bench_ours(args):
             rounds.append({"S": len(sg), "R": int(len(refs)), "W": int(r.n_windows), "C": int(r.n_candidates), "nd": int(r.numdict), "claims": int(r.n_claims),
                            "probes": int(r.n_probes), "polyAT": int(r.n_fpA + r.n_fpT)})
         w["realign"] += time.perf_counter() - t
-        counters.update({"N": n, "L": L, "N_sk": int(br.n_sketched_total), "N_grp": int(br.n_grouped), "bucket_rounds": int(br.rounds), "clusters": nc,
+        counters.update({"N": n, "L": L, "m": int(params.first_mininum), "n_idx": len(idx_calls), "seed_ref_bytes": ref_bytes,
+                         "N_sk": int(br.n_sketched_total), "N_grp": int(br.n_grouped), "bucket_rounds": int(br.rounds), "clusters": nc,
                          "singles_stage1": int(br.n_sg), "T_cb": int(sum(len(x[0]) // 2 for x in idx_calls)), "rounds": rounds})
         # bytes crossing PCIe in this step, counted from the arrays the library copies (inputs in, results out)
         h2d = (0 if device_resident else n * L) + sum(x[0].nbytes + x[1].nbytes for x in idx_calls) + sum(c[0].nbytes + (0 if same_contigs[j] else c[1].nbytes + 3 * c[2].nbytes) for j, c in enumerate(realign_calls))
@@ -320,12 +335,20 @@ def bench_ours(args):
     dom_ms, dom_cnt = kern[dom]
     ab, per_step_launches = algorithmic_bytes(dom, counters)
     if ab is None and dom in ("k:sort_scatter", "k:sort_hist"):
-        ab = 32.0 * (counters["N_sk"] + counters["T_cb"]) / max(1, dom_cnt / args.steps)
+        ab = 32.0 * counters["N_sk"] / max(1, dom_cnt / args.steps)
+    if dom in ("k:s2_kmer_sort_scatter", "k:s2_kmer_sort_hist") and ab:
+        pass                                                  # per pass (= per launch): every entry read and written once
     avg_launch_s = dom_ms / max(1, dom_cnt) / 1e3
     achieved = (ab / avg_launch_s / 1e9) if ab else None
     roof = {"bound": "hbm", "kernel": dom[2:], "achieved": round(achieved, 2) if achieved else None, "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 5) if achieved else None, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ab, "avg_launch_ms": dom_ms / max(1, dom_cnt), "share_of_device_time": round(dom_ms / max(1e-9, dev_ms(tm)), 4)}
+    # the whole path against SURVEY.md 8(d)'s formula A (what the reference's algorithm has to touch, per step)
+    L4 = (L + 3) // 4
+    A = (counters["N_sk"] * (L4 + 16) + 32 * (counters["N_sk"] + counters["T_cb"]) + 2 * L4 * counters["N_grp"]
+         + sum(r["S"] * (L4 + 12 * r["nd"]) + (r["R"] + 3) // 4 + 8 * (2 * r["nd"] - 1) * r["W"] + L4 * r["C"] for r in counters["rounds"]))
+    roof["whole_path"] = {"algorithmic_bytes_per_step": int(A), "achieved": round(A / (ms_dev_max / 1e3) / 1e9, 2), "frac": round(A / (ms_dev_max / 1e3) / 1e9 / peak, 5),
+                          "note": "SURVEY 8(d) formula A over the device time of the step; its Stage-2 term charges 8 B for each of the reference's W*(2nd-1) window probes, which the inverted join never issues"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:

@@ -141,7 +141,7 @@ struct McbSpan {
 enum { CT_SKETCHED = 0, CT_BADCHAR = 1, CT_DEGENERATE = 2, CT_NREADS = 3, CT_REFCURSOR = 4, CT_G = 5, CT_TOT_CL = 6, CT_TOT_MEM = 7,
        CT_TOT_REF = 8, CT_TOT_SG = 9, CT_TOT_RESK = 10, CT_ERR = 11, CT_SCRATCH_IDX = 12,
        CT_S2_U = 16, CT_S2_PROBES = 17, CT_S2_CAND = 18, CT_S2_NEEDEXACT = 19, CT_S2_CLAIMS = 20, CT_S2_FPA = 21, CT_S2_FPT = 22, CT_S2_ERR = 23,
-       CT_S2_MAXBIN = 24, CT_S2_DIFF = 25, CT_S2_NCAND = 26, CT_WORK0 = 32 /* ..35: consensus work-list sizes */ };
+       CT_S2_MAXBIN = 24, CT_S2_DIFF = 25, CT_S2_NCAND = 26, CT_S2_NBIGMEM = 27, CT_S2_NEVENTS = 28, CT_WORK0 = 32 /* ..35: consensus work-list sizes */ };
 
 // ---------------------------------------------------------------- context
 struct mcb_index;   // defined in mcb_index.cu

@@ -255,6 +255,29 @@ __device__ __forceinline__ uint32_t bins_exact_count(const unsigned long long *_
 	}
 }
 
+// exact mode: every (single, dictionary) whose bin is larger than maxsearch -> inbig[single] = 1 and a (bin key, single) record
+__global__ void k_s2_mark_big(const uint64_t *__restrict__ rd, uint64_t S, S2Geom gm, const unsigned long long *__restrict__ tkey, const uint32_t *__restrict__ tcnt, uint64_t hmask,
+                              uint8_t *__restrict__ inbig, unsigned long long *__restrict__ members, unsigned long long cap, unsigned long long *__restrict__ counters)
+{
+	uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= S * (uint64_t)gm.nd) return;
+	const int l = (int)(idx / S); const uint64_t s = idx - (uint64_t)l * S;
+	const uint64_t *row = rd + s * gm.WS;
+	const int bit = 2 * gm.dstart[l], wi = bit >> 6, sh = bit & 63;
+	uint64_t v = row[wi] >> sh;
+	if (sh + 2 * gm.lt > 64) v |= row[wi + 1] << (64 - sh);
+	const unsigned long long key = ((unsigned long long)l << 34) | (v & ((1ull << (2 * gm.lt)) - 1));
+	if (bins_exact_count(tkey, tcnt, hmask, key) <= (uint32_t)gm.maxsearch) return;
+	inbig[s] = 1;
+	const unsigned long long at = atomicAdd(&counters[CT_S2_NBIGMEM], 1ull);
+	if (at < cap) { members[2 * at] = key; members[2 * at + 1] = s; }
+}
+__global__ void k_s2_apply_claims(const unsigned long long *__restrict__ pairs, uint64_t n, unsigned long long *__restrict__ claim)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) claim[pairs[2 * i]] = pairs[2 * i + 1];
+}
+
 // ---------------------------------------------------------------- K7
 struct S2Join {
 	uint64_t S;
@@ -265,6 +288,9 @@ struct S2Join {
 	unsigned long long window_base;       // windows on lower ranks (0 on a single GPU)
 	unsigned long long *counters;
 	const unsigned long long *xkey; const uint32_t *xcnt; uint64_t xmask;   // exact bin sizes (null: trust the sketch)
+	// exact mode (some dictionary bin exceeds maxsearch): singles that sit in such a bin do not claim on the device; their
+	// verified matches are listed as events {priority, bin key, single} and replayed in order on the host
+	const uint8_t *inbig; unsigned long long *events; unsigned long long events_cap;
 };
 
 __device__ __forceinline__ uint64_t rev_fields(uint64_t v, int nbases)
@@ -395,6 +421,18 @@ __global__ void __launch_bounds__(128) k_s2_verify(S2Join p, S2Geom gm, const un
 				}
 				if (len_e == 0) len_e = 1;
 				ok = len_e <= gm.enc_limit;
+			}
+			if (ok && p.inbig) {                 // exact mode
+				const unsigned long long g = p.window_base + cm.woff + (unsigned long long)jj;
+				const unsigned long long prio = (g << 5) | ((unsigned long long)phase << 4) | (unsigned long long)l;
+				if (p.inbig[s]) {
+					const int bit = 2 * ds, wi = bit >> 6, shk = bit & 63;
+					uint64_t v = row[wi] >> shk;
+					if (shk + 2 * lt > 64) v |= row[wi + 1] << (64 - shk);
+					const unsigned long long at = atomicAdd(&p.counters[CT_S2_NEVENTS], 1ull);
+					if (at < p.events_cap) { p.events[3 * at] = prio; p.events[3 * at + 1] = ((unsigned long long)l << 34) | (v & ((1ull << (2 * lt)) - 1)); p.events[3 * at + 2] = s; }
+				} else atomicMin(&p.claim[s], prio);
+				ok = false;
 			}
 			if (ok) {
 				if (p.counters[CT_S2_MAXBIN] > (unsigned long long)gm.maxsearch) {
@@ -548,6 +586,103 @@ static int realign_geometry(mcb_ctx *ctx, int threshold, int maxsearch, int inin
 	return MCB_OK;
 }
 
+// Sequential bin-window emulation for the singles that sit in a dictionary bin larger than maxsearch.
+// The device lists (a) the members of every such bin and (b) every verified match of every such single ("events").  The
+// host replays the events in the reference's probe order (priority ascending; inside one probe the bin is scanned from the
+// highest sg index down, kthread_hash_realign.c:388) with the reference's rules: a match counts only if the single is among
+// the last `maxsearch` LIVE entries of the probed bin; a claimed single leaves all its bins after the probe (:409-424),
+// except that the last entry of a bin is never removed and the bin is closed instead (bbhashdict.c:51-55); singles set
+// aside by the poly-A/T diversion stay in the bins for good.  Singles outside big bins keep the parallel first-wins rule.
+#include <unordered_map>
+struct BigBin { std::vector<uint32_t> mem; std::vector<int> fen; uint32_t live = 0; bool closed = false; };
+static void fen_add(std::vector<int> &f, size_t i, int d) { for (++i; i < f.size(); i += i & (~i + 1)) f[i] += d; }
+static int fen_sum(const std::vector<int> &f, size_t i) { int r = 0; for (; i > 0; i -= i & (~i + 1)) r += f[i]; return r; }   // live among the first i members
+
+static int realign_exact_bins(mcb_ctx *ctx, S2Join jn, const S2Geom &gm, uint64_t S, uint64_t nkv, uint64_t n_listed, const unsigned long long *d_cand)
+{
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
+	DBuf b_inbig, b_mem, b_ev, b_pairs;
+	struct Rel { DBuf *b[4]; ~Rel() { for (auto x : b) x->release(); } } rel = {{&b_inbig, &b_mem, &b_ev, &b_pairs}};
+	MCB_TRY(b_inbig.ensure(S + 16)); MCB_TRY(b_mem.ensure(nkv * 16 + 16)); MCB_TRY(b_ev.ensure(n_listed * 24 + 24));
+	MCB_CUDA(cudaMemsetAsync(b_inbig.p, 0, S, ctx->stream));
+	MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NBIGMEM], 0, 16, ctx->stream));      // NBIGMEM, NEVENTS
+	MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_CAND], 0, 8, ctx->stream)); MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NEEDEXACT], 0, 8, ctx->stream));
+	MCB_CUDA(cudaMemsetAsync(jn.claim, 0x7F, S * 8, ctx->stream));
+	MCB_LAUNCH(ctx, "s2_mark_big", k_s2_mark_big, mcb_grid_for(nkv, 256), 256, 0, jn.rd, S, gm, jn.xkey, jn.xcnt, jn.xmask, b_inbig.as<uint8_t>(),
+	           b_mem.as<unsigned long long>(), (unsigned long long)nkv, dc);
+	jn.inbig = b_inbig.as<uint8_t>(); jn.events = b_ev.as<unsigned long long>(); jn.events_cap = n_listed;
+	if (n_listed) MCB_LAUNCH(ctx, "s2_verify", k_s2_verify, mcb_grid_for(n_listed, 128), 128, 0, jn, gm, d_cand, n_listed);
+	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	const uint64_t n_mem = hc[CT_S2_NBIGMEM], n_ev = hc[CT_S2_NEVENTS];
+	std::vector<unsigned long long> mem(2 * n_mem), ev(3 * n_ev);
+	std::vector<uint8_t> flagged(S);
+	if (n_mem) MCB_CUDA(cudaMemcpyAsync(mem.data(), b_mem.p, n_mem * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	if (n_ev) MCB_CUDA(cudaMemcpyAsync(ev.data(), b_ev.p, n_ev * 24, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaMemcpyAsync(flagged.data(), jn.flagged, S, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	// bins
+	std::unordered_map<unsigned long long, BigBin> bins;
+	std::unordered_map<uint32_t, std::vector<unsigned long long>> bins_of;      // single -> keys of its big bins
+	for (uint64_t i = 0; i < n_mem; ++i) { bins[mem[2 * i]].mem.push_back((uint32_t)mem[2 * i + 1]); bins_of[(uint32_t)mem[2 * i + 1]].push_back(mem[2 * i]); }
+	for (auto &kv : bins) {
+		BigBin &b = kv.second;
+		std::sort(b.mem.begin(), b.mem.end());
+		b.live = (uint32_t)b.mem.size();
+		b.fen.assign(b.mem.size() + 1, 0);
+		for (size_t i = 0; i < b.mem.size(); ++i) fen_add(b.fen, i, 1);
+	}
+	// events in probe order; inside a probe from the highest sg index down
+	std::vector<uint64_t> order(n_ev);
+	for (uint64_t i = 0; i < n_ev; ++i) order[i] = i;
+	std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+		if (ev[3 * a] != ev[3 * b]) return ev[3 * a] < ev[3 * b];
+		return ev[3 * a + 2] > ev[3 * b + 2];
+	});
+	std::unordered_map<uint32_t, unsigned long long> claimed;                  // single -> winning priority
+	std::vector<uint32_t> removed;
+	for (uint64_t i = 0; i < n_ev;) {
+		uint64_t j = i;
+		while (j < n_ev && ev[3 * order[j]] == ev[3 * order[i]]) ++j;            // one probe = one (window, phase, l) = one bin
+		const unsigned long long prio = ev[3 * order[i]], key = ev[3 * order[i] + 1];
+		auto bit = bins.find(key);
+		BigBin *bb = bit == bins.end() ? nullptr : &bit->second;
+		removed.clear();
+		if (!bb || !bb->closed) {
+			for (uint64_t q = i; q < j; ++q) {
+				const uint32_t sgi = (uint32_t)ev[3 * order[q] + 2];
+				if (flagged[sgi] || claimed.count(sgi)) continue;
+				if (bb) {                                                              // among the last maxsearch live entries?
+					const size_t pos = (size_t)(std::lower_bound(bb->mem.begin(), bb->mem.end(), sgi) - bb->mem.begin());
+					const int live_above = (int)bb->live - fen_sum(bb->fen, pos + 1);
+					if (live_above >= gm.maxsearch) continue;
+				}
+				claimed[sgi] = prio;
+				removed.push_back(sgi);
+			}
+		}
+		for (uint32_t sgi : removed)                                                  // :409-424: out of every dictionary
+			for (unsigned long long k2 : bins_of[sgi]) {
+				BigBin &b = bins[k2];
+				if (b.live == 1) { b.closed = true; continue; }                       // last entry stays, bin is closed
+				const size_t pos = (size_t)(std::lower_bound(b.mem.begin(), b.mem.end(), sgi) - b.mem.begin());
+				fen_add(b.fen, pos, -1); --b.live;
+			}
+		i = j;
+	}
+	// hand the winners back to the device claim array
+	if (!claimed.empty()) {
+		std::vector<unsigned long long> pairs; pairs.reserve(2 * claimed.size());
+		for (auto &kv : claimed) { pairs.push_back(kv.first); pairs.push_back(kv.second); }
+		MCB_TRY(b_pairs.ensure(pairs.size() * 8));
+		MCB_CUDA(cudaMemcpyAsync(b_pairs.p, pairs.data(), pairs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+		MCB_LAUNCH(ctx, "s2_apply_claims", k_s2_apply_claims, mcb_grid_for(claimed.size(), 256), 256, 0, b_pairs.as<unsigned long long>(), (uint64_t)claimed.size(), jn.claim);
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	return MCB_OK;
+}
+
 // first half: contigs, singles, join.  Leaves the claim priorities in ctx->d_x[0] (u64[S]).
 static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
                           uint64_t window_base, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
@@ -632,9 +767,17 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 		if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }
 		if (!hc[CT_S2_NEEDEXACT]) break;
 		if (attempt == 1) {
-			mcb_set_error("mcb_realign: %llu matches fall into dictionary bins with more than maxsearch=%d singles; the sequential bin-window emulation "
-			              "(kthread_hash_realign.c:388, bbhashdict.c:33-67) is not implemented", hc[CT_S2_NEEDEXACT], maxsearch);
-			return MCB_EINPUT;
+			// Some verified match lies in a bin larger than maxsearch: the reference's scan of "the last maxsearch live entries"
+			// (kthread_hash_realign.c:388) depends on which reads were already claimed.  Replay exactly those singles in order.
+			if (ctx->shard_n > 1 || window_base) {
+				mcb_set_error("mcb_realign: %llu matches fall into dictionary bins with more than maxsearch=%d singles; the sequential bin-window "
+				              "replay is not available when the contigs are sharded", hc[CT_S2_NEEDEXACT], maxsearch);
+				return MCB_EINPUT;
+			}
+			MCB_TRY(realign_exact_bins(ctx, jn, gm, S, nkv, n_listed, b_cand.as<unsigned long long>()));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+			break;
 		}
 		// the sketch only bounds bin sizes from above: count them exactly and join again
 		uint64_t H = 1024; while (H < 2 * nkv) H <<= 1;

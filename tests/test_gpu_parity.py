@@ -254,8 +254,9 @@ def test_realign_contig_cache_is_invalidated_by_content():
 
 
 def test_realign_bins_above_maxsearch():
-    """20 identical singles share every dictionary bin.  maxsearch >= 20: identical to the sequential scan.  maxsearch 4:
-    the reference would scan only the last 4 live entries per probe; the library refuses loudly instead of guessing."""
+    """20 identical singles share every dictionary bin.  The reference scans only the last `maxsearch` live entries of a bin
+    per probe (kthread_hash_realign.c:388) and removes claimed reads afterwards, so with maxsearch 4 window 0 claims them four
+    at a time, dictionary after dictionary.  The library detects the oversized bins and replays those singles sequentially."""
     import oracle_lib as O
     rng = np.random.default_rng(9)
     L = 100
@@ -267,12 +268,63 @@ def test_realign_bins_above_maxsearch():
     S = O.Stage1(O.resolve_params(L), reads)
     with api.Context(api.resolve_params(L)) as ctx:
         ctx.for_reads(reads)
-        want = S.realign(sg, contig, off, 4, 2000)
-        got = ctx.realign(sg, contig, off, 4, 2000)
-        assert np.array_equal(got.claim_y, want["claim_y"]) and len(got.claim_y) == 20
-        with pytest.raises(api.McbError):
-            ctx.realign(sg, contig, off, 4, 4)
+        for maxsearch in (2000, 4, 1, 7):
+            want = S.realign(sg, contig, off, 4, maxsearch)
+            got = ctx.realign(sg, contig, off, 4, maxsearch)
+            assert np.array_equal(got.claim_y, want["claim_y"]) and np.array_equal(got.claim_sg, want["claim_sg"]), f"maxsearch {maxsearch}"
     S.close()
+
+
+@pytest.mark.parametrize("maxsearch", [3, 11, 40])
+def test_realign_exact_replay_of_big_bins(maxsearch):
+    """High-duplication reads (31 start positions over a 130 bp genome, both strands, 1 % substitutions, a few poly-A reads
+    that stay in the bins) against the genome and its shuffled pieces as contigs, with a small maxsearch: most bins are
+    larger than the scan window, so the outcome depends on the order in which reads leave the bins."""
+    import oracle_lib as O
+    L = 100
+    genome = synth.make_genome(130, 77)
+    reads = synth.make_reads(1500, L, 130, seed=77, genome=genome, special=0.01)
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    contigs = [genome, comp[genome[::-1]], genome[:115], genome[12:]]
+    refs = np.concatenate(contigs)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in contigs])]).astype(np.uint64)
+    S = O.Stage1(O.resolve_params(L), reads)
+    sg = np.nonzero(S.cls == 0)[0].astype(np.uint32)
+    with api.Context(api.resolve_params(L)) as ctx:
+        ctx.for_reads(reads)
+        for thr in (4, 8, 30):
+            want = S.realign(sg, refs, off, thr, maxsearch)
+            got = ctx.realign(sg, refs, off, thr, maxsearch)
+            assert np.array_equal(got.claim_y, want["claim_y"]), f"thr {thr}: {len(got.claim_y)} vs {len(want['claim_y'])} claims"
+            assert np.array_equal(got.claim_contig, want["claim_contig"]) and np.array_equal(got.claim_sg, want["claim_sg"])
+            sg = sg[want["flag"] == 0]
+            if len(sg) == 0:
+                break
+    S.close()
+
+
+@pytest.mark.parametrize("n,distinct,nbuckets", [(200000, 4000, 300), (60000, 40, 7), (500000, 200000, 16384), (30000, 3, 1)])
+def test_index_posting_order_in_big_buckets(n, distinct, nbuckets):
+    """Buckets far above 64 tuples with many equal minimizers: the posting order is whatever the reference's unstable
+    in-place radix sort leaves (ksort.h:108-157); the oracle replays it on the CPU."""
+    import oracle_lib as O
+    rng = np.random.default_rng(n + distinct)
+    bks = rng.choice(1 << 14, size=nbuckets, replace=False).astype(np.uint64)
+    keys = (rng.integers(0, 1 << 48, size=distinct, dtype=np.uint64) << np.uint64(14)) | bks[rng.integers(0, nbuckets, size=distinct)]
+    xy = np.zeros((n, 2), dtype=np.uint64)
+    xy[:, 0] = keys[rng.integers(0, distinct, size=n)]
+    xy[:, 1] = np.arange(n, dtype=np.uint64)
+    off, flat = O.bucket_major(xy)
+    with api.Context(api.resolve_params(100)) as ctx:
+        ix, ox = ctx.idx_build(flat, off), O.Index(flat, off)
+        okeys, st, post = ox.flat()
+        assert ix.stats() == (ox.n_keys, ox.n_post)
+        for i in rng.choice(len(okeys), size=min(len(okeys), 3000), replace=False):
+            assert np.array_equal(ix.get(int(okeys[i])), post[int(st[i]):int(st[i + 1])]), f"key {int(okeys[i]):#x}"
+        ix.close()
+        ox.close()
 
 
 def test_empty_input():
