@@ -150,7 +150,8 @@ k_index_sort(mcb_tuple *__restrict__ t, const uint64_t *__restrict__ boff, int n
 // are in flight per SM — and the walk, a chain of dependent shared-memory loads, is bound by how many run concurrently.
 // Tuples go through a scratch copy in global memory (L2-resident per bucket).
 #define IX2_WARPS 4
-struct Ix2Smem { uint32_t *cur, *end; uint8_t *dg; uint16_t *dest; IxSeg *stk; };
+#define IX2_BYTES_PER_TUPLE 13            // xs 8 + dest/fin 2 + src 2 + digit 1
+struct Ix2Smem { uint32_t *cur, *end; uint64_t *xs; uint16_t *dest, *src; uint8_t *dg; IxSeg *stk; };
 
 __device__ void ix2_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix2Smem &m, IxSeg *gstk, int lane)
 {
@@ -165,7 +166,11 @@ __device__ void ix2_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix
 		__syncwarp();
 		for (int d = lane; d < 256; d += 32) m.cur[d] = 0;
 		__syncwarp();
-		for (uint32_t i = lane; i < cnt; i += 32) { const unsigned d = (unsigned)(a[sb + i].x >> s) & 255u; m.dg[i] = (uint8_t)d; atomicAdd(&m.cur[d], 1u); }
+		for (uint32_t i = lane; i < cnt; i += 32) {
+			const uint64_t x = a[sb + i].x;
+			const unsigned d = (unsigned)(x >> s) & 255u;
+			m.xs[i] = x; m.dg[i] = (uint8_t)d; atomicAdd(&m.cur[d], 1u);
+		}
 		__syncwarp();
 		{
 			uint32_t v[8], sum = 0;
@@ -180,7 +185,7 @@ __device__ void ix2_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix
 			for (int q = 0; q < 8; ++q) { m.cur[lane * 8 + q] = run; run += v[q]; m.end[lane * 8 + q] = run; }
 		}
 		__syncwarp();
-		if (lane == 0) {                          // the walk, on digits only
+		if (lane == 0) {                          // the walk of ksort.h:131-145, on digits only
 			for (int k = 0; k < 256;) {
 				const uint32_t ck = m.cur[k];
 				if (ck != m.end[k]) {
@@ -199,18 +204,35 @@ __device__ void ix2_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix
 			}
 		}
 		__syncwarp();
-		for (uint32_t i = lane; i < cnt; i += 32) tmp[sb + m.dest[i]] = a[sb + i];
+		for (uint32_t i = lane; i < cnt; i += 32) m.src[m.dest[i]] = (uint16_t)i;       // slot -> original index
 		__syncwarp();
-		for (uint32_t i = lane; i < cnt; i += 32) a[sb + i] = tmp[sb + i];
+		// digit regions of at most 64 tuples are insertion-sorted by the reference (stable, by the whole key): rank every slot
+		// inside its region instead.  `dest` is free now and becomes fin[final slot] = original index.  Bigger regions keep the
+		// order of the walk and are sorted by the next digit.
+		for (uint32_t p = lane; p < cnt; p += 32) {
+			const uint32_t i = m.src[p];
+			const unsigned d = m.dg[i];
+			const uint32_t rs = d ? m.end[d - 1] : 0u, re = m.end[d];
+			uint32_t at = p;
+			if (s > 0 && re - rs <= IX_SMALL && re - rs > 1) {
+				const uint64_t xi = m.xs[i];
+				uint32_t rank = 0;
+				for (uint32_t q = rs; q < re; ++q) { const uint64_t xq = m.xs[m.src[q]]; rank += (xq < xi) || (xq == xi && q < p); }
+				at = rs + rank;
+			}
+			m.dest[at] = (uint16_t)i;
+		}
+		__syncwarp();
+		for (uint32_t p = lane; p < cnt; p += 32) tmp[sb + p] = a[sb + m.dest[p]];
+		__syncwarp();
+		for (uint32_t p = lane; p < cnt; p += 32) a[sb + p] = tmp[sb + p];
 		__syncwarp();
 		if (s > 0) {
 			const int s2 = s > 8 ? s - 8 : 0;
 			for (int d0 = 0; d0 < 256; d0 += 32) {
 				const int d = d0 + lane;
 				const uint32_t rb = sb + (d == 0 ? 0u : m.end[d - 1]), re = sb + m.end[d];
-				const uint32_t sz = re - rb;
-				const bool big = sz > IX_SMALL;
-				if (!big && sz > 1) ix_insertion_sort(a + rb, sz);
+				const bool big = re - rb > IX_SMALL;
 				const unsigned bm = __ballot_sync(0xFFFFFFFFu, big);
 				if (big) {
 					const int slot = top + __popc(bm & ((1u << lane) - 1u));
@@ -230,13 +252,14 @@ k_index_sort2(mcb_tuple *__restrict__ t, mcb_tuple *__restrict__ tmp, const uint
 {
 	extern __shared__ __align__(16) unsigned char ix2_smem[];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * 3 + 15) & ~(size_t)15;
+	const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * IX2_BYTES_PER_TUPLE + 15) & ~(size_t)15;
 	unsigned char *base = ix2_smem + (size_t)wib * per_warp;
 	Ix2Smem m;
 	m.cur = (uint32_t*)base; m.end = m.cur + 256;
 	m.stk = (IxSeg*)(base + 2048);
-	m.dest = (uint16_t*)(base + 2048 + IX_SMEM_STK * sizeof(IxSeg));
-	m.dg = (uint8_t*)(m.dest + cap);
+	m.xs = (uint64_t*)(base + 2048 + IX_SMEM_STK * sizeof(IxSeg));
+	m.dest = (uint16_t*)(m.xs + cap); m.src = m.dest + cap;
+	m.dg = (uint8_t*)(m.src + cap);
 	for (int bk = blockIdx.x * IX2_WARPS + wib; bk < nb; bk += gridDim.x * IX2_WARPS) {
 		const uint64_t B0 = boff[bk], B1 = boff[bk + 1];
 		const uint32_t n = (uint32_t)(B1 - B0);
@@ -353,9 +376,11 @@ static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mc
 		McbSpan sp(ctx->tm, "idx_build");
 		uint64_t maxb = 0;
 		for (int i = 0; i < nb; ++i) maxb = std::max<uint64_t>(maxb, h_boff[i + 1] - h_boff[i]);
-		if (maxb <= 12000) {      // index-space walk: 3 bytes of shared memory per tuple of the largest bucket
+		static const bool force_old = getenv("MCB_IX_OLD") != nullptr;
+		if (getenv("MCB_IX_DEBUG")) fprintf(stderr, "[mcb] idx build: n=%llu max bucket=%llu\n", (unsigned long long)n, (unsigned long long)maxb);
+		if (maxb <= 4096 && !force_old) {      // index-space walk: 13 bytes of shared memory per tuple of the largest bucket
 			const uint32_t cap = (uint32_t)std::max<uint64_t>(64, (maxb + 63) & ~63ull);
-			const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * 3 + 15) & ~(size_t)15;
+			const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * IX2_BYTES_PER_TUPLE + 15) & ~(size_t)15;
 			const size_t smem2 = per_warp * IX2_WARPS;
 			MCB_TRY(ctx->d_scr[8].ensure(n * 16 + 16));
 			if (smem2 > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_index_sort2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
