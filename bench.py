@@ -462,8 +462,10 @@ def bench_sharded(args):
     for j, (sg, refs, off, thr, ms, nd) in enumerate(realign_calls):
         same = j > 0 and np.array_equal(refs, realign_calls[j - 1][1]) and np.array_equal(off, realign_calls[j - 1][2])
         cuts, wbase = shard.contig_partition(off, world, L)
-        c0, c1 = int(cuts[rank]), int(cuts[rank + 1])
-        my_realign.append((pin(sg), None if same else pin(refs[int(off[c0]):int(off[c1])]), None if same else (off[c0:c1 + 1] - off[c0]), int(wbase[rank]), thr, ms, nd))
+        lens = np.diff(off.astype(np.int64))
+        n_win = int(np.where(lens >= L, lens - L + 1, 0).sum())
+        g_lo, g_hi = int(wbase[rank]), (int(wbase[rank + 1]) if rank + 1 < world else n_win)
+        my_realign.append((pin(sg), None if same else pin(refs), None if same else off, g_lo, g_hi, thr, ms, nd))
     T_cb = int(sum(len(x[0]) // 2 for x in idx_calls))
     R_total = int(len(realign_calls[0][1])) if realign_calls else 0
     del idx_calls, realign_calls
@@ -484,8 +486,8 @@ def bench_sharded(args):
         for xy, off in my_idx:
             ctx.idx_build(xy, off).close()
         claims = 0
-        for sg, refs, off, wb, thr, ms, nd in my_realign:
-            r = fe.realign(sg, refs, off, wb, thr, ms, nd)
+        for sg, refs, off, g_lo, g_hi, thr, ms, nd in my_realign:
+            r = fe.realign(sg, refs, off, g_lo, g_hi, thr, ms, nd)
             claims += len(r.claim_y)
         stats.update({"seed_contigs_rank0": int(len(part.cl_n)), "singles_rank0": int(len(part.sg)), "claims_rank0": claims, "bucket_rounds": int(len(part.rounds))})
 
@@ -536,7 +538,7 @@ def bench_sharded(args):
             "ms_per_step": round(ms_dev_max, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"{args.workload} x {world}: ONE job of {n_total} x {L} bp reads ({n} per GPU), {G_total} bp random genome, 1% substitutions, mode {mode}, defaults k=31 m=6 e=4",
                        "sharding": "reads by read-id range; tuples all-to-all by bucket owner (bucket*G>>14) every round; packed reads all-gather; index builds by bucket range; "
-                                   "Stage 2 contigs partitioned, claim priorities all-reduce(MIN); results bit-identical to one GPU (tests/test_gpu_shard.py)",
+                                   "Stage 2 contig lt-mer table partitioned by hash range (each rank probes the lt-mers it owns), claim priorities all-reduce(MIN), claims emitted by window range; results bit-identical to one GPU (tests/test_gpu_shard.py)",
                        "l2": "inputs larger than L2 (reads %.0f MB per GPU per step)" % (n * L / 1e6),
                        "timing": "value = max over ranks of (CUDA-event time of the library entry points + CUDA-event time of the NCCL collectives), reads resident in HBM; e2e = max over ranks of the wall clock with pinned host inputs and results copied back",
                        "bases_per_s": round(value * L, 1), "wall_ms_per_step_device_arm": round(ms_wall_dev_max, 3), "collective_ms_per_step": round(coll_max, 3),

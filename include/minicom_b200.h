@@ -229,6 +229,14 @@ int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *ref
 int mcb_realign_begin(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
                       uint64_t window_base, int threshold, int maxsearch, int ininumdict, void **d_claim);
 int mcb_realign_finish(mcb_ctx *ctx, mcb_realign_result *res);
+/* Key-sharded variant (the one minicom_b200/shard.py uses): every rank is given ALL contigs and all singles, keeps share
+ * tab_rank of tab_ranks of the contig lt-mer table (hash ranges), probes only the lt-mers it owns — so the probe work per rank
+ * does not grow with the number of GPUs — and, after the caller's min-reduce, emits the claims of windows [g_lo, g_hi) with
+ * GLOBAL contig indices.  *maxbin_upper: upper bound of the largest dictionary bin counted on this rank; if the maximum over
+ * the ranks exceeds maxsearch the caller must stop (the sequential bin-window replay exists only on one GPU). */
+int mcb_realign_begin_keyed(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
+                            int tab_rank, int tab_ranks, uint64_t g_lo, uint64_t g_hi, int threshold, int maxsearch, int ininumdict,
+                            void **d_claim, uint64_t *maxbin_upper);
 
 /* ------------------------------------------------------------------ */
 /* host-side boundary helpers                                           */

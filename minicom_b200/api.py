@@ -57,7 +57,7 @@ EXPORTS = [
     "mcb_round_control_init", "mcb_round_control_begin", "mcb_round_control_end",
     "mcb_shard_begin", "mcb_shard_partition", "mcb_shard_recv_buffer", "mcb_shard_set_tuples", "mcb_shard_packed",
     "mcb_shard_get_nreads", "mcb_shard_set_nreads", "mcb_bucket_round_a", "mcb_bucket_round_b", "mcb_bucket_finish",
-    "mcb_realign_begin", "mcb_realign_finish",
+    "mcb_realign_begin", "mcb_realign_finish", "mcb_realign_begin_keyed",
 ]
 
 
@@ -133,6 +133,8 @@ def load_library() -> C.CDLL:
     lib.mcb_realign_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                       C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.mcb_realign_finish.argtypes = [C.c_void_p, C.POINTER(_RealignResult)]
+    lib.mcb_realign_begin_keyed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                            C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 
@@ -422,6 +424,20 @@ class Context:
             self._check(self.lib.mcb_realign_begin(self._h, sg.ctypes.data, len(sg), refs.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1,
                                                    window_base, threshold, maxsearch, ininumdict, C.byref(p)))
         return int(p.value or 0)
+
+    def realign_begin_keyed(self, sg, refs, ref_off, tab_rank, tab_ranks, g_lo, g_hi, threshold, maxsearch, ininumdict=0):
+        """(device pointer of the claim priorities, upper bound of this rank's largest dictionary bin)"""
+        sg = np.ascontiguousarray(sg, dtype=np.uint32)
+        p, mb = C.c_void_p(0), C.c_uint64(0)
+        if refs is None:
+            self._check(self.lib.mcb_realign_begin_keyed(self._h, sg.ctypes.data, len(sg), None, None, 0, tab_rank, tab_ranks, g_lo, g_hi,
+                                                         threshold, maxsearch, ininumdict, C.byref(p), C.byref(mb)))
+        else:
+            refs = np.ascontiguousarray(refs, dtype=np.uint8)
+            ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
+            self._check(self.lib.mcb_realign_begin_keyed(self._h, sg.ctypes.data, len(sg), refs.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1,
+                                                         tab_rank, tab_ranks, g_lo, g_hi, threshold, maxsearch, ininumdict, C.byref(p), C.byref(mb)))
+        return int(p.value or 0), int(mb.value)
 
     def realign_finish(self) -> RealignResult:
         r = _RealignResult()

@@ -152,6 +152,8 @@ struct McbContigIndex {
 	bool valid = false;
 	uint64_t n_contigs = 0, ref_bytes = 0, total_words = 0, n_windows = 0, n_entries = 0;
 	int L = 0, lt = 0, pbits = 0;
+	int tab_rank = 0, tab_ranks = 1;   // which share of the lt-mer table this context holds (key-sharded Stage 2), else 0 of 1
+	uint32_t b_lo = 0, b_hi = 0;         // table buckets [b_lo, b_hi) of the 2^pbits
 	DBuf refs;      // ASCII consensus strings, concatenated (kept to recognise an identical contig set)
 	DBuf roff;      // u64[n_contigs+1] offsets into refs
 	DBuf cwo;       // u64[n_contigs+1] word offsets of the packed contigs
@@ -181,6 +183,7 @@ struct McbBucketState {
 struct McbRealignState {
 	bool pending = false;
 	uint64_t S = 0, window_base = 0;
+	uint64_t g_lo = 0, g_hi = 0, g_sub = 0;   // claims of windows [g_lo, g_hi) are emitted here; g_sub = window index of this context's first contig
 	int nd = 0;
 };
 
@@ -320,7 +323,7 @@ MCB_HD uint32_t mcb_kmer_bucket(uint64_t key, int pbits) { return (uint32_t)((ke
 struct McbSortPass { int word; int shift; int bits; };  // word 0 = .x, 1 = .y
 int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const McbSortPass *passes, int n_passes,
                    ulonglong2 **sorted_out);
-int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long *b, uint64_t n, int pbits, unsigned long long **sorted_out);
+int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long *b, uint64_t n, int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long **sorted_out);
 int mcb_add_bit_passes(std::vector<McbSortPass> &v, int word, int lo, int hi);  // digits covering bits [lo,hi)
 int mcb_exclusive_scan_u32(mcb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *d_total /* device u64, may be null */);
 int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t *d_total);

@@ -23,8 +23,8 @@ struct DigitPair {
 	__device__ __forceinline__ unsigned operator()(const ulonglong2 &e) const { unsigned long long v = word ? e.y : e.x; return (unsigned)(v >> shift) & mask; }
 };
 struct DigitKmer {
-	int pbits, shift; unsigned mask;
-	__device__ __forceinline__ unsigned operator()(const unsigned long long &e) const { return (mcb_kmer_bucket(e >> MCB_S2_POS_BITS, pbits) >> shift) & mask; }
+	int pbits, shift; unsigned mask, b_lo;
+	__device__ __forceinline__ unsigned operator()(const unsigned long long &e) const { return ((mcb_kmer_bucket(e >> MCB_S2_POS_BITS, pbits) - b_lo) >> shift) & mask; }
 };
 
 template <class E, class D>
@@ -267,7 +267,7 @@ int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const
 }
 
 // Stage-2 contig table: order the 8-byte entries by the `pbits`-bit bucket hash of their lt-mer (order inside a bucket is free)
-int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long *b, uint64_t n, int pbits, unsigned long long **sorted_out)
+int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long *b, uint64_t n, int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long **sorted_out)
 {
 	*sorted_out = a;
 	if (n <= 1) return MCB_OK;
@@ -276,10 +276,11 @@ int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long
 	MCB_TRY(ctx->d_sort_hist.ensure((nb + 1) * 256 * sizeof(uint32_t)));
 	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>(), *rowsum = hist + nb * 256;
 	unsigned long long *src = a, *dst = b;
-	const int n_passes = (pbits + 7) / 8;
+	const int kbits = mcb_bits_for(b_hi - b_lo > 1 ? b_hi - b_lo - 1 : 1);            // bits of (bucket - b_lo)
+	const int n_passes = (kbits + 7) / 8;
 	for (int p = 0, lo = 0; p < n_passes; ++p) {
-		const int bits = (pbits - lo + (n_passes - p) - 1) / (n_passes - p);      // spread the bits evenly over the passes
-		DigitKmer dg = { pbits, lo, (1u << bits) - 1u };
+		const int bits = (kbits - lo + (n_passes - p) - 1) / (n_passes - p);      // spread the bits evenly over the passes
+		DigitKmer dg = { pbits, lo, (1u << bits) - 1u, b_lo };
 		MCB_LAUNCH(ctx, "s2_kmer_sort_hist", (k_sort_hist<unsigned long long, DigitKmer>), (unsigned)nb, SORT_THREADS, 0, src, n, dg, hist, (unsigned)nb);
 		MCB_LAUNCH(ctx, "sort_rowscan", k_sort_rowscan, 256, SORT_THREADS, 0, hist, (unsigned)nb, rowsum);
 		MCB_LAUNCH(ctx, "s2_kmer_sort_scatter", (k_sort_scatter<unsigned long long, DigitKmer>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb, rowsum);

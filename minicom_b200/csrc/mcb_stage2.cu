@@ -132,7 +132,8 @@ __global__ void k_s2_same(const uint64_t *__restrict__ a, const uint64_t *__rest
 // starts at base j of the word, so every store instruction covers 32 consecutive entries.
 __global__ void __launch_bounds__(256)
 k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_off, const uint64_t *__restrict__ ref_off, const uint64_t *__restrict__ ent_off,
-               uint64_t n_contigs, uint64_t total_words, int L, int lt, unsigned long long *__restrict__ ents)
+               uint64_t n_contigs, uint64_t total_words, int L, int lt, unsigned long long *__restrict__ ents,
+               int filter, int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long *__restrict__ counter, unsigned long long ents_cap)
 {
 	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
@@ -154,19 +155,30 @@ k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_
 		if (cnt == 0) continue;
 		const uint64_t a = __shfl_sync(0xFFFFFFFFu, w0, t), b = __shfl_sync(0xFFFFFFFFu, w1, t);
 		const uint64_t d = __shfl_sync(0xFFFFFFFFu, dst, t), p = __shfl_sync(0xFFFFFFFFu, pos0, t);
-		if (lane < cnt) {
-			const uint64_t key = ((a >> (2 * lane)) | (lane ? b << (64 - 2 * lane) : 0ull)) & kmask;
-			ents[d + lane] = (key << S2_POS_BITS) | (p + lane);
+		const uint64_t key = ((a >> (2 * lane)) | (lane ? b << (64 - 2 * lane) : 0ull)) & kmask;
+		if (!filter) {
+			if (lane < cnt) ents[d + lane] = (key << S2_POS_BITS) | (p + lane);
+		} else {       // key-sharded table: keep the lt-mers whose bucket this context owns, packed in arrival order
+			const uint32_t bk = kmer_bucket(key, pbits);
+			const bool own = lane < cnt && bk >= b_lo && bk < b_hi;
+			const unsigned bal = __ballot_sync(0xFFFFFFFFu, own);
+			if (bal) {
+				unsigned long long base = 0;
+				if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(bal));
+				base = __shfl_sync(0xFFFFFFFFu, base, 0);
+				const unsigned long long at = base + __popc(bal & ((1u << lane) - 1u));
+				if (own && at < ents_cap) ents[at] = (key << S2_POS_BITS) | (p + lane);
+			}
 		}
 	}
 }
 // entries are ordered by bucket: ptab[b] = end of bucket b (= start of bucket b+1)
-__global__ void k_s2_bucket_ends(const unsigned long long *__restrict__ ents, uint64_t n, int pbits, uint32_t *__restrict__ ptab)
+__global__ void k_s2_bucket_ends(const unsigned long long *__restrict__ ents, uint64_t n, int pbits, uint32_t b_lo, uint32_t b_hi, uint32_t *__restrict__ ptab)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	const uint32_t b = kmer_bucket(ents[i] >> S2_POS_BITS, pbits);
-	const uint32_t bn = i + 1 < n ? kmer_bucket(ents[i + 1] >> S2_POS_BITS, pbits) : (1u << pbits);
+	const uint32_t b = kmer_bucket(ents[i] >> S2_POS_BITS, pbits) - b_lo;
+	const uint32_t bn = i + 1 < n ? kmer_bucket(ents[i + 1] >> S2_POS_BITS, pbits) - b_lo : b_hi - b_lo;
 	if (i == 0) for (uint32_t q = 0; q < b; ++q) ptab[q] = 0;
 	for (uint32_t q = b; q < bn; ++q) ptab[q] = (uint32_t)(i + 1);
 }
@@ -175,7 +187,7 @@ __global__ void k_s2_bucket_ends(const unsigned long long *__restrict__ ents, ui
 __global__ void k_s2_singles(const uint32_t *__restrict__ sg, uint64_t S, const uint64_t *__restrict__ packed, S2Geom gm,
                              const uint32_t *__restrict__ nread_rid, const uint64_t *__restrict__ nread_mask, uint64_t n_nreads, uint64_t n_reads,
                              uint64_t *__restrict__ rd, uint8_t *__restrict__ flagged, uint32_t *__restrict__ cm, uint64_t cm_mask,
-                             unsigned long long *__restrict__ counters)
+                             int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long *__restrict__ counters)
 {
 	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned maxbin = 0;
@@ -216,7 +228,10 @@ __global__ void k_s2_singles(const uint32_t *__restrict__ sg, uint64_t S, const 
 			flagged[s] = fl;
 			// count-min sketch of the dictionary bins: an upper bound of every bin size (a bin = singles sharing a key in dictionary l)
 			for (int l = 0; l < gm.nd; ++l) {
-				unsigned long long key = ((unsigned long long)l << 34) | extract_bases(w, gm.dstart[l], gm.lt);
+				const uint64_t k0 = extract_bases(w, gm.dstart[l], gm.lt);
+				const uint32_t bg = kmer_bucket(k0, pbits);
+				if (bg < b_lo || bg >= b_hi) continue;                 // key-sharded: the owner of the lt-mer counts the bin
+				unsigned long long key = ((unsigned long long)l << 34) | k0;
 				unsigned v = atomicAdd(&cm[mix64(key) & cm_mask], 1u) + 1u;
 				maxbin = max(maxbin, v);
 			}
@@ -282,7 +297,7 @@ __global__ void k_s2_apply_claims(const unsigned long long *__restrict__ pairs, 
 struct S2Join {
 	uint64_t S;
 	const uint64_t *rd; const uint8_t *flagged;
-	const uint32_t *ptab; const unsigned long long *ents; int pbits;
+	const uint32_t *ptab; const unsigned long long *ents; int pbits; uint32_t b_lo, b_hi;   // this context's share of the table
 	const uint32_t *pblk; const S2ContigMeta *meta; const uint64_t *cw;
 	unsigned long long *claim;            // [S] min priority
 	unsigned long long window_base;       // windows on lower ranks (0 on a single GPU)
@@ -327,9 +342,12 @@ __global__ void __launch_bounds__(256) k_s2_probe_table(S2Join p, S2Geom gm, uns
 #pragma unroll
 			for (int phase = 0; phase < 2; ++phase) {
 				if (phase < nphase) {
-					const uint32_t b = kmer_bucket(key2[phase], p.pbits);
-					lo2[phase] = b ? p.ptab[b - 1] : 0u;
-					hi2[phase] = p.ptab[b];
+					const uint32_t bg = kmer_bucket(key2[phase], p.pbits);
+					if (bg >= p.b_lo && bg < p.b_hi) {           // key-sharded: other ranks look up the other lt-mers
+						const uint32_t b = bg - p.b_lo;
+						lo2[phase] = b ? p.ptab[b - 1] : 0u;
+						hi2[phase] = p.ptab[b];
+					}
 				}
 			}
 		}
@@ -467,14 +485,14 @@ __global__ void k_s2_claim_flags(const unsigned long long *__restrict__ claim, c
 	if (s >= S) return;
 	f_claim[s] = claim_mine(claim[s], g_lo, g_hi); f_a[s] = flagged[s] == 1; f_t[s] = flagged[s] == 2;
 }
-__global__ void k_s2_claim_compact(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S, uint64_t g_lo, uint64_t g_hi,
+__global__ void k_s2_claim_compact(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S, uint64_t g_lo, uint64_t g_hi, uint64_t g_sub,
                                    const uint32_t *__restrict__ p_claim, const uint32_t *__restrict__ p_a, const uint32_t *__restrict__ p_t,
                                    ulonglong2 *__restrict__ el, uint32_t *__restrict__ fpa, uint32_t *__restrict__ fpt)
 {
 	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= S) return;
 	unsigned long long c = claim[s];
-	if (claim_mine(c, g_lo, g_hi)) { ulonglong2 e; e.x = c - (g_lo << 5); e.y = 0xFFFFFFFFull - s; el[p_claim[s]] = e; }   // local window index; ascending y == descending sg index
+	if (claim_mine(c, g_lo, g_hi)) { ulonglong2 e; e.x = c - (g_sub << 5); e.y = 0xFFFFFFFFull - s; el[p_claim[s]] = e; }   // local window index; ascending y == descending sg index
 	if (flagged[s] == 1) fpa[p_a[s]] = (uint32_t)s;
 	if (flagged[s] == 2) fpt[p_t[s]] = (uint32_t)s;
 }
@@ -494,7 +512,7 @@ __global__ void k_s2_claim_emit(const ulonglong2 *__restrict__ el, uint64_t n, c
 
 // ================================================================= host
 // Upload the contigs and (re)build the lt-mer table unless the cached one was built from identical contigs.
-static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int lt)
+static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int lt, int tab_rank, int tab_ranks)
 {
 	McbContigIndex &cx = ctx->cix;
 	const int L = ctx->L;
@@ -516,7 +534,7 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	cwo[n_contigs] = total_words + 1; wo[n_contigs] = n_windows; eo[n_contigs] = n_entries;   // +1 guard word: loaders read one word ahead
 	if (n_windows >= (1ull << 58)) { mcb_set_error("too many windows"); return MCB_EINVAL; }
 	// ---- same contigs as last time?  (compare on the device: the strings have to be uploaded to find out)
-	const bool maybe_same = cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L;
+	const bool maybe_same = cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L && cx.tab_rank == tab_rank && cx.tab_ranks == tab_ranks;
 	DBuf &stage_refs = maybe_same ? ctx->d_scr[1] : cx.refs, &stage_off = maybe_same ? ctx->d_scr[2] : cx.roff;
 	const size_t refs_pad = (ref_bytes + 7) & ~(size_t)7;
 	MCB_TRY(stage_refs.ensure(refs_pad + 16)); MCB_TRY(stage_off.ensure((n_contigs + 1) * 8));
@@ -540,11 +558,15 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	}
 	// ---- build
 	cx.n_contigs = n_contigs; cx.ref_bytes = ref_bytes; cx.total_words = total_words; cx.n_windows = n_windows; cx.n_entries = n_entries; cx.L = L; cx.lt = lt;
-	int pbits = 10; while (pbits < 26 && pbits < 2 * lt && (4ull << pbits) < n_entries) ++pbits;                 // 2..4 entries per bucket
-	cx.pbits = pbits;
-	const uint64_t nbk = 1ull << pbits, n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
+	int pcap = 26; for (int q = 1; q < tab_ranks; q <<= 1) ++pcap;                                               // the bucket space is shared by all ranks
+	int pbits = 10; while (pbits < pcap && pbits < 2 * lt && pbits < 31 && (4ull << pbits) < n_entries) ++pbits;   // 2..4 entries per bucket
+	cx.pbits = pbits; cx.tab_rank = tab_rank; cx.tab_ranks = tab_ranks;
+	cx.b_lo = (uint32_t)((((uint64_t)tab_rank << pbits) + tab_ranks - 1) / tab_ranks);                            // owner(b) = b * ranks >> pbits
+	cx.b_hi = (uint32_t)((((uint64_t)(tab_rank + 1) << pbits) + tab_ranks - 1) / tab_ranks);
+	const uint64_t nbk = cx.b_hi - cx.b_lo, n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
+	const uint64_t ents_cap = tab_ranks > 1 ? n_entries / tab_ranks + n_entries / (4 * tab_ranks) + (1u << 20) : n_entries;   // hashed lt-mers spread evenly; checked below
 	MCB_TRY(cx.cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.wo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.cw.ensure((total_words + 2) * 8));
-	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16)); MCB_TRY(cx.ptab.ensure((nbk + 1) * 4)); MCB_TRY(cx.ents.ensure(n_entries * 8 + 16)); MCB_TRY(cx.ents2.ensure(n_entries * 8 + 16));
+	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16)); MCB_TRY(cx.ptab.ensure((nbk + 1) * 4)); MCB_TRY(cx.ents.ensure(ents_cap * 8 + 16)); MCB_TRY(cx.ents2.ensure(ents_cap * 8 + 16));
 	MCB_TRY(cx.eoff.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.meta.ensure((n_contigs + 2) * 32));
 	{
 		McbSpan sp(ctx->tm, "h2d");
@@ -560,11 +582,20 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	MCB_LAUNCH(ctx, "s2_pack_refs", k_s2_pack_refs, mcb_grid_for(total_words, 256), 256, 0, cx.refs.as<char>(), cx.roff.as<uint64_t>(), cx.cwo.as<uint64_t>(),
 	           n_contigs, total_words, cx.cw.as<uint64_t>(), dc);
 	MCB_LAUNCH(ctx, "s2_pos_blocks", k_s2_pos_blocks, mcb_grid_for(n_blocks, 256), 256, 0, cx.roff.as<uint64_t>(), n_contigs, n_blocks, cx.pblk.as<uint32_t>());
+	uint64_t n_own = n_entries;
+	if (tab_ranks > 1) MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NCAND], 0, 8, ctx->stream));
 	MCB_LAUNCH(ctx, "s2_kmer_emit", k_s2_kmer_emit, mcb_grid_for(total_words, 256), 256, 0, cx.cw.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.roff.as<uint64_t>(),
-	           cx.eoff.as<uint64_t>(), n_contigs, total_words, L, lt, cx.ents.as<unsigned long long>());
-	MCB_TRY(mcb_radix_sort_kmers(ctx, cx.ents.as<unsigned long long>(), cx.ents2.as<unsigned long long>(), n_entries, pbits, &cx.ents_sorted));
+	           cx.eoff.as<uint64_t>(), n_contigs, total_words, L, lt, cx.ents.as<unsigned long long>(), tab_ranks > 1 ? 1 : 0, pbits, cx.b_lo, cx.b_hi, &dc[CT_S2_NCAND], (unsigned long long)ents_cap);
+	if (tab_ranks > 1) {
+		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		n_own = ctx->h_counters.as<unsigned long long>()[CT_S2_NCAND];
+		if (n_own > ents_cap) { mcb_set_error("mcb_realign: this rank's share of the lt-mer table (%llu entries) exceeds the reserved %llu", (unsigned long long)n_own, (unsigned long long)ents_cap); return MCB_EINVAL; }
+		cx.n_entries = n_own;
+	}
+	MCB_TRY(mcb_radix_sort_kmers(ctx, cx.ents.as<unsigned long long>(), cx.ents2.as<unsigned long long>(), n_own, pbits, cx.b_lo, cx.b_hi, &cx.ents_sorted));
 	MCB_CUDA(cudaMemsetAsync(cx.ptab.p, 0, (nbk + 1) * 4, ctx->stream));
-	if (n_entries) MCB_LAUNCH(ctx, "s2_bucket_ends", k_s2_bucket_ends, mcb_grid_for(n_entries, 256), 256, 0, cx.ents_sorted, n_entries, pbits, cx.ptab.as<uint32_t>());
+	if (n_own) MCB_LAUNCH(ctx, "s2_bucket_ends", k_s2_bucket_ends, mcb_grid_for(n_own, 256), 256, 0, cx.ents_sorted, n_own, pbits, cx.b_lo, cx.b_hi, cx.ptab.as<uint32_t>());
 	cx.valid = true;
 	return MCB_OK;
 }
@@ -684,8 +715,11 @@ static int realign_exact_bins(mcb_ctx *ctx, S2Join jn, const S2Geom &gm, uint64_
 }
 
 // first half: contigs, singles, join.  Leaves the claim priorities in ctx->d_x[0] (u64[S]).
+// contig-range sharding: this context holds contigs whose first window is `window_base`, the whole table, and emits all its claims.
+// key sharding (tab_ranks > 1): this context holds ALL contigs, share tab_rank of the table, and emits the claims of windows [g_lo, g_hi).
 static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
-                          uint64_t window_base, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
+                          uint64_t window_base, int tab_rank, int tab_ranks, uint64_t g_lo, uint64_t g_hi,
+                          int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
 {
 	if (!ctx->reads_loaded) { mcb_set_error("mcb_realign: no reads loaded"); return MCB_ESTATE; }
 	if (S && !sg) { mcb_set_error("mcb_realign: null input"); return MCB_EINVAL; }
@@ -703,9 +737,9 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	McbContigIndex &cx = ctx->cix;
 	if (refs || ref_off) {
 		if (n_contigs && (!refs || !ref_off)) { mcb_set_error("mcb_realign: refs and ref_off must be given together"); return MCB_EINVAL; }
-		MCB_TRY(contig_index_update(ctx, refs, ref_off, n_contigs, gm.lt));
+		MCB_TRY(contig_index_update(ctx, refs, ref_off, n_contigs, gm.lt, tab_rank, tab_ranks));
 	} else {
-		if (!cx.valid || cx.L != L || cx.lt != gm.lt) { mcb_set_error("mcb_realign: refs == NULL but no contigs from a previous call are cached"); return MCB_ESTATE; }
+		if (!cx.valid || cx.L != L || cx.lt != gm.lt || cx.tab_rank != tab_rank || cx.tab_ranks != tab_ranks) { mcb_set_error("mcb_realign: refs == NULL but no contigs from a previous call are cached"); return MCB_ESTATE; }
 		if (n_contigs && n_contigs != cx.n_contigs) { mcb_set_error("mcb_realign: refs == NULL with a different contig count (%llu, cached %llu)", (unsigned long long)n_contigs, (unsigned long long)cx.n_contigs); return MCB_EINVAL; }
 	}
 	const uint64_t n_windows = cx.n_windows;
@@ -717,6 +751,8 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	}
 	const uint64_t nkv = S * (uint64_t)gm.nd;
 	ctx->rs.pending = true; ctx->rs.S = S; ctx->rs.window_base = window_base; ctx->rs.nd = gm.nd;
+	if (tab_ranks > 1) { ctx->rs.g_lo = g_lo; ctx->rs.g_hi = g_hi; ctx->rs.g_sub = 0; }
+	else { ctx->rs.g_lo = window_base; ctx->rs.g_hi = window_base + n_windows; ctx->rs.g_sub = window_base; }
 	MCB_TRY(ctx->d_x[0].ensure(S * 8 + 16));                   // claim priorities
 	unsigned long long *claim = ctx->d_x[0].as<unsigned long long>();
 	if (S) MCB_CUDA(cudaMemsetAsync(claim, 0x7F, S * 8, ctx->stream));          // MCB_CLAIM_NONE
@@ -734,7 +770,7 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	MCB_CUDA(cudaMemsetAsync(b_cm.p, 0, CM * 4, ctx->stream));
 	MCB_LAUNCH(ctx, "s2_singles", k_s2_singles, mcb_grid_for(S, 128), 128, 0, b_sg.as<uint32_t>(), S, ctx->d_packed.as<uint64_t>(), gm,
 	           ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->n_nreads, ctx->n_reads,
-	           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, dc);
+	           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, cx.pbits, cx.b_lo, cx.b_hi, dc);
 	if (n_windows == 0) {          // no contig long enough on this rank: the diversion lists are still needed
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -742,7 +778,7 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 		return MCB_OK;
 	}
 	S2Join jn; memset(&jn, 0, sizeof jn);
-	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents_sorted; jn.pbits = cx.pbits;
+	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents_sorted; jn.pbits = cx.pbits; jn.b_lo = cx.b_lo; jn.b_hi = cx.b_hi;
 	jn.pblk = cx.pblk.as<uint32_t>(); jn.meta = cx.meta.as<S2ContigMeta>(); jn.cw = cx.cw.as<uint64_t>();
 	jn.claim = claim; jn.window_base = window_base; jn.counters = dc;
 	// candidate list: sized from the previous call's count, grown (and the probe repeated) when it overflows
@@ -769,7 +805,7 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 		if (attempt == 1) {
 			// Some verified match lies in a bin larger than maxsearch: the reference's scan of "the last maxsearch live entries"
 			// (kthread_hash_realign.c:388) depends on which reads were already claimed.  Replay exactly those singles in order.
-			if (ctx->shard_n > 1 || window_base) {
+			if (ctx->shard_n > 1 || window_base || tab_ranks > 1) {
 				mcb_set_error("mcb_realign: %llu matches fall into dictionary bins with more than maxsearch=%d singles; the sequential bin-window "
 				              "replay is not available when the contigs are sharded", hc[CT_S2_NEEDEXACT], maxsearch);
 				return MCB_EINPUT;
@@ -798,7 +834,7 @@ static int realign_claims(mcb_ctx *ctx, mcb_realign_result *res)
 {
 	if (!ctx->rs.pending) { mcb_set_error("mcb_realign_finish: no search pending"); return MCB_ESTATE; }
 	ctx->rs.pending = false;
-	const uint64_t S = ctx->rs.S, window_base = ctx->rs.window_base;
+	const uint64_t S = ctx->rs.S, g_lo = ctx->rs.g_lo, g_hi = ctx->rs.g_hi, g_sub = ctx->rs.g_sub;
 	McbContigIndex &cx = ctx->cix;
 	const uint64_t n_windows = cx.n_windows, n_contigs = cx.n_contigs;
 	if (S == 0 || ctx->rs.nd == 0) return MCB_OK;
@@ -812,11 +848,11 @@ static int realign_claims(mcb_ctx *ctx, mcb_realign_result *res)
 	ulonglong2 *elA = b_elA.as<ulonglong2>(), *elB = b_elB.as<ulonglong2>();
 	uint32_t *d_fpa = b_fp.as<uint32_t>(), *d_fpt = d_fpa + S;
 	const int span_h = ctx->tm.begin("realign");
-	MCB_LAUNCH(ctx, "s2_claim_flags", k_s2_claim_flags, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, window_base, window_base + n_windows, f_c, f_a, f_t);
+	MCB_LAUNCH(ctx, "s2_claim_flags", k_s2_claim_flags, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, g_lo, g_hi, f_c, f_a, f_t);
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_c, S, (uint64_t*)&dc[CT_S2_CLAIMS]));
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_a, S, (uint64_t*)&dc[CT_S2_FPA]));
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_t, S, (uint64_t*)&dc[CT_S2_FPT]));
-	MCB_LAUNCH(ctx, "s2_claim_compact", k_s2_claim_compact, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, window_base, window_base + n_windows, f_c, f_a, f_t, elA, d_fpa, d_fpt);
+	MCB_LAUNCH(ctx, "s2_claim_compact", k_s2_claim_compact, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, g_lo, g_hi, g_sub, f_c, f_a, f_t, elA, d_fpa, d_fpt);
 	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	const uint64_t ncl = hc[CT_S2_CLAIMS], nfa = hc[CT_S2_FPA], nft = hc[CT_S2_FPT];
@@ -855,7 +891,7 @@ extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const c
 {
 	if (!ctx || !res) { mcb_set_error("mcb_realign: null argument"); return MCB_EINVAL; }
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, 0, threshold, maxsearch, ininumdict, res));
+	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, 0, 0, 1, 0, 0, threshold, maxsearch, ininumdict, res));
 	return realign_claims(ctx, res);
 }
 
@@ -864,7 +900,7 @@ extern "C" int mcb_realign_begin(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, c
 {
 	if (!ctx || !d_claim) { mcb_set_error("mcb_realign_begin: null argument"); return MCB_EINVAL; }
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, window_base, threshold, maxsearch, ininumdict, &g_pending_result));
+	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, window_base, 0, 1, 0, 0, threshold, maxsearch, ininumdict, &g_pending_result));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));        // the caller reduces the array on its own stream
 	*d_claim = ctx->d_x[0].p;
 	return MCB_OK;
@@ -876,4 +912,22 @@ extern "C" int mcb_realign_finish(mcb_ctx *ctx, mcb_realign_result *res)
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
 	*res = g_pending_result;
 	return realign_claims(ctx, res);
+}
+
+// Key-sharded Stage 2: every rank is given ALL contigs and ALL singles, keeps the share `tab_rank` of `tab_ranks`
+// of the lt-mer table (buckets by hash range), probes only the lt-mers it owns, and emits the claims of windows [g_lo, g_hi)
+// after the caller has min-reduced the priorities.  *maxbin_upper = upper bound of this rank's largest dictionary bin (the caller
+// takes the maximum over the ranks; a value above maxsearch means the sequential bin-window replay would be needed).
+extern "C" int mcb_realign_begin_keyed(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
+                                       int tab_rank, int tab_ranks, uint64_t g_lo, uint64_t g_hi, int threshold, int maxsearch, int ininumdict,
+                                       void **d_claim, uint64_t *maxbin_upper)
+{
+	if (!ctx || !d_claim) { mcb_set_error("mcb_realign_begin_keyed: null argument"); return MCB_EINVAL; }
+	if (tab_ranks < 1 || tab_ranks > 255 || tab_rank < 0 || tab_rank >= tab_ranks || g_hi < g_lo) { mcb_set_error("mcb_realign_begin_keyed: bad arguments"); return MCB_EINVAL; }
+	MCB_CUDA(cudaSetDevice(ctx->prm.device));
+	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, 0, tab_rank, tab_ranks, g_lo, g_hi, threshold, maxsearch, ininumdict, &g_pending_result));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	*d_claim = ctx->d_x[0].p;
+	if (maxbin_upper) *maxbin_upper = ctx->h_counters.as<unsigned long long>()[CT_S2_MAXBIN];
+	return MCB_OK;
 }

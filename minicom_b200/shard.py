@@ -10,7 +10,9 @@ Exchanges:
   Stage 1    all-gather of the 2-bit packed reads (any rank builds the consensus of its groups from any read);
              per round an all-to-all of the 16-byte (minimizer, read, position, strand) tuples by bucket owner;
              an all-gather of two counters per round (new seed contigs for the global contig ids, members for the loop control)
-  Stage 2    singles replicated, contigs partitioned; one all-reduce(MIN) of the per-single claim priorities per threshold round
+  Stage 2    contigs and singles on every rank; the contig lt-mer table partitioned by hash range (each rank probes only the
+             lt-mers it owns, so probes per rank stay constant); one all-reduce(MIN) of the per-single claim priorities per
+             threshold round; claims emitted by window range
 Concatenating the ranks' results in rank order — round by round for Stage 1 — reproduces the single-GPU (= single-threaded
 reference) order exactly; `merge_stage1` / `merge_claims` do that on one host for the callers that stay on one host (contig merge).
 
@@ -108,9 +110,11 @@ def merge_stage1(parts: list[Stage1Part]) -> Stage1Part:
                       cat("mi", p0.mi), cat("mi_cnt", p0.mi_cnt), rounds)
 
 
-def merge_claims(parts: list[tuple[np.ndarray, np.ndarray, np.ndarray]], contig_cuts: np.ndarray):
-    """Per-rank (claim_contig local, claim_sg, claim_y) -> global lists in the reference's append order."""
-    cc = [p[0].astype(np.int64) + int(contig_cuts[r]) for r, p in enumerate(parts)]
+def merge_claims(parts: list[tuple[np.ndarray, np.ndarray, np.ndarray]], contig_cuts: np.ndarray | None = None):
+    """Per-rank (claim_contig, claim_sg, claim_y) -> global lists in the reference's append order (rank order = window order).
+    contig_cuts: first contig of every rank when the contig indices are rank-local (contig-range sharding); None when they are
+    global already (key sharding)."""
+    cc = [p[0].astype(np.int64) + (int(contig_cuts[r]) if contig_cuts is not None else 0) for r, p in enumerate(parts)]
     return np.concatenate(cc).astype(np.uint32), np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts])
 
 
@@ -230,19 +234,25 @@ class ShardedFrontEnd:
         br, rounds = ctx.bucket_finish()
         return rr, Stage1Part(br.cl_n, br.cl_a, br.cl_ref, np.diff(br.cl_ref_off.astype(np.int64)).astype(np.uint64), br.sg, br.mi, br.mi_cnt, rounds)
 
-    # ---- Stage 2: one threshold round of realign_hash, contigs partitioned
-    def realign(self, sg, refs_local, off_local, window_base: int, threshold: int, maxsearch: int, ininumdict: int = 0):
-        """refs_local/off_local: this rank's contiguous range of the contigs (None/None: same as the previous round)."""
+    # ---- Stage 2: one threshold round of realign_hash
+    def realign(self, sg, refs, ref_off, g_lo: int, g_hi: int, threshold: int, maxsearch: int, ininumdict: int = 0):
+        """Key-sharded: every rank passes ALL contigs (refs/ref_off; None/None = same as the previous round) and all singles,
+        holds its hash range of the contig lt-mer table and probes only the lt-mers it owns; the claim priorities are
+        min-reduced; this rank then emits the claims of windows [g_lo, g_hi) (contig_partition gives the ranges) with global
+        contig indices."""
         torch, dist, ctx = self.torch, self.dist, self.ctx
-        err, ptr = None, 0
+        err, ptr, maxbin = None, 0, 0
         try:
-            ptr = ctx.realign_begin(sg, refs_local, off_local, window_base, threshold, maxsearch, ininumdict)
+            ptr, maxbin = ctx.realign_begin_keyed(sg, refs, ref_off, self.rank, self.world, g_lo, g_hi, threshold, maxsearch, ininumdict)
         except Exception as e:      # every rank has to reach the collective
             err = e
-        flag = torch.tensor([1 if err else 0], dtype=torch.int64, device=self.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if int(flag.item()):
-            raise err or RuntimeError("mcb_realign_begin failed on another rank")
+        flag = torch.tensor([1 if err else 0, maxbin], dtype=torch.int64, device=self.device)
+        self._coll(dist.all_reduce, flag, op=dist.ReduceOp.MAX)
+        bad, gmax = (int(x) for x in flag.cpu())
+        if bad:
+            raise err or RuntimeError("mcb_realign_begin_keyed failed on another rank")
+        if gmax > maxsearch:
+            raise RuntimeError(f"a dictionary bin may hold {gmax} singles (> maxsearch={maxsearch}): the sequential bin-window replay is single-GPU only")
         claim = dev_view(ptr, len(sg) * 8, self.device).view(torch.int64)
         if len(sg):
             self._coll(dist.all_reduce, claim, op=dist.ReduceOp.MIN)

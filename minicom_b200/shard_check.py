@@ -94,16 +94,16 @@ def main():
     # ---- Stage 2 over the seed contigs (no host merge in this check), three threshold rounds
     ref_off = np.concatenate([[0], np.cumsum(merged.cl_reflen.astype(np.int64))]).astype(np.uint64)
     cuts, wbase = shard.contig_partition(ref_off, world, L)
-    c0, c1 = int(cuts[rank]), int(cuts[rank + 1])
-    refs_local = merged.cl_ref[int(ref_off[c0]):int(ref_off[c1])]
-    off_local = ref_off[c0:c1 + 1] - ref_off[c0]
+    lens = np.diff(ref_off.astype(np.int64))
+    n_win = int(np.where(lens >= L, lens - L + 1, 0).sum())
+    g_lo = int(wbase[rank]); g_hi = int(wbase[rank + 1]) if rank + 1 < world else n_win
     sg = merged.sg.copy()
     e = ctx.params.diff_threshold
     for rnd, thr in enumerate((e, 2 * e, 3 * e)):
-        r = fe.realign(sg, refs_local if rnd == 0 else None, off_local if rnd == 0 else None, int(wbase[rank]), thr, 2000)
+        r = fe.realign(sg, merged.cl_ref if rnd == 0 else None, ref_off if rnd == 0 else None, g_lo, g_hi, thr, 2000)
         cl = [None] * world
         dist.all_gather_object(cl, (r.claim_contig, r.claim_sg, r.claim_y))
-        gc, gs, gy = shard.merge_claims(cl, cuts)
+        gc, gs, gy = shard.merge_claims(cl)
         if rank == 0:
             w = single.realign(sg, merged.cl_ref if rnd == 0 else None, ref_off if rnd == 0 else None, thr, 2000)
             check(f"claims thr {thr}: y", gy, w.claim_y)
