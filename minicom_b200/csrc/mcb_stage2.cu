@@ -150,25 +150,42 @@ k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_
 		}
 	}
 	const uint64_t kmask = (1ull << (2 * lt)) - 1;
-	for (int t = 0; t < 32; ++t) {
-		const int cnt = __shfl_sync(0xFFFFFFFFu, nstart, t);
-		if (cnt == 0) continue;
-		const uint64_t a = __shfl_sync(0xFFFFFFFFu, w0, t), b = __shfl_sync(0xFFFFFFFFu, w1, t);
-		const uint64_t d = __shfl_sync(0xFFFFFFFFu, dst, t), p = __shfl_sync(0xFFFFFFFFu, pos0, t);
-		const uint64_t key = ((a >> (2 * lane)) | (lane ? b << (64 - 2 * lane) : 0ull)) & kmask;
-		if (!filter) {
-			if (lane < cnt) ents[d + lane] = (key << S2_POS_BITS) | (p + lane);
-		} else {       // key-sharded table: keep the lt-mers whose bucket this context owns, packed in arrival order
-			const uint32_t bk = kmer_bucket(key, pbits);
-			const bool own = lane < cnt && bk >= b_lo && bk < b_hi;
-			const unsigned bal = __ballot_sync(0xFFFFFFFFu, own);
-			if (bal) {
-				unsigned long long base = 0;
-				if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(bal));
-				base = __shfl_sync(0xFFFFFFFFu, base, 0);
-				const unsigned long long at = base + __popc(bal & ((1u << lane) - 1u));
-				if (own && at < ents_cap) ents[at] = (key << S2_POS_BITS) | (p + lane);
+	if (!filter) {
+		for (int t = 0; t < 32; ++t) {
+			const int cnt = __shfl_sync(0xFFFFFFFFu, nstart, t);
+			if (cnt == 0) continue;
+			const uint64_t a = __shfl_sync(0xFFFFFFFFu, w0, t), b = __shfl_sync(0xFFFFFFFFu, w1, t);
+			const uint64_t d = __shfl_sync(0xFFFFFFFFu, dst, t), p = __shfl_sync(0xFFFFFFFFu, pos0, t);
+			if (lane < cnt) {
+				const uint64_t key = ((a >> (2 * lane)) | (lane ? b << (64 - 2 * lane) : 0ull)) & kmask;
+				ents[d + lane] = (key << S2_POS_BITS) | (p + lane);
 			}
+		}
+		return;
+	}
+	// key-sharded table: keep the lt-mers whose bucket this context owns.  Each thread walks the 32 start positions of ITS word,
+	// the warp reserves room with one atomic, and the kept entries are written packed (their order is irrelevant: they are sorted next).
+	unsigned mine = 0;
+	for (int j = 0; j < nstart; ++j) {
+		const uint64_t key = ((w0 >> (2 * j)) | (j ? w1 << (64 - 2 * j) : 0ull)) & kmask;
+		const uint32_t bk = kmer_bucket(key, pbits);
+		mine += bk >= b_lo && bk < b_hi;
+	}
+	unsigned inc = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+	const unsigned total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+	if (total == 0) return;
+	unsigned long long base = 0;
+	if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
+	base = __shfl_sync(0xFFFFFFFFu, base, 0);
+	unsigned long long at = base + (inc - mine);
+	for (int j = 0; j < nstart; ++j) {
+		const uint64_t key = ((w0 >> (2 * j)) | (j ? w1 << (64 - 2 * j) : 0ull)) & kmask;
+		const uint32_t bk = kmer_bucket(key, pbits);
+		if (bk >= b_lo && bk < b_hi) {
+			if (at < ents_cap) ents[at] = (key << S2_POS_BITS) | (pos0 + j);
+			++at;
 		}
 	}
 }
