@@ -86,6 +86,7 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 	               &ctx->h_claim_c, &ctx->h_claim_s, &ctx->h_claim_y, &ctx->h_fpA, &ctx->h_fpT, &ctx->h_in0, &ctx->h_in1, &ctx->h_in2 };
 	for (auto b : hb) b->release();
 	cudaStreamDestroy(ctx->stream);
+	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	if (ctx->pool && ctx->pool->close()) delete ctx->pool;
 	delete ctx;
 }

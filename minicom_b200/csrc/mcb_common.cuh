@@ -189,7 +189,7 @@ struct McbRealignState {
 
 struct mcb_ctx {
 	mcb_params prm;
-	cudaStream_t stream = 0;
+	cudaStream_t stream = 0, copy_stream = 0;
 	int sm_count = 148;
 	McbTimers tm;
 	// geometry

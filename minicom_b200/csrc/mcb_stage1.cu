@@ -799,7 +799,9 @@ static int ensure_elems(mcb_ctx *ctx, uint64_t n, bool keep_cur)
 	return MCB_OK;
 }
 
-static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_reads_result *res)
+// h_rows != nullptr: page-locked host rows that still have to be copied to d_rows; the copy is cut into chunks on a second
+// stream and the pack/sketch kernel of a chunk runs while the next chunk is on the bus
+static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_reads_result *res, const char *h_rows = nullptr)
 {
 	const int L = ctx->L, Wd = ctx->Wd, WS = ctx->WS;
 	const int pbase = L + ctx->prm.max_rounds;
@@ -817,14 +819,40 @@ static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_r
 	MCB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64 * 8, ctx->stream));
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
 	unsigned long long *hc = nullptr;
-	{
+	const size_t smem = RD_THREADS * 9 * sizeof(uint64_t) + (((size_t)RD_THREADS * L + 15) & ~(size_t)15) + 16;
+	if (n && !h_rows) {
 		McbSpan sp(ctx->tm, "for_reads");
-		if (n) {
-			size_t smem = RD_THREADS * 9 * sizeof(uint64_t) + (((size_t)RD_THREADS * L + 15) & ~(size_t)15) + 16;
-			MCB_LAUNCH(ctx, "pack_classify_sketch", k_pack_classify_sketch, mcb_grid_for(n, RD_THREADS), RD_THREADS, smem,
-			           d_rows, n, rid_base, L, Wd, WS, ctx->prm.k, ctx->prm.diff_threshold, pbase,
-			           ctx->d_packed.as<uint64_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+		MCB_LAUNCH(ctx, "pack_classify_sketch", k_pack_classify_sketch, mcb_grid_for(n, RD_THREADS), RD_THREADS, smem,
+		           d_rows, n, rid_base, L, Wd, WS, ctx->prm.k, ctx->prm.diff_threshold, pbase,
+		           ctx->d_packed.as<uint64_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+	} else if (n) {
+		if (!ctx->copy_stream) MCB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+		const uint64_t CH = 1u << 20;                                   // reads per chunk (a multiple of 128: tiles and 16-byte alignment hold)
+		const int nch = (int)((n + CH - 1) / CH);
+		std::vector<cudaEvent_t> ev((size_t)nch);
+		cudaEvent_t t0, t1;
+		cudaEventCreate(&t0); cudaEventCreate(&t1);
+		cudaEventRecord(t0, ctx->copy_stream);
+		for (int c = 0; c < nch; ++c) {
+			const uint64_t off = (uint64_t)c * CH, cnt = std::min(CH, n - off);
+			cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming);
+			MCB_CUDA(cudaMemcpyAsync((char*)d_rows + off * L, h_rows + off * L, cnt * L, cudaMemcpyHostToDevice, ctx->copy_stream));
+			cudaEventRecord(ev[c], ctx->copy_stream);
 		}
+		cudaEventRecord(t1, ctx->copy_stream);
+		for (int c = 0; c < nch; ++c) {
+			const uint64_t off = (uint64_t)c * CH, cnt = std::min(CH, n - off);
+			MCB_CUDA(cudaStreamWaitEvent(ctx->stream, ev[c], 0));
+			McbSpan sp(ctx->tm, "for_reads");
+			MCB_LAUNCH(ctx, "pack_classify_sketch", k_pack_classify_sketch, mcb_grid_for(cnt, RD_THREADS), RD_THREADS, smem,
+			           d_rows + off * L, cnt, rid_base + off, L, Wd, WS, ctx->prm.k, ctx->prm.diff_threshold, pbase,
+			           ctx->d_packed.as<uint64_t>(), ctx->d_cls.as<uint8_t>() + off, ctx->d_elemA.as<ulonglong2>() + off, dc);
+		}
+		MCB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (ctx->tm.enabled) { float ms = 0; if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) { int id = ctx->tm.id("h2d"); ctx->tm.ms[id] += ms; ctx->tm.cnt[id] += 1; } }
+		for (auto e : ev) cudaEventDestroy(e);
+		cudaEventDestroy(t0); cudaEventDestroy(t1);
 	}
 	MCB_TRY(sync_counters(ctx, &hc));
 	if (hc[CT_BADCHAR]) { mcb_set_error("%llu reads contain characters other than A,C,G,T,N (unsupported; the reference's behaviour on them is undefined)", hc[CT_BADCHAR]); return MCB_EINPUT; }
@@ -896,6 +924,11 @@ extern "C" int mcb_for_reads(mcb_ctx *ctx, const char *rows, uint64_t n, mcb_rea
 	if (!res || (n && !rows)) { mcb_set_error("mcb_for_reads: null argument"); return MCB_EINVAL; }
 	const size_t bytes = (size_t)n * ctx->L;
 	MCB_TRY(ctx->d_ascii.ensure(bytes + 16));
+	if (n >= (1ull << 31)) { mcb_set_error("too many reads (rid is a signed 32-bit int in the reference, kthread_bucket.c:48)"); return MCB_EINVAL; }
+	cudaPointerAttributes pa;
+	const bool pinned = cudaPointerGetAttributes(&pa, rows) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (pinned && n) return for_reads_impl(ctx, ctx->d_ascii.as<uint8_t>(), n, res, rows);     // copy and compute overlap chunk by chunk
 	{
 		McbSpan sp(ctx->tm, "h2d");
 		MCB_TRY(mcb_h2d(ctx, ctx->d_ascii.p, rows, bytes, 4));
