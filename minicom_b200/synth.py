@@ -96,13 +96,21 @@ def _inject_special(reads: np.ndarray, rng: np.random.Generator, frac: float) ->
             reads[r, int(rng.integers(0, L))] = ord("N")
 
 
-def write_fastq(path: str, reads: np.ndarray) -> None:
-    """4-line FASTQ with dummy names/qualities (all the reference reads is the sequence line)."""
+def fastq_record_bytes(L: int) -> int:
+    return 3 + L + 3 + L + 1
+
+
+def write_fastq(path: str, reads: np.ndarray, first_record: int | None = None) -> None:
+    """4-line FASTQ with dummy names/qualities (all the reference reads is the sequence line).
+    first_record: write into an EXISTING file at that record index (records have a fixed size), so that several processes
+    can fill one file side by side."""
     n, L = reads.shape
     head = b"@r\n"
     tail = b"\n+\n" + b"I" * L + b"\n"
     rec = len(head) + L + len(tail)
-    with open(path, "wb") as f:
+    with open(path, "wb" if first_record is None else "r+b") as f:
+        if first_record is not None:
+            f.seek(first_record * rec)
         chunk = 1 << 18
         for lo in range(0, n, chunk):
             hi = min(n, lo + chunk)
