@@ -38,9 +38,13 @@ WORKLOADS = {
     "C1": (1_000_000, 100, 5_000_000, "sg", {}),
     "C2": (10_000_000, 100, 50_000_000, "order", {}),
     "tiny": (100_000, 100, 500_000, "order", {}),
+    # BASELINE.json configs[3] (150 bp, non-default -w/-s/-E, stepping -S): C4 is the named size, C4s a fifth of it
+    "C4s": (10_000_000, 150, 75_000_000, "sg", {"MC_W": 20, "MC_S": 4, "MC_EMAX": 40, "MC_STEP": 2}),
+    "C4": (50_000_000, 150, 375_000_000, "sg", {"MC_W": 20, "MC_S": 4, "MC_EMAX": 40, "MC_STEP": 2}),
 }
 # bounded sample of the workload for the CPU arm: same shape and coverage, fewer reads
-CPU_SAMPLE = {"C2": (1_000_000, 100, 5_000_000), "C1": (1_000_000, 100, 5_000_000), "tiny": (100_000, 100, 500_000)}
+CPU_SAMPLE = {"C2": (1_000_000, 100, 5_000_000), "C1": (1_000_000, 100, 5_000_000), "tiny": (100_000, 100, 500_000),
+              "C4s": (500_000, 150, 3_750_000), "C4": (500_000, 150, 3_750_000)}
 
 
 def log(*a):
@@ -172,6 +176,13 @@ def algorithmic_bytes(kernel, c):
     if kernel == "k:s2_singles":
         return sum(r["S"] * 2 * L4 for r in rounds) / nr, nr
     return None, None
+
+
+def opts_text(ref_env):
+    """the reference options of a workload in minicom's own flag names"""
+    names = {"MC_K": "-k", "MC_E": "-e", "MC_M": "-m", "MC_W": "-w", "MC_S": "-s", "MC_EMAX": "-E", "MC_STEP": "-S"}
+    extra = " ".join(f"{names[k]} {v}" for k, v in ref_env.items() if k in names)
+    return "defaults k=31 m=6 e=4" + (f" with {extra}" if extra else "")
 
 
 def bench_ours(args):
@@ -358,7 +369,7 @@ def bench_ours(args):
     line = {
         "metric": "reads/sec for sketch+index+overlap stage", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev_max, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n} x {L} bp reads per GPU, {G} bp random genome, 1% substitutions, mode {mode}, defaults k=31 m=6 e=4" + ("" if world == 1 else "; independent read set per GPU, no exchange"),
+        "config": {"workload": f"{args.workload}: {n} x {L} bp reads per GPU, {G} bp random genome, 1% substitutions, mode {mode}, {opts_text(ref_env)}" + ("" if world == 1 else "; independent read set per GPU, no exchange"),
                    "l2": "inputs larger than L2 (reads %.0f MB per step)" % (n * L / 1e6), "timing": "value = CUDA-event device time of the four entry points (reads resident in HBM); e2e = wall clock through the host-buffer C-ABI",
                    "bases_per_s": round(value * L, 1), "wall_ms_per_step_device_arm": round(ms_wall_dev_max, 3),
                    "counters": {k: v for k, v in counters.items() if k != "rounds"}, "realign_rounds": counters["rounds"],
@@ -557,7 +568,7 @@ def bench_sharded(args):
         line = {
             "metric": "reads/sec for sketch+index+overlap stage", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_dev_max, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{args.workload} x {world}: ONE job of {n_total} x {L} bp reads ({n} per GPU), {G_total} bp random genome, 1% substitutions, mode {mode}, defaults k=31 m=6 e=4",
+            "config": {"workload": f"{args.workload} x {world}: ONE job of {n_total} x {L} bp reads ({n} per GPU), {G_total} bp random genome, 1% substitutions, mode {mode}, {opts_text(ref_env)}",
                        "sharding": "reads by read-id range; tuples all-to-all by bucket owner (bucket*G>>14) every round; packed reads all-gather; index builds by bucket range; "
                                    "Stage 2 contig lt-mer table partitioned by hash range (each rank probes the lt-mers it owns), claim priorities all-reduce(MIN), claims emitted by window range; results bit-identical to one GPU (tests/test_gpu_shard.py)",
                        "l2": "inputs larger than L2 (reads %.0f MB per GPU per step)" % (n * L / 1e6),
@@ -618,7 +629,7 @@ def bench_reference(args):
     wn, wL, wG, mode, _ = WORKLOADS[args.workload]
     line = {"impl": "reference", "metric": "reads/sec for sketch+index+overlap stage", "value": cpu["value"], "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": min(args.warmup, 1), "ms_per_step": cpu["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wn} x {wL} bp reads per GPU, {wG} bp random genome, 1% substitutions, mode {mode}, defaults k=31 m=6 e=4",
+            "config": {"workload": f"{args.workload}: {wn} x {wL} bp reads per GPU, {wG} bp random genome, 1% substitutions, mode {mode}, {opts_text(WORKLOADS[args.workload][4])}",
                        "note": "CPU arm timed on a bounded sample of the workload (see cpu_baseline.sample); the reference is a single-process CPU program, so its value does not grow with n_gpus"},
             "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)

@@ -29,6 +29,7 @@
 // swapping the two bits of a field, so popcounts, key equality and bin contents are identical.
 #include "mcb_common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 #define S2_MAXD 16
 #define S2_POS_BITS MCB_S2_POS_BITS
@@ -576,7 +577,8 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	// ---- build
 	cx.n_contigs = n_contigs; cx.ref_bytes = ref_bytes; cx.total_words = total_words; cx.n_windows = n_windows; cx.n_entries = n_entries; cx.L = L; cx.lt = lt;
 	int pcap = 26; for (int q = 1; q < tab_ranks; q <<= 1) ++pcap;                                               // the bucket space is shared by all ranks
-	int pbits = 10; while (pbits < pcap && pbits < 2 * lt && pbits < 31 && (4ull << pbits) < n_entries) ++pbits;   // 2..4 entries per bucket
+	static const int load_shift = getenv("MCB_S2_LOAD") ? atoi(getenv("MCB_S2_LOAD")) : 2;                   // tuning knob: 2^load_shift .. 2^(load_shift+1) entries per bucket
+	int pbits = 10; while (pbits < pcap && pbits < 2 * lt && pbits < 31 && ((1ull << load_shift) << pbits) < n_entries) ++pbits;
 	cx.pbits = pbits; cx.tab_rank = tab_rank; cx.tab_ranks = tab_ranks;
 	cx.b_lo = (uint32_t)((((uint64_t)tab_rank << pbits) + tab_ranks - 1) / tab_ranks);                            // owner(b) = b * ranks >> pbits
 	cx.b_hi = (uint32_t)((((uint64_t)(tab_rank + 1) << pbits) + tab_ranks - 1) / tab_ranks);
