@@ -82,7 +82,7 @@ k_sort_rowscan(uint32_t *__restrict__ hist, unsigned nblocks, uint32_t *__restri
 // __match_any_sync), parked in shared memory in digit order, and then written out so that consecutive threads write
 // consecutive addresses of a digit's run: global stores are whole sectors instead of 32 scattered 8/16-byte pieces.
 template <class E, class D>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, sizeof(E) == 16 ? 4 : 6)      // registers capped so that 4 (16-byte elements) / 6 (8-byte) CTAs fit an SM
 k_sort_scatter(const E *__restrict__ in, E *__restrict__ out, uint64_t n, D digit, const uint32_t *__restrict__ hist_scanned, unsigned nblocks,
                const uint32_t *__restrict__ rowsum)
 {
