@@ -150,105 +150,10 @@ k_index_sort(mcb_tuple *__restrict__ t, const uint64_t *__restrict__ boff, int n
 // are in flight per SM — and the walk, a chain of dependent shared-memory loads, is bound by how many run concurrently.
 // Tuples go through a scratch copy in global memory (L2-resident per bucket).
 #define IX2_WARPS 4
-#define IX2_BYTES_PER_TUPLE 13            // xs 8 + dest/fin 2 + src 2 + digit 1
-struct Ix2Smem { uint32_t *cur, *end; uint64_t *xs; uint16_t *dest, *src; uint8_t *dg; IxSeg *stk; };
+struct Ix2Smem { uint32_t *cur, *end; uint16_t *dest; uint8_t *dg; IxSeg *stk; };
 
-__device__ void ix2_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix2Smem &m, IxSeg *gstk, int lane)
-{
-	IxSeg *stk = m.stk;                       // shared stack first, global spill behind it
-	int top = 1;
-	if (lane == 0) { stk[0].b = 0; stk[0].e = n; stk[0].s = 56; }
-	__syncwarp();
-	while (top > 0) {
-		--top;
-		const IxSeg sg = top < IX_SMEM_STK ? stk[top] : gstk[top - IX_SMEM_STK];
-		const uint32_t sb = sg.b, se = sg.e, cnt = se - sb; const int s = sg.s;
-		__syncwarp();
-		for (int d = lane; d < 256; d += 32) m.cur[d] = 0;
-		__syncwarp();
-		for (uint32_t i = lane; i < cnt; i += 32) {
-			const uint64_t x = a[sb + i].x;
-			const unsigned d = (unsigned)(x >> s) & 255u;
-			m.xs[i] = x; m.dg[i] = (uint8_t)d; atomicAdd(&m.cur[d], 1u);
-		}
-		__syncwarp();
-		{
-			uint32_t v[8], sum = 0;
-#pragma unroll
-			for (int q = 0; q < 8; ++q) { v[q] = m.cur[lane * 8 + q]; sum += v[q]; }
-			uint32_t inc = sum;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
-			uint32_t run = inc - sum;             // positions relative to the segment
-			__syncwarp();
-#pragma unroll
-			for (int q = 0; q < 8; ++q) { m.cur[lane * 8 + q] = run; run += v[q]; m.end[lane * 8 + q] = run; }
-		}
-		__syncwarp();
-		if (lane == 0) {                          // the walk of ksort.h:131-145, on digits only
-			for (int k = 0; k < 256;) {
-				const uint32_t ck = m.cur[k];
-				if (ck != m.end[k]) {
-					uint32_t t = ck;                  // original index of the element in hand
-					int l = m.dg[t];
-					if (l != k) {
-						do {
-							const uint32_t p = m.cur[l]; m.cur[l] = p + 1;
-							m.dest[t] = (uint16_t)p;      // the element in hand lands on slot p ...
-							t = p;                        // ... and picks up p's original occupant
-							l = m.dg[t];
-						} while (l != k);
-						m.dest[t] = (uint16_t)m.cur[k]; m.cur[k] = m.cur[k] + 1;
-					} else { m.dest[t] = (uint16_t)ck; m.cur[k] = ck + 1; }
-				} else ++k;
-			}
-		}
-		__syncwarp();
-		for (uint32_t i = lane; i < cnt; i += 32) m.src[m.dest[i]] = (uint16_t)i;       // slot -> original index
-		__syncwarp();
-		// digit regions of at most 64 tuples are insertion-sorted by the reference (stable, by the whole key): rank every slot
-		// inside its region instead.  `dest` is free now and becomes fin[final slot] = original index.  Bigger regions keep the
-		// order of the walk and are sorted by the next digit.
-		for (uint32_t p = lane; p < cnt; p += 32) {
-			const uint32_t i = m.src[p];
-			const unsigned d = m.dg[i];
-			const uint32_t rs = d ? m.end[d - 1] : 0u, re = m.end[d];
-			uint32_t at = p;
-			if (s > 0 && re - rs <= IX_SMALL && re - rs > 1) {
-				const uint64_t xi = m.xs[i];
-				uint32_t rank = 0;
-				for (uint32_t q = rs; q < re; ++q) { const uint64_t xq = m.xs[m.src[q]]; rank += (xq < xi) || (xq == xi && q < p); }
-				at = rs + rank;
-			}
-			m.dest[at] = (uint16_t)i;
-		}
-		__syncwarp();
-		for (uint32_t p = lane; p < cnt; p += 32) tmp[sb + p] = a[sb + m.dest[p]];
-		__syncwarp();
-		for (uint32_t p = lane; p < cnt; p += 32) a[sb + p] = tmp[sb + p];
-		__syncwarp();
-		if (s > 0) {
-			const int s2 = s > 8 ? s - 8 : 0;
-			for (int d0 = 0; d0 < 256; d0 += 32) {
-				const int d = d0 + lane;
-				const uint32_t rb = sb + (d == 0 ? 0u : m.end[d - 1]), re = sb + m.end[d];
-				const bool big = re - rb > IX_SMALL;
-				const unsigned bm = __ballot_sync(0xFFFFFFFFu, big);
-				if (big) {
-					const int slot = top + __popc(bm & ((1u << lane) - 1u));
-					IxSeg ns; ns.b = rb; ns.e = re; ns.s = s2;
-					if (slot < IX_SMEM_STK) stk[slot] = ns; else gstk[slot - IX_SMEM_STK] = ns;
-				}
-				top += __popc(bm);
-			}
-		}
-		__syncwarp();
-	}
-}
-
-// Lean variant for large buckets: only the digits and destinations live in shared memory (3 bytes per tuple, so four times
-// more buckets are in flight); the keys needed to rank the small regions are read back from global memory after the walk's
-// permutation has been applied, where a region is a contiguous, cache-resident run.
+// Only the digits and destinations live in shared memory (3 bytes per tuple); the keys needed to rank the small regions are
+// read back from global memory after the walk's permutation has been applied, where a region is a contiguous, cache-resident run.
 __device__ void ix3_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix2Smem &m, IxSeg *gstk, int lane)
 {
 	IxSeg *stk = m.stk;
@@ -347,7 +252,6 @@ k_index_sort3(mcb_tuple *__restrict__ t, mcb_tuple *__restrict__ tmp, const uint
 	Ix2Smem m;
 	m.cur = (uint32_t*)base; m.end = m.cur + 256;
 	m.stk = (IxSeg*)(base + 2048);
-	m.xs = nullptr; m.src = nullptr;
 	m.dest = (uint16_t*)(base + 2048 + IX_SMEM_STK * sizeof(IxSeg));
 	m.dg = (uint8_t*)(m.dest + cap);
 	for (int bk = blockIdx.x * IX2_WARPS + wib; bk < nb; bk += gridDim.x * IX2_WARPS) {
@@ -356,29 +260,6 @@ k_index_sort3(mcb_tuple *__restrict__ t, mcb_tuple *__restrict__ tmp, const uint
 		if (n <= 1) continue;
 		if (n <= IX_SMALL) { ix_small_sort_warp(t + B0, n, lane); continue; }
 		ix3_flag_sort(t + B0, tmp + B0, n, m, stacks + (B0 / 65 + 8ull * bk), lane);
-	}
-}
-
-// cap = largest bucket this launch has to sort (sizes the per-warp shared memory)
-__global__ void __launch_bounds__(IX2_WARPS * 32)
-k_index_sort2(mcb_tuple *__restrict__ t, mcb_tuple *__restrict__ tmp, const uint64_t *__restrict__ boff, int nb, uint32_t cap, IxSeg *__restrict__ stacks)
-{
-	extern __shared__ __align__(16) unsigned char ix2_smem[];
-	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * IX2_BYTES_PER_TUPLE + 15) & ~(size_t)15;
-	unsigned char *base = ix2_smem + (size_t)wib * per_warp;
-	Ix2Smem m;
-	m.cur = (uint32_t*)base; m.end = m.cur + 256;
-	m.stk = (IxSeg*)(base + 2048);
-	m.xs = (uint64_t*)(base + 2048 + IX_SMEM_STK * sizeof(IxSeg));
-	m.dest = (uint16_t*)(m.xs + cap); m.src = m.dest + cap;
-	m.dg = (uint8_t*)(m.src + cap);
-	for (int bk = blockIdx.x * IX2_WARPS + wib; bk < nb; bk += gridDim.x * IX2_WARPS) {
-		const uint64_t B0 = boff[bk], B1 = boff[bk + 1];
-		const uint32_t n = (uint32_t)(B1 - B0);
-		if (n <= 1) continue;
-		if (n <= IX_SMALL) { ix_small_sort_warp(t + B0, n, lane); continue; }
-		ix2_flag_sort(t + B0, tmp + B0, n, m, stacks + (B0 / 65 + 8ull * bk), lane);
 	}
 }
 
@@ -491,8 +372,8 @@ static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mc
 		for (int i = 0; i < nb; ++i) maxb = std::max<uint64_t>(maxb, h_boff[i + 1] - h_boff[i]);
 		static const bool force_old = getenv("MCB_IX_OLD") != nullptr;
 		if (getenv("MCB_IX_DEBUG")) fprintf(stderr, "[mcb] idx build: n=%llu max bucket=%llu\n", (unsigned long long)n, (unsigned long long)maxb);
-		static const bool force_lean = getenv("MCB_IX_LEAN") != nullptr;
-		if (maxb <= 65000 && !force_old && (maxb > 1024 || force_lean)) {      // large buckets: 3 bytes of shared memory per tuple
+		bool done = false;
+		if (maxb <= 65000 && !force_old) {      // index-space walk: 3 bytes of shared memory per tuple of the largest bucket
 			const uint32_t cap = (uint32_t)std::max<uint64_t>(64, (maxb + 63) & ~63ull);
 			const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * 3 + 15) & ~(size_t)15;
 			const size_t smem3 = per_warp * IX2_WARPS;
@@ -501,23 +382,14 @@ static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mc
 				if (smem3 > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_index_sort3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
 				MCB_LAUNCH(ctx, "index_sort", k_index_sort3, mcb_grid_for(nb, IX2_WARPS), IX2_WARPS * 32, smem3, dt, ctx->d_scr[8].as<mcb_tuple>(), ctx->d_scr[1].as<uint64_t>(), nb, cap,
 				           ctx->d_scr[2].as<IxSeg>());
-				goto sorted;
+				done = true;
 			}
 		}
-		if (maxb <= 4096 && !force_old) {      // index-space walk: 13 bytes of shared memory per tuple of the largest bucket
-			const uint32_t cap = (uint32_t)std::max<uint64_t>(64, (maxb + 63) & ~63ull);
-			const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * IX2_BYTES_PER_TUPLE + 15) & ~(size_t)15;
-			const size_t smem2 = per_warp * IX2_WARPS;
-			MCB_TRY(ctx->d_scr[8].ensure(n * 16 + 16));
-			if (smem2 > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_index_sort2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-			MCB_LAUNCH(ctx, "index_sort", k_index_sort2, mcb_grid_for(nb, IX2_WARPS), IX2_WARPS * 32, smem2, dt, ctx->d_scr[8].as<mcb_tuple>(), ctx->d_scr[1].as<uint64_t>(), nb, cap,
-			           ctx->d_scr[2].as<IxSeg>());
-		} else {
+		if (!done) {       // buckets too large for that: the warp-per-bucket kernel that moves the tuples themselves
 			const size_t ix_smem = IX_WARPS * 2048 + IX_WARPS * IX_SMEM_STK * sizeof(IxSeg) + (size_t)IX_WARPS * IX_SMEM_CAP * sizeof(mcb_tuple);
 			MCB_CUDA(cudaFuncSetAttribute(k_index_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix_smem));
 			MCB_LAUNCH(ctx, "index_sort", k_index_sort, mcb_grid_for(nb, IX_WARPS), IX_WARPS * 32, ix_smem, dt, ctx->d_scr[1].as<uint64_t>(), nb, ctx->d_scr[2].as<IxSeg>());
 		}
-sorted:
 		MCB_LAUNCH(ctx, "ix_heads", k_ix_heads, mcb_grid_for(n, 256), 256, 0, dt, n, ctx->d_scr[3].as<uint32_t>());
 		MCB_TRY(mcb_exclusive_scan_u32(ctx, ctx->d_scr[3].as<uint32_t>(), n, (uint64_t*)&dc[CT_SCRATCH_IDX]));
 		MCB_LAUNCH(ctx, "ix_keys", k_ix_keys, mcb_grid_for(n, 256), 256, 0, dt, n, ctx->d_scr[3].as<uint32_t>(), &dc[CT_SCRATCH_IDX],
