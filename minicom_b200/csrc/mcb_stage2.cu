@@ -5,24 +5,27 @@
 // W windows x (2*numdict-1) random dictionary probes, of which ~98 % miss.  The join is symmetric, and the contigs do not
 // change between rounds (preprocess.c:197-232), so this implementation turns it around:
 //
-//   once per contig set   K5a k_s2_pack_refs    2-bit packed contigs
+//   once per contig set   K5a k_s2_pack_refs    2-bit packed contigs (+ one 32-byte record per contig, k_s2_contig_meta)
 //                         K5b k_s2_kmer_emit    every lt-mer of every contig (lt = 17, or 11 for L <= 80) as an 8-byte entry
 //                                               lt-mer<<30 | position, radix-sorted by a hash of the lt-mer into 2^p buckets
 //                                               (mcb_radix_sort_kmers) + k_s2_bucket_ends
 //   every round           K6  k_s2_singles      singleRead2bitset (bbhashdict.c:127-227): 2-bit singles, near-poly-A/T
 //                                               diversion, and a count-min sketch of the dictionary bins (bin sizes matter:
 //                                               the reference scans only the last `maxsearch` entries of a bin, :388)
-//                         K7  k_s2_join         one thread per (single, dictionary): its substring key, and the reverse
-//                                               complement of the key, are looked up in the contig table; each hit is a
-//                                               (window, single) candidate = exactly the pairs the reference's probes
-//                                               meet; XOR/popcount verification and the encode_byte gate (:283-314) follow
-//                         K8  claims            the single-threaded reference lets the FIRST probe step that matches a read
-//                                               claim it.  Every verified pair proposes priority P=(window, phase, l);
-//                                               atomicMin keeps the first; claims are then sorted by (P, sg index
-//                                               descending) = the reference's append order.
+//                         K7a k_s2_probe_table  one thread per (single, dictionary): its substring key, and the reverse
+//                                               complement of the key, are looked up in the contig table; every entry with
+//                                               an equal lt-mer is a (window, single) candidate = exactly the pairs the
+//                                               reference's probes meet
+//                         K7b k_s2_verify       one thread per candidate: XOR/popcount verification and the encode_byte
+//                                               gate (:283-314); the single-threaded reference lets the FIRST probe step that
+//                                               matches a read claim it, so every verified pair proposes priority
+//                                               P=(window, phase, l) and atomicMin keeps the first
+//                         K8  claims            compacted and sorted by (P, sg index descending) = the reference's append order
+//   rare                  realign_exact_bins    bins larger than maxsearch: their singles are replayed in order on the host
 //
 // Probes per round drop from 9 per window (4.7e8 at 10 M reads) to 2 per (single, dictionary) (3e7 in the first round,
-// 3e6 later), and only true key matches touch the contigs.
+// 3e6 later), and only true key matches touch the contigs.  Sharded over G GPUs, the table is partitioned by hash range
+// (mcb_realign_begin_keyed): a context keeps the buckets [b_lo, b_hi) and probes only the lt-mers that fall into them.
 //
 // Distance is the popcount of the XOR of 2-bit codes (bbhashdict.c:247-254), not a base count: A<->T and C<->G cost 2.
 // The reference's code A=00,G=01,C=10,T=11 (kthread_hash_realign.c:251-258) and ours (A0 C1 G2 T3) differ only by
