@@ -141,7 +141,7 @@ struct McbSpan {
 enum { CT_SKETCHED = 0, CT_BADCHAR = 1, CT_DEGENERATE = 2, CT_NREADS = 3, CT_REFCURSOR = 4, CT_G = 5, CT_TOT_CL = 6, CT_TOT_MEM = 7,
        CT_TOT_REF = 8, CT_TOT_SG = 9, CT_TOT_RESK = 10, CT_ERR = 11, CT_SCRATCH_IDX = 12,
        CT_S2_U = 16, CT_S2_PROBES = 17, CT_S2_CAND = 18, CT_S2_NEEDEXACT = 19, CT_S2_CLAIMS = 20, CT_S2_FPA = 21, CT_S2_FPT = 22, CT_S2_ERR = 23,
-       CT_S2_MAXBIN = 24, CT_S2_DIFF = 25, CT_S2_NCAND = 26, CT_S2_NBIGMEM = 27, CT_S2_NEVENTS = 28, CT_WORK0 = 32 /* ..35: consensus work-list sizes */ };
+       CT_S2_MAXBIN = 24, CT_S2_DIFF = 25, CT_SORT_OVERFLOW = 13, CT_S2_NCAND = 26, CT_S2_NBIGMEM = 27, CT_S2_NEVENTS = 28, CT_WORK0 = 32 /* ..35: consensus work-list sizes */ };
 
 // ---------------------------------------------------------------- context
 struct mcb_index;   // defined in mcb_index.cu
@@ -324,6 +324,7 @@ struct McbSortPass { int word; int shift; int bits; };  // word 0 = .x, 1 = .y
 int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const McbSortPass *passes, int n_passes,
                    ulonglong2 **sorted_out);
 int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long *b, uint64_t n, int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long **sorted_out);
+int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint32_t *boff, unsigned long long *overflow, ulonglong2 **sorted_out);
 int mcb_add_bit_passes(std::vector<McbSortPass> &v, int word, int lo, int hi);  // digits covering bits [lo,hi)
 int mcb_exclusive_scan_u32(mcb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *d_total /* device u64, may be null */);
 int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t *d_total);

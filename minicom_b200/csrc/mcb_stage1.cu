@@ -1091,18 +1091,29 @@ static int bucket_round_a(mcb_ctx *ctx, int r, int is_last)
 	const int kbits = r == 1 ? 2 * k : 2 * (kmer + 1);                      // tuples of round r were hashed with k-(r-1) (r>=2) or k
 	mcb_add_bit_passes(passes, 0, 0, std::max(1, kbits - 14));
 	mcb_add_bit_passes(passes, 0, 50, 64);
+	// Buckets are brought together by two radix passes on the bucket bits and sorted by the rest of the key inside shared
+	// memory (mcb_bucket_sort); a bucket too large for that makes the whole round fall back to LSD passes over the full key.
+	static const bool lsd_only = getenv("MCB_SORT_LSD") != nullptr;
 	ulonglong2 *sorted = nullptr;
-	MCB_TRY(mcb_radix_sort(ctx, bs.cur, bs.alt, bs.n_in, passes.data(), (int)passes.size(), &sorted));
-	if (sorted != bs.cur) { bs.alt = bs.cur; bs.cur = sorted; }
-	ulonglong2 *cur = bs.cur;
 	const uint64_t n = bs.n_valid;
 	bs.n = n;
-	// ---- groups
-	MCB_TRY(B.b_hs.ensure(n * 4 + 16)); MCB_TRY(B.b_gs.ensure((n + 2) * 4));
-	MCB_LAUNCH(ctx, "heads", k_heads, mcb_grid_for(n, 256), 256, 0, cur, n, B.b_hs.as<uint32_t>());
-	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_hs.as<uint32_t>(), n, (uint64_t*)&dc[CT_G]));
-	MCB_LAUNCH(ctx, "gstart", k_gstart, mcb_grid_for(n, 256), 256, 0, cur, n, B.b_hs.as<uint32_t>(), &dc[CT_G], B.b_gs.as<uint32_t>());
-	MCB_TRY(sync_counters(ctx, &hc));
+	MCB_TRY(B.b_hs.ensure(std::max<uint64_t>(n, 16400) * 4 + 16)); MCB_TRY(B.b_gs.ensure((n + 2) * 4));
+	unsigned long long *hc0 = nullptr;
+	for (int attempt = lsd_only ? 1 : 0;; ++attempt) {
+		if (attempt == 0) {
+			MCB_CUDA(cudaMemsetAsync(&dc[CT_SORT_OVERFLOW], 0, 8, ctx->stream));
+			MCB_TRY(mcb_bucket_sort(ctx, bs.cur, bs.alt, bs.n_in, B.b_hs.as<uint32_t>(), &dc[CT_SORT_OVERFLOW], &sorted));     // b_hs doubles as the bucket-offset scratch
+		} else MCB_TRY(mcb_radix_sort(ctx, bs.cur, bs.alt, bs.n_in, passes.data(), (int)passes.size(), &sorted));
+		if (sorted != bs.cur) { bs.alt = bs.cur; bs.cur = sorted; }
+		// ---- groups
+		MCB_LAUNCH(ctx, "heads", k_heads, mcb_grid_for(n, 256), 256, 0, bs.cur, n, B.b_hs.as<uint32_t>());
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_hs.as<uint32_t>(), n, (uint64_t*)&dc[CT_G]));
+		MCB_LAUNCH(ctx, "gstart", k_gstart, mcb_grid_for(n, 256), 256, 0, bs.cur, n, B.b_hs.as<uint32_t>(), &dc[CT_G], B.b_gs.as<uint32_t>());
+		MCB_TRY(sync_counters(ctx, &hc0));
+		if (attempt > 0 || hc0[CT_SORT_OVERFLOW] == 0) break;
+	}
+	hc = hc0;
+	ulonglong2 *cur = bs.cur;
 	const uint64_t G = hc[CT_G];
 	bs.G = G;
 	// ---- K3 consensus
