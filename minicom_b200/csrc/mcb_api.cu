@@ -80,7 +80,7 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 	for (auto &b : ctx->d_scan_tmp) b.release();
 	for (auto &b : ctx->d_x) b.release();
 	for (auto &b : ctx->d_out) b.release();
-	{ McbContigIndex &c = ctx->cix; DBuf *cb[] = { &c.refs, &c.roff, &c.cwo, &c.wo, &c.cw, &c.pblk, &c.ptab, &c.ents, &c.ents2, &c.eoff, &c.meta }; for (auto b : cb) b->release(); }
+	{ McbContigIndex &c = ctx->cix; DBuf *cb[] = { &c.refs, &c.roff, &c.cwo, &c.wo, &c.cw, &c.pblk, &c.ptab, &c.ents, &c.ents2, &c.eoff, &c.meta, &c.flt, &c.sgmap }; for (auto b : cb) b->release(); }
 	HBuf *hb[] = { &ctx->h_cls, &ctx->h_nrid, &ctx->h_nrepl, &ctx->h_noff, &ctx->h_npos, &ctx->h_nmask, &ctx->h_counters, &ctx->h_stage,
 	               &ctx->h_cl_n, &ctx->h_cl_a_off, &ctx->h_cl_a, &ctx->h_cl_ref_off, &ctx->h_cl_ref, &ctx->h_sg, &ctx->h_mi_cnt, &ctx->h_mi,
 	               &ctx->h_claim_c, &ctx->h_claim_s, &ctx->h_claim_y, &ctx->h_fpA, &ctx->h_fpT, &ctx->h_in0, &ctx->h_in1, &ctx->h_in2 };

@@ -165,6 +165,14 @@ struct McbContigIndex {
 	unsigned long long *ents_sorted = nullptr;
 	DBuf meta;      // S2ContigMeta[n_contigs+1]: {ref_off, cw_off, woff, len} per contig, 32 bytes
 	DBuf eoff;      // u64[n_contigs+1] entry offsets (prefix sums of len-lt+1 over contigs with windows)
+	// the table holds only the lt-mers that some single of the building call could ask for (Bloom filter over their keys)
+	bool table_valid = false;  // contigs packed AND table built
+	bool filtered = false;
+	int nd = 0, dstart0 = 0;   // dictionary geometry the filter was built for
+	DBuf flt;       // u32[flt_words] Bloom filter over the singles' dictionary keys and their reverse complements
+	uint64_t flt_words = 0;
+	uint64_t n_table = 0;      // entries kept in this context's table
+	DBuf sgmap;     // u32[n_reads/32+1] bitmap of the read ids whose keys are in the filter
 };
 
 // kt_for_bucket as a resumable round loop (the sharded driver exchanges tuples between the rounds)
@@ -231,8 +239,31 @@ struct mcb_ctx {
 // The shift-add forms of the reference are multiplications modulo 2^64 (the mask is applied afterwards in both):
 //   ~key + (key<<21) = key*(2^21-1) - 1,  key + (key<<3) + (key<<8) = key*265,  key + (key<<2) + (key<<4) = key*21,
 //   key + (key<<31) = key*(2^31+1).  A 64x32-bit multiply is 2-3 instructions on the device, each shift-add chain 6-8.
+#ifdef __CUDACC__
+// device form for 2k > 32 (mask covers the whole low word): the key lives in two 32-bit halves, every stage is one wide
+// multiply-add, one multiply-add, one AND on the high half and a funnel-shift XOR: 24 instructions instead of 34.
+__device__ __forceinline__ uint64_t mcb_hash64_wide(uint64_t key, uint32_t mh)
+{
+	uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+	uint64_t t = (uint64_t)lo * 0x1FFFFFu + 0xFFFFFFFFFFFFFFFFull;
+	hi = (hi * 0x1FFFFFu + (uint32_t)(t >> 32)) & mh; lo = (uint32_t)t;
+	lo ^= __funnelshift_r(lo, hi, 24); hi ^= hi >> 24;
+	t = (uint64_t)lo * 265u;
+	hi = (hi * 265u + (uint32_t)(t >> 32)) & mh; lo = (uint32_t)t;
+	lo ^= __funnelshift_r(lo, hi, 14); hi ^= hi >> 14;
+	t = (uint64_t)lo * 21u;
+	hi = (hi * 21u + (uint32_t)(t >> 32)) & mh; lo = (uint32_t)t;
+	lo ^= __funnelshift_r(lo, hi, 28); hi ^= hi >> 28;
+	t = (uint64_t)lo * 0x80000001u;
+	hi = (hi * 0x80000001u + (uint32_t)(t >> 32)) & mh; lo = (uint32_t)t;
+	return (uint64_t)hi << 32 | lo;
+}
+#endif
 MCB_HD uint64_t mcb_hash64_hd(uint64_t key, uint64_t mask)
 {
+#ifdef __CUDA_ARCH__
+	if ((uint32_t)mask == 0xFFFFFFFFu) return mcb_hash64_wide(key, (uint32_t)(mask >> 32));
+#endif
 	key = (key * 0x1FFFFFull - 1ull) & mask;
 	key ^= key >> 24;
 	key = (key * 265ull) & mask;
@@ -291,11 +322,16 @@ MCB_HD int mcb_k2_strand(uint64_t k2) { return (int)(k2 & 1); }
 
 // mm_sketch_two (sketch.c:238-289) over a packed, N-free read.  Returns x (UINT64_MAX if no valid k-mer) and
 // the last position / strand of the chosen k-mer.
-MCB_HD uint64_t mcb_sketch_two_packed(const uint64_t *row, int L, int k, int *pos_out, int *strand_out)
+// While the first k-1 bases are shifted in, f == r is impossible (the top field of r is the complement of the newest base and
+// the top field of f is still empty; the bottom fields likewise), so the reference's counter l (sketch.c:262-270) is simply
+// "bases seen" there; from the first full window on a symmetric k-mer is skipped and every other one is hashed.  With odd k a
+// full window is never symmetric (its middle base would be its own complement) and the test disappears.
+template <bool WIDE, bool ODD>
+MCB_HD uint64_t mcb_sketch_two_packed_t(const uint64_t *row, int L, int k, int *pos_out, int *strand_out)
 {
 	const uint64_t mask = (1ull << (2 * k)) - 1, shift1 = 2 * (k - 1);
 	uint64_t f = 0, r = 0, best = ~0ull;
-	int l = 0, bp = 0, bz = 0;
+	int bp = 0, bz = 0;
 	for (int w = 0; w * 32 < L; ++w) {
 		uint64_t word = row[w];
 		int lim = L - w * 32; if (lim > 32) lim = 32;
@@ -303,16 +339,70 @@ MCB_HD uint64_t mcb_sketch_two_packed(const uint64_t *row, int L, int k, int *po
 			uint64_t c = word & 3; word >>= 2;
 			f = (f << 2 | c) & mask;
 			r = (r >> 2) | ((3ull ^ c) << shift1);
-			if (f == r) continue;                  // symmetric k-mer: skipped and NOT counted (sketch.c:265)
-			int z = f < r ? 0 : 1;
-			if (++l >= k) {
-				uint64_t h = mcb_hash64_hd(z ? r : f, mask);
-				if (h < best) { best = h; bp = w * 32 + j; bz = z; }   // strict <: leftmost on ties (sketch.c:275)
-			}
+			if (w * 32 + j < k - 1) continue;
+			if (!ODD && f == r) continue;          // symmetric k-mer: skipped (sketch.c:265)
+			const int z = f < r ? 0 : 1;
+#ifdef __CUDA_ARCH__
+			const uint64_t h = WIDE ? mcb_hash64_wide(z ? r : f, (uint32_t)(mask >> 32)) : mcb_hash64_hd(z ? r : f, mask);
+#else
+			const uint64_t h = mcb_hash64_hd(z ? r : f, mask);
+#endif
+			if (h < best) { best = h; bp = w * 32 + j; bz = z; }   // strict <: leftmost on ties (sketch.c:275)
 		}
 	}
 	*pos_out = bp; *strand_out = bz;
 	return best;
+}
+#ifdef __CUDACC__
+// Device form for 16 < k < 32: k-mers in 32-bit halves, sixteen bases per 32-bit piece of the packed row, the partial-window
+// bases rolled in a loop of their own, and the strand of the winner recomputed once at the end instead of carried along.
+template <bool ODD>
+__device__ __forceinline__ uint64_t mcb_sketch_two_wide(const uint64_t *row, int L, int k, int *pos_out, int *strand_out)
+{
+	const uint32_t mh = (1u << (2 * k - 32)) - 1u;
+	const int s1 = 2 * (k - 1) - 32;
+	const uint32_t t3 = 3u << s1;
+	uint32_t flo = 0, fhi = 0, rlo = 0, rhi = 0, blo = ~0u, bhi = ~0u;
+	int bp = -1;
+#define MCB_S2W_ROLL() { const uint32_t c = x & 3u; x >>= 2; fhi = __funnelshift_l(flo, fhi, 2) & mh; flo = flo * 4u + c; \
+                         rlo = __funnelshift_r(rlo, rhi, 2); rhi = (rhi >> 2) | ((c << s1) ^ t3); }
+	for (int h = 0; h * 16 < L; ++h) {
+		uint32_t x = (uint32_t)(row[h >> 1] >> (32 * (h & 1)));
+		const int base = h * 16;
+		const int lim = min(16, L - base);
+		const int split = max(0, min(lim, k - 1 - base));
+		for (int j = 0; j < split; ++j) MCB_S2W_ROLL();
+		for (int j = split; j < lim; ++j) {
+			MCB_S2W_ROLL();
+			if (!ODD && flo == rlo && fhi == rhi) continue;          // symmetric k-mer: skipped (sketch.c:265)
+			const bool fwd = ((uint64_t)fhi << 32 | flo) < ((uint64_t)rhi << 32 | rlo);
+			const uint64_t hv = mcb_hash64_wide((uint64_t)(fwd ? fhi : rhi) << 32 | (fwd ? flo : rlo), mh);
+			const uint32_t hlo = (uint32_t)hv, hhi = (uint32_t)(hv >> 32);
+			const bool better = hv < ((uint64_t)bhi << 32 | blo);           // strict <: leftmost on ties (sketch.c:275)
+			blo = better ? hlo : blo; bhi = better ? hhi : bhi; bp = better ? base + j : bp;
+		}
+	}
+#undef MCB_S2W_ROLL
+	if (bp < 0) { *pos_out = 0; *strand_out = 0; return ~0ull; }
+	// strand of the winning window [bp-k+1, bp]: r is the complemented window as packed, f its field reversal
+	const int o = 2 * (bp - k + 1), wi = o >> 6, sh = o & 63;
+	uint64_t v = row[wi] >> sh;
+	if (sh + 2 * k > 64) v |= row[wi + 1] << (64 - sh);
+	const uint64_t mask = ((uint64_t)mh << 32) | 0xFFFFFFFFull;
+	v &= mask;
+	const uint64_t r = ~v & mask;
+	uint64_t f = __brevll(v) >> (64 - 2 * k);
+	f = ((f >> 1) & 0x5555555555555555ull) | ((f & 0x5555555555555555ull) << 1);
+	*pos_out = bp; *strand_out = f < r ? 0 : 1;
+	return (uint64_t)bhi << 32 | blo;
+}
+#endif
+MCB_HD uint64_t mcb_sketch_two_packed(const uint64_t *row, int L, int k, int *pos_out, int *strand_out)
+{
+#ifdef __CUDA_ARCH__
+	if (k > 16 && k < 32) return (k & 1) ? mcb_sketch_two_wide<true>(row, L, k, pos_out, strand_out) : mcb_sketch_two_wide<false>(row, L, k, pos_out, strand_out);
+#endif
+	return mcb_sketch_two_packed_t<false, false>(row, L, k, pos_out, strand_out);
 }
 
 // Stage-2 contig table entries: lt-mer << 30 | global base position; buckets by a multiplicative hash of the lt-mer

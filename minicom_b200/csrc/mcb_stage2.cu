@@ -131,13 +131,65 @@ __global__ void k_s2_same(const uint64_t *__restrict__ a, const uint64_t *__rest
 	if (__any_sync(0xFFFFFFFFu, diff) && (threadIdx.x & 31) == 0) atomicAdd(&counters[CT_S2_DIFF], 1ull);
 }
 
+// ---------------------------------------------------------------- key filter
+// Only contig lt-mers equal to a dictionary key of some single (or to the reverse complement of one) can ever be hit.  A Bloom
+// filter over those keys (one 32-bit word, three bits per key) lets the table builder drop the rest: at 20x coverage about one
+// contig lt-mer in eight survives, so the table, its sort and the probes' DRAM footprint shrink accordingly.  The filter belongs
+// to the singles of the call that built the table; later rounds may only use the table if their singles are a subset (sgmap).
+__device__ __forceinline__ void flt_slot(uint64_t key, uint64_t wmask, uint64_t *word, uint32_t *bits)
+{
+	const uint64_t h = mix64(key);
+	*word = (h >> 20) & wmask;
+	*bits = (1u << (h & 31)) | (1u << ((h >> 5) & 31)) | (1u << ((h >> 10) & 31));
+}
+__device__ __forceinline__ bool flt_has(const uint32_t *__restrict__ flt, uint64_t wmask, uint64_t key)
+{
+	uint64_t w; uint32_t b;
+	flt_slot(key, wmask, &w, &b);
+	return (flt[w] & b) == b;
+}
+__device__ __forceinline__ uint64_t rev_fields(uint64_t v, int nbases)
+{
+	// reverse the order of the low `nbases` 2-bit fields
+	uint64_t r = __brevll(v) >> (64 - 2 * nbases);
+	return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+}
+__global__ void k_s2_filter_insert(const uint64_t *__restrict__ rd, const uint8_t *__restrict__ flagged, const uint32_t *__restrict__ sg, uint64_t S, S2Geom gm,
+                                   uint32_t *__restrict__ flt, uint64_t wmask, uint32_t *__restrict__ sgmap)
+{
+	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= S * (uint64_t)gm.nd) return;
+	const int l = (int)(idx / S); const uint64_t s = idx - (uint64_t)l * S;
+	if (l == 0) { const uint32_t rid = sg[s]; atomicOr(&sgmap[rid >> 5], 1u << (rid & 31)); }
+	if (flagged[s]) return;
+	const uint64_t *row = rd + s * gm.WS;
+	const int lt = gm.lt, ds = gm.dstart[l];
+	const uint64_t kmask = (1ull << (2 * lt)) - 1;
+	const int bit = 2 * ds, wi = bit >> 6, sh = bit & 63;
+	uint64_t v = row[wi] >> sh;
+	if (sh + 2 * lt > 64) v |= row[wi + 1] << (64 - sh);
+	const uint64_t key_f = v & kmask;
+	uint64_t w; uint32_t b;
+	flt_slot(key_f, wmask, &w, &b); atomicOr(&flt[w], b);
+	if (ds > 0) { flt_slot(rev_fields(~key_f & kmask, lt), wmask, &w, &b); atomicOr(&flt[w], b); }
+}
+// are all these singles among the ones the filter was built from?
+__global__ void k_s2_sg_subset(const uint32_t *__restrict__ sg, uint64_t S, const uint32_t *__restrict__ sgmap, unsigned long long *__restrict__ counters)
+{
+	const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	bool miss = false;
+	if (s < S) { const uint32_t rid = sg[s]; miss = !((sgmap[rid >> 5] >> (rid & 31)) & 1u); }
+	if (__any_sync(0xFFFFFFFFu, miss) && (threadIdx.x & 31) == 0) atomicAdd(&counters[CT_S2_DIFF], 1ull);
+}
+
 // ---------------------------------------------------------------- K5b contig lt-mer table
 // One thread per packed word finds its contig; the warp then walks its 32 words together, lane j writing the lt-mer that
 // starts at base j of the word, so every store instruction covers 32 consecutive entries.
 __global__ void __launch_bounds__(256)
 k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_off, const uint64_t *__restrict__ ref_off, const uint64_t *__restrict__ ent_off,
                uint64_t n_contigs, uint64_t total_words, int L, int lt, unsigned long long *__restrict__ ents,
-               int filter, int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long *__restrict__ counter, unsigned long long ents_cap)
+               int filter, int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long *__restrict__ counter, unsigned long long ents_cap,
+               const uint32_t *__restrict__ flt, uint64_t flt_mask)
 {
 	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
@@ -167,14 +219,18 @@ k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_
 		}
 		return;
 	}
-	// key-sharded table: keep the lt-mers whose bucket this context owns.  Each thread walks the 32 start positions of ITS word,
-	// the warp reserves room with one atomic, and the kept entries are written packed (their order is irrelevant: they are sorted next).
-	unsigned mine = 0;
+	// filtered table: keep the lt-mers that pass the key filter and (key-sharded) whose bucket this context owns.  Each thread walks
+	// the 32 start positions of ITS word, the warp reserves room with one atomic, and the kept entries are written packed (their
+	// order is irrelevant: they are sorted next).  The keep decisions are remembered in a bit mask for the second sweep.
+	unsigned keepmask = 0;
+#pragma unroll 4
 	for (int j = 0; j < nstart; ++j) {
 		const uint64_t key = ((w0 >> (2 * j)) | (j ? w1 << (64 - 2 * j) : 0ull)) & kmask;
 		const uint32_t bk = kmer_bucket(key, pbits);
-		mine += bk >= b_lo && bk < b_hi;
+		const bool keep = bk >= b_lo && bk < b_hi && (!flt || flt_has(flt, flt_mask, key));
+		keepmask |= (unsigned)keep << j;
 	}
+	const unsigned mine = __popc(keepmask);
 	unsigned inc = mine;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
@@ -184,13 +240,11 @@ k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_
 	if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
 	base = __shfl_sync(0xFFFFFFFFu, base, 0);
 	unsigned long long at = base + (inc - mine);
-	for (int j = 0; j < nstart; ++j) {
+	for (unsigned km = keepmask; km; km &= km - 1) {
+		const int j = __ffs(km) - 1;
 		const uint64_t key = ((w0 >> (2 * j)) | (j ? w1 << (64 - 2 * j) : 0ull)) & kmask;
-		const uint32_t bk = kmer_bucket(key, pbits);
-		if (bk >= b_lo && bk < b_hi) {
-			if (at < ents_cap) ents[at] = (key << S2_POS_BITS) | (pos0 + j);
-			++at;
-		}
+		if (at < ents_cap) ents[at] = (key << S2_POS_BITS) | (pos0 + j);
+		++at;
 	}
 }
 // entries are ordered by bucket: ptab[b] = end of bucket b (= start of bucket b+1)
@@ -208,7 +262,7 @@ __global__ void k_s2_bucket_ends(const unsigned long long *__restrict__ ents, ui
 __global__ void k_s2_singles(const uint32_t *__restrict__ sg, uint64_t S, const uint64_t *__restrict__ packed, S2Geom gm,
                              const uint32_t *__restrict__ nread_rid, const uint64_t *__restrict__ nread_mask, uint64_t n_nreads, uint64_t n_reads,
                              uint64_t *__restrict__ rd, uint8_t *__restrict__ flagged, uint32_t *__restrict__ cm, uint64_t cm_mask,
-                             int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long *__restrict__ counters)
+                             int own_rank, int own_ranks, unsigned long long *__restrict__ counters)
 {
 	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned maxbin = 0;
@@ -250,8 +304,7 @@ __global__ void k_s2_singles(const uint32_t *__restrict__ sg, uint64_t S, const 
 			// count-min sketch of the dictionary bins: an upper bound of every bin size (a bin = singles sharing a key in dictionary l)
 			for (int l = 0; l < gm.nd; ++l) {
 				const uint64_t k0 = extract_bases(w, gm.dstart[l], gm.lt);
-				const uint32_t bg = kmer_bucket(k0, pbits);
-				if (bg < b_lo || bg >= b_hi) continue;                 // key-sharded: the owner of the lt-mer counts the bin
+				if (own_ranks > 1 && (int)(((uint64_t)kmer_bucket(k0, 16) * own_ranks) >> 16) != own_rank) continue;   // key-sharded: one rank counts each bin
 				unsigned long long key = ((unsigned long long)l << 34) | k0;
 				unsigned v = atomicAdd(&cm[mix64(key) & cm_mask], 1u) + 1u;
 				maxbin = max(maxbin, v);
@@ -329,12 +382,6 @@ struct S2Join {
 	const uint8_t *inbig; unsigned long long *events; unsigned long long events_cap;
 };
 
-__device__ __forceinline__ uint64_t rev_fields(uint64_t v, int nbases)
-{
-	// reverse the order of the low `nbases` 2-bit fields
-	uint64_t r = __brevll(v) >> (64 - 2 * nbases);
-	return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
-}
 
 // K7a: probe.  One thread per (single, dictionary): the key and its reverse complement are looked up in the contig table;
 // every entry with an equal lt-mer becomes a candidate record (pair index | phase | contig position), appended with one
@@ -577,18 +624,13 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 		cx.valid = false;
 		std::swap(cx.refs, ctx->d_scr[1]); std::swap(cx.roff, ctx->d_scr[2]);
 	}
-	// ---- build
+	// ---- pack
+	cx.table_valid = false;
 	cx.n_contigs = n_contigs; cx.ref_bytes = ref_bytes; cx.total_words = total_words; cx.n_windows = n_windows; cx.n_entries = n_entries; cx.L = L; cx.lt = lt;
-	int pcap = 26; for (int q = 1; q < tab_ranks; q <<= 1) ++pcap;                                               // the bucket space is shared by all ranks
-	static const int load_shift = getenv("MCB_S2_LOAD") ? atoi(getenv("MCB_S2_LOAD")) : 2;                   // tuning knob: 2^load_shift .. 2^(load_shift+1) entries per bucket
-	int pbits = 10; while (pbits < pcap && pbits < 2 * lt && pbits < 31 && ((1ull << load_shift) << pbits) < n_entries) ++pbits;
-	cx.pbits = pbits; cx.tab_rank = tab_rank; cx.tab_ranks = tab_ranks;
-	cx.b_lo = (uint32_t)((((uint64_t)tab_rank << pbits) + tab_ranks - 1) / tab_ranks);                            // owner(b) = b * ranks >> pbits
-	cx.b_hi = (uint32_t)((((uint64_t)(tab_rank + 1) << pbits) + tab_ranks - 1) / tab_ranks);
-	const uint64_t nbk = cx.b_hi - cx.b_lo, n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
-	const uint64_t ents_cap = tab_ranks > 1 ? n_entries / tab_ranks + n_entries / (4 * tab_ranks) + (1u << 20) : n_entries;   // hashed lt-mers spread evenly; checked below
+	cx.tab_rank = tab_rank; cx.tab_ranks = tab_ranks;
+	const uint64_t n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
 	MCB_TRY(cx.cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.wo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.cw.ensure((total_words + 2) * 8));
-	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16)); MCB_TRY(cx.ptab.ensure((nbk + 1) * 4)); MCB_TRY(cx.ents.ensure(ents_cap * 8 + 16)); MCB_TRY(cx.ents2.ensure(ents_cap * 8 + 16));
+	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16));
 	MCB_TRY(cx.eoff.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.meta.ensure((n_contigs + 2) * 32));
 	{
 		McbSpan sp(ctx->tm, "h2d");
@@ -604,21 +646,79 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	MCB_LAUNCH(ctx, "s2_pack_refs", k_s2_pack_refs, mcb_grid_for(total_words, 256), 256, 0, cx.refs.as<char>(), cx.roff.as<uint64_t>(), cx.cwo.as<uint64_t>(),
 	           n_contigs, total_words, cx.cw.as<uint64_t>(), dc);
 	MCB_LAUNCH(ctx, "s2_pos_blocks", k_s2_pos_blocks, mcb_grid_for(n_blocks, 256), 256, 0, cx.roff.as<uint64_t>(), n_contigs, n_blocks, cx.pblk.as<uint32_t>());
-	uint64_t n_own = n_entries;
-	if (tab_ranks > 1) MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NCAND], 0, 8, ctx->stream));
-	MCB_LAUNCH(ctx, "s2_kmer_emit", k_s2_kmer_emit, mcb_grid_for(total_words, 256), 256, 0, cx.cw.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.roff.as<uint64_t>(),
-	           cx.eoff.as<uint64_t>(), n_contigs, total_words, L, lt, cx.ents.as<unsigned long long>(), tab_ranks > 1 ? 1 : 0, pbits, cx.b_lo, cx.b_hi, &dc[CT_S2_NCAND], (unsigned long long)ents_cap);
-	if (tab_ranks > 1) {
+	cx.valid = true;
+	return MCB_OK;
+}
+
+// The lt-mer table of the packed contigs: (lt-mer, position) entries sorted by hashed bucket, with bucket end offsets.  Built
+// after the singles of the call are known, so that only the lt-mers some single can ask for are kept (key filter above); the
+// table is rebuilt when a later call brings singles that were not in the filter, or another dictionary geometry.
+static int contig_table_update(mcb_ctx *ctx, const S2Geom &gm, const uint32_t *d_sg, uint64_t S, const uint64_t *d_rd, const uint8_t *d_fl)
+{
+	McbContigIndex &cx = ctx->cix;
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
+	static const bool use_filter = !(getenv("MCB_S2_NOFILTER") && atoi(getenv("MCB_S2_NOFILTER")));
+	const int tab_rank = cx.tab_rank, tab_ranks = cx.tab_ranks;
+	if (cx.n_windows == 0 || cx.n_contigs == 0) { cx.table_valid = true; cx.filtered = false; return MCB_OK; }
+	if (cx.table_valid) {
+		if (!cx.filtered) return MCB_OK;
+		if (cx.nd == gm.nd && cx.dstart0 == gm.dstart[0]) {
+			MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_DIFF], 0, 8, ctx->stream));
+			if (S) MCB_LAUNCH(ctx, "s2_sg_subset", k_s2_sg_subset, mcb_grid_for(S, 256), 256, 0, d_sg, S, cx.sgmap.as<uint32_t>(), dc);
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+			if (hc[CT_S2_DIFF] == 0) return MCB_OK;
+		}
+		cx.table_valid = false;
+	}
+	const uint64_t n_all = cx.n_entries;          // all lt-mer start positions of the contigs that have a window
+	const uint64_t nkv = S * (uint64_t)gm.nd;
+	const bool filtered = use_filter;
+	uint64_t wmask = 0;
+	if (filtered) {
+		static const int flt_shift = getenv("MCB_S2_FLT") ? atoi(getenv("MCB_S2_FLT")) : -1;             // tuning knob: filter words per (single, dictionary), log2
+		const uint64_t want = flt_shift >= 0 ? nkv << flt_shift : nkv >> -flt_shift;
+		uint64_t W = 1024; while (W < want && W < (1ull << 28)) W <<= 1;
+		MCB_TRY(cx.flt.ensure(W * 4)); MCB_TRY(cx.sgmap.ensure((ctx->n_reads / 32 + 2) * 4));
+		MCB_CUDA(cudaMemsetAsync(cx.flt.p, 0, W * 4, ctx->stream));
+		MCB_CUDA(cudaMemsetAsync(cx.sgmap.p, 0, (ctx->n_reads / 32 + 2) * 4, ctx->stream));
+		wmask = W - 1; cx.flt_words = W;
+		if (nkv) MCB_LAUNCH(ctx, "s2_filter_insert", k_s2_filter_insert, mcb_grid_for(nkv, 256), 256, 0, d_rd, d_fl, d_sg, S, gm, cx.flt.as<uint32_t>(), wmask, cx.sgmap.as<uint32_t>());
+	}
+	// ownership of the key space among the ranks is fixed on the top 16 hash bits, so every rank may size its own bucket table
+	const uint32_t o_lo = (uint32_t)((((uint64_t)tab_rank << 16) + tab_ranks - 1) / tab_ranks), o_hi = (uint32_t)((((uint64_t)(tab_rank + 1) << 16) + tab_ranks - 1) / tab_ranks);
+	const bool compacting = filtered || tab_ranks > 1;
+	uint64_t ents_cap = !compacting ? n_all : (filtered ? n_all / (4 * tab_ranks) : n_all / tab_ranks + n_all / (4 * tab_ranks)) + (1u << 20);
+	if (ents_cap > n_all) ents_cap = n_all;
+	uint64_t n_own = n_all;
+	for (int tries = 0;; ++tries) {
+		MCB_TRY(cx.ents.ensure(ents_cap * 8 + 16));
+		if (compacting) MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NCAND], 0, 8, ctx->stream));
+		MCB_LAUNCH(ctx, "s2_kmer_emit", k_s2_kmer_emit, mcb_grid_for(cx.total_words, 256), 256, 0, cx.cw.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.roff.as<uint64_t>(),
+		           cx.eoff.as<uint64_t>(), cx.n_contigs, cx.total_words, cx.L, cx.lt, cx.ents.as<unsigned long long>(), compacting ? 1 : 0, 16, o_lo, o_hi, &dc[CT_S2_NCAND],
+		           (unsigned long long)ents_cap, filtered ? cx.flt.as<uint32_t>() : (const uint32_t*)nullptr, wmask);
+		if (!compacting) break;
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-		n_own = ctx->h_counters.as<unsigned long long>()[CT_S2_NCAND];
-		if (n_own > ents_cap) { mcb_set_error("mcb_realign: this rank's share of the lt-mer table (%llu entries) exceeds the reserved %llu", (unsigned long long)n_own, (unsigned long long)ents_cap); return MCB_EINVAL; }
-		cx.n_entries = n_own;
+		n_own = hc[CT_S2_NCAND];
+		if (n_own <= ents_cap) break;
+		if (tries) { mcb_set_error("mcb_realign: lt-mer table overflow (%llu entries, room for %llu)", (unsigned long long)n_own, (unsigned long long)ents_cap); return MCB_EINVAL; }
+		ents_cap = n_own;                                                               // the count is exact: emit again into enough room
 	}
+	cx.n_table = n_own;
+	static const int load_shift = getenv("MCB_S2_LOAD") ? atoi(getenv("MCB_S2_LOAD")) : 2;                   // tuning knob: 2^load_shift .. 2^(load_shift+1) entries per bucket
+	int pbits = tab_ranks > 1 ? 16 : 10;
+	while (pbits < 30 && pbits < 2 * cx.lt && ((1ull << load_shift) << pbits) < n_own * (uint64_t)tab_ranks) ++pbits;
+	cx.pbits = pbits;
+	if (tab_ranks > 1) { cx.b_lo = o_lo << (pbits - 16); cx.b_hi = o_hi << (pbits - 16); }
+	else { cx.b_lo = 0; cx.b_hi = 1u << pbits; }
+	const uint64_t nbk = cx.b_hi - cx.b_lo;
+	MCB_TRY(cx.ents2.ensure(n_own * 8 + 16)); MCB_TRY(cx.ptab.ensure((nbk + 1) * 4));
 	MCB_TRY(mcb_radix_sort_kmers(ctx, cx.ents.as<unsigned long long>(), cx.ents2.as<unsigned long long>(), n_own, pbits, cx.b_lo, cx.b_hi, &cx.ents_sorted));
 	MCB_CUDA(cudaMemsetAsync(cx.ptab.p, 0, (nbk + 1) * 4, ctx->stream));
 	if (n_own) MCB_LAUNCH(ctx, "s2_bucket_ends", k_s2_bucket_ends, mcb_grid_for(n_own, 256), 256, 0, cx.ents_sorted, n_own, pbits, cx.b_lo, cx.b_hi, cx.ptab.as<uint32_t>());
-	cx.valid = true;
+	cx.table_valid = true; cx.filtered = filtered; cx.nd = gm.nd; cx.dstart0 = gm.dstart[0];
 	return MCB_OK;
 }
 
@@ -792,7 +892,8 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	MCB_CUDA(cudaMemsetAsync(b_cm.p, 0, CM * 4, ctx->stream));
 	MCB_LAUNCH(ctx, "s2_singles", k_s2_singles, mcb_grid_for(S, 128), 128, 0, b_sg.as<uint32_t>(), S, ctx->d_packed.as<uint64_t>(), gm,
 	           ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->n_nreads, ctx->n_reads,
-	           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, cx.pbits, cx.b_lo, cx.b_hi, dc);
+	           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, tab_rank, tab_ranks, dc);
+	MCB_TRY(contig_table_update(ctx, gm, b_sg.as<uint32_t>(), S, b_rd.as<uint64_t>(), b_fl.as<uint8_t>()));
 	if (n_windows == 0) {          // no contig long enough on this rank: the diversion lists are still needed
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
