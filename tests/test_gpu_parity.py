@@ -187,6 +187,33 @@ def test_front_end_matches_oracle(case):
     import oracle_lib as O
     name, n, L, G, seed, special, opt = case
     reads = synth.make_reads(n, L, G, seed=seed, special=special)
+    _check_front_end_against_oracle(reads, L, opt)
+
+
+def _tandem_genome(seed, total):
+    """Random stretches interleaved with tandem repeats (period 1..40): windows that hold the same k-mer several times,
+    the case mm_sketch_lh_ori's identical-hash scans (sketch.c:141-146,159-161) exist for."""
+    rng = np.random.default_rng([seed, 0x74616E])
+    parts, n = [], 0
+    while n < total:
+        parts.append(synth.make_genome(int(rng.integers(40, 200)), int(rng.integers(1 << 30))))
+        unit = synth.make_genome(int(rng.integers(1, 41)), int(rng.integers(1 << 30)))
+        parts.append(np.tile(unit, int(rng.integers(80, 400)) // len(unit) + 1))
+        n += len(parts[-1]) + len(parts[-2])
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("L,opt,seed", [(100, {}, 51), (100, {"k": 30}, 52), (64, {"k": 20, "w": 7}, 53), (150, {"w": 40, "m": 12}, 54)],
+                         ids=["L100", "L100_even_k", "L64_w7", "L150_w40_m12"])
+def test_front_end_matches_oracle_on_tandem_repeats(L, opt, seed):
+    genome = _tandem_genome(seed, 30000)
+    reads = synth.make_reads(8000, L, len(genome), seed=seed, sub_rate=0.003, genome=genome)
+    _check_front_end_against_oracle(reads, L, opt)
+
+
+def _check_front_end_against_oracle(reads, L, opt):
+    import oracle_lib as O
+    n = len(reads)
     S = O.Stage1(O.resolve_params(L, **opt), reads)
     with api.Context(api.resolve_params(L, **opt)) as ctx:
         rr = ctx.for_reads(reads)
