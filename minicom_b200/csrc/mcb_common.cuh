@@ -281,7 +281,11 @@ MCB_HD unsigned mcb_base_at(const uint64_t *row, int i) { return (unsigned)(row[
 // process_reads counts only upper-case ACGTN, kthread_reads.c:56-73, and construct_ref indexes count_table[4] for 'N').
 MCB_HD unsigned mcb_code_of(unsigned char c)
 {
-	return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : c == 'N' ? 4u : 5u;
+	// branch-free: (c>>1)&3 maps A,C,T,G to 0,1,2,3 and x^(x>>1) turns that into A0 C1 G2 T3; the guess is accepted iff "ACGT"[code] == c.
+	// (A chain of comparisons compiles to a four-way branch that serialises whatever follows in a warp.)
+	const unsigned x = (c >> 1) & 3u, code = x ^ (x >> 1);
+	const unsigned ok = ((0x54474341u >> (8u * code)) & 0xFFu) == c;
+	return ok ? code : (c == 'N' ? 4u : 5u);
 }
 
 // reverse the order of the 32 two-bit fields of a word and complement them (A<->T, C<->G == 3-code)
