@@ -87,6 +87,7 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 	for (auto b : hb) b->release();
 	cudaStreamDestroy(ctx->stream);
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+	if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
 	if (ctx->pool && ctx->pool->close()) delete ctx->pool;
 	delete ctx;
 }
@@ -105,13 +106,20 @@ static void par_memcpy(char *dst, const char *src, size_t bytes, int n_threads)
 	for (auto &x : th) x.join();
 }
 
-int mcb_h2d(mcb_ctx *ctx, void *dst, const void *src, size_t bytes, int n_threads)
+int mcb_copy_streams(mcb_ctx *ctx)
+{
+	if (!ctx->copy_stream) MCB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	if (!ctx->copy_stream2) MCB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+	return MCB_OK;
+}
+int mcb_h2d(mcb_ctx *ctx, void *dst, const void *src, size_t bytes, int n_threads) { return mcb_h2d_on(ctx, ctx->stream, dst, src, bytes, n_threads); }
+int mcb_h2d_on(mcb_ctx *ctx, cudaStream_t stream, void *dst, const void *src, size_t bytes, int n_threads)
 {
 	if (!bytes) return MCB_OK;
 	cudaPointerAttributes pa;
 	const bool pinned = cudaPointerGetAttributes(&pa, src) == cudaSuccess && pa.type == cudaMemoryTypeHost;
 	cudaGetLastError();
-	if (pinned) { MCB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return MCB_OK; }
+	if (pinned) { MCB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); return MCB_OK; }
 	const size_t CH = 16u << 20;
 	MCB_TRY(ctx->h_stage.ensure(2 * CH));
 	cudaEvent_t ev[2];
@@ -122,8 +130,8 @@ int mcb_h2d(mcb_ctx *ctx, void *dst, const void *src, size_t bytes, int n_thread
 		char *st = ctx->h_stage.as<char>() + (size_t)slot * CH;
 		cudaEventSynchronize(ev[slot]);
 		par_memcpy(st, (const char*)src + o, len, n_threads);
-		if (cudaMemcpyAsync((char*)dst + o, st, len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { mcb_set_error("h2d staging copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = MCB_ECUDA; break; }
-		cudaEventRecord(ev[slot], ctx->stream);
+		if (cudaMemcpyAsync((char*)dst + o, st, len, cudaMemcpyHostToDevice, stream) != cudaSuccess) { mcb_set_error("h2d staging copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = MCB_ECUDA; break; }
+		cudaEventRecord(ev[slot], stream);
 	}
 	cudaEventSynchronize(ev[0]); cudaEventSynchronize(ev[1]);
 	cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);

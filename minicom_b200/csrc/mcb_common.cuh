@@ -197,7 +197,7 @@ struct McbRealignState {
 
 struct mcb_ctx {
 	mcb_params prm;
-	cudaStream_t stream = 0, copy_stream = 0;
+	cudaStream_t stream = 0, copy_stream = 0, copy_stream2 = 0;   // compute; host->device pipeline; device->host pipeline
 	int sm_count = 148;
 	McbTimers tm;
 	// geometry
@@ -426,6 +426,8 @@ int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t 
 // host -> device copy that is a true DMA whatever the source: page-locked sources go in one piece, pageable ones are staged
 // through pinned chunks filled by n_threads host threads while the previous chunk is in flight (mcb_api.cu)
 int mcb_h2d(mcb_ctx *ctx, void *dst, const void *src, size_t bytes, int n_threads);
+int mcb_h2d_on(mcb_ctx *ctx, cudaStream_t stream, void *dst, const void *src, size_t bytes, int n_threads);
+int mcb_copy_streams(mcb_ctx *ctx);   // creates copy_stream / copy_stream2 on first use
 
 static inline unsigned mcb_grid_for(uint64_t n, unsigned block, unsigned cap = 0x7FFFFFFFu)
 {

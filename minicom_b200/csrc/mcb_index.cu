@@ -8,6 +8,7 @@
 // data-dependent cycle walk on one lane, histograms / small-segment sorts / CSR construction on all lanes.
 // The hash table of the reference (khash) is replaced by sorted distinct keys per bucket + CSR postings.
 #include "mcb_common.cuh"
+#include <chrono>
 #include <stdlib.h>
 #include <thread>
 #include <algorithm>
@@ -415,6 +416,255 @@ static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mc
 	return MCB_OK;
 }
 
+// ---------------------------------------------------------------- build
+// The tuples cross PCIe in (16 B each) and the postings and keys cross it out (8 + 12 B), and both dwarf the sort itself.  The
+// build can therefore be cut into runs of buckets (MCB_IX_RUNS, at least a million tuples each): run c is uploaded on one copy
+// stream, sorted and turned into keys/postings on the compute stream, and downloaded on a second copy stream while run c+1 is
+// on its way in.  Key numbers are global: a device-side chain carries the distinct-key count from run to run (chain[c] = first
+// key of run c).  Measured on C2 (seven builds of 1-7 M tuples per step, r2c): six runs save 1.8 ms of the 17.9 ms host time of
+// the builds but triple their device time (a third of the buckets no longer fills the SMs with one warp per bucket), so the
+// default is ONE run; the knob is for hosts whose builds are tens of millions of tuples.
+// distinct keys of every (sorted) bucket: one warp per bucket
+#define IXF_WARPS 8
+__global__ void __launch_bounds__(IXF_WARPS * 32)
+k_ix_count(const mcb_tuple *__restrict__ t, const uint64_t *__restrict__ boff, int nb, uint32_t *__restrict__ cntk)
+{
+	const int lane = threadIdx.x & 31, bk = blockIdx.x * IXF_WARPS + (threadIdx.x >> 5);
+	if (bk >= nb) return;
+	const uint64_t B0 = boff[bk], n = boff[bk + 1] - B0;
+	uint32_t tot = 0;
+	for (uint64_t i0 = 0; i0 < n; i0 += 32) {
+		const uint64_t i = i0 + lane;
+		const bool head = i < n && (i == 0 || t[B0 + i].x != t[B0 + i - 1].x);
+		tot += __popc(__ballot_sync(0xFFFFFFFFu, head));
+	}
+	if (lane == 0) cntk[bk] = tot;
+}
+// first key number of every bucket of a run: exclusive scan of the counts (one CTA; a run has at most 2^b buckets) on top of
+// the keys of the earlier runs (chain[c]); chain[c+1] = first key of the next run
+__global__ void __launch_bounds__(1024)
+k_ix_scan_run(const uint32_t *__restrict__ cntk, int b0, int b1, unsigned long long *__restrict__ chain, int c, uint32_t *__restrict__ ub, int nb_total_if_last)
+{
+	__shared__ uint32_t wtot[32], wexc[32];
+	__shared__ uint32_t carry_s, tile_total;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	if (threadIdx.x == 0) carry_s = (uint32_t)chain[c];
+	__syncthreads();
+	for (int base = b0; base < b1; base += 1024) {
+		const int bidx = base + threadIdx.x;
+		const uint32_t v = bidx < b1 ? cntk[bidx] : 0u;
+		uint32_t inc = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
+		if (lane == 31) wtot[wid] = inc;
+		__syncthreads();
+		if (wid == 0) {
+			const uint32_t w = wtot[lane];
+			uint32_t winc = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, winc, o); if (lane >= o) winc += x; }
+			wexc[lane] = winc - w;
+			if (lane == 31) tile_total = winc;
+		}
+		__syncthreads();
+		const uint32_t carry = carry_s;
+		if (bidx < b1) ub[bidx] = carry + wexc[wid] + inc - v;
+		__syncthreads();
+		if (threadIdx.x == 0) carry_s = carry + tile_total;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		chain[c + 1] = carry_s;
+		if (nb_total_if_last >= 0) ub[nb_total_if_last] = carry_s;
+	}
+}
+// keys, posting offsets and postings of every bucket: one warp per bucket
+__global__ void __launch_bounds__(IXF_WARPS * 32)
+k_ix_finalize(const mcb_tuple *__restrict__ t, const uint64_t *__restrict__ boff, int nb, const uint32_t *__restrict__ ub,
+              uint64_t *__restrict__ keys, uint32_t *__restrict__ kstart, uint64_t *__restrict__ post)
+{
+	const int lane = threadIdx.x & 31, bk = blockIdx.x * IXF_WARPS + (threadIdx.x >> 5);
+	if (bk >= nb) return;
+	const uint64_t B0 = boff[bk], n = boff[bk + 1] - B0;
+	uint32_t at = ub[bk];
+	for (uint64_t i0 = 0; i0 < n; i0 += 32) {
+		const uint64_t i = i0 + lane;
+		mcb_tuple e; e.x = 0; e.y = 0;
+		bool head = false;
+		if (i < n) { e = t[B0 + i]; head = i == 0 || e.x != t[B0 + i - 1].x; post[B0 + i] = e.y; }
+		const unsigned m = __ballot_sync(0xFFFFFFFFu, head);
+		if (head) { const uint32_t u = at + __popc(m & ((1u << lane) - 1u)); keys[u] = e.x; kstart[u] = (uint32_t)(B0 + i); }
+		at += __popc(m);
+	}
+}
+
+struct IxSource {            // where the tuples of a bucket range come from
+	const mcb_tuple *flat = nullptr;                                    // bucket-major array, or
+	const mcb_tuple *const *ptrs = nullptr; const uint64_t *cnt = nullptr; // one array per bucket (mm_idx_t::B[i].a), gathered through `stage`
+	mcb_tuple *stage = nullptr; int n_threads = 1;
+};
+
+struct IxEvPair { cudaEvent_t a, b; };
+static void ix_timer_add(mcb_ctx *ctx, const char *name, std::vector<IxEvPair> &v)
+{
+	float tot = 0;
+	for (auto &p : v) { float ms = 0; if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) tot += ms; else cudaGetLastError(); cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+	if (ctx->tm.enabled && !v.empty()) { int id = ctx->tm.id(name); ctx->tm.ms[id] += tot; ctx->tm.cnt[id] += 1; }
+	v.clear();
+}
+
+static int idx_build_pipelined(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, const IxSource &src, mcb_index **out)
+{
+	const int b = ctx->prm.b, nb = 1 << b;
+	mcb_index *ix = new mcb_index(); ix->b = b; ix->n_post = n;
+	*out = ix;
+	if (n == 0) {
+		MCB_TRY(idx_alloc_host(ctx, ix, 0, 0, nb));
+		memset(ix->ub, 0, ((size_t)nb + 1) * 4); ix->kstart[0] = 0;
+		return MCB_OK;
+	}
+	if (n >= 0xFFFFFFFFull) { mcb_set_error("index too large"); return MCB_EINVAL; }
+	MCB_TRY(mcb_copy_streams(ctx));
+	// ---- runs of buckets
+	static const int max_runs = getenv("MCB_IX_RUNS") ? std::max(1, std::min(16, atoi(getenv("MCB_IX_RUNS")))) : 1;   // tuning knob, see above
+	const int C = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)max_runs, n >> 20));
+	std::vector<int> cb((size_t)C + 1);
+	cb[0] = 0; cb[C] = nb;
+	for (int c = 1; c < C; ++c) {
+		const uint64_t target = n / C * c;
+		int q = (int)(std::lower_bound(h_boff, h_boff + nb + 1, target) - h_boff);
+		cb[c] = std::max(cb[c - 1], std::min(q, nb));
+	}
+	MCB_TRY(ctx->d_scr[0].ensure(n * 16 + 16));
+	MCB_TRY(ctx->d_scr[1].ensure(((size_t)nb + 1) * 8));
+	MCB_TRY(ctx->d_scr[2].ensure((n / 65 + 8ull * nb + 8) * sizeof(IxSeg)));
+	MCB_TRY(ctx->d_scr[3].ensure(((size_t)nb + 2) * 4)); // distinct keys per bucket
+	MCB_TRY(ctx->d_scr[4].ensure(n * 8 + 16));           // keys (<= n)
+	MCB_TRY(ctx->d_scr[5].ensure((n + 2) * 4));          // kstart
+	MCB_TRY(ctx->d_scr[6].ensure(n * 8 + 16));           // postings
+	MCB_TRY(ctx->d_scr[7].ensure(((size_t)nb + 2) * 4)); // ub
+	MCB_TRY(ctx->d_scr[9].ensure((2 * (size_t)C + 2) * 8));
+	MCB_TRY(ctx->h_in2.ensure((2 * (size_t)C + 2) * 8));
+	mcb_tuple *dt = ctx->d_scr[0].as<mcb_tuple>();
+	uint64_t *d_boff = ctx->d_scr[1].as<uint64_t>();
+	uint32_t *d_flag = ctx->d_scr[3].as<uint32_t>();
+	unsigned long long *d_chain = ctx->d_scr[9].as<unsigned long long>();
+	volatile unsigned long long *h_chain = ctx->h_in2.as<unsigned long long>();
+	MCB_TRY(mcb_h2d(ctx, d_boff, h_boff, ((size_t)nb + 1) * 8, 1));
+	MCB_CUDA(cudaMemsetAsync(d_chain, 0, (2 * (size_t)C + 2) * 8, ctx->stream));
+	MCB_TRY(idx_alloc_host(ctx, ix, n, n, nb));           // the number of distinct keys is not known yet: room for n
+	// ---- sort kernel configuration (the same for all runs)
+	uint64_t maxb = 0;
+	for (int i = 0; i < nb; ++i) maxb = std::max<uint64_t>(maxb, h_boff[i + 1] - h_boff[i]);
+	static const bool force_old = getenv("MCB_IX_OLD") != nullptr;
+	if (getenv("MCB_IX_DEBUG")) fprintf(stderr, "[mcb] idx build: n=%llu max bucket=%llu runs=%d\n", (unsigned long long)n, (unsigned long long)maxb, C);
+	bool walk = false; uint32_t cap = 0; size_t smem3 = 0;
+	if (maxb <= 65000 && !force_old) {      // index-space walk: 3 bytes of shared memory per tuple of the largest bucket
+		cap = (uint32_t)std::max<uint64_t>(64, (maxb + 63) & ~63ull);
+		const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * 3 + 15) & ~(size_t)15;
+		smem3 = per_warp * IX2_WARPS;
+		if (smem3 <= 220 * 1024) {
+			walk = true;
+			MCB_TRY(ctx->d_scr[8].ensure(n * 16 + 16));
+			if (smem3 > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_index_sort3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+		}
+	}
+	const size_t ix_smem = IX_WARPS * 2048 + IX_WARPS * IX_SMEM_STK * sizeof(IxSeg) + (size_t)IX_WARPS * IX_SMEM_CAP * sizeof(mcb_tuple);
+	if (!walk) MCB_CUDA(cudaFuncSetAttribute(k_index_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix_smem));
+	std::vector<cudaEvent_t> evH((size_t)C), evC((size_t)C);
+	for (int c = 0; c < C; ++c) { cudaEventCreateWithFlags(&evH[c], cudaEventDisableTiming); cudaEventCreateWithFlags(&evC[c], cudaEventDisableTiming); }
+	std::vector<IxEvPair> t_h2d, t_d2h;
+	auto timed = [&](std::vector<IxEvPair> &v, cudaStream_t st, bool begin) {
+		if (!ctx->tm.enabled) return;
+		if (begin) { IxEvPair p; cudaEventCreate(&p.a); cudaEventCreate(&p.b); cudaEventRecord(p.a, st); v.push_back(p); }
+		else cudaEventRecord(v.back().b, st);
+	};
+	int rc = MCB_OK;
+	static const bool dbg = getenv("MCB_IX_DEBUG") != nullptr;
+	auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double T0 = dbg ? now_ms() : 0;
+	auto flush_keys = [&](int c) -> int {      // keys of run c to the host (their position needs chain[c], chain[c+1])
+		MCB_CUDA(cudaEventSynchronize(evC[c]));
+		const uint64_t k0 = h_chain[c], k1 = h_chain[c + 1];
+		if (k1 > k0) {
+			timed(t_d2h, ctx->copy_stream2, true);
+			MCB_CUDA(cudaMemcpyAsync(ix->keys + k0, ctx->d_scr[4].as<uint64_t>() + k0, (k1 - k0) * 8, cudaMemcpyDeviceToHost, ctx->copy_stream2));
+			MCB_CUDA(cudaMemcpyAsync(ix->kstart + k0, ctx->d_scr[5].as<uint32_t>() + k0, (k1 - k0) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream2));
+			timed(t_d2h, ctx->copy_stream2, false);
+		}
+		return MCB_OK;
+	};
+	auto run = [&](int c) -> int {
+		const int b0 = cb[c], b1 = cb[c + 1];
+		const uint64_t t0 = h_boff[b0], t1 = h_boff[b1], nc = t1 - t0;
+		if (nc) {
+			if (src.flat) {
+				timed(t_h2d, ctx->copy_stream, true);
+				MCB_TRY(mcb_h2d_on(ctx, ctx->copy_stream, dt + t0, src.flat + t0, nc * 16, 4));
+				timed(t_h2d, ctx->copy_stream, false);
+			} else {
+				const int T = std::max(1, std::min(src.n_threads, (int)(nc / 65536) + 1));
+				auto work = [&](int q0, int q1) { for (int i = q0; i < q1; ++i) if (src.cnt[i]) memcpy(src.stage + h_boff[i], src.ptrs[i], src.cnt[i] * 16); };
+				if (T == 1) work(b0, b1);
+				else {
+					std::vector<std::thread> th;
+					for (int t = 0; t < T; ++t) th.emplace_back(work, b0 + (int)((int64_t)(b1 - b0) * t / T), b0 + (int)((int64_t)(b1 - b0) * (t + 1) / T));
+					for (auto &x : th) x.join();
+				}
+				timed(t_h2d, ctx->copy_stream, true);
+				MCB_CUDA(cudaMemcpyAsync(dt + t0, src.stage + t0, nc * 16, cudaMemcpyHostToDevice, ctx->copy_stream));
+				timed(t_h2d, ctx->copy_stream, false);
+			}
+		}
+		MCB_CUDA(cudaEventRecord(evH[c], ctx->copy_stream));
+		MCB_CUDA(cudaStreamWaitEvent(ctx->stream, evH[c], 0));
+		{
+			McbSpan sp(ctx->tm, "idx_build");
+			if (nc) {
+				if (walk) MCB_LAUNCH(ctx, "index_sort", k_index_sort3, mcb_grid_for(b1 - b0, IX2_WARPS), IX2_WARPS * 32, smem3, dt, ctx->d_scr[8].as<mcb_tuple>(), d_boff + b0, b1 - b0, cap,
+				                     ctx->d_scr[2].as<IxSeg>());
+				else MCB_LAUNCH(ctx, "index_sort", k_index_sort, mcb_grid_for(b1 - b0, IX_WARPS), IX_WARPS * 32, ix_smem, dt, d_boff + b0, b1 - b0, ctx->d_scr[2].as<IxSeg>());
+				MCB_LAUNCH(ctx, "ix_count", k_ix_count, mcb_grid_for(b1 - b0, IXF_WARPS), IXF_WARPS * 32, 0, dt, d_boff + b0, b1 - b0, d_flag + b0);
+			} else MCB_CUDA(cudaMemsetAsync(d_flag + b0, 0, (size_t)(b1 - b0) * 4, ctx->stream));
+			MCB_LAUNCH(ctx, "ix_scan", k_ix_scan_run, 1, 1024, 0, d_flag, b0, b1, d_chain, c, ctx->d_scr[7].as<uint32_t>(), c == C - 1 ? nb : -1);
+			if (nc) MCB_LAUNCH(ctx, "ix_finalize", k_ix_finalize, mcb_grid_for(b1 - b0, IXF_WARPS), IXF_WARPS * 32, 0, dt, d_boff + b0, b1 - b0, ctx->d_scr[7].as<uint32_t>() + b0,
+			                   ctx->d_scr[4].as<uint64_t>(), ctx->d_scr[5].as<uint32_t>(), ctx->d_scr[6].as<uint64_t>());
+		}
+		MCB_CUDA(cudaMemcpyAsync((void*)h_chain, d_chain, (2 * (size_t)C + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaEventRecord(evC[c], ctx->stream));
+		MCB_CUDA(cudaStreamWaitEvent(ctx->copy_stream2, evC[c], 0));
+		if (nc) {
+			timed(t_d2h, ctx->copy_stream2, true);
+			MCB_CUDA(cudaMemcpyAsync(ix->post + t0, ctx->d_scr[6].as<uint64_t>() + t0, nc * 8, cudaMemcpyDeviceToHost, ctx->copy_stream2));
+			timed(t_d2h, ctx->copy_stream2, false);
+		}
+		if (c >= 1) MCB_TRY(flush_keys(c - 1));
+		return MCB_OK;
+	};
+	for (int c = 0; c < C && rc == MCB_OK; ++c) { rc = run(c); if (dbg) fprintf(stderr, "[mcb] idx run %d queued at +%.3f ms\n", c, now_ms() - T0); }
+	if (rc == MCB_OK) rc = flush_keys(C - 1);
+	if (rc == MCB_OK) {
+		timed(t_d2h, ctx->copy_stream2, true);
+		if (cudaMemcpyAsync(ix->ub, ctx->d_scr[7].p, ((size_t)nb + 1) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream2) != cudaSuccess) { mcb_set_error("index d2h failed: %s", cudaGetErrorString(cudaGetLastError())); rc = MCB_ECUDA; }
+		timed(t_d2h, ctx->copy_stream2, false);
+	}
+	if (dbg) fprintf(stderr, "[mcb] idx all queued at +%.3f ms\n", now_ms() - T0);
+	cudaStreamSynchronize(ctx->copy_stream); if (dbg) fprintf(stderr, "[mcb] idx h2d done +%.3f ms\n", now_ms() - T0);
+	cudaStreamSynchronize(ctx->stream); if (dbg) fprintf(stderr, "[mcb] idx compute done +%.3f ms\n", now_ms() - T0);
+	cudaStreamSynchronize(ctx->copy_stream2); if (dbg) fprintf(stderr, "[mcb] idx d2h done +%.3f ms\n", now_ms() - T0);
+	for (int c = 0; c < C; ++c) { cudaEventDestroy(evH[c]); cudaEventDestroy(evC[c]); }
+	ix_timer_add(ctx, "h2d", t_h2d); ix_timer_add(ctx, "d2h", t_d2h);
+	ctx->tm.collect();
+	if (rc != MCB_OK) return rc;
+	{ cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { mcb_set_error("index build failed: %s", cudaGetErrorString(e)); return MCB_ECUDA; } }
+	const uint64_t U = h_chain[C];
+	ix->n_keys = U;
+	ix->kstart[U] = (uint32_t)n;
+	return MCB_OK;
+}
+
+static const bool g_ix_nopipe = getenv("MCB_IX_NOPIPE") && atoi(getenv("MCB_IX_NOPIPE"));   // debugging: one upload, one sort, one download
+
 extern "C" int mcb_idx_build(mcb_ctx *ctx, const mcb_tuple *tuples, const uint64_t *bucket_off, mcb_index **out)
 {
 	if (!ctx || !out || !bucket_off) { mcb_set_error("mcb_idx_build: null argument"); return MCB_EINVAL; }
@@ -424,12 +674,18 @@ extern "C" int mcb_idx_build(mcb_ctx *ctx, const mcb_tuple *tuples, const uint64
 	const uint64_t n = bucket_off[nb];
 	if (n && !tuples) { mcb_set_error("mcb_idx_build: null tuples"); return MCB_EINVAL; }
 	MCB_TRY(ctx->d_counters.ensure(64 * 8));
-	MCB_TRY(ctx->d_scr[0].ensure(n * 16 + 16));
-	if (n) {
-		McbSpan sp(ctx->tm, "h2d");
-		MCB_TRY(mcb_h2d(ctx, ctx->d_scr[0].p, tuples, n * 16, 4));
+	int r;
+	if (!g_ix_nopipe) {
+		IxSource src; src.flat = tuples;
+		r = idx_build_pipelined(ctx, n, bucket_off, src, out);
+	} else {
+		MCB_TRY(ctx->d_scr[0].ensure(n * 16 + 16));
+		if (n) {
+			McbSpan sp(ctx->tm, "h2d");
+			MCB_TRY(mcb_h2d(ctx, ctx->d_scr[0].p, tuples, n * 16, 4));
+		}
+		r = idx_build_device(ctx, n, bucket_off, out);
 	}
-	int r = idx_build_device(ctx, n, bucket_off, out);
 	if (r != MCB_OK) { mcb_idx_destroy(*out); *out = nullptr; }
 	return r;
 }
@@ -447,6 +703,13 @@ extern "C" int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptr
 	boff[nb] = n;
 	MCB_TRY(ctx->h_in0.ensure(n * 16 + 16));
 	mcb_tuple *flat = ctx->h_in0.as<mcb_tuple>();
+	MCB_TRY(ctx->d_counters.ensure(64 * 8));
+	if (!g_ix_nopipe) {
+		IxSource src; src.ptrs = ptrs; src.cnt = cnt; src.stage = flat; src.n_threads = n_threads;
+		int r = idx_build_pipelined(ctx, n, boff, src, out);
+		if (r != MCB_OK) { mcb_idx_destroy(*out); *out = nullptr; }
+		return r;
+	}
 	{   // gather the bucket arrays into one pinned block, n_threads host threads over contiguous bucket ranges
 		const int T = std::max(1, std::min(n_threads, (int)(n / 65536) + 1));
 		auto work = [&](int b0, int b1) { for (int i = b0; i < b1; ++i) if (cnt[i]) memcpy(flat + boff[i], ptrs[i], cnt[i] * 16); };

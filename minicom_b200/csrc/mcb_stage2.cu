@@ -607,11 +607,21 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	const size_t refs_pad = (ref_bytes + 7) & ~(size_t)7;
 	MCB_TRY(stage_refs.ensure(refs_pad + 16)); MCB_TRY(stage_off.ensure((n_contigs + 1) * 8));
 	cx.valid = cx.valid && maybe_same;
-	{
-		McbSpan sp(ctx->tm, "h2d");
-		if (refs_pad > ref_bytes) MCB_CUDA(cudaMemsetAsync(stage_refs.as<char>() + (refs_pad - 8), 0, 8, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(stage_refs.p, refs, ref_bytes, cudaMemcpyHostToDevice, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(stage_off.p, ref_off, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	{   // the contig strings go up on the copy stream: the singles kernels already queued on the compute stream run meanwhile
+		MCB_TRY(mcb_copy_streams(ctx));
+		cudaEvent_t e0, e1;
+		cudaEventCreate(&e0); cudaEventCreate(&e1);
+		cudaEventRecord(e0, ctx->copy_stream);                         // (every earlier call has synchronized: nothing else touches these buffers)
+		if (refs_pad > ref_bytes) MCB_CUDA(cudaMemsetAsync(stage_refs.as<char>() + (refs_pad - 8), 0, 8, ctx->copy_stream));
+		MCB_TRY(mcb_h2d_on(ctx, ctx->copy_stream, stage_refs.p, refs, ref_bytes, 4));
+		MCB_TRY(mcb_h2d_on(ctx, ctx->copy_stream, stage_off.p, ref_off, (n_contigs + 1) * 8, 1));
+		cudaEventRecord(e1, ctx->copy_stream);
+		MCB_CUDA(cudaStreamWaitEvent(ctx->stream, e1, 0));
+		if (ctx->tm.enabled) {
+			cudaEventSynchronize(e1);
+			float ms = 0; if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) { int id = ctx->tm.id("h2d"); ctx->tm.ms[id] += ms; ctx->tm.cnt[id] += 1; }
+		}
+		cudaEventDestroy(e0); cudaEventDestroy(e1);
 	}
 	if (maybe_same) {
 		McbSpan sp(ctx->tm, "realign");
@@ -855,6 +865,24 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
 	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
 	MCB_CUDA(cudaMemsetAsync(dc + 16, 0, 16 * 8, ctx->stream));
+	// ---- singles first: they do not depend on the contigs, and the contig upload (copy stream) overlaps them
+	const uint64_t nkv = S * (uint64_t)gm.nd;
+	if (nkv >= 0xFFFFFFFFull) { mcb_set_error("dictionary too large"); return MCB_EINVAL; }
+	DBuf &b_sg = ctx->d_scr[0], &b_cm = ctx->d_scr[5], &b_rd = ctx->d_scr[6], &b_fl = ctx->d_scr[8];
+	MCB_TRY(b_sg.ensure(S * 4 + 16)); MCB_TRY(b_rd.ensure(S * WS * 8 + 16)); MCB_TRY(b_fl.ensure(S + 16));
+	if (nkv) {
+		uint64_t CM = 1024; while (CM < 2 * nkv && CM < (1ull << 28)) CM <<= 1;
+		MCB_TRY(b_cm.ensure(CM * 4));
+		{
+			McbSpan sp(ctx->tm, "h2d");
+			MCB_CUDA(cudaMemcpyAsync(b_sg.p, sg, S * 4, cudaMemcpyHostToDevice, ctx->stream));
+		}
+		McbSpan span(ctx->tm, "realign");
+		MCB_CUDA(cudaMemsetAsync(b_cm.p, 0, CM * 4, ctx->stream));
+		MCB_LAUNCH(ctx, "s2_singles", k_s2_singles, mcb_grid_for(S, 128), 128, 0, b_sg.as<uint32_t>(), S, ctx->d_packed.as<uint64_t>(), gm,
+		           ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->n_nreads, ctx->n_reads,
+		           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, tab_rank, tab_ranks, dc);
+	}
 	// ---- contigs: refs == NULL reuses the contigs (and their table) of the previous call
 	McbContigIndex &cx = ctx->cix;
 	if (refs || ref_off) {
@@ -871,28 +899,14 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 		int nrev = 0; for (int l = 0; l < gm.nd; ++l) nrev += gm.dstart[l] > 0;
 		res->n_probes = n_windows * (uint64_t)(gm.nd + nrev);                 // what the reference's window loop would issue (:355-504)
 	}
-	const uint64_t nkv = S * (uint64_t)gm.nd;
 	ctx->rs.pending = true; ctx->rs.S = S; ctx->rs.window_base = window_base; ctx->rs.nd = gm.nd;
 	if (tab_ranks > 1) { ctx->rs.g_lo = g_lo; ctx->rs.g_hi = g_hi; ctx->rs.g_sub = 0; }
 	else { ctx->rs.g_lo = window_base; ctx->rs.g_hi = window_base + n_windows; ctx->rs.g_sub = window_base; }
 	MCB_TRY(ctx->d_x[0].ensure(S * 8 + 16));                   // claim priorities
 	unsigned long long *claim = ctx->d_x[0].as<unsigned long long>();
 	if (S) MCB_CUDA(cudaMemsetAsync(claim, 0x7F, S * 8, ctx->stream));          // MCB_CLAIM_NONE
-	DBuf &b_sg = ctx->d_scr[0], &b_cm = ctx->d_scr[5], &b_rd = ctx->d_scr[6], &b_fl = ctx->d_scr[8];
-	MCB_TRY(b_sg.ensure(S * 4 + 16)); MCB_TRY(b_rd.ensure(S * WS * 8 + 16)); MCB_TRY(b_fl.ensure(S + 16));
 	if (S == 0 || gm.nd == 0) return MCB_OK;
-	if (nkv >= 0xFFFFFFFFull) { mcb_set_error("dictionary too large"); return MCB_EINVAL; }
-	uint64_t CM = 1024; while (CM < 2 * nkv && CM < (1ull << 28)) CM <<= 1;
-	MCB_TRY(b_cm.ensure(CM * 4));
-	{
-		McbSpan sp(ctx->tm, "h2d");
-		MCB_CUDA(cudaMemcpyAsync(b_sg.p, sg, S * 4, cudaMemcpyHostToDevice, ctx->stream));
-	}
 	McbSpan span(ctx->tm, "realign");
-	MCB_CUDA(cudaMemsetAsync(b_cm.p, 0, CM * 4, ctx->stream));
-	MCB_LAUNCH(ctx, "s2_singles", k_s2_singles, mcb_grid_for(S, 128), 128, 0, b_sg.as<uint32_t>(), S, ctx->d_packed.as<uint64_t>(), gm,
-	           ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->n_nreads, ctx->n_reads,
-	           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, tab_rank, tab_ranks, dc);
 	MCB_TRY(contig_table_update(ctx, gm, b_sg.as<uint32_t>(), S, b_rd.as<uint64_t>(), b_fl.as<uint8_t>()));
 	if (n_windows == 0) {          // no contig long enough on this rank: the diversion lists are still needed
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
