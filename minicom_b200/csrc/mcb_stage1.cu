@@ -624,8 +624,11 @@ k_consensus_bs(const ulonglong2 *__restrict__ el, const uint32_t *__restrict__ g
 }
 
 #define CONS_BS_MAX_MEMBERS 60000u
-// singletons are settled here; groups of 2..15 / 16..255 / 256..CONS_BS_MAX_MEMBERS members go to the three work lists of
-// k_consensus_bs (4, 8, 16 counter planes), larger ones to the fourth list, for k_consensus
+// singletons are settled here; groups of 2..15 / 16..255 / 256..CONS_BS_MAX_MEMBERS members go to the work lists of
+// k_consensus_bs (4, 8, 16 counter planes), larger ones to the last list, for k_consensus.  The sub-groups of a warp walk their
+// members in lock step up to the largest of them, so the 2..15 range (nearly all groups at 20x coverage) is split into seven
+// lists of nearly equal sizes: the warps of one launch then carry groups of the same length.
+#define CONS_NCLS 10
 __global__ void k_cons_worklist(const uint32_t *__restrict__ gstart, uint64_t G, ConsOut o, uint32_t *__restrict__ worklist, unsigned long long *__restrict__ counters)
 {
 	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -635,11 +638,12 @@ __global__ void k_cons_worklist(const uint32_t *__restrict__ gstart, uint64_t G,
 		if (cntm < 2) {
 			o.status[s] = 0; o.erank[s] = 0;
 			o.g_iscl[g] = 0; o.g_kept[g] = 0; o.g_sg[g] = 1; o.g_resk[g] = 0; o.g_reflen[g] = 0; o.g_refoff[g] = 0;
-		} else cls = cntm < 16 ? 0 : cntm < 256 ? 1 : cntm <= CONS_BS_MAX_MEMBERS ? 2 : 3;
+		} else cls = cntm == 2 ? 0 : cntm == 3 ? 1 : cntm == 4 ? 2 : cntm <= 6 ? 3 : cntm <= 8 ? 4 : cntm <= 11 ? 5 : cntm < 16 ? 6
+		           : cntm < 256 ? 7 : cntm <= CONS_BS_MAX_MEMBERS ? 8 : 9;
 	}
 	const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
 #pragma unroll
-	for (int c = 0; c < 4; ++c) {
+	for (int c = 0; c < CONS_NCLS; ++c) {
 		const unsigned bal = __ballot_sync(0xFFFFFFFFu, cls == c);
 		unsigned long long base = 0;
 		if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(&counters[CT_WORK0 + c], (unsigned long long)__popc(bal));
@@ -1235,20 +1239,23 @@ static int bucket_round_a(mcb_ctx *ctx, int r, int is_last)
 		// (kmer' = length of the k-mers these tuples were sketched with), so columns <= 2L + 2r - 2 - k  (+ margin)
 		const int max_cols = 2 * L + 2 * r - k + 2;
 		const int ncw = (max_cols + 31) / 32;
-		MCB_TRY(ctx->d_x[2].ensure(4 * G * 4 + 16));
+		MCB_TRY(ctx->d_x[2].ensure((size_t)CONS_NCLS * G * 4 + 16));
 		uint32_t *worklist = ctx->d_x[2].as<uint32_t>();
-		MCB_CUDA(cudaMemsetAsync(&dc[CT_WORK0], 0, 4 * 8, ctx->stream));
+		MCB_CUDA(cudaMemsetAsync(&dc[CT_WORK0], 0, CONS_NCLS * 8, ctx->stream));
 		MCB_LAUNCH(ctx, "cons_worklist", k_cons_worklist, mcb_grid_for(G, 256), 256, 0, B.b_gs.as<uint32_t>(), G, co, worklist, dc);
 		const unsigned bgrid = (unsigned)ctx->sm_count * 16;
 #define CONS_BS_LAUNCH(GWv, Kv, cls) MCB_LAUNCH(ctx, "consensus", (k_consensus_bs<GWv, Kv>), bgrid, 128, 0, cur, B.b_gs.as<uint32_t>(), worklist + (uint64_t)(cls) * G, \
 		&dc[CT_WORK0 + (cls)], ctx->d_packed.as<uint64_t>(), WS, ctx->Wd, L, ctx->prm.diff_threshold, is_last, co, dc, reftmp_cap)
-		if (ncw <= 8) { CONS_BS_LAUNCH(8, 4, 0); CONS_BS_LAUNCH(8, 8, 1); CONS_BS_LAUNCH(8, 16, 2); }
-		else if (ncw <= 16) { CONS_BS_LAUNCH(16, 4, 0); CONS_BS_LAUNCH(16, 8, 1); CONS_BS_LAUNCH(16, 16, 2); }
-		else { CONS_BS_LAUNCH(32, 4, 0); CONS_BS_LAUNCH(32, 8, 1); CONS_BS_LAUNCH(32, 16, 2); }
+		for (int cls = 0; cls < 7; ++cls) {
+			if (ncw <= 8) CONS_BS_LAUNCH(8, 4, cls); else if (ncw <= 16) CONS_BS_LAUNCH(16, 4, cls); else CONS_BS_LAUNCH(32, 4, cls);
+		}
+		if (ncw <= 8) { CONS_BS_LAUNCH(8, 8, 7); CONS_BS_LAUNCH(8, 16, 8); }
+		else if (ncw <= 16) { CONS_BS_LAUNCH(16, 8, 7); CONS_BS_LAUNCH(16, 16, 8); }
+		else { CONS_BS_LAUNCH(32, 8, 7); CONS_BS_LAUNCH(32, 16, 8); }
 #undef CONS_BS_LAUNCH
 		// groups too large for the bit-sliced counters (more than CONS_BS_MAX_MEMBERS members): the column-count kernel
 		MCB_LAUNCH(ctx, "consensus_huge", k_consensus, (unsigned)ctx->sm_count, CS_WARPS * 32, cs_smem, cur, B.b_gs.as<uint32_t>(), G, ctx->d_packed.as<uint64_t>(), WS, L,
-		           ctx->prm.diff_threshold, pbase, NC, is_last, co, dc, reftmp_cap, worklist + 3ull * G, &dc[CT_WORK0 + 3]);
+		           ctx->prm.diff_threshold, pbase, NC, is_last, co, dc, reftmp_cap, worklist + 9ull * G, &dc[CT_WORK0 + 9]);
 	}
 	// ---- bases
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, B.b_gc.as<uint32_t>(), G, (uint64_t*)&dc[CT_TOT_CL]));

@@ -871,7 +871,12 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	DBuf &b_sg = ctx->d_scr[0], &b_cm = ctx->d_scr[5], &b_rd = ctx->d_scr[6], &b_fl = ctx->d_scr[8];
 	MCB_TRY(b_sg.ensure(S * 4 + 16)); MCB_TRY(b_rd.ensure(S * WS * 8 + 16)); MCB_TRY(b_fl.ensure(S + 16));
 	if (nkv) {
-		uint64_t CM = 1024; while (CM < 2 * nkv && CM < (1ull << 28)) CM <<= 1;
+		// count-min sketch of the bin sizes: it only has to bound the largest bin from above (a bound above maxsearch sends the call
+		// through the exact count), so about one counter per two (single, dictionary) pairs is enough, and at that size (32 MB
+		// for 15 M pairs) the atomics resolve in L2 instead of DRAM
+		static const int cm_shift = getenv("MCB_S2_CM") ? atoi(getenv("MCB_S2_CM")) : -1;
+		const uint64_t cm_want = cm_shift >= 0 ? nkv << cm_shift : nkv >> -cm_shift;
+		uint64_t CM = 1024; while (CM < cm_want && CM < (1ull << 26)) CM <<= 1;
 		MCB_TRY(b_cm.ensure(CM * 4));
 		{
 			McbSpan sp(ctx->tm, "h2d");
