@@ -641,15 +641,26 @@ __global__ void k_cons_worklist(const uint32_t *__restrict__ gstart, uint64_t G,
 		} else cls = cntm == 2 ? 0 : cntm == 3 ? 1 : cntm == 4 ? 2 : cntm <= 6 ? 3 : cntm <= 8 ? 4 : cntm <= 11 ? 5 : cntm < 16 ? 6
 		           : cntm < 256 ? 7 : cntm <= CONS_BS_MAX_MEMBERS ? 8 : 9;
 	}
-	const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+	// one atomic per list and CTA: warp ballots -> per-warp counts in shared memory -> offsets inside the CTA
+	__shared__ unsigned long long cta_base[CONS_NCLS];
+	__shared__ uint32_t wcnt[8][CONS_NCLS];                  // launched with 256 threads
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	unsigned mybal = 0;
 #pragma unroll
 	for (int c = 0; c < CONS_NCLS; ++c) {
 		const unsigned bal = __ballot_sync(0xFFFFFFFFu, cls == c);
-		unsigned long long base = 0;
-		if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(&counters[CT_WORK0 + c], (unsigned long long)__popc(bal));
-		base = __shfl_sync(0xFFFFFFFFu, base, 0);
-		if (cls == c) worklist[(uint64_t)c * G + base + __popc(bal & lt)] = (uint32_t)g;
+		if (lane == 0) wcnt[wid][c] = __popc(bal);
+		if (cls == c) mybal = bal;
 	}
+	__syncthreads();
+	if (threadIdx.x < CONS_NCLS) {
+		const int c = threadIdx.x;
+		uint32_t tot = 0;
+		for (int w = 0; w < 8; ++w) { const uint32_t v = wcnt[w][c]; wcnt[w][c] = tot; tot += v; }
+		cta_base[c] = tot ? atomicAdd(&counters[CT_WORK0 + c], (unsigned long long)tot) : 0ull;
+	}
+	__syncthreads();
+	if (cls >= 0) worklist[(uint64_t)cls * G + cta_base[cls] + wcnt[wid][cls] + __popc(mybal & ((1u << lane) - 1u))] = (uint32_t)g;
 }
 
 // scatter per element into the compact outputs (bases come from exclusive scans over the group arrays)

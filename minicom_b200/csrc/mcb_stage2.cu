@@ -155,13 +155,13 @@ __device__ __forceinline__ uint64_t rev_fields(uint64_t v, int nbases)
 	return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
 }
 __global__ void k_s2_filter_insert(const uint64_t *__restrict__ rd, const uint8_t *__restrict__ flagged, const uint32_t *__restrict__ sg, uint64_t S, S2Geom gm,
-                                   uint32_t *__restrict__ flt, uint64_t wmask, uint32_t *__restrict__ sgmap)
+                                   uint32_t *__restrict__ flt, uint64_t wmask, uint32_t *__restrict__ sgmap, uint32_t o_lo, uint32_t o_hi)
 {
 	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= S * (uint64_t)gm.nd) return;
 	const int l = (int)(idx / S); const uint64_t s = idx - (uint64_t)l * S;
 	if (l == 0) { const uint32_t rid = sg[s]; atomicOr(&sgmap[rid >> 5], 1u << (rid & 31)); }
-	if (flagged[s]) return;
+	(void)flagged;          // diverted singles are inserted too: whether a single is diverted depends on the round's threshold
 	const uint64_t *row = rd + s * gm.WS;
 	const int lt = gm.lt, ds = gm.dstart[l];
 	const uint64_t kmask = (1ull << (2 * lt)) - 1;
@@ -170,8 +170,14 @@ __global__ void k_s2_filter_insert(const uint64_t *__restrict__ rd, const uint8_
 	if (sh + 2 * lt > 64) v |= row[wi + 1] << (64 - sh);
 	const uint64_t key_f = v & kmask;
 	uint64_t w; uint32_t b;
-	flt_slot(key_f, wmask, &w, &b); atomicOr(&flt[w], b);
-	if (ds > 0) { flt_slot(rev_fields(~key_f & kmask, lt), wmask, &w, &b); atomicOr(&flt[w], b); }
+	// key-sharded table: only the keys whose lt-mers this context keeps (the same top-16-bit hash range k_s2_kmer_emit tests)
+	uint32_t ob = kmer_bucket(key_f, 16);
+	if (ob >= o_lo && ob < o_hi) { flt_slot(key_f, wmask, &w, &b); atomicOr(&flt[w], b); }
+	if (ds > 0) {
+		const uint64_t key_r = rev_fields(~key_f & kmask, lt);
+		ob = kmer_bucket(key_r, 16);
+		if (ob >= o_lo && ob < o_hi) { flt_slot(key_r, wmask, &w, &b); atomicOr(&flt[w], b); }
+	}
 }
 // are all these singles among the ones the filter was built from?
 __global__ void k_s2_sg_subset(const uint32_t *__restrict__ sg, uint64_t S, const uint32_t *__restrict__ sgmap, unsigned long long *__restrict__ counters)
@@ -685,19 +691,20 @@ static int contig_table_update(mcb_ctx *ctx, const S2Geom &gm, const uint32_t *d
 	const uint64_t n_all = cx.n_entries;          // all lt-mer start positions of the contigs that have a window
 	const uint64_t nkv = S * (uint64_t)gm.nd;
 	const bool filtered = use_filter;
+	// ownership of the key space among the ranks is fixed on the top 16 hash bits, so every rank may size its own bucket table
+	const uint32_t o_lo = (uint32_t)((((uint64_t)tab_rank << 16) + tab_ranks - 1) / tab_ranks), o_hi = (uint32_t)((((uint64_t)(tab_rank + 1) << 16) + tab_ranks - 1) / tab_ranks);
 	uint64_t wmask = 0;
 	if (filtered) {
 		static const int flt_shift = getenv("MCB_S2_FLT") ? atoi(getenv("MCB_S2_FLT")) : -1;             // tuning knob: filter words per (single, dictionary), log2
-		const uint64_t want = flt_shift >= 0 ? nkv << flt_shift : nkv >> -flt_shift;
+		const uint64_t nkv_own = nkv / (uint64_t)tab_ranks + 1;
+		const uint64_t want = flt_shift >= 0 ? nkv_own << flt_shift : nkv_own >> -flt_shift;
 		uint64_t W = 1024; while (W < want && W < (1ull << 28)) W <<= 1;
 		MCB_TRY(cx.flt.ensure(W * 4)); MCB_TRY(cx.sgmap.ensure((ctx->n_reads / 32 + 2) * 4));
 		MCB_CUDA(cudaMemsetAsync(cx.flt.p, 0, W * 4, ctx->stream));
 		MCB_CUDA(cudaMemsetAsync(cx.sgmap.p, 0, (ctx->n_reads / 32 + 2) * 4, ctx->stream));
 		wmask = W - 1; cx.flt_words = W;
-		if (nkv) MCB_LAUNCH(ctx, "s2_filter_insert", k_s2_filter_insert, mcb_grid_for(nkv, 256), 256, 0, d_rd, d_fl, d_sg, S, gm, cx.flt.as<uint32_t>(), wmask, cx.sgmap.as<uint32_t>());
+		if (nkv) MCB_LAUNCH(ctx, "s2_filter_insert", k_s2_filter_insert, mcb_grid_for(nkv, 256), 256, 0, d_rd, d_fl, d_sg, S, gm, cx.flt.as<uint32_t>(), wmask, cx.sgmap.as<uint32_t>(), o_lo, o_hi);
 	}
-	// ownership of the key space among the ranks is fixed on the top 16 hash bits, so every rank may size its own bucket table
-	const uint32_t o_lo = (uint32_t)((((uint64_t)tab_rank << 16) + tab_ranks - 1) / tab_ranks), o_hi = (uint32_t)((((uint64_t)(tab_rank + 1) << 16) + tab_ranks - 1) / tab_ranks);
 	const bool compacting = filtered || tab_ranks > 1;
 	uint64_t ents_cap = !compacting ? n_all : (filtered ? n_all / (4 * tab_ranks) : n_all / tab_ranks + n_all / (4 * tab_ranks)) + (1u << 20);
 	if (ents_cap > n_all) ents_cap = n_all;
