@@ -409,8 +409,9 @@ MCB_HD uint64_t mcb_sketch_two_packed(const uint64_t *row, int L, int k, int *po
 	return mcb_sketch_two_packed_t<false, false>(row, L, k, pos_out, strand_out);
 }
 
-// Stage-2 contig table entries: lt-mer << 30 | global base position; buckets by a multiplicative hash of the lt-mer
-#define MCB_S2_POS_BITS 30
+// Stage-2 contig table entries: low 32 bits of the lt-mer << 32 | global base position; buckets by a multiplicative hash of
+// those 32 bits.  (lt = 17 gives 34-bit lt-mers: the 17th base is confirmed by k_s2_verify, which has both sequences at hand.)
+#define MCB_S2_POS_BITS 32
 MCB_HD uint32_t mcb_kmer_bucket(uint64_t key, int pbits) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - pbits)); }
 
 // ---------------------------------------------------------------- primitives (mcb_sort.cu)

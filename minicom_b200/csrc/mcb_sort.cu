@@ -17,7 +17,7 @@
 #define SORT_TILE (SORT_THREADS * SORT_STEPS)
 
 // digit extractors: (a) a bit field of one word of a 16-byte element, (b) a bit field of the bucket hash of a Stage-2
-// contig-table entry (lt-mer<<30 | position)
+// contig-table entry (low 32 bits of the lt-mer << 32 | position)
 struct DigitPair {
 	int word, shift; unsigned mask;
 	__device__ __forceinline__ unsigned operator()(const ulonglong2 &e) const { unsigned long long v = word ? e.y : e.x; return (unsigned)(v >> shift) & mask; }

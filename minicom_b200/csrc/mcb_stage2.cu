@@ -7,7 +7,7 @@
 //
 //   once per contig set   K5a k_s2_pack_refs    2-bit packed contigs (+ one 32-byte record per contig, k_s2_contig_meta)
 //                         K5b k_s2_kmer_emit    every lt-mer of every contig (lt = 17, or 11 for L <= 80) as an 8-byte entry
-//                                               lt-mer<<30 | position, radix-sorted by a hash of the lt-mer into 2^p buckets
+//                                               lt-mer (low 32 bits)<<32 | position, radix-sorted by a hash of those bits into 2^p buckets
 //                                               (mcb_radix_sort_kmers) + k_s2_bucket_ends
 //   every round           K6  k_s2_singles      singleRead2bitset (bbhashdict.c:127-227): 2-bit singles, near-poly-A/T
 //                                               diversion, and a count-min sketch of the dictionary bins (bin sizes matter:
@@ -36,7 +36,8 @@
 
 #define S2_MAXD 16
 #define S2_POS_BITS MCB_S2_POS_BITS
-#define S2_POS_MASK ((1ull << S2_POS_BITS) - 1)
+#define S2_POS_MASK 0xFFFFFFFFull
+#define S2_KEY32(k) ((uint64_t)(k) & 0xFFFFFFFFull)      // what a table entry keeps of an lt-mer
 #define S2_BLK_SHIFT 9
 struct S2Geom {
 	int L, Wd, WS, nd, lt;
@@ -171,11 +172,11 @@ __global__ void k_s2_filter_insert(const uint64_t *__restrict__ rd, const uint8_
 	const uint64_t key_f = v & kmask;
 	uint64_t w; uint32_t b;
 	// key-sharded table: only the keys whose lt-mers this context keeps (the same top-16-bit hash range k_s2_kmer_emit tests)
-	uint32_t ob = kmer_bucket(key_f, 16);
+	uint32_t ob = kmer_bucket(S2_KEY32(key_f), 16);
 	if (ob >= o_lo && ob < o_hi) { flt_slot(key_f, wmask, &w, &b); atomicOr(&flt[w], b); }
 	if (ds > 0) {
 		const uint64_t key_r = rev_fields(~key_f & kmask, lt);
-		ob = kmer_bucket(key_r, 16);
+		ob = kmer_bucket(S2_KEY32(key_r), 16);
 		if (ob >= o_lo && ob < o_hi) { flt_slot(key_r, wmask, &w, &b); atomicOr(&flt[w], b); }
 	}
 }
@@ -232,7 +233,7 @@ k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_
 #pragma unroll 4
 	for (int j = 0; j < nstart; ++j) {
 		const uint64_t key = ((w0 >> (2 * j)) | (j ? w1 << (64 - 2 * j) : 0ull)) & kmask;
-		const uint32_t bk = kmer_bucket(key, pbits);
+		const uint32_t bk = kmer_bucket(S2_KEY32(key), pbits);
 		const bool keep = bk >= b_lo && bk < b_hi && (!flt || flt_has(flt, flt_mask, key));
 		keepmask |= (unsigned)keep << j;
 	}
@@ -393,7 +394,7 @@ struct S2Join {
 // every entry with an equal lt-mer becomes a candidate record (pair index | phase | contig position), appended with one
 // atomic per warp.  No verification here: key matches are sparse (a fraction of a match per thread), and
 // verifying them inside this loop left 31 lanes idle around each one.
-#define S2_CAND_PHASE_BIT 30
+#define S2_CAND_PHASE_BIT 32                 // candidate record: (single, dictionary) index << 33 | phase << 32 | contig position
 __global__ void __launch_bounds__(256) k_s2_probe_table(S2Join p, S2Geom gm, unsigned long long *__restrict__ cand, unsigned long long cand_cap)
 {
 	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(256) k_s2_probe_table(S2Join p, S2Geom gm, uns
 #pragma unroll
 			for (int phase = 0; phase < 2; ++phase) {
 				if (phase < nphase) {
-					const uint32_t bg = kmer_bucket(key2[phase], p.pbits);
+					const uint32_t bg = kmer_bucket(S2_KEY32(key2[phase]), p.pbits);
 					if (bg >= p.b_lo && bg < p.b_hi) {           // key-sharded: other ranks look up the other lt-mers
 						const uint32_t b = bg - p.b_lo;
 						lo2[phase] = b ? p.ptab[b - 1] : 0u;
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(256) k_s2_probe_table(S2Join p, S2Geom gm, uns
 	unsigned mine = 0;
 #pragma unroll
 	for (int phase = 0; phase < 2; ++phase)
-		for (uint32_t i = lo2[phase]; i < hi2[phase]; ++i) mine += (p.ents[i] >> S2_POS_BITS) == key2[phase];
+		for (uint32_t i = lo2[phase]; i < hi2[phase]; ++i) mine += (p.ents[i] >> S2_POS_BITS) == S2_KEY32(key2[phase]);
 	unsigned inc = mine;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
@@ -446,8 +447,8 @@ __global__ void __launch_bounds__(256) k_s2_probe_table(S2Join p, S2Geom gm, uns
 		for (int phase = 0; phase < 2; ++phase)
 			for (uint32_t i = lo2[phase]; i < hi2[phase]; ++i) {
 				const unsigned long long e = p.ents[i];
-				if ((e >> S2_POS_BITS) == key2[phase]) {
-					if (at < cand_cap) cand[at] = (idx << 31) | ((unsigned long long)phase << S2_CAND_PHASE_BIT) | (e & S2_POS_MASK);
+				if ((e >> S2_POS_BITS) == S2_KEY32(key2[phase])) {
+					if (at < cand_cap) cand[at] = (idx << 33) | ((unsigned long long)phase << S2_CAND_PHASE_BIT) | (e & S2_POS_MASK);
 					++at;
 				}
 			}
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(128) k_s2_verify(S2Join p, S2Geom gm, const un
 	unsigned long long n_valid = 0;
 	if (ci < n_cand_listed) {
 		const unsigned long long cr = cand[ci];
-		const uint64_t idx = cr >> 31, P = cr & S2_POS_MASK;
+		const uint64_t idx = cr >> 33, P = cr & S2_POS_MASK;
 		const int phase = (int)((cr >> S2_CAND_PHASE_BIT) & 1);
 		const int l = (int)(idx / p.S); const uint64_t s = idx - (uint64_t)l * p.S;
 		const int L = gm.L, Wd = gm.Wd, lt = gm.lt, ds = gm.dstart[l];
@@ -493,10 +494,15 @@ __global__ void __launch_bounds__(128) k_s2_verify(S2Join p, S2Geom gm, const un
 				if (q == Wd - 1) { w &= tailmask; r &= tailmask; }
 				return w ^ r;
 			};
+			// the table compared only the first 16 bases of the lt-mer: a candidate whose remaining bases differ was never a
+			// dictionary hit (the reference would not have looked at this pair through this dictionary)
+			bool keyeq = true;
+			for (int f = koff + 16; f < koff + lt; ++f) keyeq = keyeq && ((xword(f >> 5) >> (2 * (f & 31))) & 3ull) == 0;
 			int pc = 0;
 #pragma unroll
 			for (int q = 0; q < 8; ++q) if (q < Wd) pc += __popcll(xword(q));
-			bool ok = pc <= gm.thr;
+			bool ok = keyeq && pc <= gm.thr;
+			if (!keyeq) n_valid = 0;
 			if (ok && (phase == 0 || gm.thr > 24)) {                                             // encode_byte gate, :393 / :461
 				int len_e = 0, eq = 0;
 #pragma unroll 1
@@ -592,7 +598,7 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	const int L = ctx->L;
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
 	const uint64_t ref_bytes = n_contigs ? ref_off[n_contigs] : 0;
-	if (ref_bytes >= (1ull << S2_POS_BITS)) { mcb_set_error("mcb_realign: %llu contig bases exceed the 2^%d positions of one call", (unsigned long long)ref_bytes, S2_POS_BITS); return MCB_EINVAL; }
+	if (ref_bytes >= 0xFFFFFFFFull) { mcb_set_error("mcb_realign: %llu contig bases exceed the 2^32 positions of one call", (unsigned long long)ref_bytes); return MCB_EINVAL; }
 	// ---- host-side offsets
 	uint64_t total_words = 0, n_windows = 0, n_entries = 0;
 	MCB_TRY(ctx->h_in0.ensure((n_contigs + 1) * 8)); MCB_TRY(ctx->h_in1.ensure((n_contigs + 1) * 8));
@@ -874,7 +880,7 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	MCB_CUDA(cudaMemsetAsync(dc + 16, 0, 16 * 8, ctx->stream));
 	// ---- singles first: they do not depend on the contigs, and the contig upload (copy stream) overlaps them
 	const uint64_t nkv = S * (uint64_t)gm.nd;
-	if (nkv >= 0xFFFFFFFFull) { mcb_set_error("dictionary too large"); return MCB_EINVAL; }
+	if (nkv >= 0x7FFFFFFFull) { mcb_set_error("dictionary too large (singles x dictionaries must stay below 2^31)"); return MCB_EINVAL; }
 	DBuf &b_sg = ctx->d_scr[0], &b_cm = ctx->d_scr[5], &b_rd = ctx->d_scr[6], &b_fl = ctx->d_scr[8];
 	MCB_TRY(b_sg.ensure(S * 4 + 16)); MCB_TRY(b_rd.ensure(S * WS * 8 + 16)); MCB_TRY(b_fl.ensure(S + 16));
 	if (nkv) {
