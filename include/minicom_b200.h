@@ -217,7 +217,10 @@ typedef struct {
  * The contigs do not change between the rounds of one -e/-S/-E schedule (preprocess.c:197-232: only updateSingle() runs
  * between two realign_hash calls), and the library keeps the device-side k-mer table it built over them: passing
  * refs == NULL and ref_off == NULL reuses the contigs of the previous call (n_contigs must be 0 or the same count).
- * When refs is given, the table is rebuilt only if the strings differ from the cached ones. */
+ * When refs is given, the contigs are re-packed only if the strings differ from the cached ones.  The k-mer table holds
+ * the contig k-mers that the singles of the call that built it can ask for; a later call reuses it when its singles are
+ * a subset of those (what updateSingle() guarantees) and rebuilds it transparently otherwise.
+ * Limits of one call: fewer than 2^32 contig bases and fewer than 2^31 (single, dictionary) pairs (MCB_EINVAL beyond). */
 int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off,
                 uint64_t n_contigs, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res);
 
