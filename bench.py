@@ -178,6 +178,23 @@ def algorithmic_bytes(kernel, c):
     return None, None
 
 
+def issue_roofline(kernel, workload, avg_launch_s, sm_count, sm_mhz, path=None):
+    """The dominant kernel against the INSTRUCTION-ISSUE roofline (it is not bandwidth bound): warp instructions
+    per launch from the committed ncu capture (profiles/instructions.json, same workload) / the live CUDA-event launch time,
+    against sm_count x 4 schedulers x the SM clock sampled during the timed region.  None when the capture has no figure."""
+    path = path or os.path.join(ROOT, "profiles", "instructions.json")
+    if not os.path.exists(path) or not avg_launch_s:
+        return None
+    with open(path) as f:
+        tab = json.load(f)
+    if tab.get("workload") != workload or kernel not in tab:
+        return None
+    peak = sm_count * 4 * (sm_mhz or 1965.0) * 1e6
+    achieved = tab[kernel] / avg_launch_s
+    return {"unit": "warp instructions/s", "achieved": round(achieved, 1), "peak": peak, "frac": round(achieved / peak, 4),
+            "warp_instructions_per_launch": tab[kernel], "source": "profiles/instructions.json (ncu smsp__inst_executed.sum, same workload) / live launch time"}
+
+
 def opts_text(ref_env):
     """the reference options of a workload in minicom's own flag names"""
     names = {"MC_K": "-k", "MC_E": "-e", "MC_M": "-m", "MC_W": "-w", "MC_S": "-s", "MC_EMAX": "-E", "MC_STEP": "-S"}
@@ -364,6 +381,7 @@ def bench_ours(args):
     if os.path.exists(prof):
         with open(prof) as f:
             roof["traffic"] = json.load(f).get(dom[2:])
+    roof["issue"] = issue_roofline(dom[2:], args.workload, avg_launch_s, torch.cuda.get_device_properties(local).multi_processor_count, clk.summary().get("sm_mhz"))
     cpu = cpu_baseline(args.workload, 1, quiet=True) if not args.no_cpu_baseline else None
     value = n * world / (ms_dev_max / 1e3)
     line = {

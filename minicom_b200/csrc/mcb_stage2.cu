@@ -496,11 +496,16 @@ __global__ void __launch_bounds__(128) k_s2_verify(S2Join p, S2Geom gm, const un
 			};
 			// the table compared only the first 16 bases of the lt-mer: a candidate whose remaining bases differ was never a
 			// dictionary hit (the reference would not have looked at this pair through this dictionary)
+			// (lt is 11 or 17: at most ONE base, field koff+16 of the XOR, is left to confirm; it is picked up on the way)
+			const int kq = lt > 16 ? (koff + 16) >> 5 : -1, ksh = 2 * ((koff + 16) & 31);
 			bool keyeq = true;
-			for (int f = koff + 16; f < koff + lt; ++f) keyeq = keyeq && ((xword(f >> 5) >> (2 * (f & 31))) & 3ull) == 0;
 			int pc = 0;
 #pragma unroll
-			for (int q = 0; q < 8; ++q) if (q < Wd) pc += __popcll(xword(q));
+			for (int q = 0; q < 8; ++q) if (q < Wd) {
+				const uint64_t x = xword(q);
+				pc += __popcll(x);
+				if (q == kq) keyeq = ((x >> ksh) & 3ull) == 0;
+			}
 			bool ok = keyeq && pc <= gm.thr;
 			if (!keyeq) n_valid = 0;
 			if (ok && (phase == 0 || gm.thr > 24)) {                                             // encode_byte gate, :393 / :461
