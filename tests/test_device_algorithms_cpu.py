@@ -156,3 +156,23 @@ def test_sketch_lh_with_block_minima(w, k):
         got = sketch_lh_block_minimum(s, w, k, 0x700)
         assert n == len(got), (w, k, s)
         assert [tuple(int(v) for v in row) for row in want] == got, (w, k, s)
+
+
+def test_oracle_agrees_with_the_reference_on_the_adversarial_strings():
+    """The strings above are nastier than the random ones the oracle was pinned with (tests/test_oracle.py): tandem repeats,
+    reverse-complement palindromes, single-base runs.  Where the reference units library is built (oracle/_ref), pin the
+    oracle on them directly against the reference's own mm_sketch_two / mm_sketch_lh_ori."""
+    import ctypes as C
+    from test_oracle import _ref_units
+    R = _ref_units()
+    rng = np.random.default_rng(77)
+    for trial, s in enumerate(_strings(rng, 120, 200)):
+        k = int(rng.integers(4, 32))
+        out = (C.c_uint64 * 2)()
+        R.ref_sketch_two(s, len(s), k, trial, out)
+        assert O.sketch_two(s, k, trial) == (int(out[0]), int(out[1])), (s, k)
+        w = int(rng.integers(1, 40))
+        buf = np.zeros((4096, 2), dtype=np.uint64)
+        cnt = R.ref_sketch_lh_ori(s, len(s), w, k, trial, buf.ctypes.data, 4096)
+        got, n_got = O.sketch_lh(s, w, k, trial, cap=4096)
+        assert n_got == cnt and np.array_equal(got, buf[:cnt]), (s, w, k)
