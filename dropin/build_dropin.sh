@@ -17,17 +17,17 @@ B=$HERE/_build/L${L}_${MODE}
 mkdir -p "$B"
 {
   echo "#pragma once"
-  echo "#include \"mcref_cfg.h\""
+  echo "#include \"mcb_cfg.h\""
   if [ "$MODE" = order ]; then echo "#define ORDER"; echo "int cmpcluster3(const void *a_, const void *b_);"; fi
   if [ "$MODE" = pe ]; then echo "#define _PE"; echo "int cmpcluster3(const void *a_, const void *b_);"; fi
   echo "#define readlen $L"
   for kv in "num_thr MC_T 1" "inik MC_K 0" "inithr MC_E 0" "inimaxthr MC_EMAX 0" "inistep MC_STEP 0" "ininumdict MC_S 0" "iniw MC_W 0" "inim MC_M 0" "inicbthr MC_CBTHR 0" "inimaxrounds MC_MAXROUNDS 0"; do
-    set -- $kv; echo "#define $1 mcref_cfg_int(\"$2\", $3)"
+    set -- $kv; echo "#define $1 mcb_cfg_int(\"$2\", $3)"
   done
-  echo "#define uniqid mcref_cfg_str(\"MC_UNIQID\", \"umc\")"
-  echo "#define output mcref_cfg_str(\"MC_TMPDIR\", \"output_mc/\")"
+  echo "#define uniqid mcb_cfg_str(\"MC_UNIQID\", \"umc\")"
+  echo "#define output mcb_cfg_str(\"MC_TMPDIR\", \"output_mc/\")"
 } > "$B/config.h"
-CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$ROOT/oracle/ref -I$REF -I$ROOT/include"
+CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$HERE -I$REF -I$ROOT/include"
 KEPT="bseq misc preprocess kthread_cb kthread_dump minicommain"
 # minicompe links from an archive (src/Makefile:24-25,33-34): kthread_dump.o is never pulled in and clashes with kthread_dump_pe.o
 [ "$MODE" = pe ] && KEPT="${KEPT/kthread_dump /kthread_dump_pe }"

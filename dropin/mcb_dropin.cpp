@@ -254,14 +254,26 @@ void realign_hash(int n_threads_, reads_t *r, int index, int max_threshold)
 	}
 	// Between two realign_hash calls of one run only updateSingle() executes (preprocess.c:197-232): the consensus strings are
 	// the ones of the previous round, so only the first round ships them; later rounds reuse the device-side contig table.
-	static std::vector<const char*> sent_refs;
-	std::vector<const char*> cur_refs(contigs.size());
-	for (size_t i = 0; i < contigs.size(); ++i) cur_refs[i] = contigs[i]->ref;
-	const bool same = g_calls[3] > 0 && cur_refs == sent_refs && !getenv("MCB_RESEND_CONTIGS");
+	// "Same contigs" is decided on content (count, total length, a 64-bit hash of the strings), never on pointers.
+	static uint64_t sent_sig[3] = { 0, 0, 0 };
+	uint64_t sig[3] = { (uint64_t)contigs.size(), (uint64_t)refs.size(), 0x9E3779B97F4A7C15ull };
+	{
+		const size_t nw = refs.size() / 8;
+		uint64_t h[4] = { 1, 2, 3, 4 };                      // four independent lanes: the multiply chain is latency bound
+		const char *d = refs.data();
+		size_t i = 0;
+		for (; i + 4 <= nw; i += 4)
+			for (int q = 0; q < 4; ++q) { uint64_t w; memcpy(&w, d + (i + q) * 8, 8); h[q] = (h[q] ^ w) * 0x9E3779B97F4A7C15ull; }
+		for (; i < nw; ++i) { uint64_t w; memcpy(&w, d + i * 8, 8); h[0] = (h[0] ^ w) * 0x9E3779B97F4A7C15ull; }
+		uint64_t tail = 0; memcpy(&tail, d + nw * 8, refs.size() - nw * 8);
+		sig[2] = ((h[0] ^ tail) * 0x9E3779B97F4A7C15ull) ^ (h[1] * 3) ^ (h[2] * 5) ^ (h[3] * 7);
+		for (size_t c = 0; c < off.size(); ++c) sig[2] = (sig[2] ^ off[c]) * 0x9E3779B97F4A7C15ull;
+	}
+	const bool same = g_calls[3] > 0 && !memcmp(sig, sent_sig, sizeof sig) && !getenv("MCB_RESEND_CONTIGS");
 	mcb_realign_result res;
 	int rc = same ? mcb_realign(ctx, r->sg.a, r->sg.n, NULL, NULL, contigs.size(), max_threshold, maxsearch, ininumdict, &res)
 	              : mcb_realign(ctx, r->sg.a, r->sg.n, refs.data(), off.data(), contigs.size(), max_threshold, maxsearch, ininumdict, &res);
-	sent_refs.swap(cur_refs);
+	memcpy(sent_sig, sig, sizeof sig);
 	if (rc) die("realign_hash", rc);
 	for (uint64_t i = 0; i < res.n_fpA; ++i) { r->sg_flag[res.fpA_sg[i]] = true; kv_push(uint32_t, r->fpA_id, r->sg.a[res.fpA_sg[i]]); }
 	for (uint64_t i = 0; i < res.n_fpT; ++i) { r->sg_flag[res.fpT_sg[i]] = true; kv_push(uint32_t, r->fpT_id, r->sg.a[res.fpT_sg[i]]); }

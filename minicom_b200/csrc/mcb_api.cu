@@ -1,6 +1,5 @@
 // mcb_api.cu — context lifetime, error reporting, timers and the host-side boundary helpers of the C-ABI.
 #include "mcb_common.cuh"
-#include "mcb_sketch_lh.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
 #include <algorithm>
@@ -189,11 +188,65 @@ extern "C" void mcb_sketch_two_host(const char *str, int len, int k, uint32_t ri
 	*out = best;
 }
 
+// mm_sketch_lh_ori (sketch.c:116-165) for one string, host side (the per-contig call of the host contig merger).  Same
+// formulation as the device kernel k_sketch_lh2 (mcb_stage1.cu): the w-slot ring is cut into blocks of w steps; when the ring
+// pointer wraps, one backward pass records for every slot the rightmost minimum of the block's suffix, a running rightmost
+// minimum covers the slots written since, and the window minimum is the smaller of the two (ties to the newer one) instead of
+// the reference's rescan.  Both carry a "same hash elsewhere" bit, so the scan for identical k-mers runs only when one exists.
+// Emission order and tie rules are the reference's (property-tested against the oracle in tests/test_device_algorithms_cpu.py).
 extern "C" int64_t mcb_sketch_lh_host(const char *str, int len, int w, int k, uint32_t rid, mcb_tuple *out, int64_t cap)
 {
 	if (len <= 0 || w <= 0 || k <= 0 || k > 31) return 0;
-	std::vector<mcb_tuple> ring((size_t)w);
-	McbLhEmitArray em; em.out = out; em.cap = out ? cap : 0; em.n = 0;
-	mcb_sketch_lh_core(str, len, w, k, rid, ring.data(), em, (int64_t)-1);
-	return em.n;
+	const uint64_t mask = (1ull << (2 * k)) - 1, shift1 = 2 * (k - 1), NONE = ~0ull;
+	std::vector<uint64_t> rx((size_t)w, NONE), rp((size_t)w, NONE);
+	std::vector<int> suf((size_t)w, w - 1);           // slot of the rightmost minimum of the previous block's slots [j, w)
+	std::vector<char> suf_tie((size_t)w, 0);
+	int64_t n_out = 0;
+	auto emit = [&](uint64_t x, uint64_t p) { if (out && n_out < cap) { out[n_out].x = x; out[n_out].y = (uint64_t)rid << 32 | p; } ++n_out; };
+	uint64_t fw = 0, rv = 0, mn_x = NONE, mn_p = NONE, run_x = NONE;
+	int run_slot = 0; bool run_tie = false;
+	int l = 0, bp = 0, mp = 0;
+	for (int i = 0; i < len; ++i) {
+		const unsigned char ch = (unsigned char)str[i];
+		const unsigned c = (ch == 'A' || ch == 'a') ? 0u : (ch == 'C' || ch == 'c') ? 1u : (ch == 'G' || ch == 'g') ? 2u : (ch == 'T' || ch == 't') ? 3u : 4u;
+		uint64_t ix = NONE, ip = NONE;
+		if (c < 4) {
+			fw = (fw << 2 | c) & mask;
+			rv = (rv >> 2) | ((3ull ^ c) << shift1);
+			if (fw == rv) continue;                                  // symmetric k-mer: no ring slot (sketch.c:135)
+			const int z = fw < rv ? 0 : 1;
+			if (++l >= k) { ix = mcb_hash64_hd(z ? rv : fw, mask); ip = (uint64_t)(uint32_t)i << 1 | (uint64_t)z; }
+		} else l = 0;                                                // ambiguous base: run restarts, slot is still used (:139-140)
+		rx[bp] = ix; rp[bp] = ip;
+		if (ix <= run_x) { run_tie = ix == run_x; run_x = ix; run_slot = bp; }
+		auto emit_equal = [&](int lo, int hi) { for (int j = lo; j < hi; ++j) if (mn_x == rx[j] && rp[j] != mn_p) emit(rx[j], rp[j]); };
+		if (l == w + k - 1) { emit_equal(bp + 1, w); emit_equal(0, bp); }      // first full window (:141-146)
+		if (ix <= mn_x) {
+			if (l >= w + k) emit(mn_x, mn_p);
+			mn_x = ix; mn_p = ip; mp = bp;
+		} else if (bp == mp) {                                       // the minimum leaves the window (:150-161)
+			if (l >= w + k - 1) emit(mn_x, mn_p);
+			uint64_t nx = run_x; int ns = run_slot; bool tie = run_tie;
+			if (bp + 1 < w) {
+				const int ss = suf[bp + 1];
+				if (rx[ss] < run_x) { nx = rx[ss]; ns = ss; tie = suf_tie[bp + 1] != 0; }
+				else if (rx[ss] == run_x) tie = true;
+			}
+			mn_x = nx; mp = ns; mn_p = rp[ns];
+			if (tie && l >= w + k - 1) { emit_equal(bp + 1, w); emit_equal(0, bp + 1); }
+		}
+		if (++bp == w) {
+			bp = 0;
+			uint64_t sx = rx[w - 1]; int ss = w - 1; char st = 0;
+			suf[w - 1] = ss; suf_tie[w - 1] = 0;
+			for (int j = w - 2; j >= 1; --j) {
+				if (rx[j] < sx) { sx = rx[j]; ss = j; st = 0; }
+				else if (rx[j] == sx) st = 1;
+				suf[j] = ss; suf_tie[j] = st;
+			}
+			run_x = NONE; run_slot = 0; run_tie = false;
+		}
+	}
+	if (mn_x != NONE) emit(mn_x, mn_p);
+	return n_out;
 }

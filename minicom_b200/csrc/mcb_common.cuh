@@ -16,6 +16,7 @@
 #include "../../include/minicom_b200.h"
 
 #define MCB_HD __host__ __device__ __forceinline__
+#define MCB_LH_WMAX 128     // widest contig minimizer window (-w): k_sketch_lh2 keeps a 7-bit slot number per ring entry
 
 // ---------------------------------------------------------------- errors
 void mcb_set_error(const char *fmt, ...);
@@ -193,6 +194,7 @@ struct McbRealignState {
 	uint64_t S = 0, window_base = 0;
 	uint64_t g_lo = 0, g_hi = 0, g_sub = 0;   // claims of windows [g_lo, g_hi) are emitted here; g_sub = window index of this context's first contig
 	int nd = 0;
+	mcb_realign_result result;                // counters of the search half, handed out by mcb_realign_finish
 };
 
 struct mcb_ctx {
@@ -419,7 +421,7 @@ struct McbSortPass { int word; int shift; int bits; };  // word 0 = .x, 1 = .y
 int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const McbSortPass *passes, int n_passes,
                    ulonglong2 **sorted_out);
 int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long *b, uint64_t n, int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long **sorted_out);
-int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint32_t *boff, unsigned long long *overflow, ulonglong2 **sorted_out);
+int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint64_t n_valid, int kbits, uint32_t *boff, unsigned long long *overflow, ulonglong2 **sorted_out);
 int mcb_add_bit_passes(std::vector<McbSortPass> &v, int word, int lo, int hi);  // digits covering bits [lo,hi)
 int mcb_exclusive_scan_u32(mcb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *d_total /* device u64, may be null */);
 int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t *d_total);

@@ -13,7 +13,6 @@
 #include <thread>
 #include <algorithm>
 
-#define IX_WARPS 4
 #define IX_SMALL 64       // RS_MIN_SIZE (ksort.h:106)
 
 struct IxSeg { uint32_t b, e; int s; };
@@ -36,112 +35,7 @@ __device__ void ix_small_sort_warp(mcb_tuple *a, uint32_t n, int lane)
 	if (h1) a[r1] = e1;
 	__syncwarp();
 }
-__device__ void ix_insertion_sort(mcb_tuple *a, uint32_t n)
-{
-	for (uint32_t i = 1; i < n; ++i) {
-		mcb_tuple t = a[i];
-		if (t.x < a[i - 1].x) {
-			uint32_t j = i;
-			while (j > 0 && t.x < a[j - 1].x) { a[j] = a[j - 1]; --j; }
-			a[j] = t;
-		}
-	}
-}
-
-// sorts a[0..n) (n > IX_SMALL) exactly like the reference; `a` may point to shared or global memory
-__device__ void ix_flag_sort(mcb_tuple *a, uint32_t n, IxSeg *stk, uint32_t *cur, uint32_t *end, int lane)
-{
-	int top = 1;
-	if (lane == 0) { stk[0].b = 0; stk[0].e = n; stk[0].s = 56; }
-	__syncwarp();
-	while (top > 0) {
-		--top;
-		const uint32_t sb = stk[top].b, se = stk[top].e; const int s = stk[top].s;
-		__syncwarp();
-		// digit histogram -> region [start,end) per digit
-		for (int d = lane; d < 256; d += 32) cur[d] = 0;
-		__syncwarp();
-		for (uint32_t i = sb + lane; i < se; i += 32) atomicAdd(&cur[(a[i].x >> s) & 255], 1u);
-		__syncwarp();
-		{
-			uint32_t v[8], sum = 0;
-#pragma unroll
-			for (int q = 0; q < 8; ++q) { v[q] = cur[lane * 8 + q]; sum += v[q]; }
-			uint32_t inc = sum;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += x; }
-			uint32_t run = sb + inc - sum;
-			__syncwarp();
-#pragma unroll
-			for (int q = 0; q < 8; ++q) { cur[lane * 8 + q] = run; run += v[q]; end[lane * 8 + q] = run; }
-		}
-		__syncwarp();
-		// cycle-leader permutation, exactly in the reference's visiting order (ksort.h:131-145)
-		if (lane == 0) {
-			for (int k = 0; k < 256;) {
-				if (cur[k] != end[k]) {
-					mcb_tuple tmp = a[cur[k]];
-					int l = (int)((tmp.x >> s) & 255);
-					if (l != k) {
-						do {
-							mcb_tuple sw = tmp;
-							uint32_t p = cur[l]++;
-							tmp = a[p]; a[p] = sw;
-							l = (int)((tmp.x >> s) & 255);
-						} while (l != k);
-						a[cur[k]++] = tmp;
-					} else ++cur[k];
-				} else ++k;
-			}
-		}
-		__syncwarp();
-		if (s > 0) {
-			const int s2 = s > 8 ? s - 8 : 0;
-			// region d spans [end[d-1], end[d]): small ones are insertion-sorted by one lane each, big ones recurse
-			for (int d0 = 0; d0 < 256; d0 += 32) {
-				int d = d0 + lane;
-				uint32_t rb = d == 0 ? sb : end[d - 1], re = end[d];
-				uint32_t sz = re - rb;
-				bool big = sz > IX_SMALL;
-				if (!big && sz > 1) ix_insertion_sort(a + rb, sz);
-				unsigned bm = __ballot_sync(0xFFFFFFFFu, big);
-				if (big) { int slot = top + __popc(bm & ((1u << lane) - 1u)); stk[slot].b = rb; stk[slot].e = re; stk[slot].s = s2; }
-				top += __popc(bm);
-			}
-		}
-		__syncwarp();
-	}
-}
-
-#define IX_SMEM_CAP 1024       // tuples of one bucket staged in shared memory (16 KB per warp)
 #define IX_SMEM_STK 32
-
-__global__ void __launch_bounds__(IX_WARPS * 32)
-k_index_sort(mcb_tuple *__restrict__ t, const uint64_t *__restrict__ boff, int nb, IxSeg *__restrict__ stacks)
-{
-	extern __shared__ __align__(16) unsigned char ix_smem[];
-	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	uint32_t *cur = (uint32_t*)ix_smem + wib * 512, *end = cur + 256;
-	IxSeg *sstk = (IxSeg*)(ix_smem + IX_WARPS * 2048) + wib * IX_SMEM_STK;
-	mcb_tuple *stage = (mcb_tuple*)(ix_smem + IX_WARPS * 2048 + IX_WARPS * IX_SMEM_STK * sizeof(IxSeg)) + (size_t)wib * IX_SMEM_CAP;
-	for (int bk = blockIdx.x * IX_WARPS + wib; bk < nb; bk += gridDim.x * IX_WARPS) {
-		const uint64_t B0 = boff[bk], B1 = boff[bk + 1];
-		const uint32_t n = (uint32_t)(B1 - B0);
-		mcb_tuple *a = t + B0;
-		if (n <= 1) continue;
-		if (n <= IX_SMALL) { ix_small_sort_warp(a, n, lane); continue; }
-		if (n <= IX_SMEM_CAP) {
-			// alive segments are disjoint and > 64 tuples each: at most n/65 <= 15 stack entries
-			for (uint32_t i = lane; i < n; i += 32) stage[i] = a[i];
-			__syncwarp();
-			ix_flag_sort(stage, n, sstk, cur, end, lane);
-			for (uint32_t i = lane; i < n; i += 32) a[i] = stage[i];
-			__syncwarp();
-		} else {
-			ix_flag_sort(a, n, stacks + (B0 / 65 + 8ull * bk), cur, end, lane);
-		}
-	}
-}
 
 // ---------------------------------------------------------------- index-space formulation of the same sort
 // The cycle-leader walk of ksort.h:131-145 only looks at digits: a slot of a digit region is visited once, left to right, and
@@ -151,11 +45,12 @@ k_index_sort(mcb_tuple *__restrict__ t, const uint64_t *__restrict__ boff, int n
 // are in flight per SM — and the walk, a chain of dependent shared-memory loads, is bound by how many run concurrently.
 // Tuples go through a scratch copy in global memory (L2-resident per bucket).
 #define IX2_WARPS 4
-struct Ix2Smem { uint32_t *cur, *end; uint16_t *dest; uint8_t *dg; IxSeg *stk; };
+template <class DT> struct Ix2Mem { uint32_t *cur, *end; DT *dest; uint8_t *dg; IxSeg *stk; };
 
 // Only the digits and destinations live in shared memory (3 bytes per tuple); the keys needed to rank the small regions are
 // read back from global memory after the walk's permutation has been applied, where a region is a contiguous, cache-resident run.
-__device__ void ix3_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix2Smem &m, IxSeg *gstk, int lane)
+template <class DT>
+__device__ void ix3_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix2Mem<DT> &m, IxSeg *gstk, int lane)
 {
 	IxSeg *stk = m.stk;
 	int top = 1;
@@ -192,12 +87,12 @@ __device__ void ix3_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix
 					if (l != k) {
 						do {
 							const uint32_t p = m.cur[l]; m.cur[l] = p + 1;
-							m.dest[t] = (uint16_t)p;
+							m.dest[t] = (DT)p;
 							t = p;
 							l = m.dg[t];
 						} while (l != k);
-						m.dest[t] = (uint16_t)m.cur[k]; m.cur[k] = m.cur[k] + 1;
-					} else { m.dest[t] = (uint16_t)ck; m.cur[k] = ck + 1; }
+						m.dest[t] = (DT)m.cur[k]; m.cur[k] = m.cur[k] + 1;
+					} else { m.dest[t] = (DT)ck; m.cur[k] = ck + 1; }
 				} else ++k;
 			}
 		}
@@ -218,7 +113,7 @@ __device__ void ix3_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix
 					for (uint32_t q = rs; q < re; ++q) { const uint64_t xq = a[sb + q].x; rank += (xq < xi) || (xq == xi && q < p); }
 					at = rs + rank;
 				}
-				m.dest[p] = (uint16_t)at;
+				m.dest[p] = (DT)at;
 			}
 			__syncwarp();
 			for (uint32_t p = lane; p < cnt; p += 32) tmp[sb + m.dest[p]] = a[sb + p];
@@ -243,49 +138,38 @@ __device__ void ix3_flag_sort(mcb_tuple *a, mcb_tuple *tmp, uint32_t n, const Ix
 	}
 }
 
+// BIG = false: IX2_WARPS buckets per CTA, digits and 16-bit destinations in shared memory, buckets above `cap` tuples skipped.
+// BIG = true: the skipped buckets, one warp per CTA, digits and 32-bit destinations in global scratch (dg_g / dest_g, one slot
+// per tuple) — rare (a bucket above ~17 000 tuples), and correct for any size.
+template <bool BIG>
 __global__ void __launch_bounds__(IX2_WARPS * 32)
-k_index_sort3(mcb_tuple *__restrict__ t, mcb_tuple *__restrict__ tmp, const uint64_t *__restrict__ boff, int nb, uint32_t cap, IxSeg *__restrict__ stacks)
+k_index_sort3(mcb_tuple *__restrict__ t, mcb_tuple *__restrict__ tmp, const uint64_t *__restrict__ boff, int nb, uint32_t cap, IxSeg *__restrict__ stacks,
+              uint8_t *__restrict__ dg_g, uint32_t *__restrict__ dest_g)
 {
 	extern __shared__ __align__(16) unsigned char ix2_smem[];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * 3 + 15) & ~(size_t)15;
+	const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (BIG ? 0 : (size_t)cap * 3) + 15) & ~(size_t)15;
 	unsigned char *base = ix2_smem + (size_t)wib * per_warp;
-	Ix2Smem m;
-	m.cur = (uint32_t*)base; m.end = m.cur + 256;
-	m.stk = (IxSeg*)(base + 2048);
-	m.dest = (uint16_t*)(base + 2048 + IX_SMEM_STK * sizeof(IxSeg));
-	m.dg = (uint8_t*)(m.dest + cap);
-	for (int bk = blockIdx.x * IX2_WARPS + wib; bk < nb; bk += gridDim.x * IX2_WARPS) {
+	const int nw = BIG ? 1 : IX2_WARPS;
+	if (BIG && wib) return;
+	for (int bk = blockIdx.x * nw + wib; bk < nb; bk += gridDim.x * nw) {
 		const uint64_t B0 = boff[bk], B1 = boff[bk + 1];
 		const uint32_t n = (uint32_t)(B1 - B0);
-		if (n <= 1) continue;
-		if (n <= IX_SMALL) { ix_small_sort_warp(t + B0, n, lane); continue; }
-		ix3_flag_sort(t + B0, tmp + B0, n, m, stacks + (B0 / 65 + 8ull * bk), lane);
+		if (BIG) {
+			if (n <= cap) continue;
+			Ix2Mem<uint32_t> m;
+			m.cur = (uint32_t*)base; m.end = m.cur + 256; m.stk = (IxSeg*)(base + 2048);
+			m.dest = dest_g + B0; m.dg = dg_g + B0;
+			ix3_flag_sort<uint32_t>(t + B0, tmp + B0, n, m, stacks + (B0 / 65 + 8ull * bk), lane);
+		} else {
+			if (n <= 1 || n > cap) continue;
+			if (n <= IX_SMALL) { ix_small_sort_warp(t + B0, n, lane); continue; }
+			Ix2Mem<uint16_t> m;
+			m.cur = (uint32_t*)base; m.end = m.cur + 256; m.stk = (IxSeg*)(base + 2048);
+			m.dest = (uint16_t*)(base + 2048 + IX_SMEM_STK * sizeof(IxSeg)); m.dg = (uint8_t*)(m.dest + cap);
+			ix3_flag_sort<uint16_t>(t + B0, tmp + B0, n, m, stacks + (B0 / 65 + 8ull * bk), lane);
+		}
 	}
-}
-
-__global__ void k_ix_heads(const mcb_tuple *__restrict__ t, uint64_t n, uint32_t *__restrict__ flag)
-{
-	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) flag[i] = (i == 0 || t[i].x != t[i - 1].x) ? 1u : 0u;
-}
-__global__ void k_ix_keys(const mcb_tuple *__restrict__ t, uint64_t n, const uint32_t *__restrict__ hscan, const unsigned long long *__restrict__ U,
-                          uint64_t *__restrict__ keys, uint32_t *__restrict__ kstart, uint64_t *__restrict__ post)
-{
-	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	mcb_tuple e = t[i];
-	post[i] = e.y;
-	if (i == 0 || e.x != t[i - 1].x) { uint32_t u = hscan[i]; keys[u] = e.x; kstart[u] = (uint32_t)i; }
-	if (i == n - 1) kstart[*U] = (uint32_t)n;
-}
-__global__ void k_ix_bucket_ranges(const uint64_t *__restrict__ boff, int nb, uint64_t n, const uint32_t *__restrict__ hscan,
-                                   const unsigned long long *__restrict__ U, uint32_t *__restrict__ ub)
-{
-	int b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b > nb) return;
-	uint64_t p = boff[b];
-	ub[b] = p < n ? hscan[p] : (uint32_t)*U;
 }
 
 struct mcb_index {
@@ -339,80 +223,6 @@ static int idx_alloc_host(mcb_ctx *ctx, mcb_index *ix, uint64_t U, uint64_t n, i
 	MCB_TRY(ix->slab.ensure(tot));
 	char *base = ix->slab.as<char>();
 	ix->keys = (uint64_t*)(base + o_keys); ix->post = (uint64_t*)(base + o_post); ix->kstart = (uint32_t*)(base + o_ks); ix->ub = (uint32_t*)(base + o_ub);
-	return MCB_OK;
-}
-
-static int idx_build_device(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff, mcb_index **out)
-{
-	// tuples are in d_scr[0] (device), bucket offsets on the host
-	const int b = ctx->prm.b, nb = 1 << b;
-	mcb_index *ix = new mcb_index(); ix->b = b; ix->n_post = n;
-	*out = ix;
-	if (n == 0) {
-		MCB_TRY(idx_alloc_host(ctx, ix, 0, 0, nb));
-		memset(ix->ub, 0, ((size_t)nb + 1) * 4); ix->kstart[0] = 0;
-		return MCB_OK;
-	}
-	if (n >= 0xFFFFFFFFull) { mcb_set_error("index too large"); return MCB_EINVAL; }
-	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
-	MCB_TRY(ctx->d_scr[1].ensure(((size_t)nb + 1) * 8));
-	MCB_TRY(ctx->d_scr[2].ensure((n / 65 + 8ull * nb + 8) * sizeof(IxSeg)));
-	MCB_TRY(ctx->d_scr[3].ensure(n * 4 + 16));
-	MCB_TRY(ctx->d_scr[4].ensure(n * 8 + 16));           // keys (<= n)
-	MCB_TRY(ctx->d_scr[5].ensure((n + 2) * 4));          // kstart
-	MCB_TRY(ctx->d_scr[6].ensure(n * 8 + 16));           // postings
-	MCB_TRY(ctx->d_scr[7].ensure(((size_t)nb + 1) * 4)); // ub
-	mcb_tuple *dt = ctx->d_scr[0].as<mcb_tuple>();
-	{
-		McbSpan sp(ctx->tm, "h2d");
-		MCB_TRY(mcb_h2d(ctx, ctx->d_scr[1].p, h_boff, ((size_t)nb + 1) * 8, 1));
-	}
-	{
-		McbSpan sp(ctx->tm, "idx_build");
-		uint64_t maxb = 0;
-		for (int i = 0; i < nb; ++i) maxb = std::max<uint64_t>(maxb, h_boff[i + 1] - h_boff[i]);
-		static const bool force_old = getenv("MCB_IX_OLD") != nullptr;
-		if (getenv("MCB_IX_DEBUG")) fprintf(stderr, "[mcb] idx build: n=%llu max bucket=%llu\n", (unsigned long long)n, (unsigned long long)maxb);
-		bool done = false;
-		if (maxb <= 65000 && !force_old) {      // index-space walk: 3 bytes of shared memory per tuple of the largest bucket
-			const uint32_t cap = (uint32_t)std::max<uint64_t>(64, (maxb + 63) & ~63ull);
-			const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * 3 + 15) & ~(size_t)15;
-			const size_t smem3 = per_warp * IX2_WARPS;
-			if (smem3 <= 220 * 1024) {
-				MCB_TRY(ctx->d_scr[8].ensure(n * 16 + 16));
-				if (smem3 > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_index_sort3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-				MCB_LAUNCH(ctx, "index_sort", k_index_sort3, mcb_grid_for(nb, IX2_WARPS), IX2_WARPS * 32, smem3, dt, ctx->d_scr[8].as<mcb_tuple>(), ctx->d_scr[1].as<uint64_t>(), nb, cap,
-				           ctx->d_scr[2].as<IxSeg>());
-				done = true;
-			}
-		}
-		if (!done) {       // buckets too large for that: the warp-per-bucket kernel that moves the tuples themselves
-			const size_t ix_smem = IX_WARPS * 2048 + IX_WARPS * IX_SMEM_STK * sizeof(IxSeg) + (size_t)IX_WARPS * IX_SMEM_CAP * sizeof(mcb_tuple);
-			MCB_CUDA(cudaFuncSetAttribute(k_index_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix_smem));
-			MCB_LAUNCH(ctx, "index_sort", k_index_sort, mcb_grid_for(nb, IX_WARPS), IX_WARPS * 32, ix_smem, dt, ctx->d_scr[1].as<uint64_t>(), nb, ctx->d_scr[2].as<IxSeg>());
-		}
-		MCB_LAUNCH(ctx, "ix_heads", k_ix_heads, mcb_grid_for(n, 256), 256, 0, dt, n, ctx->d_scr[3].as<uint32_t>());
-		MCB_TRY(mcb_exclusive_scan_u32(ctx, ctx->d_scr[3].as<uint32_t>(), n, (uint64_t*)&dc[CT_SCRATCH_IDX]));
-		MCB_LAUNCH(ctx, "ix_keys", k_ix_keys, mcb_grid_for(n, 256), 256, 0, dt, n, ctx->d_scr[3].as<uint32_t>(), &dc[CT_SCRATCH_IDX],
-		           ctx->d_scr[4].as<uint64_t>(), ctx->d_scr[5].as<uint32_t>(), ctx->d_scr[6].as<uint64_t>());
-		MCB_LAUNCH(ctx, "ix_bucket_ranges", k_ix_bucket_ranges, mcb_grid_for(nb + 1, 256), 256, 0, ctx->d_scr[1].as<uint64_t>(), nb, n,
-		           ctx->d_scr[3].as<uint32_t>(), &dc[CT_SCRATCH_IDX], ctx->d_scr[7].as<uint32_t>());
-	}
-	MCB_TRY(ctx->h_counters.ensure(64 * 8));
-	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-	const uint64_t U = ctx->h_counters.as<unsigned long long>()[CT_SCRATCH_IDX];
-	ix->n_keys = U;
-	MCB_TRY(idx_alloc_host(ctx, ix, U, n, nb));
-	{
-		McbSpan sp(ctx->tm, "d2h");
-		MCB_CUDA(cudaMemcpyAsync(ix->keys, ctx->d_scr[4].p, U * 8, cudaMemcpyDeviceToHost, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(ix->kstart, ctx->d_scr[5].p, (U + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(ix->post, ctx->d_scr[6].p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(ix->ub, ctx->d_scr[7].p, ((size_t)nb + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	}
-	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-	ctx->tm.collect();
 	return MCB_OK;
 }
 
@@ -556,21 +366,17 @@ static int idx_build_pipelined(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff,
 	// ---- sort kernel configuration (the same for all runs)
 	uint64_t maxb = 0;
 	for (int i = 0; i < nb; ++i) maxb = std::max<uint64_t>(maxb, h_boff[i + 1] - h_boff[i]);
-	static const bool force_old = getenv("MCB_IX_OLD") != nullptr;
 	if (getenv("MCB_IX_DEBUG")) fprintf(stderr, "[mcb] idx build: n=%llu max bucket=%llu runs=%d\n", (unsigned long long)n, (unsigned long long)maxb, C);
-	bool walk = false; uint32_t cap = 0; size_t smem3 = 0;
-	if (maxb <= 65000 && !force_old) {      // index-space walk: 3 bytes of shared memory per tuple of the largest bucket
-		cap = (uint32_t)std::max<uint64_t>(64, (maxb + 63) & ~63ull);
-		const size_t per_warp = (2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * 3 + 15) & ~(size_t)15;
-		smem3 = per_warp * IX2_WARPS;
-		if (smem3 <= 220 * 1024) {
-			walk = true;
-			MCB_TRY(ctx->d_scr[8].ensure(n * 16 + 16));
-			if (smem3 > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_index_sort3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-		}
-	}
-	const size_t ix_smem = IX_WARPS * 2048 + IX_WARPS * IX_SMEM_STK * sizeof(IxSeg) + (size_t)IX_WARPS * IX_SMEM_CAP * sizeof(mcb_tuple);
-	if (!walk) MCB_CUDA(cudaFuncSetAttribute(k_index_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix_smem));
+	// index-space walk: 3 bytes of shared memory per tuple of the largest bucket, up to IX_CAP_MAX; larger buckets take the
+	// global-scratch variant of the same kernel
+	const uint32_t IX_CAP_MAX = 16384;
+	const uint32_t cap = (uint32_t)std::min<uint64_t>(IX_CAP_MAX, std::max<uint64_t>(64, (maxb + 63) & ~63ull));
+	const size_t smem3 = ((2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * 3 + 15) & ~(size_t)15) * IX2_WARPS;
+	const size_t smem3_big = (2048 + IX_SMEM_STK * sizeof(IxSeg) + 15) & ~(size_t)15;
+	const bool have_big = maxb > cap;
+	MCB_TRY(ctx->d_scr[8].ensure(n * 16 + 16));
+	if (smem3 > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_index_sort3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+	if (have_big) { MCB_TRY(ctx->d_scr[10].ensure(n + 16)); MCB_TRY(ctx->d_scr[11].ensure(n * 4 + 16)); }
 	std::vector<cudaEvent_t> evH((size_t)C), evC((size_t)C);
 	for (int c = 0; c < C; ++c) { cudaEventCreateWithFlags(&evH[c], cudaEventDisableTiming); cudaEventCreateWithFlags(&evC[c], cudaEventDisableTiming); }
 	std::vector<IxEvPair> t_h2d, t_d2h;
@@ -621,9 +427,10 @@ static int idx_build_pipelined(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff,
 		{
 			McbSpan sp(ctx->tm, "idx_build");
 			if (nc) {
-				if (walk) MCB_LAUNCH(ctx, "index_sort", k_index_sort3, mcb_grid_for(b1 - b0, IX2_WARPS), IX2_WARPS * 32, smem3, dt, ctx->d_scr[8].as<mcb_tuple>(), d_boff + b0, b1 - b0, cap,
-				                     ctx->d_scr[2].as<IxSeg>());
-				else MCB_LAUNCH(ctx, "index_sort", k_index_sort, mcb_grid_for(b1 - b0, IX_WARPS), IX_WARPS * 32, ix_smem, dt, d_boff + b0, b1 - b0, ctx->d_scr[2].as<IxSeg>());
+				MCB_LAUNCH(ctx, "index_sort", k_index_sort3<false>, mcb_grid_for(b1 - b0, IX2_WARPS), IX2_WARPS * 32, smem3, dt, ctx->d_scr[8].as<mcb_tuple>(), d_boff + b0, b1 - b0, cap,
+				           ctx->d_scr[2].as<IxSeg>(), (uint8_t*)nullptr, (uint32_t*)nullptr);
+				if (have_big) MCB_LAUNCH(ctx, "index_sort_big", k_index_sort3<true>, (unsigned)std::min(b1 - b0, 4 * ctx->sm_count), IX2_WARPS * 32, smem3_big, dt, ctx->d_scr[8].as<mcb_tuple>(),
+				                         d_boff + b0, b1 - b0, cap, ctx->d_scr[2].as<IxSeg>(), ctx->d_scr[10].as<uint8_t>(), ctx->d_scr[11].as<uint32_t>());
 				MCB_LAUNCH(ctx, "ix_count", k_ix_count, mcb_grid_for(b1 - b0, IXF_WARPS), IXF_WARPS * 32, 0, dt, d_boff + b0, b1 - b0, d_flag + b0);
 			} else MCB_CUDA(cudaMemsetAsync(d_flag + b0, 0, (size_t)(b1 - b0) * 4, ctx->stream));
 			MCB_LAUNCH(ctx, "ix_scan", k_ix_scan_run, 1, 1024, 0, d_flag, b0, b1, d_chain, c, ctx->d_scr[7].as<uint32_t>(), c == C - 1 ? nb : -1);
@@ -663,8 +470,6 @@ static int idx_build_pipelined(mcb_ctx *ctx, uint64_t n, const uint64_t *h_boff,
 	return MCB_OK;
 }
 
-static const bool g_ix_nopipe = getenv("MCB_IX_NOPIPE") && atoi(getenv("MCB_IX_NOPIPE"));   // debugging: one upload, one sort, one download
-
 extern "C" int mcb_idx_build(mcb_ctx *ctx, const mcb_tuple *tuples, const uint64_t *bucket_off, mcb_index **out)
 {
 	if (!ctx || !out || !bucket_off) { mcb_set_error("mcb_idx_build: null argument"); return MCB_EINVAL; }
@@ -674,18 +479,8 @@ extern "C" int mcb_idx_build(mcb_ctx *ctx, const mcb_tuple *tuples, const uint64
 	const uint64_t n = bucket_off[nb];
 	if (n && !tuples) { mcb_set_error("mcb_idx_build: null tuples"); return MCB_EINVAL; }
 	MCB_TRY(ctx->d_counters.ensure(64 * 8));
-	int r;
-	if (!g_ix_nopipe) {
-		IxSource src; src.flat = tuples;
-		r = idx_build_pipelined(ctx, n, bucket_off, src, out);
-	} else {
-		MCB_TRY(ctx->d_scr[0].ensure(n * 16 + 16));
-		if (n) {
-			McbSpan sp(ctx->tm, "h2d");
-			MCB_TRY(mcb_h2d(ctx, ctx->d_scr[0].p, tuples, n * 16, 4));
-		}
-		r = idx_build_device(ctx, n, bucket_off, out);
-	}
+	IxSource src; src.flat = tuples;
+	const int r = idx_build_pipelined(ctx, n, bucket_off, src, out);
 	if (r != MCB_OK) { mcb_idx_destroy(*out); *out = nullptr; }
 	return r;
 }
@@ -704,29 +499,8 @@ extern "C" int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptr
 	MCB_TRY(ctx->h_in0.ensure(n * 16 + 16));
 	mcb_tuple *flat = ctx->h_in0.as<mcb_tuple>();
 	MCB_TRY(ctx->d_counters.ensure(64 * 8));
-	if (!g_ix_nopipe) {
-		IxSource src; src.ptrs = ptrs; src.cnt = cnt; src.stage = flat; src.n_threads = n_threads;
-		int r = idx_build_pipelined(ctx, n, boff, src, out);
-		if (r != MCB_OK) { mcb_idx_destroy(*out); *out = nullptr; }
-		return r;
-	}
-	{   // gather the bucket arrays into one pinned block, n_threads host threads over contiguous bucket ranges
-		const int T = std::max(1, std::min(n_threads, (int)(n / 65536) + 1));
-		auto work = [&](int b0, int b1) { for (int i = b0; i < b1; ++i) if (cnt[i]) memcpy(flat + boff[i], ptrs[i], cnt[i] * 16); };
-		if (T == 1) work(0, nb);
-		else {
-			std::vector<std::thread> th;
-			for (int t = 0; t < T; ++t) th.emplace_back(work, (int)((int64_t)nb * t / T), (int)((int64_t)nb * (t + 1) / T));
-			for (auto &x : th) x.join();
-		}
-	}
-	MCB_TRY(ctx->d_counters.ensure(64 * 8));
-	MCB_TRY(ctx->d_scr[0].ensure(n * 16 + 16));
-	if (n) {
-		McbSpan sp(ctx->tm, "h2d");
-		MCB_CUDA(cudaMemcpyAsync(ctx->d_scr[0].p, flat, n * 16, cudaMemcpyHostToDevice, ctx->stream));
-	}
-	int r = idx_build_device(ctx, n, boff, out);
+	IxSource src; src.ptrs = ptrs; src.cnt = cnt; src.stage = flat; src.n_threads = n_threads;
+	const int r = idx_build_pipelined(ctx, n, boff, src, out);
 	if (r != MCB_OK) { mcb_idx_destroy(*out); *out = nullptr; }
 	return r;
 }

@@ -327,19 +327,34 @@ int mcb_partition_by_owner(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t 
 
 // ---------------------------------------------------------------- bucket-local tuple sort
 // The tuple sort of kt_for_bucket orders by (bucket, minimizer, adjusted position desc, rid): 70+ key bits, nine 8-bit LSD passes
-// over all tuples.  Two passes on the 14 bucket bits are enough to bring every bucket together (16384 buckets of a few hundred
-// tuples); the rest of the key is then sorted inside the bucket, in shared memory, by one CTA per bucket (bitonic network on the
-// 128-bit key — keys are unique, rid is part of them).  Global traffic drops from 9 x 48 to 2 x 48 + 32 bytes per tuple.
-// Buckets above BL_CAP tuples are not sorted here: they raise *overflow and the caller falls back to the full LSD sort.
+// over all tuples.  Radix passes on the leading key bits alone — the 14 bucket bits plus, for large inputs, the top `e` bits of
+// the minimizer, chosen so that a sub-bucket holds a few hundred tuples — bring every sub-bucket together; the rest of the key
+// is then sorted inside the sub-bucket, in shared memory, by one CTA (bitonic network on the 128-bit key — keys are unique, rid
+// is part of them).  Global traffic drops from 9 x 48 to 2 x 48 + 32 bytes per tuple (3 x 48 above 2^16 sub-buckets).
+// Elements that are not tuples (reads that were not sketched: N-rich, poly-A/T) get a digit of their own past the last
+// sub-bucket, so they never inflate one.  Sub-buckets above BL_CAP tuples (one minimizer shared by thousands of reads) are
+// not sorted here: they raise *overflow and the caller falls back to the full LSD sort.
 #define BL_CAP 2048
 #define BL_THREADS 256
 
-__global__ void k_bucket_bounds(const ulonglong2 *__restrict__ e, uint64_t n, uint32_t *__restrict__ boff)
+// sub-bucket of a tuple: bucket << e | top e bits of the minimizer's remaining kx bits (K1 = bucket << 50 | x >> 14)
+struct SubBucket {
+	int e, xshift;           // xshift = kx - e
+	__device__ __forceinline__ unsigned operator()(unsigned long long k1) const
+	{ return ((unsigned)(k1 >> 50) << e) | ((unsigned)(k1 >> xshift) & ((1u << e) - 1u)); }
+};
+struct DigitSub {
+	SubBucket sb; int shift; unsigned mask, invalid_digit;     // invalid_digit: digit of the non-tuples (top pass: one past the largest), 0 elsewhere
+	__device__ __forceinline__ unsigned operator()(const ulonglong2 &el) const
+	{ return el.x == MCB_K1_INVALID ? invalid_digit : (sb(el.x) >> shift) & mask; }
+};
+
+__global__ void k_bucket_bounds(const ulonglong2 *__restrict__ e, uint64_t n, SubBucket sb, unsigned nsub, uint32_t *__restrict__ boff)
 {
 	const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b > 16384u) return;
-	uint64_t lo = 0, hi = n;                  // first element whose bucket is >= b
-	while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((unsigned)(e[mid].x >> 50) < b) lo = mid + 1; else hi = mid; }
+	if (b > nsub) return;
+	uint64_t lo = 0, hi = n;                  // first element whose sub-bucket is >= b
+	while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (sb(e[mid].x) < b) lo = mid + 1; else hi = mid; }
 	boff[b] = (uint32_t)lo;
 }
 
@@ -369,13 +384,42 @@ k_bucket_local_sort(ulonglong2 *__restrict__ e, const uint32_t *__restrict__ bof
 	for (uint32_t i = threadIdx.x; i < n; i += BL_THREADS) e[b0 + i] = s[i];
 }
 
-// a/b: double buffer; boff: device scratch u32[16386]; overflow: device counter (must be zero on entry)
-int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint32_t *boff, unsigned long long *overflow, ulonglong2 **sorted_out)
+// a/b: double buffer; n elements of which n_valid are tuples whose minimizers have `kbits` significant bits; boff: device scratch
+// u32[*n_sub_out + 2] (at most n_valid/256 + 16386 entries); overflow: device counter (must be zero on entry).  The sorted tuples
+// occupy [0, n_valid) of *sorted_out, the other elements follow.
+int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint64_t n_valid, int kbits, uint32_t *boff, unsigned long long *overflow, ulonglong2 **sorted_out)
 {
-	McbSortPass bucket_passes[2] = { {0, 50, 7}, {0, 57, 7} };
-	MCB_TRY(mcb_radix_sort(ctx, a, b, n, bucket_passes, 2, sorted_out));
+	*sorted_out = a;
 	if (n <= 1) return MCB_OK;
-	MCB_LAUNCH(ctx, "bucket_bounds", k_bucket_bounds, (16385 + 255) / 256, 256, 0, *sorted_out, n, boff);
-	MCB_LAUNCH(ctx, "bucket_local_sort", k_bucket_local_sort, 16384, BL_THREADS, 0, *sorted_out, boff, overflow);
+	const uint64_t nb = (n + SORT_TILE - 1) / SORT_TILE;
+	if (nb > 0x7FFFFFFFull) { mcb_set_error("sort input too large"); return MCB_EINVAL; }
+	MCB_TRY(ctx->d_sort_hist.ensure((nb + 1) * 256 * sizeof(uint32_t)));
+	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>(), *rowsum = hist + nb * 256;
+	const int kx = kbits > 14 ? kbits - 14 : 0;                       // bits of x >> 14
+	int e = 0;
+	while (e < 9 && e < kx && (n_valid >> (14 + e)) > 512) ++e;        // about 256..512 tuples per sub-bucket
+	const SubBucket sb = { e, kx - e };
+	const int P = 14 + e;
+	// digits, least significant first; the top one has 7 bits so that the non-tuples fit behind it as digit 128
+	int bits[3], np = 0;
+	{
+		const int rest = P - 7, nlow = (rest + 7) / 8;
+		for (int i = 0, left = rest; i < nlow; ++i) { const int bq = (left + (nlow - i) - 1) / (nlow - i); bits[np++] = bq; left -= bq; }
+		bits[np++] = 7;
+	}
+	ulonglong2 *src = a, *dst = b;
+	for (int p = 0, lo = 0; p < np; ++p) {
+		const DigitSub dg = { sb, lo, (1u << bits[p]) - 1u, p == np - 1 ? 128u : 0u };
+		MCB_LAUNCH(ctx, "sort_hist", (k_sort_hist<ulonglong2, DigitSub>), (unsigned)nb, SORT_THREADS, 0, src, n, dg, hist, (unsigned)nb);
+		MCB_LAUNCH(ctx, "sort_rowscan", k_sort_rowscan, 256, SORT_THREADS, 0, hist, (unsigned)nb, rowsum);
+		MCB_LAUNCH(ctx, "sort_scatter", (k_sort_scatter<ulonglong2, DigitSub>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb, rowsum);
+		ulonglong2 *t = src; src = dst; dst = t;
+		lo += bits[p];
+	}
+	*sorted_out = src;
+	if (n_valid <= 1) return MCB_OK;
+	const unsigned nsub = 1u << P;
+	MCB_LAUNCH(ctx, "bucket_bounds", k_bucket_bounds, (nsub + 1 + 255) / 256, 256, 0, src, n_valid, sb, nsub, boff);
+	MCB_LAUNCH(ctx, "bucket_local_sort", k_bucket_local_sort, nsub, BL_THREADS, 0, src, boff, overflow);
 	return MCB_OK;
 }

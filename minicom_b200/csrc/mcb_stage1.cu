@@ -6,7 +6,6 @@
 //   K4  k_sketch_lh              mm_sketch_lh_ori (sketch.c:116-165), first `first_mininum` tuples per seed contig
 //   round loop                   kt_for_bucket (kthread_bucket.c:562-629)
 #include "mcb_common.cuh"
-#include "mcb_sketch_lh.cuh"
 #include <algorithm>
 #include <thread>
 
@@ -708,9 +707,6 @@ __global__ void k_scatter_clusters(const uint32_t *__restrict__ gstart, uint64_t
 }
 
 // ---------------------------------------------------------------- K4: first m windowed minimizers of each new seed contig
-// mm_sketch_lh_ori (sketch.c:116-165) is a sequential scan with data-dependent tie rules, so one thread walks one contig;
-// its characters arrive through aligned 64-bit loads, and the w-slot ring buffer (hash + position/strand per slot) lives in
-// shared memory, slot-major so that the lanes of a warp hit different banks.  The walk stops after m outputs (kthread_bucket.c:463).
 #define LH_THREADS 64
 struct LhRingSmem {
 	uint64_t *x; uint32_t *ps; int tid;
@@ -719,68 +715,10 @@ struct LhRingSmem {
 	__device__ __forceinline__ uint32_t p(int j) const { return ps[j * LH_THREADS + tid]; }
 };
 
-__global__ void __launch_bounds__(LH_THREADS)
-k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count, uint64_t cid_first,
-            int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
-{
-	extern __shared__ __align__(16) unsigned char lh_smem[];
-	uint64_t *rx = (uint64_t*)lh_smem;                                        // [w][LH_THREADS]
-	uint32_t *rp = (uint32_t*)(rx + (size_t)w * LH_THREADS);                  // [w][LH_THREADS]
-	const uint64_t ci = (uint64_t)blockIdx.x * LH_THREADS + threadIdx.x;
-	if (ci >= cl_count) return;
-	const uint64_t c = cl_first + ci;
-	const uint64_t b = cl_ref_off[c], e = cl_ref_off[c + 1];
-	const int len = (int)(e - b);
-	const uint32_t rid = (uint32_t)((cid_first + ci) << 8);          // ((clusters.n-1)<<8)+tid, tid 0 (kthread_bucket.c:458)
-	// characters come eight at a time from aligned 64-bit loads (the buffer is padded past its end)
-	const uint64_t *str8 = (const uint64_t*)(cl_ref + (b & ~(uint64_t)7));
-	const int skew = (int)(b & 7);
-	uint64_t chunk = 0;
-	LhRingSmem ring; ring.x = rx; ring.ps = rp; ring.tid = threadIdx.x;
-	mcb_tuple *out = mi + c * m;
-	int n_out = 0;
-	const uint64_t mask = (1ull << (2 * k)) - 1, shift1 = 2 * (k - 1);
-	uint64_t fw = 0, rv = 0, mn_x = ~0ull; uint32_t mn_p = ~0u;
-	int l = 0, bp = 0, mp = 0;
-#define LH_EMIT(hx_, p_) do { if (n_out < m) { mcb_tuple t_; t_.x = (hx_); t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } while (0)
-	for (int j = 0; j < w; ++j) ring.set(j, ~0ull, ~0u);
-	for (int i = 0; i < len && n_out < m; ++i) {
-		const int ai = i + skew;
-		if (i == 0 || (ai & 7) == 0) chunk = str8[ai >> 3];
-		const unsigned cc = mcb_code_of((unsigned char)(chunk >> (8 * (ai & 7))));   // consensus strings are upper-case ACGT (invert_code_rule)
-		uint64_t ix = ~0ull; uint32_t ip = ~0u;
-		if (cc < 4) {
-			fw = (fw << 2 | cc) & mask;
-			rv = (rv >> 2) | ((3ull ^ cc) << shift1);
-			if (fw == rv) continue;
-			const int z = fw < rv ? 0 : 1;
-			if (++l >= k) { ix = mcb_hash64_hd(z ? rv : fw, mask); ip = (uint32_t)i << 1 | (uint32_t)z; }
-		} else l = 0;
-		ring.set(bp, ix, ip);
-		if (l == w + k - 1) {
-			for (int j = bp + 1; j < w; ++j) if (mn_x == ring.hx(j) && ring.p(j) != mn_p) LH_EMIT(ring.hx(j), ring.p(j));
-			for (int j = 0; j < bp; ++j) if (mn_x == ring.hx(j) && ring.p(j) != mn_p) LH_EMIT(ring.hx(j), ring.p(j));
-		}
-		if (ix <= mn_x) {
-			if (l >= w + k) LH_EMIT(mn_x, mn_p);
-			mn_x = ix; mn_p = ip; mp = bp;
-		} else if (bp == mp) {
-			if (l >= w + k - 1) LH_EMIT(mn_x, mn_p);
-			mn_x = ~0ull;
-			for (int j = bp + 1; j < w; ++j) { uint64_t v = ring.hx(j); if (mn_x >= v) { mn_x = v; mn_p = ring.p(j); mp = j; } }
-			for (int j = 0; j <= bp; ++j) { uint64_t v = ring.hx(j); if (mn_x >= v) { mn_x = v; mn_p = ring.p(j); mp = j; } }
-			if (l >= w + k - 1) {
-				for (int j = bp + 1; j < w; ++j) if (mn_x == ring.hx(j) && mn_p != ring.p(j)) LH_EMIT(ring.hx(j), ring.p(j));
-				for (int j = 0; j <= bp; ++j) if (mn_x == ring.hx(j) && mn_p != ring.p(j)) LH_EMIT(ring.hx(j), ring.p(j));
-			}
-		}
-		if (++bp == w) bp = 0;
-	}
-	if (n_out < m && mn_x != ~0ull) LH_EMIT(mn_x, mn_p);
-#undef LH_EMIT
-	mi_cnt[c] = (uint8_t)(n_out < m ? n_out : m);
-}
-// Same walk with a constant-time window minimum.  The reference rescans the whole ring whenever the minimum leaves the window
+// mm_sketch_lh_ori (sketch.c:116-165) is a sequential scan with data-dependent tie rules, so one thread walks one contig; its
+// characters arrive through aligned 64-bit loads, and the w-slot ring buffer (hash + position/strand per slot) lives in shared
+// memory, slot-major so that the lanes of a warp hit different banks.  The walk stops after m outputs (kthread_bucket.c:463).
+// The window minimum is found in constant time.  The reference rescans the whole ring whenever the minimum leaves the window
 // (sketch.c:150-158); with 32 contigs per warp some lane needs that at almost every step, so every warp paid the w-slot scan
 // (and the tie scan after it) all the time.  Here the ring is cut into blocks of w steps (one turn of bp): when bp wraps, one
 // backward pass stores for every slot j the slot of the rightmost minimum of the previous block's slots [j, w) (strict <
@@ -789,7 +727,7 @@ k_sketch_lh(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref
 // of the range holds the same hash" bit, so the reference's scan for identical k-mers (:159-161) runs only when there is one.
 // bp is the same in all lanes of a warp unless a lane meets a symmetric k-mer (even k only), so the passes do not diverge.
 #define LH2_SLOT_MASK 0x7Fu
-#define LH2_WMAX 128
+#define LH2_WMAX MCB_LH_WMAX
 template <bool WIDE>
 __global__ void __launch_bounds__(LH_THREADS)
 k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count, uint64_t cid_first,
@@ -886,20 +824,6 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 #undef LH_EMIT
 	mi_cnt[c] = (uint8_t)(n_out < m ? n_out : m);
 }
-// fallback for windows too wide for shared memory: ring buffer in local memory
-__global__ void k_sketch_lh_local(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count, uint64_t cid_first,
-                                  int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
-{
-	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= cl_count) return;
-	const uint64_t c = cl_first + i;
-	const uint64_t b = cl_ref_off[c], e = cl_ref_off[c + 1];
-	McbLhEmitArray em; em.out = mi + c * m; em.cap = m; em.n = 0;
-	mcb_tuple ring[MCB_LH_WMAX];
-	mcb_sketch_lh_core(cl_ref + b, (int)(e - b), w, k, (uint32_t)((cid_first + i) << 8), ring, em, (int64_t)m);
-	mi_cnt[c] = (uint8_t)(em.n < m ? em.n : m);
-}
-
 // ================================================================= host side
 static int sync_counters(mcb_ctx *ctx, unsigned long long **hc)
 {
@@ -1218,12 +1142,12 @@ static int bucket_round_a(mcb_ctx *ctx, int r, int is_last)
 	ulonglong2 *sorted = nullptr;
 	const uint64_t n = bs.n_valid;
 	bs.n = n;
-	MCB_TRY(B.b_hs.ensure(std::max<uint64_t>(n, 16400) * 4 + 16)); MCB_TRY(B.b_gs.ensure((n + 2) * 4));
+	MCB_TRY(B.b_hs.ensure(std::max<uint64_t>(n, n / 256 + 16400) * 4 + 16)); MCB_TRY(B.b_gs.ensure((n + 2) * 4));
 	unsigned long long *hc0 = nullptr;
 	for (int attempt = lsd_only ? 1 : 0;; ++attempt) {
 		if (attempt == 0) {
 			MCB_CUDA(cudaMemsetAsync(&dc[CT_SORT_OVERFLOW], 0, 8, ctx->stream));
-			MCB_TRY(mcb_bucket_sort(ctx, bs.cur, bs.alt, bs.n_in, B.b_hs.as<uint32_t>(), &dc[CT_SORT_OVERFLOW], &sorted));     // b_hs doubles as the bucket-offset scratch
+			MCB_TRY(mcb_bucket_sort(ctx, bs.cur, bs.alt, bs.n_in, bs.n_valid, kbits, B.b_hs.as<uint32_t>(), &dc[CT_SORT_OVERFLOW], &sorted));     // b_hs doubles as the bucket-offset scratch
 		} else MCB_TRY(mcb_radix_sort(ctx, bs.cur, bs.alt, bs.n_in, passes.data(), (int)passes.size(), &sorted));
 		if (sorted != bs.cur) { bs.alt = bs.cur; bs.cur = sorted; }
 		// ---- groups
@@ -1323,22 +1247,12 @@ static int bucket_round_b(mcb_ctx *ctx, uint64_t cid_first)
 		MCB_TRY(grow_preserve(ctx, B.d_mi, tot_cl * m * 16, (tot_cl + n_cl_new) * m * 16 + 16));
 		MCB_TRY(grow_preserve(ctx, B.d_micnt, tot_cl, tot_cl + n_cl_new + 16));
 		if (n_cl_new) {
-			const int rw = ctx->prm.rw;
-			const size_t lh_smem = (size_t)rw * LH_THREADS * 12;
-			static const bool lh_old = getenv("MCB_LH_OLD") && atoi(getenv("MCB_LH_OLD"));      // debugging: the reference-shaped rescanning walk
+			const int rw = ctx->prm.rw;                                   // mcb_create admits rw <= MCB_LH_WMAX = LH2_WMAX
 			const size_t lh2_smem = (size_t)rw * LH_THREADS * 13;
-			if (!lh_old && rw <= LH2_WMAX && lh2_smem <= 200 * 1024) {
-				auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
-				if (lh2_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh2_smem));
-				MCB_LAUNCH(ctx, "sketch_lh", kern, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh2_smem, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
-				           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>());
-			} else if (lh_smem <= 160 * 1024) {
-				if (lh_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_sketch_lh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh_smem));
-				MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh_smem, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
-				           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>());
-			} else
-				MCB_LAUNCH(ctx, "sketch_lh", k_sketch_lh_local, mcb_grid_for(n_cl_new, 64), 64, 0, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
-				           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>());
+			auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
+			if (lh2_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh2_smem));
+			MCB_LAUNCH(ctx, "sketch_lh", kern, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh2_smem, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
+			           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>());
 		}
 		bs.tot_cl += n_cl_new; bs.tot_mem += n_mem_new; bs.tot_ref += n_ref_new; bs.tot_sg += n_sg_new;
 		// ---- rejected reads go to the next round with a shorter k-mer (kthread_bucket.c:205-212,488-496)

@@ -626,19 +626,21 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	cx.valid = cx.valid && maybe_same;
 	{   // the contig strings go up on the copy stream: the singles kernels already queued on the compute stream run meanwhile
 		MCB_TRY(mcb_copy_streams(ctx));
-		cudaEvent_t e0, e1;
-		cudaEventCreate(&e0); cudaEventCreate(&e1);
-		cudaEventRecord(e0, ctx->copy_stream);                         // (every earlier call has synchronized: nothing else touches these buffers)
+		struct EvPair {                   // destroyed on every exit path
+			cudaEvent_t a = nullptr, b = nullptr;
+			~EvPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+		} ev;
+		MCB_CUDA(cudaEventCreate(&ev.a)); MCB_CUDA(cudaEventCreate(&ev.b));
+		MCB_CUDA(cudaEventRecord(ev.a, ctx->copy_stream));             // (every earlier call has synchronized: nothing else touches these buffers)
 		if (refs_pad > ref_bytes) MCB_CUDA(cudaMemsetAsync(stage_refs.as<char>() + (refs_pad - 8), 0, 8, ctx->copy_stream));
 		MCB_TRY(mcb_h2d_on(ctx, ctx->copy_stream, stage_refs.p, refs, ref_bytes, 4));
 		MCB_TRY(mcb_h2d_on(ctx, ctx->copy_stream, stage_off.p, ref_off, (n_contigs + 1) * 8, 1));
-		cudaEventRecord(e1, ctx->copy_stream);
-		MCB_CUDA(cudaStreamWaitEvent(ctx->stream, e1, 0));
+		MCB_CUDA(cudaEventRecord(ev.b, ctx->copy_stream));
+		MCB_CUDA(cudaStreamWaitEvent(ctx->stream, ev.b, 0));
 		if (ctx->tm.enabled) {
-			cudaEventSynchronize(e1);
-			float ms = 0; if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) { int id = ctx->tm.id("h2d"); ctx->tm.ms[id] += ms; ctx->tm.cnt[id] += 1; }
+			cudaEventSynchronize(ev.b);
+			float ms = 0; if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { int id = ctx->tm.id("h2d"); ctx->tm.ms[id] += ms; ctx->tm.cnt[id] += 1; }
 		}
-		cudaEventDestroy(e0); cudaEventDestroy(e1);
 	}
 	if (maybe_same) {
 		McbSpan sp(ctx->tm, "realign");
@@ -1044,8 +1046,6 @@ static int realign_claims(mcb_ctx *ctx, mcb_realign_result *res)
 	return MCB_OK;
 }
 
-static mcb_realign_result g_pending_result;   // counters of the search half, carried to mcb_realign_finish (one pending search per process is enough for the sharded driver)
-
 extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
                            int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
 {
@@ -1060,7 +1060,7 @@ extern "C" int mcb_realign_begin(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, c
 {
 	if (!ctx || !d_claim) { mcb_set_error("mcb_realign_begin: null argument"); return MCB_EINVAL; }
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, window_base, 0, 1, 0, 0, threshold, maxsearch, ininumdict, &g_pending_result));
+	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, window_base, 0, 1, 0, 0, threshold, maxsearch, ininumdict, &ctx->rs.result));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));        // the caller reduces the array on its own stream
 	*d_claim = ctx->d_x[0].p;
 	return MCB_OK;
@@ -1070,7 +1070,7 @@ extern "C" int mcb_realign_finish(mcb_ctx *ctx, mcb_realign_result *res)
 {
 	if (!ctx || !res) { mcb_set_error("mcb_realign_finish: null argument"); return MCB_EINVAL; }
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	*res = g_pending_result;
+	*res = ctx->rs.result;               // counters of the search half
 	return realign_claims(ctx, res);
 }
 
@@ -1085,7 +1085,7 @@ extern "C" int mcb_realign_begin_keyed(mcb_ctx *ctx, const uint32_t *sg, uint64_
 	if (!ctx || !d_claim) { mcb_set_error("mcb_realign_begin_keyed: null argument"); return MCB_EINVAL; }
 	if (tab_ranks < 1 || tab_ranks > 255 || tab_rank < 0 || tab_rank >= tab_ranks || g_hi < g_lo) { mcb_set_error("mcb_realign_begin_keyed: bad arguments"); return MCB_EINVAL; }
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, 0, tab_rank, tab_ranks, g_lo, g_hi, threshold, maxsearch, ininumdict, &g_pending_result));
+	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, 0, tab_rank, tab_ranks, g_lo, g_hi, threshold, maxsearch, ininumdict, &ctx->rs.result));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	*d_claim = ctx->d_x[0].p;
 	if (maxbin_upper) *maxbin_upper = ctx->h_counters.as<unsigned long long>()[CT_S2_MAXBIN];

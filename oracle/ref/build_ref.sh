@@ -19,25 +19,25 @@ B=$OUT/build_L${L}_${MODE}
 mkdir -p "$B"
 {
   echo "#pragma once"
-  echo "#include \"mcref_cfg.h\""
+  echo "#include \"mcb_cfg.h\""
   if [ "$MODE" = order ]; then echo "#define ORDER"; echo "int cmpcluster3(const void *a_, const void *b_);"; fi
   if [ "$MODE" = pe ]; then echo "#define _PE"; echo "int cmpcluster3(const void *a_, const void *b_);"; fi
   echo "#define readlen $L"
-  echo "#define num_thr mcref_cfg_int(\"MC_T\", 1)"
-  echo "#define uniqid mcref_cfg_str(\"MC_UNIQID\", \"umc\")"
-  echo "#define output mcref_cfg_str(\"MC_TMPDIR\", \"output_mc/\")"
-  echo "#define inik mcref_cfg_int(\"MC_K\", 0)"
-  echo "#define inithr mcref_cfg_int(\"MC_E\", 0)"
-  echo "#define inimaxthr mcref_cfg_int(\"MC_EMAX\", 0)"
-  echo "#define inistep mcref_cfg_int(\"MC_STEP\", 0)"
-  echo "#define ininumdict mcref_cfg_int(\"MC_S\", 0)"
-  echo "#define iniw mcref_cfg_int(\"MC_W\", 0)"
-  echo "#define inim mcref_cfg_int(\"MC_M\", 0)"
-  echo "#define inicbthr mcref_cfg_int(\"MC_CBTHR\", 0)"
-  echo "#define inimaxrounds mcref_cfg_int(\"MC_MAXROUNDS\", 0)"
+  echo "#define num_thr mcb_cfg_int(\"MC_T\", 1)"
+  echo "#define uniqid mcb_cfg_str(\"MC_UNIQID\", \"umc\")"
+  echo "#define output mcb_cfg_str(\"MC_TMPDIR\", \"output_mc/\")"
+  echo "#define inik mcb_cfg_int(\"MC_K\", 0)"
+  echo "#define inithr mcb_cfg_int(\"MC_E\", 0)"
+  echo "#define inimaxthr mcb_cfg_int(\"MC_EMAX\", 0)"
+  echo "#define inistep mcb_cfg_int(\"MC_STEP\", 0)"
+  echo "#define ininumdict mcb_cfg_int(\"MC_S\", 0)"
+  echo "#define iniw mcb_cfg_int(\"MC_W\", 0)"
+  echo "#define inim mcb_cfg_int(\"MC_M\", 0)"
+  echo "#define inicbthr mcb_cfg_int(\"MC_CBTHR\", 0)"
+  echo "#define inimaxrounds mcb_cfg_int(\"MC_MAXROUNDS\", 0)"
 } > "$B/config.h"
 # -march=x86-64-v3 instead of the reference's -march=native so the binary also runs on the GPU box's host CPU
-CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$HERE -I$REF"
+CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$HERE -I$HERE/../../dropin -I$REF"
 OBJS="bseq misc preprocess sketch bbhashdict kthread_reads kthread_bucket kthread_idx kthread_cb kthread_dump kthread_hash_realign minicommain"
 # the reference links minicompe from an archive (src/Makefile:24-25,33-34): kthread_dump.o is never pulled in there and
 # defines the same cmp() as kthread_dump_pe.o
@@ -50,11 +50,11 @@ WRAP="-Wl,--wrap=_Z12kt_for_readsiP7reads_tl -Wl,--wrap=_Z13kt_for_bucketiP7read
 ALL=""; for f in $OBJS; do ALL="$ALL $B/$f.o"; done
 g++ -O3 -fopenmp $ALL "$B/mcref_wrap.o" $WRAP -o "$OUT/minicom_ref_L${L}_${MODE}" -lm -lz -lpthread
 if [ ! -x "$OUT/decompress" ]; then
-  g++ -O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -include stdint.h -I$B -I$HERE -I$REF "$REF/decompress.c" -o "$OUT/decompress" -lm -lz -lpthread
+  g++ -O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -include stdint.h -I$B -I$HERE -I$HERE/../../dropin -I$REF "$REF/decompress.c" -o "$OUT/decompress" -lm -lz -lpthread
 fi
 echo "built $OUT/minicom_ref_L${L}_${MODE}"
 # unit-level entry points of the reference (hash64, mm_sketch_two, mm_sketch_lh_ori, radix_sort_128x) for ctypes tests
 if [ ! -f "$OUT/libmcref_units.so" ] || [ "$HERE/mcref_units.cpp" -nt "$OUT/libmcref_units.so" ]; then
-  g++ -O2 -std=c++11 -w -fPIC -shared -I$B -I$HERE -I$REF "$HERE/mcref_units.cpp" "$HERE/mcref_units_sort.cpp" "$REF/misc.c" -o "$OUT/libmcref_units.so"
+  g++ -O2 -std=c++11 -w -fPIC -shared -I$B -I$HERE -I$HERE/../../dropin -I$REF "$HERE/mcref_units.cpp" "$HERE/mcref_units_sort.cpp" "$REF/misc.c" -o "$OUT/libmcref_units.so"
   echo "built $OUT/libmcref_units.so"
 fi

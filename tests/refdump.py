@@ -71,7 +71,9 @@ def run_reference(reads: np.ndarray, workdir: str, mode: str = "sg", env_opts: d
     env.update({"MC_T": str(threads), "MC_TMPDIR": tmpd, "MC_TIMING": os.path.join(workdir, "timing.json"), "OMP_NUM_THREADS": str(threads),
                 "MCB_TIMING": os.path.join(workdir, "timing.json")})
     if dump:
-        env.update({"MC_DUMP": dumpdir, "MC_DUMP_SEQS": "1"})
+        env.update({"MC_DUMP": dumpdir})
+        if dump != "noseqs":             # the N-replaced reads as text: as large as the input
+            env["MC_DUMP_SEQS"] = "1"
     for k, v in (env_opts or {}).items():
         env[k] = str(v)
     p = subprocess.run(args, env=env, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, preexec_fn=_unlimit_stack)
@@ -211,3 +213,54 @@ def load_golden(name):
     meta = eval(z["meta"].tobytes().decode(), {"__builtins__": {}})
     out = {k[4:]: z[k].tobytes() for k in z.files if k.startswith("out/")}
     return z["reads"], meta, GoldenDump(z), out
+
+
+def roundtrip(outdir: str, workdir: str, mode: str, reads: np.ndarray, reads2: np.ndarray | None = None, threads: int = 1) -> dict:
+    """Feeds a pre-back-end output directory (the reference's or the drop-in's) to the reference's own decompressor
+    (oracle/_ref/decompress, built from /root/reference/src/decompress.c; CLI as in minicom:383) and checks what `minicom -d`
+    promises: default mode gives the input reads back as a multiset (minicom:389 concatenates the part files), -p gives them
+    back in the original order, -1/-2 gives the read PAIRS back as a multiset."""
+    import subprocess
+    dec = os.path.join(REF_DIR, "decompress")
+    if not os.path.exists(dec):
+        raise FileNotFoundError(f"{dec} missing: run oracle/ref/build_ref.sh where /root/reference exists")
+    d = os.path.join(workdir, "dec_in")
+    shutil.rmtree(d, ignore_errors=True)
+    shutil.copytree(outdir, d)
+    res, res2 = os.path.join(workdir, "dec.reads"), os.path.join(workdir, "dec2.reads")
+    args = [dec, d, res, "true" if mode == "pe" else "false", "true" if mode == "order" else "false", str(threads)] + ([res2] if mode == "pe" else [])
+    p = subprocess.run(args, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, preexec_fn=_unlimit_stack)
+    if p.returncode != 0:
+        raise RuntimeError(f"decompress failed ({p.returncode}): {p.stdout.decode()[-2000:]}")
+
+    def lines(path):
+        with open(path, "rb") as f:
+            return np.frombuffer(f.read(), dtype=np.uint8)
+
+    def as_rows(blob, L):
+        assert blob.size % (L + 1) == 0, "decoded file is not a whole number of reads"
+        rows = blob.reshape(-1, L + 1)
+        assert (rows[:, L] == 10).all(), "decoded reads are not newline-terminated rows"
+        return rows[:, :L]
+
+    def sorted_rows(a):
+        return a[np.lexsort(a.T[::-1])]
+
+    L = reads.shape[1]
+    parts = lambda names: np.concatenate([as_rows(lines(os.path.join(d, f)), L) for f in names])          # noqa: E731
+    results = sorted((f for f in os.listdir(d) if f.startswith("result_") and f.endswith(".seq")), key=lambda f: int(f[7:-4]))
+    if mode == "order":
+        got = as_rows(lines(res), L)
+        assert got.shape == reads.shape and np.array_equal(got, reads), "order-preserving round trip: decoded reads differ from the input"
+        return {"reads": len(got), "kind": "exact order"}
+    if mode == "pe":
+        # file 1 comes back as a multiset in cluster order (catsh.sh, decompress.c:1298-1308) and argv[6] holds the mates line
+        # for line (decompress.c:1311-1315): the PAIRS are what must survive
+        got1 = parts(["aatt.fasta", "single_dec.fasta"] + results)
+        got2 = as_rows(lines(res2), L)
+        assert got1.shape == reads.shape and got2.shape == reads2.shape, "paired-end round trip: read counts differ"
+        assert np.array_equal(sorted_rows(np.hstack([got1, got2])), sorted_rows(np.hstack([reads, reads2]))), "paired-end round trip: decoded pairs differ from the input pairs"
+        return {"reads": len(got1), "kind": "multiset of pairs"}
+    got = parts(["aatt.fasta", "single_N.seq", "single_dec.fasta"] + results)   # minicom:389
+    assert got.shape == reads.shape and np.array_equal(sorted_rows(got), sorted_rows(reads)), "round trip: decoded multiset differs from the input"
+    return {"reads": len(got), "kind": "multiset"}

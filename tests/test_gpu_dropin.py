@@ -31,23 +31,6 @@ def compare_dirs(a, b):
     return fa
 
 
-def roundtrip(outdir, reads, workdir):
-    dec = os.path.join(refdump.REF_DIR, "decompress")
-    if not os.path.exists(dec):
-        pytest.skip("decompress not built")
-    res = os.path.join(workdir, "dec.reads")
-    d2 = os.path.join(workdir, "dec_in")
-    shutil.rmtree(d2, ignore_errors=True)
-    shutil.copytree(outdir, d2)
-    p = subprocess.run([dec, d2, res, "false", "false", "1"], cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-    assert p.returncode == 0, p.stdout.decode()[-2000:]
-    # non-order mode: the reads come back as a multiset spread over several files (minicom:389)
-    got = []
-    for fn in sorted(os.listdir(workdir)):
-        pass
-    return res
-
-
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_dropin_directory_is_byte_identical(case):
     name, n, L, G, seed, special, env = case
@@ -62,7 +45,8 @@ def test_dropin_directory_is_byte_identical(case):
     with tempfile.TemporaryDirectory() as wd:
         r = refdump.run_reference(reads, wd, mode="sg", env_opts=env, dump=False, exe=exe)
         files = compare_dirs(ref_out, r["out"])
-        print(name, "identical files:", len(files), "timing:", r["timing"])
+        rt = refdump.roundtrip(r["out"], wd, "sg", reads)                   # `minicom -d` gives the reads back (multiset)
+        print(name, "identical files:", len(files), "round trip:", rt, "timing:", r["timing"])
 
 
 @pytest.mark.parametrize("name", refdump.golden_names())
@@ -76,9 +60,11 @@ def test_dropin_matches_golden_output_directory(name):
     with tempfile.TemporaryDirectory() as wd:
         r = refdump.run_reference(reads, wd, mode=meta["mode"], env_opts=meta["env"], dump=False, exe=exe)
         got = {f: open(os.path.join(r["out"], f), "rb").read() for f in os.listdir(r["out"])}
+        rt = refdump.roundtrip(r["out"], wd, meta["mode"], reads)          # exact order under -p, multiset otherwise
     assert sorted(got) == sorted(want), f"file sets differ: {set(got) ^ set(want)}"
     bad = [f for f in want if got[f] != want[f]]
     assert not bad, f"files differ: {bad}"
+    assert rt["reads"] == len(reads)
 
 
 def test_dropin_paired_end_mode():
@@ -98,4 +84,5 @@ def test_dropin_paired_end_mode():
         a = refdump.run_reference(r1, wa, mode="pe", dump=False, reads2=r2)
         b = refdump.run_reference(r1, wb, mode="pe", dump=False, reads2=r2, exe=exe)
         files = compare_dirs(a["out"], b["out"])
-        print("PE identical files:", len(files))
+        rt = refdump.roundtrip(b["out"], wb, "pe", r1, r2)
+        print("PE identical files:", len(files), "round trip:", rt)

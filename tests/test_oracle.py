@@ -268,3 +268,22 @@ def test_no_gpu_means_loud_failure():
         pass
     with pytest.raises(api.McbError):
         api.Context(api.resolve_params(100))
+
+
+@pytest.mark.parametrize("name", ["g100_default", "g100_order", "g75_default", "g150_default", "g100_opts"])
+def test_reference_directory_round_trips_through_decompress(name):
+    """Pins the round-trip procedure itself (tests/refdump.py:roundtrip, used by the GPU drop-in tests) on the committed
+    reference output directories: `minicom -d` = the reference's decompress program (minicom:383-389)."""
+    import tempfile
+    import refdump
+    if not os.path.exists(os.path.join(refdump.REF_DIR, "decompress")):
+        pytest.skip("oracle/_ref/decompress not built")
+    reads, meta, _, out = refdump.load_golden(name)
+    with tempfile.TemporaryDirectory() as wd:
+        d = os.path.join(wd, "out")
+        os.makedirs(d)
+        for f, b in out.items():
+            with open(os.path.join(d, f), "wb") as fh:
+                fh.write(b)
+        r = refdump.roundtrip(d, wd, meta["mode"], reads)
+    assert r["reads"] == len(reads)
