@@ -146,33 +146,6 @@ int  mcb_round_control_begin(mcb_round_control *rc, int k, int max_rounds);
 int  mcb_round_control_end(mcb_round_control *rc, uint64_t members_total);
 
 /* ------------------------------------------------------------------ */
-/* sharding across the GPUs of one box                   */
-/* ------------------------------------------------------------------ */
-/* One context per GPU (one process per GPU).  Reads are split into contiguous read-id ranges; every minimizer bucket
- * (16384 of them) is owned by one rank: owner = bucket * n_ranks >> 14.  The library does the device work and exposes
- * device pointers; the caller moves data between ranks (NCCL all-to-all / all-gather, see minicom_b200/shard.py):
- *
- *   mcb_shard_begin(rank, n_ranks, n_total, rid_base)      then mcb_for_reads*() on the slice: read ids are global
- *   all-gather of the packed reads   mcb_shard_packed() -> [n_total][row_bytes], this rank's rows already in place
- *   all-gather of the N side table   mcb_shard_get_nreads() / mcb_shard_set_nreads()
- *   per round r = 1, 2, ... (loop control: mcb_round_control on the GLOBAL member count)
- *     mcb_shard_partition()  -> tuples grouped by owner + counts; all-to-all into mcb_shard_recv_buffer(); mcb_shard_set_tuples()
- *     mcb_bucket_round_a()   -> sort, group, consensus; reports the new seed contigs / members / singles / rejects of this rank
- *     mcb_bucket_round_b(cid_first)  cid_first = global index of this rank's first new contig in the single-GPU order
- *                                    (contigs of earlier rounds on all ranks + this round's contigs on lower ranks)
- *   mcb_bucket_finish()      -> this rank's contigs / singles in round order + what each round contributed
- * Concatenating, round by round, the ranks' contributions in rank order reproduces the single-GPU result exactly. */
-int mcb_shard_begin(mcb_ctx *ctx, int rank, int n_ranks, uint64_t n_total, uint64_t rid_base);
-int mcb_shard_partition(mcb_ctx *ctx, uint64_t *counts /* [n_ranks] */, void **d_tuples /* 16-byte elements, grouped by owner */);
-int mcb_shard_recv_buffer(mcb_ctx *ctx, uint64_t n_tuples, void **d_recv, void **d_send /* current address of the partitioned tuples */);
-int mcb_shard_set_tuples(mcb_ctx *ctx, uint64_t n_tuples);
-int mcb_shard_packed(mcb_ctx *ctx, void **d_packed, uint64_t *row_bytes);
-int mcb_shard_get_nreads(mcb_ctx *ctx, const uint32_t **rid, const uint64_t **mask /* [n][row_bytes/8] */, uint64_t *n);
-int mcb_shard_set_nreads(mcb_ctx *ctx, const uint32_t *rid, const uint64_t *mask, uint64_t n);
-int mcb_bucket_round_a(mcb_ctx *ctx, int round, int is_last, uint64_t *out4 /* new contigs, members, singles, rejects */);
-int mcb_bucket_round_b(mcb_ctx *ctx, uint64_t cid_first);
-int mcb_bucket_finish(mcb_ctx *ctx, mcb_bucket_result *res, uint64_t *round_counts /* [4*cap_rounds]: contigs, members, consensus bytes, singles */, int cap_rounds);
-/* ------------------------------------------------------------------ */
 /* mm_idx_generation / mm_idx_get (kthread_idx.c:170,84)                */
 /* ------------------------------------------------------------------ */
 typedef struct mcb_index mcb_index;
@@ -200,6 +173,8 @@ typedef struct {
 	const uint32_t *claim_contig; /* index into the contig list passed in */
 	const uint32_t *claim_sg;     /* index into sg (sg_flag[claim_sg]=true) */
 	const uint64_t *claim_y;      /* rid<<32 | jj<<1 | dir  (kthread_hash_realign.c:405,472) */
+	const uint64_t *claim_prio;   /* (window index over all contigs)<<5 | reverse<<4 | dictionary: the step of the reference's
+	                                 window loop that made the claim; ascending along the list (sharding: the merge key) */
 	/* singles diverted to the near-poly-A / near-poly-T lists (bbhashdict.c:157-216), ascending sg index */
 	uint64_t n_fpA, n_fpT;
 	const uint32_t *fpA_sg, *fpT_sg;
@@ -224,22 +199,39 @@ typedef struct {
 int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off,
                 uint64_t n_contigs, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res);
 
-/* Stage 2 sharded: every rank holds all singles and a contiguous range of the contigs.  window_base = number of contig
- * windows on lower ranks.  mcb_realign_begin runs the search and exposes the per-single claim priorities (u64[n_sg], all
- * ones = unclaimed); the caller min-reduces them over the ranks in place; mcb_realign_finish then emits the claims that
- * fall on this rank's contigs.  Rank-order concatenation of the claim lists is the single-GPU list. */
 #define MCB_CLAIM_NONE 0x7F7F7F7F7F7F7F7Fll
-int mcb_realign_begin(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
-                      uint64_t window_base, int threshold, int maxsearch, int ininumdict, void **d_claim);
-int mcb_realign_finish(mcb_ctx *ctx, mcb_realign_result *res);
-/* Key-sharded variant (the one minicom_b200/shard.py uses): every rank is given ALL contigs and all singles, keeps share
- * tab_rank of tab_ranks of the contig lt-mer table (hash ranges), probes only the lt-mers it owns — so the probe work per rank
- * does not grow with the number of GPUs — and, after the caller's min-reduce, emits the claims of windows [g_lo, g_hi) with
- * GLOBAL contig indices.  *maxbin_upper: upper bound of the largest dictionary bin counted on this rank; if the maximum over
- * the ranks exceeds maxsearch the caller must stop (the sequential bin-window replay exists only on one GPU). */
-int mcb_realign_begin_keyed(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
-                            int tab_rank, int tab_ranks, uint64_t g_lo, uint64_t g_hi, int threshold, int maxsearch, int ininumdict,
-                            void **d_claim, uint64_t *maxbin_upper);
+
+/* ------------------------------------------------------------------ */
+/* the same path over the GPUs of one box                */
+/* ------------------------------------------------------------------ */
+/* One context per GPU — one per process (torchrun-style launch) or several in one process, one host thread each (the drop-in
+ * host program: dropin/mcb_dropin.cpp with MCB_DEVICES=0,1,...).  The contexts of a job share an NCCL communicator; all data
+ * movement between GPUs (grouped ncclSend/ncclRecv over NVLink) happens inside the library, on the context's stream.
+ *
+ *   reads    contiguous read-id ranges: rank r loads [rid_base, rid_base + n) with mcb_for_reads* after mcb_shard_begin
+ *   buckets  the 16384 minimizer buckets in contiguous ranges, owner = bucket * n_ranks >> 14; every round of kt_for_bucket
+ *            sends each tuple, together with the 2-bit packed row of its read, to the owner of its bucket
+ *   index    every rank builds (mcb_idx_build) the buckets it owns
+ *   Stage 2  a rank realigns the singles it produced in Stage 1 against ALL contigs (mcb_shard_realign)
+ *
+ * The job's results are the ranks' results concatenated in rank order — round by round for kt_for_bucket (round_counts) — and
+ * the claim lists merged by (claim_prio ascending, claim_sg descending); that reproduces one GPU (= the single-threaded
+ * reference) bit for bit.  Functions marked "collective" must be called by every rank of the communicator. */
+#define MCB_NCCL_ID_BYTES 128
+int mcb_shard_unique_id(void *id128);                                               /* ncclGetUniqueId; one rank makes it, all ranks pass it to mcb_shard_init */
+int mcb_shard_init(mcb_ctx *ctx, const void *id128, int rank, int n_ranks);        /* collective: ncclCommInitRank on the context's device */
+int mcb_shard_attach(mcb_ctx *ctx, void *nccl_comm, int rank, int n_ranks);        /* or: use a communicator (ncclComm_t) the caller made, e.g. with ncclCommInitAll */
+int mcb_shard_begin(mcb_ctx *ctx, uint64_t n_total, uint64_t rid_base);            /* a new job of n_total reads; read ids are global from here on */
+/* kt_for_bucket over the job (collective).  res: this rank's seed contigs / singles / index tuples in its own round order, contig
+ * ids inside res->mi global; round_counts[4 r .. 4 r + 3] = contigs, members, consensus bytes, singles contributed by round r. */
+int mcb_shard_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res, uint64_t *round_counts, int cap_rounds);
+/* realign_hash over the job (collective).  sg: the singles of the job's list that THIS rank produced in Stage 1, in the list's
+ * order; sg_index: their positions in the job's list (ascending); n_sg_total: length of the job's list.  refs / ref_off: ALL
+ * contigs (NULL, NULL reuses the previous call's, as in mcb_realign).  res: the claims on this rank's singles in the reference's
+ * append order, claim_contig global, claim_sg / fpA_sg / fpT_sg positions in the job's list.  Dictionary bins span the singles
+ * of the whole job: their sizes are bounded collectively, and bins above maxsearch are replayed like on one GPU. */
+int mcb_shard_realign(mcb_ctx *ctx, const uint32_t *sg, const uint32_t *sg_index, uint64_t n_sg_local, uint64_t n_sg_total,
+                      const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res);
 
 /* ------------------------------------------------------------------ */
 /* host-side boundary helpers                                           */
@@ -256,7 +248,8 @@ uint64_t mcb_hash64(uint64_t key, uint64_t mask);
 /* measurement                                                          */
 /* ------------------------------------------------------------------ */
 /* Device-time accounting (CUDA events on the library's stream).  Timer names: "for_reads", "for_bucket",
- * "idx_build", "realign" (whole entry point, device work only), "h2d", "d2h", and per-kernel names "k:<kernel>".
+ * "idx_build", "realign" (whole entry point, device work only), "h2d", "d2h", per-kernel names "k:<kernel>", and, sharded,
+ * "nccl:<what>" (CUDA-event time of the collectives) plus "nccl_bytes_sent" (bytes, not milliseconds).
  * mcb_timer_get returns accumulated milliseconds and the launch count; mcb_timers_reset zeroes everything. */
 void   mcb_timers_enable(mcb_ctx *ctx, int on);
 void   mcb_timers_reset(mcb_ctx *ctx);

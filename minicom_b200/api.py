@@ -42,7 +42,7 @@ class _BucketResult(C.Structure):
 
 class _RealignResult(C.Structure):
     _fields_ = [("n_claims", C.c_uint64), ("claim_contig", C.c_void_p), ("claim_sg", C.c_void_p), ("claim_y", C.c_void_p),
-                ("n_fpA", C.c_uint64), ("n_fpT", C.c_uint64), ("fpA_sg", C.c_void_p), ("fpT_sg", C.c_void_p),
+                ("claim_prio", C.c_void_p), ("n_fpA", C.c_uint64), ("n_fpT", C.c_uint64), ("fpA_sg", C.c_void_p), ("fpT_sg", C.c_void_p),
                 ("n_windows", C.c_uint64), ("n_probes", C.c_uint64), ("n_candidates", C.c_uint64),
                 ("n_dict_keys", C.c_uint64), ("numdict", C.c_int32)]
 
@@ -55,10 +55,9 @@ EXPORTS = [
     "mcb_realign", "mcb_sketch_lh_host", "mcb_sketch_two_host", "mcb_hash64",
     "mcb_timers_enable", "mcb_timers_reset", "mcb_timer_get", "mcb_timers_dump", "mcb_kernel_launches",
     "mcb_round_control_init", "mcb_round_control_begin", "mcb_round_control_end",
-    "mcb_shard_begin", "mcb_shard_partition", "mcb_shard_recv_buffer", "mcb_shard_set_tuples", "mcb_shard_packed",
-    "mcb_shard_get_nreads", "mcb_shard_set_nreads", "mcb_bucket_round_a", "mcb_bucket_round_b", "mcb_bucket_finish",
-    "mcb_realign_begin", "mcb_realign_finish", "mcb_realign_begin_keyed",
+    "mcb_shard_unique_id", "mcb_shard_init", "mcb_shard_attach", "mcb_shard_begin", "mcb_shard_for_bucket", "mcb_shard_realign",
 ]
+NCCL_ID_BYTES = 128
 
 
 class RoundControl(C.Structure):
@@ -120,21 +119,13 @@ def load_library() -> C.CDLL:
     lib.mcb_round_control_init.restype = None
     lib.mcb_round_control_begin.argtypes = [C.POINTER(RoundControl), C.c_int, C.c_int]
     lib.mcb_round_control_end.argtypes = [C.POINTER(RoundControl), C.c_uint64]
-    lib.mcb_shard_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
-    lib.mcb_shard_partition.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
-    lib.mcb_shard_recv_buffer.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
-    lib.mcb_shard_set_tuples.argtypes = [C.c_void_p, C.c_uint64]
-    lib.mcb_shard_packed.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
-    lib.mcb_shard_get_nreads.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
-    lib.mcb_shard_set_nreads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
-    lib.mcb_bucket_round_a.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
-    lib.mcb_bucket_round_b.argtypes = [C.c_void_p, C.c_uint64]
-    lib.mcb_bucket_finish.argtypes = [C.c_void_p, C.POINTER(_BucketResult), C.c_void_p, C.c_int]
-    lib.mcb_realign_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
-                                      C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
-    lib.mcb_realign_finish.argtypes = [C.c_void_p, C.POINTER(_RealignResult)]
-    lib.mcb_realign_begin_keyed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
-                                            C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.mcb_shard_unique_id.argtypes = [C.c_void_p]
+    lib.mcb_shard_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.mcb_shard_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.mcb_shard_begin.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.mcb_shard_for_bucket.argtypes = [C.c_void_p, C.POINTER(_BucketResult), C.c_void_p, C.c_int]
+    lib.mcb_shard_realign.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                      C.c_int, C.c_int, C.c_int, C.POINTER(_RealignResult)]
     _lib = lib
     return lib
 
@@ -211,6 +202,7 @@ class RealignResult:
     claim_contig: np.ndarray
     claim_sg: np.ndarray
     claim_y: np.ndarray
+    claim_prio: np.ndarray
     fpA_sg: np.ndarray
     fpT_sg: np.ndarray
     n_windows: int
@@ -344,10 +336,7 @@ class Context:
             ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
             self._check(self.lib.mcb_realign(self._h, sg.ctypes.data, len(sg), refs.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1,
                                              threshold, maxsearch, ininumdict, C.byref(r)))
-        n = r.n_claims
-        return RealignResult(_view(r.claim_contig, n, np.uint32), _view(r.claim_sg, n, np.uint32), _view(r.claim_y, n, np.uint64),
-                             _view(r.fpA_sg, r.n_fpA, np.uint32), _view(r.fpT_sg, r.n_fpT, np.uint32),
-                             int(r.n_windows), int(r.n_probes), int(r.n_candidates), int(r.n_dict_keys), int(r.numdict))
+        return self._realign_result(r)
 
     def _bucket_result(self, r: _BucketResult) -> BucketResult:
         nc, m = r.n_clusters, self.params.first_mininum
@@ -361,87 +350,37 @@ class Context:
     def _realign_result(self, r: _RealignResult) -> RealignResult:
         n = r.n_claims
         return RealignResult(_view(r.claim_contig, n, np.uint32), _view(r.claim_sg, n, np.uint32), _view(r.claim_y, n, np.uint64),
-                             _view(r.fpA_sg, r.n_fpA, np.uint32), _view(r.fpT_sg, r.n_fpT, np.uint32),
+                             _view(r.claim_prio, n, np.uint64), _view(r.fpA_sg, r.n_fpA, np.uint32), _view(r.fpT_sg, r.n_fpT, np.uint32),
                              int(r.n_windows), int(r.n_probes), int(r.n_candidates), int(r.n_dict_keys), int(r.numdict))
 
-    # -- sharding (include/minicom_b200.h "sharding across the GPUs of one box"); device pointers are plain ints
-    def shard_begin(self, rank: int, n_ranks: int, n_total: int, rid_base: int):
-        self._check(self.lib.mcb_shard_begin(self._h, rank, n_ranks, n_total, rid_base))
+    # -- the same path over several GPUs (include/minicom_b200.h, "the same path over the GPUs of one box")
+    def shard_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        assert len(unique_id) == NCCL_ID_BYTES
+        self._check(self.lib.mcb_shard_init(self._h, unique_id, rank, n_ranks))
 
-    def shard_partition(self, n_ranks: int):
-        counts = np.zeros(n_ranks, dtype=np.uint64)
-        p = C.c_void_p(0)
-        self._check(self.lib.mcb_shard_partition(self._h, counts.ctypes.data, C.byref(p)))
-        return counts, int(p.value or 0)
+    def shard_begin(self, n_total: int, rid_base: int):
+        self._check(self.lib.mcb_shard_begin(self._h, n_total, rid_base))
 
-    def shard_recv_buffer(self, n_tuples: int):
-        """(receive buffer, current address of the partitioned tuples to send)"""
-        p, q = C.c_void_p(0), C.c_void_p(0)
-        self._check(self.lib.mcb_shard_recv_buffer(self._h, n_tuples, C.byref(p), C.byref(q)))
-        return int(p.value or 0), int(q.value or 0)
-
-    def shard_set_tuples(self, n_tuples: int):
-        self._check(self.lib.mcb_shard_set_tuples(self._h, n_tuples))
-
-    def shard_packed(self):
-        p, rb = C.c_void_p(0), C.c_uint64(0)
-        self._check(self.lib.mcb_shard_packed(self._h, C.byref(p), C.byref(rb)))
-        return int(p.value or 0), int(rb.value)
-
-    def shard_get_nreads(self):
-        r, m, n = C.c_void_p(0), C.c_void_p(0), C.c_uint64(0)
-        self._check(self.lib.mcb_shard_get_nreads(self._h, C.byref(r), C.byref(m), C.byref(n)))
-        ws = ((((self.params.readlen + 31) // 32) + 1) & ~1)
-        return _view(r.value, n.value, np.uint32), _view(m.value, n.value * ws, np.uint64).reshape(-1, ws)
-
-    def shard_set_nreads(self, rid: np.ndarray, mask: np.ndarray):
-        rid = np.ascontiguousarray(rid, dtype=np.uint32)
-        mask = np.ascontiguousarray(mask, dtype=np.uint64)
-        self._check(self.lib.mcb_shard_set_nreads(self._h, rid.ctypes.data, mask.ctypes.data, len(rid)))
-
-    def bucket_round_a(self, rnd: int, is_last: int):
-        out = np.zeros(4, dtype=np.uint64)
-        self._check(self.lib.mcb_bucket_round_a(self._h, rnd, is_last, out.ctypes.data))
-        return [int(x) for x in out]          # new contigs, members, singles, rejects
-
-    def bucket_round_b(self, cid_first: int):
-        self._check(self.lib.mcb_bucket_round_b(self._h, cid_first))
-
-    def bucket_finish(self, cap_rounds: int = 64):
+    def shard_for_bucket(self, cap_rounds: int = 64):
+        """(this rank's BucketResult, per-round counts (n_rounds, 4): contigs, members, consensus bytes, singles)"""
         r = _BucketResult()
         rc = np.zeros(4 * cap_rounds, dtype=np.uint64)
-        self._check(self.lib.mcb_bucket_finish(self._h, C.byref(r), rc.ctypes.data, cap_rounds))
+        self._check(self.lib.mcb_shard_for_bucket(self._h, C.byref(r), rc.ctypes.data, cap_rounds))
         return self._bucket_result(r), rc.reshape(cap_rounds, 4)[:int(r.rounds)].copy()
 
-    def realign_begin(self, sg, refs, ref_off, window_base, threshold, maxsearch, ininumdict=0) -> int:
+    def shard_realign(self, sg, sg_index, n_sg_total, refs, ref_off, threshold, maxsearch, ininumdict=0) -> RealignResult:
         sg = np.ascontiguousarray(sg, dtype=np.uint32)
-        p = C.c_void_p(0)
-        if refs is None:
-            self._check(self.lib.mcb_realign_begin(self._h, sg.ctypes.data, len(sg), None, None, 0, window_base, threshold, maxsearch, ininumdict, C.byref(p)))
-        else:
-            refs = np.ascontiguousarray(refs, dtype=np.uint8)
-            ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
-            self._check(self.lib.mcb_realign_begin(self._h, sg.ctypes.data, len(sg), refs.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1,
-                                                   window_base, threshold, maxsearch, ininumdict, C.byref(p)))
-        return int(p.value or 0)
-
-    def realign_begin_keyed(self, sg, refs, ref_off, tab_rank, tab_ranks, g_lo, g_hi, threshold, maxsearch, ininumdict=0):
-        """(device pointer of the claim priorities, upper bound of this rank's largest dictionary bin)"""
-        sg = np.ascontiguousarray(sg, dtype=np.uint32)
-        p, mb = C.c_void_p(0), C.c_uint64(0)
-        if refs is None:
-            self._check(self.lib.mcb_realign_begin_keyed(self._h, sg.ctypes.data, len(sg), None, None, 0, tab_rank, tab_ranks, g_lo, g_hi,
-                                                         threshold, maxsearch, ininumdict, C.byref(p), C.byref(mb)))
-        else:
-            refs = np.ascontiguousarray(refs, dtype=np.uint8)
-            ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
-            self._check(self.lib.mcb_realign_begin_keyed(self._h, sg.ctypes.data, len(sg), refs.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1,
-                                                         tab_rank, tab_ranks, g_lo, g_hi, threshold, maxsearch, ininumdict, C.byref(p), C.byref(mb)))
-        return int(p.value or 0), int(mb.value)
-
-    def realign_finish(self) -> RealignResult:
+        sg_index = np.ascontiguousarray(sg_index, dtype=np.uint32)
+        assert len(sg) == len(sg_index)
         r = _RealignResult()
-        self._check(self.lib.mcb_realign_finish(self._h, C.byref(r)))
+        if refs is None:
+            self._check(self.lib.mcb_shard_realign(self._h, sg.ctypes.data, sg_index.ctypes.data, len(sg), n_sg_total, None, None, 0,
+                                                   threshold, maxsearch, ininumdict, C.byref(r)))
+        else:
+            refs = np.ascontiguousarray(refs, dtype=np.uint8)
+            ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
+            self._check(self.lib.mcb_shard_realign(self._h, sg.ctypes.data, sg_index.ctypes.data, len(sg), n_sg_total, refs.ctypes.data, ref_off.ctypes.data,
+                                                   len(ref_off) - 1, threshold, maxsearch, ininumdict, C.byref(r)))
         return self._realign_result(r)
 
     # -- measurement

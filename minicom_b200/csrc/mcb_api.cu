@@ -66,14 +66,18 @@ extern "C" int mcb_create(const mcb_params *p, mcb_ctx **out)
 	return MCB_OK;
 }
 
+void mcb_shard_release(mcb_ctx *ctx);      // mcb_shard.cu
+
 extern "C" void mcb_destroy(mcb_ctx *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->prm.device);
 	cudaStreamSynchronize(ctx->stream);
+	mcb_shard_release(ctx);
 	ctx->tm.collect();
 	for (auto e : ctx->tm.pool) cudaEventDestroy(e);
-	DBuf *db[] = { &ctx->d_ascii, &ctx->d_packed, &ctx->d_cls, &ctx->d_elemA, &ctx->d_elemB, &ctx->d_counters, &ctx->d_nread_rid, &ctx->d_nread_mask, &ctx->d_sort_hist };
+	DBuf *db[] = { &ctx->d_ascii, &ctx->d_packed, &ctx->d_cls, &ctx->d_elemA, &ctx->d_elemB, &ctx->d_counters, &ctx->d_nread_rid, &ctx->d_nread_mask, &ctx->d_sort_hist,
+	               &ctx->d_rows_send, &ctx->d_rows_recv, &ctx->d_coll };
 	for (auto b : db) b->release();
 	for (auto &b : ctx->d_scr) b.release();
 	for (auto &b : ctx->d_scan_tmp) b.release();
@@ -82,7 +86,7 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 	{ McbContigIndex &c = ctx->cix; DBuf *cb[] = { &c.refs, &c.roff, &c.cwo, &c.wo, &c.cw, &c.pblk, &c.ptab, &c.ents, &c.ents2, &c.eoff, &c.meta, &c.flt, &c.sgmap }; for (auto b : cb) b->release(); }
 	HBuf *hb[] = { &ctx->h_cls, &ctx->h_nrid, &ctx->h_nrepl, &ctx->h_noff, &ctx->h_npos, &ctx->h_nmask, &ctx->h_counters, &ctx->h_stage,
 	               &ctx->h_cl_n, &ctx->h_cl_a_off, &ctx->h_cl_a, &ctx->h_cl_ref_off, &ctx->h_cl_ref, &ctx->h_sg, &ctx->h_mi_cnt, &ctx->h_mi,
-	               &ctx->h_claim_c, &ctx->h_claim_s, &ctx->h_claim_y, &ctx->h_fpA, &ctx->h_fpT, &ctx->h_in0, &ctx->h_in1, &ctx->h_in2 };
+	               &ctx->h_claim_c, &ctx->h_claim_s, &ctx->h_claim_y, &ctx->h_claim_p, &ctx->h_fpA, &ctx->h_fpT, &ctx->h_in0, &ctx->h_in1, &ctx->h_in2, &ctx->h_coll };
 	for (auto b : hb) b->release();
 	cudaStreamDestroy(ctx->stream);
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

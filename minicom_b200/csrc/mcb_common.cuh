@@ -153,8 +153,7 @@ struct McbContigIndex {
 	bool valid = false;
 	uint64_t n_contigs = 0, ref_bytes = 0, total_words = 0, n_windows = 0, n_entries = 0;
 	int L = 0, lt = 0, pbits = 0;
-	int tab_rank = 0, tab_ranks = 1;   // which share of the lt-mer table this context holds (key-sharded Stage 2), else 0 of 1
-	uint32_t b_lo = 0, b_hi = 0;         // table buckets [b_lo, b_hi) of the 2^pbits
+	uint32_t b_lo = 0, b_hi = 0;         // table buckets [b_lo, b_hi) of the 2^pbits (the whole table)
 	DBuf refs;      // ASCII consensus strings, concatenated (kept to recognise an identical contig set)
 	DBuf roff;      // u64[n_contigs+1] offsets into refs
 	DBuf cwo;       // u64[n_contigs+1] word offsets of the packed contigs
@@ -191,10 +190,9 @@ struct McbBucketState {
 // mcb_realign between its two halves (search / claim emission)
 struct McbRealignState {
 	bool pending = false;
-	uint64_t S = 0, window_base = 0;
-	uint64_t g_lo = 0, g_hi = 0, g_sub = 0;   // claims of windows [g_lo, g_hi) are emitted here; g_sub = window index of this context's first contig
+	uint64_t S = 0;
 	int nd = 0;
-	mcb_realign_result result;                // counters of the search half, handed out by mcb_realign_finish
+	bool have_index = false;                  // sharded: d_x[1] holds the position of every local single in the job's sg list
 };
 
 struct mcb_ctx {
@@ -208,6 +206,10 @@ struct mcb_ctx {
 	uint64_t n_reads = 0;                // size of the read-id space (all reads of the job; == n_local unless sharded)
 	uint64_t n_local = 0, rid_base = 0;  // this context's slice [rid_base, rid_base + n_local)
 	int shard_rank = 0, shard_n = 1;
+	void *comm = nullptr;                // ncclComm_t of this rank (mcb_shard.cu); null on a single GPU
+	bool own_comm = false;
+	DBuf d_rows_send, d_rows_recv, d_coll;   // sharded Stage 1: packed rows travelling with their tuples; small collectives
+	HBuf h_coll;
 	uint64_t elem_cap = 0;               // capacity (elements) of d_elemA / d_elemB
 	bool reads_loaded = false, bucket_done = false;
 	McbBucketState bs;
@@ -232,7 +234,7 @@ struct mcb_ctx {
 	// host result buffers
 	HBuf h_cls, h_nrid, h_nrepl, h_noff, h_npos, h_nmask, h_counters, h_stage;
 	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref, h_sg, h_mi_cnt, h_mi;
-	HBuf h_claim_c, h_claim_s, h_claim_y, h_fpA, h_fpT, h_in0, h_in1, h_in2;
+	HBuf h_claim_c, h_claim_s, h_claim_y, h_claim_p, h_fpA, h_fpT, h_in0, h_in1, h_in2;
 	std::vector<uint64_t> tmp_off;
 };
 
@@ -431,6 +433,11 @@ int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t 
 int mcb_h2d(mcb_ctx *ctx, void *dst, const void *src, size_t bytes, int n_threads);
 int mcb_h2d_on(mcb_ctx *ctx, cudaStream_t stream, void *dst, const void *src, size_t bytes, int n_threads);
 int mcb_copy_streams(mcb_ctx *ctx);   // creates copy_stream / copy_stream2 on first use
+
+// collectives over the context's communicator, enqueued on ctx->stream (mcb_shard.cu)
+int mcb_coll_allreduce_sum_u64(mcb_ctx *ctx, unsigned long long *d_inout, size_t n);
+int mcb_coll_allreduce_sum_u32(mcb_ctx *ctx, uint32_t *d_inout, size_t n);
+int mcb_coll_allgatherv(mcb_ctx *ctx, const void *d_send, uint64_t bytes, std::vector<unsigned long long> &host_out);   // variable-size all-gather of 8-byte words to the host, rank order
 
 static inline unsigned mcb_grid_for(uint64_t n, unsigned block, unsigned cap = 0x7FFFFFFFu)
 {

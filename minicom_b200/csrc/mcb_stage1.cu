@@ -1093,7 +1093,7 @@ struct BucketBufs {
 };
 static inline int consensus_cols(const mcb_ctx *ctx) { return ((2 * ctx->L + 2 * ctx->prm.max_rounds + 8 + 31) / 32) * 32; }
 
-static int bucket_begin(mcb_ctx *ctx)
+int mcb_bucket_begin(mcb_ctx *ctx)
 {
 	if (!ctx->reads_loaded || ctx->bucket_done) { mcb_set_error("kt_for_bucket: needs a fresh mcb_for_reads"); return MCB_ESTATE; }
 	McbBucketState &bs = ctx->bs;
@@ -1107,7 +1107,7 @@ static int bucket_begin(mcb_ctx *ctx)
 }
 
 // sort + group + consensus of the current tuples; leaves the per-round totals in bs (n_cl_new, n_mem_new, n_sg_new, n_resk)
-static int bucket_round_a(mcb_ctx *ctx, int r, int is_last)
+int mcb_bucket_round_a_impl(mcb_ctx *ctx, int r, int is_last)
 {
 	McbBucketState &bs = ctx->bs;
 	if (!bs.active || bs.half) { mcb_set_error("bucket round: call order violated"); return MCB_ESTATE; }
@@ -1206,7 +1206,7 @@ static int bucket_round_a(mcb_ctx *ctx, int r, int is_last)
 }
 
 // scatter into the accumulated outputs, index tuples of the new seed contigs (ids cid_first, cid_first+1, ...), re-sketch of the rejects
-static int bucket_round_b(mcb_ctx *ctx, uint64_t cid_first)
+int mcb_bucket_round_b_impl(mcb_ctx *ctx, uint64_t cid_first)
 {
 	McbBucketState &bs = ctx->bs;
 	if (!bs.active || !bs.half) { mcb_set_error("bucket round: call order violated"); return MCB_ESTATE; }
@@ -1267,8 +1267,16 @@ static int bucket_round_b(mcb_ctx *ctx, uint64_t cid_first)
 	return MCB_OK;
 }
 
-static int bucket_finish(mcb_ctx *ctx, mcb_bucket_result *res)
+int mcb_bucket_finish_impl(mcb_ctx *ctx, mcb_bucket_result *res, uint64_t *round_counts, int cap_rounds)
 {
+	{
+		const McbBucketState &b0 = ctx->bs;
+		const int nr = (int)b0.round_cl.size();
+		if (round_counts) {
+			if (cap_rounds < nr) { mcb_set_error("kt_for_bucket: %d rounds, room for %d", nr, cap_rounds); return MCB_EINVAL; }
+			for (int i = 0; i < nr; ++i) { round_counts[4 * i] = b0.round_cl[i]; round_counts[4 * i + 1] = b0.round_mem[i]; round_counts[4 * i + 2] = b0.round_ref[i]; round_counts[4 * i + 3] = b0.round_sg[i]; }
+		}
+	}
 	McbBucketState &bs = ctx->bs;
 	if (!bs.active || bs.half) { mcb_set_error("bucket finish: call order violated"); return MCB_ESTATE; }
 	BucketBufs B(ctx);
@@ -1327,127 +1335,28 @@ extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)
 {
 	MCB_TRY(check_ctx(ctx));
 	if (!res) { mcb_set_error("mcb_for_bucket: null result"); return MCB_EINVAL; }
-	if (ctx->shard_n > 1) { mcb_set_error("mcb_for_bucket: context is sharded, drive the rounds with mcb_bucket_round_a/_b"); return MCB_ESTATE; }
-	MCB_TRY(bucket_begin(ctx));
+	if (ctx->shard_n > 1) { mcb_set_error("mcb_for_bucket: context is sharded, use mcb_shard_for_bucket"); return MCB_ESTATE; }
+	MCB_TRY(mcb_bucket_begin(ctx));
 	mcb_round_control rc; mcb_round_control_init(&rc);
 	for (;;) {
 		const int is_last = mcb_round_control_begin(&rc, ctx->prm.k, ctx->prm.max_rounds);
-		MCB_TRY(bucket_round_a(ctx, rc.round, is_last));
-		MCB_TRY(bucket_round_b(ctx, ctx->bs.tot_cl));
+		MCB_TRY(mcb_bucket_round_a_impl(ctx, rc.round, is_last));
+		MCB_TRY(mcb_bucket_round_b_impl(ctx, ctx->bs.tot_cl));
 		if (mcb_round_control_end(&rc, ctx->bs.tot_mem)) break;
 	}
-	return bucket_finish(ctx, res);
+	return mcb_bucket_finish_impl(ctx, res, nullptr, 0);
 }
 
-// ---------------------------------------------------------------- sharding (one context per GPU, see include/minicom_b200.h)
-extern "C" int mcb_shard_begin(mcb_ctx *ctx, int rank, int n_ranks, uint64_t n_total, uint64_t rid_base)
+// room for n_tuples (+1) in both halves of the sort double buffer; the current half (bs.cur, bs.n_in elements) survives
+int mcb_elems_reserve(mcb_ctx *ctx, uint64_t n_tuples)
 {
-	MCB_TRY(check_ctx(ctx));
-	if (n_ranks < 1 || n_ranks > 255 || rank < 0 || rank >= n_ranks || rid_base > n_total) { mcb_set_error("mcb_shard_begin: bad arguments"); return MCB_EINVAL; }
-	if (n_total >= (1ull << 31)) { mcb_set_error("too many reads (rid is a signed 32-bit int in the reference, kthread_bucket.c:48)"); return MCB_EINVAL; }
-	ctx->shard_rank = rank; ctx->shard_n = n_ranks; ctx->n_reads = n_total; ctx->rid_base = rid_base;
-	ctx->reads_loaded = false; ctx->bucket_done = false; ctx->bs.active = false;
-	return MCB_OK;
-}
-
-int mcb_partition_by_owner(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, int n_ranks, uint64_t *counts /* host [n_ranks+1] */);   // mcb_sort.cu
-
-extern "C" int mcb_shard_partition(mcb_ctx *ctx, uint64_t *counts, void **d_tuples)
-{
-	MCB_TRY(check_ctx(ctx));
-	if (!counts || !d_tuples) { mcb_set_error("mcb_shard_partition: null argument"); return MCB_EINVAL; }
 	McbBucketState &bs = ctx->bs;
-	if (!ctx->reads_loaded) { mcb_set_error("mcb_shard_partition: no reads loaded"); return MCB_ESTATE; }
-	if (!bs.active) MCB_TRY(bucket_begin(ctx));
-	if (bs.half) { mcb_set_error("mcb_shard_partition: round in progress"); return MCB_ESTATE; }
-	std::vector<uint64_t> c((size_t)ctx->shard_n + 1, 0);
-	MCB_TRY(mcb_partition_by_owner(ctx, bs.cur, bs.alt, bs.n_in, ctx->shard_n, c.data()));
-	if (bs.n_in > 1) { ulonglong2 *t = bs.cur; bs.cur = bs.alt; bs.alt = t; }
-	for (int i = 0; i < ctx->shard_n; ++i) counts[i] = c[i];
-	*d_tuples = bs.cur;
+	if (n_tuples + 1 <= ctx->elem_cap) return MCB_OK;
+	const bool cur_is_A = bs.cur == ctx->d_elemA.as<ulonglong2>();
+	DBuf &keep = cur_is_A ? ctx->d_elemA : ctx->d_elemB, &other = cur_is_A ? ctx->d_elemB : ctx->d_elemA;
+	MCB_TRY(other.ensure((n_tuples + 1) * 16 + 16));
+	MCB_TRY(grow_preserve(ctx, keep, bs.n_in * 16, (n_tuples + 1) * 16 + 16));
+	ctx->elem_cap = std::min(ctx->d_elemA.cap, ctx->d_elemB.cap) / 16;
+	bs.cur = keep.as<ulonglong2>(); bs.alt = other.as<ulonglong2>();
 	return MCB_OK;
-}
-
-extern "C" int mcb_shard_recv_buffer(mcb_ctx *ctx, uint64_t n_tuples, void **d_recv, void **d_send)
-{
-	MCB_TRY(check_ctx(ctx));
-	McbBucketState &bs = ctx->bs;
-	if (!bs.active || bs.half || !d_recv || !d_send) { mcb_set_error("mcb_shard_recv_buffer: call order violated"); return MCB_ESTATE; }
-	if (n_tuples + 1 > ctx->elem_cap) {
-		// grow both halves of the sort double buffer; the send side (bs.cur) must survive
-		const bool cur_is_A = bs.cur == ctx->d_elemA.as<ulonglong2>();
-		DBuf &keep = cur_is_A ? ctx->d_elemA : ctx->d_elemB, &other = cur_is_A ? ctx->d_elemB : ctx->d_elemA;
-		MCB_TRY(other.ensure((n_tuples + 1) * 16 + 16));
-		MCB_TRY(grow_preserve(ctx, keep, bs.n_in * 16, (n_tuples + 1) * 16 + 16));
-		ctx->elem_cap = std::min(ctx->d_elemA.cap, ctx->d_elemB.cap) / 16;
-		bs.cur = keep.as<ulonglong2>(); bs.alt = other.as<ulonglong2>();
-	}
-	*d_recv = bs.alt; *d_send = bs.cur;     // growing the buffers may have moved the partitioned tuples
-	return MCB_OK;
-}
-
-extern "C" int mcb_shard_set_tuples(mcb_ctx *ctx, uint64_t n_tuples)
-{
-	MCB_TRY(check_ctx(ctx));
-	McbBucketState &bs = ctx->bs;
-	if (!bs.active || bs.half) { mcb_set_error("mcb_shard_set_tuples: call order violated"); return MCB_ESTATE; }
-	if (n_tuples > ctx->elem_cap) { mcb_set_error("mcb_shard_set_tuples: more tuples than mcb_shard_recv_buffer reserved"); return MCB_EINVAL; }
-	ulonglong2 *t = bs.cur; bs.cur = bs.alt; bs.alt = t;      // the receive buffer becomes the input of the next round
-	bs.n_in = bs.n_valid = n_tuples;
-	return MCB_OK;
-}
-
-extern "C" int mcb_shard_packed(mcb_ctx *ctx, void **d_packed, uint64_t *row_bytes)
-{
-	MCB_TRY(check_ctx(ctx));
-	if (!ctx->reads_loaded) { mcb_set_error("mcb_shard_packed: no reads loaded"); return MCB_ESTATE; }
-	*d_packed = ctx->d_packed.p; *row_bytes = (uint64_t)ctx->WS * 8;
-	return MCB_OK;
-}
-
-// the side table of reads that contained N, for all reads of the job (ascending rid); replaces the slice-local one
-extern "C" int mcb_shard_set_nreads(mcb_ctx *ctx, const uint32_t *rid, const uint64_t *mask, uint64_t n)
-{
-	MCB_TRY(check_ctx(ctx));
-	const int WS = ctx->WS;
-	MCB_TRY(ctx->d_nread_rid.ensure(n * 4 + 16)); MCB_TRY(ctx->d_nread_mask.ensure(n * WS * 8 + 16));
-	if (n) {
-		MCB_CUDA(cudaMemcpyAsync(ctx->d_nread_rid.p, rid, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-		MCB_CUDA(cudaMemcpyAsync(ctx->d_nread_mask.p, mask, n * WS * 8, cudaMemcpyHostToDevice, ctx->stream));
-		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-	}
-	ctx->n_nreads = n;
-	return MCB_OK;
-}
-extern "C" int mcb_shard_get_nreads(mcb_ctx *ctx, const uint32_t **rid, const uint64_t **mask, uint64_t *n)
-{
-	MCB_TRY(check_ctx(ctx));
-	*rid = ctx->h_nrid.as<uint32_t>(); *mask = ctx->h_nmask.as<uint64_t>(); *n = ctx->n_nreads;
-	return MCB_OK;
-}
-
-extern "C" int mcb_bucket_round_a(mcb_ctx *ctx, int round, int is_last, uint64_t *out4)
-{
-	MCB_TRY(check_ctx(ctx));
-	if (!ctx->bs.active) MCB_TRY(bucket_begin(ctx));
-	MCB_TRY(bucket_round_a(ctx, round, is_last));
-	if (out4) { out4[0] = ctx->bs.n_cl_new; out4[1] = ctx->bs.n_mem_new; out4[2] = ctx->bs.n_sg_new; out4[3] = ctx->bs.n_resk; }
-	return MCB_OK;
-}
-extern "C" int mcb_bucket_round_b(mcb_ctx *ctx, uint64_t cid_first)
-{
-	MCB_TRY(check_ctx(ctx));
-	return bucket_round_b(ctx, cid_first);
-}
-extern "C" int mcb_bucket_finish(mcb_ctx *ctx, mcb_bucket_result *res, uint64_t *round_counts /* [4*rounds]: clusters, members, ref bytes, singles per round */, int cap_rounds)
-{
-	MCB_TRY(check_ctx(ctx));
-	if (!res) { mcb_set_error("mcb_bucket_finish: null result"); return MCB_EINVAL; }
-	const McbBucketState &bs = ctx->bs;
-	const int nr = (int)bs.round_cl.size();
-	if (round_counts) {
-		if (cap_rounds < nr) { mcb_set_error("mcb_bucket_finish: %d rounds, room for %d", nr, cap_rounds); return MCB_EINVAL; }
-		for (int i = 0; i < nr; ++i) { round_counts[4 * i] = bs.round_cl[i]; round_counts[4 * i + 1] = bs.round_mem[i]; round_counts[4 * i + 2] = bs.round_ref[i]; round_counts[4 * i + 3] = bs.round_sg[i]; }
-	}
-	return bucket_finish(ctx, res);
 }

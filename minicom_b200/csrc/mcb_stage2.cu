@@ -24,8 +24,9 @@
 //   rare                  realign_exact_bins    bins larger than maxsearch: their singles are replayed in order on the host
 //
 // Probes per round drop from 9 per window (4.7e8 at 10 M reads) to 2 per (single, dictionary) (3e7 in the first round,
-// 3e6 later), and only true key matches touch the contigs.  Sharded over G GPUs, the table is partitioned by hash range
-// (mcb_realign_begin_keyed): a context keeps the buckets [b_lo, b_hi) and probes only the lt-mers that fall into them.
+// 3e6 later), and only true key matches touch the contigs.  Sharded over G GPUs (mcb_shard_realign, mcb_shard.cu) every rank
+// runs this same path on the singles IT produced in Stage 1 (their packed rows are local) against all contigs — packed contigs
+// are a few bytes per read — so no claim ever crosses ranks; only the dictionary bin-size guard is a collective.
 //
 // Distance is the popcount of the XOR of 2-bit codes (bbhashdict.c:247-254), not a base count: A<->T and C<->G cost 2.
 // The reference's code A=00,G=01,C=10,T=11 (kthread_hash_realign.c:251-258) and ours (A0 C1 G2 T3) differ only by
@@ -156,7 +157,7 @@ __device__ __forceinline__ uint64_t rev_fields(uint64_t v, int nbases)
 	return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
 }
 __global__ void k_s2_filter_insert(const uint64_t *__restrict__ rd, const uint8_t *__restrict__ flagged, const uint32_t *__restrict__ sg, uint64_t S, S2Geom gm,
-                                   uint32_t *__restrict__ flt, uint64_t wmask, uint32_t *__restrict__ sgmap, uint32_t o_lo, uint32_t o_hi)
+                                   uint32_t *__restrict__ flt, uint64_t wmask, uint32_t *__restrict__ sgmap)
 {
 	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= S * (uint64_t)gm.nd) return;
@@ -171,13 +172,10 @@ __global__ void k_s2_filter_insert(const uint64_t *__restrict__ rd, const uint8_
 	if (sh + 2 * lt > 64) v |= row[wi + 1] << (64 - sh);
 	const uint64_t key_f = v & kmask;
 	uint64_t w; uint32_t b;
-	// key-sharded table: only the keys whose lt-mers this context keeps (the same top-16-bit hash range k_s2_kmer_emit tests)
-	uint32_t ob = kmer_bucket(S2_KEY32(key_f), 16);
-	if (ob >= o_lo && ob < o_hi) { flt_slot(key_f, wmask, &w, &b); atomicOr(&flt[w], b); }
+	flt_slot(key_f, wmask, &w, &b); atomicOr(&flt[w], b);
 	if (ds > 0) {
 		const uint64_t key_r = rev_fields(~key_f & kmask, lt);
-		ob = kmer_bucket(S2_KEY32(key_r), 16);
-		if (ob >= o_lo && ob < o_hi) { flt_slot(key_r, wmask, &w, &b); atomicOr(&flt[w], b); }
+		flt_slot(key_r, wmask, &w, &b); atomicOr(&flt[w], b);
 	}
 }
 // are all these singles among the ones the filter was built from?
@@ -195,7 +193,7 @@ __global__ void k_s2_sg_subset(const uint32_t *__restrict__ sg, uint64_t S, cons
 __global__ void __launch_bounds__(256)
 k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_off, const uint64_t *__restrict__ ref_off, const uint64_t *__restrict__ ent_off,
                uint64_t n_contigs, uint64_t total_words, int L, int lt, unsigned long long *__restrict__ ents,
-               int filter, int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long *__restrict__ counter, unsigned long long ents_cap,
+               int filter, unsigned long long *__restrict__ counter, unsigned long long ents_cap,
                const uint32_t *__restrict__ flt, uint64_t flt_mask)
 {
 	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,15 +224,14 @@ k_s2_kmer_emit(const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cw_
 		}
 		return;
 	}
-	// filtered table: keep the lt-mers that pass the key filter and (key-sharded) whose bucket this context owns.  Each thread walks
+	// filtered table: keep the lt-mers that pass the key filter.  Each thread walks
 	// the 32 start positions of ITS word, the warp reserves room with one atomic, and the kept entries are written packed (their
 	// order is irrelevant: they are sorted next).  The keep decisions are remembered in a bit mask for the second sweep.
 	unsigned keepmask = 0;
 #pragma unroll 4
 	for (int j = 0; j < nstart; ++j) {
 		const uint64_t key = ((w0 >> (2 * j)) | (j ? w1 << (64 - 2 * j) : 0ull)) & kmask;
-		const uint32_t bk = kmer_bucket(S2_KEY32(key), pbits);
-		const bool keep = bk >= b_lo && bk < b_hi && (!flt || flt_has(flt, flt_mask, key));
+		const bool keep = flt_has(flt, flt_mask, key);
 		keepmask |= (unsigned)keep << j;
 	}
 	const unsigned mine = __popc(keepmask);
@@ -269,7 +266,7 @@ __global__ void k_s2_bucket_ends(const unsigned long long *__restrict__ ents, ui
 __global__ void k_s2_singles(const uint32_t *__restrict__ sg, uint64_t S, const uint64_t *__restrict__ packed, S2Geom gm,
                              const uint32_t *__restrict__ nread_rid, const uint64_t *__restrict__ nread_mask, uint64_t n_nreads, uint64_t n_reads,
                              uint64_t *__restrict__ rd, uint8_t *__restrict__ flagged, uint32_t *__restrict__ cm, uint64_t cm_mask,
-                             int own_rank, int own_ranks, unsigned long long *__restrict__ counters)
+                             unsigned long long *__restrict__ counters)
 {
 	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned maxbin = 0;
@@ -311,7 +308,6 @@ __global__ void k_s2_singles(const uint32_t *__restrict__ sg, uint64_t S, const 
 			// count-min sketch of the dictionary bins: an upper bound of every bin size (a bin = singles sharing a key in dictionary l)
 			for (int l = 0; l < gm.nd; ++l) {
 				const uint64_t k0 = extract_bases(w, gm.dstart[l], gm.lt);
-				if (own_ranks > 1 && (int)(((uint64_t)kmer_bucket(k0, 16) * own_ranks) >> 16) != own_rank) continue;   // key-sharded: one rank counts each bin
 				unsigned long long key = ((unsigned long long)l << 34) | k0;
 				unsigned v = atomicAdd(&cm[mix64(key) & cm_mask], 1u) + 1u;
 				maxbin = max(maxbin, v);
@@ -352,7 +348,10 @@ __device__ __forceinline__ uint32_t bins_exact_count(const unsigned long long *_
 }
 
 // exact mode: every (single, dictionary) whose bin is larger than maxsearch -> inbig[single] = 1 and a (bin key, single) record
-__global__ void k_s2_mark_big(const uint64_t *__restrict__ rd, uint64_t S, S2Geom gm, const unsigned long long *__restrict__ tkey, const uint32_t *__restrict__ tcnt, uint64_t hmask,
+// (bins are judged by the exact table on one GPU and by the job-wide count-min sketch when sharded; records carry the single's
+// position in the job's sg list and its diversion flag, so that the replay can run on any rank)
+__global__ void k_s2_mark_big(const uint64_t *__restrict__ rd, const uint8_t *__restrict__ flagged, const uint32_t *__restrict__ sidx, uint64_t S, S2Geom gm,
+                              const unsigned long long *__restrict__ tkey, const uint32_t *__restrict__ tcnt, uint64_t hmask, const uint32_t *__restrict__ cmg, uint64_t cmg_mask,
                               uint8_t *__restrict__ inbig, unsigned long long *__restrict__ members, unsigned long long cap, unsigned long long *__restrict__ counters)
 {
 	uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,10 +362,10 @@ __global__ void k_s2_mark_big(const uint64_t *__restrict__ rd, uint64_t S, S2Geo
 	uint64_t v = row[wi] >> sh;
 	if (sh + 2 * gm.lt > 64) v |= row[wi + 1] << (64 - sh);
 	const unsigned long long key = ((unsigned long long)l << 34) | (v & ((1ull << (2 * gm.lt)) - 1));
-	if (bins_exact_count(tkey, tcnt, hmask, key) <= (uint32_t)gm.maxsearch) return;
+	if ((tkey ? bins_exact_count(tkey, tcnt, hmask, key) : cmg[mix64(key) & cmg_mask]) <= (uint32_t)gm.maxsearch) return;
 	inbig[s] = 1;
 	const unsigned long long at = atomicAdd(&counters[CT_S2_NBIGMEM], 1ull);
-	if (at < cap) { members[2 * at] = key; members[2 * at + 1] = s; }
+	if (at < cap) { members[2 * at] = key; members[2 * at + 1] = (unsigned long long)(sidx ? sidx[s] : (uint32_t)s) | ((unsigned long long)flagged[s] << 32); }
 }
 __global__ void k_s2_apply_claims(const unsigned long long *__restrict__ pairs, uint64_t n, unsigned long long *__restrict__ claim)
 {
@@ -378,15 +377,16 @@ __global__ void k_s2_apply_claims(const unsigned long long *__restrict__ pairs, 
 struct S2Join {
 	uint64_t S;
 	const uint64_t *rd; const uint8_t *flagged;
-	const uint32_t *ptab; const unsigned long long *ents; int pbits; uint32_t b_lo, b_hi;   // this context's share of the table
+	const uint32_t *ptab; const unsigned long long *ents; int pbits;
 	const uint32_t *pblk; const S2ContigMeta *meta; const uint64_t *cw;
 	unsigned long long *claim;            // [S] min priority
-	unsigned long long window_base;       // windows on lower ranks (0 on a single GPU)
 	unsigned long long *counters;
 	const unsigned long long *xkey; const uint32_t *xcnt; uint64_t xmask;   // exact bin sizes (null: trust the sketch)
+	const uint32_t *cmg; uint64_t cmg_mask;                                 // sharded: count-min sketch summed over the ranks (bounds every bin of the JOB)
 	// exact mode (some dictionary bin exceeds maxsearch): singles that sit in such a bin do not claim on the device; their
 	// verified matches are listed as events {priority, bin key, single} and replayed in order on the host
 	const uint8_t *inbig; unsigned long long *events; unsigned long long events_cap;
+	const uint32_t *sidx;                 // position of every single in the job's sg list (null = identity)
 };
 
 
@@ -417,12 +417,9 @@ __global__ void __launch_bounds__(256) k_s2_probe_table(S2Join p, S2Geom gm, uns
 #pragma unroll
 			for (int phase = 0; phase < 2; ++phase) {
 				if (phase < nphase) {
-					const uint32_t bg = kmer_bucket(S2_KEY32(key2[phase]), p.pbits);
-					if (bg >= p.b_lo && bg < p.b_hi) {           // key-sharded: other ranks look up the other lt-mers
-						const uint32_t b = bg - p.b_lo;
-						lo2[phase] = b ? p.ptab[b - 1] : 0u;
-						hi2[phase] = p.ptab[b];
-					}
+					const uint32_t b = kmer_bucket(S2_KEY32(key2[phase]), p.pbits);
+					lo2[phase] = b ? p.ptab[b - 1] : 0u;
+					hi2[phase] = p.ptab[b];
 				}
 			}
 		}
@@ -526,14 +523,14 @@ __global__ void __launch_bounds__(128) k_s2_verify(S2Join p, S2Geom gm, const un
 				ok = len_e <= gm.enc_limit;
 			}
 			if (ok && p.inbig) {                 // exact mode
-				const unsigned long long g = p.window_base + cm.woff + (unsigned long long)jj;
+				const unsigned long long g = cm.woff + (unsigned long long)jj;
 				const unsigned long long prio = (g << 5) | ((unsigned long long)phase << 4) | (unsigned long long)l;
 				if (p.inbig[s]) {
 					const int bit = 2 * ds, wi = bit >> 6, shk = bit & 63;
 					uint64_t v = row[wi] >> shk;
 					if (shk + 2 * lt > 64) v |= row[wi + 1] << (64 - shk);
 					const unsigned long long at = atomicAdd(&p.counters[CT_S2_NEVENTS], 1ull);
-					if (at < p.events_cap) { p.events[3 * at] = prio; p.events[3 * at + 1] = ((unsigned long long)l << 34) | (v & ((1ull << (2 * lt)) - 1)); p.events[3 * at + 2] = s; }
+					if (at < p.events_cap) { p.events[3 * at] = prio; p.events[3 * at + 1] = ((unsigned long long)l << 34) | (v & ((1ull << (2 * lt)) - 1)); p.events[3 * at + 2] = p.sidx ? p.sidx[s] : (uint32_t)s; }
 				} else atomicMin(&p.claim[s], prio);
 				ok = false;
 			}
@@ -542,15 +539,16 @@ __global__ void __launch_bounds__(128) k_s2_verify(S2Join p, S2Geom gm, const un
 					// The reference scans only the last `maxsearch` live entries of a bin (:388); with every bin at most that
 					// large the scan sees everything and "all matches, first one wins" is exact.
 					bool big = true;
-					if (p.xkey) {
+					if (p.xkey || p.cmg) {
 						const int bit = 2 * ds, wi = bit >> 6, shk = bit & 63;
 						uint64_t v = row[wi] >> shk;
 						if (shk + 2 * lt > 64) v |= row[wi + 1] << (64 - shk);
-						big = bins_exact_count(p.xkey, p.xcnt, p.xmask, ((unsigned long long)l << 34) | (v & ((1ull << (2 * lt)) - 1))) > (uint32_t)gm.maxsearch;
+						const unsigned long long bkey = ((unsigned long long)l << 34) | (v & ((1ull << (2 * lt)) - 1));
+						big = p.xkey ? bins_exact_count(p.xkey, p.xcnt, p.xmask, bkey) > (uint32_t)gm.maxsearch : p.cmg[mix64(bkey) & p.cmg_mask] > (uint32_t)gm.maxsearch;
 					}
 					if (big) atomicAdd(&p.counters[CT_S2_NEEDEXACT], 1ull);
 				}
-				const unsigned long long g = p.window_base + cm.woff + (unsigned long long)jj;
+				const unsigned long long g = cm.woff + (unsigned long long)jj;
 				atomicMin(&p.claim[s], (g << 5) | ((unsigned long long)phase << 4) | (unsigned long long)l);
 			}
 		}
@@ -560,29 +558,29 @@ __global__ void __launch_bounds__(128) k_s2_verify(S2Join p, S2Geom gm, const un
 }
 
 // ---------------------------------------------------------------- K8
-// a claim belongs to this rank when its window lies in [g_lo, g_hi) (all of them on a single GPU)
+// sidx: position of every single in the job's sg list (sharded: the local singles are a subsequence of it); null = identity
 #define S2_NOCLAIM ((unsigned long long)MCB_CLAIM_NONE)
-__device__ __forceinline__ bool claim_mine(unsigned long long c, uint64_t g_lo, uint64_t g_hi) { return c != S2_NOCLAIM && (c >> 5) >= g_lo && (c >> 5) < g_hi; }
-__global__ void k_s2_claim_flags(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S, uint64_t g_lo, uint64_t g_hi,
+__global__ void k_s2_claim_flags(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S,
                                  uint32_t *__restrict__ f_claim, uint32_t *__restrict__ f_a, uint32_t *__restrict__ f_t)
 {
 	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= S) return;
-	f_claim[s] = claim_mine(claim[s], g_lo, g_hi); f_a[s] = flagged[s] == 1; f_t[s] = flagged[s] == 2;
+	f_claim[s] = claim[s] != S2_NOCLAIM; f_a[s] = flagged[s] == 1; f_t[s] = flagged[s] == 2;
 }
-__global__ void k_s2_claim_compact(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S, uint64_t g_lo, uint64_t g_hi, uint64_t g_sub,
+__global__ void k_s2_claim_compact(const unsigned long long *__restrict__ claim, const uint8_t *__restrict__ flagged, uint64_t S, const uint32_t *__restrict__ sidx,
                                    const uint32_t *__restrict__ p_claim, const uint32_t *__restrict__ p_a, const uint32_t *__restrict__ p_t,
                                    ulonglong2 *__restrict__ el, uint32_t *__restrict__ fpa, uint32_t *__restrict__ fpt)
 {
 	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= S) return;
-	unsigned long long c = claim[s];
-	if (claim_mine(c, g_lo, g_hi)) { ulonglong2 e; e.x = c - (g_sub << 5); e.y = 0xFFFFFFFFull - s; el[p_claim[s]] = e; }   // local window index; ascending y == descending sg index
-	if (flagged[s] == 1) fpa[p_a[s]] = (uint32_t)s;
-	if (flagged[s] == 2) fpt[p_t[s]] = (uint32_t)s;
+	const unsigned long long c = claim[s];
+	if (c != S2_NOCLAIM) { ulonglong2 e; e.x = c; e.y = 0xFFFFFFFFull - s; el[p_claim[s]] = e; }   // ascending y == descending sg index (local order == job order)
+	const uint32_t gs = sidx ? sidx[s] : (uint32_t)s;
+	if (flagged[s] == 1) fpa[p_a[s]] = gs;
+	if (flagged[s] == 2) fpt[p_t[s]] = gs;
 }
 __global__ void k_s2_claim_emit(const ulonglong2 *__restrict__ el, uint64_t n, const uint64_t *__restrict__ woff, uint64_t n_contigs, const uint32_t *__restrict__ sg,
-                                uint32_t *__restrict__ out_c, uint32_t *__restrict__ out_s, uint64_t *__restrict__ out_y)
+                                const uint32_t *__restrict__ sidx, uint32_t *__restrict__ out_c, uint32_t *__restrict__ out_s, uint64_t *__restrict__ out_y, uint64_t *__restrict__ out_p)
 {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -591,13 +589,14 @@ __global__ void k_s2_claim_emit(const ulonglong2 *__restrict__ el, uint64_t n, c
 	const uint32_t s = (uint32_t)(0xFFFFFFFFull - e.y);
 	uint64_t lo = 0, hi = n_contigs;
 	while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (woff[mid] <= g) lo = mid; else hi = mid; }
-	out_c[i] = (uint32_t)lo; out_s[i] = s;
+	out_c[i] = (uint32_t)lo; out_s[i] = sidx ? sidx[s] : s;
 	out_y[i] = ((uint64_t)sg[s] << 32) | ((g - woff[lo]) << 1) | dir;
+	out_p[i] = e.x;
 }
 
 // ================================================================= host
 // Upload the contigs and (re)build the lt-mer table unless the cached one was built from identical contigs.
-static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int lt, int tab_rank, int tab_ranks)
+static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int lt)
 {
 	McbContigIndex &cx = ctx->cix;
 	const int L = ctx->L;
@@ -619,7 +618,7 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	cwo[n_contigs] = total_words + 1; wo[n_contigs] = n_windows; eo[n_contigs] = n_entries;   // +1 guard word: loaders read one word ahead
 	if (n_windows >= (1ull << 58)) { mcb_set_error("too many windows"); return MCB_EINVAL; }
 	// ---- same contigs as last time?  (compare on the device: the strings have to be uploaded to find out)
-	const bool maybe_same = cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L && cx.tab_rank == tab_rank && cx.tab_ranks == tab_ranks;
+	const bool maybe_same = cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L;
 	DBuf &stage_refs = maybe_same ? ctx->d_scr[1] : cx.refs, &stage_off = maybe_same ? ctx->d_scr[2] : cx.roff;
 	const size_t refs_pad = (ref_bytes + 7) & ~(size_t)7;
 	MCB_TRY(stage_refs.ensure(refs_pad + 16)); MCB_TRY(stage_off.ensure((n_contigs + 1) * 8));
@@ -656,7 +655,6 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	// ---- pack
 	cx.table_valid = false;
 	cx.n_contigs = n_contigs; cx.ref_bytes = ref_bytes; cx.total_words = total_words; cx.n_windows = n_windows; cx.n_entries = n_entries; cx.L = L; cx.lt = lt;
-	cx.tab_rank = tab_rank; cx.tab_ranks = tab_ranks;
 	const uint64_t n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
 	MCB_TRY(cx.cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.wo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.cw.ensure((total_words + 2) * 8));
 	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16));
@@ -688,7 +686,6 @@ static int contig_table_update(mcb_ctx *ctx, const S2Geom &gm, const uint32_t *d
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
 	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
 	static const bool use_filter = !(getenv("MCB_S2_NOFILTER") && atoi(getenv("MCB_S2_NOFILTER")));
-	const int tab_rank = cx.tab_rank, tab_ranks = cx.tab_ranks;
 	if (cx.n_windows == 0 || cx.n_contigs == 0) { cx.table_valid = true; cx.filtered = false; return MCB_OK; }
 	if (cx.table_valid) {
 		if (!cx.filtered) return MCB_OK;
@@ -704,29 +701,26 @@ static int contig_table_update(mcb_ctx *ctx, const S2Geom &gm, const uint32_t *d
 	const uint64_t n_all = cx.n_entries;          // all lt-mer start positions of the contigs that have a window
 	const uint64_t nkv = S * (uint64_t)gm.nd;
 	const bool filtered = use_filter;
-	// ownership of the key space among the ranks is fixed on the top 16 hash bits, so every rank may size its own bucket table
-	const uint32_t o_lo = (uint32_t)((((uint64_t)tab_rank << 16) + tab_ranks - 1) / tab_ranks), o_hi = (uint32_t)((((uint64_t)(tab_rank + 1) << 16) + tab_ranks - 1) / tab_ranks);
 	uint64_t wmask = 0;
 	if (filtered) {
 		static const int flt_shift = getenv("MCB_S2_FLT") ? atoi(getenv("MCB_S2_FLT")) : -1;             // tuning knob: filter words per (single, dictionary), log2
-		const uint64_t nkv_own = nkv / (uint64_t)tab_ranks + 1;
-		const uint64_t want = flt_shift >= 0 ? nkv_own << flt_shift : nkv_own >> -flt_shift;
+		const uint64_t want = flt_shift >= 0 ? (nkv + 1) << flt_shift : (nkv + 1) >> -flt_shift;
 		uint64_t W = 1024; while (W < want && W < (1ull << 28)) W <<= 1;
 		MCB_TRY(cx.flt.ensure(W * 4)); MCB_TRY(cx.sgmap.ensure((ctx->n_reads / 32 + 2) * 4));
 		MCB_CUDA(cudaMemsetAsync(cx.flt.p, 0, W * 4, ctx->stream));
 		MCB_CUDA(cudaMemsetAsync(cx.sgmap.p, 0, (ctx->n_reads / 32 + 2) * 4, ctx->stream));
 		wmask = W - 1; cx.flt_words = W;
-		if (nkv) MCB_LAUNCH(ctx, "s2_filter_insert", k_s2_filter_insert, mcb_grid_for(nkv, 256), 256, 0, d_rd, d_fl, d_sg, S, gm, cx.flt.as<uint32_t>(), wmask, cx.sgmap.as<uint32_t>(), o_lo, o_hi);
+		if (nkv) MCB_LAUNCH(ctx, "s2_filter_insert", k_s2_filter_insert, mcb_grid_for(nkv, 256), 256, 0, d_rd, d_fl, d_sg, S, gm, cx.flt.as<uint32_t>(), wmask, cx.sgmap.as<uint32_t>());
 	}
-	const bool compacting = filtered || tab_ranks > 1;
-	uint64_t ents_cap = !compacting ? n_all : (filtered ? n_all / (4 * tab_ranks) : n_all / tab_ranks + n_all / (4 * tab_ranks)) + (1u << 20);
+	const bool compacting = filtered;
+	uint64_t ents_cap = !compacting ? n_all : n_all / 4 + (1u << 20);
 	if (ents_cap > n_all) ents_cap = n_all;
 	uint64_t n_own = n_all;
 	for (int tries = 0;; ++tries) {
 		MCB_TRY(cx.ents.ensure(ents_cap * 8 + 16));
 		if (compacting) MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NCAND], 0, 8, ctx->stream));
 		MCB_LAUNCH(ctx, "s2_kmer_emit", k_s2_kmer_emit, mcb_grid_for(cx.total_words, 256), 256, 0, cx.cw.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.roff.as<uint64_t>(),
-		           cx.eoff.as<uint64_t>(), cx.n_contigs, cx.total_words, cx.L, cx.lt, cx.ents.as<unsigned long long>(), compacting ? 1 : 0, 16, o_lo, o_hi, &dc[CT_S2_NCAND],
+		           cx.eoff.as<uint64_t>(), cx.n_contigs, cx.total_words, cx.L, cx.lt, cx.ents.as<unsigned long long>(), compacting ? 1 : 0, &dc[CT_S2_NCAND],
 		           (unsigned long long)ents_cap, filtered ? cx.flt.as<uint32_t>() : (const uint32_t*)nullptr, wmask);
 		if (!compacting) break;
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -738,11 +732,10 @@ static int contig_table_update(mcb_ctx *ctx, const S2Geom &gm, const uint32_t *d
 	}
 	cx.n_table = n_own;
 	static const int load_shift = getenv("MCB_S2_LOAD") ? atoi(getenv("MCB_S2_LOAD")) : 2;                   // tuning knob: 2^load_shift .. 2^(load_shift+1) entries per bucket
-	int pbits = tab_ranks > 1 ? 16 : 10;
-	while (pbits < 30 && pbits < 2 * cx.lt && ((1ull << load_shift) << pbits) < n_own * (uint64_t)tab_ranks) ++pbits;
+	int pbits = 10;
+	while (pbits < 30 && pbits < 2 * cx.lt && ((1ull << load_shift) << pbits) < n_own) ++pbits;
 	cx.pbits = pbits;
-	if (tab_ranks > 1) { cx.b_lo = o_lo << (pbits - 16); cx.b_hi = o_hi << (pbits - 16); }
-	else { cx.b_lo = 0; cx.b_hi = 1u << pbits; }
+	cx.b_lo = 0; cx.b_hi = 1u << pbits;
 	const uint64_t nbk = cx.b_hi - cx.b_lo;
 	MCB_TRY(cx.ents2.ensure(n_own * 8 + 16)); MCB_TRY(cx.ptab.ensure((nbk + 1) * 4));
 	MCB_TRY(mcb_radix_sort_kmers(ctx, cx.ents.as<unsigned long long>(), cx.ents2.as<unsigned long long>(), n_own, pbits, cx.b_lo, cx.b_hi, &cx.ents_sorted));
@@ -781,34 +774,46 @@ struct BigBin { std::vector<uint32_t> mem; std::vector<int> fen; uint32_t live =
 static void fen_add(std::vector<int> &f, size_t i, int d) { for (++i; i < f.size(); i += i & (~i + 1)) f[i] += d; }
 static int fen_sum(const std::vector<int> &f, size_t i) { int r = 0; for (; i > 0; i -= i & (~i + 1)) r += f[i]; return r; }   // live among the first i members
 
-static int realign_exact_bins(mcb_ctx *ctx, S2Join jn, const S2Geom &gm, uint64_t S, uint64_t nkv, uint64_t n_listed, const unsigned long long *d_cand)
+static int realign_exact_bins(mcb_ctx *ctx, S2Join jn, const S2Geom &gm, uint64_t S, uint64_t nkv, uint64_t n_listed, const unsigned long long *d_cand, const uint32_t *h_sidx)
 {
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
 	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
 	DBuf b_inbig, b_mem, b_ev, b_pairs;
 	struct Rel { DBuf *b[4]; ~Rel() { for (auto x : b) x->release(); } } rel = {{&b_inbig, &b_mem, &b_ev, &b_pairs}};
 	MCB_TRY(b_inbig.ensure(S + 16)); MCB_TRY(b_mem.ensure(nkv * 16 + 16)); MCB_TRY(b_ev.ensure(n_listed * 24 + 24));
-	MCB_CUDA(cudaMemsetAsync(b_inbig.p, 0, S, ctx->stream));
+	MCB_CUDA(cudaMemsetAsync(b_inbig.p, 0, S + 16, ctx->stream));
 	MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NBIGMEM], 0, 16, ctx->stream));      // NBIGMEM, NEVENTS
 	MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_CAND], 0, 8, ctx->stream)); MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NEEDEXACT], 0, 8, ctx->stream));
-	MCB_CUDA(cudaMemsetAsync(jn.claim, 0x7F, S * 8, ctx->stream));
-	MCB_LAUNCH(ctx, "s2_mark_big", k_s2_mark_big, mcb_grid_for(nkv, 256), 256, 0, jn.rd, S, gm, jn.xkey, jn.xcnt, jn.xmask, b_inbig.as<uint8_t>(),
-	           b_mem.as<unsigned long long>(), (unsigned long long)nkv, dc);
+	if (S) MCB_CUDA(cudaMemsetAsync(jn.claim, 0x7F, S * 8, ctx->stream));
+	if (nkv) MCB_LAUNCH(ctx, "s2_mark_big", k_s2_mark_big, mcb_grid_for(nkv, 256), 256, 0, jn.rd, jn.flagged, jn.sidx, S, gm, jn.xkey, jn.xcnt, jn.xmask, jn.cmg, jn.cmg_mask,
+	                    b_inbig.as<uint8_t>(), b_mem.as<unsigned long long>(), (unsigned long long)nkv, dc);
 	jn.inbig = b_inbig.as<uint8_t>(); jn.events = b_ev.as<unsigned long long>(); jn.events_cap = n_listed;
 	if (n_listed) MCB_LAUNCH(ctx, "s2_verify", k_s2_verify, mcb_grid_for(n_listed, 128), 128, 0, jn, gm, d_cand, n_listed);
 	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-	const uint64_t n_mem = hc[CT_S2_NBIGMEM], n_ev = hc[CT_S2_NEVENTS];
-	std::vector<unsigned long long> mem(2 * n_mem), ev(3 * n_ev);
-	std::vector<uint8_t> flagged(S);
-	if (n_mem) MCB_CUDA(cudaMemcpyAsync(mem.data(), b_mem.p, n_mem * 16, cudaMemcpyDeviceToHost, ctx->stream));
-	if (n_ev) MCB_CUDA(cudaMemcpyAsync(ev.data(), b_ev.p, n_ev * 24, cudaMemcpyDeviceToHost, ctx->stream));
-	MCB_CUDA(cudaMemcpyAsync(flagged.data(), jn.flagged, S, cudaMemcpyDeviceToHost, ctx->stream));
-	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	uint64_t n_mem = hc[CT_S2_NBIGMEM], n_ev = hc[CT_S2_NEVENTS];
+	std::vector<unsigned long long> mem, ev;
+	if (ctx->shard_n > 1) {
+		// sharded: the bins and the events of the whole job on every rank (they are few); each rank replays all of them and keeps
+		// the winners among its own singles
+		MCB_TRY(mcb_coll_allgatherv(ctx, b_mem.p, n_mem * 16, mem));
+		MCB_TRY(mcb_coll_allgatherv(ctx, b_ev.p, n_ev * 24, ev));
+		n_mem = mem.size() / 2; n_ev = ev.size() / 3;
+	} else {
+		mem.resize(2 * n_mem); ev.resize(3 * n_ev);
+		if (n_mem) MCB_CUDA(cudaMemcpyAsync(mem.data(), b_mem.p, n_mem * 16, cudaMemcpyDeviceToHost, ctx->stream));
+		if (n_ev) MCB_CUDA(cudaMemcpyAsync(ev.data(), b_ev.p, n_ev * 24, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
 	// bins
 	std::unordered_map<unsigned long long, BigBin> bins;
 	std::unordered_map<uint32_t, std::vector<unsigned long long>> bins_of;      // single -> keys of its big bins
-	for (uint64_t i = 0; i < n_mem; ++i) { bins[mem[2 * i]].mem.push_back((uint32_t)mem[2 * i + 1]); bins_of[(uint32_t)mem[2 * i + 1]].push_back(mem[2 * i]); }
+	std::unordered_map<uint32_t, uint8_t> flagged;                                // singles of the big bins set aside by the poly-A/T diversion
+	for (uint64_t i = 0; i < n_mem; ++i) {
+		const uint32_t sgi = (uint32_t)mem[2 * i + 1];
+		bins[mem[2 * i]].mem.push_back(sgi); bins_of[sgi].push_back(mem[2 * i]);
+		if (mem[2 * i + 1] >> 32) flagged[sgi] = 1;
+	}
 	for (auto &kv : bins) {
 		BigBin &b = kv.second;
 		std::sort(b.mem.begin(), b.mem.end());
@@ -835,7 +840,7 @@ static int realign_exact_bins(mcb_ctx *ctx, S2Join jn, const S2Geom &gm, uint64_
 		if (!bb || !bb->closed) {
 			for (uint64_t q = i; q < j; ++q) {
 				const uint32_t sgi = (uint32_t)ev[3 * order[q] + 2];
-				if (flagged[sgi] || claimed.count(sgi)) continue;
+				if (flagged.count(sgi) || claimed.count(sgi)) continue;
 				if (bb) {                                                              // among the last maxsearch live entries?
 					const size_t pos = (size_t)(std::lower_bound(bb->mem.begin(), bb->mem.end(), sgi) - bb->mem.begin());
 					const int live_above = (int)bb->live - fen_sum(bb->fen, pos + 1);
@@ -854,28 +859,38 @@ static int realign_exact_bins(mcb_ctx *ctx, S2Join jn, const S2Geom &gm, uint64_
 			}
 		i = j;
 	}
-	// hand the winners back to the device claim array
-	if (!claimed.empty()) {
-		std::vector<unsigned long long> pairs; pairs.reserve(2 * claimed.size());
-		for (auto &kv : claimed) { pairs.push_back(kv.first); pairs.push_back(kv.second); }
+	// hand the winners among this context's singles back to the device claim array (job position -> local position)
+	std::vector<unsigned long long> pairs; pairs.reserve(2 * claimed.size());
+	for (auto &kv : claimed) {
+		uint64_t local = kv.first;
+		if (h_sidx) {
+			const uint32_t *q = std::lower_bound(h_sidx, h_sidx + S, kv.first);
+			if (q == h_sidx + S || *q != kv.first) continue;                            // another rank's single
+			local = (uint64_t)(q - h_sidx);
+		}
+		pairs.push_back(local); pairs.push_back(kv.second);
+	}
+	if (!pairs.empty()) {
 		MCB_TRY(b_pairs.ensure(pairs.size() * 8));
 		MCB_CUDA(cudaMemcpyAsync(b_pairs.p, pairs.data(), pairs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-		MCB_LAUNCH(ctx, "s2_apply_claims", k_s2_apply_claims, mcb_grid_for(claimed.size(), 256), 256, 0, b_pairs.as<unsigned long long>(), (uint64_t)claimed.size(), jn.claim);
+		MCB_LAUNCH(ctx, "s2_apply_claims", k_s2_apply_claims, mcb_grid_for(pairs.size() / 2, 256), 256, 0, b_pairs.as<unsigned long long>(), (uint64_t)pairs.size() / 2, jn.claim);
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	}
 	return MCB_OK;
 }
 
 // first half: contigs, singles, join.  Leaves the claim priorities in ctx->d_x[0] (u64[S]).
-// contig-range sharding: this context holds contigs whose first window is `window_base`, the whole table, and emits all its claims.
-// key sharding (tab_ranks > 1): this context holds ALL contigs, share tab_rank of the table, and emits the claims of windows [g_lo, g_hi).
-static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
-                          uint64_t window_base, int tab_rank, int tab_ranks, uint64_t g_lo, uint64_t g_hi,
+// sg_index (sharded): position of every local single in the job's sg list, ascending; n_sg_total = length of that list.  The
+// dictionary bins of the reference span the singles of the whole job, so the bin-size guard is summed over the ranks.
+static int realign_search(mcb_ctx *ctx, const uint32_t *sg, const uint32_t *sg_index, uint64_t S, uint64_t n_sg_total, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
                           int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
 {
 	if (!ctx->reads_loaded) { mcb_set_error("mcb_realign: no reads loaded"); return MCB_ESTATE; }
 	if (S && !sg) { mcb_set_error("mcb_realign: null input"); return MCB_EINVAL; }
-	if (S >= 0xFFFFFFFFull) { mcb_set_error("mcb_realign: too many singles"); return MCB_EINVAL; }
+	if (n_sg_total >= 0xFFFFFFFFull || S > n_sg_total) { mcb_set_error("mcb_realign: too many singles"); return MCB_EINVAL; }
+	const bool sharded = ctx->shard_n > 1;
+	if (sharded && !ctx->comm) { mcb_set_error("mcb_realign: sharded context without a communicator (mcb_shard_init)"); return MCB_ESTATE; }
+	if (sharded && S && !sg_index) { mcb_set_error("mcb_shard_realign: sg_index is required"); return MCB_EINVAL; }
 	memset(res, 0, sizeof(*res));
 	const int L = ctx->L, WS = ctx->WS;
 	S2Geom gm;
@@ -886,80 +901,81 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
 	MCB_CUDA(cudaMemsetAsync(dc + 16, 0, 16 * 8, ctx->stream));
 	// ---- singles first: they do not depend on the contigs, and the contig upload (copy stream) overlaps them
-	const uint64_t nkv = S * (uint64_t)gm.nd;
+	const uint64_t nkv = S * (uint64_t)gm.nd, nkv_job = n_sg_total * (uint64_t)gm.nd;
 	if (nkv >= 0x7FFFFFFFull) { mcb_set_error("dictionary too large (singles x dictionaries must stay below 2^31)"); return MCB_EINVAL; }
-	DBuf &b_sg = ctx->d_scr[0], &b_cm = ctx->d_scr[5], &b_rd = ctx->d_scr[6], &b_fl = ctx->d_scr[8];
+	DBuf &b_sg = ctx->d_scr[0], &b_cm = ctx->d_scr[5], &b_rd = ctx->d_scr[6], &b_fl = ctx->d_scr[8], &b_sidx = ctx->d_x[1];
 	MCB_TRY(b_sg.ensure(S * 4 + 16)); MCB_TRY(b_rd.ensure(S * WS * 8 + 16)); MCB_TRY(b_fl.ensure(S + 16));
+	ctx->rs.have_index = sg_index != nullptr;
+	if (sg_index) MCB_TRY(b_sidx.ensure(S * 4 + 16));
+	// count-min sketch of the bin sizes: it only has to bound the largest bin from above (a bound above maxsearch sends the call
+	// through the exact count), so about one counter per two (single, dictionary) pairs is enough, and at that size (32 MB
+	// for 15 M pairs) the atomics resolve in L2 instead of DRAM.  Sized from the JOB's singles: every rank uses the same array.
+	static const int cm_shift = getenv("MCB_S2_CM") ? atoi(getenv("MCB_S2_CM")) : -1;
+	const uint64_t cm_want = cm_shift >= 0 ? nkv_job << cm_shift : nkv_job >> -cm_shift;
+	uint64_t CM = 1024; while (CM < cm_want && CM < (1ull << 26)) CM <<= 1;
+	if (nkv_job) MCB_TRY(b_cm.ensure(CM * 4));
 	if (nkv) {
-		// count-min sketch of the bin sizes: it only has to bound the largest bin from above (a bound above maxsearch sends the call
-		// through the exact count), so about one counter per two (single, dictionary) pairs is enough, and at that size (32 MB
-		// for 15 M pairs) the atomics resolve in L2 instead of DRAM
-		static const int cm_shift = getenv("MCB_S2_CM") ? atoi(getenv("MCB_S2_CM")) : -1;
-		const uint64_t cm_want = cm_shift >= 0 ? nkv << cm_shift : nkv >> -cm_shift;
-		uint64_t CM = 1024; while (CM < cm_want && CM < (1ull << 26)) CM <<= 1;
-		MCB_TRY(b_cm.ensure(CM * 4));
 		{
 			McbSpan sp(ctx->tm, "h2d");
 			MCB_CUDA(cudaMemcpyAsync(b_sg.p, sg, S * 4, cudaMemcpyHostToDevice, ctx->stream));
+			if (sg_index) MCB_CUDA(cudaMemcpyAsync(b_sidx.p, sg_index, S * 4, cudaMemcpyHostToDevice, ctx->stream));
 		}
 		McbSpan span(ctx->tm, "realign");
 		MCB_CUDA(cudaMemsetAsync(b_cm.p, 0, CM * 4, ctx->stream));
 		MCB_LAUNCH(ctx, "s2_singles", k_s2_singles, mcb_grid_for(S, 128), 128, 0, b_sg.as<uint32_t>(), S, ctx->d_packed.as<uint64_t>(), gm,
 		           ctx->d_nread_rid.as<uint32_t>(), ctx->d_nread_mask.as<uint64_t>(), ctx->n_nreads, ctx->n_reads,
-		           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, tab_rank, tab_ranks, dc);
-	}
+		           b_rd.as<uint64_t>(), b_fl.as<uint8_t>(), b_cm.as<uint32_t>(), CM - 1, dc);
+	} else if (nkv_job && sharded) MCB_CUDA(cudaMemsetAsync(b_cm.p, 0, CM * 4, ctx->stream));
+	// sharded: a bin of the job is at most the sum of the ranks' largest bins — one scalar all-reduce, and usually the end of it
+	if (sharded && nkv_job) { McbSpan span(ctx->tm, "nccl:guard"); MCB_TRY(mcb_coll_allreduce_sum_u64(ctx, &dc[CT_S2_MAXBIN], 1)); }
 	// ---- contigs: refs == NULL reuses the contigs (and their table) of the previous call
 	McbContigIndex &cx = ctx->cix;
 	if (refs || ref_off) {
 		if (n_contigs && (!refs || !ref_off)) { mcb_set_error("mcb_realign: refs and ref_off must be given together"); return MCB_EINVAL; }
-		MCB_TRY(contig_index_update(ctx, refs, ref_off, n_contigs, gm.lt, tab_rank, tab_ranks));
+		MCB_TRY(contig_index_update(ctx, refs, ref_off, n_contigs, gm.lt));
 	} else {
-		if (!cx.valid || cx.L != L || cx.lt != gm.lt || cx.tab_rank != tab_rank || cx.tab_ranks != tab_ranks) { mcb_set_error("mcb_realign: refs == NULL but no contigs from a previous call are cached"); return MCB_ESTATE; }
+		if (!cx.valid || cx.L != L || cx.lt != gm.lt) { mcb_set_error("mcb_realign: refs == NULL but no contigs from a previous call are cached"); return MCB_ESTATE; }
 		if (n_contigs && n_contigs != cx.n_contigs) { mcb_set_error("mcb_realign: refs == NULL with a different contig count (%llu, cached %llu)", (unsigned long long)n_contigs, (unsigned long long)cx.n_contigs); return MCB_EINVAL; }
 	}
 	const uint64_t n_windows = cx.n_windows;
-	if (window_base + n_windows >= (1ull << 57)) { mcb_set_error("too many windows"); return MCB_EINVAL; }
+	if (n_windows >= (1ull << 57)) { mcb_set_error("too many windows"); return MCB_EINVAL; }
 	res->n_windows = n_windows;
 	{
 		int nrev = 0; for (int l = 0; l < gm.nd; ++l) nrev += gm.dstart[l] > 0;
 		res->n_probes = n_windows * (uint64_t)(gm.nd + nrev);                 // what the reference's window loop would issue (:355-504)
 	}
-	ctx->rs.pending = true; ctx->rs.S = S; ctx->rs.window_base = window_base; ctx->rs.nd = gm.nd;
-	if (tab_ranks > 1) { ctx->rs.g_lo = g_lo; ctx->rs.g_hi = g_hi; ctx->rs.g_sub = 0; }
-	else { ctx->rs.g_lo = window_base; ctx->rs.g_hi = window_base + n_windows; ctx->rs.g_sub = window_base; }
+	ctx->rs.pending = true; ctx->rs.S = S; ctx->rs.nd = gm.nd;
 	MCB_TRY(ctx->d_x[0].ensure(S * 8 + 16));                   // claim priorities
 	unsigned long long *claim = ctx->d_x[0].as<unsigned long long>();
 	if (S) MCB_CUDA(cudaMemsetAsync(claim, 0x7F, S * 8, ctx->stream));          // MCB_CLAIM_NONE
-	if (S == 0 || gm.nd == 0) return MCB_OK;
+	if (n_sg_total == 0 || gm.nd == 0) return MCB_OK;
 	McbSpan span(ctx->tm, "realign");
-	MCB_TRY(contig_table_update(ctx, gm, b_sg.as<uint32_t>(), S, b_rd.as<uint64_t>(), b_fl.as<uint8_t>()));
-	if (n_windows == 0) {          // no contig long enough on this rank: the diversion lists are still needed
-		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-		if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }
-		return MCB_OK;
-	}
+	if (S) MCB_TRY(contig_table_update(ctx, gm, b_sg.as<uint32_t>(), S, b_rd.as<uint64_t>(), b_fl.as<uint8_t>()));
 	S2Join jn; memset(&jn, 0, sizeof jn);
-	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents_sorted; jn.pbits = cx.pbits; jn.b_lo = cx.b_lo; jn.b_hi = cx.b_hi;
+	jn.S = S; jn.rd = b_rd.as<uint64_t>(); jn.flagged = b_fl.as<uint8_t>(); jn.ptab = cx.ptab.as<uint32_t>(); jn.ents = cx.ents_sorted; jn.pbits = cx.pbits;
 	jn.pblk = cx.pblk.as<uint32_t>(); jn.meta = cx.meta.as<S2ContigMeta>(); jn.cw = cx.cw.as<uint64_t>();
-	jn.claim = claim; jn.window_base = window_base; jn.counters = dc;
+	jn.claim = claim; jn.counters = dc; jn.sidx = sg_index ? b_sidx.as<uint32_t>() : nullptr;
 	// candidate list: sized from the previous call's count, grown (and the probe repeated) when it overflows
 	DBuf &b_cand = ctx->d_x[3];
-	if (b_cand.cap < (nkv / 2 + 1024) * 8) MCB_TRY(b_cand.ensure((nkv / 2 + 1024) * 8));
 	uint64_t n_listed = 0;
-	for (int tries = 0;; ++tries) {
-		const uint64_t cap = b_cand.cap / 8;
-		MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NCAND], 0, 8, ctx->stream));
-		MCB_LAUNCH(ctx, "s2_probe_table", k_s2_probe_table, mcb_grid_for(nkv, 256), 256, 0, jn, gm, b_cand.as<unsigned long long>(), (unsigned long long)cap);
-		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-		n_listed = hc[CT_S2_NCAND];
-		if (n_listed <= cap) break;
-		if (tries) { mcb_set_error("mcb_realign: candidate list overflow"); return MCB_EINVAL; }
-		MCB_TRY(b_cand.ensure(n_listed * 8 + 1024));
+	if (S && n_windows) {
+		if (b_cand.cap < (nkv / 2 + 1024) * 8) MCB_TRY(b_cand.ensure((nkv / 2 + 1024) * 8));
+		for (int tries = 0;; ++tries) {
+			const uint64_t cap = b_cand.cap / 8;
+			MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NCAND], 0, 8, ctx->stream));
+			MCB_LAUNCH(ctx, "s2_probe_table", k_s2_probe_table, mcb_grid_for(nkv, 256), 256, 0, jn, gm, b_cand.as<unsigned long long>(), (unsigned long long)cap);
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+			n_listed = hc[CT_S2_NCAND];
+			if (n_listed <= cap) break;
+			if (tries) { mcb_set_error("mcb_realign: candidate list overflow"); return MCB_EINVAL; }
+			MCB_TRY(b_cand.ensure(n_listed * 8 + 1024));
+		}
 	}
 	for (int attempt = 0;; ++attempt) {
 		if (n_listed) MCB_LAUNCH(ctx, "s2_verify", k_s2_verify, mcb_grid_for(n_listed, 128), 128, 0, jn, gm, b_cand.as<unsigned long long>(), n_listed);
+		// every rank must take the same way through the guard: the decision counters are summed over the ranks first
+		if (sharded) { McbSpan sp2(ctx->tm, "nccl:guard"); MCB_TRY(mcb_coll_allreduce_sum_u64(ctx, &dc[CT_S2_NEEDEXACT], 1)); }
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 		if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }
@@ -967,42 +983,44 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const ch
 		if (attempt == 1) {
 			// Some verified match lies in a bin larger than maxsearch: the reference's scan of "the last maxsearch live entries"
 			// (kthread_hash_realign.c:388) depends on which reads were already claimed.  Replay exactly those singles in order.
-			if (ctx->shard_n > 1 || window_base || tab_ranks > 1) {
-				mcb_set_error("mcb_realign: %llu matches fall into dictionary bins with more than maxsearch=%d singles; the sequential bin-window "
-				              "replay is not available when the contigs are sharded", hc[CT_S2_NEEDEXACT], maxsearch);
-				return MCB_EINPUT;
-			}
-			MCB_TRY(realign_exact_bins(ctx, jn, gm, S, nkv, n_listed, b_cand.as<unsigned long long>()));
+			MCB_TRY(realign_exact_bins(ctx, jn, gm, S, nkv, n_listed, b_cand.as<unsigned long long>(), sg_index));
 			MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 			MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 			break;
 		}
-		// the sketch only bounds bin sizes from above: count them exactly and join again
-		uint64_t H = 1024; while (H < 2 * nkv) H <<= 1;
-		MCB_TRY(b_cm.ensure(H * 12 + 16));
-		unsigned long long *tkey = b_cm.as<unsigned long long>(); uint32_t *tcnt = (uint32_t*)(b_cm.as<char>() + H * 8);
-		MCB_CUDA(cudaMemsetAsync(tkey, 0xFF, H * 8, ctx->stream)); MCB_CUDA(cudaMemsetAsync(tcnt, 0, H * 4, ctx->stream));
-		MCB_LAUNCH(ctx, "s2_bins_exact", k_s2_bins_exact, mcb_grid_for(nkv, 256), 256, 0, b_rd.as<uint64_t>(), S, gm, tkey, tcnt, H - 1);
-		jn.xkey = tkey; jn.xcnt = tcnt; jn.xmask = H - 1;
+		// the bound was too coarse: judge every bin by itself and join again
+		if (!sharded) {               // exact bin sizes
+			uint64_t H = 1024; while (H < 2 * nkv) H <<= 1;
+			MCB_TRY(b_cm.ensure(H * 12 + 16));
+			unsigned long long *tkey = b_cm.as<unsigned long long>(); uint32_t *tcnt = (uint32_t*)(b_cm.as<char>() + H * 8);
+			MCB_CUDA(cudaMemsetAsync(tkey, 0xFF, H * 8, ctx->stream)); MCB_CUDA(cudaMemsetAsync(tcnt, 0, H * 4, ctx->stream));
+			MCB_LAUNCH(ctx, "s2_bins_exact", k_s2_bins_exact, mcb_grid_for(nkv, 256), 256, 0, b_rd.as<uint64_t>(), S, gm, tkey, tcnt, H - 1);
+			jn.xkey = tkey; jn.xcnt = tcnt; jn.xmask = H - 1;
+		} else {                      // the count-min sketch summed over the ranks bounds every bin of the job
+			McbSpan sp2(ctx->tm, "nccl:guard");
+			MCB_TRY(mcb_coll_allreduce_sum_u32(ctx, b_cm.as<uint32_t>(), CM));
+			jn.cmg = b_cm.as<uint32_t>(); jn.cmg_mask = CM - 1;
+		}
 		MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_CAND], 0, 8, ctx->stream)); MCB_CUDA(cudaMemsetAsync(&dc[CT_S2_NEEDEXACT], 0, 8, ctx->stream));
-		MCB_CUDA(cudaMemsetAsync(claim, 0x7F, S * 8, ctx->stream));
+		if (S) MCB_CUDA(cudaMemsetAsync(claim, 0x7F, S * 8, ctx->stream));
 	}
 	res->n_candidates = hc[CT_S2_CAND];
 	return MCB_OK;
 }
 
-// second half (K8): compact the claims that lie on this context's contigs, order them, copy the lists to the host
+// second half (K8): compact the claims, order them, copy the lists to the host
 static int realign_claims(mcb_ctx *ctx, mcb_realign_result *res)
 {
-	if (!ctx->rs.pending) { mcb_set_error("mcb_realign_finish: no search pending"); return MCB_ESTATE; }
+	if (!ctx->rs.pending) { mcb_set_error("mcb_realign: no search pending"); return MCB_ESTATE; }
 	ctx->rs.pending = false;
-	const uint64_t S = ctx->rs.S, g_lo = ctx->rs.g_lo, g_hi = ctx->rs.g_hi, g_sub = ctx->rs.g_sub;
+	const uint64_t S = ctx->rs.S;
 	McbContigIndex &cx = ctx->cix;
 	const uint64_t n_windows = cx.n_windows, n_contigs = cx.n_contigs;
 	if (S == 0 || ctx->rs.nd == 0) return MCB_OK;
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
 	unsigned long long *hc = ctx->h_counters.as<unsigned long long>();
 	unsigned long long *claim = ctx->d_x[0].as<unsigned long long>();
+	const uint32_t *sidx = ctx->rs.have_index ? ctx->d_x[1].as<uint32_t>() : nullptr;
 	DBuf &b_sg = ctx->d_scr[0], &b_fl3 = ctx->d_scr[3], &b_fp = ctx->d_scr[4], &b_fl = ctx->d_scr[8], &b_elA = ctx->d_scr[9], &b_elB = ctx->d_scr[10], &b_out = ctx->d_scr[11];
 	MCB_TRY(b_fl3.ensure(S * 12 + 64));
 	uint32_t *f_c = b_fl3.as<uint32_t>(), *f_a = f_c + S, *f_t = f_a + S;
@@ -1010,11 +1028,11 @@ static int realign_claims(mcb_ctx *ctx, mcb_realign_result *res)
 	ulonglong2 *elA = b_elA.as<ulonglong2>(), *elB = b_elB.as<ulonglong2>();
 	uint32_t *d_fpa = b_fp.as<uint32_t>(), *d_fpt = d_fpa + S;
 	const int span_h = ctx->tm.begin("realign");
-	MCB_LAUNCH(ctx, "s2_claim_flags", k_s2_claim_flags, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, g_lo, g_hi, f_c, f_a, f_t);
+	MCB_LAUNCH(ctx, "s2_claim_flags", k_s2_claim_flags, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, f_c, f_a, f_t);
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_c, S, (uint64_t*)&dc[CT_S2_CLAIMS]));
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_a, S, (uint64_t*)&dc[CT_S2_FPA]));
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, f_t, S, (uint64_t*)&dc[CT_S2_FPT]));
-	MCB_LAUNCH(ctx, "s2_claim_compact", k_s2_claim_compact, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, g_lo, g_hi, g_sub, f_c, f_a, f_t, elA, d_fpa, d_fpt);
+	MCB_LAUNCH(ctx, "s2_claim_compact", k_s2_claim_compact, mcb_grid_for(S, 256), 256, 0, claim, b_fl.as<uint8_t>(), S, sidx, f_c, f_a, f_t, elA, d_fpa, d_fpt);
 	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	const uint64_t ncl = hc[CT_S2_CLAIMS], nfa = hc[CT_S2_FPA], nft = hc[CT_S2_FPT];
@@ -1023,11 +1041,11 @@ static int realign_claims(mcb_ctx *ctx, mcb_realign_result *res)
 	mcb_add_bit_passes(passes, 0, 0, 5 + mcb_bits_for(n_windows));
 	ulonglong2 *els = nullptr;
 	MCB_TRY(mcb_radix_sort(ctx, elA, elB, ncl, passes.data(), (int)passes.size(), &els));
-	MCB_TRY(b_out.ensure(ncl * 16 + 64));
-	uint64_t *o_y = b_out.as<uint64_t>(); uint32_t *o_c = (uint32_t*)(o_y + ncl), *o_s = o_c + ncl;
-	if (ncl) MCB_LAUNCH(ctx, "s2_claim_emit", k_s2_claim_emit, mcb_grid_for(ncl, 256), 256, 0, els, ncl, cx.wo.as<uint64_t>(), n_contigs, b_sg.as<uint32_t>(), o_c, o_s, o_y);
+	MCB_TRY(b_out.ensure(ncl * 24 + 64));
+	uint64_t *o_y = b_out.as<uint64_t>(), *o_p = o_y + ncl; uint32_t *o_c = (uint32_t*)(o_p + ncl), *o_s = o_c + ncl;
+	if (ncl) MCB_LAUNCH(ctx, "s2_claim_emit", k_s2_claim_emit, mcb_grid_for(ncl, 256), 256, 0, els, ncl, cx.wo.as<uint64_t>(), n_contigs, b_sg.as<uint32_t>(), sidx, o_c, o_s, o_y, o_p);
 	ctx->tm.end(span_h);
-	MCB_TRY(ctx->h_claim_c.ensure(ncl * 4 + 16)); MCB_TRY(ctx->h_claim_s.ensure(ncl * 4 + 16)); MCB_TRY(ctx->h_claim_y.ensure(ncl * 8 + 16));
+	MCB_TRY(ctx->h_claim_c.ensure(ncl * 4 + 16)); MCB_TRY(ctx->h_claim_s.ensure(ncl * 4 + 16)); MCB_TRY(ctx->h_claim_y.ensure(ncl * 8 + 16)); MCB_TRY(ctx->h_claim_p.ensure(ncl * 8 + 16));
 	MCB_TRY(ctx->h_fpA.ensure(nfa * 4 + 16)); MCB_TRY(ctx->h_fpT.ensure(nft * 4 + 16));
 	{
 		McbSpan sp(ctx->tm, "d2h");
@@ -1035,6 +1053,7 @@ static int realign_claims(mcb_ctx *ctx, mcb_realign_result *res)
 			MCB_CUDA(cudaMemcpyAsync(ctx->h_claim_c.p, o_c, ncl * 4, cudaMemcpyDeviceToHost, ctx->stream));
 			MCB_CUDA(cudaMemcpyAsync(ctx->h_claim_s.p, o_s, ncl * 4, cudaMemcpyDeviceToHost, ctx->stream));
 			MCB_CUDA(cudaMemcpyAsync(ctx->h_claim_y.p, o_y, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_claim_p.p, o_p, ncl * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		}
 		if (nfa) MCB_CUDA(cudaMemcpyAsync(ctx->h_fpA.p, d_fpa, nfa * 4, cudaMemcpyDeviceToHost, ctx->stream));
 		if (nft) MCB_CUDA(cudaMemcpyAsync(ctx->h_fpT.p, d_fpt, nft * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1042,6 +1061,7 @@ static int realign_claims(mcb_ctx *ctx, mcb_realign_result *res)
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->tm.collect();
 	res->n_claims = ncl; res->claim_contig = ctx->h_claim_c.as<uint32_t>(); res->claim_sg = ctx->h_claim_s.as<uint32_t>(); res->claim_y = ctx->h_claim_y.as<uint64_t>();
+	res->claim_prio = ctx->h_claim_p.as<uint64_t>();
 	res->n_fpA = nfa; res->n_fpT = nft; res->fpA_sg = ctx->h_fpA.as<uint32_t>(); res->fpT_sg = ctx->h_fpT.as<uint32_t>();
 	return MCB_OK;
 }
@@ -1051,43 +1071,20 @@ extern "C" int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const c
 {
 	if (!ctx || !res) { mcb_set_error("mcb_realign: null argument"); return MCB_EINVAL; }
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, 0, 0, 1, 0, 0, threshold, maxsearch, ininumdict, res));
+	if (ctx->shard_n > 1) { mcb_set_error("mcb_realign: context is sharded, use mcb_shard_realign"); return MCB_ESTATE; }
+	MCB_TRY(realign_search(ctx, sg, nullptr, S, S, refs, ref_off, n_contigs, threshold, maxsearch, ininumdict, res));
 	return realign_claims(ctx, res);
 }
 
-extern "C" int mcb_realign_begin(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
-                                 uint64_t window_base, int threshold, int maxsearch, int ininumdict, void **d_claim)
+// Sharded Stage 2: this rank's singles — a subsequence of the job's sg list, given with their positions in it —
+// against ALL contigs.  Claims come back in the reference's append order restricted to these singles, with claim_sg / fpA_sg /
+// fpT_sg as positions in the job's list and claim_prio as the merge key: the job's list is the ranks' lists merged by
+// (claim_prio ascending, claim_sg descending).  Collective: every rank of the communicator must call it.
+extern "C" int mcb_shard_realign(mcb_ctx *ctx, const uint32_t *sg, const uint32_t *sg_index, uint64_t n_sg_local, uint64_t n_sg_total,
+                                 const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res)
 {
-	if (!ctx || !d_claim) { mcb_set_error("mcb_realign_begin: null argument"); return MCB_EINVAL; }
+	if (!ctx || !res) { mcb_set_error("mcb_shard_realign: null argument"); return MCB_EINVAL; }
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, window_base, 0, 1, 0, 0, threshold, maxsearch, ininumdict, &ctx->rs.result));
-	MCB_CUDA(cudaStreamSynchronize(ctx->stream));        // the caller reduces the array on its own stream
-	*d_claim = ctx->d_x[0].p;
-	return MCB_OK;
-}
-
-extern "C" int mcb_realign_finish(mcb_ctx *ctx, mcb_realign_result *res)
-{
-	if (!ctx || !res) { mcb_set_error("mcb_realign_finish: null argument"); return MCB_EINVAL; }
-	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	*res = ctx->rs.result;               // counters of the search half
+	MCB_TRY(realign_search(ctx, sg, ctx->shard_n > 1 ? sg_index : (sg_index ? sg_index : nullptr), n_sg_local, n_sg_total, refs, ref_off, n_contigs, threshold, maxsearch, ininumdict, res));
 	return realign_claims(ctx, res);
-}
-
-// Key-sharded Stage 2: every rank is given ALL contigs and ALL singles, keeps the share `tab_rank` of `tab_ranks`
-// of the lt-mer table (buckets by hash range), probes only the lt-mers it owns, and emits the claims of windows [g_lo, g_hi)
-// after the caller has min-reduced the priorities.  *maxbin_upper = upper bound of this rank's largest dictionary bin (the caller
-// takes the maximum over the ranks; a value above maxsearch means the sequential bin-window replay would be needed).
-extern "C" int mcb_realign_begin_keyed(mcb_ctx *ctx, const uint32_t *sg, uint64_t S, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
-                                       int tab_rank, int tab_ranks, uint64_t g_lo, uint64_t g_hi, int threshold, int maxsearch, int ininumdict,
-                                       void **d_claim, uint64_t *maxbin_upper)
-{
-	if (!ctx || !d_claim) { mcb_set_error("mcb_realign_begin_keyed: null argument"); return MCB_EINVAL; }
-	if (tab_ranks < 1 || tab_ranks > 255 || tab_rank < 0 || tab_rank >= tab_ranks || g_hi < g_lo) { mcb_set_error("mcb_realign_begin_keyed: bad arguments"); return MCB_EINVAL; }
-	MCB_CUDA(cudaSetDevice(ctx->prm.device));
-	MCB_TRY(realign_search(ctx, sg, S, refs, ref_off, n_contigs, 0, tab_rank, tab_ranks, g_lo, g_hi, threshold, maxsearch, ininumdict, &ctx->rs.result));
-	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-	*d_claim = ctx->d_x[0].p;
-	if (maxbin_upper) *maxbin_upper = ctx->h_counters.as<unsigned long long>()[CT_S2_MAXBIN];
-	return MCB_OK;
 }

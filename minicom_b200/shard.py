@@ -1,20 +1,18 @@
-"""Sharding of the front end across the GPUs of one box: one process per GPU, `torch.distributed` (NCCL over NVLink) for the
-plumbing, libminicom_b200.so for the device work (include/minicom_b200.h, "sharding across the GPUs of one box").
+"""The front end over the GPUs of one box, one process per GPU: thin driver over the sharded C-ABI (include/minicom_b200.h,
+"the same path over the GPUs of one box").  All exchanges between GPUs — NCCL grouped send/recv over NVLink — happen inside
+libminicom_b200.so (csrc/mcb_shard.cu); this module only hands every rank its inputs and knows how the ranks' results combine.
 
 Partitioning rules:
   reads      contiguous read-id ranges, rank r owns [r*cap, min((r+1)*cap, N)), cap = ceil(N / G)
   buckets    the 16384 minimizer buckets (x & 0x3FFF, kthread_reads.c:213) in contiguous ranges, owner = bucket*G >> 14
-  contigs    contiguous ranges of the contig list, cut so that every rank gets about the same number of bases
+  singles    a single belongs to the rank whose bucket it was left alone in (that rank holds its packed row)
 
 Exchanges:
-  Stage 1    all-gather of the 2-bit packed reads (any rank builds the consensus of its groups from any read);
-             per round an all-to-all of the 16-byte (minimizer, read, position, strand) tuples by bucket owner;
-             an all-gather of two counters per round (new seed contigs for the global contig ids, members for the loop control)
-  Stage 2    contigs and singles on every rank; the contig lt-mer table partitioned by hash range (each rank probes only the
-             lt-mers it owns, so probes per rank stay constant); one all-reduce(MIN) of the per-single claim priorities per
-             threshold round; claims emitted by window range
-Concatenating the ranks' results in rank order — round by round for Stage 1 — reproduces the single-GPU (= single-threaded
-reference) order exactly; `merge_stage1` / `merge_claims` do that on one host for the callers that stay on one host (contig merge).
+  Stage 1    per round ONE exchange of (16-byte tuple + packed row of its read) by bucket owner, plus two counters per rank
+             (new seed contigs for the global contig ids, members for the loop control)
+  Stage 2    none for the data: every rank realigns its own singles against all contigs; scalar guards of the bin sizes
+Concatenating the ranks' Stage-1 results in rank order — round by round — and merging the claim lists by priority reproduces
+the single-GPU (= single-threaded reference) order exactly; `merge_stage1` / `merge_claims` do that on one host.
 
 The pure partition/merge arithmetic has no CUDA dependency and is tested on CPU with the gloo backend (tests/test_shard_cpu.py).
 """
@@ -44,24 +42,6 @@ def bucket_range(rank: int, n_ranks: int):
     b0 = (rank * NB + n_ranks - 1) // n_ranks
     b1 = ((rank + 1) * NB + n_ranks - 1) // n_ranks
     return b0, b1
-
-
-def contig_partition(ref_off: np.ndarray, n_ranks: int, readlen: int):
-    """Cut the contig list into n_ranks contiguous ranges of about equal bases.
-    Returns (cuts[n_ranks+1] contig indices, window_base[n_ranks]) with windows = max(0, len-L+1) per contig."""
-    ref_off = np.asarray(ref_off, dtype=np.uint64).astype(np.int64)
-    n = len(ref_off) - 1
-    total = int(ref_off[-1]) if n > 0 else 0
-    cuts = [0]
-    for r in range(1, n_ranks):
-        cuts.append(int(np.searchsorted(ref_off, total * r // n_ranks, side="left")) if n else 0)
-    cuts.append(n)
-    cuts = np.minimum.accumulate(np.array(cuts[::-1]))[::-1]          # monotone, ends at n
-    cuts = np.maximum.accumulate(np.minimum(cuts, n))
-    lens = np.diff(ref_off)
-    win = np.where(lens >= readlen, lens - readlen + 1, 0)
-    wcum = np.concatenate([[0], np.cumsum(win)])
-    return cuts.astype(np.int64), wcum[cuts[:-1]].astype(np.int64)
 
 
 def exchange_plan(send_counts: np.ndarray, recv_counts: np.ndarray):
@@ -110,29 +90,29 @@ def merge_stage1(parts: list[Stage1Part]) -> Stage1Part:
                       cat("mi", p0.mi), cat("mi_cnt", p0.mi_cnt), rounds)
 
 
-def merge_claims(parts: list[tuple[np.ndarray, np.ndarray, np.ndarray]], contig_cuts: np.ndarray | None = None):
-    """Per-rank (claim_contig, claim_sg, claim_y) -> global lists in the reference's append order (rank order = window order).
-    contig_cuts: first contig of every rank when the contig indices are rank-local (contig-range sharding); None when they are
-    global already (key sharding)."""
-    cc = [p[0].astype(np.int64) + (int(contig_cuts[r]) if contig_cuts is not None else 0) for r, p in enumerate(parts)]
-    return np.concatenate(cc).astype(np.uint32), np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts])
+def merge_claims(parts):
+    """Per-rank (claim_contig, claim_sg, claim_y, claim_prio) -> the job's lists in the reference's append order: ascending
+    priority (window, forward-then-reverse, dictionary), inside one step descending position in the job's sg list."""
+    c = np.concatenate([p[0] for p in parts]); s = np.concatenate([p[1] for p in parts])
+    y = np.concatenate([p[2] for p in parts]); pr = np.concatenate([p[3] for p in parts])
+    order = np.lexsort((np.uint32(0xFFFFFFFF) - s, pr))
+    return c[order], s[order], y[order], pr[order]
 
 
-# ---------------------------------------------------------------- device plumbing
-class _DevMem:
-    """Zero-copy torch view of library-owned device memory."""
-
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
-def dev_view(ptr: int, nbytes: int, device):
-    import torch
-    if nbytes == 0:
-        return torch.empty(0, dtype=torch.uint8, device=device)
-    return torch.as_tensor(_DevMem(ptr, nbytes), device=device)
+def owned_mask(n_reads: int, sg_of_rank: np.ndarray) -> np.ndarray:
+    """bitmap over read ids: the singles this rank produced in Stage 1 (it holds their packed rows)"""
+    m = np.zeros(n_reads, dtype=bool)
+    m[np.asarray(sg_of_rank, dtype=np.int64)] = True
+    return m
 
 
+def local_singles(mask: np.ndarray, sg_job: np.ndarray):
+    """the entries of the job's sg list that this rank owns, with their positions in the list"""
+    pos = np.nonzero(mask[np.asarray(sg_job, dtype=np.int64)])[0]
+    return np.ascontiguousarray(np.asarray(sg_job)[pos], dtype=np.uint32), pos.astype(np.uint32)
+
+
+# ---------------------------------------------------------------- host model of the exchange (CPU tests)
 def all_to_all_rows(dist, send, send_counts, device):
     """All-to-all of row blocks: `send` is (n, w) with the rows for rank q at [so[q], so[q+1]).  Returns (recv_counts, recv).
     Works on CPU tensors (gloo) and CUDA tensors (NCCL)."""
@@ -147,118 +127,49 @@ def all_to_all_rows(dist, send, send_counts, device):
     return recv_counts, recv
 
 
+def make_unique_id(dist) -> bytes:
+    """rank 0 asks NCCL for a unique id (through the library) and the process group hands it to everyone"""
+    from . import api
+    box = [None]
+    if dist.get_rank() == 0:
+        buf = C.create_string_buffer(api.NCCL_ID_BYTES)
+        lib = api.load_library()
+        if lib.mcb_shard_unique_id(buf) != 0:
+            raise api.McbError(lib.mcb_last_error().decode())
+        box[0] = buf.raw
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
 class ShardedFrontEnd:
-    """Drives one rank of the sharded front end.  `ctx` is an api.Context on this rank's GPU."""
+    """Drives one rank of the sharded front end.  `ctx` is an api.Context on this rank's GPU; the communicator is created
+    inside the library from `unique_id` (make_unique_id)."""
 
-    def __init__(self, ctx, dist, device):
-        import torch
-        self.ctx, self.dist, self.device, self.torch = ctx, dist, device, torch
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.bytes_exchanged = 0
-        self.time_collectives = False
-        self._events = []
-
-    def _coll(self, fn, *a, **kw):
-        """run a collective; when asked, bracket it with CUDA events on the stream it is enqueued on"""
-        if not self.time_collectives:
-            return fn(*a, **kw)
-        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = fn(*a, **kw)
-        e1.record()
-        self._events.append((e0, e1))
-        return r
-
-    def collective_ms(self, reset=True):
-        self.torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in self._events)
-        if reset:
-            self._events = []
-        return ms
+    def __init__(self, ctx, rank: int, world: int, unique_id: bytes):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        ctx.shard_init(unique_id, rank, world)
+        self.mask = None
 
     # ---- Stage 1: kt_for_reads + kt_for_bucket over the whole read set
     def stage1(self, rows_local, n_total: int, device_resident: bool = False):
         """rows_local: this rank's reads, (n_local, L) uint8 (numpy, or a CUDA tensor when device_resident).
         Returns (ReadsResult of the slice, Stage1Part of this rank)."""
-        from . import api
-        torch, dist, ctx = self.torch, self.dist, self.ctx
+        ctx = self.ctx
         lo, hi = rid_range(n_total, self.rank, self.world)
-        ctx.shard_begin(self.rank, self.world, n_total, lo)
+        ctx.shard_begin(n_total, lo)
         rr = ctx.for_reads_device(rows_local.data_ptr(), hi - lo) if device_resident else ctx.for_reads(rows_local)
-        # all-gather of the packed reads (equal chunks of `cap` rows; the last one overhangs into the slack the library allocated)
-        ptr, rb = ctx.shard_packed()
-        cap = (n_total + self.world - 1) // self.world
-        whole = dev_view(ptr, self.world * cap * rb, self.device)
-        mine = whole[self.rank * cap * rb:(self.rank + 1) * cap * rb].clone()
-        self._coll(dist.all_gather_into_tensor, whole, mine)
-        self.bytes_exchanged += whole.numel()
-        # the (rare) reads that contained N: every rank needs all of them for the near-poly-A/T test of Stage 2
-        nrid, nmask = ctx.shard_get_nreads()
-        ncnt = torch.tensor([len(nrid)], dtype=torch.int64, device=self.device)
-        nall = torch.empty(self.world, dtype=torch.int64, device=self.device)
-        self._coll(dist.all_gather_into_tensor, nall, ncnt)
-        if int(nall.sum().item()):
-            gathered = [None] * self.world
-            dist.all_gather_object(gathered, (np.array(nrid), np.array(nmask)))
-            ctx.shard_set_nreads(np.concatenate([g[0] for g in gathered]), np.concatenate([g[1] for g in gathered]))
-        torch.cuda.synchronize()
-        # rounds
-        rc = api.RoundControl()
-        ctx.lib.mcb_round_control_init(C.byref(rc))
-        tot_cl = members = 0
-        while True:
-            is_last = ctx.lib.mcb_round_control_begin(C.byref(rc), ctx.params.k, ctx.params.max_rounds)
-            counts, _ = ctx.shard_partition(self.world)
-            sc = torch.as_tensor(counts.astype(np.int64), device=self.device)
-            rcnt = torch.empty(self.world, dtype=torch.int64, device=self.device)
-            self._coll(dist.all_to_all_single, rcnt, sc)
-            recv_counts = rcnt.cpu().numpy()
-            n_send, n_recv = int(counts.sum()), int(recv_counts.sum())
-            rptr, sptr = ctx.shard_recv_buffer(n_recv)
-            send = dev_view(sptr, n_send * 16, self.device).view(torch.int64).view(-1, 2)
-            recv = dev_view(rptr, n_recv * 16, self.device).view(torch.int64).view(-1, 2)
-            self._coll(dist.all_to_all_single, recv, send, output_split_sizes=[int(x) for x in recv_counts], input_split_sizes=[int(x) for x in counts])
-            torch.cuda.synchronize()
-            self.bytes_exchanged += n_send * 16
-            ctx.shard_set_tuples(n_recv)
-            n_cl_new, n_mem_new, _, _ = ctx.bucket_round_a(int(rc.round), int(is_last))
-            mine2 = torch.tensor([n_cl_new, n_mem_new], dtype=torch.int64, device=self.device)
-            allc = torch.empty((self.world, 2), dtype=torch.int64, device=self.device)
-            self._coll(dist.all_gather_into_tensor, allc, mine2)
-            allc = allc.cpu().numpy()
-            ctx.bucket_round_b(tot_cl + int(allc[:self.rank, 0].sum()))
-            tot_cl += int(allc[:, 0].sum())
-            members += int(allc[:, 1].sum())
-            if ctx.lib.mcb_round_control_end(C.byref(rc), members):
-                break
-        br, rounds = ctx.bucket_finish()
+        br, rounds = ctx.shard_for_bucket()
+        self.mask = owned_mask(n_total, br.sg)
         return rr, Stage1Part(br.cl_n, br.cl_a, br.cl_ref, np.diff(br.cl_ref_off.astype(np.int64)).astype(np.uint64), br.sg, br.mi, br.mi_cnt, rounds)
 
     # ---- Stage 2: one threshold round of realign_hash
-    def realign(self, sg, refs, ref_off, g_lo: int, g_hi: int, threshold: int, maxsearch: int, ininumdict: int = 0):
-        """Key-sharded: every rank passes ALL contigs (refs/ref_off; None/None = same as the previous round) and all singles,
-        holds its hash range of the contig lt-mer table and probes only the lt-mers it owns; the claim priorities are
-        min-reduced; this rank then emits the claims of windows [g_lo, g_hi) (contig_partition gives the ranges) with global
-        contig indices."""
-        torch, dist, ctx = self.torch, self.dist, self.ctx
-        err, ptr, maxbin = None, 0, 0
-        try:
-            ptr, maxbin = ctx.realign_begin_keyed(sg, refs, ref_off, self.rank, self.world, g_lo, g_hi, threshold, maxsearch, ininumdict)
-        except Exception as e:      # every rank has to reach the collective
-            err = e
-        flag = torch.tensor([1 if err else 0, maxbin], dtype=torch.int64, device=self.device)
-        self._coll(dist.all_reduce, flag, op=dist.ReduceOp.MAX)
-        bad, gmax = (int(x) for x in flag.cpu())
-        if bad:
-            raise err or RuntimeError("mcb_realign_begin_keyed failed on another rank")
-        if gmax > maxsearch:
-            raise RuntimeError(f"a dictionary bin may hold {gmax} singles (> maxsearch={maxsearch}): the sequential bin-window replay is single-GPU only")
-        claim = dev_view(ptr, len(sg) * 8, self.device).view(torch.int64)
-        if len(sg):
-            self._coll(dist.all_reduce, claim, op=dist.ReduceOp.MIN)
-            self.bytes_exchanged += len(sg) * 8
-        torch.cuda.synchronize()
-        return ctx.realign_finish()
+    def select(self, sg_job):
+        """(this rank's singles of the job's list, their positions in it)"""
+        return local_singles(self.mask, sg_job)
+
+    def realign(self, sg_local, sg_index, n_sg_total: int, refs, ref_off, threshold: int, maxsearch: int, ininumdict: int = 0):
+        """ALL contigs (refs/ref_off; None/None = the previous round's) against this rank's singles.  Collective."""
+        return self.ctx.shard_realign(sg_local, sg_index, n_sg_total, refs, ref_off, threshold, maxsearch, ininumdict)
 
     # ---- index builds: every rank sorts the buckets it owns
     def idx_build(self, tuples, bucket_off):

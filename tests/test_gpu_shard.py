@@ -18,7 +18,8 @@ def _n_gpus():
         return 0
 
 
-@pytest.mark.parametrize("world,extra", [(2, []), (2, ["--reads", "20011", "--readlen", "75", "--genome", "90000"])])
+@pytest.mark.parametrize("world,extra", [(2, []), (2, ["--reads", "20011", "--readlen", "75", "--genome", "90000"]),
+                                         (2, ["--bigbins"])])          # dictionary bins above maxsearch: the sequential replay, sharded
 def test_sharded_front_end_matches_single_gpu(world, extra):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -32,21 +32,16 @@ def test_bucket_ranges_match_owner_rule():
             assert np.array_equal(np.nonzero(own == q)[0], np.arange(b0, b1))
 
 
-def test_contig_partition_is_contiguous_and_counts_windows():
-    rng = np.random.default_rng(1)
-    lens = rng.integers(40, 400, size=1000)
-    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
-    L = 100
-    win = np.where(lens >= L, lens - L + 1, 0)
-    for g in (1, 2, 3, 8):
-        cuts, wb = shard.contig_partition(off, g, L)
-        assert cuts[0] == 0 and cuts[-1] == len(lens) and np.all(np.diff(cuts) >= 0)
-        for q in range(g):
-            assert wb[q] == win[:cuts[q]].sum()
-        bases = [int(off[cuts[q + 1]] - off[cuts[q]]) for q in range(g)]
-        assert max(bases) - min(bases) <= 2 * lens.max()
-    cuts, wb = shard.contig_partition(np.array([0], dtype=np.uint64), 4, L)       # no contigs at all
-    assert list(cuts) == [0] * 5 and list(wb) == [0] * 4
+def test_local_singles_pick_the_owned_entries_in_list_order():
+    n = 50
+    own0, own1 = np.array([3, 9, 40, 41]), np.array([5, 7, 30])
+    m0, m1 = shard.owned_mask(n, own0), shard.owned_mask(n, own1)
+    job = np.array([41, 5, 3, 30, 9, 7], dtype=np.uint32)                 # the job's sg list after some updateSingle()
+    s0, i0 = shard.local_singles(m0, job)
+    s1, i1 = shard.local_singles(m1, job)
+    assert list(s0) == [41, 3, 9] and list(i0) == [0, 2, 4]
+    assert list(s1) == [5, 30, 7] and list(i1) == [1, 3, 5]
+    assert sorted(list(i0) + list(i1)) == list(range(len(job)))
 
 
 def test_merge_stage1_is_round_major_then_rank():
@@ -66,12 +61,14 @@ def test_merge_stage1_is_round_major_then_rank():
     assert mg.rounds.tolist() == [[3, 8, 21, 5], [1, 2, 7, 4]]
 
 
-def test_merge_claims_offsets_contig_ids():
-    cuts = np.array([0, 10, 25])
-    p0 = (np.array([0, 3, 9], np.uint32), np.array([5, 4, 1], np.uint32), np.array([11, 12, 13], np.uint64))
-    p1 = (np.array([0, 14], np.uint32), np.array([7, 2], np.uint32), np.array([21, 22], np.uint64))
-    c, s, y = shard.merge_claims([p0, p1], cuts)
-    assert list(c) == [0, 3, 9, 10, 24] and list(s) == [5, 4, 1, 7, 2] and list(y) == [11, 12, 13, 21, 22]
+def test_merge_claims_by_priority_then_descending_single():
+    # (contig, position in the job's sg list, y, priority); one step of the window loop (priority 64) claims on both ranks
+    p0 = (np.array([0, 3, 9], np.uint32), np.array([5, 4, 1], np.uint32), np.array([11, 12, 13], np.uint64), np.array([32, 64, 900], np.uint64))
+    p1 = (np.array([1, 3, 14], np.uint32), np.array([7, 6, 2], np.uint32), np.array([21, 22, 23], np.uint64), np.array([40, 64, 70], np.uint64))
+    c, s, y, pr = shard.merge_claims([p0, p1])
+    assert list(pr) == [32, 40, 64, 64, 70, 900]
+    assert list(s) == [5, 7, 6, 4, 2, 1]                                  # inside priority 64: higher sg position first (kthread_hash_realign.c:388)
+    assert list(y) == [11, 21, 22, 12, 23, 13] and list(c) == [0, 1, 3, 3, 14, 9]
 
 
 WORKER = r'''
