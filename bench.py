@@ -8,7 +8,11 @@ realign_hash of the -e/-S/-E schedule — issued through the C-ABI of libminicom
 The host stages that sit BETWEEN those calls (contig merge, kthread_cb.c) are not part of the path; their outputs are
 needed as inputs, so the workload is prepared once, untimed, by running the drop-in executable (reference host objects +
 this library) with MCB_RECORD: it writes the host-side inputs of every index build / realign call, and each timed step
-replays exactly that call sequence.
+replays exactly that call sequence.  At N = 1 the recording run uses num_thr = 1, the reference's only deterministic
+configuration, so a step has ONE right answer: before the timed region the results of one step (read classes, tuples, seed
+contigs, singles, every index, the claims of every threshold round) are digested and compared with the manifest of the
+single-threaded reference for the workload (tests/golden/manifest_<workload>.json) -> `parity` in the JSON line.  At N > 1 the
+sharded results are merged and compared with one GPU running the whole job on the same inputs.
 
 Two timed regions per run:
   value : device time (CUDA events inside the library, on its stream) of the four entry points with the reads resident
@@ -16,7 +20,8 @@ Two timed regions per run:
   e2e   : wall clock of the same calls through the host-buffer C-ABI (pinned host rows in, results copied back to host
           memory every step).
 `--impl reference` times the reference's own multithreaded CPU implementation (oracle/_ref, built from the unmodified
-sources) on a bounded sample of the workload.
+sources) on the SAME workload, all host threads; a step is minutes of CPU, so that arm caps itself at one timed step.
+`cpu_baseline` inside our own line is the same binary on a bounded sample (named in its fields).
 """
 import argparse
 import json
@@ -81,7 +86,7 @@ def unlimit_stack():
         pass
 
 
-def run_binary(exe, fastq, workdir, env_extra, threads):
+def run_binary(exe, fastq, workdir, env_extra, threads, fastq2=None):
     out, tmpd = os.path.join(workdir, "out"), os.path.join(workdir, "tmp") + "/"
     for d in (out, tmpd):
         shutil.rmtree(d, ignore_errors=True)
@@ -91,7 +96,7 @@ def run_binary(exe, fastq, workdir, env_extra, threads):
     env.update({"MC_T": str(threads), "OMP_NUM_THREADS": str(threads), "MC_TMPDIR": tmpd, "MC_TIMING": timing, "MCB_TIMING": timing})
     env.update({k: str(v) for k, v in env_extra.items()})
     t0 = time.time()
-    p = subprocess.run([exe, fastq, out], env=env, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, preexec_fn=unlimit_stack)
+    p = subprocess.run([exe, fastq] + ([fastq2] if fastq2 else []) + [out], env=env, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, preexec_fn=unlimit_stack)
     if p.returncode != 0:
         raise RuntimeError(f"{exe} failed ({p.returncode}): {p.stdout.decode()[-3000:]}")
     with open(timing) as f:
@@ -214,6 +219,8 @@ def bench_ours(args):
     if args.reads:
         n, G = args.reads, max(1000, args.reads * 5)
     threads = args.host_threads or min(os.cpu_count() or 1, 32) // max(1, world) or 1
+    # the host stages of the recording run (contig merge) are deterministic with one thread only
+    rec_threads = args.record_threads or 1
     exe = os.path.join(ROOT, "dropin", "_build", f"minicom_b200_L{L}_{mode}")
     if not os.path.exists(exe):
         raise SystemExit(f"{exe} missing: run __graft_entry__.build() where /root/reference exists (no CPU fallback)")
@@ -225,8 +232,8 @@ def bench_ours(args):
     os.makedirs(rec)
     fq = os.path.join(wd, "in.fastq")
     synth.write_fastq(fq, reads)
-    log(f"[rank {rank}] workload {args.workload}: {n} x {L} bp synthesized in {time.time() - t0:.1f}s; running the drop-in executable once to record the call sequence")
-    dt = run_binary(exe, fq, wd, dict(ref_env, MCB_RECORD=rec, MCB_DEVICE=local), threads)
+    log(f"[rank {rank}] workload {args.workload}: {n} x {L} bp synthesized in {time.time() - t0:.1f}s; running the drop-in executable once (num_thr={rec_threads}) to record the call sequence")
+    dt = run_binary(exe, fq, wd, dict(ref_env, MCB_RECORD=rec, MCB_DEVICE=local), rec_threads)
     os.remove(fq)
     log(f"[rank {rank}] drop-in run: front end {front_end_seconds(dt):.3f}s wall inside the entry points (first call includes CUDA context creation); whole program {dt['wall_total']:.1f}s")
     idx_calls, realign_calls = [], []
@@ -323,6 +330,8 @@ def bench_ours(args):
     def dev_ms(tm):
         return sum(tm.get(k, (0.0, 0))[0] for k in ("for_reads", "for_bucket", "idx_build", "realign"))
 
+    par = parity_step(ctx, args, params, rows_pinned.numpy(), idx_calls, realign_calls, same_contigs, rec_threads) if world == 1 else {"status": "unchecked", "note": "replica mode"}
+    log(f"[rank {rank}] parity: {json.dumps(par)}")
     for _ in range(args.warmup):
         step(True)
         step(False)
@@ -387,7 +396,7 @@ def bench_ours(args):
     line = {
         "metric": "reads/sec for sketch+index+overlap stage", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev_max, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n} x {L} bp reads per GPU, {G} bp random genome, 1% substitutions, mode {mode}, {opts_text(ref_env)}" + ("" if world == 1 else "; independent read set per GPU, no exchange"),
+        "config": {"workload": f"{args.workload}: {n} x {L} bp reads, {G} bp random genome, 1% substitutions, mode {mode}, {opts_text(ref_env)}" + ("" if world == 1 else "; independent read set per GPU, no exchange"),
                    "l2": "inputs larger than L2 (reads %.0f MB per step)" % (n * L / 1e6), "timing": "value = CUDA-event device time of the four entry points (reads resident in HBM); e2e = wall clock through the host-buffer C-ABI",
                    "bases_per_s": round(value * L, 1), "wall_ms_per_step_device_arm": round(ms_wall_dev_max, 3),
                    "counters": {k: v for k, v in counters.items() if k != "rounds"}, "realign_rounds": counters["rounds"],
@@ -401,11 +410,50 @@ def bench_ours(args):
         "clocks": clk.summary(),
         "roofline": roof,
         "cpu_baseline": cpu,
+        "parity": par,
     }
     emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_step(ctx, args, params, rows, idx_calls, realign_calls, same_contigs, rec_threads):
+    """One untimed pass of the step through the copying API; every result is digested (minicom_b200/parity.py) and compared with the
+    manifest of the single-threaded reference for this workload."""
+    from minicom_b200 import parity
+    got = {}
+    rr = ctx.for_reads(rows)
+    tuples = ctx.debug_read_tuples(len(rows))
+    br = ctx.for_bucket()
+    m = int(params.first_mininum)
+    got.update(parity.stage1_digests(rr.cls, tuples, br.cl_n, br.cl_a, br.cl_ref, np.diff(br.cl_ref_off.astype(np.int64)), br.sg,
+                                     br.mi[np.arange(m)[None, :] < br.mi_cnt[:, None]]))
+    del tuples
+    for j, (xy, off) in enumerate(idx_calls):
+        ix = ctx.idx_build(xy, off)
+        got.update(parity.index_digests(j, *ix.arrays()))
+        ix.close()
+    if realign_calls:
+        got["contigs.ref"] = parity.digest(realign_calls[0][1])
+        got["contigs.reflen"] = parity.digest(np.diff(realign_calls[0][2].astype(np.int64)).astype(np.uint64))
+    claims = []
+    for j, (sg, refs, off, thr, ms, nd) in enumerate(realign_calls):
+        r = ctx.realign(sg, None if same_contigs[j] else refs, None if same_contigs[j] else off, thr, ms, nd)
+        got.update(parity.realign_digests(j, sg, len(off) - 1, r.claim_contig, r.claim_sg, r.claim_y, r.fpA_sg, r.fpT_sg))
+        claims.append(len(r.claim_y))
+    path = os.path.join(ROOT, "tests", "golden", f"manifest_{args.workload}.json")
+    out = {"status": "unchecked", "digests": len(got), "claims": claims}
+    if args.reads or rec_threads != 1 or not os.path.exists(path):
+        out["note"] = "no manifest applies (size override, multi-threaded recording, or none committed for this workload)"
+        return out
+    with open(path) as f:
+        man = json.load(f)
+    out.update(parity.compare(got, man["state"]))
+    out.update({"manifest": os.path.relpath(path, ROOT), "against": "unmodified reference, num_thr=1, same seeded reads (tests/golden/make_manifests.py)",
+                "covers": "read classes, minimizer tuples, seed contigs, singles, index tuples, every index (keys + posting order), the recorded contigs, "
+                          "and per threshold round the singles, claims in append order, sg_flag and poly-A/T diversions"})
+    return out
 
 
 def load_recorded(rec, pin):
@@ -424,17 +472,19 @@ def load_recorded(rec, pin):
 
 
 def bench_sharded(args):
-    """N > 1: ONE job over N x n reads, sharded as SURVEY.md 8e says (minicom_b200/shard.py): reads by read-id range, tuples
-    all-to-all by bucket owner, packed reads all-gathered, index builds by bucket range, contigs partitioned for Stage 2 with a
-    min-reduce of the claim priorities.  The host-side inputs (what the contig merger hands to mm_idx_generation / realign_hash)
-    come from one untimed drop-in run of the whole job on rank 0."""
+    """N > 1: ONE job over N x n reads, sharded as SURVEY.md 8e says (csrc/mcb_shard.cu, minicom_b200/shard.py): reads by read-id
+    range; every round of kt_for_bucket each tuple travels with the packed row of its read to the owner of its bucket (NCCL
+    grouped send/recv inside the library); index builds by bucket range; Stage 2 on the rank that owns the single, against all
+    contigs.  The host-side inputs (what the contig merger hands to mm_idx_generation / realign_hash) come from one untimed
+    drop-in run of the whole job on rank 0.  Before the timed region the ranks' results of one step are merged and compared,
+    digest by digest, with ONE GPU running the whole job on the same inputs -> `parity`."""
     import torch
     import torch.distributed as dist
-    from minicom_b200 import api, shard, synth
+    from minicom_b200 import api, parity, shard, synth
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    dist.init_process_group("nccl", device_id=dev)       # launcher plumbing: barriers, the max over ranks, the unique id
     n, L, G, mode, ref_env = WORKLOADS[args.workload]
     if args.reads:
         n, G = args.reads, max(1000, args.reads * 5)
@@ -469,8 +519,6 @@ def bench_sharded(args):
     dist.barrier()
     idx_calls, realign_calls = load_recorded(rec, None)
     dist.barrier()
-    if rank == 0:
-        shutil.rmtree(wd, ignore_errors=True)
     keep = []
 
     def pin(a):
@@ -478,6 +526,20 @@ def bench_sharded(args):
         keep.append(t)
         return t.numpy()
 
+    rows_pinned = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
+    rows_pinned.numpy()[:] = reads
+    rows_dev = rows_pinned.to(dev)
+    params = api.resolve_params(L, device=local, **{k: int(ref_env[e]) for k, e in (("k", "MC_K"), ("e", "MC_E"), ("w", "MC_W"), ("m", "MC_M")) if e in ref_env})
+    ctx = api.Context(params)
+    ctx.timers_enable(True)
+    fe = shard.ShardedFrontEnd(ctx, rank, world, shard.make_unique_id(dist))
+    m = int(params.first_mininum)
+    # ---- parity pass (untimed, copying API): this rank's results -> files; rank 0 merges them and compares with one GPU
+    pdir = os.path.join(wd, "parity")
+    if rank == 0:
+        os.makedirs(pdir)
+    dist.barrier()
+    rr, part = fe.stage1(rows_dev, n_total, True)
     # this rank's share of every recorded call
     b0, b1 = shard.bucket_range(rank, world)
     my_idx = []
@@ -490,23 +552,63 @@ def bench_sharded(args):
     my_realign = []
     for j, (sg, refs, off, thr, ms, nd) in enumerate(realign_calls):
         same = j > 0 and np.array_equal(refs, realign_calls[j - 1][1]) and np.array_equal(off, realign_calls[j - 1][2])
-        cuts, wbase = shard.contig_partition(off, world, L)
-        lens = np.diff(off.astype(np.int64))
-        n_win = int(np.where(lens >= L, lens - L + 1, 0).sum())
-        g_lo, g_hi = int(wbase[rank]), (int(wbase[rank + 1]) if rank + 1 < world else n_win)
-        my_realign.append((pin(sg), None if same else pin(refs), None if same else off, g_lo, g_hi, thr, ms, nd))
+        mine, pos = fe.select(sg)                                  # the singles of the job's list that this rank produced in Stage 1
+        my_realign.append((pin(mine), pin(pos), len(sg), None if same else pin(refs), None if same else off, thr, ms, nd))
+    blob = {"cls": rr.cls, "cl_n": part.cl_n, "cl_a": part.cl_a, "cl_ref": part.cl_ref, "cl_reflen": part.cl_reflen, "sg": part.sg, "mi": part.mi, "mi_cnt": part.mi_cnt, "rounds": part.rounds}
+    for j, (xy, off) in enumerate(my_idx):
+        ix = ctx.idx_build(xy, off)
+        k, ks, po = ix.arrays()
+        blob.update({f"ik{j}": k, f"ic{j}": np.diff(ks.astype(np.int64)).astype(np.uint32), f"ip{j}": po})
+        ix.close()
+    for j, (sgl, pos, n_job, refs, off, thr, ms, nd) in enumerate(my_realign):
+        r = fe.realign(sgl, pos, n_job, refs, off, thr, ms, nd)
+        blob.update({f"cc{j}": r.claim_contig, f"cs{j}": r.claim_sg, f"cy{j}": r.claim_y, f"cp{j}": r.claim_prio, f"fa{j}": r.fpA_sg, f"ft{j}": r.fpT_sg})
+    np.savez(os.path.join(pdir, f"rank{rank}.npz"), **blob)
+    np.save(os.path.join(pdir, f"rows{rank}.npy"), reads)
+    del reads, blob
+    dist.barrier()
+    par = None
+    if rank == 0:
+        zs = [np.load(os.path.join(pdir, f"rank{q}.npz")) for q in range(world)]
+        got = {}
+        mg = shard.merge_stage1([shard.Stage1Part(z["cl_n"], z["cl_a"], z["cl_ref"], z["cl_reflen"], z["sg"], z["mi"], z["mi_cnt"], z["rounds"]) for z in zs])
+        got.update({"cls": parity.digest(np.concatenate([z["cls"] for z in zs])), "seed.cl_n": parity.digest(mg.cl_n), "seed.cl_a": parity.digest(mg.cl_a),
+                    "seed.cl_ref": parity.digest(mg.cl_ref), "seed.cl_reflen": parity.digest(mg.cl_reflen), "sg": parity.digest(mg.sg),
+                    "seed.mi": parity.digest(parity.bucket_major(mg.mi[np.arange(m)[None, :] < mg.mi_cnt[:, None]]))})
+        for j in range(len(idx_calls)):
+            got.update({f"idx{j}.keys": parity.digest(np.concatenate([z[f"ik{j}"] for z in zs])), f"idx{j}.cnt": parity.digest(np.concatenate([z[f"ic{j}"] for z in zs])),
+                        f"idx{j}.post": parity.digest(np.concatenate([z[f"ip{j}"] for z in zs]))})
+        for j, (sg, refs, off, thr, ms, nd) in enumerate(realign_calls):
+            gc, gs, gy, _ = shard.merge_claims([(z[f"cc{j}"], z[f"cs{j}"], z[f"cy{j}"], z[f"cp{j}"]) for z in zs])
+            got.update(parity.realign_digests(j, sg, len(off) - 1, gc, gs, gy, np.sort(np.concatenate([z[f"fa{j}"] for z in zs])), np.sort(np.concatenate([z[f"ft{j}"] for z in zs]))))
+        # the whole job on ONE GPU, same inputs
+        all_rows = np.concatenate([np.load(os.path.join(pdir, f"rows{q}.npy")) for q in range(world)])
+        one = api.Context(params)
+        want = {}
+        r1 = one.for_reads(all_rows)
+        del all_rows
+        bq = one.for_bucket()
+        want.update(parity.stage1_digests(r1.cls, np.zeros((0, 2), np.uint64), bq.cl_n, bq.cl_a, bq.cl_ref, np.diff(bq.cl_ref_off.astype(np.int64)), bq.sg,
+                                          bq.mi[np.arange(m)[None, :] < bq.mi_cnt[:, None]]))
+        want.pop("tuples")
+        for j, (xy, off) in enumerate(idx_calls):
+            ix = one.idx_build(xy, off)
+            want.update(parity.index_digests(j, *ix.arrays()))
+            ix.close()
+        for j, (sg, refs, off, thr, ms, nd) in enumerate(realign_calls):
+            same = j > 0 and np.array_equal(refs, realign_calls[j - 1][1]) and np.array_equal(off, realign_calls[j - 1][2])
+            r = one.realign(sg, None if same else refs, None if same else off, thr, ms, nd)
+            want.update(parity.realign_digests(j, sg, len(off) - 1, r.claim_contig, r.claim_sg, r.claim_y, r.fpA_sg, r.fpT_sg))
+        one.close()
+        par = parity.compare(got, want)
+        par.update({"against": f"one GPU running the whole job of {n_total} reads on the same inputs (library single-GPU path, itself checked against the reference manifests at N=1)",
+                    "covers": "read classes, seed contigs, singles, index tuples, every index (keys + posting order), per threshold round claims in append order, sg_flag, poly-A/T diversions"})
+        log(f"[rank 0] parity: {json.dumps(par)}")
+        shutil.rmtree(wd, ignore_errors=True)
+    dist.barrier()
     T_cb = int(sum(len(x[0]) // 2 for x in idx_calls))
     R_total = int(len(realign_calls[0][1])) if realign_calls else 0
     del idx_calls, realign_calls
-    rows_pinned = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
-    rows_pinned.numpy()[:] = reads
-    rows_dev = rows_pinned.to(dev)
-    del reads
-    params = api.resolve_params(L, device=local, **{k: int(ref_env[e]) for k, e in (("k", "MC_K"), ("e", "MC_E"), ("w", "MC_W"), ("m", "MC_M")) if e in ref_env})
-    ctx = api.Context(params)
-    ctx.timers_enable(True)
-    fe = shard.ShardedFrontEnd(ctx, dist, dev)
-    fe.time_collectives = True
     api.VIEW_COPY = False          # results are consumed (counted) before the next call: no second copy on the host
     stats = {}
 
@@ -515,12 +617,11 @@ def bench_sharded(args):
         for xy, off in my_idx:
             ctx.idx_build(xy, off).close()
         claims, rounds, d2h = 0, [], 0
-        for sg, refs, off, g_lo, g_hi, thr, ms, nd in my_realign:
-            r = fe.realign(sg, refs, off, g_lo, g_hi, thr, ms, nd)
+        for sgl, pos, n_job, refs, off, thr, ms, nd in my_realign:
+            r = fe.realign(sgl, pos, n_job, refs, off, thr, ms, nd)
             claims += len(r.claim_y)
-            rounds.append({"S": len(sg), "R": R_total, "W": int(r.n_windows), "C": int(r.n_candidates), "nd": int(r.numdict)})
-            d2h += len(r.claim_y) * 16 + (len(r.fpA_sg) + len(r.fpT_sg)) * 4
-        m = int(params.first_mininum)
+            rounds.append({"S": len(sgl), "R": R_total, "W": int(r.n_windows), "C": int(r.n_candidates), "nd": int(r.numdict)})
+            d2h += len(r.claim_y) * 24 + (len(r.fpA_sg) + len(r.fpT_sg)) * 4
         d2h += len(rr.cls) + part.cl_n.nbytes + part.cl_a.nbytes + part.cl_ref.nbytes + len(part.cl_n) * (16 + 1 + 16 * m) + part.sg.nbytes
         d2h += sum(len(xy) * 8 + len(xy) * 12 + (shard.NB + 1) * 4 for xy, _ in my_idx)      # postings + (at most) one key/start per tuple + bucket table
         stats.update({"seed_contigs_rank0": int(len(part.cl_n)), "singles_rank0": int(len(part.sg)), "claims_rank0": claims, "bucket_rounds": int(len(part.rounds)),
@@ -534,14 +635,16 @@ def bench_sharded(args):
         torch.cuda.synchronize()
 
     def dev_ms(tm):
-        return sum(tm.get(k, (0.0, 0))[0] for k in ("for_reads", "for_bucket", "idx_build", "realign"))
+        """entry points (library CUDA events on its stream) + the collectives the library issues between them"""
+        return sum(tm.get(k, (0.0, 0))[0] for k in ("for_reads", "for_bucket", "idx_build", "realign")) + coll_ms(tm)
+
+    def coll_ms(tm):
+        return sum(v[0] for k, v in tm.items() if k.startswith("nccl:"))
 
     for _ in range(args.warmup):
         step(True)
         step(False)
     ctx.timers_reset()
-    fe.collective_ms()
-    fe.bytes_exchanged = 0
     barrier()
     with ClockSampler(local) as clk:
         w0 = time.perf_counter()
@@ -551,8 +654,6 @@ def bench_sharded(args):
         wall_dev_arm = time.perf_counter() - w0
         tm = ctx.timers()
         launches = ctx.kernel_launches()
-        coll_ms = fe.collective_ms()
-        sent = fe.bytes_exchanged
         ctx.timers_reset()
         barrier()
         w0 = time.perf_counter()
@@ -561,8 +662,8 @@ def bench_sharded(args):
         barrier()
         wall_e2e = time.perf_counter() - w0
         tm_e2e = ctx.timers()
-    ms_dev = (dev_ms(tm) + coll_ms) / args.steps
-    vals = torch.tensor([ms_dev, wall_e2e / args.steps * 1e3, wall_dev_arm / args.steps * 1e3, coll_ms / args.steps], dtype=torch.float64, device=dev)
+    ms_dev = dev_ms(tm) / args.steps
+    vals = torch.tensor([ms_dev, wall_e2e / args.steps * 1e3, wall_dev_arm / args.steps * 1e3, coll_ms(tm) / args.steps], dtype=torch.float64, device=dev)
     dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     ms_dev_max, ms_e2e_max, ms_wall_dev_max, coll_max = (float(x) for x in vals.cpu())
     if rank == 0:
@@ -583,25 +684,29 @@ def bench_sharded(args):
             with open(prof) as f:
                 roof["traffic"] = json.load(f).get(dom[2:])
         stats.pop("counters", None)
+        sent = int(tm.get("nccl_bytes_sent", (0.0, 0))[0])
         line = {
             "metric": "reads/sec for sketch+index+overlap stage", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_dev_max, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"{args.workload} x {world}: ONE job of {n_total} x {L} bp reads ({n} per GPU), {G_total} bp random genome, 1% substitutions, mode {mode}, {opts_text(ref_env)}",
-                       "sharding": "reads by read-id range; tuples all-to-all by bucket owner (bucket*G>>14) every round; packed reads all-gather; index builds by bucket range; "
-                                   "Stage 2 contig lt-mer table partitioned by hash range (each rank probes the lt-mers it owns), claim priorities all-reduce(MIN), claims emitted by window range; results bit-identical to one GPU (tests/test_gpu_shard.py)",
+                       "sharding": "reads by read-id range; every round each tuple + the packed row of its read go to the owner of its bucket (bucket*G>>14) in one grouped NCCL send/recv "
+                                   "inside the library; index builds by bucket range; Stage 2 on the rank that owns the single, against all contigs (no claim crosses ranks); "
+                                   "results bit-identical to one GPU (see parity)",
                        "l2": "inputs larger than L2 (reads %.0f MB per GPU per step)" % (n * L / 1e6),
-                       "timing": "value = max over ranks of (CUDA-event time of the library entry points + CUDA-event time of the NCCL collectives), reads resident in HBM; e2e = max over ranks of the wall clock with pinned host inputs and results copied back",
+                       "timing": "value = max over ranks of (CUDA-event time of the library entry points + CUDA-event time of the NCCL collectives it issues), reads resident in HBM; e2e = max over ranks of the wall clock with pinned host inputs and results copied back",
                        "bases_per_s": round(value * L, 1), "wall_ms_per_step_device_arm": round(ms_wall_dev_max, 3), "collective_ms_per_step": round(coll_max, 3),
+                       "collective_ms_per_step_rank0": {k[5:]: round(v[0] / args.steps, 4) for k, v in tm.items() if k.startswith("nccl:")},
                        "nccl_bytes_sent_per_step_rank0": int(sent // max(1, args.steps)), "T_cb": T_cb, "contig_bases": R_total, "rank0": stats,
                        "device_ms_by_entry_point_rank0": {k: round(tm[k][0] / args.steps, 4) for k in ("for_reads", "for_bucket", "idx_build", "realign") if k in tm},
-                       "kernel_ms_per_step_rank0": {k[2:]: round(v[0] / args.steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:12]}, "host_threads": threads},
-            "e2e": {"value": round(n_total / (ms_e2e_max / 1e3), 1), "unit": "reads/s", "h2d_bytes_per_step": int(n * L + sum(x[0].nbytes + x[1].nbytes for x in my_idx) + sum(c[0].nbytes + (c[1].nbytes if c[1] is not None else 0) for c in my_realign)),
+                       "kernel_ms_per_step_rank0": {k[2:]: round(v[0] / args.steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:14]}, "host_threads": threads},
+            "e2e": {"value": round(n_total / (ms_e2e_max / 1e3), 1), "unit": "reads/s", "h2d_bytes_per_step": int(n * L + sum(x[0].nbytes + x[1].nbytes for x in my_idx) + sum(c[0].nbytes + c[1].nbytes + (c[3].nbytes if c[3] is not None else 0) for c in my_realign)),
                     "d2h_bytes_per_step": stats.get("d2h"), "ms_per_step": round(ms_e2e_max, 3), "copy_ms_per_step_rank0": {k: round(tm_e2e[k][0] / args.steps, 3) for k in ("h2d", "d2h") if k in tm_e2e},
-                    "note": "byte counts are rank 0's"},
+                    "note": "byte counts are rank 0's; each rank hands its own results to its host (merging the ranks' lists is the caller's, as in shard.merge_*)"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": roof,
             "cpu_baseline": None,
+            "parity": par,
         }
         emit(line)
     ctx.close()
@@ -609,11 +714,12 @@ def bench_sharded(args):
     dist.destroy_process_group()
 
 
-def cpu_baseline(workload, steps, quiet=False, warmup=0):
-    """The reference's own CPU implementation (oracle/_ref, unmodified sources) on a bounded sample, all host threads."""
+def cpu_baseline(workload, steps, quiet=False, warmup=0, full=False):
+    """The reference's own CPU implementation (oracle/_ref, unmodified sources), all host threads.  full=False: a bounded sample of
+    the workload (same shape and coverage, fewer reads) for the `cpu_baseline` field of our own line; full=True: the workload itself."""
     from minicom_b200 import synth
-    n, L, G = CPU_SAMPLE[workload]
-    mode = WORKLOADS[workload][3]
+    wn, wL, wG, mode, ref_env = WORKLOADS[workload]
+    n, L, G = (wn, wL, wG) if full else CPU_SAMPLE[workload]
     exe = os.path.join(ROOT, "oracle", "_ref", f"minicom_ref_L{L}_{mode}")
     if not os.path.exists(exe):
         return {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {exe} not built"}
@@ -623,32 +729,40 @@ def cpu_baseline(workload, steps, quiet=False, warmup=0):
     reads = synth.make_reads(n, L, G, seed=1)
     fq = os.path.join(wd, "in.fastq")
     synth.write_fastq(fq, reads)
-    secs = []
+    del reads
+    secs, last = [], None
     for i in range(warmup + steps):
-        t = run_binary(exe, fq, wd, WORKLOADS[workload][4], threads)
+        t = run_binary(exe, fq, wd, ref_env, threads)
+        last = t
         if i >= warmup:
             secs.append(front_end_seconds(t))
         if not quiet:
             log(f"[reference] step {i}: front end {front_end_seconds(t):.2f}s (reads {t['kt_for_reads']:.2f} bucket {t['kt_for_bucket']:.2f} idx {t['mm_idx_generation']:.2f} realign {t['realign_hash']:.2f}), host merge {t.get('host_combine', 0):.2f}s")
     shutil.rmtree(wd, ignore_errors=True)
     s = sum(secs) / len(secs)
+    what = "the workload itself" if (n, L, G) == (wn, wL, wG) else f"a bounded sample of the workload ({n} of {wn} reads, same read length and 20x coverage)"
     return {"value": round(n / s, 1), "unit": "reads/s", "cores": threads, "kind": "reference",
-            "sample": f"{n} x {L} bp reads over a {G} bp genome (same shape and 20x coverage as the workload, -t {threads}), wall time inside kt_for_reads+kt_for_bucket+mm_idx_generation+realign_hash = {s:.2f}s",
-            "seconds": round(s, 3)}
+            "sample": f"{what}: {n} x {L} bp reads over a {G} bp genome, -t {threads}, wall time inside kt_for_reads+kt_for_bucket+mm_idx_generation+realign_hash = {s:.2f}s",
+            "sample_reads": n, "workload_reads": wn, "same_config": (n, L, G) == (wn, wL, wG), "seconds": round(s, 3),
+            "phases_s": {k: round(last[k], 3) for k in ("kt_for_reads", "kt_for_bucket", "mm_idx_generation", "realign_hash", "host_combine") if k in last}}
 
 
 def bench_reference(args):
+    """The reference arm runs the SAME workload as ours (C2: 10 M reads).  One step is minutes of CPU, so whatever --steps / --warmup
+    say, it times ONE step without warm-up (the reference is a cold-start batch program anyway) and reports steps = 1."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", 1))
-    cpu = cpu_baseline(args.workload, args.steps, warmup=min(args.warmup, 1))
-    n, L, G = CPU_SAMPLE[args.workload]
+    steps = max(1, min(args.steps, args.ref_steps))
+    cpu = cpu_baseline(args.workload, steps, warmup=0, full=not args.ref_sample)
     wn, wL, wG, mode, _ = WORKLOADS[args.workload]
-    line = {"impl": "reference", "metric": "reads/sec for sketch+index+overlap stage", "value": cpu["value"], "unit": "reads/s", "n_gpus": world, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": cpu["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wn} x {wL} bp reads per GPU, {wG} bp random genome, 1% substitutions, mode {mode}, {opts_text(WORKLOADS[args.workload][4])}",
-                       "note": "CPU arm timed on a bounded sample of the workload (see cpu_baseline.sample); the reference is a single-process CPU program, so its value does not grow with n_gpus"},
+    line = {"impl": "reference", "metric": "reads/sec for sketch+index+overlap stage", "value": cpu["value"], "unit": "reads/s", "n_gpus": world, "steps": steps,
+            "warmup": 0, "ms_per_step": cpu["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cpu['sample_reads']} x {wL} bp reads, {wG if cpu['same_config'] else CPU_SAMPLE[args.workload][2]} bp random genome, 1% substitutions, mode {mode}, {opts_text(WORKLOADS[args.workload][4])}",
+                       "same_config_as_ours": cpu["same_config"],
+                       "note": f"unmodified reference (oracle/_ref), -t {cpu['cores']}; steps capped at {steps} (requested {args.steps}) because one step is minutes of CPU; "
+                               "the reference is a single-process CPU program, so its value does not grow with n_gpus"},
             "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
@@ -663,6 +777,9 @@ def main():
     ap.add_argument("--reads", type=int, default=0, help="override reads per GPU (debug)")
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--record-threads", type=int, default=0, help="num_thr of the untimed recording run at N=1 (default 1: deterministic, manifest parity applies)")
+    ap.add_argument("--ref-steps", type=int, default=1, help="--impl reference: cap on the timed steps (one step of C2 is minutes of CPU)")
+    ap.add_argument("--ref-sample", action="store_true", help="--impl reference: time the bounded sample instead of the full workload")
     ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent single-GPU jobs instead of one sharded job")
     args = ap.parse_args()
     claim_stdout()

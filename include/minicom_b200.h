@@ -162,6 +162,10 @@ const uint64_t *mcb_idx_get(const mcb_index *idx, uint64_t minier, int *n);
 void mcb_idx_destroy(mcb_index *idx);
 /* Introspection for tests: number of distinct keys and postings. */
 void mcb_idx_stats(const mcb_index *idx, uint64_t *n_keys, uint64_t *n_post);
+/* The whole index as flat host arrays (valid until mcb_idx_destroy): keys[n_keys] distinct minimizers, bucket-major and ascending
+ * inside a bucket; kstart[n_keys+1] posting offsets; post[n_post] the y values, per key in the reference's order;
+ * bucket_keys[2^b+1] first key of every bucket.  Any of the four pointers may be NULL. */
+void mcb_idx_arrays(const mcb_index *idx, const uint64_t **keys, const uint32_t **kstart, const uint64_t **post, const uint32_t **bucket_keys);
 
 /* ------------------------------------------------------------------ */
 /* realign_hash (kthread_hash_realign.c:569)                            */

@@ -51,7 +51,7 @@ EXPORTS = [
     "mcb_resolve_params", "mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version",
     "mcb_for_reads", "mcb_for_reads_ptrs", "mcb_for_reads_device",
     "mcb_debug_read_tuples", "mcb_debug_sketch_two", "mcb_debug_unpack_reads",
-    "mcb_for_bucket", "mcb_idx_build", "mcb_idx_build_scattered", "mcb_idx_get", "mcb_idx_destroy", "mcb_idx_stats",
+    "mcb_for_bucket", "mcb_idx_build", "mcb_idx_build_scattered", "mcb_idx_get", "mcb_idx_destroy", "mcb_idx_stats", "mcb_idx_arrays",
     "mcb_realign", "mcb_sketch_lh_host", "mcb_sketch_two_host", "mcb_hash64",
     "mcb_timers_enable", "mcb_timers_reset", "mcb_timer_get", "mcb_timers_dump", "mcb_kernel_launches",
     "mcb_round_control_init", "mcb_round_control_begin", "mcb_round_control_end",
@@ -97,6 +97,8 @@ def load_library() -> C.CDLL:
     lib.mcb_idx_destroy.restype = None
     lib.mcb_idx_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.mcb_idx_stats.restype = None
+    lib.mcb_idx_arrays.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4
+    lib.mcb_idx_arrays.restype = None
     lib.mcb_realign.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                 C.c_int, C.c_int, C.c_int, C.POINTER(_RealignResult)]
     lib.mcb_sketch_lh_host.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int64]
@@ -225,6 +227,13 @@ class Index:
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._lib.mcb_idx_stats(self._h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def arrays(self):
+        """(keys, kstart, post) of the whole index (copies)"""
+        nk, npost = self.stats()
+        k, ks, po = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)
+        self._lib.mcb_idx_arrays(self._h, C.byref(k), C.byref(ks), C.byref(po), None)
+        return _view(k.value, nk, np.uint64), _view(ks.value, nk + 1, np.uint32), _view(po.value, npost, np.uint64)
 
     def close(self):
         if self._h:

@@ -197,6 +197,14 @@ extern "C" void mcb_idx_stats(const mcb_index *ix, uint64_t *n_keys, uint64_t *n
 	if (n_post) *n_post = ix ? ix->n_post : 0;
 }
 
+extern "C" void mcb_idx_arrays(const mcb_index *ix, const uint64_t **keys, const uint32_t **kstart, const uint64_t **post, const uint32_t **bucket_keys)
+{
+	if (keys) *keys = ix ? ix->keys : nullptr;
+	if (kstart) *kstart = ix ? ix->kstart : nullptr;
+	if (post) *post = ix ? ix->post : nullptr;
+	if (bucket_keys) *bucket_keys = ix ? ix->ub : nullptr;
+}
+
 extern "C" const uint64_t *mcb_idx_get(const mcb_index *ix, uint64_t minier, int *n)
 {
 	*n = 0;

@@ -975,7 +975,7 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, const uint32_t *sg_i
 	for (int attempt = 0;; ++attempt) {
 		if (n_listed) MCB_LAUNCH(ctx, "s2_verify", k_s2_verify, mcb_grid_for(n_listed, 128), 128, 0, jn, gm, b_cand.as<unsigned long long>(), n_listed);
 		// every rank must take the same way through the guard: the decision counters are summed over the ranks first
-		if (sharded) { McbSpan sp2(ctx->tm, "nccl:guard"); MCB_TRY(mcb_coll_allreduce_sum_u64(ctx, &dc[CT_S2_NEEDEXACT], 1)); }
+		if (sharded) MCB_TRY(mcb_coll_allreduce_sum_u64(ctx, &dc[CT_S2_NEEDEXACT], 1));       // (inside the "realign" span)
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 		if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }
@@ -997,7 +997,6 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, const uint32_t *sg_i
 			MCB_LAUNCH(ctx, "s2_bins_exact", k_s2_bins_exact, mcb_grid_for(nkv, 256), 256, 0, b_rd.as<uint64_t>(), S, gm, tkey, tcnt, H - 1);
 			jn.xkey = tkey; jn.xcnt = tcnt; jn.xmask = H - 1;
 		} else {                      // the count-min sketch summed over the ranks bounds every bin of the job
-			McbSpan sp2(ctx->tm, "nccl:guard");
 			MCB_TRY(mcb_coll_allreduce_sum_u32(ctx, b_cm.as<uint32_t>(), CM));
 			jn.cmg = b_cm.as<uint32_t>(); jn.cmg_mask = CM - 1;
 		}
