@@ -34,6 +34,7 @@ unsigned char seq_nt4_table[256] = {
 const char invert_code_rule[4] = {'A', 'C', 'G', 'T'};
 
 static mcb_ctx *g_ctx = 0;
+static mcb_group *g_grp = 0;    // MCB_DEVICES=0,1,...: the same calls over several GPUs (one context per device inside the library)
 static double g_wall[4];      // for_reads, for_bucket, idx_build, realign (host wall seconds inside the entry points)
 static int g_calls[4];
 static std::string g_realign_detail;
@@ -65,7 +66,8 @@ struct McbAtExit {
 			if (f) {
 				static char buf[1 << 16];
 				buf[0] = 0;
-				if (g_ctx) mcb_timers_dump(g_ctx, buf, sizeof buf);
+				if (g_grp) mcb_group_timers_dump(g_grp, buf, sizeof buf);
+				else if (g_ctx) mcb_timers_dump(g_ctx, buf, sizeof buf);
 				std::string dev = "{";
 				for (char *line = strtok(buf, "\n"); line; line = strtok(0, "\n")) {
 					char name[128]; double ms; unsigned long long cnt;
@@ -79,10 +81,11 @@ struct McbAtExit {
 				        "\"mm_idx_generation\": %.6f, \"n_idx\": %d, \"realign_hash\": %.6f, \"n_realign\": %d, \"realign_rounds\": [%s], "
 				        "\"kernel_launches\": %llu, \"device_ms\": %s}\n",
 				        reads ? reads->n_seq : 0, reads ? reads->seq_len : 0, n_threads, g_wall[0], g_wall[1], g_wall[2], g_calls[2], g_wall[3], g_calls[3],
-				        g_realign_detail.c_str(), g_ctx ? (unsigned long long)mcb_kernel_launches(g_ctx) : 0ull, dev.c_str());
+				        g_realign_detail.c_str(), g_ctx ? (unsigned long long)mcb_kernel_launches(g_ctx) : 0ull, dev.c_str());     // (group: rank 0's launches, per-timer maximum over the ranks)
 				fclose(f);
 			}
 		}
+		if (g_grp) { mcb_group_destroy(g_grp); g_grp = 0; g_ctx = 0; }
 		if (g_ctx) { mcb_destroy(g_ctx); g_ctx = 0; }
 	}
 };
@@ -97,6 +100,17 @@ static mcb_ctx *ctx_for(reads_t *r)
 	p.first_mininum = first_mininum; p.diff_threshold = diff_threshold; p.max_rounds = max_rounds;
 	const char *dev = getenv("MCB_DEVICE");
 	p.device = dev ? atoi(dev) : 0;
+	std::vector<int> devs;                                    // MCB_DEVICES=0,1,...  (more than one device: the sharded path)
+	if (const char *list = getenv("MCB_DEVICES"))
+		for (const char *q = list; *q;) { char *e; long v = strtol(q, &e, 10); if (e == q) break; devs.push_back((int)v); q = *e ? e + 1 : e; }
+	if (devs.size() > 1) {
+		int rc = mcb_group_create(&p, devs.data(), (int)devs.size(), &g_grp);
+		if (rc) die("mcb_group_create", rc);
+		g_ctx = mcb_group_context(g_grp, 0);
+		if (getenv("MCB_TIMING")) for (int i = 0; i < mcb_group_size(g_grp); ++i) mcb_timers_enable(mcb_group_context(g_grp, i), 1);
+		return g_ctx;
+	}
+	if (devs.size() == 1) p.device = devs[0];
 	int rc = mcb_create(&p, &g_ctx);
 	if (rc) die("mcb_create", rc);
 	if (getenv("MCB_TIMING")) mcb_timers_enable(g_ctx, 1);
@@ -109,7 +123,8 @@ void kt_for_reads(int n_threads_, reads_t *r, long n)
 	double t0 = realtime();
 	mcb_ctx *ctx = ctx_for(r);
 	mcb_reads_result res;
-	int rc = mcb_for_reads_ptrs(ctx, &r->seq[0].seq, sizeof(bseq1_t), (uint64_t)n, n_threads_, &res);
+	int rc = g_grp ? mcb_group_for_reads_ptrs(g_grp, &r->seq[0].seq, sizeof(bseq1_t), (uint64_t)n, n_threads_, &res)
+	               : mcb_for_reads_ptrs(ctx, &r->seq[0].seq, sizeof(bseq1_t), (uint64_t)n, n_threads_, &res);
 	if (rc) die("kt_for_reads", rc);
 	sp_reads_t *s = r->sp;
 	for (long i = 0; i < n; ++i) {
@@ -143,7 +158,7 @@ void kt_for_bucket(int n_threads_, reads_t *r, long n)
 	double t0 = realtime();
 	mcb_ctx *ctx = ctx_for(r);
 	mcb_bucket_result res;
-	int rc = mcb_for_bucket(ctx, &res);
+	int rc = g_grp ? mcb_group_for_bucket(g_grp, &res) : mcb_for_bucket(ctx, &res);
 	if (rc) die("kt_for_bucket", rc);
 	cluster_v *cv = &r->clusters[0][0];
 	for (uint64_t c = 0; c < res.n_clusters; ++c) {
@@ -195,7 +210,7 @@ void mm_idx_generation(int n_threads_, mm_idx_t *mi)
 		record("idx", g_calls[2], "xy.u64", flat.data(), flat.size() * sizeof(mcb_tuple));
 	}
 	mcb_index *ix = 0;
-	int rc = mcb_idx_build_scattered(ctx, ptrs.data(), cnt.data(), n_threads_, &ix);
+	int rc = g_grp ? mcb_group_idx_build_scattered(g_grp, ptrs.data(), cnt.data(), n_threads_, &ix) : mcb_idx_build_scattered(ctx, ptrs.data(), cnt.data(), n_threads_, &ix);
 	if (rc) die("mm_idx_generation", rc);
 	for (int i = 0; i < nb; ++i) { free(mi->B[i].a.a); mi->B[i].a.a = 0; mi->B[i].a.n = mi->B[i].a.m = 0; }   // kthread_idx.c:166-167
 	if (mi->B[0].h) mcb_idx_destroy((mcb_index*)mi->B[0].h);
@@ -271,8 +286,10 @@ void realign_hash(int n_threads_, reads_t *r, int index, int max_threshold)
 	}
 	const bool same = g_calls[3] > 0 && !memcmp(sig, sent_sig, sizeof sig) && !getenv("MCB_RESEND_CONTIGS");
 	mcb_realign_result res;
-	int rc = same ? mcb_realign(ctx, r->sg.a, r->sg.n, NULL, NULL, contigs.size(), max_threshold, maxsearch, ininumdict, &res)
-	              : mcb_realign(ctx, r->sg.a, r->sg.n, refs.data(), off.data(), contigs.size(), max_threshold, maxsearch, ininumdict, &res);
+	const char *rp = same ? NULL : refs.data();
+	const uint64_t *op = same ? NULL : off.data();
+	int rc = g_grp ? mcb_group_realign(g_grp, r->sg.a, r->sg.n, rp, op, contigs.size(), max_threshold, maxsearch, ininumdict, &res)
+	               : mcb_realign(ctx, r->sg.a, r->sg.n, rp, op, contigs.size(), max_threshold, maxsearch, ininumdict, &res);
 	memcpy(sent_sig, sig, sizeof sig);
 	if (rc) die("realign_hash", rc);
 	for (uint64_t i = 0; i < res.n_fpA; ++i) { r->sg_flag[res.fpA_sg[i]] = true; kv_push(uint32_t, r->fpA_id, r->sg.a[res.fpA_sg[i]]); }

@@ -237,6 +237,22 @@ int mcb_shard_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res, uint64_t *round_c
 int mcb_shard_realign(mcb_ctx *ctx, const uint32_t *sg, const uint32_t *sg_index, uint64_t n_sg_local, uint64_t n_sg_total,
                       const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res);
 
+/* Several GPUs behind the single-GPU call shapes, for a host program that is one process (what the drop-in shim uses when
+ * MCB_DEVICES lists more than one device): one context per device, one host thread per context while a call runs, results
+ * merged into exactly what one GPU returns.  The arguments and result structs mean what they mean in mcb_for_reads_ptrs,
+ * mcb_for_bucket, mcb_idx_build_scattered (the returned index answers mcb_idx_get / mcb_idx_destroy) and mcb_realign. */
+typedef struct mcb_group mcb_group;
+int  mcb_group_create(const mcb_params *p, const int *devices, int n_devices, mcb_group **out);   /* p->device is ignored */
+void mcb_group_destroy(mcb_group *g);
+int  mcb_group_size(const mcb_group *g);
+mcb_ctx *mcb_group_context(mcb_group *g, int rank);                                                 /* e.g. for mcb_timers_enable */
+int  mcb_group_for_reads_ptrs(mcb_group *g, const void *first_seq_ptr, size_t stride, uint64_t n, int n_threads, mcb_reads_result *res);
+int  mcb_group_for_bucket(mcb_group *g, mcb_bucket_result *res);
+int  mcb_group_idx_build_scattered(mcb_group *g, const mcb_tuple *const *ptrs, const uint64_t *cnt, int n_threads, mcb_index **out);
+int  mcb_group_realign(mcb_group *g, const uint32_t *sg, uint64_t n_sg, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
+                       int threshold, int maxsearch, int ininumdict, mcb_realign_result *res);
+size_t mcb_group_timers_dump(mcb_group *g, char *buf, size_t cap);                                  /* per timer: the maximum over the ranks */
+
 /* ------------------------------------------------------------------ */
 /* host-side boundary helpers                                           */
 /* ------------------------------------------------------------------ */

@@ -55,6 +55,8 @@ EXPORTS = [
     "mcb_realign", "mcb_sketch_lh_host", "mcb_sketch_two_host", "mcb_hash64",
     "mcb_timers_enable", "mcb_timers_reset", "mcb_timer_get", "mcb_timers_dump", "mcb_kernel_launches",
     "mcb_round_control_init", "mcb_round_control_begin", "mcb_round_control_end",
+    "mcb_group_create", "mcb_group_destroy", "mcb_group_size", "mcb_group_context", "mcb_group_for_reads_ptrs", "mcb_group_for_bucket",
+    "mcb_group_idx_build_scattered", "mcb_group_realign", "mcb_group_timers_dump",
     "mcb_shard_unique_id", "mcb_shard_init", "mcb_shard_attach", "mcb_shard_begin", "mcb_shard_for_bucket", "mcb_shard_realign",
 ]
 NCCL_ID_BYTES = 128

@@ -181,11 +181,21 @@ struct mcb_index {
 	uint32_t *ub = nullptr;        // [2^b+1]    key range of each bucket
 	HBuf slab;                     // one pinned allocation behind the four arrays (recycled through the context's pool)
 	McbPinnedPool *pool = nullptr;
+	std::vector<mcb_index*> parts; // several GPUs (mcb_group.cu): part r holds the buckets rank r owns (bucket * G >> b); this node holds nothing itself
 };
+
+mcb_index *mcb_index_make_group(std::vector<mcb_index*> &parts, int b)
+{
+	mcb_index *ix = new mcb_index();
+	ix->b = b; ix->parts = parts;
+	for (auto p : parts) { ix->n_keys += p->n_keys; ix->n_post += p->n_post; }
+	return ix;
+}
 
 extern "C" void mcb_idx_destroy(mcb_index *ix)
 {
 	if (!ix) return;
+	for (auto p : ix->parts) mcb_idx_destroy(p);
 	if (ix->pool) { if (ix->pool->give(ix->slab)) delete ix->pool; }
 	else ix->slab.release();
 	delete ix;
@@ -199,6 +209,7 @@ extern "C" void mcb_idx_stats(const mcb_index *ix, uint64_t *n_keys, uint64_t *n
 
 extern "C" void mcb_idx_arrays(const mcb_index *ix, const uint64_t **keys, const uint32_t **kstart, const uint64_t **post, const uint32_t **bucket_keys)
 {
+	if (ix && !ix->parts.empty()) ix = nullptr;          // a group index has no flat arrays of its own
 	if (keys) *keys = ix ? ix->keys : nullptr;
 	if (kstart) *kstart = ix ? ix->kstart : nullptr;
 	if (post) *post = ix ? ix->post : nullptr;
@@ -210,6 +221,7 @@ extern "C" const uint64_t *mcb_idx_get(const mcb_index *ix, uint64_t minier, int
 	*n = 0;
 	if (!ix || !ix->n_keys) return nullptr;
 	const uint32_t bk = (uint32_t)(minier & ((1ull << ix->b) - 1));
+	if (!ix->parts.empty()) return mcb_idx_get(ix->parts[((uint64_t)bk * ix->parts.size()) >> ix->b], minier, n);
 	uint32_t lo = ix->ub[bk], hi = ix->ub[bk + 1];
 	while (lo < hi) {
 		uint32_t mid = lo + ((hi - lo) >> 1);
