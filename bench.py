@@ -612,16 +612,25 @@ def bench_sharded(args):
     api.VIEW_COPY = False          # results are consumed (counted) before the next call: no second copy on the host
     stats = {}
 
+    wall = {}
+
     def step(device_resident):
-        rr, part = fe.stage1(rows_dev if device_resident else rows_pinned.numpy(), n_total, device_resident)
+        w = wall.setdefault("device" if device_resident else "host", {"stage1": 0.0, "idx_build": 0.0, "realign": 0.0})
+        t = time.perf_counter()
+        rr, part = fe.stage1(rows_dev if device_resident else rows_pinned.numpy(), n_total, device_resident, keep_mask=True)
+        w["stage1"] += time.perf_counter() - t
+        t = time.perf_counter()
         for xy, off in my_idx:
             ctx.idx_build(xy, off).close()
+        w["idx_build"] += time.perf_counter() - t
+        t = time.perf_counter()
         claims, rounds, d2h = 0, [], 0
         for sgl, pos, n_job, refs, off, thr, ms, nd in my_realign:
             r = fe.realign(sgl, pos, n_job, refs, off, thr, ms, nd)
             claims += len(r.claim_y)
             rounds.append({"S": len(sgl), "R": R_total, "W": int(r.n_windows), "C": int(r.n_candidates), "nd": int(r.numdict)})
             d2h += len(r.claim_y) * 24 + (len(r.fpA_sg) + len(r.fpT_sg)) * 4
+        w["realign"] += time.perf_counter() - t
         d2h += len(rr.cls) + part.cl_n.nbytes + part.cl_a.nbytes + part.cl_ref.nbytes + len(part.cl_n) * (16 + 1 + 16 * m) + part.sg.nbytes
         d2h += sum(len(xy) * 8 + len(xy) * 12 + (shard.NB + 1) * 4 for xy, _ in my_idx)      # postings + (at most) one key/start per tuple + bucket table
         stats.update({"seed_contigs_rank0": int(len(part.cl_n)), "singles_rank0": int(len(part.sg)), "claims_rank0": claims, "bucket_rounds": int(len(part.rounds)),
@@ -644,6 +653,7 @@ def bench_sharded(args):
     for _ in range(args.warmup):
         step(True)
         step(False)
+    wall.clear()
     ctx.timers_reset()
     barrier()
     with ClockSampler(local) as clk:
@@ -695,7 +705,8 @@ def bench_sharded(args):
                        "l2": "inputs larger than L2 (reads %.0f MB per GPU per step)" % (n * L / 1e6),
                        "timing": "value = max over ranks of (CUDA-event time of the library entry points + CUDA-event time of the NCCL collectives it issues), reads resident in HBM; e2e = max over ranks of the wall clock with pinned host inputs and results copied back",
                        "bases_per_s": round(value * L, 1), "wall_ms_per_step_device_arm": round(ms_wall_dev_max, 3), "collective_ms_per_step": round(coll_max, 3),
-                       "collective_ms_per_step_rank0": {k[5:]: round(v[0] / args.steps, 4) for k, v in tm.items() if k.startswith("nccl:")},
+                       "collective_ms_per_step_rank0": {k.split(":", 1)[1]: round(v[0] / args.steps, 4) for k, v in tm.items() if k.startswith("nccl:") or k.startswith("nccl_in:")},
+                       "host_wall_ms_per_step_rank0": {a: {k: round(v / args.steps * 1e3, 3) for k, v in d.items()} for a, d in wall.items()},
                        "nccl_bytes_sent_per_step_rank0": int(sent // max(1, args.steps)), "T_cb": T_cb, "contig_bases": R_total, "rank0": stats,
                        "device_ms_by_entry_point_rank0": {k: round(tm[k][0] / args.steps, 4) for k in ("for_reads", "for_bucket", "idx_build", "realign") if k in tm},
                        "kernel_ms_per_step_rank0": {k[2:]: round(v[0] / args.steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:14]}, "host_threads": threads},

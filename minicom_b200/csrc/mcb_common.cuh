@@ -141,7 +141,7 @@ struct McbSpan {
 // slots of the device scalar block ctx->d_counters (u64[64])
 enum { CT_SKETCHED = 0, CT_BADCHAR = 1, CT_DEGENERATE = 2, CT_NREADS = 3, CT_REFCURSOR = 4, CT_G = 5, CT_TOT_CL = 6, CT_TOT_MEM = 7,
        CT_TOT_REF = 8, CT_TOT_SG = 9, CT_TOT_RESK = 10, CT_ERR = 11, CT_SCRATCH_IDX = 12,
-       CT_S2_U = 16, CT_S2_PROBES = 17, CT_S2_CAND = 18, CT_S2_NEEDEXACT = 19, CT_S2_CLAIMS = 20, CT_S2_FPA = 21, CT_S2_FPT = 22, CT_S2_ERR = 23,
+       CT_S2_U = 16, CT_S2_PROBES = 17, CT_S2_CAND = 18, CT_S2_NEEDEXACT = 19, CT_S2_ERR = 20 /* adjacent to NEEDEXACT: summed over the ranks together */, CT_S2_FPA = 21, CT_S2_FPT = 22, CT_S2_CLAIMS = 23,
        CT_S2_MAXBIN = 24, CT_S2_DIFF = 25, CT_SORT_OVERFLOW = 13, CT_S2_NCAND = 26, CT_S2_NBIGMEM = 27, CT_S2_NEVENTS = 28, CT_WORK0 = 32 /* ..35: consensus work-list sizes */ };
 
 // ---------------------------------------------------------------- context
@@ -437,6 +437,7 @@ int mcb_copy_streams(mcb_ctx *ctx);   // creates copy_stream / copy_stream2 on f
 // collectives over the context's communicator, enqueued on ctx->stream (mcb_shard.cu)
 int mcb_coll_allreduce_sum_u64(mcb_ctx *ctx, unsigned long long *d_inout, size_t n);
 int mcb_coll_allreduce_sum_u32(mcb_ctx *ctx, uint32_t *d_inout, size_t n);
+int mcb_coll_allgather_inplace_u64(mcb_ctx *ctx, uint64_t *d_buf, size_t chunk_words);      // rank r contributes d_buf[r*chunk, (r+1)*chunk)
 int mcb_coll_allgatherv(mcb_ctx *ctx, const void *d_send, uint64_t bytes, std::vector<unsigned long long> &host_out);   // variable-size all-gather of 8-byte words to the host, rank order
 
 static inline unsigned mcb_grid_for(uint64_t n, unsigned block, unsigned cap = 0x7FFFFFFFu)

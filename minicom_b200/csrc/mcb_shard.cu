@@ -103,6 +103,13 @@ int mcb_coll_allreduce_sum_u32(mcb_ctx *ctx, uint32_t *d, size_t n)
 	return MCB_OK;
 }
 
+int mcb_coll_allgather_inplace_u64(mcb_ctx *ctx, uint64_t *d_buf, size_t chunk_words)
+{
+	if (ctx->shard_n <= 1 || !chunk_words) return MCB_OK;
+	MCB_NCCL(ncclAllGather(d_buf + (size_t)ctx->shard_rank * chunk_words, d_buf, chunk_words, ncclUint64, comm_of(ctx), ctx->stream));
+	return MCB_OK;
+}
+
 // every rank contributes `n` 8-byte words, all ranks get the [n_ranks][n] table on the host
 static int allgather_words(mcb_ctx *ctx, const unsigned long long *h_mine, int n, unsigned long long *h_all)
 {

@@ -85,10 +85,10 @@ __device__ bool enc_ok(const uint64_t *x, int L, int limit)
 // ---------------------------------------------------------------- K5a contig packing
 // contig c occupies words [cw_off[c], cw_off[c+1]) (ceil(len/32)+1 words, zero padded)
 __global__ void k_s2_pack_refs(const char *__restrict__ refs, const uint64_t *__restrict__ ref_off, const uint64_t *__restrict__ cw_off, uint64_t n_contigs,
-                               uint64_t total_words, uint64_t *__restrict__ cw, unsigned long long *__restrict__ counters)
+                               uint64_t w_begin, uint64_t w_end, uint64_t *__restrict__ cw, unsigned long long *__restrict__ counters)
 {
-	uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= total_words) return;
+	const uint64_t q = w_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;      // words [w_begin, w_end): all of them, or this rank's share
+	if (q >= w_end) return;
 	uint64_t lo = 0, hi = n_contigs;          // last c with cw_off[c] <= q
 	while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (cw_off[mid] <= q) lo = mid; else hi = mid; }
 	const uint64_t c = lo, wq = q - cw_off[c];
@@ -618,7 +618,22 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	cwo[n_contigs] = total_words + 1; wo[n_contigs] = n_windows; eo[n_contigs] = n_entries;   // +1 guard word: loaders read one word ahead
 	if (n_windows >= (1ull << 58)) { mcb_set_error("too many windows"); return MCB_EINVAL; }
 	// ---- same contigs as last time?  (compare on the device: the strings have to be uploaded to find out)
-	const bool maybe_same = cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L;
+	// Sharded: every rank needs all packed contigs, but each uploads and packs only its share of the words (an equal slice of the
+	// padded word array) and one in-place all-gather over NVLink completes the array; nothing is compared with the cache then
+	// (the caller says "same contigs" by passing NULL).
+	const bool sharded = ctx->shard_n > 1 && ctx->comm;
+	const uint64_t chunk = sharded ? (total_words + 2 + ctx->shard_n - 1) / ctx->shard_n : total_words + 2;
+	const uint64_t w_begin = sharded ? std::min<uint64_t>((uint64_t)ctx->shard_rank * chunk, total_words) : 0;
+	const uint64_t w_end = sharded ? std::min<uint64_t>(w_begin + chunk, total_words) : total_words;
+	uint64_t b_lo = 0, b_hi = ref_bytes;                  // characters the words [w_begin, w_end) are made of
+	if (sharded && n_contigs) {
+		if (w_end > w_begin) {
+			const uint64_t c0 = (uint64_t)(std::upper_bound(cwo, cwo + n_contigs, w_begin) - cwo) - 1, c1 = (uint64_t)(std::upper_bound(cwo, cwo + n_contigs, w_end - 1) - cwo) - 1;
+			b_lo = std::min(ref_off[c0] + (w_begin - cwo[c0]) * 32, ref_off[c0 + 1]);
+			b_hi = std::min(ref_off[c1] + (w_end - cwo[c1]) * 32, ref_off[c1 + 1]);
+		} else b_lo = b_hi = 0;
+	}
+	const bool maybe_same = !sharded && cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L;
 	DBuf &stage_refs = maybe_same ? ctx->d_scr[1] : cx.refs, &stage_off = maybe_same ? ctx->d_scr[2] : cx.roff;
 	const size_t refs_pad = (ref_bytes + 7) & ~(size_t)7;
 	MCB_TRY(stage_refs.ensure(refs_pad + 16)); MCB_TRY(stage_off.ensure((n_contigs + 1) * 8));
@@ -632,7 +647,7 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 		MCB_CUDA(cudaEventCreate(&ev.a)); MCB_CUDA(cudaEventCreate(&ev.b));
 		MCB_CUDA(cudaEventRecord(ev.a, ctx->copy_stream));             // (every earlier call has synchronized: nothing else touches these buffers)
 		if (refs_pad > ref_bytes) MCB_CUDA(cudaMemsetAsync(stage_refs.as<char>() + (refs_pad - 8), 0, 8, ctx->copy_stream));
-		MCB_TRY(mcb_h2d_on(ctx, ctx->copy_stream, stage_refs.p, refs, ref_bytes, 4));
+		if (b_hi > b_lo) MCB_TRY(mcb_h2d_on(ctx, ctx->copy_stream, stage_refs.as<char>() + b_lo, refs + b_lo, b_hi - b_lo, 4));
 		MCB_TRY(mcb_h2d_on(ctx, ctx->copy_stream, stage_off.p, ref_off, (n_contigs + 1) * 8, 1));
 		MCB_CUDA(cudaEventRecord(ev.b, ctx->copy_stream));
 		MCB_CUDA(cudaStreamWaitEvent(ctx->stream, ev.b, 0));
@@ -656,7 +671,7 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	cx.table_valid = false;
 	cx.n_contigs = n_contigs; cx.ref_bytes = ref_bytes; cx.total_words = total_words; cx.n_windows = n_windows; cx.n_entries = n_entries; cx.L = L; cx.lt = lt;
 	const uint64_t n_blocks = (ref_bytes >> S2_BLK_SHIFT) + 1;
-	MCB_TRY(cx.cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.wo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.cw.ensure((total_words + 2) * 8));
+	MCB_TRY(cx.cwo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.wo.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.cw.ensure((chunk * (sharded ? ctx->shard_n : 1) + 2) * 8));
 	MCB_TRY(cx.pblk.ensure(n_blocks * 4 + 16));
 	MCB_TRY(cx.eoff.ensure((n_contigs + 1) * 8)); MCB_TRY(cx.meta.ensure((n_contigs + 2) * 32));
 	{
@@ -669,9 +684,13 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 	McbSpan sp(ctx->tm, "realign");
 	MCB_LAUNCH(ctx, "s2_contig_meta", k_s2_contig_meta, mcb_grid_for(n_contigs + 1, 256), 256, 0, cx.roff.as<uint64_t>(), cx.cwo.as<uint64_t>(), cx.wo.as<uint64_t>(), n_contigs,
 	           cx.meta.as<S2ContigMeta>());
-	MCB_CUDA(cudaMemsetAsync(cx.cw.as<uint64_t>() + total_words, 0, 16, ctx->stream));
-	MCB_LAUNCH(ctx, "s2_pack_refs", k_s2_pack_refs, mcb_grid_for(total_words, 256), 256, 0, cx.refs.as<char>(), cx.roff.as<uint64_t>(), cx.cwo.as<uint64_t>(),
-	           n_contigs, total_words, cx.cw.as<uint64_t>(), dc);
+	if (w_end > w_begin) MCB_LAUNCH(ctx, "s2_pack_refs", k_s2_pack_refs, mcb_grid_for(w_end - w_begin, 256), 256, 0, cx.refs.as<char>(), cx.roff.as<uint64_t>(), cx.cwo.as<uint64_t>(),
+	                                n_contigs, w_begin, w_end, cx.cw.as<uint64_t>(), dc);
+	if (sharded) {                 // ("nccl_in:" = a collective inside the entry point's own span)
+		McbSpan sp2(ctx->tm, "nccl_in:contigs");
+		MCB_TRY(mcb_coll_allgather_inplace_u64(ctx, cx.cw.as<uint64_t>(), chunk));
+	}
+	MCB_CUDA(cudaMemsetAsync(cx.cw.as<uint64_t>() + total_words, 0, 16, ctx->stream));              // guard words: loaders read one word ahead
 	MCB_LAUNCH(ctx, "s2_pos_blocks", k_s2_pos_blocks, mcb_grid_for(n_blocks, 256), 256, 0, cx.roff.as<uint64_t>(), n_contigs, n_blocks, cx.pblk.as<uint32_t>());
 	cx.valid = true;
 	return MCB_OK;
@@ -912,7 +931,7 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, const uint32_t *sg_i
 	// for 15 M pairs) the atomics resolve in L2 instead of DRAM.  Sized from the JOB's singles: every rank uses the same array.
 	static const int cm_shift = getenv("MCB_S2_CM") ? atoi(getenv("MCB_S2_CM")) : -1;
 	const uint64_t cm_want = cm_shift >= 0 ? nkv_job << cm_shift : nkv_job >> -cm_shift;
-	uint64_t CM = 1024; while (CM < cm_want && CM < (1ull << 26)) CM <<= 1;
+	uint64_t CM = 1024; while (CM < cm_want && CM < (1ull << 23)) CM <<= 1;                          // at most 32 MB: it has to stay in L2
 	if (nkv_job) MCB_TRY(b_cm.ensure(CM * 4));
 	if (nkv) {
 		{
@@ -975,7 +994,7 @@ static int realign_search(mcb_ctx *ctx, const uint32_t *sg, const uint32_t *sg_i
 	for (int attempt = 0;; ++attempt) {
 		if (n_listed) MCB_LAUNCH(ctx, "s2_verify", k_s2_verify, mcb_grid_for(n_listed, 128), 128, 0, jn, gm, b_cand.as<unsigned long long>(), n_listed);
 		// every rank must take the same way through the guard: the decision counters are summed over the ranks first
-		if (sharded) MCB_TRY(mcb_coll_allreduce_sum_u64(ctx, &dc[CT_S2_NEEDEXACT], 1));       // (inside the "realign" span)
+		if (sharded) MCB_TRY(mcb_coll_allreduce_sum_u64(ctx, &dc[CT_S2_NEEDEXACT], 2));       // NEEDEXACT and ERR (inside the "realign" span)
 		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, dc, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 		if (hc[CT_S2_ERR]) { mcb_set_error("mcb_realign: %llu invalid inputs (sg id out of range or non-ACGT contig character)", hc[CT_S2_ERR]); return MCB_EINPUT; }

@@ -151,15 +151,17 @@ class ShardedFrontEnd:
         self.mask = None
 
     # ---- Stage 1: kt_for_reads + kt_for_bucket over the whole read set
-    def stage1(self, rows_local, n_total: int, device_resident: bool = False):
+    def stage1(self, rows_local, n_total: int, device_resident: bool = False, keep_mask: bool = False):
         """rows_local: this rank's reads, (n_local, L) uint8 (numpy, or a CUDA tensor when device_resident).
-        Returns (ReadsResult of the slice, Stage1Part of this rank)."""
+        Returns (ReadsResult of the slice, Stage1Part of this rank).  keep_mask: the ownership bitmap of an earlier call on the
+        same reads is still right (repeated runs of one job), do not rebuild it."""
         ctx = self.ctx
         lo, hi = rid_range(n_total, self.rank, self.world)
         ctx.shard_begin(n_total, lo)
         rr = ctx.for_reads_device(rows_local.data_ptr(), hi - lo) if device_resident else ctx.for_reads(rows_local)
         br, rounds = ctx.shard_for_bucket()
-        self.mask = owned_mask(n_total, br.sg)
+        if not (keep_mask and self.mask is not None):
+            self.mask = owned_mask(n_total, br.sg)
         return rr, Stage1Part(br.cl_n, br.cl_a, br.cl_ref, np.diff(br.cl_ref_off.astype(np.int64)).astype(np.uint64), br.sg, br.mi, br.mi_cnt, rounds)
 
     # ---- Stage 2: one threshold round of realign_hash
