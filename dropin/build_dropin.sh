@@ -35,6 +35,10 @@ pids=()
 for f in $KEPT; do g++ $CXXFLAGS -c "$REF/$f.c" -o "$B/$f.o" & pids+=($!); done
 g++ $CXXFLAGS -c "$HERE/mcb_dropin.cpp" -o "$B/mcb_dropin.o" & pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
+# kthread_cb.o stays linked (cmpcluster2/3, match_pro and construct_ref2 are used by the kept dump stage), but its combine_cluster
+# is renamed so that the shim's combine_cluster (the GPU contig merge) is the one preprocess.o calls; the reference's own host
+# merge remains reachable as mcb_ref_combine_cluster (MCB_HOST_MERGE=1, and the multi-GPU path).
+objcopy --redefine-sym _Z15combine_clusteriP7reads_tPi=_Z23mcb_ref_combine_clusteriP7reads_tPi "$B/kthread_cb.o"
 ALL=""; for f in $KEPT; do ALL="$ALL $B/$f.o"; done
 LIBDIR=$ROOT/minicom_b200
 g++ -O3 -fopenmp $ALL "$B/mcb_dropin.o" -L"$LIBDIR" -lminicom_b200 -Wl,-rpath,'$ORIGIN/../../minicom_b200' -o "$HERE/_build/minicom_b200_L${L}_${MODE}" -lm -lz -lpthread

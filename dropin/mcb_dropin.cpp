@@ -37,6 +37,7 @@ static mcb_ctx *g_ctx = 0;
 static mcb_group *g_grp = 0;    // MCB_DEVICES=0,1,...: the same calls over several GPUs (one context per device inside the library)
 static double g_wall[4];      // for_reads, for_bucket, idx_build, realign (host wall seconds inside the entry points)
 static int g_calls[4];
+static double g_wall_combine = 0;   // combine_cluster (the contig merge)
 static std::string g_realign_detail;
 
 // MCB_RECORD=<dir>: write the host-side inputs of every mm_idx_generation / realign_hash call as flat little-endian
@@ -79,9 +80,9 @@ struct McbAtExit {
 				dev += "}";
 				fprintf(f, "{\"n_reads\": %d, \"readlen\": %d, \"threads\": %d, \"kt_for_reads\": %.6f, \"kt_for_bucket\": %.6f, "
 				        "\"mm_idx_generation\": %.6f, \"n_idx\": %d, \"realign_hash\": %.6f, \"n_realign\": %d, \"realign_rounds\": [%s], "
-				        "\"kernel_launches\": %llu, \"device_ms\": %s}\n",
+				        "\"kernel_launches\": %llu, \"combine_cluster\": %.6f, \"device_ms\": %s}\n",
 				        reads ? reads->n_seq : 0, reads ? reads->seq_len : 0, n_threads, g_wall[0], g_wall[1], g_wall[2], g_calls[2], g_wall[3], g_calls[3],
-				        g_realign_detail.c_str(), g_ctx ? (unsigned long long)mcb_kernel_launches(g_ctx) : 0ull, dev.c_str());     // (group: rank 0's launches, per-timer maximum over the ranks)
+				        g_realign_detail.c_str(), g_ctx ? (unsigned long long)mcb_kernel_launches(g_ctx) : 0ull, g_wall_combine, dev.c_str());     // (group: rank 0's launches, per-timer maximum over the ranks)
 				fclose(f);
 			}
 		}
@@ -183,6 +184,48 @@ void kt_for_bucket(int n_threads_, reads_t *r, long n)
 			kv_push(mm128_t, *pp, v);
 		}
 	g_wall[1] += realtime() - t0; g_calls[1]++;
+}
+
+// ---- combine_cluster (kthread_cb.c:570): the contig merge, on the seed contigs kt_for_bucket left on the device.
+// The reference's own host merge is linked under another name (build_dropin.sh) and used when MCB_HOST_MERGE is set or when the
+// job runs on several GPUs (the merge needs the contigs and the packed reads of the whole job on one device).
+void mcb_ref_combine_cluster(int n_threads, reads_t *reads, int *index_);
+void combine_cluster(int n_threads_, reads_t *r, int *index_)
+{
+	if (getenv("MCB_HOST_MERGE") || g_grp) { mcb_ref_combine_cluster(n_threads_, r, index_); return; }
+	double t0 = realtime();
+	mcb_ctx *ctx = ctx_for(r);
+	mcb_combine_result res;
+	int rc = mcb_combine(ctx, cbthreshold, &res);
+	if (rc) die("combine_cluster", rc);
+	const int index = *index_;
+	// what the reference's loop leaves behind (:573-630): the seed contigs destroyed, the final set in clusters[idxv][0] with
+	// idxv flipped once per iteration, every mm_idx_t but the caller's first one gone
+	for (int t = 0; t < n_threads_; ++t) {
+		cluster_v *old = &r->clusters[index][t];
+		for (size_t i = 0; i < old->n; ++i) cluster_destroy(old->a[i]);
+		old->n = 0;
+	}
+	const int idxv = index ^ (res.iterations & 1);
+	for (int t = 0; t < n_threads_; ++t) { kv_init(r->clusters[idxv][t]); kv_resize(cluster_t, r->clusters[idxv][t], 1 << 10); }
+	if (idxv != index) for (int t = 0; t < n_threads_; ++t) { free(r->clusters[index][t].a); kv_init(r->clusters[index][t]); kv_resize(cluster_t, r->clusters[index][t], 1 << 10); }
+	cluster_v *cv = &r->clusters[idxv][0];
+	for (uint64_t c = 0; c < res.n_clusters; ++c) {
+		cluster_t *p;
+		kv_pushp(cluster_t, *cv, &p);
+		kv_init(*p);
+		size_t nm = res.cl_n[c], len = (size_t)(res.cl_ref_off[c + 1] - res.cl_ref_off[c]);
+		kv_resize(uint64_t, *p, nm);
+		memcpy(p->a, res.cl_a + res.cl_a_off[c], nm * sizeof(uint64_t));
+		p->n = nm;
+		p->ref = (char*)calloc(len + 1, 1);
+		memcpy(p->ref, res.cl_ref + res.cl_ref_off[c], len);
+		p->ennum = 0;                                           // written by construct_ref2, never read (kthread_cb.c:329 is commented out)
+	}
+	mm_idx_destroy(r->mi[index]);                              // the index objects the host loop would have gone through (:585,:628)
+	r->mi[index] = 0;
+	*index_ = idxv;
+	g_wall_combine += realtime() - t0;
 }
 
 // ---- minimizer index (kthread_idx.c:77-173).  mm_idx_t keeps the reference's layout; the device-built index hangs off B[0].h.

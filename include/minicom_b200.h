@@ -10,6 +10,8 @@
  *                                                                    mm_sketch_lh_ori sketch.c:116)
  *   mcb_idx_build       <- mm_idx_generation   kthread_idx.c:170    (worker_post :116, radix_sort_128x ksort.h:108)
  *   mcb_idx_get         <- mm_idx_get          kthread_idx.c:84
+ *   mcb_combine         <- combine_cluster     kthread_cb.c:570     (find_next :220, match_pro :36, construct_ref2 :105, cp_cluster :374;
+ *                                               the caller between kt_for_bucket and realign_hash: SURVEY.md 8f, N1)
  *   mcb_realign         <- realign_hash        kthread_hash_realign.c:569 (singleRead2bitset bbhashdict.c:127,
  *                                               constructdictionary_realign :3, realign_hash_search :316)
  *   mcb_sketch_lh_host  <- mm_sketch_lh_ori    sketch.c:116  (per-contig call made by the host contig merger,
@@ -166,6 +168,29 @@ void mcb_idx_stats(const mcb_index *idx, uint64_t *n_keys, uint64_t *n_post);
  * inside a bucket; kstart[n_keys+1] posting offsets; post[n_post] the y values, per key in the reference's order;
  * bucket_keys[2^b+1] first key of every bucket.  Any of the four pointers may be NULL. */
 void mcb_idx_arrays(const mcb_index *idx, const uint64_t **keys, const uint32_t **kstart, const uint64_t **post, const uint32_t **bucket_keys);
+
+/* ------------------------------------------------------------------ */
+/* combine_cluster (kthread_cb.c:570): the contig merge                 */
+/* ------------------------------------------------------------------ */
+typedef struct {
+	/* the contigs after the merge, in the order the single-threaded reference leaves them in reads->clusters[idxv][0]:
+	 * per iteration the merged contigs in the order of their first partner, then the untouched ones (kthread_cb.c:460-494) */
+	uint64_t n_clusters;
+	const uint32_t *cl_n;        /* [n_clusters] members per contig */
+	const uint64_t *cl_a_off;    /* [n_clusters+1] */
+	const uint64_t *cl_a;        /* members: rid<<32 | offset<<1 | dir; merged contigs sorted by (offset, dir) (construct_ref2, :107) */
+	const uint64_t *cl_ref_off;  /* [n_clusters+1] */
+	const char     *cl_ref;      /* consensus strings, concatenated, no terminators */
+	int32_t iterations;          /* iterations of the loop at :573-627 = mm_idx_generation calls made (idxv = iterations & 1) */
+	uint64_t n_merges;           /* pairs merged over all iterations */
+} mcb_combine_result;
+
+/* Runs on the seed contigs mcb_for_bucket left on the device (call it right after mcb_for_bucket, same context): per iteration
+ * the minimizer index of the contigs (device-resident, reference posting order), every contig's (w,k)-minimizers, the ordered
+ * lists of partners that pass the strand and match_pro <= cbthreshold tests, the first-come resolution in contig order, and the
+ * merged consensus strings.  cbthreshold: the reference's global (2 * diff_threshold unless -g, minicommain.c:122-126).
+ * The index lookups (mm_idx_get) and the sketches of kthread_cb.c happen on the device; nothing is uploaded. */
+int mcb_combine(mcb_ctx *ctx, int cbthreshold, mcb_combine_result *res);
 
 /* ------------------------------------------------------------------ */
 /* realign_hash (kthread_hash_realign.c:569)                            */

@@ -40,6 +40,11 @@ class _BucketResult(C.Structure):
                 ("n_grouped", C.c_uint64)]
 
 
+class _CombineResult(C.Structure):
+    _fields_ = [("n_clusters", C.c_uint64), ("cl_n", C.c_void_p), ("cl_a_off", C.c_void_p), ("cl_a", C.c_void_p), ("cl_ref_off", C.c_void_p),
+                ("cl_ref", C.c_void_p), ("iterations", C.c_int32), ("n_merges", C.c_uint64)]
+
+
 class _RealignResult(C.Structure):
     _fields_ = [("n_claims", C.c_uint64), ("claim_contig", C.c_void_p), ("claim_sg", C.c_void_p), ("claim_y", C.c_void_p),
                 ("claim_prio", C.c_void_p), ("n_fpA", C.c_uint64), ("n_fpT", C.c_uint64), ("fpA_sg", C.c_void_p), ("fpT_sg", C.c_void_p),
@@ -52,7 +57,7 @@ EXPORTS = [
     "mcb_for_reads", "mcb_for_reads_ptrs", "mcb_for_reads_device",
     "mcb_debug_read_tuples", "mcb_debug_sketch_two", "mcb_debug_unpack_reads",
     "mcb_for_bucket", "mcb_idx_build", "mcb_idx_build_scattered", "mcb_idx_get", "mcb_idx_destroy", "mcb_idx_stats", "mcb_idx_arrays",
-    "mcb_realign", "mcb_sketch_lh_host", "mcb_sketch_two_host", "mcb_hash64",
+    "mcb_combine", "mcb_realign", "mcb_sketch_lh_host", "mcb_sketch_two_host", "mcb_hash64",
     "mcb_timers_enable", "mcb_timers_reset", "mcb_timer_get", "mcb_timers_dump", "mcb_kernel_launches",
     "mcb_round_control_init", "mcb_round_control_begin", "mcb_round_control_end",
     "mcb_group_create", "mcb_group_destroy", "mcb_group_size", "mcb_group_context", "mcb_group_for_reads_ptrs", "mcb_group_for_bucket",
@@ -101,6 +106,7 @@ def load_library() -> C.CDLL:
     lib.mcb_idx_stats.restype = None
     lib.mcb_idx_arrays.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4
     lib.mcb_idx_arrays.restype = None
+    lib.mcb_combine.argtypes = [C.c_void_p, C.c_int, C.POINTER(_CombineResult)]
     lib.mcb_realign.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                 C.c_int, C.c_int, C.c_int, C.POINTER(_RealignResult)]
     lib.mcb_sketch_lh_host.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int64]
@@ -199,6 +205,17 @@ class BucketResult:
     rounds: int
     n_sketched_total: int
     n_grouped: int
+
+
+@dataclass
+class CombineResult:
+    cl_n: np.ndarray
+    cl_a_off: np.ndarray
+    cl_a: np.ndarray
+    cl_ref_off: np.ndarray
+    cl_ref: np.ndarray
+    iterations: int
+    n_merges: int
 
 
 @dataclass
@@ -326,6 +343,16 @@ class Context:
                             _view(r.cl_ref, int(r_off[-1]) if nc else 0, np.uint8), _view(r.sg, r.n_sg, np.uint32),
                             _view(r.mi_cnt, nc, np.uint8), _view(r.mi, nc * m * 2, np.uint64).reshape(nc, m, 2),
                             int(r.rounds), int(r.n_sketched_total), int(r.n_grouped))
+
+    # -- combine_cluster (the contig merge, on the seed contigs mcb_for_bucket left on the device)
+    def combine(self, cbthreshold: int) -> CombineResult:
+        r = _CombineResult()
+        self._check(self.lib.mcb_combine(self._h, cbthreshold, C.byref(r)))
+        nc = r.n_clusters
+        a_off = _view(r.cl_a_off, nc + 1, np.uint64)
+        r_off = _view(r.cl_ref_off, nc + 1, np.uint64)
+        return CombineResult(_view(r.cl_n, nc, np.uint32), a_off, _view(r.cl_a, int(a_off[-1]) if nc else 0, np.uint64), r_off,
+                             _view(r.cl_ref, int(r_off[-1]) if nc else 0, np.uint8), int(r.iterations), int(r.n_merges))
 
     # -- mm_idx_generation
     def idx_build(self, tuples: np.ndarray, bucket_off: np.ndarray) -> Index:

@@ -67,6 +67,7 @@ extern "C" int mcb_create(const mcb_params *p, mcb_ctx **out)
 }
 
 void mcb_shard_release(mcb_ctx *ctx);      // mcb_shard.cu
+void mcb_combine_release(mcb_ctx *ctx);    // mcb_combine.cu
 
 extern "C" void mcb_destroy(mcb_ctx *ctx)
 {
@@ -74,6 +75,7 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 	cudaSetDevice(ctx->prm.device);
 	cudaStreamSynchronize(ctx->stream);
 	mcb_shard_release(ctx);
+	mcb_combine_release(ctx);
 	ctx->tm.collect();
 	for (auto e : ctx->tm.pool) cudaEventDestroy(e);
 	DBuf *db[] = { &ctx->d_ascii, &ctx->d_packed, &ctx->d_cls, &ctx->d_elemA, &ctx->d_elemB, &ctx->d_counters, &ctx->d_nread_rid, &ctx->d_nread_mask, &ctx->d_sort_hist,

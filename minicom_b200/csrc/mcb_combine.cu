@@ -1,0 +1,505 @@
+// mcb_combine.cu — combine_cluster (kthread_cb.c:570-630) on the device: the contig merge that sits between kt_for_bucket and
+// realign_hash.  SURVEY.md 8(f) N1.
+//
+// The reference walks the contigs in order; contig i sketches its consensus (all (w,k)-minimizers, kthread_cb.c:234), looks every
+// minimizer up in the index of the first-m minimizers of all contigs (:269), and merges with the FIRST posting whose contig is
+// still unmerged, lies on the same strand and whose consensus differs from i's in at most cbthreshold characters over their
+// overlap (match_pro, :36-53, :289-290).  Both contigs are then flagged; merged contigs come first in the new set, the untouched
+// ones are copied behind them (:474-494); the loop ends when the number of contigs changes by less than 100 (:625).
+//
+// Everything but the flags is independent of the order of processing: which postings contig i meets, in which order, and which
+// of them pass the strand and match_pro tests.  So one iteration is
+//   1  index of the current first-m tuples, built on the device (mcb_index_build_device: the reference's posting order)
+//   2  all minimizers of every contig                   k_sketch_lh2 in its ALL mode, count + emit
+//   3  (minimizer, posting) pairs in the reference's visiting order, strand / self test, match_pro on 2-bit packed contigs
+//      -> per contig the ordered list of acceptable partners                      k_cb_lookup, k_cb_pairs, k_cb_match
+//   4  the sequential part, which is tiny: walk the contigs in order, take the first partner that is still free
+//      (= greedy matching by edge priority (i, position in i's list))             host loop over the compacted lists
+//   5  the new contig set: member lists concatenated with the offset shift (:300-317) and stably sorted by (position, strand)
+//      (construct_ref2's qsort, :107), consensus by column majority over the oriented reads (:120-150), untouched contigs
+//      copied, first-m minimizers of every new contig                             k_cb_members, radix sort, k_cb_consensus, k_sketch_lh2
+// The contig set, the packed reads and the index never leave the device; the host sees two small lists per iteration.
+#include "mcb_common.cuh"
+#include "mcb_lh.cuh"
+#include <algorithm>
+#include <limits.h>
+
+struct CbSet {                       // one contig set on the device
+	DBuf n, aoff, a, roff, ref, mi, micnt;
+	uint64_t ncl = 0, nmem = 0, nref = 0;
+	void release() { n.release(); aoff.release(); a.release(); roff.release(); ref.release(); mi.release(); micnt.release(); }
+};
+struct McbCombineState {
+	CbSet set[2];
+	DBuf tup, tup2, boff, moff, mins, pcnt, cand, pass, plist, loff, cw, cwo, flag, pairs, src, keyA, keyB, len2, tmp32;
+	HBuf h_boff, h_list, h_loff, h_pairs, h_flag, h_small;
+	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref;
+	void release()
+	{
+		set[0].release(); set[1].release();
+		DBuf *d[] = { &tup, &tup2, &boff, &moff, &mins, &pcnt, &cand, &pass, &plist, &loff, &cw, &cwo, &flag, &pairs, &src, &keyA, &keyB, &len2, &tmp32 };
+		for (auto b : d) b->release();
+		HBuf *h[] = { &h_boff, &h_list, &h_loff, &h_pairs, &h_flag, &h_small, &h_cl_n, &h_cl_a_off, &h_cl_a, &h_cl_ref_off, &h_cl_ref };
+		for (auto b : h) b->release();
+	}
+};
+void mcb_combine_release(mcb_ctx *ctx) { if (ctx->cb) { ctx->cb->release(); delete ctx->cb; ctx->cb = nullptr; } }
+
+// ---------------------------------------------------------------- 1: tuples of the current set, in push order
+__global__ void k_cb_widen_u8(const uint8_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = in[i];
+}
+__global__ void k_cb_gather_tuples(const mcb_tuple *__restrict__ mi, const uint8_t *__restrict__ micnt, const uint32_t *__restrict__ off, uint64_t ncl, int m, ulonglong2 *__restrict__ out)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= ncl * (uint64_t)m) return;
+	const uint64_t c = i / m; const int j = (int)(i - c * m);
+	if (j < micnt[c]) { const mcb_tuple t = mi[i]; out[off[c] + j] = make_ulonglong2(t.x, t.y); }
+}
+__global__ void k_cb_bucket_bounds(const ulonglong2 *__restrict__ t, uint64_t n, int nb, uint64_t *__restrict__ boff)
+{
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b > nb) return;
+	uint64_t lo = 0, hi = n;                  // first tuple whose bucket is >= b
+	while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((int)(t[mid].x & (uint64_t)(nb - 1)) < b) lo = mid + 1; else hi = mid; }
+	boff[b] = lo;
+}
+
+// ---------------------------------------------------------------- 3: contigs packed 2 bits per base (as in Stage 2), lookups, match_pro
+__global__ void k_cb_word_offsets(const uint64_t *__restrict__ roff, uint64_t ncl, uint64_t *__restrict__ wcnt)
+{
+	const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < ncl) wcnt[c] = (roff[c + 1] - roff[c] + 31) / 32 + 1;
+}
+__global__ void k_cb_pack(const char *__restrict__ ref, const uint64_t *__restrict__ roff, const uint64_t *__restrict__ cwo, uint64_t ncl, uint64_t total_words, uint64_t *__restrict__ cw)
+{
+	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= total_words) return;
+	uint64_t lo = 0, hi = ncl;                // last c with cwo[c] <= q
+	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (cwo[mid] <= q) lo = mid; else hi = mid; }
+	const uint64_t c = lo, wq = q - cwo[c], b = roff[c], len = roff[c + 1] - b;
+	uint64_t v = 0;
+	for (int j = 0; j < 32; ++j) {
+		const uint64_t p = wq * 32 + j;
+		if (p < len) v |= (uint64_t)(mcb_code_of((unsigned char)ref[b + p]) & 3u) << (2 * j);
+	}
+	cw[q] = v;
+}
+// postings of one minimizer in the device index (mm_idx_get, kthread_idx.c:84-101)
+__device__ __forceinline__ uint32_t cb_lookup(const McbDeviceIndex &ix, uint64_t x, uint32_t *first)
+{
+	const uint32_t bk = (uint32_t)(x & ((1ull << ix.b) - 1));
+	uint32_t lo = ix.ub[bk], hi = ix.ub[bk + 1];
+	while (lo < hi) {
+		const uint32_t mid = lo + ((hi - lo) >> 1);
+		const uint64_t kx = ix.keys[mid];
+		if (kx < x) lo = mid + 1; else if (kx > x) hi = mid; else { *first = ix.kstart[mid]; return ix.kstart[mid + 1] - ix.kstart[mid]; }
+	}
+	*first = 0;
+	return 0;
+}
+__global__ void k_cb_lookup(const mcb_tuple *__restrict__ mins, uint64_t M, McbDeviceIndex ix, uint32_t *__restrict__ pcnt, uint32_t *__restrict__ pfirst)
+{
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= M) return;
+	uint32_t first;
+	pcnt[t] = cb_lookup(ix, mins[t].x, &first);
+	pfirst[t] = first;
+}
+// one record per (minimizer of contig i, posting): the partner contig and the two anchor positions; partner = ~0 when the posting
+// is contig i itself or lies on the other strand (kthread_cb.c:276-289)
+struct CbCand { uint32_t i, c, pos_ori, pos; };
+__global__ void k_cb_pairs(const mcb_tuple *__restrict__ mins, uint64_t M, McbDeviceIndex ix, const uint32_t *__restrict__ poff, const uint32_t *__restrict__ pfirst,
+                           const uint32_t *__restrict__ pcnt, CbCand *__restrict__ cand)
+{
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= M) return;
+	const mcb_tuple mn = mins[t];
+	const uint32_t rid_ori = (uint32_t)(mn.y >> 32), pos_ori = (uint32_t)mn.y >> 1, dir_ori = (uint32_t)mn.y & 1u;
+	const uint32_t n = pcnt[t], f = pfirst[t], o = poff[t];
+	for (uint32_t q = 0; q < n; ++q) {
+		const uint64_t y = ix.post[f + q];
+		const uint32_t rid = (uint32_t)(y >> 32);
+		CbCand r; r.i = rid_ori >> 8; r.pos_ori = pos_ori; r.pos = (uint32_t)y >> 1;
+		r.c = (rid != rid_ori && ((uint32_t)y & 1u) == dir_ori) ? rid >> 8 : 0xFFFFFFFFu;
+		cand[o + q] = r;
+	}
+}
+// match_pro (kthread_cb.c:36-53): mismatching characters over the overlap of the two consensus strings aligned at (pos_ori, pos)
+__device__ __forceinline__ uint64_t cb_bases32(const uint64_t *__restrict__ w, int64_t base)       // 32 bases starting at `base` >= 0 (guard word behind every contig)
+{
+	const int64_t wi = base >> 5; const int sh = 2 * (int)(base & 31);
+	const uint64_t a = w[wi];
+	return sh ? (a >> sh) | (w[wi + 1] << (64 - sh)) : a;
+}
+__global__ void k_cb_match(const CbCand *__restrict__ cand, uint64_t n, const uint64_t *__restrict__ cw, const uint64_t *__restrict__ cwo, const uint64_t *__restrict__ roff,
+                           int cbthr, uint32_t *__restrict__ pass)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n) return;
+	const CbCand r = cand[e];
+	uint32_t ok = 0;
+	if (r.c != 0xFFFFFFFFu) {
+		const int64_t li = (int64_t)(roff[r.i + 1] - roff[r.i]), lc = (int64_t)(roff[r.c + 1] - roff[r.c]);
+		const int64_t d = (int64_t)r.pos_ori - (int64_t)r.pos;                 // column x of contig i meets column x - d of contig c
+		const int64_t lo = d > 0 ? d : 0, hi = li < lc + d ? li : lc + d;
+		const uint64_t *wi = cw + cwo[r.i], *wc = cw + cwo[r.c];
+		int mism = 0;
+		for (int64_t x = lo; x < hi && mism <= cbthr; x += 32) {
+			uint64_t v = cb_bases32(wi, x) ^ cb_bases32(wc, x - d);
+			v = (v | (v >> 1)) & 0x5555555555555555ull;
+			if (hi - x < 32) v &= (1ull << (2 * (hi - x))) - 1;
+			mism += __popcll(v);
+		}
+		ok = mism <= cbthr;
+	}
+	pass[e] = ok;
+}
+__global__ void k_cb_compact(const CbCand *__restrict__ cand, const uint32_t *__restrict__ pass_scan, const uint32_t *__restrict__ passed, uint64_t n, CbCand *__restrict__ out)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < n && passed[e]) out[pass_scan[e]] = cand[e];
+}
+__global__ void k_cb_list_bounds(const CbCand *__restrict__ list, uint64_t P, uint64_t ncl, uint32_t *__restrict__ loff)
+{
+	const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c > ncl) return;
+	uint64_t lo = 0, hi = P;                  // first entry whose contig is >= c
+	while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (list[mid].i < c) lo = mid + 1; else hi = mid; }
+	loff[c] = (uint32_t)lo;
+}
+
+// ---------------------------------------------------------------- 5: the new contig set
+// new contig q < nm is the merge pairs[q] = (i, c, pos_ori, pos); q >= nm is the copy of old contig src[q - nm]
+__global__ void k_cb_new_sizes(const CbCand *__restrict__ pairs, uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint32_t *__restrict__ cl_n, uint32_t *__restrict__ n_new)
+{
+	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= n2) return;
+	n_new[q] = q < nm ? cl_n[pairs[q].i] + cl_n[pairs[q].c] : cl_n[src[q - nm]];
+}
+__global__ void k_cb_prefix64(const uint32_t *__restrict__ scan32, uint64_t n, uint64_t *__restrict__ out, const unsigned long long *__restrict__ total)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = scan32[i];
+	if (i == n) out[n] = *total;
+}
+// one warp per new contig: members of the first contig as they are, those of the second shifted by the anchor difference
+// (kthread_cb.c:300-317); merged contigs also get the sort key (new contig, position, strand) of every member
+__global__ void k_cb_members(const CbCand *__restrict__ pairs, uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ aoff, const uint64_t *__restrict__ a,
+                             const uint64_t *__restrict__ aoff2, uint64_t *__restrict__ a2, ulonglong2 *__restrict__ keyed)
+{
+	const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (q >= n2) return;
+	const uint64_t o = aoff2[q];
+	if (q >= nm) {
+		const uint32_t s = src[q - nm];
+		const uint64_t b = aoff[s], cnt = aoff[s + 1] - b;
+		for (uint64_t u = lane; u < cnt; u += 32) a2[o + u] = a[b + u];
+		return;
+	}
+	const CbCand p = pairs[q];
+	const bool i_first = p.pos_ori >= p.pos;
+	const uint32_t first = i_first ? p.i : p.c, second = i_first ? p.c : p.i;
+	const uint64_t shift = i_first ? p.pos_ori - p.pos : p.pos - p.pos_ori;
+	const uint64_t b1 = aoff[first], n1 = aoff[first + 1] - b1, b2 = aoff[second], n2m = aoff[second + 1] - b2;
+	for (uint64_t u = lane; u < n1 + n2m; u += 32) {
+		uint64_t y;
+		if (u < n1) y = a[b1 + u];
+		else { const uint64_t v = a[b2 + u - n1]; y = (v >> 32 << 32) | ((((uint64_t)((uint32_t)v >> 1)) + shift) << 1) | (v & 1); }
+		keyed[o + u] = make_ulonglong2((q << 32) | (uint64_t)(uint32_t)y, y);          // (new contig, position << 1 | strand)
+	}
+}
+__global__ void k_cb_unkey(const ulonglong2 *__restrict__ keyed, uint64_t n, uint64_t *__restrict__ a2)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) a2[i] = keyed[i].y;
+}
+// consensus lengths: a merged contig ends with its right-most member (members sorted by position), a copy keeps its length
+__global__ void k_cb_new_lengths(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ aoff2, const uint64_t *__restrict__ a2,
+                                 const uint64_t *__restrict__ roff, int L, uint64_t *__restrict__ len2)
+{
+	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= n2) return;
+	if (q < nm) len2[q] = (uint64_t)((uint32_t)a2[aoff2[q + 1] - 1] >> 1) + (uint64_t)L;
+	else { const uint32_t s = src[q - nm]; len2[q] = roff[s + 1] - roff[s]; }
+}
+// construct_ref2 (kthread_cb.c:105-150): one thread per column of a merged contig counts the bases the oriented members put there;
+// 'A' unless a base has strictly more votes, in the order A, C, G, T.  Members are sorted by position, so the ones covering a
+// column are a contiguous run found by binary search.
+__global__ void k_cb_consensus(uint64_t nm, const uint64_t *__restrict__ roff2, const uint64_t *__restrict__ aoff2, const uint64_t *__restrict__ a2,
+                               const uint64_t *__restrict__ packed, int WS, int L, uint64_t total_cols, char *__restrict__ ref2)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= total_cols) return;
+	uint64_t lo = 0, hi = nm;                 // last q with roff2[q] <= g
+	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (roff2[mid] <= g) lo = mid; else hi = mid; }
+	const uint64_t q = lo;
+	const int64_t col = (int64_t)(g - roff2[q]);
+	const uint64_t mb = aoff2[q], me = aoff2[q + 1];
+	uint64_t s = mb, e = me;                  // first member with position > col - L
+	while (s < e) { const uint64_t mid = (s + e) >> 1; if ((int64_t)((uint32_t)a2[mid] >> 1) <= col - L) s = mid + 1; else e = mid; }
+	unsigned cnt[4] = { 0, 0, 0, 0 };
+	for (uint64_t u = s; u < me; ++u) {
+		const uint64_t y = a2[u];
+		const int64_t pos = (int64_t)((uint32_t)y >> 1);
+		if (pos > col) break;
+		const int p = (int)(col - pos);
+		const uint64_t *row = packed + (y >> 32) * (uint64_t)WS;
+		const unsigned bse = (y & 1) ? 3u - mcb_base_at(row, L - 1 - p) : mcb_base_at(row, p);
+		++cnt[bse];
+	}
+	unsigned best = 0, mx = cnt[0];
+	if (cnt[1] > mx) { mx = cnt[1]; best = 1; }
+	if (cnt[2] > mx) { mx = cnt[2]; best = 2; }
+	if (cnt[3] > mx) { mx = cnt[3]; best = 3; }
+	ref2[g] = "ACGT"[best];
+}
+__global__ void k_cb_copy_refs(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ roff, const char *__restrict__ ref,
+                               const uint64_t *__restrict__ roff2, char *__restrict__ ref2)
+{
+	const uint64_t q = nm + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
+	if (q >= n2) return;
+	const uint32_t s = src[q - nm];
+	const uint64_t b = roff[s], len = roff[s + 1] - b, o = roff2[q];
+	for (uint64_t u = lane; u < len; u += 32) ref2[o + u] = ref[b + u];
+}
+
+// ================================================================= host
+static int cb_counter(mcb_ctx *ctx, int slot, uint64_t *out)          // one device scalar to the host (synchronizes)
+{
+	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	*out = ctx->h_counters.as<unsigned long long>()[slot];
+	return MCB_OK;
+}
+enum { CT_CB_A = 48, CT_CB_B = 49, CT_CB_C = 50, CT_CB_D = 51 };          // scratch slots of ctx->d_counters (32..41 are the consensus work lists)
+
+// first-m minimizers of every contig of a set (kthread_cb.c:365,:418; kthread_bucket.c:458 for the seeds)
+static int cb_first_m(mcb_ctx *ctx, CbSet &S)
+{
+	const int rw = ctx->prm.rw, k = ctx->prm.k, m = ctx->prm.first_mininum;
+	MCB_TRY(S.mi.ensure(S.ncl * m * 16 + 16)); MCB_TRY(S.micnt.ensure(S.ncl + 16));
+	if (!S.ncl) return MCB_OK;
+	const size_t smem = (size_t)rw * LH_THREADS * 13;
+	auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
+	if (smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	MCB_LAUNCH(ctx, "sketch_lh", kern, mcb_grid_for(S.ncl, LH_THREADS), LH_THREADS, smem, S.ref.as<char>(), S.roff.as<uint64_t>(), (uint64_t)0, S.ncl, (uint64_t)0,
+	           rw, k, m, S.mi.as<mcb_tuple>(), S.micnt.as<uint8_t>(), (const uint64_t*)nullptr, (uint32_t*)nullptr);
+	return MCB_OK;
+}
+
+static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSet &nxt, int cbthr, uint64_t *n_merged)
+{
+	const int L = ctx->L, WS = ctx->WS, m = ctx->prm.first_mininum, nb = 1 << ctx->prm.b, rw = ctx->prm.rw, k = ctx->prm.k;
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	const uint64_t ncl = cur.ncl;
+	*n_merged = 0;
+	// ---- 1: index of the first-m tuples (mm_idx_generation, kthread_cb.c:574)
+	uint64_t T = 0;
+	McbDeviceIndex ix;
+	{
+		McbSpan sp(ctx->tm, "combine");
+		MCB_TRY(cb.tmp32.ensure((ncl + 2) * 4));
+		MCB_LAUNCH(ctx, "cb_widen", k_cb_widen_u8, mcb_grid_for(ncl, 256), 256, 0, cur.micnt.as<uint8_t>(), ncl, cb.tmp32.as<uint32_t>());
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, cb.tmp32.as<uint32_t>(), ncl, (uint64_t*)&dc[CT_CB_A]));
+		MCB_TRY(cb_counter(ctx, CT_CB_A, &T));
+		MCB_TRY(cb.tup.ensure(T * 16 + 16)); MCB_TRY(cb.tup2.ensure(T * 16 + 16)); MCB_TRY(cb.boff.ensure(((size_t)nb + 2) * 8)); MCB_TRY(cb.h_boff.ensure(((size_t)nb + 2) * 8));
+		MCB_LAUNCH(ctx, "cb_gather_tuples", k_cb_gather_tuples, mcb_grid_for(ncl * m, 256), 256, 0, cur.mi.as<mcb_tuple>(), cur.micnt.as<uint8_t>(), cb.tmp32.as<uint32_t>(), ncl, m, cb.tup.as<ulonglong2>());
+		McbSortPass bp[2] = { {0, 0, 7}, {0, 7, 7} };        // stable by bucket: inside a bucket the tuples keep their push order
+		ulonglong2 *sorted = nullptr;
+		MCB_TRY(mcb_radix_sort(ctx, cb.tup.as<ulonglong2>(), cb.tup2.as<ulonglong2>(), T, bp, 2, &sorted));
+		if (sorted != cb.tup.as<ulonglong2>()) std::swap(cb.tup, cb.tup2);
+		MCB_LAUNCH(ctx, "cb_bucket_bounds", k_cb_bucket_bounds, (nb + 1 + 255) / 256, 256, 0, cb.tup.as<ulonglong2>(), T, nb, cb.boff.as<uint64_t>());
+		MCB_CUDA(cudaMemcpyAsync(cb.h_boff.p, cb.boff.p, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	MCB_TRY(mcb_index_build_device(ctx, cb.tup.as<mcb_tuple>(), T, cb.boff.as<uint64_t>(), cb.h_boff.as<uint64_t>(), &ix));
+	McbSpan sp(ctx->tm, "combine");
+	// ---- 2: all minimizers of every contig (kthread_cb.c:234), count then emit
+	uint64_t M = 0;
+	{
+		const size_t smem = (size_t)rw * LH_THREADS * 13;
+		auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
+		if (smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		MCB_TRY(cb.moff.ensure((ncl + 2) * 8));
+		MCB_LAUNCH(ctx, "cb_sketch_count", kern, mcb_grid_for(ncl, LH_THREADS), LH_THREADS, smem, cur.ref.as<char>(), cur.roff.as<uint64_t>(), (uint64_t)0, ncl, (uint64_t)0,
+		           rw, k, INT_MAX, (mcb_tuple*)nullptr, (uint8_t*)nullptr, (const uint64_t*)nullptr, cb.tmp32.as<uint32_t>());
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, cb.tmp32.as<uint32_t>(), ncl, (uint64_t*)&dc[CT_CB_A]));
+		MCB_LAUNCH(ctx, "cb_prefix64", k_cb_prefix64, mcb_grid_for(ncl + 1, 256), 256, 0, cb.tmp32.as<uint32_t>(), ncl, cb.moff.as<uint64_t>(), &dc[CT_CB_A]);
+		MCB_TRY(cb_counter(ctx, CT_CB_A, &M));
+		if (M >= 0xFFFFFFFFull) { mcb_set_error("mcb_combine: too many contig minimizers"); return MCB_EINVAL; }
+		MCB_TRY(cb.mins.ensure(M * 16 + 16));
+		MCB_LAUNCH(ctx, "cb_sketch_all", kern, mcb_grid_for(ncl, LH_THREADS), LH_THREADS, smem, cur.ref.as<char>(), cur.roff.as<uint64_t>(), (uint64_t)0, ncl, (uint64_t)0,
+		           rw, k, INT_MAX, cb.mins.as<mcb_tuple>(), (uint8_t*)nullptr, cb.moff.as<uint64_t>(), cb.tmp32.as<uint32_t>());
+	}
+	// ---- 3: packed contigs, (minimizer, posting) pairs in visiting order, match_pro
+	uint64_t total_words = 0, C = 0, P = 0;
+	{
+		MCB_TRY(cb.cwo.ensure((ncl + 2) * 8));
+		MCB_LAUNCH(ctx, "cb_word_offsets", k_cb_word_offsets, mcb_grid_for(ncl, 256), 256, 0, cur.roff.as<uint64_t>(), ncl, cb.cwo.as<uint64_t>());
+		MCB_TRY(mcb_exclusive_scan_u64(ctx, cb.cwo.as<uint64_t>(), ncl, (uint64_t*)&dc[CT_CB_B]));
+		MCB_TRY(cb.pcnt.ensure((M + 2) * 12));
+		uint32_t *pcnt = cb.pcnt.as<uint32_t>(), *pfirst = pcnt + (M + 1), *poff = pfirst + (M + 1);
+		if (M) MCB_LAUNCH(ctx, "cb_lookup", k_cb_lookup, mcb_grid_for(M, 256), 256, 0, cb.mins.as<mcb_tuple>(), M, ix, pcnt, pfirst);
+		MCB_CUDA(cudaMemcpyAsync(poff, pcnt, M * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, poff, M, (uint64_t*)&dc[CT_CB_C]));
+		MCB_TRY(cb_counter(ctx, CT_CB_C, &C));
+		total_words = ctx->h_counters.as<unsigned long long>()[CT_CB_B];
+		if (C >= 0xFFFFFFFFull) { mcb_set_error("mcb_combine: too many (minimizer, posting) pairs"); return MCB_EINVAL; }
+		MCB_TRY(cb.cw.ensure((total_words + 2) * 8));
+		MCB_CUDA(cudaMemsetAsync(cb.cw.as<uint64_t>() + total_words, 0, 16, ctx->stream));
+		if (total_words) MCB_LAUNCH(ctx, "cb_pack", k_cb_pack, mcb_grid_for(total_words, 256), 256, 0, cur.ref.as<char>(), cur.roff.as<uint64_t>(), cb.cwo.as<uint64_t>(), ncl, total_words, cb.cw.as<uint64_t>());
+		MCB_TRY(cb.cand.ensure(C * 16 + 16)); MCB_TRY(cb.pass.ensure((C + 2) * 8));
+		uint32_t *passed = cb.pass.as<uint32_t>(), *pscan = passed + (C + 1);
+		if (M) MCB_LAUNCH(ctx, "cb_pairs", k_cb_pairs, mcb_grid_for(M, 256), 256, 0, cb.mins.as<mcb_tuple>(), M, ix, poff, pfirst, pcnt, cb.cand.as<CbCand>());
+		if (C) MCB_LAUNCH(ctx, "cb_match", k_cb_match, mcb_grid_for(C, 256), 256, 0, cb.cand.as<CbCand>(), C, cb.cw.as<uint64_t>(), cb.cwo.as<uint64_t>(), cur.roff.as<uint64_t>(), cbthr, passed);
+		MCB_CUDA(cudaMemcpyAsync(pscan, passed, C * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, pscan, C, (uint64_t*)&dc[CT_CB_D]));
+		MCB_TRY(cb_counter(ctx, CT_CB_D, &P));
+		MCB_TRY(cb.plist.ensure(P * 16 + 16)); MCB_TRY(cb.loff.ensure((ncl + 2) * 4));
+		if (C) MCB_LAUNCH(ctx, "cb_compact", k_cb_compact, mcb_grid_for(C, 256), 256, 0, cb.cand.as<CbCand>(), pscan, passed, C, cb.plist.as<CbCand>());
+		MCB_LAUNCH(ctx, "cb_list_bounds", k_cb_list_bounds, mcb_grid_for(ncl + 1, 256), 256, 0, cb.plist.as<CbCand>(), P, ncl, cb.loff.as<uint32_t>());
+	}
+	// ---- 4: the sequential part (kthread_cb.c:460-466 with one thread): contigs in order, first partner that is still free
+	MCB_TRY(cb.h_list.ensure(P * 16 + 16)); MCB_TRY(cb.h_loff.ensure((ncl + 2) * 4)); MCB_TRY(cb.h_pairs.ensure((ncl / 2 + 2) * 16)); MCB_TRY(cb.h_flag.ensure((ncl + 2) * 4));
+	if (P) MCB_CUDA(cudaMemcpyAsync(cb.h_list.p, cb.plist.p, P * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaMemcpyAsync(cb.h_loff.p, cb.loff.p, (ncl + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	uint64_t nm = 0, n_copy = 0;
+	{
+		const CbCand *list = cb.h_list.as<CbCand>();
+		const uint32_t *loff = cb.h_loff.as<uint32_t>();
+		CbCand *pairs = cb.h_pairs.as<CbCand>();
+		std::vector<uint8_t> flag(ncl + 1, 0);
+		for (uint64_t i = 0; i < ncl; ++i) {
+			if (flag[i]) continue;
+			for (uint32_t e = loff[i]; e < loff[i + 1]; ++e)
+				if (!flag[list[e].c]) { flag[i] = flag[list[e].c] = 1; pairs[nm++] = list[e]; break; }
+		}
+		uint32_t *src = cb.h_flag.as<uint32_t>();               // the untouched contigs, in order
+		for (uint64_t i = 0; i < ncl; ++i) if (!flag[i]) src[n_copy++] = (uint32_t)i;
+	}
+	*n_merged = nm;
+	const uint64_t n2 = nm + n_copy;
+	// ---- 5: the new set
+	MCB_TRY(cb.pairs.ensure(nm * 16 + 16)); MCB_TRY(cb.src.ensure(n_copy * 4 + 16));
+	if (nm) MCB_CUDA(cudaMemcpyAsync(cb.pairs.p, cb.h_pairs.p, nm * 16, cudaMemcpyHostToDevice, ctx->stream));
+	if (n_copy) MCB_CUDA(cudaMemcpyAsync(cb.src.p, cb.h_flag.p, n_copy * 4, cudaMemcpyHostToDevice, ctx->stream));
+	nxt.ncl = n2; nxt.nmem = cur.nmem;
+	MCB_TRY(nxt.n.ensure((n2 + 2) * 4)); MCB_TRY(nxt.aoff.ensure((n2 + 2) * 8)); MCB_TRY(nxt.a.ensure(cur.nmem * 8 + 16)); MCB_TRY(nxt.roff.ensure((n2 + 2) * 8));
+	MCB_TRY(cb.tmp32.ensure((n2 + 2) * 4)); MCB_TRY(cb.len2.ensure((n2 + 2) * 8));
+	if (!n2) { nxt.nref = 0; return MCB_OK; }
+	MCB_LAUNCH(ctx, "cb_new_sizes", k_cb_new_sizes, mcb_grid_for(n2, 256), 256, 0, cb.pairs.as<CbCand>(), nm, cb.src.as<uint32_t>(), n2, cur.n.as<uint32_t>(), nxt.n.as<uint32_t>());
+	MCB_CUDA(cudaMemcpyAsync(cb.tmp32.p, nxt.n.p, n2 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, cb.tmp32.as<uint32_t>(), n2, (uint64_t*)&dc[CT_CB_A]));
+	MCB_LAUNCH(ctx, "cb_prefix64", k_cb_prefix64, mcb_grid_for(n2 + 1, 256), 256, 0, cb.tmp32.as<uint32_t>(), n2, nxt.aoff.as<uint64_t>(), &dc[CT_CB_A]);
+	// members of the merged contigs go through a stable sort on (new contig, position, strand); the copies are final at once
+	uint64_t n_mm = 0;                                           // members of merged contigs = aoff2[nm]
+	if (nm) {
+		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, nxt.aoff.as<uint64_t>() + nm, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		n_mm = ctx->h_counters.as<unsigned long long>()[0];
+	}
+	MCB_TRY(cb.keyA.ensure(n_mm * 16 + 16)); MCB_TRY(cb.keyB.ensure(n_mm * 16 + 16));
+	MCB_LAUNCH(ctx, "cb_members", k_cb_members, mcb_grid_for(n2 * 32, 256), 256, 0, cb.pairs.as<CbCand>(), nm, cb.src.as<uint32_t>(), n2, cur.aoff.as<uint64_t>(), cur.a.as<uint64_t>(),
+	           nxt.aoff.as<uint64_t>(), nxt.a.as<uint64_t>(), cb.keyA.as<ulonglong2>());
+	if (n_mm) {
+		std::vector<McbSortPass> passes;
+		mcb_add_bit_passes(passes, 0, 0, 32);                    // position << 1 | strand
+		mcb_add_bit_passes(passes, 0, 32, 32 + mcb_bits_for(nm));
+		ulonglong2 *sorted = nullptr;
+		MCB_TRY(mcb_radix_sort(ctx, cb.keyA.as<ulonglong2>(), cb.keyB.as<ulonglong2>(), n_mm, passes.data(), (int)passes.size(), &sorted));
+		MCB_LAUNCH(ctx, "cb_unkey", k_cb_unkey, mcb_grid_for(n_mm, 256), 256, 0, sorted, n_mm, nxt.a.as<uint64_t>());
+	}
+	// consensus strings
+	MCB_LAUNCH(ctx, "cb_new_lengths", k_cb_new_lengths, mcb_grid_for(n2, 256), 256, 0, nm, cb.src.as<uint32_t>(), n2, nxt.aoff.as<uint64_t>(), nxt.a.as<uint64_t>(), cur.roff.as<uint64_t>(), L, cb.len2.as<uint64_t>());
+	MCB_CUDA(cudaMemcpyAsync(nxt.roff.p, cb.len2.p, n2 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	MCB_TRY(mcb_exclusive_scan_u64(ctx, nxt.roff.as<uint64_t>(), n2, (uint64_t*)&dc[CT_CB_B]));
+	MCB_CUDA(cudaMemcpyAsync(nxt.roff.as<uint64_t>() + n2, &dc[CT_CB_B], 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	uint64_t nref2 = 0, merged_cols = 0;
+	MCB_TRY(cb_counter(ctx, CT_CB_B, &nref2));
+	if (nm) {
+		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, nxt.roff.as<uint64_t>() + nm, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		merged_cols = ctx->h_counters.as<unsigned long long>()[0];
+	}
+	nxt.nref = nref2;
+	MCB_TRY(nxt.ref.ensure(nref2 + 32));
+	MCB_CUDA(cudaMemsetAsync(nxt.ref.as<char>() + (nref2 & ~(uint64_t)7), 0, 24, ctx->stream));      // the sketch kernel reads whole 8-byte words
+	if (merged_cols) MCB_LAUNCH(ctx, "cb_consensus", k_cb_consensus, mcb_grid_for(merged_cols, 128), 128, 0, nm, nxt.roff.as<uint64_t>(), nxt.aoff.as<uint64_t>(), nxt.a.as<uint64_t>(),
+	                            ctx->d_packed.as<uint64_t>(), WS, L, merged_cols, nxt.ref.as<char>());
+	if (n_copy) MCB_LAUNCH(ctx, "cb_copy_refs", k_cb_copy_refs, mcb_grid_for(n_copy * 32, 256), 256, 0, nm, cb.src.as<uint32_t>(), n2, cur.roff.as<uint64_t>(), cur.ref.as<char>(),
+	                       nxt.roff.as<uint64_t>(), nxt.ref.as<char>());
+	// first-m minimizers of every new contig (ids = positions in the new set)
+	MCB_TRY(cb_first_m(ctx, nxt));
+	return MCB_OK;
+}
+
+extern "C" int mcb_combine(mcb_ctx *ctx, int cbthreshold, mcb_combine_result *res)
+{
+	if (!ctx || !res) { mcb_set_error("mcb_combine: null argument"); return MCB_EINVAL; }
+	MCB_CUDA(cudaSetDevice(ctx->prm.device));
+	if (!ctx->bucket_done) { mcb_set_error("mcb_combine: needs mcb_for_bucket first"); return MCB_ESTATE; }
+	if (ctx->shard_n > 1) { mcb_set_error("mcb_combine: the contig merge runs on one GPU (gather the seed contigs first)"); return MCB_ESTATE; }
+	if (cbthreshold < 0) { mcb_set_error("mcb_combine: bad cbthreshold"); return MCB_EINVAL; }
+	memset(res, 0, sizeof *res);
+	if (!ctx->cb) ctx->cb = new McbCombineState();
+	McbCombineState &cb = *ctx->cb;
+	MCB_TRY(ctx->h_counters.ensure(64 * 8));
+	const int m = ctx->prm.first_mininum;
+	const McbBucketState &bs = ctx->bs;
+	// ---- the seed contigs of kt_for_bucket are still on the device (ctx->d_out): they are set 0
+	CbSet &s0 = cb.set[0];
+	s0.ncl = bs.tot_cl; s0.nmem = bs.tot_mem; s0.nref = bs.tot_ref;
+	MCB_TRY(s0.n.ensure((s0.ncl + 2) * 4)); MCB_TRY(s0.aoff.ensure((s0.ncl + 2) * 8)); MCB_TRY(s0.a.ensure(s0.nmem * 8 + 16)); MCB_TRY(s0.roff.ensure((s0.ncl + 2) * 8));
+	MCB_TRY(s0.ref.ensure(s0.nref + 32)); MCB_TRY(s0.mi.ensure(s0.ncl * m * 16 + 16)); MCB_TRY(s0.micnt.ensure(s0.ncl + 16));
+	{
+		McbSpan sp(ctx->tm, "combine");
+		const cudaMemcpyKind DD = cudaMemcpyDeviceToDevice;
+		MCB_CUDA(cudaMemsetAsync(s0.ref.as<char>() + (s0.nref & ~(uint64_t)7), 0, 24, ctx->stream));     // zero tail first: the sketch kernel reads whole 8-byte words
+		if (s0.ncl) {
+			MCB_CUDA(cudaMemcpyAsync(s0.n.p, ctx->d_out[0].p, s0.ncl * 4, DD, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(s0.aoff.p, ctx->d_out[1].p, (s0.ncl + 1) * 8, DD, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(s0.a.p, ctx->d_out[2].p, s0.nmem * 8, DD, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(s0.roff.p, ctx->d_out[3].p, (s0.ncl + 1) * 8, DD, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(s0.ref.p, ctx->d_out[4].p, s0.nref, DD, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(s0.mi.p, ctx->d_out[6].p, s0.ncl * m * 16, DD, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(s0.micnt.p, ctx->d_out[7].p, s0.ncl, DD, ctx->stream));
+		}
+	}
+	int cur = 0, iterations = 0;
+	long pre_tot = 0;
+	uint64_t merges_total = 0;
+	for (;;) {
+		uint64_t nm = 0;
+		MCB_TRY(combine_iteration(ctx, cb, cb.set[cur], cb.set[cur ^ 1], cbthreshold, &nm));
+		cur ^= 1; ++iterations; merges_total += nm;
+		const long tot = (long)cb.set[cur].ncl;
+		if (labs(pre_tot - tot) < 100) break;                      // kthread_cb.c:625
+		pre_tot = tot;
+	}
+	// ---- the final contigs to the host
+	CbSet &F = cb.set[cur];
+	MCB_TRY(cb.h_cl_n.ensure(F.ncl * 4 + 16)); MCB_TRY(cb.h_cl_a_off.ensure((F.ncl + 1) * 8)); MCB_TRY(cb.h_cl_a.ensure(F.nmem * 8 + 16));
+	MCB_TRY(cb.h_cl_ref_off.ensure((F.ncl + 1) * 8)); MCB_TRY(cb.h_cl_ref.ensure(F.nref + 16));
+	{
+		McbSpan sp(ctx->tm, "d2h");
+		if (F.ncl) {
+			MCB_CUDA(cudaMemcpyAsync(cb.h_cl_n.p, F.n.p, F.ncl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(cb.h_cl_a_off.p, F.aoff.p, (F.ncl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(cb.h_cl_a.p, F.a.p, F.nmem * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(cb.h_cl_ref_off.p, F.roff.p, (F.ncl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(cb.h_cl_ref.p, F.ref.p, F.nref, cudaMemcpyDeviceToHost, ctx->stream));
+		} else { cb.h_cl_a_off.as<uint64_t>()[0] = 0; cb.h_cl_ref_off.as<uint64_t>()[0] = 0; }
+	}
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->tm.collect();
+	res->n_clusters = F.ncl; res->cl_n = cb.h_cl_n.as<uint32_t>(); res->cl_a_off = cb.h_cl_a_off.as<uint64_t>(); res->cl_a = cb.h_cl_a.as<uint64_t>();
+	res->cl_ref_off = cb.h_cl_ref_off.as<uint64_t>(); res->cl_ref = cb.h_cl_ref.as<char>();
+	res->iterations = iterations; res->n_merges = merges_total;
+	return MCB_OK;
+}

@@ -231,6 +231,7 @@ struct mcb_ctx {
 	DBuf d_out[8];                       // kt_for_bucket outputs accumulated over the rounds
 	McbContigIndex cix;                  // stage-2 contig k-mer index (cached across threshold rounds)
 	McbPinnedPool *pool = nullptr;       // pinned slabs of the minimizer indexes
+	struct McbCombineState *cb = nullptr; // contig merge (mcb_combine.cu), created on first use
 	// host result buffers
 	HBuf h_cls, h_nrid, h_nrepl, h_noff, h_npos, h_nmask, h_counters, h_stage;
 	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref, h_sg, h_mi_cnt, h_mi;
@@ -427,6 +428,11 @@ int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint
 int mcb_add_bit_passes(std::vector<McbSortPass> &v, int word, int lo, int hi);  // digits covering bits [lo,hi)
 int mcb_exclusive_scan_u32(mcb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *d_total /* device u64, may be null */);
 int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t *d_total);
+
+// the minimizer index as device arrays (mcb_index.cu): keys[U] distinct minimizers, bucket-major ascending; kstart[U+1] posting
+// offsets; post[n] y values in the reference's order; ub[2^b+1] first key of every bucket
+struct McbDeviceIndex { int b; uint64_t n_post; const uint64_t *keys; const uint32_t *kstart; const uint64_t *post; const uint32_t *ub; };
+int mcb_index_build_device(mcb_ctx *ctx, mcb_tuple *d_tuples, uint64_t n, const uint64_t *d_boff, const uint64_t *h_boff, McbDeviceIndex *out);
 
 // host -> device copy that is a true DMA whatever the source: page-locked sources go in one piece, pageable ones are staged
 // through pinned chunks filled by n_threads host threads while the previous chunk is in flight (mcb_api.cu)

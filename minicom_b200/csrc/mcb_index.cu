@@ -328,6 +328,9 @@ k_ix_finalize(const mcb_tuple *__restrict__ t, const uint64_t *__restrict__ boff
 	}
 }
 
+// posting offsets end at the number of tuples: kstart[number of keys] = n
+__global__ void k_ix_close(const uint32_t *__restrict__ ub, int nb, uint32_t *__restrict__ kstart, uint32_t n) { kstart[ub[nb]] = n; }
+
 struct IxSource {            // where the tuples of a bucket range come from
 	const mcb_tuple *flat = nullptr;                                    // bucket-major array, or
 	const mcb_tuple *const *ptrs = nullptr; const uint64_t *cnt = nullptr; // one array per bucket (mm_idx_t::B[i].a), gathered through `stage`
@@ -523,4 +526,46 @@ extern "C" int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptr
 	const int r = idx_build_pipelined(ctx, n, boff, src, out);
 	if (r != MCB_OK) { mcb_idx_destroy(*out); *out = nullptr; }
 	return r;
+}
+
+// ---------------------------------------------------------------- device-resident index (the contig merge, mcb_combine.cu)
+// Same sort and CSR build as above on tuples that are already on the device, bucket-major (d_tuples, sorted in place); the key,
+// offset and posting arrays stay on the device (d_scr[4..7]) for the lookups of the merge kernels.
+int mcb_index_build_device(mcb_ctx *ctx, mcb_tuple *d_tuples, uint64_t n, const uint64_t *d_boff, const uint64_t *h_boff, McbDeviceIndex *out)
+{
+	const int b = ctx->prm.b, nb = 1 << b;
+	memset(out, 0, sizeof *out);
+	out->b = b; out->n_post = n;
+	if (n >= 0xFFFFFFFFull) { mcb_set_error("index too large"); return MCB_EINVAL; }
+	MCB_TRY(ctx->d_scr[2].ensure((n / 65 + 8ull * nb + 8) * sizeof(IxSeg)));
+	MCB_TRY(ctx->d_scr[3].ensure(((size_t)nb + 2) * 4));
+	MCB_TRY(ctx->d_scr[4].ensure(n * 8 + 16)); MCB_TRY(ctx->d_scr[5].ensure((n + 2) * 4)); MCB_TRY(ctx->d_scr[6].ensure(n * 8 + 16));
+	MCB_TRY(ctx->d_scr[7].ensure(((size_t)nb + 2) * 4)); MCB_TRY(ctx->d_scr[9].ensure(4 * 8));
+	uint64_t maxb = 0;
+	for (int i = 0; i < nb; ++i) maxb = std::max<uint64_t>(maxb, h_boff[i + 1] - h_boff[i]);
+	const uint32_t IX_CAP_MAX = 16384;
+	const uint32_t cap = (uint32_t)std::min<uint64_t>(IX_CAP_MAX, std::max<uint64_t>(64, (maxb + 63) & ~63ull));
+	const size_t smem3 = ((2048 + IX_SMEM_STK * sizeof(IxSeg) + (size_t)cap * 3 + 15) & ~(size_t)15) * IX2_WARPS;
+	const size_t smem3_big = (2048 + IX_SMEM_STK * sizeof(IxSeg) + 15) & ~(size_t)15;
+	const bool have_big = maxb > cap;
+	unsigned long long *d_chain = ctx->d_scr[9].as<unsigned long long>();
+	uint32_t *d_cnt = ctx->d_scr[3].as<uint32_t>(), *d_ub = ctx->d_scr[7].as<uint32_t>();
+	McbSpan sp(ctx->tm, "idx_build");
+	MCB_CUDA(cudaMemsetAsync(d_chain, 0, 4 * 8, ctx->stream));
+	if (n) {
+		MCB_TRY(ctx->d_scr[8].ensure(n * 16 + 16));
+		if (smem3 > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_index_sort3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+		if (have_big) { MCB_TRY(ctx->d_scr[10].ensure(n + 16)); MCB_TRY(ctx->d_scr[11].ensure(n * 4 + 16)); }
+		MCB_LAUNCH(ctx, "index_sort", k_index_sort3<false>, mcb_grid_for(nb, IX2_WARPS), IX2_WARPS * 32, smem3, d_tuples, ctx->d_scr[8].as<mcb_tuple>(), d_boff, nb, cap,
+		           ctx->d_scr[2].as<IxSeg>(), (uint8_t*)nullptr, (uint32_t*)nullptr);
+		if (have_big) MCB_LAUNCH(ctx, "index_sort_big", k_index_sort3<true>, (unsigned)std::min(nb, 4 * ctx->sm_count), IX2_WARPS * 32, smem3_big, d_tuples, ctx->d_scr[8].as<mcb_tuple>(),
+		                         d_boff, nb, cap, ctx->d_scr[2].as<IxSeg>(), ctx->d_scr[10].as<uint8_t>(), ctx->d_scr[11].as<uint32_t>());
+		MCB_LAUNCH(ctx, "ix_count", k_ix_count, mcb_grid_for(nb, IXF_WARPS), IXF_WARPS * 32, 0, d_tuples, d_boff, nb, d_cnt);
+	} else MCB_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)nb * 4, ctx->stream));
+	MCB_LAUNCH(ctx, "ix_scan", k_ix_scan_run, 1, 1024, 0, d_cnt, 0, nb, d_chain, 0, d_ub, nb);
+	if (n) MCB_LAUNCH(ctx, "ix_finalize", k_ix_finalize, mcb_grid_for(nb, IXF_WARPS), IXF_WARPS * 32, 0, d_tuples, d_boff, nb, d_ub,
+	                  ctx->d_scr[4].as<uint64_t>(), ctx->d_scr[5].as<uint32_t>(), ctx->d_scr[6].as<uint64_t>());
+	MCB_LAUNCH(ctx, "ix_close", k_ix_close, 1, 1, 0, d_ub, nb, ctx->d_scr[5].as<uint32_t>(), (uint32_t)n);
+	out->keys = ctx->d_scr[4].as<uint64_t>(); out->kstart = ctx->d_scr[5].as<uint32_t>(); out->post = ctx->d_scr[6].as<uint64_t>(); out->ub = d_ub;
+	return MCB_OK;
 }

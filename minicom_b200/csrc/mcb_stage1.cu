@@ -6,6 +6,7 @@
 //   K4  k_sketch_lh              mm_sketch_lh_ori (sketch.c:116-165), first `first_mininum` tuples per seed contig
 //   round loop                   kt_for_bucket (kthread_bucket.c:562-629)
 #include "mcb_common.cuh"
+#include "mcb_lh.cuh"
 #include <algorithm>
 #include <thread>
 
@@ -706,124 +707,8 @@ __global__ void k_scatter_clusters(const uint32_t *__restrict__ gstart, uint64_t
 	for (unsigned long long c = lane; c < len; c += 32) cl_ref[ref_base + rb + c] = reftmp[so + c];
 }
 
-// ---------------------------------------------------------------- K4: first m windowed minimizers of each new seed contig
-#define LH_THREADS 64
-struct LhRingSmem {
-	uint64_t *x; uint32_t *ps; int tid;
-	__device__ __forceinline__ void set(int j, uint64_t hx, uint32_t p) { x[j * LH_THREADS + tid] = hx; ps[j * LH_THREADS + tid] = p; }
-	__device__ __forceinline__ uint64_t hx(int j) const { return x[j * LH_THREADS + tid]; }
-	__device__ __forceinline__ uint32_t p(int j) const { return ps[j * LH_THREADS + tid]; }
-};
+// K4 (first m windowed minimizers of each new seed contig): k_sketch_lh2 in mcb_lh.cuh
 
-// mm_sketch_lh_ori (sketch.c:116-165) is a sequential scan with data-dependent tie rules, so one thread walks one contig; its
-// characters arrive through aligned 64-bit loads, and the w-slot ring buffer (hash + position/strand per slot) lives in shared
-// memory, slot-major so that the lanes of a warp hit different banks.  The walk stops after m outputs (kthread_bucket.c:463).
-// The window minimum is found in constant time.  The reference rescans the whole ring whenever the minimum leaves the window
-// (sketch.c:150-158); with 32 contigs per warp some lane needs that at almost every step, so every warp paid the w-slot scan
-// (and the tie scan after it) all the time.  Here the ring is cut into blocks of w steps (one turn of bp): when bp wraps, one
-// backward pass stores for every slot j the slot of the rightmost minimum of the previous block's slots [j, w) (strict <
-// from the right = the reference's ">=" from the left); a running rightmost minimum P covers the slots [0, bp] written in the
-// current block.  The minimum of the window is then min(S[bp+1], P), ties going to P (newer).  Both carry a "some other slot
-// of the range holds the same hash" bit, so the reference's scan for identical k-mers (:159-161) runs only when there is one.
-// bp is the same in all lanes of a warp unless a lane meets a symmetric k-mer (even k only), so the passes do not diverge.
-#define LH2_SLOT_MASK 0x7Fu
-#define LH2_WMAX MCB_LH_WMAX
-template <bool WIDE>
-__global__ void __launch_bounds__(LH_THREADS)
-k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count, uint64_t cid_first,
-             int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt)
-{
-	extern __shared__ __align__(16) unsigned char lh_smem[];
-	uint64_t *rx = (uint64_t*)lh_smem;                                        // [w][LH_THREADS]
-	uint32_t *rp = (uint32_t*)(rx + (size_t)w * LH_THREADS);                  // [w][LH_THREADS]
-	uint8_t *ss = (uint8_t*)(rp + (size_t)w * LH_THREADS);                    // [w][LH_THREADS] suffix-minimum slot | tie << 7
-	const uint64_t ci = (uint64_t)blockIdx.x * LH_THREADS + threadIdx.x;
-	if (ci >= cl_count) return;
-	const uint64_t c = cl_first + ci;
-	const uint64_t b = cl_ref_off[c], e = cl_ref_off[c + 1];
-	const int len = (int)(e - b);
-	const uint32_t rid = (uint32_t)((cid_first + ci) << 8);          // ((clusters.n-1)<<8)+tid, tid 0 (kthread_bucket.c:458)
-	const uint64_t *str8 = (const uint64_t*)(cl_ref + (b & ~(uint64_t)7));
-	const int skew = (int)(b & 7);
-	uint64_t chunk = 0;
-	LhRingSmem ring; ring.x = rx; ring.ps = rp; ring.tid = threadIdx.x;
-	uint8_t *sst = ss + threadIdx.x;
-	mcb_tuple *out = mi + c * m;
-	int n_out = 0;
-	const uint64_t mask = (1ull << (2 * k)) - 1, shift1 = 2 * (k - 1);
-	const uint32_t mh = (uint32_t)(mask >> 32);
-	const int s1 = WIDE ? 2 * (k - 1) - 32 : 0;
-	const uint32_t t3 = 3u << s1;
-	uint64_t fw = 0, rv = 0;
-	uint32_t flo = 0, fhi = 0, rlo = 0, rhi = 0;
-	uint64_t mn_x = ~0ull; uint32_t mn_p = ~0u;
-	uint64_t px = ~0ull; int pslot = 0; bool ptie = false;             // rightmost minimum of the slots written in this block
-	int l = 0, bp = 0, mp = 0;
-#define LH_EMIT(hx_, p_) do { if (n_out < m) { mcb_tuple t_; t_.x = (hx_); t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } while (0)
-	for (int j = 0; j < w; ++j) { ring.set(j, ~0ull, ~0u); sst[j * LH_THREADS] = (uint8_t)(w - 1); }
-	for (int i = 0; i < len && n_out < m; ++i) {
-		const int ai = i + skew;
-		if (i == 0 || (ai & 7) == 0) chunk = str8[ai >> 3];
-		const unsigned cc = mcb_code_of((unsigned char)(chunk >> (8 * (ai & 7))));   // consensus strings are upper-case ACGT (invert_code_rule)
-		uint64_t ix = ~0ull; uint32_t ip = ~0u;
-		if (cc < 4) {
-			if (WIDE) {
-				fhi = __funnelshift_l(flo, fhi, 2) & mh; flo = flo * 4u + cc;
-				rlo = __funnelshift_r(rlo, rhi, 2); rhi = (rhi >> 2) | ((cc << s1) ^ t3);
-				fw = (uint64_t)fhi << 32 | flo; rv = (uint64_t)rhi << 32 | rlo;
-			} else {
-				fw = (fw << 2 | cc) & mask;
-				rv = (rv >> 2) | ((3ull ^ cc) << shift1);
-			}
-			if (fw == rv) continue;
-			const int z = fw < rv ? 0 : 1;
-			if (++l >= k) { ix = WIDE ? mcb_hash64_wide(z ? rv : fw, mh) : mcb_hash64_hd(z ? rv : fw, mask); ip = (uint32_t)i << 1 | (uint32_t)z; }
-		} else l = 0;
-		ring.set(bp, ix, ip);
-		{
-			const bool ple = ix <= px;
-			ptie = ple ? (ix == px) : ptie; px = ple ? ix : px; pslot = ple ? bp : pslot;
-		}
-		if (l == w + k - 1) {
-			for (int j = bp + 1; j < w; ++j) if (mn_x == ring.hx(j) && ring.p(j) != mn_p) LH_EMIT(ring.hx(j), ring.p(j));
-			for (int j = 0; j < bp; ++j) if (mn_x == ring.hx(j) && ring.p(j) != mn_p) LH_EMIT(ring.hx(j), ring.p(j));
-		}
-		if (ix <= mn_x) {
-			if (l >= w + k) LH_EMIT(mn_x, mn_p);
-			mn_x = ix; mn_p = ip; mp = bp;
-		} else if (bp == mp) {
-			if (l >= w + k - 1) LH_EMIT(mn_x, mn_p);
-			uint64_t nx = px; int ns = pslot; bool tie = ptie;
-			if (bp + 1 < w) {
-				const unsigned sv = sst[(bp + 1) * LH_THREADS];
-				const int sslot = (int)(sv & LH2_SLOT_MASK);
-				const uint64_t sx = ring.hx(sslot);
-				if (sx < px) { nx = sx; ns = sslot; tie = (sv >> 7) != 0; }
-				else if (sx == px) tie = true;
-			}
-			mn_x = nx; mp = ns; mn_p = ring.p(ns);
-			if (tie && l >= w + k - 1) {
-				for (int j = bp + 1; j < w; ++j) if (mn_x == ring.hx(j) && mn_p != ring.p(j)) LH_EMIT(ring.hx(j), ring.p(j));
-				for (int j = 0; j <= bp; ++j) if (mn_x == ring.hx(j) && mn_p != ring.p(j)) LH_EMIT(ring.hx(j), ring.p(j));
-			}
-		}
-		if (++bp == w) {
-			bp = 0;
-			uint64_t sx = ring.hx(w - 1); unsigned sv = (unsigned)(w - 1);
-			sst[(w - 1) * LH_THREADS] = (uint8_t)sv;
-			for (int j = w - 2; j >= 1; --j) {
-				const uint64_t v = ring.hx(j);
-				if (v < sx) { sx = v; sv = (unsigned)j; }
-				else if (v == sx) sv |= 0x80u;
-				sst[j * LH_THREADS] = (uint8_t)sv;
-			}
-			px = ~0ull; pslot = 0; ptie = false;
-		}
-	}
-	if (n_out < m && mn_x != ~0ull) LH_EMIT(mn_x, mn_p);
-#undef LH_EMIT
-	mi_cnt[c] = (uint8_t)(n_out < m ? n_out : m);
-}
 // ================================================================= host side
 static int sync_counters(mcb_ctx *ctx, unsigned long long **hc)
 {
@@ -1252,7 +1137,7 @@ int mcb_bucket_round_b_impl(mcb_ctx *ctx, uint64_t cid_first)
 			auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
 			if (lh2_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh2_smem));
 			MCB_LAUNCH(ctx, "sketch_lh", kern, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh2_smem, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
-			           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>());
+			           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>(), (const uint64_t*)nullptr, (uint32_t*)nullptr);
 		}
 		bs.tot_cl += n_cl_new; bs.tot_mem += n_mem_new; bs.tot_ref += n_ref_new; bs.tot_sg += n_sg_new;
 		// ---- rejected reads go to the next round with a shorter k-mer (kthread_bucket.c:205-212,488-496)

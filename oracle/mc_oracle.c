@@ -15,6 +15,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+static char *dup_str(const char *s) { size_t n = strlen(s) + 1; char *d = (char*)malloc(n); memcpy(d, s, n); return d; }
+
 typedef struct { uint64_t x, y; } mco_tuple;
 
 typedef struct {
@@ -515,6 +517,190 @@ const uint64_t *mco_idx_keys(const mco_index *ix) { return ix->keys; }
 const uint64_t *mco_idx_postings(const mco_index *ix) { return ix->post; }
 void mco_idx_key_starts(const mco_index *ix, uint64_t *out) { for (size_t i = 0; i <= ix->n_keys; ++i) out[i] = ix->pstart[i]; }
 void mco_idx_free(mco_index *ix) { if (!ix) return; free(ix->koff); free(ix->keys); free(ix->pstart); free(ix->post); free(ix); }
+
+/* ------------------------------------------------------------------ N1: combine_cluster (kthread_cb.c:570-630), the contig merge */
+/* Restated for the GPU merge (mcb_combine); follows the num_thr=1 schedule: clusters in array order, flags set by the first
+ * acceptable hit (kthread_cb.c:267-343), merged clusters first, untouched ones copied behind them (:474-494), until the
+ * number of clusters changes by less than 100 (:625). */
+typedef struct { vec_u64 a; char *ref; } mco_cl;
+typedef struct mco_combine_out {
+	vec_u32 cl_n; vec_u64 cl_a_off, cl_a, cl_ref_off; vec_chr cl_ref;
+	int iterations;
+	vec_u64 iter_tuples_off;      /* [iterations+1] into iter_tuples: the tuples handed to mm_idx_generation number j (push order) */
+	vec_tup iter_tuples;
+	vec_u32 iter_merges;          /* merges per iteration */
+} mco_combine_out;
+
+/* match_pro (kthread_cb.c:36-53): character mismatches over the overlap of two strings aligned at (i_, j_) */
+static int match_pro(const char *s0, int n0, const char *s1, int n1, int i_, int j_)
+{
+	int tot = 0, match = 0;
+	for (int i = i_, j = j_; i < n0 && j < n1; ++i, ++j) { ++tot; match += s0[i] == s1[j]; }
+	for (int i = i_ - 1, j = j_ - 1; i >= 0 && j >= 0; --i, --j) { ++tot; match += s0[i] == s1[j]; }
+	return tot - match;
+}
+/* cmpcluster2 (kthread_cb.c:55-70): position ascending, then direction */
+static int cmp_pos_dir(const void *a_, const void *b_)
+{
+	uint64_t a = *(const uint64_t*)a_, b = *(const uint64_t*)b_;
+	int pa = (int)((uint32_t)a >> 1), pb = (int)((uint32_t)b >> 1);
+	if (pa == pb) return (int)(a & 1) - (int)(b & 1);
+	return pa - pb;
+}
+/* construct_ref2 (kthread_cb.c:105-218): sort the members, pile the oriented reads up, majority per column ('A' unless a
+ * base has strictly more votes, in the order A, C, G, T), length = end of the right-most member */
+static char *construct_ref2(const mco_stage1 *S, vec_u64 *m)
+{
+	const int L = S->p.readlen;
+	qsort(m->a, m->n, sizeof(uint64_t), cmp_pos_dir);              /* :107, the same libc sort as the reference */
+	const int tot_len = (int)((uint32_t)m->a[m->n - 1] >> 1) + 2 * L;
+	uint32_t *cnt = (uint32_t*)calloc((size_t)4 * (tot_len + 1), sizeof(uint32_t));
+	char *buf = (char*)malloc(L + 1);
+	int rend = 0;
+	for (size_t q = 0; q < m->n; ++q) {
+		const uint64_t y = m->a[q];
+		const int pos = (int)((uint32_t)y >> 1);
+		oriented(S, (uint32_t)(y >> 32), (int)(y & 1), buf);
+		for (int t = 0; t < L; ++t) ++cnt[(size_t)nt4((unsigned char)buf[t]) * (tot_len + 1) + pos + t];
+		if (pos + L > rend) rend = pos + L;
+	}
+	char *ref = (char*)calloc((size_t)rend + 1, 1);
+	for (int c = 0; c < rend; ++c) {
+		uint32_t mx = cnt[c]; char ch = 'A';
+		for (int b = 1; b < 4; ++b) if (cnt[(size_t)b * (tot_len + 1) + c] > mx) { mx = cnt[(size_t)b * (tot_len + 1) + c]; ch = "ACGT"[b]; }
+		ref[c] = ch;
+	}
+	free(cnt); free(buf);
+	return ref;
+}
+
+static void push_first_m(const mco_stage1 *S, const char *ref, uint32_t cid, vec_tup *tuples, mco_tuple *scratch, int64_t cap)
+{
+	const int64_t n = mco_sketch_lh(ref, (int)strlen(ref), S->p.rw, S->p.k, cid << 8, scratch, cap);      /* win + win_step, win_step = 0 (:572) */
+	for (int64_t j = 0; j < n && j < S->p.first_mininum && j < cap; ++j) vpush(mco_tuple, *tuples, scratch[j]);
+}
+
+mco_combine_out *mco_combine(const mco_stage1 *S, int cbthreshold)
+{
+	mco_combine_out *o = (mco_combine_out*)calloc(1, sizeof *o);
+	const int b = S->p.b;
+	const size_t nb = (size_t)1 << b;
+	size_t n = S->cl_n.n;
+	mco_cl *cur = (mco_cl*)calloc(n + 1, sizeof(mco_cl));
+	for (size_t c = 0; c < n; ++c) {
+		for (uint64_t q = S->cl_a_off.a[c]; q < S->cl_a_off.a[c + 1]; ++q) vpush(uint64_t, cur[c].a, S->cl_a.a[q]);
+		const size_t len = (size_t)(S->cl_ref_off.a[c + 1] - S->cl_ref_off.a[c]);
+		cur[c].ref = (char*)calloc(len + 1, 1);
+		memcpy(cur[c].ref, S->cl_ref.a + S->cl_ref_off.a[c], len);
+	}
+	vec_tup tuples = {0, 0, 0};
+	for (size_t i = 0; i < S->mi.n; ++i) vpush(mco_tuple, tuples, S->mi.a[i]);
+	const int64_t cap = 1 << 20;
+	mco_tuple *mini = (mco_tuple*)malloc((size_t)cap * sizeof(mco_tuple)), *scratch = (mco_tuple*)malloc((size_t)cap * sizeof(mco_tuple));
+	long pre_tot = 0;
+	vpush(uint64_t, o->iter_tuples_off, 0);
+	for (;;) {
+		/* mm_idx_generation over the tuples pushed for this cluster set (:574) */
+		for (size_t i = 0; i < tuples.n; ++i) vpush(mco_tuple, o->iter_tuples, tuples.a[i]);
+		vpush(uint64_t, o->iter_tuples_off, o->iter_tuples.n);
+		mco_tuple *bm = (mco_tuple*)malloc((tuples.n + 1) * sizeof(mco_tuple));
+		size_t *off = (size_t*)calloc(nb + 1, sizeof(size_t));
+		bucket_partition(tuples.a, tuples.n, b, bm, off);
+		uint64_t *off64 = (uint64_t*)malloc((nb + 1) * 8);
+		for (size_t i = 0; i <= nb; ++i) off64[i] = off[i];
+		mco_index *ix = mco_idx_build(bm, off64, b);
+		free(bm); free(off); free(off64);
+		tuples.n = 0;
+		/* kt_find_next_for (:502-568) with one thread */
+		uint8_t *flag = (uint8_t*)calloc(n + 1, 1);
+		mco_cl *nxt = (mco_cl*)calloc(n + 1, sizeof(mco_cl));
+		size_t nn = 0; uint32_t merges = 0;
+		for (size_t i = 0; i < n; ++i) {
+			if (flag[i]) continue;
+			/* find_next (:220-372) */
+			const char *ref = cur[i].ref;
+			const int len = (int)strlen(ref);
+			const uint32_t rid_ori = (uint32_t)i << 8;
+			const int64_t nm = mco_sketch_lh(ref, len, S->p.rw, S->p.k, rid_ori, mini, cap);
+			int done = 0;
+			for (int64_t j = 0; j < nm && j < cap && !done; ++j) {
+				int np = 0;
+				const uint64_t *r = mco_idx_get(ix, mini[j].x, &np);
+				const uint32_t pos_ori = (uint32_t)mini[j].y >> 1, dir_ori = (uint32_t)(mini[j].y & 1);
+				for (int q = 0; q < np && !done; ++q) {
+					const uint32_t rid = (uint32_t)(r[q] >> 32);
+					if (rid == rid_ori) continue;
+					const size_t cid = rid >> 8;
+					const uint32_t pos = (uint32_t)r[q] >> 1, dir = (uint32_t)(r[q] & 1);
+					if (dir != dir_ori || flag[i] || flag[cid]) continue;
+					if (match_pro(ref, len, cur[cid].ref, (int)strlen(cur[cid].ref), (int)pos_ori, (int)pos) > cbthreshold) continue;
+					mco_cl t; memset(&t, 0, sizeof t);
+					const mco_cl *first = pos_ori >= pos ? &cur[i] : &cur[cid], *second = pos_ori >= pos ? &cur[cid] : &cur[i];
+					const uint64_t shift = pos_ori >= pos ? pos_ori - pos : pos - pos_ori;
+					for (size_t u = 0; u < first->a.n; ++u) vpush(uint64_t, t.a, first->a.a[u]);
+					for (size_t u = 0; u < second->a.n; ++u) {
+						const uint64_t y = second->a.a[u];
+						vpush(uint64_t, t.a, y >> 32 << 32 | (((uint64_t)((uint32_t)y >> 1) + shift) << 1) | (y & 1));      /* :300-317 */
+					}
+					t.ref = construct_ref2(S, &t.a);
+					flag[i] = flag[cid] = 1; done = 1; ++merges;
+					nxt[nn] = t;
+					push_first_m(S, t.ref, (uint32_t)nn, &tuples, scratch, cap);                                       /* :359-368 */
+					++nn;
+				}
+			}
+		}
+		for (size_t i = 0; i < n; ++i) {           /* cp_cluster (:374-403) for everything left */
+			if (flag[i]) continue;
+			mco_cl t; memset(&t, 0, sizeof t);
+			for (size_t u = 0; u < cur[i].a.n; ++u) vpush(uint64_t, t.a, cur[i].a.a[u]);
+			t.ref = dup_str(cur[i].ref);
+			nxt[nn] = t;
+			push_first_m(S, t.ref, (uint32_t)nn, &tuples, scratch, cap);
+			++nn;
+		}
+		vpush(uint32_t, o->iter_merges, merges);
+		for (size_t c = 0; c < n; ++c) { free(cur[c].a.a); free(cur[c].ref); }
+		free(cur); free(flag); mco_idx_free(ix);
+		cur = nxt; n = nn;
+		++o->iterations;
+		if (labs(pre_tot - (long)n) < 100) break;          /* :625 */
+		pre_tot = (long)n;
+	}
+	vpush(uint64_t, o->cl_a_off, 0); vpush(uint64_t, o->cl_ref_off, 0);
+	for (size_t c = 0; c < n; ++c) {
+		vpush(uint32_t, o->cl_n, (uint32_t)cur[c].a.n);
+		for (size_t u = 0; u < cur[c].a.n; ++u) vpush(uint64_t, o->cl_a, cur[c].a.a[u]);
+		vpush(uint64_t, o->cl_a_off, o->cl_a.n);
+		for (const char *q = cur[c].ref; *q; ++q) vpush(char, o->cl_ref, *q);
+		vpush(uint64_t, o->cl_ref_off, o->cl_ref.n);
+		free(cur[c].a.a); free(cur[c].ref);
+	}
+	free(cur); free(tuples.a); free(mini); free(scratch);
+	return o;
+}
+enum { MCO_CB_CL_N = 0, MCO_CB_CL_A_OFF, MCO_CB_CL_A, MCO_CB_CL_REF_OFF, MCO_CB_CL_REF, MCO_CB_ITER_OFF, MCO_CB_ITER_TUPLES, MCO_CB_ITER_MERGES };
+const void *mco_combine_field(const mco_combine_out *o, int what, uint64_t *count)
+{
+	switch (what) {
+	case MCO_CB_CL_N: *count = o->cl_n.n; return o->cl_n.a;
+	case MCO_CB_CL_A_OFF: *count = o->cl_a_off.n; return o->cl_a_off.a;
+	case MCO_CB_CL_A: *count = o->cl_a.n; return o->cl_a.a;
+	case MCO_CB_CL_REF_OFF: *count = o->cl_ref_off.n; return o->cl_ref_off.a;
+	case MCO_CB_CL_REF: *count = o->cl_ref.n; return o->cl_ref.a;
+	case MCO_CB_ITER_OFF: *count = o->iter_tuples_off.n; return o->iter_tuples_off.a;
+	case MCO_CB_ITER_TUPLES: *count = o->iter_tuples.n; return o->iter_tuples.a;
+	case MCO_CB_ITER_MERGES: *count = o->iter_merges.n; return o->iter_merges.a;
+	default: *count = 0; return NULL;
+	}
+}
+int mco_combine_iterations(const mco_combine_out *o) { return o->iterations; }
+void mco_combine_free(mco_combine_out *o)
+{
+	if (!o) return;
+	free(o->cl_n.a); free(o->cl_a_off.a); free(o->cl_a.a); free(o->cl_ref_off.a); free(o->cl_ref.a); free(o->iter_tuples_off.a); free(o->iter_tuples.a); free(o->iter_merges.a);
+	free(o);
+}
 
 /* ------------------------------------------------------------------ stage 2: realign_hash (kthread_hash_realign.c:569-594) */
 /* 2-bit read images.  The reference's std::bitset<2L> puts base i at bits 2i,2i+1 with A=00 C=10 G=01 T=11 (bit 2i first;

@@ -60,6 +60,12 @@ def lib():
         L.mco_realign_field.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_uint64]
         L.mco_realign_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.mco_realign_free.argtypes = [C.c_void_p]
+        L.mco_combine.restype = C.c_void_p
+        L.mco_combine.argtypes = [C.c_void_p, C.c_int]
+        L.mco_combine_field.restype = C.c_void_p
+        L.mco_combine_field.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        L.mco_combine_iterations.argtypes = [C.c_void_p]
+        L.mco_combine_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -148,6 +154,17 @@ class Stage1:
         out = {"claim_contig": f(0, np.uint32), "claim_sg": f(1, np.uint32), "claim_y": f(2, np.uint64), "fpA_sg": f(3, np.uint32), "fpT_sg": f(4, np.uint32),
                "flag": f(5, np.uint8), "n_windows": int(cnt[0]), "n_probes": int(cnt[1]), "n_candidates": int(cnt[2]), "numdict": int(cnt[3])}
         lib().mco_realign_free(h)
+        return out
+
+    def combine(self, cbthreshold: int):
+        """combine_cluster (kthread_cb.c:570-630) over the seed contigs of this run.  Returns a dict with the final contigs, the
+        number of iterations, and the tuples handed to every mm_idx_generation in push order."""
+        h = lib().mco_combine(self._h, cbthreshold)
+        f = lambda w, dt: _field(lib().mco_combine_field, h, w, dt)  # noqa: E731
+        out = {"cl_n": f(0, np.uint32), "cl_a_off": f(1, np.uint64), "cl_a": f(2, np.uint64), "cl_ref_off": f(3, np.uint64), "cl_ref": f(4, np.uint8),
+               "iter_off": f(5, np.uint64), "iter_tuples": _field(lib().mco_combine_field, h, 6, np.uint64, per=2).reshape(-1, 2), "iter_merges": f(7, np.uint32),
+               "iterations": int(lib().mco_combine_iterations(h))}
+        lib().mco_combine_free(h)
         return out
 
     def close(self):

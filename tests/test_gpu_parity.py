@@ -403,3 +403,44 @@ if __name__ == "__main__":
             traceback.print_exc()
         print("\n".join("   " + l for l in log))
     sys.exit(rc)
+
+
+# ---------------------------------------------------------------- N1: the contig merge (combine_cluster, kthread_cb.c:570-630)
+@pytest.mark.parametrize("name", refdump.golden_names())
+def test_combine_matches_reference_dump(name):
+    """mcb_combine on the device-resident seed contigs against the contigs the unmodified reference holds after combine_cluster
+    (num_thr = 1; c_cl_* of the committed fixtures): members, their order, consensus strings, number of iterations."""
+    reads, meta, d, _ = refdump.load_golden(name)
+    env = meta["env"]
+    p = api.resolve_params(meta["L"], k=int(env.get("MC_K", 0)), e=int(env.get("MC_E", 0)), w=int(env.get("MC_W", 0)), m=int(env.get("MC_M", 0)))
+    cbthr = int(env.get("MC_CBTHR", 0)) or 2 * p.diff_threshold
+    c = d.clusters("c_cl")
+    with api.Context(p) as ctx:
+        ctx.for_reads(reads)
+        ctx.for_bucket()
+        r = ctx.combine(cbthr)
+    assert r.iterations == d.n_idx()
+    assert np.array_equal(r.cl_n, c["n"].astype(np.uint32))
+    assert np.array_equal(r.cl_a, c["a"]) and np.array_equal(r.cl_a_off, c["a_off"])
+    assert np.array_equal(r.cl_ref, c["ref"]) and np.array_equal(r.cl_ref_off, c["ref_off"])
+
+
+@pytest.mark.parametrize("n,L,G,seed,opts", [(40000, 100, 200000, 5, {}), (30000, 150, 150000, 6, {"w": 20}), (25000, 75, 120000, 7, {}),
+                                             (30000, 100, 9000, 8, {}),          # 300x coverage: long contigs, hundreds of members, many partners
+                                             (20000, 100, 100000, 9, {"k": 24, "e": 6, "m": 3, "w": 10})])
+def test_combine_matches_oracle(n, L, G, seed, opts):
+    import oracle_lib as O
+    reads = synth.make_reads(n, L, G, seed=seed, special=0.005)
+    S = O.Stage1(O.resolve_params(L, **opts), reads)
+    p = api.resolve_params(L, **opts)
+    for cbthr in (2 * p.diff_threshold, 3):
+        want = S.combine(cbthr)
+        with api.Context(p) as ctx:
+            ctx.for_reads(reads)
+            ctx.for_bucket()
+            r = ctx.combine(cbthr)
+        assert r.iterations == want["iterations"], (r.iterations, want["iterations"])
+        assert np.array_equal(r.cl_n, want["cl_n"]) and np.array_equal(r.cl_a, want["cl_a"]), "members differ"
+        assert np.array_equal(r.cl_ref, want["cl_ref"]) and np.array_equal(r.cl_ref_off, want["cl_ref_off"]), "consensus strings differ"
+        assert r.n_merges == int(want["iter_merges"].sum())
+    S.close()
