@@ -233,7 +233,7 @@ def bench_ours(args):
     fq = os.path.join(wd, "in.fastq")
     synth.write_fastq(fq, reads)
     log(f"[rank {rank}] workload {args.workload}: {n} x {L} bp synthesized in {time.time() - t0:.1f}s; running the drop-in executable once (num_thr={rec_threads}) to record the call sequence")
-    dt = run_binary(exe, fq, wd, dict(ref_env, MCB_RECORD=rec, MCB_DEVICE=local), rec_threads)
+    dt = run_binary(exe, fq, wd, dict(ref_env, MCB_RECORD=rec, MCB_DEVICE=local, MCB_HOST_MERGE=1), rec_threads)
     os.remove(fq)
     log(f"[rank {rank}] drop-in run: front end {front_end_seconds(dt):.3f}s wall inside the entry points (first call includes CUDA context creation); whole program {dt['wall_total']:.1f}s")
     idx_calls, realign_calls = [], []
@@ -418,6 +418,210 @@ def bench_ours(args):
         dist.destroy_process_group()
 
 
+def bench_pipeline(args):
+    """N = 1 (default): the whole front end stays on the device.  A step = kt_for_reads, kt_for_bucket, combine_cluster (the contig
+    merge: every mm_idx_generation of the run happens inside it, on device-resident tuples), and every realign_hash of the
+    -e/-S/-E schedule against the merged contigs, which never leave the device.  The only recorded inputs are the singles of every
+    threshold round (the reference's host computes them with updateSingle(), preprocess.c:243-255), taken from one untimed run of
+    the drop-in executable; that run is deterministic at any thread count now that the merge is on the device."""
+    import torch
+    from minicom_b200 import api, parity, synth
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    n, L, G, mode, ref_env = WORKLOADS[args.workload]
+    if args.reads:
+        n, G = args.reads, max(1000, args.reads * 5)
+    threads = args.host_threads or min(os.cpu_count() or 1, 32)
+    exe = os.path.join(ROOT, "dropin", "_build", f"minicom_b200_L{L}_{mode}")
+    if not os.path.exists(exe):
+        raise SystemExit(f"{exe} missing: run __graft_entry__.build() where /root/reference exists (no CPU fallback)")
+    t0 = time.time()
+    reads = synth.make_reads(n, L, G, seed=1)
+    wd = tempfile.mkdtemp(prefix="mcb_bench_")
+    rec = os.path.join(wd, "rec")
+    os.makedirs(rec)
+    fq = os.path.join(wd, "in.fastq")
+    synth.write_fastq(fq, reads)
+    log(f"workload {args.workload}: {n} x {L} bp synthesized in {time.time() - t0:.1f}s; running the drop-in executable once (num_thr={threads}) to record the singles of every threshold round")
+    dt = run_binary(exe, fq, wd, dict(ref_env, MCB_RECORD=rec, MCB_DEVICE=local), threads)
+    os.remove(fq)
+    log(f"drop-in run: front end {front_end_seconds(dt):.3f}s wall inside the entry points + contig merge {dt.get('combine_cluster', 0):.3f}s; whole program {dt['wall_total']:.1f}s")
+    keep_alive = []
+
+    def pin(a):
+        t = torch.from_numpy(a).pin_memory()
+        keep_alive.append(t)
+        return t.numpy()
+
+    _, realign_calls = load_recorded(rec, None)
+    shutil.rmtree(wd, ignore_errors=True)
+    rounds_in = [(pin(sg), int(len(off) - 1), thr, ms, nd) for sg, refs, off, thr, ms, nd in realign_calls]
+    rec_contigs = (realign_calls[0][1], realign_calls[0][2]) if realign_calls else None
+    del realign_calls
+    rows_pinned = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
+    rows_pinned.numpy()[:] = reads
+    rows_dev = rows_pinned.to("cuda", non_blocking=False)
+    del reads
+    params = api.resolve_params(L, device=local, **{k: int(ref_env[e]) for k, e in (("k", "MC_K"), ("e", "MC_E"), ("w", "MC_W"), ("m", "MC_M")) if e in ref_env})
+    cbthr = int(ref_env.get("MC_CBTHR", 0)) or 2 * int(params.diff_threshold)          # minicommain.c:122-126
+    ctx = api.Context(params)
+    ctx.timers_enable(True)
+    m = int(params.first_mininum)
+    ws = (((L + 31) // 32) + 1) & ~1
+    # ---- parity (untimed, copying API)
+    got = {}
+    rr = ctx.for_reads(rows_pinned.numpy())
+    tuples = ctx.debug_read_tuples(n)
+    br = ctx.for_bucket()
+    mi_valid = br.mi[np.arange(m)[None, :] < br.mi_cnt[:, None]]
+    got.update(parity.stage1_digests(rr.cls, tuples, br.cl_n, br.cl_a, br.cl_ref, np.diff(br.cl_ref_off.astype(np.int64)), br.sg, mi_valid))
+    del tuples
+    bm = parity.bucket_major(mi_valid)                                                  # the first mm_idx_generation, rebuilt from the host side: posting order
+    off0 = np.zeros((1 << 14) + 1, dtype=np.uint64)
+    np.cumsum(np.bincount((bm[:, 0] & parity.NB_MASK).astype(np.int64), minlength=1 << 14), out=off0[1:])
+    ix = ctx.idx_build(bm, off0)
+    got.update(parity.index_digests(0, *ix.arrays()))
+    ix.close()
+    del bm, mi_valid, br
+    ctx.for_reads(rows_pinned.numpy())
+    ctx.for_bucket()
+    cr = ctx.combine(cbthr)
+    got.update(parity.contig_digests(cr.cl_n, cr.cl_a, cr.cl_ref, np.diff(cr.cl_ref_off.astype(np.int64))))
+    consistent = rec_contigs is not None and np.array_equal(cr.cl_ref, rec_contigs[0]) and np.array_equal(cr.cl_ref_off, rec_contigs[1])
+    n_contigs, claims = len(cr.cl_n), []
+    for j, (sg, nc, thr, ms, nd) in enumerate(rounds_in):
+        r = ctx.realign(sg, None, None, thr, ms, nd)
+        got.update(parity.realign_digests(j, sg, n_contigs, r.claim_contig, r.claim_sg, r.claim_y, r.fpA_sg, r.fpT_sg))
+        claims.append(len(r.claim_y))
+    par = {"status": "unchecked", "digests": len(got), "claims": claims, "iterations": cr.iterations, "contigs": n_contigs, "recorded_contigs_equal_merged": bool(consistent)}
+    path = os.path.join(ROOT, "tests", "golden", f"manifest_{args.workload}.json")
+    if not args.reads and os.path.exists(path):
+        with open(path) as f:
+            man = json.load(f)
+        par.update(parity.compare(got, man["state"]))
+        par.update({"manifest": os.path.relpath(path, ROOT), "against": "unmodified reference, num_thr=1, same seeded reads (tests/golden/make_manifests.py)",
+                    "covers": "read classes, minimizer tuples, seed contigs, singles, index tuples, the first index (keys + posting order), the contigs after the device merge "
+                              "(members, order, consensus), and per threshold round the singles, claims in append order, sg_flag and poly-A/T diversions"})
+    log(f"parity: {json.dumps(par)}")
+    del cr, got
+    api.VIEW_COPY = False
+    counters, wall = {}, {}
+
+    def step(device_resident):
+        C = api.C
+        w = wall.setdefault("device" if device_resident else "host", {"for_reads": 0.0, "for_bucket": 0.0, "combine": 0.0, "realign": 0.0})
+        t = time.perf_counter()
+        rr = api._ReadsResult()
+        if device_resident:
+            ctx._check(ctx.lib.mcb_for_reads_device(ctx._h, rows_dev.data_ptr(), n, C.byref(rr)))
+        else:
+            ctx._check(ctx.lib.mcb_for_reads(ctx._h, rows_pinned.data_ptr(), n, C.byref(rr)))
+        w["for_reads"] += time.perf_counter() - t
+        t = time.perf_counter()
+        br = api._BucketResult()
+        ctx._check(ctx.lib.mcb_for_bucket_keep(ctx._h, C.byref(br)))
+        w["for_bucket"] += time.perf_counter() - t
+        t = time.perf_counter()
+        cr = api._CombineResult()
+        ctx._check(ctx.lib.mcb_combine(ctx._h, cbthr, C.byref(cr)))
+        nc = int(cr.n_clusters)
+        mem = int(C.cast(cr.cl_a_off, C.POINTER(C.c_uint64))[nc]) if nc else 0
+        ref_bytes = int(C.cast(cr.cl_ref_off, C.POINTER(C.c_uint64))[nc]) if nc else 0
+        w["combine"] += time.perf_counter() - t
+        t = time.perf_counter()
+        rounds = []
+        for sg, nc_rec, thr, ms, nd in rounds_in:
+            r = api._RealignResult()
+            ctx._check(ctx.lib.mcb_realign(ctx._h, sg.ctypes.data, len(sg), None, None, nc, thr, ms, nd, C.byref(r)))
+            rounds.append({"S": len(sg), "R": ref_bytes, "W": int(r.n_windows), "C": int(r.n_candidates), "nd": int(r.numdict), "claims": int(r.n_claims),
+                           "probes": int(r.n_probes), "polyAT": int(r.n_fpA + r.n_fpT)})
+        w["realign"] += time.perf_counter() - t
+        counters.update({"N": n, "L": L, "m": m, "n_idx": int(cr.iterations), "seed_ref_bytes": 0, "N_sk": int(br.n_sketched_total), "N_grp": int(br.n_grouped),
+                         "bucket_rounds": int(br.rounds), "clusters": int(br.n_clusters), "singles_stage1": int(br.n_sg), "contigs": nc, "merges": int(cr.n_merges),
+                         "merge_iterations": int(cr.iterations), "T_cb": int(cr.n_index_tuples), "rounds": rounds})
+        nn = int(rr.n_nreads)
+        h2d = (0 if device_resident else n * L) + sum(x[0].nbytes for x in rounds_in)
+        d2h = n + nn * (5 + ws * 8) + int(br.n_sg) * 4 + nc * (4 + 16) + mem * 8 + ref_bytes + sum(r["claims"] * 24 + r["polyAT"] * 4 for r in rounds)
+        return h2d, d2h
+
+    def metric_ms(tm):         # SURVEY.md 8(d): kt_for_reads + kt_for_bucket + all mm_idx_generation + all realign_hash
+        return sum(tm.get(k, (0.0, 0))[0] for k in ("for_reads", "for_bucket", "idx_build", "realign"))
+
+    for _ in range(args.warmup):
+        step(True)
+        step(False)
+    wall.clear()
+    ctx.timers_reset()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clk:
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            step(True)
+        torch.cuda.synchronize()
+        wall_dev_arm = time.perf_counter() - w0
+        tm = ctx.timers()
+        launches = ctx.kernel_launches()
+        ctx.timers_reset()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            h2d, d2h = step(False)
+        torch.cuda.synchronize()
+        wall_e2e = time.perf_counter() - w0
+        tm_e2e = ctx.timers()
+    ms_dev = metric_ms(tm) / args.steps
+    ms_merge = tm.get("combine", (0.0, 0))[0] / args.steps
+    ms_e2e = wall_e2e / args.steps * 1e3
+    peak, peak_src = measured_peaks()
+    kern = {k: v for k, v in tm.items() if k.startswith("k:")}
+    path_kern = {k: v for k, v in kern.items() if not k.startswith("k:cb_")}              # the merge's own kernels are outside the metric
+    dom = max(path_kern, key=lambda k: path_kern[k][0])
+    dom_ms, dom_cnt = kern[dom]
+    ab, _ = algorithmic_bytes(dom, counters)
+    if ab is None and dom in ("k:sort_scatter", "k:sort_hist"):
+        ab = 32.0 * counters["N_sk"] / max(1, dom_cnt / args.steps)
+    avg_launch_s = dom_ms / max(1, dom_cnt) / 1e3
+    achieved = (ab / avg_launch_s / 1e9) if ab else None
+    roof = {"bound": "hbm", "kernel": dom[2:], "achieved": round(achieved, 2) if achieved else None, "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 5) if achieved else None, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ab, "avg_launch_ms": dom_ms / max(1, dom_cnt), "share_of_device_time": round(dom_ms / max(1e-9, metric_ms(tm)), 4)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            roof["traffic"] = json.load(f).get(dom[2:])
+    roof["issue"] = issue_roofline(dom[2:], args.workload, avg_launch_s, torch.cuda.get_device_properties(local).multi_processor_count, clk.summary().get("sm_mhz"))
+    cpu = cpu_baseline(args.workload, 1, quiet=True) if not args.no_cpu_baseline else None
+    value = n / (ms_dev / 1e3)
+    line = {
+        "metric": "reads/sec for sketch+index+overlap stage", "value": round(value, 1), "unit": "reads/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_dev, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n} x {L} bp reads, {G} bp random genome, 1% substitutions, mode {mode}, {opts_text(ref_env)}",
+                   "step": "kt_for_reads, kt_for_bucket, combine_cluster on the device (all mm_idx_generation calls inside it), every realign_hash of the schedule; "
+                           "seed contigs, index tuples, indexes and merged contigs never leave the device",
+                   "l2": "inputs larger than L2 (reads %.0f MB per step)" % (n * L / 1e6),
+                   "timing": "value = CUDA-event device time of kt_for_reads + kt_for_bucket + all index builds + all realign_hash rounds (SURVEY 8d: the contig merge is not part of the metric; "
+                             "its device time is merge_ms_per_step and value_with_merge includes it), reads resident in HBM; e2e = wall clock of the whole step, merge included, through the host-buffer C-ABI",
+                   "bases_per_s": round(value * L, 1), "merge_ms_per_step": round(ms_merge, 4), "value_with_merge": round(n / ((ms_dev + ms_merge) / 1e3), 1),
+                   "wall_ms_per_step_device_arm": round(wall_dev_arm / args.steps * 1e3, 3),
+                   "counters": {k: v for k, v in counters.items() if k != "rounds"}, "realign_rounds": counters["rounds"],
+                   "device_ms_by_entry_point": {k: round(tm[k][0] / args.steps, 4) for k in ("for_reads", "for_bucket", "idx_build", "combine", "realign") if k in tm},
+                   "kernel_ms_per_step": {k[2:]: round(v[0] / args.steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])},
+                   "host_wall_ms_per_step": {a: {k: round(v / args.steps * 1e3, 3) for k, v in d.items()} for a, d in wall.items()},
+                   "dropin_run_s": {"front_end": round(front_end_seconds(dt), 3), "contig_merge": round(dt.get("combine_cluster", 0), 3), "whole_program": round(dt["wall_total"], 1)},
+                   "host_threads": threads},
+        "e2e": {"value": round(n / (ms_e2e / 1e3), 1), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e, 3),
+                "copy_ms_per_step": {k: round(tm_e2e[k][0] / args.steps, 3) for k in ("h2d", "d2h") if k in tm_e2e},
+                "note": "wall clock of the whole step including the contig merge, which the metric (and the reference arm's figure) leaves out"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "parity": par,
+    }
+    emit(line)
+    ctx.close()
+
+
 def parity_step(ctx, args, params, rows, idx_calls, realign_calls, same_contigs, rec_threads):
     """One untimed pass of the step through the copying API; every result is digested (minicom_b200/parity.py) and compared with the
     manifest of the single-threaded reference for this workload."""
@@ -513,7 +717,7 @@ def bench_sharded(args):
     if rank == 0:
         os.makedirs(rec)
         log(f"[rank 0] job: {n_total} x {L} bp over {world} GPUs, inputs ready in {time.time() - t0:.1f}s; one untimed drop-in run records the call sequence")
-        dt = run_binary(exe, fq, wd, dict(ref_env, MCB_RECORD=rec, MCB_DEVICE=local), threads)
+        dt = run_binary(exe, fq, wd, dict(ref_env, MCB_RECORD=rec, MCB_DEVICE=local, MCB_HOST_MERGE=1), threads)     # host merge: its mm_idx_generation calls are what the ranks replay
         os.remove(fq)
         log(f"[rank 0] drop-in run: front end {front_end_seconds(dt):.3f}s inside the entry points; whole program {dt['wall_total']:.1f}s")
     dist.barrier()
@@ -791,6 +995,7 @@ def main():
     ap.add_argument("--record-threads", type=int, default=0, help="num_thr of the untimed recording run at N=1 (default 1: deterministic, manifest parity applies)")
     ap.add_argument("--ref-steps", type=int, default=1, help="--impl reference: cap on the timed steps (one step of C2 is minutes of CPU)")
     ap.add_argument("--ref-sample", action="store_true", help="--impl reference: time the bounded sample instead of the full workload")
+    ap.add_argument("--replay", action="store_true", help="N = 1: replay the host merger's recorded mm_idx_generation / realign_hash calls (contig merge on the host, num_thr=1 recording) instead of the device-resident pipeline")
     ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent single-GPU jobs instead of one sharded job")
     args = ap.parse_args()
     claim_stdout()
@@ -798,8 +1003,10 @@ def main():
         bench_reference(args)
     elif int(os.environ.get("WORLD_SIZE", 1)) > 1 and not args.replicas:
         bench_sharded(args)
-    else:
+    elif args.replay or int(os.environ.get("WORLD_SIZE", 1)) > 1:
         bench_ours(args)
+    else:
+        bench_pipeline(args)
 
 
 if __name__ == "__main__":

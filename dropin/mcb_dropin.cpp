@@ -38,6 +38,7 @@ static mcb_group *g_grp = 0;    // MCB_DEVICES=0,1,...: the same calls over seve
 static double g_wall[4];      // for_reads, for_bucket, idx_build, realign (host wall seconds inside the entry points)
 static int g_calls[4];
 static double g_wall_combine = 0;   // combine_cluster (the contig merge)
+static bool g_contigs_on_device = false;   // the device merge handed its contigs to Stage 2: realign_hash need not ship them
 static std::string g_realign_detail;
 
 // MCB_RECORD=<dir>: write the host-side inputs of every mm_idx_generation / realign_hash call as flat little-endian
@@ -159,10 +160,12 @@ void kt_for_bucket(int n_threads_, reads_t *r, long n)
 	double t0 = realtime();
 	mcb_ctx *ctx = ctx_for(r);
 	mcb_bucket_result res;
-	int rc = g_grp ? mcb_group_for_bucket(g_grp, &res) : mcb_for_bucket(ctx, &res);
+	// with the contig merge on the device (the default on one GPU) the host never looks at the seed contigs: only the singles come back
+	const bool keep = !g_grp && !getenv("MCB_HOST_MERGE");
+	int rc = g_grp ? mcb_group_for_bucket(g_grp, &res) : keep ? mcb_for_bucket_keep(ctx, &res) : mcb_for_bucket(ctx, &res);
 	if (rc) die("kt_for_bucket", rc);
 	cluster_v *cv = &r->clusters[0][0];
-	for (uint64_t c = 0; c < res.n_clusters; ++c) {
+	for (uint64_t c = 0; c < (keep ? 0 : res.n_clusters); ++c) {
 		cluster_t *p;
 		kv_pushp(cluster_t, *cv, &p);
 		kv_init(*p);
@@ -176,7 +179,7 @@ void kt_for_bucket(int n_threads_, reads_t *r, long n)
 	}
 	for (uint64_t i = 0; i < res.n_sg; ++i) kv_push(uint32_t, r->sg, res.sg[i]);
 	const int mask = (1 << r->b) - 1, m = first_mininum;
-	for (uint64_t c = 0; c < res.n_clusters; ++c)
+	for (uint64_t c = 0; c < (keep ? 0 : res.n_clusters); ++c)
 		for (int j = 0; j < res.mi_cnt[c]; ++j) {
 			const mcb_tuple *t = &res.mi[c * m + j];
 			mm128_t v; v.x = t->x; v.y = t->y;
@@ -225,6 +228,7 @@ void combine_cluster(int n_threads_, reads_t *r, int *index_)
 	mm_idx_destroy(r->mi[index]);                              // the index objects the host loop would have gone through (:585,:628)
 	r->mi[index] = 0;
 	*index_ = idxv;
+	g_contigs_on_device = true;
 	g_wall_combine += realtime() - t0;
 }
 
@@ -327,7 +331,7 @@ void realign_hash(int n_threads_, reads_t *r, int index, int max_threshold)
 		sig[2] = ((h[0] ^ tail) * 0x9E3779B97F4A7C15ull) ^ (h[1] * 3) ^ (h[2] * 5) ^ (h[3] * 7);
 		for (size_t c = 0; c < off.size(); ++c) sig[2] = (sig[2] ^ off[c]) * 0x9E3779B97F4A7C15ull;
 	}
-	const bool same = g_calls[3] > 0 && !memcmp(sig, sent_sig, sizeof sig) && !getenv("MCB_RESEND_CONTIGS");
+	const bool same = ((g_calls[3] > 0 && !memcmp(sig, sent_sig, sizeof sig)) || (g_calls[3] == 0 && g_contigs_on_device)) && !getenv("MCB_RESEND_CONTIGS");
 	mcb_realign_result res;
 	const char *rp = same ? NULL : refs.data();
 	const uint64_t *op = same ? NULL : off.data();

@@ -139,6 +139,9 @@ typedef struct {
 } mcb_bucket_result;
 
 int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res);
+/* Same for a caller that continues with mcb_combine on this context: the seed contigs and their index tuples stay on the device;
+ * only n_clusters, the singles (n_sg, sg) and the counters of *res are filled, the other pointers are NULL. */
+int mcb_for_bucket_keep(mcb_ctx *ctx, mcb_bucket_result *res);
 
 /* kt_for_bucket's loop control (kthread_bucket.c:584-585,594,607-622), for callers that drive the rounds themselves:
  *   is_last = mcb_round_control_begin(&rc, k, max_rounds);  ... one round ...;  stop = mcb_round_control_end(&rc, members so far) */
@@ -183,6 +186,7 @@ typedef struct {
 	const char     *cl_ref;      /* consensus strings, concatenated, no terminators */
 	int32_t iterations;          /* iterations of the loop at :573-627 = mm_idx_generation calls made (idxv = iterations & 1) */
 	uint64_t n_merges;           /* pairs merged over all iterations */
+	uint64_t n_index_tuples;     /* tuples indexed over all iterations (T_cb of the roofline formula) */
 } mcb_combine_result;
 
 /* Runs on the seed contigs mcb_for_bucket left on the device (call it right after mcb_for_bucket, same context): per iteration

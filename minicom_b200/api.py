@@ -42,7 +42,7 @@ class _BucketResult(C.Structure):
 
 class _CombineResult(C.Structure):
     _fields_ = [("n_clusters", C.c_uint64), ("cl_n", C.c_void_p), ("cl_a_off", C.c_void_p), ("cl_a", C.c_void_p), ("cl_ref_off", C.c_void_p),
-                ("cl_ref", C.c_void_p), ("iterations", C.c_int32), ("n_merges", C.c_uint64)]
+                ("cl_ref", C.c_void_p), ("iterations", C.c_int32), ("n_merges", C.c_uint64), ("n_index_tuples", C.c_uint64)]
 
 
 class _RealignResult(C.Structure):
@@ -56,7 +56,7 @@ EXPORTS = [
     "mcb_resolve_params", "mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version",
     "mcb_for_reads", "mcb_for_reads_ptrs", "mcb_for_reads_device",
     "mcb_debug_read_tuples", "mcb_debug_sketch_two", "mcb_debug_unpack_reads",
-    "mcb_for_bucket", "mcb_idx_build", "mcb_idx_build_scattered", "mcb_idx_get", "mcb_idx_destroy", "mcb_idx_stats", "mcb_idx_arrays",
+    "mcb_for_bucket", "mcb_for_bucket_keep", "mcb_idx_build", "mcb_idx_build_scattered", "mcb_idx_get", "mcb_idx_destroy", "mcb_idx_stats", "mcb_idx_arrays",
     "mcb_combine", "mcb_realign", "mcb_sketch_lh_host", "mcb_sketch_two_host", "mcb_hash64",
     "mcb_timers_enable", "mcb_timers_reset", "mcb_timer_get", "mcb_timers_dump", "mcb_kernel_launches",
     "mcb_round_control_init", "mcb_round_control_begin", "mcb_round_control_end",
@@ -96,6 +96,7 @@ def load_library() -> C.CDLL:
     lib.mcb_debug_sketch_two.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     lib.mcb_debug_unpack_reads.argtypes = [C.c_void_p, C.c_void_p]
     lib.mcb_for_bucket.argtypes = [C.c_void_p, C.POINTER(_BucketResult)]
+    lib.mcb_for_bucket_keep.argtypes = [C.c_void_p, C.POINTER(_BucketResult)]
     lib.mcb_idx_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.mcb_idx_build_scattered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.mcb_idx_get.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]

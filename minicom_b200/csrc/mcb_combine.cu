@@ -43,6 +43,7 @@ struct McbCombineState {
 		for (auto b : h) b->release();
 	}
 };
+int mcb_realign_prime_contigs(mcb_ctx *ctx, const char *d_refs, const uint64_t *h_ref_off, uint64_t n_contigs);     // mcb_stage2.cu
 void mcb_combine_release(mcb_ctx *ctx) { if (ctx->cb) { ctx->cb->release(); delete ctx->cb; ctx->cb = nullptr; } }
 
 // ---------------------------------------------------------------- 1: tuples of the current set, in push order
@@ -292,7 +293,7 @@ static int cb_first_m(mcb_ctx *ctx, CbSet &S)
 	return MCB_OK;
 }
 
-static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSet &nxt, int cbthr, uint64_t *n_merged)
+static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSet &nxt, int cbthr, uint64_t *n_merged, uint64_t *n_tuples)
 {
 	const int L = ctx->L, WS = ctx->WS, m = ctx->prm.first_mininum, nb = 1 << ctx->prm.b, rw = ctx->prm.rw, k = ctx->prm.k;
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
@@ -307,6 +308,7 @@ static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSe
 		MCB_LAUNCH(ctx, "cb_widen", k_cb_widen_u8, mcb_grid_for(ncl, 256), 256, 0, cur.micnt.as<uint8_t>(), ncl, cb.tmp32.as<uint32_t>());
 		MCB_TRY(mcb_exclusive_scan_u32(ctx, cb.tmp32.as<uint32_t>(), ncl, (uint64_t*)&dc[CT_CB_A]));
 		MCB_TRY(cb_counter(ctx, CT_CB_A, &T));
+		*n_tuples = T;
 		MCB_TRY(cb.tup.ensure(T * 16 + 16)); MCB_TRY(cb.tup2.ensure(T * 16 + 16)); MCB_TRY(cb.boff.ensure(((size_t)nb + 2) * 8)); MCB_TRY(cb.h_boff.ensure(((size_t)nb + 2) * 8));
 		MCB_LAUNCH(ctx, "cb_gather_tuples", k_cb_gather_tuples, mcb_grid_for(ncl * m, 256), 256, 0, cur.mi.as<mcb_tuple>(), cur.micnt.as<uint8_t>(), cb.tmp32.as<uint32_t>(), ncl, m, cb.tup.as<ulonglong2>());
 		McbSortPass bp[2] = { {0, 0, 7}, {0, 7, 7} };        // stable by bucket: inside a bucket the tuples keep their push order
@@ -473,11 +475,11 @@ extern "C" int mcb_combine(mcb_ctx *ctx, int cbthreshold, mcb_combine_result *re
 	}
 	int cur = 0, iterations = 0;
 	long pre_tot = 0;
-	uint64_t merges_total = 0;
+	uint64_t merges_total = 0, tuples_total = 0;
 	for (;;) {
-		uint64_t nm = 0;
-		MCB_TRY(combine_iteration(ctx, cb, cb.set[cur], cb.set[cur ^ 1], cbthreshold, &nm));
-		cur ^= 1; ++iterations; merges_total += nm;
+		uint64_t nm = 0, nt = 0;
+		MCB_TRY(combine_iteration(ctx, cb, cb.set[cur], cb.set[cur ^ 1], cbthreshold, &nm, &nt));
+		cur ^= 1; ++iterations; merges_total += nm; tuples_total += nt;
 		const long tot = (long)cb.set[cur].ncl;
 		if (labs(pre_tot - tot) < 100) break;                      // kthread_cb.c:625
 		pre_tot = tot;
@@ -497,9 +499,12 @@ extern "C" int mcb_combine(mcb_ctx *ctx, int cbthreshold, mcb_combine_result *re
 		} else { cb.h_cl_a_off.as<uint64_t>()[0] = 0; cb.h_cl_ref_off.as<uint64_t>()[0] = 0; }
 	}
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	// the merged contigs are what realign_hash runs against (preprocess.c:197-232): Stage 2 takes them from the device
+	MCB_TRY(mcb_realign_prime_contigs(ctx, F.ref.as<char>(), cb.h_cl_ref_off.as<uint64_t>(), F.ncl));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->tm.collect();
 	res->n_clusters = F.ncl; res->cl_n = cb.h_cl_n.as<uint32_t>(); res->cl_a_off = cb.h_cl_a_off.as<uint64_t>(); res->cl_a = cb.h_cl_a.as<uint64_t>();
 	res->cl_ref_off = cb.h_cl_ref_off.as<uint64_t>(); res->cl_ref = cb.h_cl_ref.as<char>();
-	res->iterations = iterations; res->n_merges = merges_total;
+	res->iterations = iterations; res->n_merges = merges_total; res->n_index_tuples = tuples_total;
 	return MCB_OK;
 }

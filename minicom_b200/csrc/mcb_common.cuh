@@ -212,6 +212,7 @@ struct mcb_ctx {
 	HBuf h_coll;
 	uint64_t elem_cap = 0;               // capacity (elements) of d_elemA / d_elemB
 	bool reads_loaded = false, bucket_done = false;
+	bool seed_results_on_device_only = false;   // mcb_for_bucket_keep
 	McbBucketState bs;
 	McbRealignState rs;
 	DBuf d_ascii;                        // N*L bytes (kept until the N masks are extracted)

@@ -1171,12 +1171,15 @@ int mcb_bucket_finish_impl(mcb_ctx *ctx, mcb_bucket_result *res, uint64_t *round
 	if (hc[CT_DEGENERATE]) { mcb_set_error("%llu re-sketched reads have no valid k-mer", hc[CT_DEGENERATE]); return MCB_EINPUT; }
 	const uint64_t tot_cl = bs.tot_cl, tot_mem = bs.tot_mem, tot_ref = bs.tot_ref, tot_sg = bs.tot_sg;
 	// ---- results to the host
-	MCB_TRY(ctx->h_cl_n.ensure(tot_cl * 4 + 16)); MCB_TRY(ctx->h_cl_a_off.ensure((tot_cl + 1) * 8)); MCB_TRY(ctx->h_cl_ref_off.ensure((tot_cl + 1) * 8));
-	MCB_TRY(ctx->h_cl_a.ensure(tot_mem * 8 + 16)); MCB_TRY(ctx->h_cl_ref.ensure(tot_ref + 16)); MCB_TRY(ctx->h_sg.ensure(tot_sg * 4 + 16));
-	MCB_TRY(ctx->h_mi.ensure(tot_cl * m * 16 + 16)); MCB_TRY(ctx->h_mi_cnt.ensure(tot_cl + 16));
+	MCB_TRY(ctx->h_sg.ensure(tot_sg * 4 + 16)); MCB_TRY(ctx->h_cl_a_off.ensure(16)); MCB_TRY(ctx->h_cl_ref_off.ensure(16));
+	if (!ctx->seed_results_on_device_only) {
+		MCB_TRY(ctx->h_cl_n.ensure(tot_cl * 4 + 16)); MCB_TRY(ctx->h_cl_a_off.ensure((tot_cl + 1) * 8)); MCB_TRY(ctx->h_cl_ref_off.ensure((tot_cl + 1) * 8));
+		MCB_TRY(ctx->h_cl_a.ensure(tot_mem * 8 + 16)); MCB_TRY(ctx->h_cl_ref.ensure(tot_ref + 16));
+		MCB_TRY(ctx->h_mi.ensure(tot_cl * m * 16 + 16)); MCB_TRY(ctx->h_mi_cnt.ensure(tot_cl + 16));
+	}
 	{
 		McbSpan sp(ctx->tm, "d2h");
-		if (tot_cl) {
+		if (tot_cl && !ctx->seed_results_on_device_only) {
 			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_n.p, B.d_cl_n.p, tot_cl * 4, cudaMemcpyDeviceToHost, ctx->stream));
 			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_a_off.p, B.d_cl_aoff.p, (tot_cl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
 			MCB_CUDA(cudaMemcpyAsync(ctx->h_cl_ref_off.p, B.d_cl_roff.p, (tot_cl + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1191,8 +1194,9 @@ int mcb_bucket_finish_impl(mcb_ctx *ctx, mcb_bucket_result *res, uint64_t *round
 	ctx->tm.collect();
 	res->n_clusters = tot_cl; res->cl_n = ctx->h_cl_n.as<uint32_t>(); res->cl_a_off = ctx->h_cl_a_off.as<uint64_t>(); res->cl_a = ctx->h_cl_a.as<uint64_t>();
 	res->cl_ref_off = ctx->h_cl_ref_off.as<uint64_t>(); res->cl_ref = ctx->h_cl_ref.as<char>();
+	if (ctx->seed_results_on_device_only) { res->cl_n = nullptr; res->cl_a_off = nullptr; res->cl_a = nullptr; res->cl_ref_off = nullptr; res->cl_ref = nullptr; }
 	res->n_sg = tot_sg; res->sg = ctx->h_sg.as<uint32_t>();
-	res->mi_cnt = ctx->h_mi_cnt.as<uint8_t>(); res->mi = ctx->h_mi.as<mcb_tuple>();
+	res->mi_cnt = ctx->seed_results_on_device_only ? nullptr : ctx->h_mi_cnt.as<uint8_t>(); res->mi = ctx->seed_results_on_device_only ? nullptr : ctx->h_mi.as<mcb_tuple>();
 	res->rounds = bs.r; res->n_sketched_total = bs.tot_sk; res->n_grouped = tot_mem;
 	bs.active = false;
 	ctx->bucket_done = true;
@@ -1214,6 +1218,17 @@ extern "C" int mcb_round_control_end(mcb_round_control *rc, uint64_t members_tot
 	if ((long long)members_total - rc->pre_members < 100) ++rc->last_rounds;
 	rc->pre_members = (long long)members_total;
 	return rc->last_rounds > 1 ? 1 : 0;                // stop
+}
+
+// kt_for_bucket for a caller that goes on with mcb_combine: the seed contigs and their index tuples stay on the device, only the
+// singles (and the counts) come back; the array pointers of *res other than sg are NULL
+extern "C" int mcb_for_bucket_keep(mcb_ctx *ctx, mcb_bucket_result *res)
+{
+	if (!ctx) { mcb_set_error("null context"); return MCB_EINVAL; }
+	ctx->seed_results_on_device_only = true;
+	const int rc = mcb_for_bucket(ctx, res);
+	ctx->seed_results_on_device_only = false;
+	return rc;
 }
 
 extern "C" int mcb_for_bucket(mcb_ctx *ctx, mcb_bucket_result *res)

@@ -596,7 +596,8 @@ __global__ void k_s2_claim_emit(const ulonglong2 *__restrict__ el, uint64_t n, c
 
 // ================================================================= host
 // Upload the contigs and (re)build the lt-mer table unless the cached one was built from identical contigs.
-static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int lt)
+// d_refs != null: the strings are already on the device (the contig merge just made them): copied device to device, never compared.
+static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *ref_off, uint64_t n_contigs, int lt, const char *d_refs = nullptr)
 {
 	McbContigIndex &cx = ctx->cix;
 	const int L = ctx->L;
@@ -633,12 +634,16 @@ static int contig_index_update(mcb_ctx *ctx, const char *refs, const uint64_t *r
 			b_hi = std::min(ref_off[c1] + (w_end - cwo[c1]) * 32, ref_off[c1 + 1]);
 		} else b_lo = b_hi = 0;
 	}
-	const bool maybe_same = !sharded && cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L;
+	const bool maybe_same = !sharded && !d_refs && cx.valid && cx.n_contigs == n_contigs && cx.ref_bytes == ref_bytes && cx.lt == lt && cx.L == L;
 	DBuf &stage_refs = maybe_same ? ctx->d_scr[1] : cx.refs, &stage_off = maybe_same ? ctx->d_scr[2] : cx.roff;
 	const size_t refs_pad = (ref_bytes + 7) & ~(size_t)7;
 	MCB_TRY(stage_refs.ensure(refs_pad + 16)); MCB_TRY(stage_off.ensure((n_contigs + 1) * 8));
 	cx.valid = cx.valid && maybe_same;
-	{   // the contig strings go up on the copy stream: the singles kernels already queued on the compute stream run meanwhile
+	if (d_refs) {
+		if (ref_bytes) MCB_CUDA(cudaMemcpyAsync(stage_refs.p, d_refs, ref_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+		if (refs_pad > ref_bytes) MCB_CUDA(cudaMemsetAsync(stage_refs.as<char>() + ref_bytes, 0, refs_pad - ref_bytes, ctx->stream));
+		MCB_CUDA(cudaMemcpyAsync(stage_off.p, ref_off, (n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	} else {   // the contig strings go up on the copy stream: the singles kernels already queued on the compute stream run meanwhile
 		MCB_TRY(mcb_copy_streams(ctx));
 		struct EvPair {                   // destroyed on every exit path
 			cudaEvent_t a = nullptr, b = nullptr;
@@ -1105,4 +1110,12 @@ extern "C" int mcb_shard_realign(mcb_ctx *ctx, const uint32_t *sg, const uint32_
 	MCB_CUDA(cudaSetDevice(ctx->prm.device));
 	MCB_TRY(realign_search(ctx, sg, ctx->shard_n > 1 ? sg_index : (sg_index ? sg_index : nullptr), n_sg_local, n_sg_total, refs, ref_off, n_contigs, threshold, maxsearch, ininumdict, res));
 	return realign_claims(ctx, res);
+}
+
+// The contig merge hands its result straight to Stage 2: the next mcb_realign calls with refs == NULL use these contigs.
+int mcb_realign_prime_contigs(mcb_ctx *ctx, const char *d_refs, const uint64_t *h_ref_off, uint64_t n_contigs)
+{
+	const int lt = ctx->L <= 80 ? 11 : 17;               // realign_geometry
+	if (ctx->shard_n > 1) return MCB_OK;
+	return contig_index_update(ctx, nullptr, h_ref_off, n_contigs, lt, d_refs);
 }
