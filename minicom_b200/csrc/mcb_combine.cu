@@ -25,19 +25,21 @@
 #include <limits.h>
 
 struct CbSet {                       // one contig set on the device
-	DBuf n, aoff, a, roff, ref, mi, micnt;
-	uint64_t ncl = 0, nmem = 0, nref = 0;
-	void release() { n.release(); aoff.release(); a.release(); roff.release(); ref.release(); mi.release(); micnt.release(); }
+	DBuf n, aoff, a, roff, ref;
+	DBuf mins, moff;                   // ALL (w,k)-minimizers of every contig, contig-major in position order; moff u64[ncl+1].  The first
+	                                   // first_mininum of a contig's list are its index tuples (kthread_cb.c:359-368: the same sketch, cut short)
+	uint64_t ncl = 0, nmem = 0, nref = 0, nmin = 0;
+	void release() { n.release(); aoff.release(); a.release(); roff.release(); ref.release(); mins.release(); moff.release(); }
 };
 struct McbCombineState {
 	CbSet set[2];
-	DBuf tup, tup2, boff, moff, mins, pcnt, cand, pass, plist, loff, cw, cwo, flag, pairs, src, keyA, keyB, len2, tmp32;
+	DBuf tup, tup2, boff, pcnt, cand, pass, plist, loff, cw, cwo, flag, pairs, src, keyA, keyB, len2, tmp32;
 	HBuf h_boff, h_list, h_loff, h_pairs, h_flag, h_small;
 	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref;
 	void release()
 	{
 		set[0].release(); set[1].release();
-		DBuf *d[] = { &tup, &tup2, &boff, &moff, &mins, &pcnt, &cand, &pass, &plist, &loff, &cw, &cwo, &flag, &pairs, &src, &keyA, &keyB, &len2, &tmp32 };
+		DBuf *d[] = { &tup, &tup2, &boff, &pcnt, &cand, &pass, &plist, &loff, &cw, &cwo, &flag, &pairs, &src, &keyA, &keyB, &len2, &tmp32 };
 		for (auto b : d) b->release();
 		HBuf *h[] = { &h_boff, &h_list, &h_loff, &h_pairs, &h_flag, &h_small, &h_cl_n, &h_cl_a_off, &h_cl_a, &h_cl_ref_off, &h_cl_ref };
 		for (auto b : h) b->release();
@@ -47,18 +49,35 @@ int mcb_realign_prime_contigs(mcb_ctx *ctx, const char *d_refs, const uint64_t *
 void mcb_combine_release(mcb_ctx *ctx) { if (ctx->cb) { ctx->cb->release(); delete ctx->cb; ctx->cb = nullptr; } }
 
 // ---------------------------------------------------------------- 1: tuples of the current set, in push order
-__global__ void k_cb_widen_u8(const uint8_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out)
+__global__ void k_cb_first_m_counts(const uint64_t *__restrict__ moff, uint64_t ncl, int m, uint32_t *__restrict__ out)
 {
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) out[i] = in[i];
+	const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < ncl) out[c] = (uint32_t)min((uint64_t)m, moff[c + 1] - moff[c]);
 }
-__global__ void k_cb_gather_tuples(const mcb_tuple *__restrict__ mi, const uint8_t *__restrict__ micnt, const uint32_t *__restrict__ off, uint64_t ncl, int m, ulonglong2 *__restrict__ out)
+__global__ void k_cb_gather_tuples(const mcb_tuple *__restrict__ mins, const uint64_t *__restrict__ moff, const uint32_t *__restrict__ off, uint64_t ncl, int m, ulonglong2 *__restrict__ out)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= ncl * (uint64_t)m) return;
-	const uint64_t c = i / m; const int j = (int)(i - c * m);
-	if (j < micnt[c]) { const mcb_tuple t = mi[i]; out[off[c] + j] = make_ulonglong2(t.x, t.y); }
+	const uint64_t c = i / m, j = i - c * m, b = moff[c];
+	if (b + j < moff[c + 1]) { const mcb_tuple t = mins[b + j]; out[off[c] + j] = make_ulonglong2(t.x, t.y); }
 }
+// minimizer lists of the untouched contigs move to the new set with their new contig id
+__global__ void k_cb_copy_min_counts(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ moff, uint32_t *__restrict__ cnt2)
+{
+	const uint64_t q = nm + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q < n2) { const uint32_t s = src[q - nm]; cnt2[q] = (uint32_t)(moff[s + 1] - moff[s]); }
+}
+__global__ void k_cb_copy_mins(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ moff, const mcb_tuple *__restrict__ mins,
+                               const uint64_t *__restrict__ moff2, mcb_tuple *__restrict__ mins2)
+{
+	const uint64_t q = nm + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3);           // eight lanes per contig
+	const int lane = threadIdx.x & 7;
+	if (q >= n2) return;
+	const uint32_t s = src[q - nm];
+	const uint64_t b = moff[s], cnt = moff[s + 1] - b, o = moff2[q];
+	for (uint64_t u = lane; u < cnt; u += 8) { mcb_tuple t = mins[b + u]; t.y = ((q << 8) << 32) | (uint64_t)(uint32_t)t.y; mins2[o + u] = t; }
+}
+
 __global__ void k_cb_bucket_bounds(const ulonglong2 *__restrict__ t, uint64_t n, int nb, uint64_t *__restrict__ boff)
 {
 	const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,6 +191,17 @@ __global__ void k_cb_list_bounds(const CbCand *__restrict__ list, uint64_t P, ui
 	loff[c] = (uint32_t)lo;
 }
 
+// a partner that already appears earlier in the same contig's list can never be the pick (if it is free the earlier entry takes it)
+__global__ void k_cb_dedupe(const CbCand *__restrict__ list, uint64_t P, uint32_t *__restrict__ keep)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= P) return;
+	const CbCand r = list[e];
+	uint32_t k = 1;
+	for (uint64_t f = e; f-- > 0 && list[f].i == r.i;) if (list[f].c == r.c) { k = 0; break; }
+	keep[e] = k;
+}
+
 // ---------------------------------------------------------------- 5: the new contig set
 // new contig q < nm is the merge pairs[q] = (i, c, pos_ori, pos); q >= nm is the copy of old contig src[q - nm]
 __global__ void k_cb_new_sizes(const CbCand *__restrict__ pairs, uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint32_t *__restrict__ cl_n, uint32_t *__restrict__ n_new)
@@ -220,12 +250,17 @@ __global__ void k_cb_unkey(const ulonglong2 *__restrict__ keyed, uint64_t n, uin
 }
 // consensus lengths: a merged contig ends with its right-most member (members sorted by position), a copy keeps its length
 __global__ void k_cb_new_lengths(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ aoff2, const uint64_t *__restrict__ a2,
-                                 const uint64_t *__restrict__ roff, int L, uint64_t *__restrict__ len2)
+                                 const uint64_t *__restrict__ roff, int L, uint64_t *__restrict__ len2, unsigned long long *__restrict__ max_len)
 {
 	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= n2) return;
-	if (q < nm) len2[q] = (uint64_t)((uint32_t)a2[aoff2[q + 1] - 1] >> 1) + (uint64_t)L;
-	else { const uint32_t s = src[q - nm]; len2[q] = roff[s + 1] - roff[s]; }
+	unsigned long long len = 0;
+	if (q < n2) {
+		if (q < nm) len = (uint64_t)((uint32_t)a2[aoff2[q + 1] - 1] >> 1) + (uint64_t)L;
+		else { const uint32_t s = src[q - nm]; len = roff[s + 1] - roff[s]; }
+		len2[q] = len;
+	}
+	for (int o = 16; o; o >>= 1) len = max(len, __shfl_xor_sync(0xFFFFFFFFu, len, o));
+	if ((threadIdx.x & 31) == 0 && len) atomicMax(max_len, len);
 }
 // construct_ref2 (kthread_cb.c:105-150): one thread per column of a merged contig counts the bases the oriented members put there;
 // 'A' unless a base has strictly more votes, in the order A, C, G, T.  Members are sorted by position, so the ones covering a
@@ -270,105 +305,121 @@ __global__ void k_cb_copy_refs(uint64_t nm, const uint32_t *__restrict__ src, ui
 }
 
 // ================================================================= host
-static int cb_counter(mcb_ctx *ctx, int slot, uint64_t *out)          // one device scalar to the host (synchronizes)
+static int cb_counters(mcb_ctx *ctx)          // the device scalars to the host (synchronizes)
 {
 	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-	*out = ctx->h_counters.as<unsigned long long>()[slot];
 	return MCB_OK;
 }
-enum { CT_CB_A = 48, CT_CB_B = 49, CT_CB_C = 50, CT_CB_D = 51 };          // scratch slots of ctx->d_counters (32..41 are the consensus work lists)
+enum { CT_CB_A = 48, CT_CB_B = 49, CT_CB_C = 50, CT_CB_D = 51, CT_CB_E = 52 };          // scratch slots of ctx->d_counters (32..41 are the consensus work lists)
+#define CB_HC(ctx, slot) ((ctx)->h_counters.as<unsigned long long>()[slot])
 
-// first-m minimizers of every contig of a set (kthread_cb.c:365,:418; kthread_bucket.c:458 for the seeds)
-static int cb_first_m(mcb_ctx *ctx, CbSet &S)
+// all (w,k)-minimizers (mm_sketch_lh_ori, sketch.c:116-165; window rw, kthread_cb.c:234 / :359 with win_step = 0) of the contigs
+// [0, count) of a set, appended to S.mins behind `first_slot` entries; cnt32[c] receives the list lengths, moff must hold the
+// offsets of these contigs already when emit is set
+static int cb_sketch(mcb_ctx *ctx, CbSet &S, uint64_t count, uint32_t *cnt32, bool emit)
 {
-	const int rw = ctx->prm.rw, k = ctx->prm.k, m = ctx->prm.first_mininum;
-	MCB_TRY(S.mi.ensure(S.ncl * m * 16 + 16)); MCB_TRY(S.micnt.ensure(S.ncl + 16));
-	if (!S.ncl) return MCB_OK;
+	if (!count) return MCB_OK;
+	const int rw = ctx->prm.rw, k = ctx->prm.k;
 	const size_t smem = (size_t)rw * LH_THREADS * 13;
 	auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
 	if (smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	MCB_LAUNCH(ctx, "sketch_lh", kern, mcb_grid_for(S.ncl, LH_THREADS), LH_THREADS, smem, S.ref.as<char>(), S.roff.as<uint64_t>(), (uint64_t)0, S.ncl, (uint64_t)0,
-	           rw, k, m, S.mi.as<mcb_tuple>(), S.micnt.as<uint8_t>(), (const uint64_t*)nullptr, (uint32_t*)nullptr);
+	MCB_LAUNCH(ctx, "cb_sketch", kern, mcb_grid_for(count, LH_THREADS), LH_THREADS, smem, S.ref.as<char>(), S.roff.as<uint64_t>(), (uint64_t)0, count, (uint64_t)0,
+	           rw, k, INT_MAX, emit ? S.mins.as<mcb_tuple>() : (mcb_tuple*)nullptr, (uint8_t*)nullptr, emit ? S.moff.as<uint64_t>() : (const uint64_t*)nullptr, cnt32);
 	return MCB_OK;
 }
 
-static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSet &nxt, int cbthr, uint64_t *n_merged, uint64_t *n_tuples)
+// minimizer lists of a new set: the merged contigs [0, nm) are sketched, the untouched ones take their lists along (src = old ids;
+// null with nm == ncl: sketch everything, the seed set)
+static int cb_min_lists(mcb_ctx *ctx, McbCombineState &cb, CbSet &S, uint64_t nm, const CbSet *old, const uint32_t *d_src)
 {
-	const int L = ctx->L, WS = ctx->WS, m = ctx->prm.first_mininum, nb = 1 << ctx->prm.b, rw = ctx->prm.rw, k = ctx->prm.k;
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
-	const uint64_t ncl = cur.ncl;
+	const uint64_t n2 = S.ncl;
+	MCB_TRY(cb.tmp32.ensure((n2 + 2) * 4)); MCB_TRY(S.moff.ensure((n2 + 2) * 8));
+	uint32_t *cnt = cb.tmp32.as<uint32_t>();
+	MCB_TRY(cb_sketch(ctx, S, nm, cnt, false));
+	if (n2 > nm) MCB_LAUNCH(ctx, "cb_copy_min_counts", k_cb_copy_min_counts, mcb_grid_for(n2 - nm, 256), 256, 0, nm, d_src, n2, old->moff.as<uint64_t>(), cnt);
+	MCB_TRY(mcb_exclusive_scan_u32(ctx, cnt, n2, (uint64_t*)&dc[CT_CB_A]));
+	MCB_LAUNCH(ctx, "cb_prefix64", k_cb_prefix64, mcb_grid_for(n2 + 1, 256), 256, 0, cnt, n2, S.moff.as<uint64_t>(), &dc[CT_CB_A]);
+	MCB_TRY(cb_counters(ctx));
+	S.nmin = CB_HC(ctx, CT_CB_A);
+	if (S.nmin >= 0xFFFFFFFFull) { mcb_set_error("mcb_combine: too many contig minimizers"); return MCB_EINVAL; }
+	MCB_TRY(S.mins.ensure(S.nmin * 16 + 16));
+	MCB_TRY(cb_sketch(ctx, S, nm, cnt, true));             // (cnt is rewritten with the same lengths)
+	if (n2 > nm) MCB_LAUNCH(ctx, "cb_copy_mins", k_cb_copy_mins, mcb_grid_for((n2 - nm) * 8, 256), 256, 0, nm, d_src, n2, old->moff.as<uint64_t>(), old->mins.as<mcb_tuple>(),
+	                        S.moff.as<uint64_t>(), S.mins.as<mcb_tuple>());
+	return MCB_OK;
+}
+
+static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSet &nxt, int cbthr, uint64_t *n_merged, uint64_t *n_tuples, uint64_t *max_len)
+{
+	const int L = ctx->L, WS = ctx->WS, m = ctx->prm.first_mininum, nb = 1 << ctx->prm.b;
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	const uint64_t ncl = cur.ncl, M = cur.nmin;
 	*n_merged = 0;
-	// ---- 1: index of the first-m tuples (mm_idx_generation, kthread_cb.c:574)
-	uint64_t T = 0;
+	// ---- 1: index of the first-m tuples (mm_idx_generation, kthread_cb.c:574), and meanwhile-independent preparations
+	uint64_t T = 0, total_words = 0, C = 0;
 	McbDeviceIndex ix;
+	MCB_TRY(cb.pcnt.ensure((M + 2) * 12));
+	uint32_t *pcnt = cb.pcnt.as<uint32_t>(), *pfirst = pcnt + (M + 1), *poff = pfirst + (M + 1);
 	{
 		McbSpan sp(ctx->tm, "combine");
-		MCB_TRY(cb.tmp32.ensure((ncl + 2) * 4));
-		MCB_LAUNCH(ctx, "cb_widen", k_cb_widen_u8, mcb_grid_for(ncl, 256), 256, 0, cur.micnt.as<uint8_t>(), ncl, cb.tmp32.as<uint32_t>());
+		MCB_TRY(cb.tmp32.ensure((ncl + 2) * 4)); MCB_TRY(cb.cwo.ensure((ncl + 2) * 8));
+		MCB_LAUNCH(ctx, "cb_first_m_counts", k_cb_first_m_counts, mcb_grid_for(ncl, 256), 256, 0, cur.moff.as<uint64_t>(), ncl, m, cb.tmp32.as<uint32_t>());
 		MCB_TRY(mcb_exclusive_scan_u32(ctx, cb.tmp32.as<uint32_t>(), ncl, (uint64_t*)&dc[CT_CB_A]));
-		MCB_TRY(cb_counter(ctx, CT_CB_A, &T));
+		MCB_LAUNCH(ctx, "cb_word_offsets", k_cb_word_offsets, mcb_grid_for(ncl, 256), 256, 0, cur.roff.as<uint64_t>(), ncl, cb.cwo.as<uint64_t>());
+		MCB_TRY(mcb_exclusive_scan_u64(ctx, cb.cwo.as<uint64_t>(), ncl, (uint64_t*)&dc[CT_CB_B]));
+		MCB_TRY(cb_counters(ctx));
+		T = CB_HC(ctx, CT_CB_A); total_words = CB_HC(ctx, CT_CB_B);
 		*n_tuples = T;
 		MCB_TRY(cb.tup.ensure(T * 16 + 16)); MCB_TRY(cb.tup2.ensure(T * 16 + 16)); MCB_TRY(cb.boff.ensure(((size_t)nb + 2) * 8)); MCB_TRY(cb.h_boff.ensure(((size_t)nb + 2) * 8));
-		MCB_LAUNCH(ctx, "cb_gather_tuples", k_cb_gather_tuples, mcb_grid_for(ncl * m, 256), 256, 0, cur.mi.as<mcb_tuple>(), cur.micnt.as<uint8_t>(), cb.tmp32.as<uint32_t>(), ncl, m, cb.tup.as<ulonglong2>());
+		MCB_LAUNCH(ctx, "cb_gather_tuples", k_cb_gather_tuples, mcb_grid_for(ncl * m, 256), 256, 0, cur.mins.as<mcb_tuple>(), cur.moff.as<uint64_t>(), cb.tmp32.as<uint32_t>(), ncl, m, cb.tup.as<ulonglong2>());
 		McbSortPass bp[2] = { {0, 0, 7}, {0, 7, 7} };        // stable by bucket: inside a bucket the tuples keep their push order
 		ulonglong2 *sorted = nullptr;
 		MCB_TRY(mcb_radix_sort(ctx, cb.tup.as<ulonglong2>(), cb.tup2.as<ulonglong2>(), T, bp, 2, &sorted));
 		if (sorted != cb.tup.as<ulonglong2>()) std::swap(cb.tup, cb.tup2);
 		MCB_LAUNCH(ctx, "cb_bucket_bounds", k_cb_bucket_bounds, (nb + 1 + 255) / 256, 256, 0, cb.tup.as<ulonglong2>(), T, nb, cb.boff.as<uint64_t>());
 		MCB_CUDA(cudaMemcpyAsync(cb.h_boff.p, cb.boff.p, ((size_t)nb + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		// the packed contigs do not depend on the index: queued before the host waits for the bucket bounds
+		MCB_TRY(cb.cw.ensure((total_words + 2) * 8));
+		MCB_CUDA(cudaMemsetAsync(cb.cw.as<uint64_t>() + total_words, 0, 16, ctx->stream));
+		if (total_words) MCB_LAUNCH(ctx, "cb_pack", k_cb_pack, mcb_grid_for(total_words, 256), 256, 0, cur.ref.as<char>(), cur.roff.as<uint64_t>(), cb.cwo.as<uint64_t>(), ncl, total_words, cb.cw.as<uint64_t>());
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	}
 	MCB_TRY(mcb_index_build_device(ctx, cb.tup.as<mcb_tuple>(), T, cb.boff.as<uint64_t>(), cb.h_boff.as<uint64_t>(), &ix));
 	McbSpan sp(ctx->tm, "combine");
-	// ---- 2: all minimizers of every contig (kthread_cb.c:234), count then emit
-	uint64_t M = 0;
+	// ---- 3: (minimizer, posting) pairs in visiting order, match_pro, ordered partner lists without repeats
+	uint64_t P = 0, P2 = 0;
 	{
-		const size_t smem = (size_t)rw * LH_THREADS * 13;
-		auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
-		if (smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		MCB_TRY(cb.moff.ensure((ncl + 2) * 8));
-		MCB_LAUNCH(ctx, "cb_sketch_count", kern, mcb_grid_for(ncl, LH_THREADS), LH_THREADS, smem, cur.ref.as<char>(), cur.roff.as<uint64_t>(), (uint64_t)0, ncl, (uint64_t)0,
-		           rw, k, INT_MAX, (mcb_tuple*)nullptr, (uint8_t*)nullptr, (const uint64_t*)nullptr, cb.tmp32.as<uint32_t>());
-		MCB_TRY(mcb_exclusive_scan_u32(ctx, cb.tmp32.as<uint32_t>(), ncl, (uint64_t*)&dc[CT_CB_A]));
-		MCB_LAUNCH(ctx, "cb_prefix64", k_cb_prefix64, mcb_grid_for(ncl + 1, 256), 256, 0, cb.tmp32.as<uint32_t>(), ncl, cb.moff.as<uint64_t>(), &dc[CT_CB_A]);
-		MCB_TRY(cb_counter(ctx, CT_CB_A, &M));
-		if (M >= 0xFFFFFFFFull) { mcb_set_error("mcb_combine: too many contig minimizers"); return MCB_EINVAL; }
-		MCB_TRY(cb.mins.ensure(M * 16 + 16));
-		MCB_LAUNCH(ctx, "cb_sketch_all", kern, mcb_grid_for(ncl, LH_THREADS), LH_THREADS, smem, cur.ref.as<char>(), cur.roff.as<uint64_t>(), (uint64_t)0, ncl, (uint64_t)0,
-		           rw, k, INT_MAX, cb.mins.as<mcb_tuple>(), (uint8_t*)nullptr, cb.moff.as<uint64_t>(), cb.tmp32.as<uint32_t>());
-	}
-	// ---- 3: packed contigs, (minimizer, posting) pairs in visiting order, match_pro
-	uint64_t total_words = 0, C = 0, P = 0;
-	{
-		MCB_TRY(cb.cwo.ensure((ncl + 2) * 8));
-		MCB_LAUNCH(ctx, "cb_word_offsets", k_cb_word_offsets, mcb_grid_for(ncl, 256), 256, 0, cur.roff.as<uint64_t>(), ncl, cb.cwo.as<uint64_t>());
-		MCB_TRY(mcb_exclusive_scan_u64(ctx, cb.cwo.as<uint64_t>(), ncl, (uint64_t*)&dc[CT_CB_B]));
-		MCB_TRY(cb.pcnt.ensure((M + 2) * 12));
-		uint32_t *pcnt = cb.pcnt.as<uint32_t>(), *pfirst = pcnt + (M + 1), *poff = pfirst + (M + 1);
-		if (M) MCB_LAUNCH(ctx, "cb_lookup", k_cb_lookup, mcb_grid_for(M, 256), 256, 0, cb.mins.as<mcb_tuple>(), M, ix, pcnt, pfirst);
+		if (M) MCB_LAUNCH(ctx, "cb_lookup", k_cb_lookup, mcb_grid_for(M, 256), 256, 0, cur.mins.as<mcb_tuple>(), M, ix, pcnt, pfirst);
 		MCB_CUDA(cudaMemcpyAsync(poff, pcnt, M * 4, cudaMemcpyDeviceToDevice, ctx->stream));
 		MCB_TRY(mcb_exclusive_scan_u32(ctx, poff, M, (uint64_t*)&dc[CT_CB_C]));
-		MCB_TRY(cb_counter(ctx, CT_CB_C, &C));
-		total_words = ctx->h_counters.as<unsigned long long>()[CT_CB_B];
+		MCB_TRY(cb_counters(ctx));
+		C = CB_HC(ctx, CT_CB_C);
 		if (C >= 0xFFFFFFFFull) { mcb_set_error("mcb_combine: too many (minimizer, posting) pairs"); return MCB_EINVAL; }
-		MCB_TRY(cb.cw.ensure((total_words + 2) * 8));
-		MCB_CUDA(cudaMemsetAsync(cb.cw.as<uint64_t>() + total_words, 0, 16, ctx->stream));
-		if (total_words) MCB_LAUNCH(ctx, "cb_pack", k_cb_pack, mcb_grid_for(total_words, 256), 256, 0, cur.ref.as<char>(), cur.roff.as<uint64_t>(), cb.cwo.as<uint64_t>(), ncl, total_words, cb.cw.as<uint64_t>());
 		MCB_TRY(cb.cand.ensure(C * 16 + 16)); MCB_TRY(cb.pass.ensure((C + 2) * 8));
 		uint32_t *passed = cb.pass.as<uint32_t>(), *pscan = passed + (C + 1);
-		if (M) MCB_LAUNCH(ctx, "cb_pairs", k_cb_pairs, mcb_grid_for(M, 256), 256, 0, cb.mins.as<mcb_tuple>(), M, ix, poff, pfirst, pcnt, cb.cand.as<CbCand>());
+		if (M) MCB_LAUNCH(ctx, "cb_pairs", k_cb_pairs, mcb_grid_for(M, 256), 256, 0, cur.mins.as<mcb_tuple>(), M, ix, poff, pfirst, pcnt, cb.cand.as<CbCand>());
 		if (C) MCB_LAUNCH(ctx, "cb_match", k_cb_match, mcb_grid_for(C, 256), 256, 0, cb.cand.as<CbCand>(), C, cb.cw.as<uint64_t>(), cb.cwo.as<uint64_t>(), cur.roff.as<uint64_t>(), cbthr, passed);
 		MCB_CUDA(cudaMemcpyAsync(pscan, passed, C * 4, cudaMemcpyDeviceToDevice, ctx->stream));
 		MCB_TRY(mcb_exclusive_scan_u32(ctx, pscan, C, (uint64_t*)&dc[CT_CB_D]));
-		MCB_TRY(cb_counter(ctx, CT_CB_D, &P));
+		MCB_TRY(cb_counters(ctx));
+		P = CB_HC(ctx, CT_CB_D);
 		MCB_TRY(cb.plist.ensure(P * 16 + 16)); MCB_TRY(cb.loff.ensure((ncl + 2) * 4));
 		if (C) MCB_LAUNCH(ctx, "cb_compact", k_cb_compact, mcb_grid_for(C, 256), 256, 0, cb.cand.as<CbCand>(), pscan, passed, C, cb.plist.as<CbCand>());
-		MCB_LAUNCH(ctx, "cb_list_bounds", k_cb_list_bounds, mcb_grid_for(ncl + 1, 256), 256, 0, cb.plist.as<CbCand>(), P, ncl, cb.loff.as<uint32_t>());
+		// second compaction: the first occurrence of every partner only (cand is free again: it takes the short lists)
+		uint32_t *keep = cb.pass.as<uint32_t>(), *kscan = keep + (C + 1);
+		if (P) MCB_LAUNCH(ctx, "cb_dedupe", k_cb_dedupe, mcb_grid_for(P, 256), 256, 0, cb.plist.as<CbCand>(), P, keep);
+		MCB_CUDA(cudaMemcpyAsync(kscan, keep, P * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, kscan, P, (uint64_t*)&dc[CT_CB_E]));
+		if (P) MCB_LAUNCH(ctx, "cb_compact", k_cb_compact, mcb_grid_for(P, 256), 256, 0, cb.plist.as<CbCand>(), kscan, keep, P, cb.cand.as<CbCand>());
+		MCB_TRY(cb_counters(ctx));
+		P2 = CB_HC(ctx, CT_CB_E);
+		MCB_LAUNCH(ctx, "cb_list_bounds", k_cb_list_bounds, mcb_grid_for(ncl + 1, 256), 256, 0, cb.cand.as<CbCand>(), P2, ncl, cb.loff.as<uint32_t>());
 	}
 	// ---- 4: the sequential part (kthread_cb.c:460-466 with one thread): contigs in order, first partner that is still free
-	MCB_TRY(cb.h_list.ensure(P * 16 + 16)); MCB_TRY(cb.h_loff.ensure((ncl + 2) * 4)); MCB_TRY(cb.h_pairs.ensure((ncl / 2 + 2) * 16)); MCB_TRY(cb.h_flag.ensure((ncl + 2) * 4));
-	if (P) MCB_CUDA(cudaMemcpyAsync(cb.h_list.p, cb.plist.p, P * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	MCB_TRY(cb.h_list.ensure(P2 * 16 + 16)); MCB_TRY(cb.h_loff.ensure((ncl + 2) * 4)); MCB_TRY(cb.h_pairs.ensure((ncl / 2 + 2) * 16)); MCB_TRY(cb.h_flag.ensure((ncl + 2) * 5));
+	if (P2) MCB_CUDA(cudaMemcpyAsync(cb.h_list.p, cb.cand.p, P2 * 16, cudaMemcpyDeviceToHost, ctx->stream));
 	MCB_CUDA(cudaMemcpyAsync(cb.h_loff.p, cb.loff.p, (ncl + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	uint64_t nm = 0, n_copy = 0;
@@ -376,13 +427,14 @@ static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSe
 		const CbCand *list = cb.h_list.as<CbCand>();
 		const uint32_t *loff = cb.h_loff.as<uint32_t>();
 		CbCand *pairs = cb.h_pairs.as<CbCand>();
-		std::vector<uint8_t> flag(ncl + 1, 0);
+		uint32_t *src = cb.h_flag.as<uint32_t>();               // the untouched contigs, in order
+		uint8_t *flag = (uint8_t*)(src + ncl + 1);
+		memset(flag, 0, ncl + 1);
 		for (uint64_t i = 0; i < ncl; ++i) {
 			if (flag[i]) continue;
 			for (uint32_t e = loff[i]; e < loff[i + 1]; ++e)
 				if (!flag[list[e].c]) { flag[i] = flag[list[e].c] = 1; pairs[nm++] = list[e]; break; }
 		}
-		uint32_t *src = cb.h_flag.as<uint32_t>();               // the untouched contigs, in order
 		for (uint64_t i = 0; i < ncl; ++i) if (!flag[i]) src[n_copy++] = (uint32_t)i;
 	}
 	*n_merged = nm;
@@ -394,7 +446,7 @@ static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSe
 	nxt.ncl = n2; nxt.nmem = cur.nmem;
 	MCB_TRY(nxt.n.ensure((n2 + 2) * 4)); MCB_TRY(nxt.aoff.ensure((n2 + 2) * 8)); MCB_TRY(nxt.a.ensure(cur.nmem * 8 + 16)); MCB_TRY(nxt.roff.ensure((n2 + 2) * 8));
 	MCB_TRY(cb.tmp32.ensure((n2 + 2) * 4)); MCB_TRY(cb.len2.ensure((n2 + 2) * 8));
-	if (!n2) { nxt.nref = 0; return MCB_OK; }
+	if (!n2) { nxt.nref = 0; nxt.nmin = 0; MCB_TRY(nxt.moff.ensure(16)); MCB_CUDA(cudaMemsetAsync(nxt.moff.p, 0, 8, ctx->stream)); return MCB_OK; }
 	MCB_LAUNCH(ctx, "cb_new_sizes", k_cb_new_sizes, mcb_grid_for(n2, 256), 256, 0, cb.pairs.as<CbCand>(), nm, cb.src.as<uint32_t>(), n2, cur.n.as<uint32_t>(), nxt.n.as<uint32_t>());
 	MCB_CUDA(cudaMemcpyAsync(cb.tmp32.p, nxt.n.p, n2 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, cb.tmp32.as<uint32_t>(), n2, (uint64_t*)&dc[CT_CB_A]));
@@ -411,24 +463,23 @@ static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSe
 	           nxt.aoff.as<uint64_t>(), nxt.a.as<uint64_t>(), cb.keyA.as<ulonglong2>());
 	if (n_mm) {
 		std::vector<McbSortPass> passes;
-		mcb_add_bit_passes(passes, 0, 0, 32);                    // position << 1 | strand
+		mcb_add_bit_passes(passes, 0, 0, 1 + mcb_bits_for(2 * *max_len));     // position << 1 | strand; a shifted position stays below the sum of two old lengths
 		mcb_add_bit_passes(passes, 0, 32, 32 + mcb_bits_for(nm));
 		ulonglong2 *sorted = nullptr;
 		MCB_TRY(mcb_radix_sort(ctx, cb.keyA.as<ulonglong2>(), cb.keyB.as<ulonglong2>(), n_mm, passes.data(), (int)passes.size(), &sorted));
 		MCB_LAUNCH(ctx, "cb_unkey", k_cb_unkey, mcb_grid_for(n_mm, 256), 256, 0, sorted, n_mm, nxt.a.as<uint64_t>());
 	}
 	// consensus strings
-	MCB_LAUNCH(ctx, "cb_new_lengths", k_cb_new_lengths, mcb_grid_for(n2, 256), 256, 0, nm, cb.src.as<uint32_t>(), n2, nxt.aoff.as<uint64_t>(), nxt.a.as<uint64_t>(), cur.roff.as<uint64_t>(), L, cb.len2.as<uint64_t>());
+	MCB_CUDA(cudaMemsetAsync(&dc[CT_CB_C], 0, 8, ctx->stream));
+	MCB_LAUNCH(ctx, "cb_new_lengths", k_cb_new_lengths, mcb_grid_for(n2, 256), 256, 0, nm, cb.src.as<uint32_t>(), n2, nxt.aoff.as<uint64_t>(), nxt.a.as<uint64_t>(), cur.roff.as<uint64_t>(), L,
+	           cb.len2.as<uint64_t>(), &dc[CT_CB_C]);
 	MCB_CUDA(cudaMemcpyAsync(nxt.roff.p, cb.len2.p, n2 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 	MCB_TRY(mcb_exclusive_scan_u64(ctx, nxt.roff.as<uint64_t>(), n2, (uint64_t*)&dc[CT_CB_B]));
 	MCB_CUDA(cudaMemcpyAsync(nxt.roff.as<uint64_t>() + n2, &dc[CT_CB_B], 8, cudaMemcpyDeviceToDevice, ctx->stream));
-	uint64_t nref2 = 0, merged_cols = 0;
-	MCB_TRY(cb_counter(ctx, CT_CB_B, &nref2));
-	if (nm) {
-		MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, nxt.roff.as<uint64_t>() + nm, 8, cudaMemcpyDeviceToHost, ctx->stream));
-		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-		merged_cols = ctx->h_counters.as<unsigned long long>()[0];
-	}
+	if (nm) MCB_CUDA(cudaMemcpyAsync(&dc[CT_CB_D], nxt.roff.as<uint64_t>() + nm, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	MCB_TRY(cb_counters(ctx));
+	const uint64_t nref2 = CB_HC(ctx, CT_CB_B), merged_cols = nm ? CB_HC(ctx, CT_CB_D) : 0;
+	*max_len = std::max<uint64_t>(1, CB_HC(ctx, CT_CB_C));
 	nxt.nref = nref2;
 	MCB_TRY(nxt.ref.ensure(nref2 + 32));
 	MCB_CUDA(cudaMemsetAsync(nxt.ref.as<char>() + (nref2 & ~(uint64_t)7), 0, 24, ctx->stream));      // the sketch kernel reads whole 8-byte words
@@ -436,8 +487,8 @@ static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSe
 	                            ctx->d_packed.as<uint64_t>(), WS, L, merged_cols, nxt.ref.as<char>());
 	if (n_copy) MCB_LAUNCH(ctx, "cb_copy_refs", k_cb_copy_refs, mcb_grid_for(n_copy * 32, 256), 256, 0, nm, cb.src.as<uint32_t>(), n2, cur.roff.as<uint64_t>(), cur.ref.as<char>(),
 	                       nxt.roff.as<uint64_t>(), nxt.ref.as<char>());
-	// first-m minimizers of every new contig (ids = positions in the new set)
-	MCB_TRY(cb_first_m(ctx, nxt));
+	// minimizers of the new set: sketches of the merged contigs, lists of the others taken along
+	MCB_TRY(cb_min_lists(ctx, cb, nxt, nm, &cur, cb.src.as<uint32_t>()));
 	return MCB_OK;
 }
 
@@ -452,33 +503,32 @@ extern "C" int mcb_combine(mcb_ctx *ctx, int cbthreshold, mcb_combine_result *re
 	if (!ctx->cb) ctx->cb = new McbCombineState();
 	McbCombineState &cb = *ctx->cb;
 	MCB_TRY(ctx->h_counters.ensure(64 * 8));
-	const int m = ctx->prm.first_mininum;
 	const McbBucketState &bs = ctx->bs;
 	// ---- the seed contigs of kt_for_bucket are still on the device (ctx->d_out): they are set 0
 	CbSet &s0 = cb.set[0];
 	s0.ncl = bs.tot_cl; s0.nmem = bs.tot_mem; s0.nref = bs.tot_ref;
 	MCB_TRY(s0.n.ensure((s0.ncl + 2) * 4)); MCB_TRY(s0.aoff.ensure((s0.ncl + 2) * 8)); MCB_TRY(s0.a.ensure(s0.nmem * 8 + 16)); MCB_TRY(s0.roff.ensure((s0.ncl + 2) * 8));
-	MCB_TRY(s0.ref.ensure(s0.nref + 32)); MCB_TRY(s0.mi.ensure(s0.ncl * m * 16 + 16)); MCB_TRY(s0.micnt.ensure(s0.ncl + 16));
+	MCB_TRY(s0.ref.ensure(s0.nref + 32));
 	{
 		McbSpan sp(ctx->tm, "combine");
 		const cudaMemcpyKind DD = cudaMemcpyDeviceToDevice;
 		MCB_CUDA(cudaMemsetAsync(s0.ref.as<char>() + (s0.nref & ~(uint64_t)7), 0, 24, ctx->stream));     // zero tail first: the sketch kernel reads whole 8-byte words
+		MCB_CUDA(cudaMemsetAsync(s0.roff.p, 0, 8, ctx->stream)); MCB_CUDA(cudaMemsetAsync(s0.aoff.p, 0, 8, ctx->stream));
 		if (s0.ncl) {
 			MCB_CUDA(cudaMemcpyAsync(s0.n.p, ctx->d_out[0].p, s0.ncl * 4, DD, ctx->stream));
 			MCB_CUDA(cudaMemcpyAsync(s0.aoff.p, ctx->d_out[1].p, (s0.ncl + 1) * 8, DD, ctx->stream));
 			MCB_CUDA(cudaMemcpyAsync(s0.a.p, ctx->d_out[2].p, s0.nmem * 8, DD, ctx->stream));
 			MCB_CUDA(cudaMemcpyAsync(s0.roff.p, ctx->d_out[3].p, (s0.ncl + 1) * 8, DD, ctx->stream));
 			MCB_CUDA(cudaMemcpyAsync(s0.ref.p, ctx->d_out[4].p, s0.nref, DD, ctx->stream));
-			MCB_CUDA(cudaMemcpyAsync(s0.mi.p, ctx->d_out[6].p, s0.ncl * m * 16, DD, ctx->stream));
-			MCB_CUDA(cudaMemcpyAsync(s0.micnt.p, ctx->d_out[7].p, s0.ncl, DD, ctx->stream));
 		}
+		MCB_TRY(cb_min_lists(ctx, cb, s0, s0.ncl, nullptr, nullptr));          // every seed contig is sketched once; later only what a merge created
 	}
 	int cur = 0, iterations = 0;
 	long pre_tot = 0;
-	uint64_t merges_total = 0, tuples_total = 0;
+	uint64_t merges_total = 0, tuples_total = 0, max_len = (uint64_t)4 * ctx->L + 4 * ctx->prm.max_rounds;      // seed contigs span fewer than 2L + 2 max_rounds columns
 	for (;;) {
 		uint64_t nm = 0, nt = 0;
-		MCB_TRY(combine_iteration(ctx, cb, cb.set[cur], cb.set[cur ^ 1], cbthreshold, &nm, &nt));
+		MCB_TRY(combine_iteration(ctx, cb, cb.set[cur], cb.set[cur ^ 1], cbthreshold, &nm, &nt, &max_len));
 		cur ^= 1; ++iterations; merges_total += nm; tuples_total += nt;
 		const long tot = (long)cb.set[cur].ncl;
 		if (labs(pre_tot - tot) < 100) break;                      // kthread_cb.c:625
