@@ -33,13 +33,13 @@ struct CbSet {                       // one contig set on the device
 };
 struct McbCombineState {
 	CbSet set[2];
-	DBuf tup, tup2, boff, pcnt, cand, pass, plist, loff, cw, cwo, flag, pairs, src, keyA, keyB, len2, tmp32;
+	DBuf tup, tup2, boff, chn, chc, chs, cho, cho64, pcnt, cand, pass, plist, loff, cw, cwo, flag, pairs, src, keyA, keyB, len2, tmp32;
 	HBuf h_boff, h_list, h_loff, h_pairs, h_flag, h_small;
 	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref;
 	void release()
 	{
 		set[0].release(); set[1].release();
-		DBuf *d[] = { &tup, &tup2, &boff, &pcnt, &cand, &pass, &plist, &loff, &cw, &cwo, &flag, &pairs, &src, &keyA, &keyB, &len2, &tmp32 };
+		DBuf *d[] = { &tup, &tup2, &boff, &chn, &chc, &chs, &cho, &cho64, &pcnt, &cand, &pass, &plist, &loff, &cw, &cwo, &flag, &pairs, &src, &keyA, &keyB, &len2, &tmp32 };
 		for (auto b : d) b->release();
 		HBuf *h[] = { &h_boff, &h_list, &h_loff, &h_pairs, &h_flag, &h_small, &h_cl_n, &h_cl_a_off, &h_cl_a, &h_cl_ref_off, &h_cl_ref };
 		for (auto b : h) b->release();
@@ -60,6 +60,34 @@ __global__ void k_cb_gather_tuples(const mcb_tuple *__restrict__ mins, const uin
 	if (i >= ncl * (uint64_t)m) return;
 	const uint64_t c = i / m, j = i - c * m, b = moff[c];
 	if (b + j < moff[c + 1]) { const mcb_tuple t = mins[b + j]; out[off[c] + j] = make_ulonglong2(t.x, t.y); }
+}
+// long contigs are sketched in stretches of CB_CHUNK bases, one thread each (k_sketch_lh2's chunk mode)
+#define CB_CHUNK 192
+__global__ void k_cb_chunk_counts(const uint64_t *__restrict__ roff, uint64_t count, int chunk, uint32_t *__restrict__ nch)
+{
+	const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < count) { const uint64_t len = roff[c + 1] - roff[c]; nch[c] = chunk ? (uint32_t)max((uint64_t)1, (len + chunk - 1) / chunk) : 1u; }
+}
+__global__ void k_cb_chunk_table(const uint32_t *__restrict__ first, uint64_t count, uint64_t nch, int chunk, uint32_t *__restrict__ ch_contig, uint32_t *__restrict__ ch_start)
+{
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nch) return;
+	uint64_t lo = 0, hi = count;              // last contig whose first chunk is <= t
+	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (first[mid] <= t) lo = mid; else hi = mid; }
+	ch_contig[t] = (uint32_t)lo; ch_start[t] = (uint32_t)(t - first[lo]) * (uint32_t)chunk;
+}
+// list length of a contig = the tuples of its stretches
+__global__ void k_cb_contig_counts(const uint32_t *__restrict__ first, uint64_t count, uint64_t nch, const uint32_t *__restrict__ choff, const unsigned long long *__restrict__ total, uint32_t *__restrict__ cnt)
+{
+	const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= count) return;
+	const uint32_t a = choff[first[c]], b = c + 1 < count ? choff[first[c + 1]] : (uint32_t)*total;
+	cnt[c] = b - a;
+}
+__global__ void k_cb_widen(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = in[i];
 }
 // minimizer lists of the untouched contigs move to the new set with their new contig id
 __global__ void k_cb_copy_min_counts(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ moff, uint32_t *__restrict__ cnt2)
@@ -277,7 +305,7 @@ __global__ void k_cb_consensus(uint64_t nm, const uint64_t *__restrict__ roff2, 
 	const uint64_t mb = aoff2[q], me = aoff2[q + 1];
 	uint64_t s = mb, e = me;                  // first member with position > col - L
 	while (s < e) { const uint64_t mid = (s + e) >> 1; if ((int64_t)((uint32_t)a2[mid] >> 1) <= col - L) s = mid + 1; else e = mid; }
-	unsigned cnt[4] = { 0, 0, 0, 0 };
+	uint64_t cAC = 0, cGT = 0;                // two 32-bit counters per word: no dynamically indexed (= local memory) array
 	for (uint64_t u = s; u < me; ++u) {
 		const uint64_t y = a2[u];
 		const int64_t pos = (int64_t)((uint32_t)y >> 1);
@@ -285,12 +313,14 @@ __global__ void k_cb_consensus(uint64_t nm, const uint64_t *__restrict__ roff2, 
 		const int p = (int)(col - pos);
 		const uint64_t *row = packed + (y >> 32) * (uint64_t)WS;
 		const unsigned bse = (y & 1) ? 3u - mcb_base_at(row, L - 1 - p) : mcb_base_at(row, p);
-		++cnt[bse];
+		const uint64_t one = 1ull << (32 * (bse & 1u));
+		cAC += (bse & 2u) ? 0ull : one; cGT += (bse & 2u) ? one : 0ull;
 	}
-	unsigned best = 0, mx = cnt[0];
-	if (cnt[1] > mx) { mx = cnt[1]; best = 1; }
-	if (cnt[2] > mx) { mx = cnt[2]; best = 2; }
-	if (cnt[3] > mx) { mx = cnt[3]; best = 3; }
+	const unsigned cnt0 = (unsigned)cAC, cnt1 = (unsigned)(cAC >> 32), cnt2 = (unsigned)cGT, cnt3 = (unsigned)(cGT >> 32);
+	unsigned best = 0, mx = cnt0;
+	if (cnt1 > mx) { mx = cnt1; best = 1; }
+	if (cnt2 > mx) { mx = cnt2; best = 2; }
+	if (cnt3 > mx) { mx = cnt3; best = 3; }
 	ref2[g] = "ACGT"[best];
 }
 __global__ void k_cb_copy_refs(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ roff, const char *__restrict__ ref,
@@ -314,30 +344,44 @@ static int cb_counters(mcb_ctx *ctx)          // the device scalars to the host 
 enum { CT_CB_A = 48, CT_CB_B = 49, CT_CB_C = 50, CT_CB_D = 51, CT_CB_E = 52 };          // scratch slots of ctx->d_counters (32..41 are the consensus work lists)
 #define CB_HC(ctx, slot) ((ctx)->h_counters.as<unsigned long long>()[slot])
 
-// all (w,k)-minimizers (mm_sketch_lh_ori, sketch.c:116-165; window rw, kthread_cb.c:234 / :359 with win_step = 0) of the contigs
-// [0, count) of a set, appended to S.mins behind `first_slot` entries; cnt32[c] receives the list lengths, moff must hold the
-// offsets of these contigs already when emit is set
-static int cb_sketch(mcb_ctx *ctx, CbSet &S, uint64_t count, uint32_t *cnt32, bool emit)
+// all (w,k)-minimizers (mm_sketch_lh_ori, sketch.c:116-165; window rw, kthread_cb.c:234 / :359 with win_step = 0) of the work items
+// [0, n_items) of a set: whole contigs, or stretches of contigs (ch_* given).  cnt32 receives the number of tuples per item; with
+// `emit` they are written to S.mins at off[item]
+static int cb_sketch(mcb_ctx *ctx, CbSet &S, uint64_t n_items, uint32_t *cnt32, const uint64_t *off, const uint32_t *ch_contig, const uint32_t *ch_start, int ch_len)
 {
-	if (!count) return MCB_OK;
+	if (!n_items) return MCB_OK;
 	const int rw = ctx->prm.rw, k = ctx->prm.k;
 	const size_t smem = (size_t)rw * LH_THREADS * 13;
 	auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
 	if (smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	MCB_LAUNCH(ctx, "cb_sketch", kern, mcb_grid_for(count, LH_THREADS), LH_THREADS, smem, S.ref.as<char>(), S.roff.as<uint64_t>(), (uint64_t)0, count, (uint64_t)0,
-	           rw, k, INT_MAX, emit ? S.mins.as<mcb_tuple>() : (mcb_tuple*)nullptr, (uint8_t*)nullptr, emit ? S.moff.as<uint64_t>() : (const uint64_t*)nullptr, cnt32);
+	MCB_LAUNCH(ctx, "cb_sketch", kern, mcb_grid_for(n_items, LH_THREADS), LH_THREADS, smem, S.ref.as<char>(), S.roff.as<uint64_t>(), (uint64_t)0, n_items, (uint64_t)0,
+	           rw, k, INT_MAX, off ? S.mins.as<mcb_tuple>() : (mcb_tuple*)nullptr, (uint8_t*)nullptr, off, cnt32, ch_contig, ch_start, ch_len);
 	return MCB_OK;
 }
 
-// minimizer lists of a new set: the merged contigs [0, nm) are sketched, the untouched ones take their lists along (src = old ids;
-// null with nm == ncl: sketch everything, the seed set)
+// minimizer lists of a new set: the merged contigs [0, nm) are sketched — in stretches, so that a contig of thousands of bases is
+// not one thread's sequential walk — and the untouched ones take their lists along (d_src = their old ids; the seed set has
+// nm == ncl and sketches everything)
 static int cb_min_lists(mcb_ctx *ctx, McbCombineState &cb, CbSet &S, uint64_t nm, const CbSet *old, const uint32_t *d_src)
 {
 	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
 	const uint64_t n2 = S.ncl;
-	MCB_TRY(cb.tmp32.ensure((n2 + 2) * 4)); MCB_TRY(S.moff.ensure((n2 + 2) * 8));
-	uint32_t *cnt = cb.tmp32.as<uint32_t>();
-	MCB_TRY(cb_sketch(ctx, S, nm, cnt, false));
+	const int chunk = (ctx->prm.k & 1) ? CB_CHUNK : 0;          // stretches need odd k (no k-mer equal to its reverse complement); else whole contigs
+	MCB_TRY(cb.tmp32.ensure((n2 + 2) * 4)); MCB_TRY(S.moff.ensure((n2 + 2) * 8)); MCB_TRY(cb.chn.ensure((nm + 2) * 4));
+	uint32_t *cnt = cb.tmp32.as<uint32_t>(), *first = cb.chn.as<uint32_t>();
+	uint64_t nch = 0;
+	if (nm) {
+		MCB_LAUNCH(ctx, "cb_chunk_counts", k_cb_chunk_counts, mcb_grid_for(nm, 256), 256, 0, S.roff.as<uint64_t>(), nm, chunk, first);
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, first, nm, (uint64_t*)&dc[CT_CB_A]));
+		MCB_TRY(cb_counters(ctx));
+		nch = CB_HC(ctx, CT_CB_A);
+		MCB_TRY(cb.chc.ensure(nch * 4 + 16)); MCB_TRY(cb.chs.ensure(nch * 4 + 16)); MCB_TRY(cb.cho.ensure((nch + 2) * 4)); MCB_TRY(cb.cho64.ensure((nch + 2) * 8));
+		MCB_LAUNCH(ctx, "cb_chunk_table", k_cb_chunk_table, mcb_grid_for(nch, 256), 256, 0, first, nm, nch, chunk ? chunk : INT_MAX, cb.chc.as<uint32_t>(), cb.chs.as<uint32_t>());
+		MCB_TRY(cb_sketch(ctx, S, nch, cb.cho.as<uint32_t>(), nullptr, cb.chc.as<uint32_t>(), cb.chs.as<uint32_t>(), chunk ? chunk : INT_MAX));
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, cb.cho.as<uint32_t>(), nch, (uint64_t*)&dc[CT_CB_B]));
+		MCB_LAUNCH(ctx, "cb_contig_counts", k_cb_contig_counts, mcb_grid_for(nm, 256), 256, 0, first, nm, nch, cb.cho.as<uint32_t>(), &dc[CT_CB_B], cnt);
+		MCB_LAUNCH(ctx, "cb_widen", k_cb_widen, mcb_grid_for(nch, 256), 256, 0, cb.cho.as<uint32_t>(), nch, cb.cho64.as<uint64_t>());
+	}
 	if (n2 > nm) MCB_LAUNCH(ctx, "cb_copy_min_counts", k_cb_copy_min_counts, mcb_grid_for(n2 - nm, 256), 256, 0, nm, d_src, n2, old->moff.as<uint64_t>(), cnt);
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, cnt, n2, (uint64_t*)&dc[CT_CB_A]));
 	MCB_LAUNCH(ctx, "cb_prefix64", k_cb_prefix64, mcb_grid_for(n2 + 1, 256), 256, 0, cnt, n2, S.moff.as<uint64_t>(), &dc[CT_CB_A]);
@@ -345,7 +389,8 @@ static int cb_min_lists(mcb_ctx *ctx, McbCombineState &cb, CbSet &S, uint64_t nm
 	S.nmin = CB_HC(ctx, CT_CB_A);
 	if (S.nmin >= 0xFFFFFFFFull) { mcb_set_error("mcb_combine: too many contig minimizers"); return MCB_EINVAL; }
 	MCB_TRY(S.mins.ensure(S.nmin * 16 + 16));
-	MCB_TRY(cb_sketch(ctx, S, nm, cnt, true));             // (cnt is rewritten with the same lengths)
+	// the merged contigs come first in the set, so the tuples of stretch t start at cho[t] in the set's list as well
+	if (nm) MCB_TRY(cb_sketch(ctx, S, nch, cb.cho.as<uint32_t>() /* free again: rewritten with the lengths */, cb.cho64.as<uint64_t>(), cb.chc.as<uint32_t>(), cb.chs.as<uint32_t>(), chunk ? chunk : INT_MAX));
 	if (n2 > nm) MCB_LAUNCH(ctx, "cb_copy_mins", k_cb_copy_mins, mcb_grid_for((n2 - nm) * 8, 256), 256, 0, nm, d_src, n2, old->moff.as<uint64_t>(), old->mins.as<mcb_tuple>(),
 	                        S.moff.as<uint64_t>(), S.mins.as<mcb_tuple>());
 	return MCB_OK;

@@ -28,7 +28,8 @@ struct LhRingSmem {
 template <bool WIDE>
 __global__ void __launch_bounds__(LH_THREADS)
 k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count, uint64_t cid_first,
-             int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ cnt32)
+             int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ cnt32,
+             const uint32_t *__restrict__ ch_contig = nullptr, const uint32_t *__restrict__ ch_start = nullptr, int ch_len = 0)
 {
 	extern __shared__ __align__(16) unsigned char lh_smem[];
 	uint64_t *rx = (uint64_t*)lh_smem;                                        // [w][LH_THREADS]
@@ -36,10 +37,19 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 	uint8_t *ss = (uint8_t*)(rp + (size_t)w * LH_THREADS);                    // [w][LH_THREADS] suffix-minimum slot | tie << 7
 	const uint64_t ci = (uint64_t)blockIdx.x * LH_THREADS + threadIdx.x;
 	if (ci >= cl_count) return;
-	const uint64_t c = cl_first + ci;
+	// Chunk mode (ALL mode, odd k, no ambiguous bases: the contig merge): work item ci is the stretch [start, start + ch_len) of
+	// contig ch_contig[ci].  With odd k no k-mer is its own reverse complement, so every base occupies a ring slot, the current
+	// minimum is the rightmost minimum of the last w k-mers, and what the walk emits at a step depends on the last w + 1 k-mers
+	// and the position only: a walk that starts w + k - 1 bases early, counts positions from there and stays silent until
+	// `start` emits exactly what the walk from the beginning of the string emits inside the stretch.
+	const uint64_t crel = ch_contig ? ch_contig[ci] : ci;
+	const uint64_t c = cl_first + crel;
 	const uint64_t b = cl_ref_off[c], e = cl_ref_off[c + 1];
 	const int len = (int)(e - b);
-	const uint32_t rid = (uint32_t)((cid_first + ci) << 8);          // ((clusters.n-1)<<8)+tid, tid 0 (kthread_bucket.c:458)
+	const int start = ch_contig ? (int)ch_start[ci] : 0;
+	const int end = ch_contig ? min(len, start + ch_len) : len;
+	const int b0 = max(0, start - (w + k - 1));
+	const uint32_t rid = (uint32_t)((cid_first + crel) << 8);        // ((clusters.n-1)<<8)+tid, tid 0 (kthread_bucket.c:458)
 	const uint64_t *str8 = (const uint64_t*)(cl_ref + (b & ~(uint64_t)7));
 	const int skew = (int)(b & 7);
 	uint64_t chunk = 0;
@@ -57,12 +67,14 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 	uint32_t flo = 0, fhi = 0, rlo = 0, rhi = 0;
 	uint64_t mn_x = ~0ull; uint32_t mn_p = ~0u;
 	uint64_t px = ~0ull; int pslot = 0; bool ptie = false;             // rightmost minimum of the slots written in this block
-	int l = 0, bp = 0, mp = 0;
-#define LH_EMIT(hx_, p_) do { if (out && n_out < m) { mcb_tuple t_; t_.x = (hx_); t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } while (0)
+	int l = b0, seen = 0, bp = 0, mp = 0;                               // l: bases since the last ambiguous one (= position here); seen: bases rolled into fw / rv
+	bool on = b0 >= start;
+#define LH_EMIT(hx_, p_) do { if (on) { if (out && n_out < m) { mcb_tuple t_; t_.x = (hx_); t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } } while (0)
 	for (int j = 0; j < w; ++j) { ring.set(j, ~0ull, ~0u); sst[j * LH_THREADS] = (uint8_t)(w - 1); }
-	for (int i = 0; i < len && n_out < m; ++i) {
+	for (int i = b0; i < end && n_out < m; ++i) {
 		const int ai = i + skew;
-		if (i == 0 || (ai & 7) == 0) chunk = str8[ai >> 3];
+		if (i == b0 || (ai & 7) == 0) chunk = str8[ai >> 3];
+		on = i >= start;
 		const unsigned cc = mcb_code_of((unsigned char)(chunk >> (8 * (ai & 7))));   // consensus strings are upper-case ACGT (invert_code_rule)
 		uint64_t ix = ~0ull; uint32_t ip = ~0u;
 		if (cc < 4) {
@@ -76,8 +88,9 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 			}
 			if (fw == rv) continue;
 			const int z = fw < rv ? 0 : 1;
-			if (++l >= k) { ix = WIDE ? mcb_hash64_wide(z ? rv : fw, mh) : mcb_hash64_hd(z ? rv : fw, mask); ip = (uint32_t)i << 1 | (uint32_t)z; }
-		} else l = 0;
+			++l;
+			if (++seen >= k) { ix = WIDE ? mcb_hash64_wide(z ? rv : fw, mh) : mcb_hash64_hd(z ? rv : fw, mask); ip = (uint32_t)i << 1 | (uint32_t)z; }
+		} else { l = 0; seen = 0; }
 		ring.set(bp, ix, ip);
 		{
 			const bool ple = ix <= px;
@@ -119,6 +132,7 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 			px = ~0ull; pslot = 0; ptie = false;
 		}
 	}
+	on = end == len;                                                    // the closing minimum (sketch.c:163-164) belongs to the last stretch
 	if (n_out < m && mn_x != ~0ull) LH_EMIT(mn_x, mn_p);
 #undef LH_EMIT
 	if (mi_cnt) mi_cnt[c] = (uint8_t)(n_out < m ? n_out : m);
