@@ -33,13 +33,13 @@ struct CbSet {                       // one contig set on the device
 };
 struct McbCombineState {
 	CbSet set[2];
-	DBuf tup, tup2, boff, chn, chc, chs, cho, cho64, pcnt, cand, pass, plist, loff, cw, cwo, flag, pairs, src, keyA, keyB, len2, tmp32;
+	DBuf alive, best, pick, tup, tup2, boff, chn, chc, chs, cho, cho64, pcnt, cand, pass, plist, loff, cw, cwo, flag, pairs, src, keyA, keyB, len2, tmp32;
 	HBuf h_boff, h_list, h_loff, h_pairs, h_flag, h_small;
 	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref;
 	void release()
 	{
 		set[0].release(); set[1].release();
-		DBuf *d[] = { &tup, &tup2, &boff, &chn, &chc, &chs, &cho, &cho64, &pcnt, &cand, &pass, &plist, &loff, &cw, &cwo, &flag, &pairs, &src, &keyA, &keyB, &len2, &tmp32 };
+		DBuf *d[] = { &alive, &best, &pick, &tup, &tup2, &boff, &chn, &chc, &chs, &cho, &cho64, &pcnt, &cand, &pass, &plist, &loff, &cw, &cwo, &flag, &pairs, &src, &keyA, &keyB, &len2, &tmp32 };
 		for (auto b : d) b->release();
 		HBuf *h[] = { &h_boff, &h_list, &h_loff, &h_pairs, &h_flag, &h_small, &h_cl_n, &h_cl_a_off, &h_cl_a, &h_cl_ref_off, &h_cl_ref };
 		for (auto b : h) b->release();
@@ -228,6 +228,54 @@ __global__ void k_cb_dedupe(const CbCand *__restrict__ list, uint64_t P, uint32_
 	uint32_t k = 1;
 	for (uint64_t f = e; f-- > 0 && list[f].i == r.i;) if (list[f].c == r.c) { k = 0; break; }
 	keep[e] = k;
+}
+
+// ---------------------------------------------------------------- 4: first-come resolution
+// The reference takes the contigs in order and gives contig i the first entry of its list whose partner is still free; both
+// are then taken.  That is greedy matching over the entries in list order (entry e of the concatenated lists has priority e):
+// an entry is accepted iff no earlier accepted entry touches either of its contigs.  Equivalent rounds: every live entry
+// bids for both of its contigs with its index (atomicMin); an entry that holds the minimum at BOTH contigs cannot be
+// pre-empted by anything earlier and is accepted; entries that touch a taken contig die.  The earliest live entry always
+// wins its round, so the loop ends, and contig ids are in hash order, so dependency chains stay short (tens of rounds).
+#define CB_NONE 0xFFFFFFFFu
+__global__ void k_cb_bid(const CbCand *__restrict__ list, uint64_t P, const uint8_t *__restrict__ taken, uint8_t *__restrict__ alive, uint32_t *__restrict__ best,
+                         unsigned long long *__restrict__ n_live)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	bool live = false;
+	if (e < P && alive[e]) {
+		const CbCand r = list[e];
+		if (taken[r.i] || taken[r.c]) alive[e] = 0;
+		else { atomicMin(&best[r.i], (uint32_t)e); atomicMin(&best[r.c], (uint32_t)e); live = true; }
+	}
+	const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+	if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_live, (unsigned long long)__popc(m));
+}
+__global__ void k_cb_accept(const CbCand *__restrict__ list, uint64_t P, uint8_t *__restrict__ taken, uint8_t *__restrict__ alive, const uint32_t *__restrict__ best, uint32_t *__restrict__ pick)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= P || !alive[e]) return;
+	const CbCand r = list[e];
+	if (best[r.i] == (uint32_t)e && best[r.c] == (uint32_t)e) { taken[r.i] = 1; taken[r.c] = 1; pick[r.i] = (uint32_t)e; alive[e] = 0; }
+}
+__global__ void k_cb_round_reset(const CbCand *__restrict__ list, uint64_t P, const uint8_t *__restrict__ alive, uint32_t *__restrict__ best)
+{
+	const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < P && alive[e]) { best[list[e].i] = CB_NONE; best[list[e].c] = CB_NONE; }
+}
+// the outcome as two ordered lists: the accepted entries in the order of their first contig, the untouched contigs in order
+__global__ void k_cb_outcome_flags(const uint32_t *__restrict__ pick, const uint8_t *__restrict__ taken, uint64_t ncl, uint32_t *__restrict__ f_pick, uint32_t *__restrict__ f_free)
+{
+	const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < ncl) { f_pick[c] = pick[c] != CB_NONE; f_free[c] = !taken[c]; }
+}
+__global__ void k_cb_outcome(const CbCand *__restrict__ list, const uint32_t *__restrict__ pick, const uint8_t *__restrict__ taken, uint64_t ncl,
+                             const uint32_t *__restrict__ s_pick, const uint32_t *__restrict__ s_free, CbCand *__restrict__ pairs, uint32_t *__restrict__ src)
+{
+	const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= ncl) return;
+	if (pick[c] != CB_NONE) pairs[s_pick[c]] = list[pick[c]];
+	if (!taken[c]) src[s_free[c]] = (uint32_t)c;
 }
 
 // ---------------------------------------------------------------- 5: the new contig set
@@ -462,32 +510,39 @@ static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSe
 		P2 = CB_HC(ctx, CT_CB_E);
 		MCB_LAUNCH(ctx, "cb_list_bounds", k_cb_list_bounds, mcb_grid_for(ncl + 1, 256), 256, 0, cb.cand.as<CbCand>(), P2, ncl, cb.loff.as<uint32_t>());
 	}
-	// ---- 4: the sequential part (kthread_cb.c:460-466 with one thread): contigs in order, first partner that is still free
-	MCB_TRY(cb.h_list.ensure(P2 * 16 + 16)); MCB_TRY(cb.h_loff.ensure((ncl + 2) * 4)); MCB_TRY(cb.h_pairs.ensure((ncl / 2 + 2) * 16)); MCB_TRY(cb.h_flag.ensure((ncl + 2) * 5));
-	if (P2) MCB_CUDA(cudaMemcpyAsync(cb.h_list.p, cb.cand.p, P2 * 16, cudaMemcpyDeviceToHost, ctx->stream));
-	MCB_CUDA(cudaMemcpyAsync(cb.h_loff.p, cb.loff.p, (ncl + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	// ---- 4: first-come resolution in contig order (kthread_cb.c:460-466 with one thread), as bidding rounds on the device
 	uint64_t nm = 0, n_copy = 0;
 	{
-		const CbCand *list = cb.h_list.as<CbCand>();
-		const uint32_t *loff = cb.h_loff.as<uint32_t>();
-		CbCand *pairs = cb.h_pairs.as<CbCand>();
-		uint32_t *src = cb.h_flag.as<uint32_t>();               // the untouched contigs, in order
-		uint8_t *flag = (uint8_t*)(src + ncl + 1);
-		memset(flag, 0, ncl + 1);
-		for (uint64_t i = 0; i < ncl; ++i) {
-			if (flag[i]) continue;
-			for (uint32_t e = loff[i]; e < loff[i + 1]; ++e)
-				if (!flag[list[e].c]) { flag[i] = flag[list[e].c] = 1; pairs[nm++] = list[e]; break; }
+		MCB_TRY(cb.alive.ensure(P2 + 16)); MCB_TRY(cb.best.ensure((ncl + 2) * 4)); MCB_TRY(cb.pick.ensure((ncl + 2) * 4)); MCB_TRY(cb.flag.ensure(ncl + 16));
+		MCB_TRY(cb.pairs.ensure((ncl / 2 + 2) * 16)); MCB_TRY(cb.src.ensure((ncl + 2) * 4)); MCB_TRY(cb.tmp32.ensure((2 * ncl + 4) * 4));
+		uint8_t *alive = cb.alive.as<uint8_t>(), *taken = cb.flag.as<uint8_t>();
+		uint32_t *best = cb.best.as<uint32_t>(), *pick = cb.pick.as<uint32_t>();
+		const CbCand *list = cb.cand.as<CbCand>();
+		MCB_CUDA(cudaMemsetAsync(alive, 1, P2, ctx->stream)); MCB_CUDA(cudaMemsetAsync(taken, 0, ncl, ctx->stream));
+		MCB_CUDA(cudaMemsetAsync(best, 0xFF, ncl * 4, ctx->stream)); MCB_CUDA(cudaMemsetAsync(pick, 0xFF, ncl * 4, ctx->stream));
+		for (int round = 0; P2; ++round) {
+			if (round > 100000) { mcb_set_error("mcb_combine: resolution does not converge"); return MCB_EINVAL; }
+			const bool check = (round & 3) == 3;          // every fourth round the host looks at the number of live entries
+			if (check) MCB_CUDA(cudaMemsetAsync(&dc[CT_CB_A], 0, 8, ctx->stream));
+			MCB_LAUNCH(ctx, "cb_bid", k_cb_bid, mcb_grid_for(P2, 256), 256, 0, list, P2, taken, alive, best, &dc[check ? CT_CB_A : CT_CB_E]);
+			MCB_LAUNCH(ctx, "cb_accept", k_cb_accept, mcb_grid_for(P2, 256), 256, 0, list, P2, taken, alive, best, pick);
+			MCB_LAUNCH(ctx, "cb_round_reset", k_cb_round_reset, mcb_grid_for(P2, 256), 256, 0, list, P2, alive, best);
+			if (check) {
+				MCB_TRY(cb_counters(ctx));
+				if (CB_HC(ctx, CT_CB_A) == 0) break;
+			}
 		}
-		for (uint64_t i = 0; i < ncl; ++i) if (!flag[i]) src[n_copy++] = (uint32_t)i;
+		uint32_t *f_pick = cb.tmp32.as<uint32_t>(), *f_free = f_pick + (ncl + 1);
+		MCB_LAUNCH(ctx, "cb_outcome_flags", k_cb_outcome_flags, mcb_grid_for(ncl, 256), 256, 0, pick, taken, ncl, f_pick, f_free);
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, f_pick, ncl, (uint64_t*)&dc[CT_CB_A]));
+		MCB_TRY(mcb_exclusive_scan_u32(ctx, f_free, ncl, (uint64_t*)&dc[CT_CB_B]));
+		MCB_LAUNCH(ctx, "cb_outcome", k_cb_outcome, mcb_grid_for(ncl, 256), 256, 0, list, pick, taken, ncl, f_pick, f_free, cb.pairs.as<CbCand>(), cb.src.as<uint32_t>());
+		MCB_TRY(cb_counters(ctx));
+		nm = CB_HC(ctx, CT_CB_A); n_copy = CB_HC(ctx, CT_CB_B);
 	}
 	*n_merged = nm;
 	const uint64_t n2 = nm + n_copy;
 	// ---- 5: the new set
-	MCB_TRY(cb.pairs.ensure(nm * 16 + 16)); MCB_TRY(cb.src.ensure(n_copy * 4 + 16));
-	if (nm) MCB_CUDA(cudaMemcpyAsync(cb.pairs.p, cb.h_pairs.p, nm * 16, cudaMemcpyHostToDevice, ctx->stream));
-	if (n_copy) MCB_CUDA(cudaMemcpyAsync(cb.src.p, cb.h_flag.p, n_copy * 4, cudaMemcpyHostToDevice, ctx->stream));
 	nxt.ncl = n2; nxt.nmem = cur.nmem;
 	MCB_TRY(nxt.n.ensure((n2 + 2) * 4)); MCB_TRY(nxt.aoff.ensure((n2 + 2) * 8)); MCB_TRY(nxt.a.ensure(cur.nmem * 8 + 16)); MCB_TRY(nxt.roff.ensure((n2 + 2) * 8));
 	MCB_TRY(cb.tmp32.ensure((n2 + 2) * 4)); MCB_TRY(cb.len2.ensure((n2 + 2) * 8));
