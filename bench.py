@@ -880,6 +880,10 @@ def bench_sharded(args):
     vals = torch.tensor([ms_dev, wall_e2e / args.steps * 1e3, wall_dev_arm / args.steps * 1e3, coll_ms(tm) / args.steps], dtype=torch.float64, device=dev)
     dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     ms_dev_max, ms_e2e_max, ms_wall_dev_max, coll_max = (float(x) for x in vals.cpu())
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {"ms": round(ms_dev, 3), "entry": {k: round(tm[k][0] / args.steps, 3) for k in ("for_reads", "for_bucket", "idx_build", "realign") if k in tm},
+                                      "coll": round(coll_ms(tm) / args.steps, 3), "sort_lsd_fallbacks": tm.get("sort_lsd_fallbacks", (0, 0))[1],
+                                      "top": {k[2:]: round(v[0] / args.steps, 3) for k, v in sorted(((k, v) for k, v in tm.items() if k.startswith("k:")), key=lambda kv: -kv[1][0])[:8]}})
     if rank == 0:
         peak, peak_src = measured_peaks()
         kern = {k: v for k, v in tm.items() if k.startswith("k:")}
@@ -911,6 +915,7 @@ def bench_sharded(args):
                        "bases_per_s": round(value * L, 1), "wall_ms_per_step_device_arm": round(ms_wall_dev_max, 3), "collective_ms_per_step": round(coll_max, 3),
                        "collective_ms_per_step_rank0": {k.split(":", 1)[1]: round(v[0] / args.steps, 4) for k, v in tm.items() if k.startswith("nccl:") or k.startswith("nccl_in:")},
                        "host_wall_ms_per_step_rank0": {a: {k: round(v / args.steps * 1e3, 3) for k, v in d.items()} for a, d in wall.items()},
+                       "per_rank": per_rank,
                        "nccl_bytes_sent_per_step_rank0": int(sent // max(1, args.steps)), "T_cb": T_cb, "contig_bases": R_total, "rank0": stats,
                        "device_ms_by_entry_point_rank0": {k: round(tm[k][0] / args.steps, 4) for k in ("for_reads", "for_bucket", "idx_build", "realign") if k in tm},
                        "kernel_ms_per_step_rank0": {k[2:]: round(v[0] / args.steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:14]}, "host_threads": threads},

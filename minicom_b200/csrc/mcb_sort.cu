@@ -340,8 +340,9 @@ int mcb_partition_by_owner(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t 
 // sub-bucket of a tuple: bucket << e | top e bits of the minimizer's remaining kx bits (K1 = bucket << 50 | x >> 14)
 struct SubBucket {
 	int e, xshift;           // xshift = kx - e
+	unsigned b_lo;           // first bucket this context holds (sharded: a contiguous range of the 16384)
 	__device__ __forceinline__ unsigned operator()(unsigned long long k1) const
-	{ return ((unsigned)(k1 >> 50) << e) | ((unsigned)(k1 >> xshift) & ((1u << e) - 1u)); }
+	{ return (((unsigned)(k1 >> 50) - b_lo) << e) | ((unsigned)(k1 >> xshift) & ((1u << e) - 1u)); }
 };
 struct DigitSub {
 	SubBucket sb; int shift; unsigned mask, invalid_digit;     // invalid_digit: digit of the non-tuples (top pass: one past the largest), 0 elsewhere
@@ -397,15 +398,19 @@ int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint
 	uint32_t *hist = ctx->d_sort_hist.as<uint32_t>(), *rowsum = hist + nb * 256;
 	const int kx = kbits > 14 ? kbits - 14 : 0;                       // bits of x >> 14
 	int e = 0;
-	while (e < 9 && e < kx && (n_valid >> (14 + e)) > 512) ++e;        // about 256..512 tuples per sub-bucket
-	const SubBucket sb = { e, kx - e };
-	const int P = 14 + e;
-	// digits, least significant first; the top one has 7 bits so that the non-tuples fit behind it as digit 128
-	int bits[3], np = 0;
+	// about 256..512 tuples per sub-bucket; a sharded context holds 1/shard_n of the buckets, so its buckets are shard_n times fuller
+	while (e < 9 && e < kx && ((n_valid * (uint64_t)ctx->shard_n) >> (14 + e)) > 512) ++e;
+	// the buckets of this context: all of them, or the contiguous range a sharded context owns (owner = bucket * G >> 14)
+	const unsigned G = (unsigned)ctx->shard_n, rk = (unsigned)ctx->shard_rank;
+	const unsigned b_lo = (rk * 16384u + G - 1) / G, b_hi = ((rk + 1) * 16384u + G - 1) / G;
+	const SubBucket sb = { e, kx - e, b_lo };
+	const int P = mcb_bits_for(b_hi - b_lo > 1 ? b_hi - b_lo - 1 : 1) + e;
+	// digits, least significant first; the top one has at most 7 bits so that the non-tuples fit behind it as digit 128
+	int bits[4], np = 0;
 	{
-		const int rest = P - 7, nlow = (rest + 7) / 8;
+		const int top = P < 7 ? P : 7, rest = P - top, nlow = (rest + 7) / 8;
 		for (int i = 0, left = rest; i < nlow; ++i) { const int bq = (left + (nlow - i) - 1) / (nlow - i); bits[np++] = bq; left -= bq; }
-		bits[np++] = 7;
+		bits[np++] = top;
 	}
 	ulonglong2 *src = a, *dst = b;
 	for (int p = 0, lo = 0; p < np; ++p) {
@@ -418,7 +423,7 @@ int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint
 	}
 	*sorted_out = src;
 	if (n_valid <= 1) return MCB_OK;
-	const unsigned nsub = 1u << P;
+	const unsigned nsub = (b_hi - b_lo) << e;
 	MCB_LAUNCH(ctx, "bucket_bounds", k_bucket_bounds, (nsub + 1 + 255) / 256, 256, 0, src, n_valid, sb, nsub, boff);
 	MCB_LAUNCH(ctx, "bucket_local_sort", k_bucket_local_sort, nsub, BL_THREADS, 0, src, boff, overflow);
 	return MCB_OK;

@@ -1033,7 +1033,10 @@ int mcb_bucket_round_a_impl(mcb_ctx *ctx, int r, int is_last)
 		if (attempt == 0) {
 			MCB_CUDA(cudaMemsetAsync(&dc[CT_SORT_OVERFLOW], 0, 8, ctx->stream));
 			MCB_TRY(mcb_bucket_sort(ctx, bs.cur, bs.alt, bs.n_in, bs.n_valid, kbits, B.b_hs.as<uint32_t>(), &dc[CT_SORT_OVERFLOW], &sorted));     // b_hs doubles as the bucket-offset scratch
-		} else MCB_TRY(mcb_radix_sort(ctx, bs.cur, bs.alt, bs.n_in, passes.data(), (int)passes.size(), &sorted));
+		} else {
+			if (ctx->tm.enabled) { const int id = ctx->tm.id("sort_lsd_fallbacks"); ctx->tm.ms[id] += 1; ctx->tm.cnt[id] += 1; }      // (a count, not milliseconds)
+			MCB_TRY(mcb_radix_sort(ctx, bs.cur, bs.alt, bs.n_in, passes.data(), (int)passes.size(), &sorted));
+		}
 		if (sorted != bs.cur) { bs.alt = bs.cur; bs.cur = sorted; }
 		// ---- groups
 		MCB_LAUNCH(ctx, "heads", k_heads, mcb_grid_for(n, 256), 256, 0, bs.cur, n, B.b_hs.as<uint32_t>());
