@@ -818,8 +818,17 @@ def bench_sharded(args):
 
     wall = {}
 
+    def phase_barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
     def step(device_resident):
         w = wall.setdefault("device" if device_resident else "host", {"stage1": 0.0, "idx_build": 0.0, "realign": 0.0})
+        # The phases with collectives start together: the index builds in between move their tuples and results over PCIe, whose
+        # speed differs between ranks (shared host bridges), and without the barrier that skew would be booked as collective time
+        # on the ranks that wait.  The barrier itself is outside every timer; the wall clock (e2e) contains it.
+        phase_barrier()
         t = time.perf_counter()
         rr, part = fe.stage1(rows_dev if device_resident else rows_pinned.numpy(), n_total, device_resident, keep_mask=True)
         w["stage1"] += time.perf_counter() - t
@@ -827,6 +836,7 @@ def bench_sharded(args):
         for xy, off in my_idx:
             ctx.idx_build(xy, off).close()
         w["idx_build"] += time.perf_counter() - t
+        phase_barrier()
         t = time.perf_counter()
         claims, rounds, d2h = 0, [], 0
         for sgl, pos, n_job, refs, off, thr, ms, nd in my_realign:

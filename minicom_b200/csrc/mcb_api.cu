@@ -79,7 +79,7 @@ extern "C" void mcb_destroy(mcb_ctx *ctx)
 	ctx->tm.collect();
 	for (auto e : ctx->tm.pool) cudaEventDestroy(e);
 	DBuf *db[] = { &ctx->d_ascii, &ctx->d_packed, &ctx->d_cls, &ctx->d_elemA, &ctx->d_elemB, &ctx->d_counters, &ctx->d_nread_rid, &ctx->d_nread_mask, &ctx->d_sort_hist,
-	               &ctx->d_rows_send, &ctx->d_rows_recv, &ctx->d_coll };
+	               &ctx->d_rows_send, &ctx->d_rows_recv, &ctx->d_coll, &ctx->d_subthr };
 	for (auto b : db) b->release();
 	for (auto &b : ctx->d_scr) b.release();
 	for (auto &b : ctx->d_scan_tmp) b.release();

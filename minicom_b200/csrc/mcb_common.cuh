@@ -208,6 +208,7 @@ struct mcb_ctx {
 	int shard_rank = 0, shard_n = 1;
 	void *comm = nullptr;                // ncclComm_t of this rank (mcb_shard.cu); null on a single GPU
 	bool own_comm = false;
+	DBuf d_subthr;                        // sub-bucket thresholds of the tuple sort (mcb_sort.cu)
 	DBuf d_rows_send, d_rows_recv, d_coll;   // sharded Stage 1: packed rows travelling with their tuples; small collectives
 	HBuf h_coll;
 	uint64_t elem_cap = 0;               // capacity (elements) of d_elemA / d_elemB
@@ -425,7 +426,7 @@ struct McbSortPass { int word; int shift; int bits; };  // word 0 = .x, 1 = .y
 int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const McbSortPass *passes, int n_passes,
                    ulonglong2 **sorted_out);
 int mcb_radix_sort_kmers(mcb_ctx *ctx, unsigned long long *a, unsigned long long *b, uint64_t n, int pbits, uint32_t b_lo, uint32_t b_hi, unsigned long long **sorted_out);
-int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint64_t n_valid, int kbits, uint32_t *boff, unsigned long long *overflow, ulonglong2 **sorted_out);
+int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint64_t n_valid, int kbits, int n_kmers, uint32_t *boff, unsigned long long *overflow, ulonglong2 **sorted_out);
 int mcb_add_bit_passes(std::vector<McbSortPass> &v, int word, int lo, int hi);  // digits covering bits [lo,hi)
 int mcb_exclusive_scan_u32(mcb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *d_total /* device u64, may be null */);
 int mcb_exclusive_scan_u64(mcb_ctx *ctx, uint64_t *d_data, uint64_t n, uint64_t *d_total);

@@ -337,12 +337,22 @@ int mcb_partition_by_owner(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t 
 #define BL_CAP 2048
 #define BL_THREADS 256
 
-// sub-bucket of a tuple: bucket << e | top e bits of the minimizer's remaining kx bits (K1 = bucket << 50 | x >> 14)
+// sub-bucket of a tuple: (bucket - b_lo) << e | which of 2^e value ranges of x >> 14 the minimizer falls into (K1 = bucket << 50 |
+// x >> 14).  A minimizer is the MINIMUM of the read's k-mer hashes, so its leading bits are almost always zero: equal-width
+// ranges would put every tuple into the first one.  The ranges are therefore the 2^e quantiles of the minimum of n_k uniform
+// hashes (thr[j], ascending, computed on the host); the rank of a value among them is monotone in the value, so sub-bucket
+// order is sort order.  A skewed input only unbalances the sub-buckets (-> the LSD fallback), it cannot misorder anything.
 struct SubBucket {
-	int e, xshift;           // xshift = kx - e
+	int e;
 	unsigned b_lo;           // first bucket this context holds (sharded: a contiguous range of the 16384)
+	const unsigned long long *thr;      // [2^e - 1]
 	__device__ __forceinline__ unsigned operator()(unsigned long long k1) const
-	{ return (((unsigned)(k1 >> 50) - b_lo) << e) | ((unsigned)(k1 >> xshift) & ((1u << e) - 1u)); }
+	{
+		const unsigned long long xv = k1 & 0x3FFFFFFFFFFFFull;
+		unsigned lo = 0, hi = (1u << e) - 1u;                  // number of thresholds <= xv
+		while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (thr[mid] <= xv) lo = mid + 1; else hi = mid; }
+		return (((unsigned)(k1 >> 50) - b_lo) << e) | lo;
+	}
 };
 struct DigitSub {
 	SubBucket sb; int shift; unsigned mask, invalid_digit;     // invalid_digit: digit of the non-tuples (top pass: one past the largest), 0 elsewhere
@@ -388,7 +398,8 @@ k_bucket_local_sort(ulonglong2 *__restrict__ e, const uint32_t *__restrict__ bof
 // a/b: double buffer; n elements of which n_valid are tuples whose minimizers have `kbits` significant bits; boff: device scratch
 // u32[*n_sub_out + 2] (at most n_valid/256 + 16386 entries); overflow: device counter (must be zero on entry).  The sorted tuples
 // occupy [0, n_valid) of *sorted_out, the other elements follow.
-int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint64_t n_valid, int kbits, uint32_t *boff, unsigned long long *overflow, ulonglong2 **sorted_out)
+#include <math.h>
+int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint64_t n_valid, int kbits, int n_kmers, uint32_t *boff, unsigned long long *overflow, ulonglong2 **sorted_out)
 {
 	*sorted_out = a;
 	if (n <= 1) return MCB_OK;
@@ -403,7 +414,22 @@ int mcb_bucket_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, uint
 	// the buckets of this context: all of them, or the contiguous range a sharded context owns (owner = bucket * G >> 14)
 	const unsigned G = (unsigned)ctx->shard_n, rk = (unsigned)ctx->shard_rank;
 	const unsigned b_lo = (rk * 16384u + G - 1) / G, b_hi = ((rk + 1) * 16384u + G - 1) / G;
-	const SubBucket sb = { e, kx - e, b_lo };
+	// quantiles of the minimum of n_kmers uniform kbits-bit hashes, on the scale of x >> 14: F(x) = 1 - (1 - x / 2^kbits)^n_kmers
+	MCB_TRY(ctx->d_subthr.ensure(((size_t)1 << e) * 8 + 16));
+	if (e > 0) {
+		unsigned long long thr[512];
+		const long double scale = ldexpl(1.0L, kx), nk = (long double)(n_kmers > 0 ? n_kmers : 1);
+		for (int j = 1; j < (1 << e); ++j) {
+			const long double q = (long double)j / (long double)(1 << e);
+			long double t = scale * (1.0L - powl(1.0L - q, 1.0L / nk));
+			if (t < 0) t = 0;
+			thr[j - 1] = t >= scale ? (unsigned long long)scale - 1 : (unsigned long long)t;
+			if (j > 1 && thr[j - 1] < thr[j - 2]) thr[j - 1] = thr[j - 2];
+		}
+		MCB_CUDA(cudaMemcpyAsync(ctx->d_subthr.p, thr, ((size_t)(1 << e) - 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));             // thr lives on this stack frame
+	}
+	const SubBucket sb = { e, b_lo, ctx->d_subthr.as<unsigned long long>() };
 	const int P = mcb_bits_for(b_hi - b_lo > 1 ? b_hi - b_lo - 1 : 1) + e;
 	// digits, least significant first; the top one has at most 7 bits so that the non-tuples fit behind it as digit 128
 	int bits[4], np = 0;

@@ -1032,9 +1032,17 @@ int mcb_bucket_round_a_impl(mcb_ctx *ctx, int r, int is_last)
 	for (int attempt = lsd_only ? 1 : 0;; ++attempt) {
 		if (attempt == 0) {
 			MCB_CUDA(cudaMemsetAsync(&dc[CT_SORT_OVERFLOW], 0, 8, ctx->stream));
-			MCB_TRY(mcb_bucket_sort(ctx, bs.cur, bs.alt, bs.n_in, bs.n_valid, kbits, B.b_hs.as<uint32_t>(), &dc[CT_SORT_OVERFLOW], &sorted));     // b_hs doubles as the bucket-offset scratch
+			MCB_TRY(mcb_bucket_sort(ctx, bs.cur, bs.alt, bs.n_in, bs.n_valid, kbits, L - (r == 1 ? k : kmer + 1) + 1, B.b_hs.as<uint32_t>(), &dc[CT_SORT_OVERFLOW], &sorted));     // b_hs doubles as the bucket-offset scratch
 		} else {
 			if (ctx->tm.enabled) { const int id = ctx->tm.id("sort_lsd_fallbacks"); ctx->tm.ms[id] += 1; ctx->tm.cnt[id] += 1; }      // (a count, not milliseconds)
+			if (getenv("MCB_SORT_DEBUG")) {          // which sub-buckets were too large?
+				std::vector<uint32_t> hb(70000);
+				cudaMemcpy(hb.data(), B.b_hs.p, hb.size() * 4, cudaMemcpyDeviceToHost);
+				uint32_t mx = 0, at = 0, bad = 0;
+				for (size_t i = 0; i + 1 < hb.size(); ++i) { const uint32_t d = hb[i + 1] - hb[i]; if (d > 2048 && d < 0x80000000u) { if (d > mx) { mx = d; at = (uint32_t)i; } ++bad; } }
+				fprintf(stderr, "[mcb rank %d] round %d: bucket sort overflowed (%llu sub-buckets reported): n_in=%llu n_valid=%llu largest %u at sub-bucket %u (%u above 2048 among the first 70000); boff[0..3]=%u %u %u %u\n",
+				        ctx->shard_rank, r, hc0[CT_SORT_OVERFLOW], (unsigned long long)bs.n_in, (unsigned long long)bs.n_valid, mx, at, bad, hb[0], hb[1], hb[2], hb[3]);
+			}
 			MCB_TRY(mcb_radix_sort(ctx, bs.cur, bs.alt, bs.n_in, passes.data(), (int)passes.size(), &sorted));
 		}
 		if (sorted != bs.cur) { bs.alt = bs.cur; bs.cur = sorted; }
