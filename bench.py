@@ -162,7 +162,7 @@ def algorithmic_bytes(kernel, c):
     L4 = (c["L"] + 3) // 4
     rounds = c["rounds"]
     nr = max(1, len(rounds))
-    if kernel == "k:pack_classify_sketch":        # packed read + tuple per read
+    if kernel in ("k:pack_classify_sketch", "k:classify_sketch_packed"):        # packed read + tuple per read
         return c["N"] * (L4 + 16), 1
     if kernel in ("k:sort_scatter", "k:sort_hist"):
         return None, None                          # filled by the caller: 32 B x tuples, spread over the passes
@@ -458,19 +458,37 @@ def bench_pipeline(args):
     rounds_in = [(pin(sg), int(len(off) - 1), thr, ms, nd) for sg, refs, off, thr, ms, nd in realign_calls]
     rec_contigs = (realign_calls[0][1], realign_calls[0][2]) if realign_calls else None
     del realign_calls
-    rows_pinned = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
-    rows_pinned.numpy()[:] = reads
-    rows_dev = rows_pinned.to("cuda", non_blocking=False)
-    del reads
     params = api.resolve_params(L, device=local, **{k: int(ref_env[e]) for k, e in (("k", "MC_K"), ("e", "MC_E"), ("w", "MC_W"), ("m", "MC_M")) if e in ref_env})
+    ws = (((L + 31) // 32) + 1) & ~1
+    packed_input = not args.ascii
+    if packed_input:
+        # the reads as the library's FASTQ reader hands them to kt_for_reads (csrc/mcb_fastq.cu): 2-bit rows in
+        # page-locked memory + the side table of the reads with N; made here, untimed, like the FASTQ load the metric excludes (8d)
+        rs = api.ReadSet(L)
+        t0 = time.time()
+        rs.add_rows(reads, threads)
+        log(f"reads packed on the host by {threads} threads in {time.time() - t0:.2f}s ({n * ws * 8 / 1e6:.0f} MB page-locked)")
+        rsv = rs.view()
+        pk, nrid_h, nmask_h = rs.arrays()
+        pk_dev, nrid_dev, nmask_dev = torch.from_numpy(pk).to("cuda"), torch.from_numpy(nrid_h.view(np.int32).copy()).to("cuda"), torch.from_numpy(nmask_h.view(np.int64).copy()).to("cuda")
+        rows_pinned = rows_dev = None
+        reads_h2d = n * ws * 8 + int(rsv.n_nreads) * (4 + ws * 8)
+    else:
+        rows_pinned = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
+        rows_pinned.numpy()[:] = reads
+        rows_dev = rows_pinned.to("cuda", non_blocking=False)
+        reads_h2d = n * L
+    del reads
+
+    def load_reads(ctx_):
+        return ctx_.for_reads_packed(rs) if packed_input else ctx_.for_reads(rows_pinned.numpy())
     cbthr = int(ref_env.get("MC_CBTHR", 0)) or 2 * int(params.diff_threshold)          # minicommain.c:122-126
     ctx = api.Context(params)
     ctx.timers_enable(True)
     m = int(params.first_mininum)
-    ws = (((L + 31) // 32) + 1) & ~1
     # ---- parity (untimed, copying API)
     got = {}
-    rr = ctx.for_reads(rows_pinned.numpy())
+    rr = load_reads(ctx)
     tuples = ctx.debug_read_tuples(n)
     br = ctx.for_bucket()
     mi_valid = br.mi[np.arange(m)[None, :] < br.mi_cnt[:, None]]
@@ -483,7 +501,7 @@ def bench_pipeline(args):
     got.update(parity.index_digests(0, *ix.arrays()))
     ix.close()
     del bm, mi_valid, br
-    ctx.for_reads(rows_pinned.numpy())
+    load_reads(ctx)
     ctx.for_bucket()
     cr = ctx.combine(cbthr)
     got.update(parity.contig_digests(cr.cl_n, cr.cl_a, cr.cl_ref, np.diff(cr.cl_ref_off.astype(np.int64))))
@@ -512,7 +530,11 @@ def bench_pipeline(args):
         w = wall.setdefault("device" if device_resident else "host", {"for_reads": 0.0, "for_bucket": 0.0, "combine": 0.0, "realign": 0.0})
         t = time.perf_counter()
         rr = api._ReadsResult()
-        if device_resident:
+        if packed_input and device_resident:
+            ctx._check(ctx.lib.mcb_for_reads_packed_device(ctx._h, pk_dev.data_ptr(), n, nrid_dev.data_ptr(), nmask_dev.data_ptr(), rsv.n_nreads, C.byref(rr)))
+        elif packed_input:
+            ctx._check(ctx.lib.mcb_for_reads_packed(ctx._h, rsv.packed, n, rsv.nread_rid, rsv.nmask, rsv.n_nreads, C.byref(rr)))
+        elif device_resident:
             ctx._check(ctx.lib.mcb_for_reads_device(ctx._h, rows_dev.data_ptr(), n, C.byref(rr)))
         else:
             ctx._check(ctx.lib.mcb_for_reads(ctx._h, rows_pinned.data_ptr(), n, C.byref(rr)))
@@ -540,8 +562,8 @@ def bench_pipeline(args):
                          "bucket_rounds": int(br.rounds), "clusters": int(br.n_clusters), "singles_stage1": int(br.n_sg), "contigs": nc, "merges": int(cr.n_merges),
                          "merge_iterations": int(cr.iterations), "T_cb": int(cr.n_index_tuples), "rounds": rounds})
         nn = int(rr.n_nreads)
-        h2d = (0 if device_resident else n * L) + sum(x[0].nbytes for x in rounds_in)
-        d2h = n + nn * (5 + ws * 8) + int(br.n_sg) * 4 + nc * (4 + 16) + mem * 8 + ref_bytes + sum(r["claims"] * 24 + r["polyAT"] * 4 for r in rounds)
+        h2d = (0 if device_resident else reads_h2d) + sum(x[0].nbytes for x in rounds_in)
+        d2h = n + nn * (5 + (0 if packed_input else ws * 8)) + int(br.n_sg) * 4 + nc * (4 + 16) + mem * 8 + ref_bytes + sum(r["claims"] * 24 + r["polyAT"] * 4 for r in rounds)
         return h2d, d2h
 
     def metric_ms(tm):         # kt_for_reads + kt_for_bucket + all mm_idx_generation + all realign_hash
@@ -598,7 +620,9 @@ def bench_pipeline(args):
         "config": {"workload": f"{args.workload}: {n} x {L} bp reads, {G} bp random genome, 1% substitutions, mode {mode}, {opts_text(ref_env)}",
                    "step": "kt_for_reads, kt_for_bucket, combine_cluster on the device (all mm_idx_generation calls inside it), every realign_hash of the schedule; "
                            "seed contigs, index tuples, indexes and merged contigs never leave the device",
-                   "l2": "inputs larger than L2 (reads %.0f MB per step)" % (n * L / 1e6),
+                   "reads_input": ("2-bit packed rows (%d B/read) + N side table, as the library's FASTQ reader (mcb_readset_add_fastq, SURVEY 8f N3) leaves them in page-locked memory" % (ws * 8)) if packed_input
+                                  else "ASCII rows (%d B/read)" % L,
+                   "l2": "inputs larger than L2 (reads %.0f MB per step)" % ((n * ws * 8 if packed_input else n * L) / 1e6),
                    "timing": "value = CUDA-event device time of kt_for_reads + kt_for_bucket + all index builds + all realign_hash rounds (SURVEY 8d: the contig merge is not part of the metric; "
                              "its device time is merge_ms_per_step and value_with_merge includes it), reads resident in HBM; e2e = wall clock of the whole step, merge included, through the host-buffer C-ABI",
                    "bases_per_s": round(value * L, 1), "merge_ms_per_step": round(ms_merge, 4), "value_with_merge": round(n / ((ms_dev + ms_merge) / 1e3), 1),
@@ -1011,6 +1035,7 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=1, help="--impl reference: cap on the timed steps (one step of C2 is minutes of CPU)")
     ap.add_argument("--ref-sample", action="store_true", help="--impl reference: time the bounded sample instead of the full workload")
     ap.add_argument("--replay", action="store_true", help="N = 1: replay the host merger's recorded mm_idx_generation / realign_hash calls (contig merge on the host, num_thr=1 recording) instead of the device-resident pipeline")
+    ap.add_argument("--ascii", action="store_true", help="N = 1: hand kt_for_reads the reads as ASCII rows (mcb_for_reads) instead of the packed rows of the library's FASTQ reader")
     ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent single-GPU jobs instead of one sharded job")
     args = ap.parse_args()
     claim_stdout()

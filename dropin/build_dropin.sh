@@ -28,7 +28,9 @@ mkdir -p "$B"
   echo "#define output mcb_cfg_str(\"MC_TMPDIR\", \"output_mc/\")"
 } > "$B/config.h"
 CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$HERE -I$REF -I$ROOT/include"
-KEPT="bseq misc preprocess kthread_cb kthread_dump minicommain"
+# bseq.o (the FASTQ reader) is replaced by the shim's packing reader (N3) unless MCB_KEEP_BSEQ=1
+KEPT="misc preprocess kthread_cb kthread_dump minicommain"
+if [ "${MCB_KEEP_BSEQ:-0}" = 1 ]; then KEPT="bseq $KEPT"; CXXFLAGS="$CXXFLAGS -DMCB_KEEP_BSEQ"; fi
 # minicompe links from an archive (src/Makefile:24-25,33-34): kthread_dump.o is never pulled in and clashes with kthread_dump_pe.o
 [ "$MODE" = pe ] && KEPT="${KEPT/kthread_dump /kthread_dump_pe }"
 pids=()

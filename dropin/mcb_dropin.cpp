@@ -1,11 +1,14 @@
 // mcb_dropin.cpp — the reference-side binding of libminicom_b200.so.
 //
 // Defines, with the reference's own (C++-mangled) signatures, exactly the ten symbols that the KEPT objects of
-// yuansliu/minicom (minicommain.o preprocess.o kthread_cb.o kthread_dump[_pe].o bseq.o misc.o) import from the
+// yuansliu/minicom (minicommain.o preprocess.o kthread_cb.o kthread_dump[_pe].o misc.o) import from the
 // objects this project replaces (sketch.o kthread_reads.o kthread_bucket.o kthread_idx.o kthread_hash_realign.o
 // bbhashdict.o) — SURVEY.md §8b:
 //     kt_for_reads  kt_for_bucket  mm_idx_init  mm_idx_generation  mm_idx_get  mm_idx_destroy  realign_hash
 //     mm_sketch_lh_ori  seq_nt4_table  invert_code_rule
+// plus combine_cluster (N1: the contig merge on the device, kthread_cb.o's own is kept under another name) and the five
+// functions of bseq.o (N3: bseq_open bseq_read bseq_read_second bseq_close bseq_eof — the FASTQ reader, which here packs the
+// reads for the device while it parses; build with MCB_KEEP_BSEQ=1 to link the reference's bseq.o instead).
 // It is compiled inside the reference tree against the reference's headers (breads.h, kvec.h and the generated
 // config.h), the way a maintainer would add it; it contains marshalling only — every computation is
 // a call into the C-ABI (include/minicom_b200.h).  Cluster placement equals the num_thr=1 layout of the reference
@@ -58,6 +61,64 @@ static void die(const char *where, int rc)
 	fprintf(stderr, "minicom_b200: %s failed (%d): %s\n", where, rc, mcb_last_error());
 	exit(1);
 }
+
+// ---- bseq_open / bseq_read / bseq_read_second / bseq_close / bseq_eof (bseq.c:19-101), N3.
+// The parser of the library reads the file (zlib, kseq record grammar), hands back the NUL-terminated strings the kept host
+// stages go on using (reads->seq[i].seq: dump, N replacement) and keeps every read 2-bit packed in page-locked memory;
+// kt_for_reads then uploads those rows (a quarter of the characters) instead of gathering and shipping the strings.
+static mcb_readset *g_rs = 0;
+#ifndef MCB_KEEP_BSEQ
+#include "bseq.h"
+struct bseq_file_s { std::string path; int is_eof; };
+
+bseq_file_t *bseq_open(const char *fn)
+{
+	if (!fn || !strcmp(fn, "-")) { fprintf(stderr, "minicom_b200: reading from stdin is not supported by the packed reader\n"); return 0; }
+	FILE *f = fopen(fn, "rb");
+	if (!f) return 0;                                        // preprocess.c:46-49 reports it
+	fclose(f);
+	bseq_file_t *fp = new bseq_file_s();
+	fp->path = fn; fp->is_eof = 0;
+	return fp;
+}
+
+void bseq_close(bseq_file_t *fp) { delete fp; }
+int bseq_eof(bseq_file_t *fp) { return fp->is_eof; }
+
+static void read_into(bseq1_t *&seqs, bseq_file_t *fp, int *n_, int seq_len, int n_before)
+{
+	if (!g_rs) { int rc = mcb_readset_create(seq_len, &g_rs); if (rc) die("bseq_read", rc); }
+	char *ascii = 0;
+	uint64_t added = 0;
+	int rc = mcb_readset_add_fastq(g_rs, fp->path.c_str(), n_threads > 0 ? n_threads : 1, &ascii, &added);
+	if (rc) {
+		if (strstr(mcb_last_error(), "Length of reads are different")) fprintf(stderr, "Length of reads are different. The program can not compress it.\n");   // bseq.c:55
+		die("bseq_read", rc);
+	}
+	seqs = (bseq1_t*)realloc(seqs, ((size_t)n_before + added + 1) * sizeof(bseq1_t));
+	for (uint64_t i = 0; i < added; ++i) {
+		bseq1_t *s = &seqs[n_before + i];
+		s->rid = 0; s->n_pos = 0;
+		s->seq = ascii + i * (size_t)(seq_len + 1);          // one block for the whole file; nothing in the reference frees the strings
+	}
+	if (added == 0) fp->is_eof = 1;
+	*n_ = n_before + (int)added;
+}
+
+bseq1_t *bseq_read(bseq_file_t *fp, int *n_, int seq_len)
+{
+	bseq1_t *seqs = 0;
+	if (g_rs) { mcb_readset_destroy(g_rs); g_rs = 0; }
+	read_into(seqs, fp, n_, seq_len, 0);
+	if (*n_ == 0) { free(seqs); seqs = 0; }
+	return seqs;
+}
+
+void bseq_read_second(bseq1_t *&seqs, bseq_file_t *fp, int *n_, int seq_len)
+{
+	read_into(seqs, fp, n_, seq_len, *n_);
+}
+#endif
 
 struct McbAtExit {
 	~McbAtExit()
@@ -125,9 +186,16 @@ void kt_for_reads(int n_threads_, reads_t *r, long n)
 	double t0 = realtime();
 	mcb_ctx *ctx = ctx_for(r);
 	mcb_reads_result res;
-	int rc = g_grp ? mcb_group_for_reads_ptrs(g_grp, &r->seq[0].seq, sizeof(bseq1_t), (uint64_t)n, n_threads_, &res)
-	               : mcb_for_reads_ptrs(ctx, &r->seq[0].seq, sizeof(bseq1_t), (uint64_t)n, n_threads_, &res);
+	mcb_readset_view v;
+	memset(&v, 0, sizeof v);
+	if (g_rs) mcb_readset_get(g_rs, &v);
+	int rc;
+	if (g_grp) rc = mcb_group_for_reads_ptrs(g_grp, &r->seq[0].seq, sizeof(bseq1_t), (uint64_t)n, n_threads_, &res);
+	else if (g_rs && v.n_reads == (uint64_t)n && !getenv("MCB_ASCII_READS"))       // the reads as the shim's own bseq_read packed them
+		rc = mcb_for_reads_packed(ctx, v.packed, v.n_reads, v.nread_rid, v.nmask, v.n_nreads, &res);
+	else rc = mcb_for_reads_ptrs(ctx, &r->seq[0].seq, sizeof(bseq1_t), (uint64_t)n, n_threads_, &res);
 	if (rc) die("kt_for_reads", rc);
+	if (g_rs && !g_grp) { mcb_readset_destroy(g_rs); g_rs = 0; }                   // the packed rows are on the device now
 	sp_reads_t *s = r->sp;
 	for (long i = 0; i < n; ++i) {
 		r->seq[i].n_pos = NULL;

@@ -107,6 +107,46 @@ int mcb_for_reads_ptrs(mcb_ctx *ctx, const void *first_seq_ptr, size_t stride, u
 /* Same with the rows already resident in device memory (d_rows: device pointer, n*L bytes). */
 int mcb_for_reads_device(mcb_ctx *ctx, const char *d_rows, uint64_t n, mcb_reads_result *res);
 
+/* ------------------------------------------------------------------ */
+/* FASTQ -> packed reads (bseq.c:19-96), SURVEY.md 8f row N3            */
+/* ------------------------------------------------------------------ */
+/* A read set on the host in the layout the device works on: row i = row_words 64-bit words, base j of the read in word j/32 at
+ * bits 2*(j%32), codes A0 C1 G2 T3 (seq_nt4_table, sketch.c:8-25), unused bits zero; an 'N' is stored as code 0 and recorded
+ * in the side table of the reads that contain one: nread_rid ascending, nmask[j*row_words + w] has bit 2*(i%32) of word i/32
+ * set where read nread_rid[j] has an N at position i (what process_reads keeps as seq->n_pos, kthread_reads.c:69-80).
+ * The rows live in page-locked memory when a CUDA device is present.  mcb_readset_add_fastq replaces bseq_open + bseq_read +
+ * bseq_close (a second call appends, like bseq_read_second for -1/-2): the file (plain or gzip, through zlib like the
+ * reference) is parsed with kseq_read's record grammar (kseq.h:185-224: FASTA and FASTQ, multi-line sequences, CR LF), every
+ * sequence must be `readlen` long (bseq.c:54-57) and consist of A,C,G,T,N (MCB_EINPUT otherwise).  n_threads host threads pack.
+ * ascii_out (may be NULL): receives a malloc'd block of n_added rows of readlen+1 bytes, NUL-terminated — the strings the
+ * reference's host stages keep in reads->seq[i].seq; the caller frees it. */
+typedef struct mcb_readset mcb_readset;
+typedef struct {
+	uint64_t n_reads;
+	int32_t readlen, row_words;
+	const uint64_t *packed;      /* [n_reads][row_words] */
+	uint64_t n_nreads;
+	const uint32_t *nread_rid;   /* [n_nreads] */
+	const uint64_t *nmask;       /* [n_nreads][row_words] */
+} mcb_readset_view;
+int  mcb_readset_create(int readlen, mcb_readset **out);
+void mcb_readset_destroy(mcb_readset *rs);
+int  mcb_readset_add_fastq(mcb_readset *rs, const char *path, int n_threads, char **ascii_out, uint64_t *n_added);
+int  mcb_readset_add_fastq_buffer(mcb_readset *rs, const char *buf, uint64_t len, int n_threads, char **ascii_out, uint64_t *n_added);
+/* the same packing for reads that are already rows of readlen characters in memory */
+int  mcb_readset_add_rows(mcb_readset *rs, const char *rows, uint64_t n, int n_threads);
+void mcb_readset_get(const mcb_readset *rs, mcb_readset_view *view);   /* valid until the next add / destroy */
+
+/* kt_for_reads on packed reads: same results as mcb_for_reads on the ASCII rows they were packed from, ceil(L/4) (rounded to
+ * 16) bytes per read over PCIe instead of L.  packed / nread_rid / nmask: host memory in the mcb_readset_view layout
+ * (nread_rid relative to this call's first row).  Rows with non-zero unused bits, masks outside the read or over a non-zero
+ * code are rejected (MCB_EINPUT). */
+int mcb_for_reads_packed(mcb_ctx *ctx, const uint64_t *packed, uint64_t n, const uint32_t *nread_rid, const uint64_t *nmask, uint64_t n_nreads,
+                         mcb_reads_result *res);
+/* Same with the three arrays already resident in device memory (16-byte aligned). */
+int mcb_for_reads_packed_device(mcb_ctx *ctx, const uint64_t *d_packed, uint64_t n, const uint32_t *d_nread_rid, const uint64_t *d_nmask, uint64_t n_nreads,
+                                mcb_reads_result *res);
+
 /* Test/debug view of B[0] (kthread_reads.c:213-218): one tuple per read in rid order,
  * {~0,~0} for reads that were not sketched.  out: host, n_reads tuples. */
 int mcb_debug_read_tuples(mcb_ctx *ctx, mcb_tuple *out);

@@ -33,6 +33,11 @@ class _ReadsResult(C.Structure):
                 ("nread_repl", C.c_void_p), ("nread_off", C.c_void_p), ("npos", C.c_void_p), ("n_sketched", C.c_uint64)]
 
 
+class _ReadsetView(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("readlen", C.c_int32), ("row_words", C.c_int32), ("packed", C.c_void_p), ("n_nreads", C.c_uint64),
+                ("nread_rid", C.c_void_p), ("nmask", C.c_void_p)]
+
+
 class _BucketResult(C.Structure):
     _fields_ = [("n_clusters", C.c_uint64), ("cl_n", C.c_void_p), ("cl_a_off", C.c_void_p), ("cl_a", C.c_void_p),
                 ("cl_ref_off", C.c_void_p), ("cl_ref", C.c_void_p), ("n_sg", C.c_uint64), ("sg", C.c_void_p),
@@ -54,7 +59,8 @@ class _RealignResult(C.Structure):
 
 EXPORTS = [
     "mcb_resolve_params", "mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version",
-    "mcb_for_reads", "mcb_for_reads_ptrs", "mcb_for_reads_device",
+    "mcb_for_reads", "mcb_for_reads_ptrs", "mcb_for_reads_device", "mcb_for_reads_packed", "mcb_for_reads_packed_device",
+    "mcb_readset_create", "mcb_readset_destroy", "mcb_readset_add_fastq", "mcb_readset_add_fastq_buffer", "mcb_readset_add_rows", "mcb_readset_get",
     "mcb_debug_read_tuples", "mcb_debug_sketch_two", "mcb_debug_unpack_reads",
     "mcb_for_bucket", "mcb_for_bucket_keep", "mcb_idx_build", "mcb_idx_build_scattered", "mcb_idx_get", "mcb_idx_destroy", "mcb_idx_stats", "mcb_idx_arrays",
     "mcb_combine", "mcb_realign", "mcb_sketch_lh_host", "mcb_sketch_two_host", "mcb_hash64",
@@ -92,6 +98,16 @@ def load_library() -> C.CDLL:
     lib.mcb_for_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_ReadsResult)]
     lib.mcb_for_reads_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_ReadsResult)]
     lib.mcb_for_reads_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.POINTER(_ReadsResult)]
+    lib.mcb_for_reads_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_ReadsResult)]
+    lib.mcb_for_reads_packed_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_ReadsResult)]
+    lib.mcb_readset_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.mcb_readset_destroy.argtypes = [C.c_void_p]
+    lib.mcb_readset_destroy.restype = None
+    lib.mcb_readset_add_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.mcb_readset_add_fastq_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.mcb_readset_add_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    lib.mcb_readset_get.argtypes = [C.c_void_p, C.POINTER(_ReadsetView)]
+    lib.mcb_readset_get.restype = None
     lib.mcb_debug_read_tuples.argtypes = [C.c_void_p, C.c_void_p]
     lib.mcb_debug_sketch_two.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     lib.mcb_debug_unpack_reads.argtypes = [C.c_void_p, C.c_void_p]
@@ -234,6 +250,77 @@ class RealignResult:
     numdict: int
 
 
+class ReadSet:
+    """mcb_readset: reads parsed from FASTQ (or packed from rows) into the device layout, on the host.
+    Host code only; needs no GPU (the rows are page-locked when there is one)."""
+
+    def __init__(self, readlen: int):
+        self.lib = load_library()
+        self.readlen = readlen
+        h = C.c_void_p(0)
+        self._check(self.lib.mcb_readset_create(readlen, C.byref(h)))
+        self._h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise McbError(f"minicom_b200 error {rc}: {self.lib.mcb_last_error().decode()}")
+
+    def _add(self, call, want_ascii):
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        a, n = C.c_void_p(0), C.c_uint64(0)
+        self._check(call(C.byref(a) if want_ascii else None, C.byref(n)))
+        if not want_ascii:
+            return int(n.value)
+        L = self.readlen
+        rows = np.zeros((n.value, L), dtype=np.uint8)
+        if n.value:
+            blob = np.frombuffer((C.c_char * (n.value * (L + 1))).from_address(a.value), dtype=np.uint8).reshape(n.value, L + 1)
+            assert (blob[:, L] == 0).all()
+            rows[:] = blob[:, :L]
+            libc.free(a)
+        return rows
+
+    def add_fastq(self, path: str, n_threads: int = 1, want_ascii: bool = False):
+        """appends every record of the file; returns the number of reads added, or (want_ascii) their rows as the host stages see them"""
+        return self._add(lambda a, n: self.lib.mcb_readset_add_fastq(self._h, path.encode(), n_threads, a, n), want_ascii)
+
+    def add_fastq_buffer(self, data: bytes, n_threads: int = 1, want_ascii: bool = False):
+        return self._add(lambda a, n: self.lib.mcb_readset_add_fastq_buffer(self._h, data, len(data), n_threads, a, n), want_ascii)
+
+    def add_rows(self, rows: np.ndarray, n_threads: int = 1) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        assert rows.ndim == 2 and rows.shape[1] == self.readlen
+        self._check(self.lib.mcb_readset_add_rows(self._h, rows.ctypes.data, rows.shape[0], n_threads))
+
+    def view(self) -> _ReadsetView:
+        v = _ReadsetView()
+        self.lib.mcb_readset_get(self._h, C.byref(v))
+        return v
+
+    def arrays(self):
+        """(packed u64[n][WS], nread_rid u32[nn], nmask u64[nn][WS]) as numpy views of the read set's own memory"""
+        v = self.view()
+        ws = v.row_words
+
+        def arr(ptr, count, dt):
+            if not count or not ptr:
+                return np.zeros(0, dtype=dt)
+            return np.frombuffer((C.c_char * (int(count) * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt)
+        return arr(v.packed, v.n_reads * ws, np.uint64).reshape(-1, ws), arr(v.nread_rid, v.n_nreads, np.uint32), arr(v.nmask, v.n_nreads * ws, np.uint64).reshape(-1, ws)
+
+    def __len__(self):
+        return int(self.view().n_reads)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mcb_readset_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
 class Index:
     def __init__(self, lib, handle):
         self._lib, self._h = lib, handle
@@ -304,6 +391,20 @@ class Context:
         assert rows.ndim == 2 and rows.shape[1] == self.params.readlen
         r = _ReadsResult()
         self._check(self.lib.mcb_for_reads(self._h, rows.ctypes.data, rows.shape[0], C.byref(r)))
+        return self._reads_result(r)
+
+    def for_reads_packed(self, packed, nread_rid=None, nmask=None) -> ReadsResult:
+        """packed: a ReadSet, or u64[n][WS] rows with the side table of the reads that contain N"""
+        r = _ReadsResult()
+        if isinstance(packed, ReadSet):
+            v = packed.view()
+            assert v.readlen == self.params.readlen
+            self._check(self.lib.mcb_for_reads_packed(self._h, v.packed, v.n_reads, v.nread_rid, v.nmask, v.n_nreads, C.byref(r)))
+            return self._reads_result(r)
+        packed = np.ascontiguousarray(packed, dtype=np.uint64)
+        nread_rid = np.ascontiguousarray(nread_rid if nread_rid is not None else np.zeros(0), dtype=np.uint32)
+        nmask = np.ascontiguousarray(nmask if nmask is not None else np.zeros(0), dtype=np.uint64)
+        self._check(self.lib.mcb_for_reads_packed(self._h, packed.ctypes.data, packed.shape[0], nread_rid.ctypes.data, nmask.ctypes.data, len(nread_rid), C.byref(r)))
         return self._reads_result(r)
 
     def for_reads_device(self, dptr: int, n: int) -> ReadsResult:

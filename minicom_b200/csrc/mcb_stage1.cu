@@ -166,6 +166,127 @@ __global__ void k_hasn_extract(const uint8_t *__restrict__ ascii, uint8_t *__res
 	nrepl[o] = repl < 0 ? 0 : (uint8_t)"ACGT"[repl];
 }
 
+// ---------------------------------------------------------------- kt_for_reads on packed rows (N3: the host parser of
+// mcb_fastq.cu already turned the characters into 2-bit codes, N as code 0 + a side table of N masks)
+__global__ void k_mark_nreads(const uint32_t *__restrict__ nrid_local, uint64_t nn, uint64_t n, uint32_t *__restrict__ bits, unsigned long long *__restrict__ counters)
+{
+	uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= nn) return;
+	const uint32_t r = nrid_local[j];
+	if (r >= n || (j && nrid_local[j - 1] >= r)) { atomicAdd(&counters[CT_BADCHAR], 1ull); return; }      // out of range / not ascending
+	atomicOr(&bits[r >> 5], 1u << (r & 31));
+}
+
+// A, C, G, T counts of a packed row whose unused bits are zero (N positions, code 0, are taken out of `a` by the caller)
+__device__ __forceinline__ bool mcb_count_packed(const uint64_t *row, int L, int Wd, int WS, McbCounts *q)
+{
+	int nt = 0, ng = 0, nc = 0;
+	bool bad = false;
+#pragma unroll
+	for (int w = 0; w < 8; ++w) {
+		if (w < WS) {
+			const uint64_t v = row[w];
+			if (w < Wd) {
+				const uint64_t lo = v & 0x5555555555555555ull, hi = (v >> 1) & 0x5555555555555555ull;
+				nt += __popcll(lo & hi); ng += __popcll(hi & ~lo); nc += __popcll(lo & ~hi);
+				const int lim = L - w * 32;
+				if (lim < 32 && (v >> (2 * lim))) bad = true;
+			} else if (v) bad = true;
+		}
+	}
+	q->t = nt; q->g = ng; q->c = nc; q->n = 0; q->a = L - nt - ng - nc;
+	return bad;
+}
+
+// thread per read without N: classification from popcounts, sketch, sort element.  src == dst when the rows were uploaded in
+// place; otherwise (rows resident in the caller's device buffer) the row is also copied into the context's read table
+__global__ void __launch_bounds__(RD_THREADS)
+k_classify_sketch_packed(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, uint64_t n, uint64_t lid0, uint64_t rid_base, int L, int Wd, int WS, int k, int e, int pbase,
+                         const uint32_t *__restrict__ hasn_bits, uint8_t *__restrict__ cls, ulonglong2 *__restrict__ elem, unsigned long long *__restrict__ counters)
+{
+	__shared__ uint64_t sp[RD_THREADS][9];
+	const int t = threadIdx.x;
+	const uint64_t i = (uint64_t)blockIdx.x * RD_THREADS + t;
+	bool sketched = false, bad = false, degenerate = false;
+	if (i < n) {
+		const uint64_t lid = lid0 + i, rid = rid_base + lid;
+		const bool hasn = hasn_bits && ((hasn_bits[lid >> 5] >> (lid & 31)) & 1u);
+		if (!hasn) {                                              // reads with N: k_nreads_packed
+			const uint4 *s4 = (const uint4*)(src + i * WS);
+#pragma unroll
+			for (int v = 0; v < 4; ++v)
+				if (2 * v < WS) {
+					const uint4 q4 = s4[v];
+					sp[t][2 * v] = (uint64_t)q4.y << 32 | q4.x; sp[t][2 * v + 1] = (uint64_t)q4.w << 32 | q4.z;
+					if (dst != src) ((uint4*)(dst + i * WS))[v] = q4;
+				}
+			McbCounts q;
+			bad = mcb_count_packed(sp[t], L, Wd, WS, &q);
+			int repl;
+			const int c = mcb_classify(q, L, e, &repl);
+			cls[lid] = (uint8_t)c;
+			ulonglong2 el; el.x = MCB_K1_INVALID; el.y = mcb_make_k2_invalid((uint32_t)rid);
+			if (c == MCB_CLS_SKETCHED && !bad) {
+				int pos, z;
+				const uint64_t x = mcb_sketch_two_packed(sp[t], L, k, &pos, &z);
+				if (x == ~0ull) degenerate = true;
+				else { el.x = mcb_make_k1(x); el.y = mcb_make_k2((uint32_t)rid, pos, z, L, k, pbase); sketched = true; }
+			}
+			elem[lid] = el;
+		}
+	}
+	unsigned m;
+	m = __ballot_sync(0xFFFFFFFFu, sketched);   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_SKETCHED], (unsigned long long)__popc(m));
+	m = __ballot_sync(0xFFFFFFFFu, bad);        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_BADCHAR], (unsigned long long)__popc(m));
+	m = __ballot_sync(0xFFFFFFFFu, degenerate); if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CT_DEGENERATE], (unsigned long long)__popc(m));
+}
+
+// thread per read with N: counts with the mask, classification, N replacement in the read table (kthread_reads.c:185-204), sketch,
+// and the context's side table (global read id, mask, replacement character)
+__global__ void __launch_bounds__(RD_THREADS)
+k_nreads_packed(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, const uint32_t *__restrict__ nrid_local, const uint64_t *__restrict__ nmask, uint64_t nn, uint64_t n,
+                uint64_t rid_base, int L, int Wd, int WS, int k, int e, int pbase, uint32_t *__restrict__ nrid_out, uint8_t *__restrict__ nrepl,
+                uint8_t *__restrict__ cls, ulonglong2 *__restrict__ elem, unsigned long long *__restrict__ counters)
+{
+	__shared__ uint64_t sp[RD_THREADS][9];
+	const int t = threadIdx.x;
+	const uint64_t j = (uint64_t)blockIdx.x * RD_THREADS + t;
+	if (j >= nn) return;
+	const uint64_t lid = nrid_local[j];
+	if (lid >= n) return;                                        // counted by k_mark_nreads
+	const uint64_t rid = rid_base + lid;
+	nrid_out[j] = (uint32_t)rid;
+	for (int w = 0; w < WS; ++w) sp[t][w] = src[lid * WS + w];
+	McbCounts q;
+	bool bad = mcb_count_packed(sp[t], L, Wd, WS, &q);
+	int nn_ = 0;
+	for (int w = 0; w < WS; ++w) {
+		const uint64_t m = nmask[j * WS + w];
+		const int lim = L - w * 32;
+		if ((m & 0xAAAAAAAAAAAAAAAAull) || (lim <= 0 && m) || (lim > 0 && lim < 32 && (m >> (2 * lim))) || (sp[t][w] & (m * 3ull))) bad = true;
+		nn_ += __popcll(m);
+	}
+	if (nn_ == 0) bad = true;                                    // listed as a read with N, but has none
+	q.n = nn_; q.a -= nn_;
+	int repl;
+	const int c = mcb_classify(q, L, e, &repl);
+	nrepl[j] = repl < 0 ? 0 : (uint8_t)"ACGT"[repl];
+	if (c == MCB_CLS_SKETCHED && repl > 0)
+		for (int w = 0; w < Wd; ++w) sp[t][w] |= nmask[j * WS + w] * (uint64_t)repl;
+	for (int w = 0; w < WS; ++w) dst[lid * WS + w] = sp[t][w];
+	cls[lid] = (uint8_t)c;
+	ulonglong2 el; el.x = MCB_K1_INVALID; el.y = mcb_make_k2_invalid((uint32_t)rid);
+	if (bad) atomicAdd(&counters[CT_BADCHAR], 1ull);
+	else if (c == MCB_CLS_SKETCHED) {
+		int pos, z;
+		const uint64_t x = mcb_sketch_two_packed(sp[t], L, k, &pos, &z);
+		if (x == ~0ull) atomicAdd(&counters[CT_DEGENERATE], 1ull);
+		else { el.x = mcb_make_k1(x); el.y = mcb_make_k2((uint32_t)rid, pos, z, L, k, pbase); atomicAdd(&counters[CT_SKETCHED], 1ull); }
+	}
+	elem[lid] = el;
+	atomicAdd(&counters[CT_NREADS], 1ull);
+}
+
 // batched mm_sketch_two over already packed reads (rounds >= 2: kthread_bucket.c:205,489)
 __global__ void k_resketch(const uint64_t *__restrict__ packed, int WS, int L, int k_orig, int kmer, int pbase,
                            const uint32_t *__restrict__ rids, uint64_t n, ulonglong2 *__restrict__ elem, unsigned long long *__restrict__ counters)
@@ -905,6 +1026,160 @@ extern "C" int mcb_for_reads_ptrs(mcb_ctx *ctx, const void *first_seq_ptr, size_
 		cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
 	}
 	return mcb_for_reads_device(ctx, ctx->d_ascii.as<char>(), n, res);
+}
+
+// ---------------------------------------------------------------- kt_for_reads on packed rows
+// rows / nrid / nmask: host memory (on_device = false: page-locked rows are uploaded chunk by chunk on the copy stream, straight
+// into the read table, and the kernel of a chunk runs while the next chunk is on the bus) or device memory (on_device = true)
+static int for_reads_packed_impl(mcb_ctx *ctx, const uint64_t *rows, uint64_t n, const uint32_t *nrid, const uint64_t *nmask, uint64_t nn, bool on_device, mcb_reads_result *res)
+{
+	const int L = ctx->L, Wd = ctx->Wd, WS = ctx->WS;
+	const int pbase = L + ctx->prm.max_rounds;
+	if (nn > n) { mcb_set_error("mcb_for_reads_packed: more reads with N (%llu) than reads (%llu)", (unsigned long long)nn, (unsigned long long)n); return MCB_EINVAL; }
+	if (ctx->shard_n > 1) {
+		if (ctx->rid_base + n > ctx->n_reads) { mcb_set_error("mcb_for_reads_packed: slice [%llu,+%llu) exceeds the %llu reads declared by mcb_shard_begin", (unsigned long long)ctx->rid_base, (unsigned long long)n, (unsigned long long)ctx->n_reads); return MCB_EINVAL; }
+	} else { ctx->n_reads = n; ctx->rid_base = 0; }
+	ctx->n_local = n; ctx->reads_loaded = false; ctx->bucket_done = false; ctx->bs.active = false;
+	ctx->cix.valid = false;
+	const uint64_t rid_base = ctx->rid_base;
+	MCB_TRY(ctx->d_packed.ensure((size_t)(ctx->n_reads + ctx->shard_n) * WS * 8 + 16));
+	MCB_TRY(ctx->d_cls.ensure(n + 16));
+	ctx->elem_cap = std::min(ctx->d_elemA.cap, ctx->d_elemB.cap) / 16;
+	MCB_TRY(ensure_elems(ctx, n + 1, false));
+	MCB_TRY(ctx->d_counters.ensure(64 * 8));
+	MCB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64 * 8, ctx->stream));
+	unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+	unsigned long long *hc = nullptr;
+	uint64_t *slice = ctx->d_packed.as<uint64_t>() + rid_base * WS;
+	// ---- side table of the reads with N, and the bitmap that keeps the main kernel off them
+	MCB_TRY(ctx->d_nread_rid.ensure(nn * 4 + 16));
+	MCB_TRY(ctx->d_nread_mask.ensure(nn * WS * 8 + 16));
+	MCB_TRY(ctx->d_scr[0].ensure((n / 32 + 1) * 4 + 16));
+	MCB_TRY(ctx->d_scr[1].ensure(nn + 16));
+	MCB_TRY(ctx->d_scr[2].ensure(nn * 4 + 16));
+	const uint32_t *d_nrid_local = nullptr;
+	const uint64_t *d_nmask = nullptr;
+	uint32_t *bits = nullptr;
+	if (nn) {
+		if (on_device) { d_nrid_local = nrid; d_nmask = nmask; }
+		else {
+			McbSpan sp(ctx->tm, "h2d");
+			MCB_TRY(mcb_h2d(ctx, ctx->d_scr[2].p, nrid, nn * 4, 1));
+			MCB_TRY(mcb_h2d(ctx, ctx->d_nread_mask.p, nmask, nn * WS * 8, 1));
+			d_nrid_local = ctx->d_scr[2].as<uint32_t>(); d_nmask = ctx->d_nread_mask.as<uint64_t>();
+		}
+		McbSpan sp(ctx->tm, "for_reads");
+		bits = ctx->d_scr[0].as<uint32_t>();
+		MCB_CUDA(cudaMemsetAsync(bits, 0, (n / 32 + 1) * 4, ctx->stream));
+		MCB_LAUNCH(ctx, "mark_nreads", k_mark_nreads, mcb_grid_for(nn, 256), 256, 0, d_nrid_local, nn, n, bits, dc);
+	}
+	// ---- the rows
+	bool pinned = false;
+	if (!on_device && n) {
+		cudaPointerAttributes pa;
+		pinned = cudaPointerGetAttributes(&pa, rows) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+	}
+	if (n && (on_device || !pinned)) {
+		const uint64_t *src = rows;
+		if (!on_device) {
+			McbSpan sp(ctx->tm, "h2d");
+			MCB_TRY(mcb_h2d(ctx, slice, rows, (size_t)n * WS * 8, 4));
+			src = slice;
+		}
+		McbSpan sp(ctx->tm, "for_reads");
+		MCB_LAUNCH(ctx, "classify_sketch_packed", k_classify_sketch_packed, mcb_grid_for(n, RD_THREADS), RD_THREADS, 0, src, slice, n, (uint64_t)0, rid_base, L, Wd, WS,
+		           ctx->prm.k, ctx->prm.diff_threshold, pbase, bits, ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+		if (nn) MCB_LAUNCH(ctx, "nreads_packed", k_nreads_packed, mcb_grid_for(nn, RD_THREADS), RD_THREADS, 0, src, slice, d_nrid_local, d_nmask, nn, n, rid_base, L, Wd, WS,
+		                   ctx->prm.k, ctx->prm.diff_threshold, pbase, ctx->d_nread_rid.as<uint32_t>(), ctx->d_scr[1].as<uint8_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+	} else if (n) {
+		if (!ctx->copy_stream) MCB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+		const uint64_t CH = 1u << 21;                                   // reads per chunk: 64 MB at L = 100
+		const int nch = (int)((n + CH - 1) / CH);
+		std::vector<cudaEvent_t> ev((size_t)nch);
+		cudaEvent_t t0, t1;
+		cudaEventCreate(&t0); cudaEventCreate(&t1);
+		cudaEventRecord(t0, ctx->copy_stream);
+		for (int c = 0; c < nch; ++c) {
+			const uint64_t off = (uint64_t)c * CH, cnt = std::min(CH, n - off);
+			cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming);
+			MCB_CUDA(cudaMemcpyAsync(slice + off * WS, rows + off * WS, cnt * WS * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+			cudaEventRecord(ev[c], ctx->copy_stream);
+		}
+		cudaEventRecord(t1, ctx->copy_stream);
+		for (int c = 0; c < nch; ++c) {
+			const uint64_t off = (uint64_t)c * CH, cnt = std::min(CH, n - off);
+			MCB_CUDA(cudaStreamWaitEvent(ctx->stream, ev[c], 0));
+			McbSpan sp(ctx->tm, "for_reads");
+			MCB_LAUNCH(ctx, "classify_sketch_packed", k_classify_sketch_packed, mcb_grid_for(cnt, RD_THREADS), RD_THREADS, 0, slice + off * WS, slice + off * WS, cnt, off, rid_base, L, Wd, WS,
+			           ctx->prm.k, ctx->prm.diff_threshold, pbase, bits, ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+		}
+		if (nn) {
+			McbSpan sp(ctx->tm, "for_reads");
+			MCB_LAUNCH(ctx, "nreads_packed", k_nreads_packed, mcb_grid_for(nn, RD_THREADS), RD_THREADS, 0, slice, slice, d_nrid_local, d_nmask, nn, n, rid_base, L, Wd, WS,
+			           ctx->prm.k, ctx->prm.diff_threshold, pbase, ctx->d_nread_rid.as<uint32_t>(), ctx->d_scr[1].as<uint8_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+		}
+		MCB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (ctx->tm.enabled) { float ms = 0; if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) { int id = ctx->tm.id("h2d"); ctx->tm.ms[id] += ms; ctx->tm.cnt[id] += 1; } }
+		for (auto e : ev) cudaEventDestroy(e);
+		cudaEventDestroy(t0); cudaEventDestroy(t1);
+	}
+	if (on_device && nn && d_nmask != ctx->d_nread_mask.as<uint64_t>())
+		MCB_CUDA(cudaMemcpyAsync(ctx->d_nread_mask.p, d_nmask, nn * WS * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	MCB_TRY(sync_counters(ctx, &hc));
+	if (hc[CT_BADCHAR]) { mcb_set_error("%llu packed reads are malformed (non-zero unused bits, or an N table that is unsorted, out of range or inconsistent with the rows)", hc[CT_BADCHAR]); return MCB_EINPUT; }
+	if (hc[CT_DEGENERATE]) { mcb_set_error("%llu reads have no valid k-mer (reference would index read 0xFFFFFFFF)", hc[CT_DEGENERATE]); return MCB_EINPUT; }
+	if (hc[CT_NREADS] != nn) { mcb_set_error("internal: %llu of %llu reads with N processed", hc[CT_NREADS], (unsigned long long)nn); return MCB_ECUDA; }
+	ctx->n_valid_round1 = hc[CT_SKETCHED]; ctx->n_nreads = nn;
+	// ---- results to the host
+	MCB_TRY(ctx->h_cls.ensure(n + 16));
+	MCB_TRY(ctx->h_nrid.ensure(nn * 4 + 16));
+	MCB_TRY(ctx->h_nrepl.ensure(nn + 16));
+	MCB_TRY(ctx->h_nmask.ensure(nn * WS * 8 + 16));
+	{
+		McbSpan sp(ctx->tm, "d2h");
+		if (n) MCB_CUDA(cudaMemcpyAsync(ctx->h_cls.p, ctx->d_cls.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+		if (nn) {
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_nrid.p, ctx->d_nread_rid.p, nn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			MCB_CUDA(cudaMemcpyAsync(ctx->h_nrepl.p, ctx->d_scr[1].p, nn, cudaMemcpyDeviceToHost, ctx->stream));
+			if (on_device) MCB_CUDA(cudaMemcpyAsync(ctx->h_nmask.p, ctx->d_nread_mask.p, nn * WS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+	}
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->tm.collect();
+	const uint64_t *nm = on_device ? ctx->h_nmask.as<uint64_t>() : nmask;       // the caller's masks are the N positions
+	MCB_TRY(ctx->h_noff.ensure((nn + 1) * 8));
+	uint64_t *noff = ctx->h_noff.as<uint64_t>();
+	uint64_t tot = 0;
+	for (uint64_t i = 0; i < nn; ++i) { noff[i] = tot; for (int w = 0; w < Wd; ++w) tot += __builtin_popcountll(nm[i * WS + w]); }
+	noff[nn] = tot;
+	MCB_TRY(ctx->h_npos.ensure(tot * 4 + 16));
+	uint32_t *np = ctx->h_npos.as<uint32_t>();
+	for (uint64_t i = 0, o = 0; i < nn; ++i)
+		for (int w = 0; w < Wd; ++w) { uint64_t m = nm[i * WS + w]; while (m) { int bit = __builtin_ctzll(m); np[o++] = (uint32_t)(w * 32 + bit / 2); m &= m - 1; } }
+	res->n_reads = n; res->cls = ctx->h_cls.as<uint8_t>();
+	res->n_nreads = nn; res->nread_rid = ctx->h_nrid.as<uint32_t>(); res->nread_repl = ctx->h_nrepl.as<uint8_t>();
+	res->nread_off = noff; res->npos = np; res->n_sketched = hc[CT_SKETCHED];
+	ctx->reads_loaded = true;
+	return MCB_OK;
+}
+
+extern "C" int mcb_for_reads_packed(mcb_ctx *ctx, const uint64_t *packed, uint64_t n, const uint32_t *nread_rid, const uint64_t *nmask, uint64_t n_nreads, mcb_reads_result *res)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!res || (n && !packed) || (n_nreads && (!nread_rid || !nmask))) { mcb_set_error("mcb_for_reads_packed: null argument"); return MCB_EINVAL; }
+	if (n >= (1ull << 31)) { mcb_set_error("too many reads (rid is a signed 32-bit int in the reference, kthread_bucket.c:48)"); return MCB_EINVAL; }
+	return for_reads_packed_impl(ctx, packed, n, nread_rid, nmask, n_nreads, false, res);
+}
+
+extern "C" int mcb_for_reads_packed_device(mcb_ctx *ctx, const uint64_t *d_packed, uint64_t n, const uint32_t *d_nread_rid, const uint64_t *d_nmask, uint64_t n_nreads, mcb_reads_result *res)
+{
+	MCB_TRY(check_ctx(ctx));
+	if (!res || (n && !d_packed) || (n_nreads && (!d_nread_rid || !d_nmask))) { mcb_set_error("mcb_for_reads_packed_device: null argument"); return MCB_EINVAL; }
+	if (((uintptr_t)d_packed & 15) != 0) { mcb_set_error("mcb_for_reads_packed_device: rows must be 16-byte aligned"); return MCB_EINVAL; }
+	if (n >= (1ull << 31)) { mcb_set_error("too many reads (rid is a signed 32-bit int in the reference, kthread_bucket.c:48)"); return MCB_EINVAL; }
+	return for_reads_packed_impl(ctx, d_packed, n, d_nread_rid, d_nmask, n_nreads, true, res);
 }
 
 extern "C" int mcb_debug_read_tuples(mcb_ctx *ctx, mcb_tuple *out)

@@ -917,3 +917,85 @@ void mco_realign_free(mco_realign_out *o)
 	if (!o) return;
 	free(o->claim_contig.a); free(o->claim_sg.a); free(o->claim_y.a); free(o->fpA.a); free(o->fpT.a); free(o->flag); free(o);
 }
+
+/* ------------------------------------------------------------------ N3: FASTQ records (bseq.c:38-66, kseq.h:185-224) */
+/* kseq's buffered stream over a file, here over memory: ks_getc (kseq.h:78-91) and ks_getuntil2 (kseq.h:94-141) */
+typedef struct { const unsigned char *p; size_t n, at; } mco_stream;
+static int st_getc(mco_stream *s) { return s->at < s->n ? s->p[s->at++] : -1; }
+static int st_isspace(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+/* delimiter 0 = white space, 2 = newline (KS_SEP_SPACE / KS_SEP_LINE); returns the string length or -1 at end of input */
+static long st_getuntil(mco_stream *s, int delimiter, vec_chr *str, int *dret, int append)
+{
+	if (dret) *dret = 0;
+	if (!append) str->n = 0;
+	if (s->at >= s->n) return -1;
+	while (s->at < s->n) {
+		int c = s->p[s->at++];
+		if (delimiter == 2 ? c == '\n' : st_isspace(c)) { if (dret) *dret = c; break; }
+		vpush(char, *str, (char)c);
+	}
+	if (delimiter == 2 && str->n > 1 && str->a[str->n - 1] == '\r') --str->n;     /* kseq.h:138 */
+	return (long)str->n;
+}
+
+/* kseq_read + the loop of bseq_read: every sequence of the input, concatenated into seqs (no terminators), its length in
+ * lens[i]; stops like the reference at end of input or at the first record whose quality string is missing or of another
+ * length (kseq_read < 0, bseq.c:44).  Returns the number of sequences. */
+int64_t mco_kseq_all(const char *buf, uint64_t len, char *seqs, uint64_t seqs_cap, uint32_t *lens, int64_t lens_cap)
+{
+	mco_stream s = { (const unsigned char*)buf, (size_t)len, 0 };
+	vec_chr name = {0, 0, 0}, comment = {0, 0, 0}, seq = {0, 0, 0}, qual = {0, 0, 0};
+	int last_char = 0, c;
+	int64_t n = 0;
+	uint64_t used = 0;
+	for (;;) {
+		if (last_char == 0) {                                    /* kseq.h:189-193 */
+			while ((c = st_getc(&s)) != -1 && c != '>' && c != '@');
+			if (c == -1) break;
+			last_char = c;
+		}
+		seq.n = qual.n = comment.n = 0;
+		if (st_getuntil(&s, 0, &name, &c, 0) < 0) break;          /* :195 */
+		if (c != '\n') st_getuntil(&s, 2, &comment, 0, 0);        /* :196 */
+		while ((c = st_getc(&s)) != -1 && c != '>' && c != '+' && c != '@') {   /* :201-205 */
+			if (c == '\n') continue;
+			vpush(char, seq, (char)c);
+			st_getuntil(&s, 2, &seq, 0, 1);
+		}
+		if (c == '>' || c == '@') last_char = c;                  /* :206 */
+		if (c == '+') {                                           /* :213-222 */
+			while ((c = st_getc(&s)) != -1 && c != '\n');
+			if (c == -1) break;                                   /* -2: no quality string */
+			while (st_getuntil(&s, 2, &qual, 0, 1) >= 0 && qual.n < seq.n);
+			last_char = 0;
+			if (seq.n != qual.n) break;                           /* -2 */
+		}
+		if (n < lens_cap) lens[n] = (uint32_t)seq.n;
+		if (used + seq.n <= seqs_cap) memcpy(seqs + used, seq.a, seq.n);
+		used += seq.n; ++n;
+	}
+	free(name.a); free(comment.a); free(seq.a); free(qual.a);
+	return n;
+}
+
+/* one read in the device layout: base j -> word j/32, bits 2*(j%32), A0 C1 G2 T3 (seq_nt4_table, upper case
+ * only: process_reads counts nothing else, kthread_reads.c:56-73), N as code 0 with its position in mask (seq->n_pos, :69-80).
+ * Returns 0, 1 (has N) or -1 (a character outside ACGTN). */
+int mco_pack_row(const char *s, int L, int WS, uint64_t *row, uint64_t *mask)
+{
+	int hasn = 0;
+	for (int w = 0; w < WS; ++w) row[w] = mask[w] = 0;
+	for (int j = 0; j < L; ++j) {
+		uint64_t code;
+		switch (s[j]) {
+		case 'A': code = 0; break;
+		case 'C': code = 1; break;
+		case 'G': code = 2; break;
+		case 'T': code = 3; break;
+		case 'N': code = 0; hasn = 1; mask[j / 32] |= 1ull << (2 * (j % 32)); break;
+		default: return -1;
+		}
+		row[j / 32] |= code << (2 * (j % 32));
+	}
+	return hasn;
+}

@@ -53,8 +53,8 @@ if [ ! -x "$OUT/decompress" ]; then
   g++ -O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -include stdint.h -I$B -I$HERE -I$HERE/../../dropin -I$REF "$REF/decompress.c" -o "$OUT/decompress" -lm -lz -lpthread
 fi
 echo "built $OUT/minicom_ref_L${L}_${MODE}"
-# unit-level entry points of the reference (hash64, mm_sketch_two, mm_sketch_lh_ori, radix_sort_128x) for ctypes tests
-if [ ! -f "$OUT/libmcref_units.so" ] || [ "$HERE/mcref_units.cpp" -nt "$OUT/libmcref_units.so" ]; then
-  g++ -O2 -std=c++11 -w -fPIC -shared -I$B -I$HERE -I$HERE/../../dropin -I$REF "$HERE/mcref_units.cpp" "$HERE/mcref_units_sort.cpp" "$REF/misc.c" -o "$OUT/libmcref_units.so"
+# unit-level entry points of the reference (hash64, mm_sketch_two, mm_sketch_lh_ori, radix_sort_128x, bseq_read) for ctypes tests
+if [ ! -f "$OUT/libmcref_units.so" ] || [ "$HERE/mcref_units.cpp" -nt "$OUT/libmcref_units.so" ] || [ "$HERE/mcref_units_bseq.cpp" -nt "$OUT/libmcref_units.so" ]; then
+  g++ -O2 -std=c++11 -w -fPIC -shared -I$B -I$HERE -I$HERE/../../dropin -I$REF "$HERE/mcref_units.cpp" "$HERE/mcref_units_sort.cpp" "$HERE/mcref_units_bseq.cpp" "$REF/misc.c" "$REF/bseq.c" -o "$OUT/libmcref_units.so" -lz
   echo "built $OUT/libmcref_units.so"
 fi

@@ -7,7 +7,7 @@ TAG=${1:-r1}; WL=${2:-C2}; STEPS=${3:-tests,bench,launches,full}
 O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi_$TAG.txt 2>&1
 if [[ $STEPS == *tests* ]]; then
-  python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu_$TAG.log; tail -5 $O/pytest_gpu_$TAG.log
+  T0=$(date +%s); python -m pytest tests -m gpu -x -q --durations=15 > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$? ($(( $(date +%s) - T0 )) s)" | tee -a $O/pytest_gpu_$TAG.log; tail -5 $O/pytest_gpu_$TAG.log
 fi
 if [[ $STEPS == *bench* ]]; then
   python bench.py --workload $WL --steps 3 --warmup 3 > $O/bench_${WL}_$TAG.json 2> $O/bench_${WL}_$TAG.err; echo "bench rc=$?"
@@ -19,8 +19,8 @@ if [[ $STEPS == *launches* ]]; then
   echo "ncu launches rc=$?"
 fi
 if [[ $STEPS == *full* ]]; then
-  KREGEX=${KREGEX:-'regex:k_s2_|k_index_sort|k_consensus|k_pack_classify|k_sketch_lh'}
-  $CMD > $O/plain2_$TAG.log 2>&1 &&
+  KREGEX=${KREGEX:-'regex:k_s2_|k_ix_|k_index_sort|k_consensus|k_pack_classify|k_sketch_lh|k_resketch|k_sort_|k_bucket_local|k_cb_match|k_cb_consensus'}
+  { [[ $STEPS == *launches* ]] || $CMD > $O/plain2_$TAG.log 2>&1; } &&
   ncu --target-processes application-only --set full --clock-control none -k "$KREGEX" -c ${KCOUNT:-40} -o $O/prof_${WL}_$TAG -f $CMD > $O/ncu_full_$TAG.log 2>&1
   echo "ncu full rc=$?"
   ncu -i $O/prof_${WL}_$TAG.ncu-rep --page raw --csv > $O/prof_${WL}_${TAG}_raw.csv 2> /dev/null

@@ -35,6 +35,9 @@ def lib():
         L.mco_radix_sort_x.argtypes = [C.c_void_p, C.c_int64]
         L.mco_classify.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p]
         L.mco_encode_byte_ok.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.mco_kseq_all.restype = C.c_int64
+        L.mco_kseq_all.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64]
+        L.mco_pack_row.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mco_stage1_run.restype = C.c_void_p
         L.mco_stage1_run.argtypes = [C.POINTER(Params), C.c_void_p, C.c_uint64]
         L.mco_stage1_free.argtypes = [C.c_void_p]
@@ -106,6 +109,29 @@ def classify(seq: bytes, e: int):
     repl = C.create_string_buffer(2)
     c = lib().mco_classify(seq, len(seq), e, repl)
     return c, repl.raw[:1] if repl.raw[0] else b""
+
+
+def kseq_all(data: bytes):
+    """every sequence kseq_read / bseq_read would deliver from the file contents `data` (list of bytes)"""
+    seqs = np.zeros(len(data) + 1, dtype=np.uint8)
+    lens = np.zeros(len(data) // 2 + 2, dtype=np.uint32)
+    n = lib().mco_kseq_all(data, len(data), seqs.ctypes.data, len(seqs), lens.ctypes.data, len(lens))
+    out, o = [], 0
+    for i in range(n):
+        out.append(seqs[o:o + int(lens[i])].tobytes())
+        o += int(lens[i])
+    return out
+
+
+def pack_rows(rows: np.ndarray):
+    """(packed u64[n][WS], mask u64[n][WS], status[n]) of ASCII rows in the device layout; status 0 / 1 (has N) / -1 (bad character)"""
+    n, L = rows.shape
+    ws = (((L + 31) // 32) + 1) & ~1
+    packed, mask, st = np.zeros((n, ws), np.uint64), np.zeros((n, ws), np.uint64), np.zeros(n, np.int32)
+    f = lib().mco_pack_row
+    for i in range(n):
+        st[i] = f(rows[i].tobytes(), L, ws, packed[i].ctypes.data, mask[i].ctypes.data)
+    return packed, mask, st
 
 
 def encode_byte_ok(read_oriented: bytes, ref_window: bytes):
