@@ -26,20 +26,24 @@
 
 struct CbSet {                       // one contig set on the device
 	DBuf n, aoff, a, roff, ref;
+	DBuf coff;                         // u64[ncl]: where the per-column base counts of the contig start in the arena McbCombineState::cols
 	DBuf mins, moff;                   // ALL (w,k)-minimizers of every contig, contig-major in position order; moff u64[ncl+1].  The first
 	                                   // first_mininum of a contig's list are its index tuples (kthread_cb.c:359-368: the same sketch, cut short)
 	uint64_t ncl = 0, nmem = 0, nref = 0, nmin = 0;
-	void release() { n.release(); aoff.release(); a.release(); roff.release(); ref.release(); mins.release(); moff.release(); }
+	void release() { n.release(); aoff.release(); a.release(); roff.release(); ref.release(); coff.release(); mins.release(); moff.release(); }
 };
 struct McbCombineState {
 	CbSet set[2];
-	DBuf alive, best, pick, tup, tup2, boff, chn, chc, chs, cho, cho64, pcnt, cand, pass, plist, loff, cw, cwo, flag, pairs, src, keyA, keyB, len2, tmp32;
+	DBuf alive, best, pick, tup, tup2, boff, chn, chc, chs, cho, cho64, pcnt, cand, pass, plist, loff, cw, cwo, flag, pairs, src, keyA, keyB, len2, tmp32, slots;
+	DBuf cols;                         // uint4 per contig column: how many member reads put A, C, G, T there.  Append-only over the iterations:
+	uint64_t cols_used = 0;            // a merged contig's counts are the sum of its two parents' (construct_ref2 counts every member again,
+	                                   // kthread_cb.c:120-137, and counting is additive), untouched contigs keep pointing at theirs
 	HBuf h_boff, h_list, h_loff, h_pairs, h_flag, h_small;
 	HBuf h_cl_n, h_cl_a_off, h_cl_a, h_cl_ref_off, h_cl_ref;
 	void release()
 	{
-		set[0].release(); set[1].release();
-		DBuf *d[] = { &alive, &best, &pick, &tup, &tup2, &boff, &chn, &chc, &chs, &cho, &cho64, &pcnt, &cand, &pass, &plist, &loff, &cw, &cwo, &flag, &pairs, &src, &keyA, &keyB, &len2, &tmp32 };
+		set[0].release(); set[1].release(); cols.release(); cols_used = 0;
+		DBuf *d[] = { &alive, &best, &pick, &tup, &tup2, &boff, &chn, &chc, &chs, &cho, &cho64, &pcnt, &cand, &pass, &plist, &loff, &cw, &cwo, &flag, &pairs, &src, &keyA, &keyB, &len2, &tmp32, &slots };
 		for (auto b : d) b->release();
 		HBuf *h[] = { &h_boff, &h_list, &h_loff, &h_pairs, &h_flag, &h_small, &h_cl_n, &h_cl_a_off, &h_cl_a, &h_cl_ref_off, &h_cl_ref };
 		for (auto b : h) b->release();
@@ -84,10 +88,22 @@ __global__ void k_cb_contig_counts(const uint32_t *__restrict__ first, uint64_t 
 	const uint32_t a = choff[first[c]], b = c + 1 < count ? choff[first[c + 1]] : (uint32_t)*total;
 	cnt[c] = b - a;
 }
-__global__ void k_cb_widen(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out)
+__global__ void k_cb_widen(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out, const unsigned long long *__restrict__ total, uint32_t cap, unsigned long long *__restrict__ overflow)
 {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) out[i] = in[i];
+	if (i >= n) return;
+	out[i] = in[i];
+	const uint32_t cnt = (i + 1 < n ? in[i + 1] : (uint32_t)*total) - in[i];           // `in` is the exclusive scan of the per-stretch counts
+	if (cap && cnt > cap) atomicAdd(overflow, 1ull);
+}
+// the tuples a counting pass parked in fixed-size slots (k_sketch_lh2 with slot_cap) move to their place in the contig-major list
+__global__ void k_cb_unslot(const mcb_tuple *__restrict__ slots, uint32_t cap, const uint32_t *__restrict__ off, uint64_t nch, const unsigned long long *__restrict__ total, mcb_tuple *__restrict__ mins)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t t = i / cap; const uint32_t j = (uint32_t)(i - t * cap);
+	if (t >= nch) return;
+	const uint32_t o = off[t], cnt = (t + 1 < nch ? off[t + 1] : (uint32_t)*total) - o;
+	if (j < cnt) mins[(uint64_t)o + j] = slots[t * cap + j];
 }
 // minimizer lists of the untouched contigs move to the new set with their new contig id
 __global__ void k_cb_copy_min_counts(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ moff, uint32_t *__restrict__ cnt2)
@@ -338,24 +354,59 @@ __global__ void k_cb_new_lengths(uint64_t nm, const uint32_t *__restrict__ src, 
 	for (int o = 16; o; o >>= 1) len = max(len, __shfl_xor_sync(0xFFFFFFFFu, len, o));
 	if ((threadIdx.x & 31) == 0 && len) atomicMax(max_len, len);
 }
-// construct_ref2 (kthread_cb.c:105-150): one thread per column of a merged contig counts the bases the oriented members put there;
-// 'A' unless a base has strictly more votes, in the order A, C, G, T.  Members are sorted by position, so the ones covering a
-// column are a contiguous run found by binary search.
-__global__ void k_cb_consensus(uint64_t nm, const uint64_t *__restrict__ roff2, const uint64_t *__restrict__ aoff2, const uint64_t *__restrict__ a2,
-                               const uint64_t *__restrict__ packed, int WS, int L, uint64_t total_cols, char *__restrict__ ref2)
+// construct_ref2 (kthread_cb.c:105-150) recounts, for every column of a merged contig, the bases its oriented members put there;
+// the consensus is 'A' unless a base has strictly more votes, in the order A, C, G, T.  Counting is additive, so the counts of a
+// merged contig are the sums of its parents' counts, the second parent shifted by the anchor difference (:300-317): one thread per
+// column adds two uint4 and takes the majority, whatever the coverage.  The counts of the seed contigs are made once (below).
+__device__ __forceinline__ char cb_majority(uint4 v)
+{
+	unsigned best = 0, mx = v.x;
+	if (v.y > mx) { mx = v.y; best = 1; }
+	if (v.z > mx) { mx = v.z; best = 2; }
+	if (v.w > mx) { mx = v.w; best = 3; }
+	return "ACGT"[best];
+}
+__global__ void k_cb_merge_counts(const CbCand *__restrict__ pairs, uint64_t nm, const uint64_t *__restrict__ roff2, const uint64_t *__restrict__ roff, const uint64_t *__restrict__ coff,
+                                  uint4 *__restrict__ cols, uint64_t new_base, uint64_t total_cols, char *__restrict__ ref2)
 {
 	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= total_cols) return;
 	uint64_t lo = 0, hi = nm;                 // last q with roff2[q] <= g
 	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (roff2[mid] <= g) lo = mid; else hi = mid; }
+	const CbCand p = pairs[lo];
+	const uint64_t col = g - roff2[lo];
+	const bool i_first = p.pos_ori >= p.pos;
+	const uint32_t first = i_first ? p.i : p.c, second = i_first ? p.c : p.i;
+	const uint64_t shift = i_first ? p.pos_ori - p.pos : p.pos - p.pos_ori;
+	const uint64_t l1 = roff[first + 1] - roff[first], l2 = roff[second + 1] - roff[second];
+	uint4 v = make_uint4(0, 0, 0, 0);
+	if (col < l1) v = cols[coff[first] + col];
+	if (col >= shift && col - shift < l2) { const uint4 u = cols[coff[second] + col - shift]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+	cols[new_base + g] = v;
+	ref2[g] = cb_majority(v);
+}
+__global__ void k_cb_new_coff(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ roff2, const uint64_t *__restrict__ coff, uint64_t new_base, uint64_t *__restrict__ coff2)
+{
+	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q < n2) coff2[q] = q < nm ? new_base + roff2[q] : coff[src[q - nm]];
+}
+// the counts of the seed contigs: one thread per column walks the members that cover it (sorted by position: a contiguous run
+// found by binary search).  Column g of the set's concatenated consensus strings = arena entry g (coff = roff).
+__global__ void k_cb_seed_counts(uint64_t ncl, const uint64_t *__restrict__ roff, const uint64_t *__restrict__ aoff, const uint64_t *__restrict__ a,
+                                 const uint64_t *__restrict__ packed, int WS, int L, uint64_t total_cols, uint4 *__restrict__ cols)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= total_cols) return;
+	uint64_t lo = 0, hi = ncl;                // last q with roff[q] <= g
+	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (roff[mid] <= g) lo = mid; else hi = mid; }
 	const uint64_t q = lo;
-	const int64_t col = (int64_t)(g - roff2[q]);
-	const uint64_t mb = aoff2[q], me = aoff2[q + 1];
+	const int64_t col = (int64_t)(g - roff[q]);
+	const uint64_t mb = aoff[q], me = aoff[q + 1];
 	uint64_t s = mb, e = me;                  // first member with position > col - L
-	while (s < e) { const uint64_t mid = (s + e) >> 1; if ((int64_t)((uint32_t)a2[mid] >> 1) <= col - L) s = mid + 1; else e = mid; }
+	while (s < e) { const uint64_t mid = (s + e) >> 1; if ((int64_t)((uint32_t)a[mid] >> 1) <= col - L) s = mid + 1; else e = mid; }
 	uint64_t cAC = 0, cGT = 0;                // two 32-bit counters per word: no dynamically indexed (= local memory) array
 	for (uint64_t u = s; u < me; ++u) {
-		const uint64_t y = a2[u];
+		const uint64_t y = a[u];
 		const int64_t pos = (int64_t)((uint32_t)y >> 1);
 		if (pos > col) break;
 		const int p = (int)(col - pos);
@@ -364,12 +415,7 @@ __global__ void k_cb_consensus(uint64_t nm, const uint64_t *__restrict__ roff2, 
 		const uint64_t one = 1ull << (32 * (bse & 1u));
 		cAC += (bse & 2u) ? 0ull : one; cGT += (bse & 2u) ? one : 0ull;
 	}
-	const unsigned cnt0 = (unsigned)cAC, cnt1 = (unsigned)(cAC >> 32), cnt2 = (unsigned)cGT, cnt3 = (unsigned)(cGT >> 32);
-	unsigned best = 0, mx = cnt0;
-	if (cnt1 > mx) { mx = cnt1; best = 1; }
-	if (cnt2 > mx) { mx = cnt2; best = 2; }
-	if (cnt3 > mx) { mx = cnt3; best = 3; }
-	ref2[g] = "ACGT"[best];
+	cols[g] = make_uint4((unsigned)cAC, (unsigned)(cAC >> 32), (unsigned)cGT, (unsigned)(cGT >> 32));
 }
 __global__ void k_cb_copy_refs(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ roff, const char *__restrict__ ref,
                                const uint64_t *__restrict__ roff2, char *__restrict__ ref2)
@@ -383,6 +429,20 @@ __global__ void k_cb_copy_refs(uint64_t nm, const uint32_t *__restrict__ src, ui
 }
 
 // ================================================================= host
+// the count arena grows without losing what it holds
+static int cb_cols_reserve(mcb_ctx *ctx, McbCombineState &cb, uint64_t columns)
+{
+	const size_t need = (size_t)columns * 16 + 16;
+	if (need <= cb.cols.cap) return MCB_OK;
+	DBuf bigger;
+	MCB_TRY(bigger.ensure(need + need / 2));
+	if (cb.cols_used) MCB_CUDA(cudaMemcpyAsync(bigger.p, cb.cols.p, (size_t)cb.cols_used * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+	cb.cols.release();
+	cb.cols = bigger;
+	return MCB_OK;
+}
+
 static int cb_counters(mcb_ctx *ctx)          // the device scalars to the host (synchronizes)
 {
 	MCB_CUDA(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -395,7 +455,8 @@ enum { CT_CB_A = 48, CT_CB_B = 49, CT_CB_C = 50, CT_CB_D = 51, CT_CB_E = 52 };  
 // all (w,k)-minimizers (mm_sketch_lh_ori, sketch.c:116-165; window rw, kthread_cb.c:234 / :359 with win_step = 0) of the work items
 // [0, n_items) of a set: whole contigs, or stretches of contigs (ch_* given).  cnt32 receives the number of tuples per item; with
 // `emit` they are written to S.mins at off[item]
-static int cb_sketch(mcb_ctx *ctx, CbSet &S, uint64_t n_items, uint32_t *cnt32, const uint64_t *off, const uint32_t *ch_contig, const uint32_t *ch_start, int ch_len)
+static int cb_sketch(mcb_ctx *ctx, CbSet &S, uint64_t n_items, uint32_t *cnt32, const uint64_t *off, const uint32_t *ch_contig, const uint32_t *ch_start, int ch_len,
+                     mcb_tuple *slots = nullptr, int slot_cap = 0)
 {
 	if (!n_items) return MCB_OK;
 	const int rw = ctx->prm.rw, k = ctx->prm.k;
@@ -403,7 +464,7 @@ static int cb_sketch(mcb_ctx *ctx, CbSet &S, uint64_t n_items, uint32_t *cnt32, 
 	auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
 	if (smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	MCB_LAUNCH(ctx, "cb_sketch", kern, mcb_grid_for(n_items, LH_THREADS), LH_THREADS, smem, S.ref.as<char>(), S.roff.as<uint64_t>(), (uint64_t)0, n_items, (uint64_t)0,
-	           rw, k, INT_MAX, off ? S.mins.as<mcb_tuple>() : (mcb_tuple*)nullptr, (uint8_t*)nullptr, off, cnt32, ch_contig, ch_start, ch_len);
+	           rw, k, INT_MAX, slots ? slots : off ? S.mins.as<mcb_tuple>() : (mcb_tuple*)nullptr, (uint8_t*)nullptr, off, cnt32, ch_contig, ch_start, ch_len, slots ? slot_cap : 0);
 	return MCB_OK;
 }
 
@@ -418,6 +479,12 @@ static int cb_min_lists(mcb_ctx *ctx, McbCombineState &cb, CbSet &S, uint64_t nm
 	MCB_TRY(cb.tmp32.ensure((n2 + 2) * 4)); MCB_TRY(S.moff.ensure((n2 + 2) * 8)); MCB_TRY(cb.chn.ensure((nm + 2) * 4));
 	uint32_t *cnt = cb.tmp32.as<uint32_t>(), *first = cb.chn.as<uint32_t>();
 	uint64_t nch = 0;
+	// one sketch pass instead of two: the counting pass parks the tuples of every stretch in a slot of `cap` tuples (three times what
+	// the window density 2/(w+1) predicts); they are moved once the counts are scanned.  A stretch that needs more than a slot (long
+	// runs of equal hashes) makes the call fall back to the second, emitting pass.
+	uint32_t cap = (uint32_t)std::min(CB_CHUNK, std::max(16, 3 * CB_CHUNK / (ctx->prm.rw + 1) + 8));
+	if (const char *e = getenv("MCB_CB_SLOTCAP")) cap = (uint32_t)std::max(1, atoi(e));          // tests: a tiny slot forces the fallback
+	const bool use_slots = chunk != 0 && !getenv("MCB_CB_TWOPASS");
 	if (nm) {
 		MCB_LAUNCH(ctx, "cb_chunk_counts", k_cb_chunk_counts, mcb_grid_for(nm, 256), 256, 0, S.roff.as<uint64_t>(), nm, chunk, first);
 		MCB_TRY(mcb_exclusive_scan_u32(ctx, first, nm, (uint64_t*)&dc[CT_CB_A]));
@@ -425,10 +492,12 @@ static int cb_min_lists(mcb_ctx *ctx, McbCombineState &cb, CbSet &S, uint64_t nm
 		nch = CB_HC(ctx, CT_CB_A);
 		MCB_TRY(cb.chc.ensure(nch * 4 + 16)); MCB_TRY(cb.chs.ensure(nch * 4 + 16)); MCB_TRY(cb.cho.ensure((nch + 2) * 4)); MCB_TRY(cb.cho64.ensure((nch + 2) * 8));
 		MCB_LAUNCH(ctx, "cb_chunk_table", k_cb_chunk_table, mcb_grid_for(nch, 256), 256, 0, first, nm, nch, chunk ? chunk : INT_MAX, cb.chc.as<uint32_t>(), cb.chs.as<uint32_t>());
-		MCB_TRY(cb_sketch(ctx, S, nch, cb.cho.as<uint32_t>(), nullptr, cb.chc.as<uint32_t>(), cb.chs.as<uint32_t>(), chunk ? chunk : INT_MAX));
+		if (use_slots) MCB_TRY(cb.slots.ensure(nch * cap * 16 + 16));
+		MCB_TRY(cb_sketch(ctx, S, nch, cb.cho.as<uint32_t>(), nullptr, cb.chc.as<uint32_t>(), cb.chs.as<uint32_t>(), chunk ? chunk : INT_MAX, use_slots ? cb.slots.as<mcb_tuple>() : nullptr, (int)cap));
 		MCB_TRY(mcb_exclusive_scan_u32(ctx, cb.cho.as<uint32_t>(), nch, (uint64_t*)&dc[CT_CB_B]));
 		MCB_LAUNCH(ctx, "cb_contig_counts", k_cb_contig_counts, mcb_grid_for(nm, 256), 256, 0, first, nm, nch, cb.cho.as<uint32_t>(), &dc[CT_CB_B], cnt);
-		MCB_LAUNCH(ctx, "cb_widen", k_cb_widen, mcb_grid_for(nch, 256), 256, 0, cb.cho.as<uint32_t>(), nch, cb.cho64.as<uint64_t>());
+		MCB_CUDA(cudaMemsetAsync(&dc[CT_CB_C], 0, 8, ctx->stream));
+		MCB_LAUNCH(ctx, "cb_widen", k_cb_widen, mcb_grid_for(nch, 256), 256, 0, cb.cho.as<uint32_t>(), nch, cb.cho64.as<uint64_t>(), &dc[CT_CB_B], use_slots ? cap : 0u, &dc[CT_CB_C]);
 	}
 	if (n2 > nm) MCB_LAUNCH(ctx, "cb_copy_min_counts", k_cb_copy_min_counts, mcb_grid_for(n2 - nm, 256), 256, 0, nm, d_src, n2, old->moff.as<uint64_t>(), cnt);
 	MCB_TRY(mcb_exclusive_scan_u32(ctx, cnt, n2, (uint64_t*)&dc[CT_CB_A]));
@@ -438,7 +507,9 @@ static int cb_min_lists(mcb_ctx *ctx, McbCombineState &cb, CbSet &S, uint64_t nm
 	if (S.nmin >= 0xFFFFFFFFull) { mcb_set_error("mcb_combine: too many contig minimizers"); return MCB_EINVAL; }
 	MCB_TRY(S.mins.ensure(S.nmin * 16 + 16));
 	// the merged contigs come first in the set, so the tuples of stretch t start at cho[t] in the set's list as well
-	if (nm) MCB_TRY(cb_sketch(ctx, S, nch, cb.cho.as<uint32_t>() /* free again: rewritten with the lengths */, cb.cho64.as<uint64_t>(), cb.chc.as<uint32_t>(), cb.chs.as<uint32_t>(), chunk ? chunk : INT_MAX));
+	if (nm && use_slots && CB_HC(ctx, CT_CB_C) == 0)
+		MCB_LAUNCH(ctx, "cb_unslot", k_cb_unslot, mcb_grid_for(nch * cap, 256), 256, 0, cb.slots.as<mcb_tuple>(), cap, cb.cho.as<uint32_t>(), nch, &dc[CT_CB_B], S.mins.as<mcb_tuple>());
+	else if (nm) MCB_TRY(cb_sketch(ctx, S, nch, cb.cho.as<uint32_t>() /* free again: rewritten with the lengths */, cb.cho64.as<uint64_t>(), cb.chc.as<uint32_t>(), cb.chs.as<uint32_t>(), chunk ? chunk : INT_MAX));
 	if (n2 > nm) MCB_LAUNCH(ctx, "cb_copy_mins", k_cb_copy_mins, mcb_grid_for((n2 - nm) * 8, 256), 256, 0, nm, d_src, n2, old->moff.as<uint64_t>(), old->mins.as<mcb_tuple>(),
 	                        S.moff.as<uint64_t>(), S.mins.as<mcb_tuple>());
 	return MCB_OK;
@@ -583,8 +654,12 @@ static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSe
 	nxt.nref = nref2;
 	MCB_TRY(nxt.ref.ensure(nref2 + 32));
 	MCB_CUDA(cudaMemsetAsync(nxt.ref.as<char>() + (nref2 & ~(uint64_t)7), 0, 24, ctx->stream));      // the sketch kernel reads whole 8-byte words
-	if (merged_cols) MCB_LAUNCH(ctx, "cb_consensus", k_cb_consensus, mcb_grid_for(merged_cols, 128), 128, 0, nm, nxt.roff.as<uint64_t>(), nxt.aoff.as<uint64_t>(), nxt.a.as<uint64_t>(),
-	                            ctx->d_packed.as<uint64_t>(), WS, L, merged_cols, nxt.ref.as<char>());
+	MCB_TRY(cb_cols_reserve(ctx, cb, cb.cols_used + merged_cols));
+	MCB_TRY(nxt.coff.ensure((n2 + 2) * 8));
+	if (merged_cols) MCB_LAUNCH(ctx, "cb_consensus", k_cb_merge_counts, mcb_grid_for(merged_cols, 256), 256, 0, cb.pairs.as<CbCand>(), nm, nxt.roff.as<uint64_t>(), cur.roff.as<uint64_t>(),
+	                            cur.coff.as<uint64_t>(), cb.cols.as<uint4>(), cb.cols_used, merged_cols, nxt.ref.as<char>());
+	MCB_LAUNCH(ctx, "cb_new_coff", k_cb_new_coff, mcb_grid_for(n2, 256), 256, 0, nm, cb.src.as<uint32_t>(), n2, nxt.roff.as<uint64_t>(), cur.coff.as<uint64_t>(), cb.cols_used, nxt.coff.as<uint64_t>());
+	cb.cols_used += merged_cols;
 	if (n_copy) MCB_LAUNCH(ctx, "cb_copy_refs", k_cb_copy_refs, mcb_grid_for(n_copy * 32, 256), 256, 0, nm, cb.src.as<uint32_t>(), n2, cur.roff.as<uint64_t>(), cur.ref.as<char>(),
 	                       nxt.roff.as<uint64_t>(), nxt.ref.as<char>());
 	// minimizers of the new set: sketches of the merged contigs, lists of the others taken along
@@ -621,6 +696,14 @@ extern "C" int mcb_combine(mcb_ctx *ctx, int cbthreshold, mcb_combine_result *re
 			MCB_CUDA(cudaMemcpyAsync(s0.roff.p, ctx->d_out[3].p, (s0.ncl + 1) * 8, DD, ctx->stream));
 			MCB_CUDA(cudaMemcpyAsync(s0.ref.p, ctx->d_out[4].p, s0.nref, DD, ctx->stream));
 		}
+		// per-column base counts of the seed contigs: the start of the arena, column g of the concatenated strings at entry g
+		cb.cols_used = 0;
+		MCB_TRY(cb_cols_reserve(ctx, cb, 2 * s0.nref));
+		MCB_TRY(s0.coff.ensure((s0.ncl + 2) * 8));
+		if (s0.ncl) MCB_CUDA(cudaMemcpyAsync(s0.coff.p, s0.roff.p, s0.ncl * 8, DD, ctx->stream));
+		if (s0.nref) MCB_LAUNCH(ctx, "cb_seed_counts", k_cb_seed_counts, mcb_grid_for(s0.nref, 128), 128, 0, s0.ncl, s0.roff.as<uint64_t>(), s0.aoff.as<uint64_t>(), s0.a.as<uint64_t>(),
+		                        ctx->d_packed.as<uint64_t>(), ctx->WS, ctx->L, s0.nref, cb.cols.as<uint4>());
+		cb.cols_used = s0.nref;
 		MCB_TRY(cb_min_lists(ctx, cb, s0, s0.ncl, nullptr, nullptr));          // every seed contig is sketched once; later only what a merge created
 	}
 	int cur = 0, iterations = 0;

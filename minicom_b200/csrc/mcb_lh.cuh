@@ -29,7 +29,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(LH_THREADS)
 k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count, uint64_t cid_first,
              int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ cnt32,
-             const uint32_t *__restrict__ ch_contig = nullptr, const uint32_t *__restrict__ ch_start = nullptr, int ch_len = 0)
+             const uint32_t *__restrict__ ch_contig = nullptr, const uint32_t *__restrict__ ch_start = nullptr, int ch_len = 0, int slot_cap = 0)
 {
 	extern __shared__ __align__(16) unsigned char lh_smem[];
 	uint64_t *rx = (uint64_t*)lh_smem;                                        // [w][LH_THREADS]
@@ -56,8 +56,10 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 	LhRingSmem ring; ring.x = rx; ring.ps = rp; ring.tid = threadIdx.x;
 	uint8_t *sst = ss + threadIdx.x;
 	// two uses: the first m tuples of contig c at mi[c*m ..] (kthread_bucket.c:463; mi_cnt given), or ALL tuples (m = INT_MAX, cnt32
-	// given) at mi[out_off[ci] ..] — a pass with mi == null only counts them
-	mcb_tuple *out = cnt32 ? (mi ? mi + out_off[ci] : nullptr) : mi + c * m;
+	// given) at mi[out_off[ci] ..] — a pass with mi == null only counts them; with slot_cap > 0 the pass counts AND parks the first
+	// slot_cap tuples of the item at mi[ci * slot_cap ..] (the caller compacts the slots once the counts are scanned)
+	mcb_tuple *out = cnt32 ? (mi ? (slot_cap ? mi + ci * (uint64_t)slot_cap : mi + out_off[ci]) : nullptr) : mi + c * m;
+	const int wlim = slot_cap ? slot_cap : m;
 	int n_out = 0;
 	const uint64_t mask = (1ull << (2 * k)) - 1, shift1 = 2 * (k - 1);
 	const uint32_t mh = (uint32_t)(mask >> 32);
@@ -69,7 +71,7 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 	uint64_t px = ~0ull; int pslot = 0; bool ptie = false;             // rightmost minimum of the slots written in this block
 	int l = b0, seen = 0, bp = 0, mp = 0;                               // l: bases since the last ambiguous one (= position here); seen: bases rolled into fw / rv
 	bool on = b0 >= start;
-#define LH_EMIT(hx_, p_) do { if (on) { if (out && n_out < m) { mcb_tuple t_; t_.x = (hx_); t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } } while (0)
+#define LH_EMIT(hx_, p_) do { if (on) { if (out && n_out < wlim) { mcb_tuple t_; t_.x = (hx_); t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } } while (0)
 	for (int j = 0; j < w; ++j) { ring.set(j, ~0ull, ~0u); sst[j * LH_THREADS] = (uint8_t)(w - 1); }
 	for (int i = b0; i < end && n_out < m; ++i) {
 		const int ai = i + skew;

@@ -257,9 +257,9 @@ int mcb_radix_sort(mcb_ctx *ctx, ulonglong2 *a, ulonglong2 *b, uint64_t n, const
 	ulonglong2 *src = a, *dst = b;
 	for (int p = 0; p < n_passes; ++p) {
 		DigitPair dg = { passes[p].word, passes[p].shift, (1u << passes[p].bits) - 1u };
-		MCB_LAUNCH(ctx, "sort_hist", (k_sort_hist<ulonglong2, DigitPair>), (unsigned)nb, SORT_THREADS, 0, src, n, dg, hist, (unsigned)nb);
+		MCB_LAUNCH(ctx, "radix_hist", (k_sort_hist<ulonglong2, DigitPair>), (unsigned)nb, SORT_THREADS, 0, src, n, dg, hist, (unsigned)nb);
 		MCB_LAUNCH(ctx, "sort_rowscan", k_sort_rowscan, 256, SORT_THREADS, 0, hist, (unsigned)nb, rowsum);
-		MCB_LAUNCH(ctx, "sort_scatter", (k_sort_scatter<ulonglong2, DigitPair>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb, rowsum);
+		MCB_LAUNCH(ctx, "radix_scatter", (k_sort_scatter<ulonglong2, DigitPair>), (unsigned)nb, SORT_THREADS, 0, src, dst, n, dg, hist, (unsigned)nb, rowsum);
 		ulonglong2 *t = src; src = dst; dst = t;
 	}
 	*sorted_out = src;

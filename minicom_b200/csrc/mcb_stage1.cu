@@ -1423,7 +1423,7 @@ int mcb_bucket_round_b_impl(mcb_ctx *ctx, uint64_t cid_first)
 			auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
 			if (lh2_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh2_smem));
 			MCB_LAUNCH(ctx, "sketch_lh", kern, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh2_smem, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
-			           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>(), (const uint64_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
+			           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>(), (const uint64_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, 0);
 		}
 		bs.tot_cl += n_cl_new; bs.tot_mem += n_mem_new; bs.tot_ref += n_ref_new; bs.tot_sg += n_sg_new;
 		// ---- rejected reads go to the next round with a shorter k-mer (kthread_bucket.c:205-212,488-496)

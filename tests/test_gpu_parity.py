@@ -444,3 +444,29 @@ def test_combine_matches_oracle(n, L, G, seed, opts):
         assert np.array_equal(r.cl_ref, want["cl_ref"]) and np.array_equal(r.cl_ref_off, want["cl_ref_off"]), "consensus strings differ"
         assert r.n_merges == int(want["iter_merges"].sum())
     S.close()
+
+
+@pytest.mark.parametrize("knob", [{}, {"MCB_CB_SLOTCAP": "2"}, {"MCB_CB_TWOPASS": "1"}], ids=["slots", "slot_overflow_fallback", "two_pass"])
+def test_combine_sketch_paths_agree_on_repeats(knob, monkeypatch):
+    """The merge sketches its contigs in one pass that parks the tuples of every stretch in a fixed slot; a stretch that needs more
+    (forced here with a two-tuple slot) falls back to the counting + emitting passes.  Tandem repeats put identical k-mers into one
+    window (the tie scans of mm_sketch_lh_ori), deep coverage makes long contigs of many stretches."""
+    import oracle_lib as O
+    for k, v in knob.items():
+        monkeypatch.setenv(k, v)
+    L = 100
+    genome = _tandem_genome(61, 12000)
+    reads = synth.make_reads(30000, L, len(genome), seed=61, sub_rate=0.004, genome=genome)
+    S = O.Stage1(O.resolve_params(L), reads)
+    p = api.resolve_params(L)
+    want = S.combine(2 * p.diff_threshold)
+    with api.Context(p) as ctx:
+        ctx.for_reads(reads)
+        ctx.for_bucket()
+        r = ctx.combine(2 * p.diff_threshold)
+        r2 = (ctx.for_reads(reads), ctx.for_bucket(), ctx.combine(2 * p.diff_threshold))[2]      # a second run on the same context starts a fresh count arena
+    for got in (r, r2):
+        assert got.iterations == want["iterations"]
+        assert np.array_equal(got.cl_n, want["cl_n"]) and np.array_equal(got.cl_a, want["cl_a"]), "members differ"
+        assert np.array_equal(got.cl_ref, want["cl_ref"]) and np.array_equal(got.cl_ref_off, want["cl_ref_off"]), "consensus strings differ"
+    S.close()
