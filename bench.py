@@ -763,9 +763,20 @@ def bench_sharded(args):
         keep.append(t)
         return t.numpy()
 
-    rows_pinned = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
-    rows_pinned.numpy()[:] = reads
-    rows_dev = rows_pinned.to(dev)
+    ws = (((L + 31) // 32) + 1) & ~1
+    if args.ascii:
+        rows_pinned = torch.empty((n, L), dtype=torch.uint8, pin_memory=True)
+        rows_pinned.numpy()[:] = reads
+        rows_dev = rows_pinned.to(dev)
+        in_host, in_dev, reads_h2d = rows_pinned.numpy(), rows_dev, n * L
+    else:
+        # this rank's reads as the library's FASTQ reader leaves them: 2-bit rows in page-locked memory + N side table
+        rs = api.ReadSet(L)
+        rs.add_rows(reads, max(1, threads // world))
+        pk, nrid_h, nmask_h = rs.arrays()
+        keep_dev = (torch.from_numpy(pk).to(dev), torch.from_numpy(nrid_h.view(np.int32).copy()).to(dev), torch.from_numpy(nmask_h.view(np.int64).copy()).to(dev))
+        in_host, in_dev = rs, (keep_dev[0].data_ptr(), keep_dev[1].data_ptr(), keep_dev[2].data_ptr(), len(nrid_h))
+        reads_h2d = n * ws * 8 + len(nrid_h) * (4 + ws * 8)
     params = api.resolve_params(L, device=local, **{k: int(ref_env[e]) for k, e in (("k", "MC_K"), ("e", "MC_E"), ("w", "MC_W"), ("m", "MC_M")) if e in ref_env})
     ctx = api.Context(params)
     ctx.timers_enable(True)
@@ -776,7 +787,7 @@ def bench_sharded(args):
     if rank == 0:
         os.makedirs(pdir)
     dist.barrier()
-    rr, part = fe.stage1(rows_dev, n_total, True)
+    rr, part = fe.stage1(in_dev, n_total, True)
     # this rank's share of every recorded call
     b0, b1 = shard.bucket_range(rank, world)
     my_idx = []
@@ -863,7 +874,7 @@ def bench_sharded(args):
         # on the ranks that wait.  The barrier itself is outside every timer; the wall clock (e2e) contains it.
         phase_barrier()
         t = time.perf_counter()
-        rr, part = fe.stage1(rows_dev if device_resident else rows_pinned.numpy(), n_total, device_resident, keep_mask=True)
+        rr, part = fe.stage1(in_dev if device_resident else in_host, n_total, device_resident, keep_mask=True)
         w["stage1"] += time.perf_counter() - t
         t = time.perf_counter()
         for xy, off in my_idx:
@@ -953,7 +964,8 @@ def bench_sharded(args):
                        "sharding": "reads by read-id range; every round each tuple + the packed row of its read go to the owner of its bucket (bucket*G>>14) in one grouped NCCL send/recv "
                                    "inside the library; index builds by bucket range; Stage 2 on the rank that owns the single, against all contigs (no claim crosses ranks); "
                                    "results bit-identical to one GPU (see parity)",
-                       "l2": "inputs larger than L2 (reads %.0f MB per GPU per step)" % (n * L / 1e6),
+                       "reads_input": "ASCII rows" if args.ascii else "2-bit packed rows + N side table (the library's FASTQ reader, SURVEY 8f N3)",
+                       "l2": "inputs larger than L2 (reads %.0f MB per GPU per step)" % (reads_h2d / 1e6),
                        "timing": "value = max over ranks of (CUDA-event time of the library entry points + CUDA-event time of the NCCL collectives it issues), reads resident in HBM; e2e = max over ranks of the wall clock with pinned host inputs and results copied back",
                        "bases_per_s": round(value * L, 1), "wall_ms_per_step_device_arm": round(ms_wall_dev_max, 3), "collective_ms_per_step": round(coll_max, 3),
                        "collective_ms_per_step_rank0": {k.split(":", 1)[1]: round(v[0] / args.steps, 4) for k, v in tm.items() if k.startswith("nccl:") or k.startswith("nccl_in:")},
@@ -962,7 +974,7 @@ def bench_sharded(args):
                        "nccl_bytes_sent_per_step_rank0": int(sent // max(1, args.steps)), "T_cb": T_cb, "contig_bases": R_total, "rank0": stats,
                        "device_ms_by_entry_point_rank0": {k: round(tm[k][0] / args.steps, 4) for k in ("for_reads", "for_bucket", "idx_build", "realign") if k in tm},
                        "kernel_ms_per_step_rank0": {k[2:]: round(v[0] / args.steps, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:14]}, "host_threads": threads},
-            "e2e": {"value": round(n_total / (ms_e2e_max / 1e3), 1), "unit": "reads/s", "h2d_bytes_per_step": int(n * L + sum(x[0].nbytes + x[1].nbytes for x in my_idx) + sum(c[0].nbytes + c[1].nbytes + (c[3].nbytes if c[3] is not None else 0) for c in my_realign)),
+            "e2e": {"value": round(n_total / (ms_e2e_max / 1e3), 1), "unit": "reads/s", "h2d_bytes_per_step": int(reads_h2d + sum(x[0].nbytes + x[1].nbytes for x in my_idx) + sum(c[0].nbytes + c[1].nbytes + (c[3].nbytes if c[3] is not None else 0) for c in my_realign)),
                     "d2h_bytes_per_step": stats.get("d2h"), "ms_per_step": round(ms_e2e_max, 3), "copy_ms_per_step_rank0": {k: round(tm_e2e[k][0] / args.steps, 3) for k in ("h2d", "d2h") if k in tm_e2e},
                     "note": "byte counts are rank 0's; each rank hands its own results to its host (merging the ranks' lists is the caller's, as in shard.merge_*)"},
             "gpu_launches": int(launches),

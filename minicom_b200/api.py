@@ -407,6 +407,12 @@ class Context:
         self._check(self.lib.mcb_for_reads_packed(self._h, packed.ctypes.data, packed.shape[0], nread_rid.ctypes.data, nmask.ctypes.data, len(nread_rid), C.byref(r)))
         return self._reads_result(r)
 
+    def for_reads_packed_device(self, d_packed: int, n: int, d_nread_rid: int = 0, d_nmask: int = 0, n_nreads: int = 0) -> ReadsResult:
+        """the same with the three arrays resident in device memory (raw device pointers)"""
+        r = _ReadsResult()
+        self._check(self.lib.mcb_for_reads_packed_device(self._h, d_packed, n, d_nread_rid, d_nmask, n_nreads, C.byref(r)))
+        return self._reads_result(r)
+
     def for_reads_device(self, dptr: int, n: int) -> ReadsResult:
         r = _ReadsResult()
         self._check(self.lib.mcb_for_reads_device(self._h, dptr, n, C.byref(r)))

@@ -366,56 +366,66 @@ __device__ __forceinline__ char cb_majority(uint4 v)
 	if (v.w > mx) { mx = v.w; best = 3; }
 	return "ACGT"[best];
 }
-__global__ void k_cb_merge_counts(const CbCand *__restrict__ pairs, uint64_t nm, const uint64_t *__restrict__ roff2, const uint64_t *__restrict__ roff, const uint64_t *__restrict__ coff,
-                                  uint4 *__restrict__ cols, uint64_t new_base, uint64_t total_cols, char *__restrict__ ref2)
+// one warp per merged contig: lanes stride over its columns, so the parents' counts arrive as coalesced 16-byte loads
+__global__ void __launch_bounds__(256)
+k_cb_merge_counts(const CbCand *__restrict__ pairs, uint64_t nm, const uint64_t *__restrict__ roff2, const uint64_t *__restrict__ roff, const uint64_t *__restrict__ coff,
+                  uint4 *__restrict__ cols, uint64_t new_base, char *__restrict__ ref2)
 {
-	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (g >= total_cols) return;
-	uint64_t lo = 0, hi = nm;                 // last q with roff2[q] <= g
-	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (roff2[mid] <= g) lo = mid; else hi = mid; }
-	const CbCand p = pairs[lo];
-	const uint64_t col = g - roff2[lo];
+	const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (q >= nm) return;
+	const CbCand p = pairs[q];
 	const bool i_first = p.pos_ori >= p.pos;
 	const uint32_t first = i_first ? p.i : p.c, second = i_first ? p.c : p.i;
 	const uint64_t shift = i_first ? p.pos_ori - p.pos : p.pos - p.pos_ori;
 	const uint64_t l1 = roff[first + 1] - roff[first], l2 = roff[second + 1] - roff[second];
-	uint4 v = make_uint4(0, 0, 0, 0);
-	if (col < l1) v = cols[coff[first] + col];
-	if (col >= shift && col - shift < l2) { const uint4 u = cols[coff[second] + col - shift]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
-	cols[new_base + g] = v;
-	ref2[g] = cb_majority(v);
+	const uint64_t o2 = roff2[q], len = roff2[q + 1] - o2;
+	const uint4 *c1 = cols + coff[first], *c2 = cols + coff[second];
+	for (uint64_t col = lane; col < len; col += 32) {
+		uint4 v = make_uint4(0, 0, 0, 0);
+		if (col < l1) v = c1[col];
+		if (col >= shift && col - shift < l2) { const uint4 u = c2[col - shift]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+		cols[new_base + o2 + col] = v;
+		ref2[o2 + col] = cb_majority(v);
+	}
 }
 __global__ void k_cb_new_coff(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ roff2, const uint64_t *__restrict__ coff, uint64_t new_base, uint64_t *__restrict__ coff2)
 {
 	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (q < n2) coff2[q] = q < nm ? new_base + roff2[q] : coff[src[q - nm]];
 }
-// the counts of the seed contigs: one thread per column walks the members that cover it (sorted by position: a contiguous run
-// found by binary search).  Column g of the set's concatenated consensus strings = arena entry g (coff = roff).
-__global__ void k_cb_seed_counts(uint64_t ncl, const uint64_t *__restrict__ roff, const uint64_t *__restrict__ aoff, const uint64_t *__restrict__ a,
-                                 const uint64_t *__restrict__ packed, int WS, int L, uint64_t total_cols, uint4 *__restrict__ cols)
+// the counts of the seed contigs: one warp per contig takes the members in turn, its lanes the bases of the member, and votes
+// into a table in shared memory (a member's bases fall into distinct columns, so the lanes never meet; members are serialised
+// by __syncwarp).  Column g of the set's concatenated consensus strings = arena entry g (coff = roff).
+#define CB_SEED_WARPS 4
+__global__ void __launch_bounds__(CB_SEED_WARPS * 32)
+k_cb_seed_counts(uint64_t ncl, const uint64_t *__restrict__ roff, const uint64_t *__restrict__ aoff, const uint64_t *__restrict__ a,
+                 const uint64_t *__restrict__ packed, int WS, int L, int maxcols, uint4 *__restrict__ cols, unsigned long long *__restrict__ err)
 {
-	const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (g >= total_cols) return;
-	uint64_t lo = 0, hi = ncl;                // last q with roff[q] <= g
-	while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (roff[mid] <= g) lo = mid; else hi = mid; }
-	const uint64_t q = lo;
-	const int64_t col = (int64_t)(g - roff[q]);
+	extern __shared__ uint32_t cb_votes[];                       // [CB_SEED_WARPS][4][maxcols]
+	const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint64_t q = (uint64_t)blockIdx.x * CB_SEED_WARPS + wrp;
+	if (q >= ncl) return;
+	uint32_t *v = cb_votes + (size_t)wrp * 4 * maxcols;
+	const uint64_t o = roff[q];
+	const int len = (int)(roff[q + 1] - o);
+	if (len > maxcols) { if (lane == 0) atomicAdd(err, 1ull); return; }
+	for (int i = lane; i < 4 * maxcols; i += 32) v[i] = 0;
+	__syncwarp();
 	const uint64_t mb = aoff[q], me = aoff[q + 1];
-	uint64_t s = mb, e = me;                  // first member with position > col - L
-	while (s < e) { const uint64_t mid = (s + e) >> 1; if ((int64_t)((uint32_t)a[mid] >> 1) <= col - L) s = mid + 1; else e = mid; }
-	uint64_t cAC = 0, cGT = 0;                // two 32-bit counters per word: no dynamically indexed (= local memory) array
-	for (uint64_t u = s; u < me; ++u) {
+	for (uint64_t u = mb; u < me; ++u) {
 		const uint64_t y = a[u];
-		const int64_t pos = (int64_t)((uint32_t)y >> 1);
-		if (pos > col) break;
-		const int p = (int)(col - pos);
+		const int pos = (int)((uint32_t)y >> 1);
 		const uint64_t *row = packed + (y >> 32) * (uint64_t)WS;
-		const unsigned bse = (y & 1) ? 3u - mcb_base_at(row, L - 1 - p) : mcb_base_at(row, p);
-		const uint64_t one = 1ull << (32 * (bse & 1u));
-		cAC += (bse & 2u) ? 0ull : one; cGT += (bse & 2u) ? one : 0ull;
+		if (pos + L <= len)
+			for (int b = lane; b < L; b += 32) {
+				const unsigned bse = (y & 1) ? 3u - mcb_base_at(row, L - 1 - b) : mcb_base_at(row, b);
+				v[bse * maxcols + pos + b] += 1;
+			}
+		else if (lane == 0) atomicAdd(err, 1ull);
+		__syncwarp();
 	}
-	cols[g] = make_uint4((unsigned)cAC, (unsigned)(cAC >> 32), (unsigned)cGT, (unsigned)(cGT >> 32));
+	for (int c = lane; c < len; c += 32) cols[o + c] = make_uint4(v[c], v[maxcols + c], v[2 * maxcols + c], v[3 * maxcols + c]);
 }
 __global__ void k_cb_copy_refs(uint64_t nm, const uint32_t *__restrict__ src, uint64_t n2, const uint64_t *__restrict__ roff, const char *__restrict__ ref,
                                const uint64_t *__restrict__ roff2, char *__restrict__ ref2)
@@ -449,7 +459,7 @@ static int cb_counters(mcb_ctx *ctx)          // the device scalars to the host 
 	MCB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return MCB_OK;
 }
-enum { CT_CB_A = 48, CT_CB_B = 49, CT_CB_C = 50, CT_CB_D = 51, CT_CB_E = 52 };          // scratch slots of ctx->d_counters (32..41 are the consensus work lists)
+enum { CT_CB_A = 48, CT_CB_B = 49, CT_CB_C = 50, CT_CB_D = 51, CT_CB_E = 52, CT_CB_F = 53 };          // scratch slots of ctx->d_counters (32..41 are the consensus work lists)
 #define CB_HC(ctx, slot) ((ctx)->h_counters.as<unsigned long long>()[slot])
 
 // all (w,k)-minimizers (mm_sketch_lh_ori, sketch.c:116-165; window rw, kthread_cb.c:234 / :359 with win_step = 0) of the work items
@@ -464,7 +474,7 @@ static int cb_sketch(mcb_ctx *ctx, CbSet &S, uint64_t n_items, uint32_t *cnt32, 
 	auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
 	if (smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	MCB_LAUNCH(ctx, "cb_sketch", kern, mcb_grid_for(n_items, LH_THREADS), LH_THREADS, smem, S.ref.as<char>(), S.roff.as<uint64_t>(), (uint64_t)0, n_items, (uint64_t)0,
-	           rw, k, INT_MAX, slots ? slots : off ? S.mins.as<mcb_tuple>() : (mcb_tuple*)nullptr, (uint8_t*)nullptr, off, cnt32, ch_contig, ch_start, ch_len, slots ? slot_cap : 0);
+	           rw, k, mcb_ta_mul(k), INT_MAX, slots ? slots : off ? S.mins.as<mcb_tuple>() : (mcb_tuple*)nullptr, (uint8_t*)nullptr, off, cnt32, ch_contig, ch_start, ch_len, slots ? slot_cap : 0);
 	return MCB_OK;
 }
 
@@ -656,8 +666,8 @@ static int combine_iteration(mcb_ctx *ctx, McbCombineState &cb, CbSet &cur, CbSe
 	MCB_CUDA(cudaMemsetAsync(nxt.ref.as<char>() + (nref2 & ~(uint64_t)7), 0, 24, ctx->stream));      // the sketch kernel reads whole 8-byte words
 	MCB_TRY(cb_cols_reserve(ctx, cb, cb.cols_used + merged_cols));
 	MCB_TRY(nxt.coff.ensure((n2 + 2) * 8));
-	if (merged_cols) MCB_LAUNCH(ctx, "cb_consensus", k_cb_merge_counts, mcb_grid_for(merged_cols, 256), 256, 0, cb.pairs.as<CbCand>(), nm, nxt.roff.as<uint64_t>(), cur.roff.as<uint64_t>(),
-	                            cur.coff.as<uint64_t>(), cb.cols.as<uint4>(), cb.cols_used, merged_cols, nxt.ref.as<char>());
+	if (merged_cols) MCB_LAUNCH(ctx, "cb_consensus", k_cb_merge_counts, mcb_grid_for(nm * 32, 256), 256, 0, cb.pairs.as<CbCand>(), nm, nxt.roff.as<uint64_t>(), cur.roff.as<uint64_t>(),
+	                            cur.coff.as<uint64_t>(), cb.cols.as<uint4>(), cb.cols_used, nxt.ref.as<char>());
 	MCB_LAUNCH(ctx, "cb_new_coff", k_cb_new_coff, mcb_grid_for(n2, 256), 256, 0, nm, cb.src.as<uint32_t>(), n2, nxt.roff.as<uint64_t>(), cur.coff.as<uint64_t>(), cb.cols_used, nxt.coff.as<uint64_t>());
 	cb.cols_used += merged_cols;
 	if (n_copy) MCB_LAUNCH(ctx, "cb_copy_refs", k_cb_copy_refs, mcb_grid_for(n_copy * 32, 256), 256, 0, nm, cb.src.as<uint32_t>(), n2, cur.roff.as<uint64_t>(), cur.ref.as<char>(),
@@ -675,6 +685,7 @@ extern "C" int mcb_combine(mcb_ctx *ctx, int cbthreshold, mcb_combine_result *re
 	if (ctx->shard_n > 1) { mcb_set_error("mcb_combine: the contig merge runs on one GPU (gather the seed contigs first)"); return MCB_ESTATE; }
 	if (cbthreshold < 0) { mcb_set_error("mcb_combine: bad cbthreshold"); return MCB_EINVAL; }
 	memset(res, 0, sizeof *res);
+	McbMergeScope merge_scope(ctx->tm, 1);                     // kernel timers of the merge are booked apart from the metric path's
 	if (!ctx->cb) ctx->cb = new McbCombineState();
 	McbCombineState &cb = *ctx->cb;
 	MCB_TRY(ctx->h_counters.ensure(64 * 8));
@@ -701,10 +712,19 @@ extern "C" int mcb_combine(mcb_ctx *ctx, int cbthreshold, mcb_combine_result *re
 		MCB_TRY(cb_cols_reserve(ctx, cb, 2 * s0.nref));
 		MCB_TRY(s0.coff.ensure((s0.ncl + 2) * 8));
 		if (s0.ncl) MCB_CUDA(cudaMemcpyAsync(s0.coff.p, s0.roff.p, s0.ncl * 8, DD, ctx->stream));
-		if (s0.nref) MCB_LAUNCH(ctx, "cb_seed_counts", k_cb_seed_counts, mcb_grid_for(s0.nref, 128), 128, 0, s0.ncl, s0.roff.as<uint64_t>(), s0.aoff.as<uint64_t>(), s0.a.as<uint64_t>(),
-		                        ctx->d_packed.as<uint64_t>(), ctx->WS, ctx->L, s0.nref, cb.cols.as<uint4>());
+		if (s0.nref) {
+			// a seed contig spans fewer than 2L + 2 max_rounds columns (construct_ref: every member overlaps the first one's minimizer)
+			const int maxcols = ((2 * ctx->L + 2 * ctx->prm.max_rounds + 8 + 31) / 32) * 32;
+			const size_t smem = (size_t)CB_SEED_WARPS * 4 * maxcols * 4;
+			if (smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_cb_seed_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			unsigned long long *dc = ctx->d_counters.as<unsigned long long>();
+			MCB_CUDA(cudaMemsetAsync(&dc[CT_CB_F], 0, 8, ctx->stream));
+			MCB_LAUNCH(ctx, "cb_seed_counts", k_cb_seed_counts, mcb_grid_for(s0.ncl, CB_SEED_WARPS), CB_SEED_WARPS * 32, smem, s0.ncl, s0.roff.as<uint64_t>(), s0.aoff.as<uint64_t>(), s0.a.as<uint64_t>(),
+			           ctx->d_packed.as<uint64_t>(), ctx->WS, ctx->L, maxcols, cb.cols.as<uint4>(), &dc[CT_CB_F]);
+		}
 		cb.cols_used = s0.nref;
 		MCB_TRY(cb_min_lists(ctx, cb, s0, s0.ncl, nullptr, nullptr));          // every seed contig is sketched once; later only what a merge created
+		if (s0.ncl && CB_HC(ctx, CT_CB_F)) { mcb_set_error("mcb_combine: internal: %llu seed contigs / members outside the expected column range", CB_HC(ctx, CT_CB_F)); return MCB_ECUDA; }
 	}
 	int cur = 0, iterations = 0;
 	long pre_tot = 0;

@@ -106,9 +106,13 @@ struct McbTimers {
 		if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
 		cudaEvent_t e; cudaEventCreate(&e); return e;
 	}
+	int merge_scope = 0;          // inside mcb_combine: kernel timers are booked as "k:cb_<name>" (the merge is outside the metric)
 	int begin(const char *n) {
 		if (!enabled) return -1;
-		Rec r; r.name = id(n); r.a = ev(); r.b = ev();
+		Rec r;
+		if (merge_scope && n[0] == 'k' && n[1] == ':' && strncmp(n + 2, "cb_", 3) != 0) { char buf[96]; snprintf(buf, sizeof buf, "k:cb_%s", n + 2); r.name = id(buf); }
+		else r.name = id(n);
+		r.a = ev(); r.b = ev();
 		cudaEventRecord(r.a, stream); pending.push_back(r); return (int)pending.size() - 1;
 	}
 	void end(int h) { if (h >= 0) cudaEventRecord(pending[h].b, stream); }
@@ -123,6 +127,11 @@ struct McbTimers {
 	void reset() { collect(); for (auto &v : ms) v = 0; for (auto &v : cnt) v = 0; launches = 0; }
 };
 
+struct McbMergeScope {          // RAII: on / off for the duration of a block
+	McbTimers &t; int saved;
+	McbMergeScope(McbTimers &t_, int on) : t(t_), saved(t_.merge_scope) { t_.merge_scope = on; }
+	~McbMergeScope() { t.merge_scope = saved; }
+};
 // RAII span for whole-entry-point / copy timers
 struct McbSpan {
 	McbTimers &t; int h;
@@ -406,6 +415,88 @@ __device__ __forceinline__ uint64_t mcb_sketch_two_wide(const uint64_t *row, int
 	f = ((f >> 1) & 0x5555555555555555ull) | ((f & 0x5555555555555555ull) << 1);
 	*pos_out = bp; *strand_out = f < r ? 0 : 1;
 	return (uint64_t)bhi << 32 | blo;
+}
+#endif
+// ---- "top-aligned" arithmetic for 16 < k < 32 (device): a 2k-bit k-mer or hash lives in the TOP 2k bits of a 64-bit pair of
+// 32-bit halves (value << (64 - 2k)).  Multiplication modulo 2^(2k) is then plain wrap-around modulo 2^64, so the four "& mask"
+// after hash64's multiplications (sketch.c:28-36) disappear; x ^= x >> s needs the shifted-in low bits cleared, which folds into
+// the XOR (one LOP3: a ^ (b & c)); order is preserved, so minima and the f < r test are those of the plain values.
+// Pipes: the loop is bound by the ALU pipe (LOP3 / SHF / ISETP / SEL; one warp instruction per two cycles per SM sub-partition,
+// like the FMA pipe), so the high half's x >> s, the reverse k-mer's high half and one funnel shift run as IMAD / IMAD.HI with
+// powers of two that arrive as kernel arguments (ptxas cannot turn those back into shifts).  Measured on B200 with
+// scripts/microbench/sketch_variants.cu: 1.77 -> 1.43 ms per 10 M reads of 100 bases (profiles/r2_sketch_variants.txt).
+struct McbTaMul { uint32_t lm, csh, m24, m14, m28, p30, neg30, sub1lo, sub1hi; int32_t sh; };
+static inline McbTaMul mcb_ta_mul(int k)
+{
+	McbTaMul M;
+	memset(&M, 0, sizeof M);
+	if (k <= 16 || k >= 32) return M;
+	M.sh = 64 - 2 * k; M.lm = ~((1u << M.sh) - 1u); M.csh = 1u << M.sh; M.m24 = 1u << 8; M.m14 = 1u << 18; M.m28 = 1u << 4;
+	M.p30 = 1u << 30; M.neg30 = 0u - (1u << 30);
+	const uint64_t sub = 0ull - (1ull << M.sh);
+	M.sub1lo = (uint32_t)sub; M.sub1hi = (uint32_t)(sub >> 32);
+	return M;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t mcb_madhi(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+// hash64 of a top-aligned key, top-aligned result
+__device__ __forceinline__ uint64_t mcb_hash64_ta(uint32_t lo, uint32_t hi, const McbTaMul &M)
+{
+	uint64_t t = (uint64_t)lo * 0x1FFFFFu + ((uint64_t)M.sub1hi << 32 | M.sub1lo);
+	hi = hi * 0x1FFFFFu + (uint32_t)(t >> 32); lo = (uint32_t)t;
+	{ const uint32_t fl = mcb_madhi(lo, M.m24, hi * M.m24), u = __umulhi(hi, M.m24); lo ^= fl & M.lm; hi ^= u; }
+	t = (uint64_t)lo * 265u; hi = hi * 265u + (uint32_t)(t >> 32); lo = (uint32_t)t;
+	{ const uint32_t fl = __funnelshift_r(lo, hi, 14), u = __umulhi(hi, M.m14); lo ^= fl & M.lm; hi ^= u; }
+	t = (uint64_t)lo * 21u; hi = hi * 21u + (uint32_t)(t >> 32); lo = (uint32_t)t;
+	{ const uint32_t fl = __funnelshift_r(lo, hi, 28), u = __umulhi(hi, M.m28); lo ^= fl & M.lm; hi ^= u; }
+	t = (uint64_t)lo * 0x80000001u; hi = hi * 0x80000001u + (uint32_t)(t >> 32); lo = (uint32_t)t;
+	return (uint64_t)hi << 32 | lo;
+}
+// one base into the top-aligned forward / reverse k-mer (sketch.c:257-259)
+#define MCB_TA_ROLL(c, flo, fhi, rlo, rhi, M) { \
+	fhi = __funnelshift_l(flo, fhi, 2); flo = flo * 4u + (c) * (M).csh; \
+	rlo = __funnelshift_r(rlo, rhi, 2) & (M).lm; \
+	rhi = mcb_madhi(rhi, (M).p30, (c) * (M).neg30 + 0xC0000000u); }
+// mm_sketch_two (sketch.c:238-289) over a packed, N-free read, 16 < k < 32: same walk as mcb_sketch_two_wide on top-aligned values
+template <bool ODD>
+__device__ __forceinline__ uint64_t mcb_sketch_two_ta(const uint64_t *row, int L, int k, const McbTaMul &M, int *pos_out, int *strand_out)
+{
+	uint32_t flo = 0, fhi = 0, rlo = 0, rhi = 0, blo = ~0u, bhi = ~0u;
+	int bp = -1;
+	for (int h = 0; h * 16 < L; ++h) {
+		uint32_t x = (uint32_t)(row[h >> 1] >> (32 * (h & 1)));
+		const int base = h * 16;
+		const int lim = min(16, L - base);
+		const int split = max(0, min(lim, k - 1 - base));
+		for (int j = 0; j < split; ++j) { const uint32_t c = x & 3u; x >>= 2; MCB_TA_ROLL(c, flo, fhi, rlo, rhi, M); }
+		for (int j = split; j < lim; ++j) {
+			const uint32_t c = x & 3u; x >>= 2;
+			MCB_TA_ROLL(c, flo, fhi, rlo, rhi, M);
+			if (!ODD && flo == rlo && fhi == rhi) continue;          // symmetric k-mer: skipped (sketch.c:265)
+			const bool fwd = ((uint64_t)fhi << 32 | flo) < ((uint64_t)rhi << 32 | rlo);
+			const uint64_t hv = mcb_hash64_ta(fwd ? flo : rlo, fwd ? fhi : rhi, M);
+			const bool better = hv < ((uint64_t)bhi << 32 | blo);           // strict <: leftmost on ties (sketch.c:275)
+			blo = better ? (uint32_t)hv : blo; bhi = better ? (uint32_t)(hv >> 32) : bhi; bp = better ? base + j : bp;
+		}
+	}
+	if (bp < 0) { *pos_out = 0; *strand_out = 0; return ~0ull; }
+	// strand of the winning window [bp-k+1, bp]: r is the complemented window as packed, f its field reversal
+	const int o = 2 * (bp - k + 1), wi = o >> 6, sh = o & 63;
+	uint64_t v = row[wi] >> sh;
+	if (sh + 2 * k > 64) v |= row[wi + 1] << (64 - sh);
+	const uint64_t mask = (1ull << (2 * k)) - 1;
+	v &= mask;
+	const uint64_t r = ~v & mask;
+	uint64_t f = __brevll(v) >> (64 - 2 * k);
+	f = ((f >> 1) & 0x5555555555555555ull) | ((f & 0x5555555555555555ull) << 1);
+	*pos_out = bp; *strand_out = f < r ? 0 : 1;
+	return ((uint64_t)bhi << 32 | blo) >> M.sh;
+}
+// the device kernels' entry: top-aligned walk for 16 < k < 32, the generic one otherwise
+__device__ __forceinline__ uint64_t mcb_sketch_two_dev(const uint64_t *row, int L, int k, const McbTaMul &M, int *pos_out, int *strand_out)
+{
+	if (k > 16 && k < 32) return (k & 1) ? mcb_sketch_two_ta<true>(row, L, k, M, pos_out, strand_out) : mcb_sketch_two_ta<false>(row, L, k, M, pos_out, strand_out);
+	return mcb_sketch_two_packed_t<false, false>(row, L, k, pos_out, strand_out);
 }
 #endif
 MCB_HD uint64_t mcb_sketch_two_packed(const uint64_t *row, int L, int k, int *pos_out, int *strand_out)

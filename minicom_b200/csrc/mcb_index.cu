@@ -533,6 +533,7 @@ extern "C" int mcb_idx_build_scattered(mcb_ctx *ctx, const mcb_tuple *const *ptr
 // offset and posting arrays stay on the device (d_scr[4..7]) for the lookups of the merge kernels.
 int mcb_index_build_device(mcb_ctx *ctx, mcb_tuple *d_tuples, uint64_t n, const uint64_t *d_boff, const uint64_t *h_boff, McbDeviceIndex *out)
 {
+	McbMergeScope metric_scope(ctx->tm, 0);                    // mm_idx_generation is part of the metric even when the merge calls it
 	const int b = ctx->prm.b, nb = 1 << b;
 	memset(out, 0, sizeof *out);
 	out->b = b; out->n_post = n;

@@ -34,7 +34,7 @@ MCB_HD int mcb_classify(const McbCounts &q, int L, int e, int *repl_code)
 #define HASN_BIT 0x80
 
 __global__ void __launch_bounds__(RD_THREADS)
-k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, uint64_t rid_base, int L, int Wd, int WS, int k, int e, int pbase,
+k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, uint64_t rid_base, int L, int Wd, int WS, int k, McbTaMul TM, int e, int pbase,
                        uint64_t *__restrict__ packed, uint8_t *__restrict__ cls, ulonglong2 *__restrict__ elem,
                        unsigned long long *__restrict__ counters)
 {
@@ -113,7 +113,7 @@ k_pack_classify_sketch(const uint8_t *__restrict__ ascii, uint64_t n, uint64_t r
 		ulonglong2 el; el.x = MCB_K1_INVALID; el.y = mcb_make_k2_invalid((uint32_t)rid);
 		if (c == MCB_CLS_SKETCHED && !bad) {
 			int pos, z;
-			uint64_t x = mcb_sketch_two_packed(sp[t], L, k, &pos, &z);
+			uint64_t x = mcb_sketch_two_dev(sp[t], L, k, TM, &pos, &z);
 			if (x == ~0ull) degenerate = true;
 			else { el.x = mcb_make_k1(x); el.y = mcb_make_k2((uint32_t)rid, pos, z, L, k, pbase); sketched = true; }
 		}
@@ -201,7 +201,7 @@ __device__ __forceinline__ bool mcb_count_packed(const uint64_t *row, int L, int
 // thread per read without N: classification from popcounts, sketch, sort element.  src == dst when the rows were uploaded in
 // place; otherwise (rows resident in the caller's device buffer) the row is also copied into the context's read table
 __global__ void __launch_bounds__(RD_THREADS)
-k_classify_sketch_packed(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, uint64_t n, uint64_t lid0, uint64_t rid_base, int L, int Wd, int WS, int k, int e, int pbase,
+k_classify_sketch_packed(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, uint64_t n, uint64_t lid0, uint64_t rid_base, int L, int Wd, int WS, int k, McbTaMul TM, int e, int pbase,
                          const uint32_t *__restrict__ hasn_bits, uint8_t *__restrict__ cls, ulonglong2 *__restrict__ elem, unsigned long long *__restrict__ counters)
 {
 	__shared__ uint64_t sp[RD_THREADS][9];
@@ -228,7 +228,7 @@ k_classify_sketch_packed(const uint64_t *__restrict__ src, uint64_t *__restrict_
 			ulonglong2 el; el.x = MCB_K1_INVALID; el.y = mcb_make_k2_invalid((uint32_t)rid);
 			if (c == MCB_CLS_SKETCHED && !bad) {
 				int pos, z;
-				const uint64_t x = mcb_sketch_two_packed(sp[t], L, k, &pos, &z);
+				const uint64_t x = mcb_sketch_two_dev(sp[t], L, k, TM, &pos, &z);
 				if (x == ~0ull) degenerate = true;
 				else { el.x = mcb_make_k1(x); el.y = mcb_make_k2((uint32_t)rid, pos, z, L, k, pbase); sketched = true; }
 			}
@@ -245,7 +245,7 @@ k_classify_sketch_packed(const uint64_t *__restrict__ src, uint64_t *__restrict_
 // and the context's side table (global read id, mask, replacement character)
 __global__ void __launch_bounds__(RD_THREADS)
 k_nreads_packed(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, const uint32_t *__restrict__ nrid_local, const uint64_t *__restrict__ nmask, uint64_t nn, uint64_t n,
-                uint64_t rid_base, int L, int Wd, int WS, int k, int e, int pbase, uint32_t *__restrict__ nrid_out, uint8_t *__restrict__ nrepl,
+                uint64_t rid_base, int L, int Wd, int WS, int k, McbTaMul TM, int e, int pbase, uint32_t *__restrict__ nrid_out, uint8_t *__restrict__ nrepl,
                 uint8_t *__restrict__ cls, ulonglong2 *__restrict__ elem, unsigned long long *__restrict__ counters)
 {
 	__shared__ uint64_t sp[RD_THREADS][9];
@@ -279,7 +279,7 @@ k_nreads_packed(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, co
 	if (bad) atomicAdd(&counters[CT_BADCHAR], 1ull);
 	else if (c == MCB_CLS_SKETCHED) {
 		int pos, z;
-		const uint64_t x = mcb_sketch_two_packed(sp[t], L, k, &pos, &z);
+		const uint64_t x = mcb_sketch_two_dev(sp[t], L, k, TM, &pos, &z);
 		if (x == ~0ull) atomicAdd(&counters[CT_DEGENERATE], 1ull);
 		else { el.x = mcb_make_k1(x); el.y = mcb_make_k2((uint32_t)rid, pos, z, L, k, pbase); atomicAdd(&counters[CT_SKETCHED], 1ull); }
 	}
@@ -288,7 +288,7 @@ k_nreads_packed(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, co
 }
 
 // batched mm_sketch_two over already packed reads (rounds >= 2: kthread_bucket.c:205,489)
-__global__ void k_resketch(const uint64_t *__restrict__ packed, int WS, int L, int k_orig, int kmer, int pbase,
+__global__ void k_resketch(const uint64_t *__restrict__ packed, int WS, int L, int k_orig, int kmer, McbTaMul TM, int pbase,
                            const uint32_t *__restrict__ rids, uint64_t n, ulonglong2 *__restrict__ elem, unsigned long long *__restrict__ counters)
 {
 	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,7 +298,7 @@ __global__ void k_resketch(const uint64_t *__restrict__ packed, int WS, int L, i
 #pragma unroll
 	for (int w = 0; w < 8; ++w) row[w] = w < WS ? packed[(uint64_t)rid * WS + w] : 0ull;
 	int pos, z;
-	uint64_t x = mcb_sketch_two_packed(row, L, kmer, &pos, &z);
+	uint64_t x = mcb_sketch_two_dev(row, L, kmer, TM, &pos, &z);
 	ulonglong2 el;
 	if (x == ~0ull) { atomicAdd(&counters[CT_DEGENERATE], 1ull); el.x = MCB_K1_INVALID; el.y = mcb_make_k2_invalid(rid); }
 	else { el.x = mcb_make_k1(x); el.y = mcb_make_k2(rid, pos, z, L, k_orig, pbase); }
@@ -874,7 +874,7 @@ static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_r
 	if (n && !h_rows) {
 		McbSpan sp(ctx->tm, "for_reads");
 		MCB_LAUNCH(ctx, "pack_classify_sketch", k_pack_classify_sketch, mcb_grid_for(n, RD_THREADS), RD_THREADS, smem,
-		           d_rows, n, rid_base, L, Wd, WS, ctx->prm.k, ctx->prm.diff_threshold, pbase,
+		           d_rows, n, rid_base, L, Wd, WS, ctx->prm.k, mcb_ta_mul(ctx->prm.k), ctx->prm.diff_threshold, pbase,
 		           ctx->d_packed.as<uint64_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
 	} else if (n) {
 		if (!ctx->copy_stream) MCB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -896,7 +896,7 @@ static int for_reads_impl(mcb_ctx *ctx, const uint8_t *d_rows, uint64_t n, mcb_r
 			MCB_CUDA(cudaStreamWaitEvent(ctx->stream, ev[c], 0));
 			McbSpan sp(ctx->tm, "for_reads");
 			MCB_LAUNCH(ctx, "pack_classify_sketch", k_pack_classify_sketch, mcb_grid_for(cnt, RD_THREADS), RD_THREADS, smem,
-			           d_rows + off * L, cnt, rid_base + off, L, Wd, WS, ctx->prm.k, ctx->prm.diff_threshold, pbase,
+			           d_rows + off * L, cnt, rid_base + off, L, Wd, WS, ctx->prm.k, mcb_ta_mul(ctx->prm.k), ctx->prm.diff_threshold, pbase,
 			           ctx->d_packed.as<uint64_t>(), ctx->d_cls.as<uint8_t>() + off, ctx->d_elemA.as<ulonglong2>() + off, dc);
 		}
 		MCB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
@@ -1089,9 +1089,9 @@ static int for_reads_packed_impl(mcb_ctx *ctx, const uint64_t *rows, uint64_t n,
 		}
 		McbSpan sp(ctx->tm, "for_reads");
 		MCB_LAUNCH(ctx, "classify_sketch_packed", k_classify_sketch_packed, mcb_grid_for(n, RD_THREADS), RD_THREADS, 0, src, slice, n, (uint64_t)0, rid_base, L, Wd, WS,
-		           ctx->prm.k, ctx->prm.diff_threshold, pbase, bits, ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+		           ctx->prm.k, mcb_ta_mul(ctx->prm.k), ctx->prm.diff_threshold, pbase, bits, ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
 		if (nn) MCB_LAUNCH(ctx, "nreads_packed", k_nreads_packed, mcb_grid_for(nn, RD_THREADS), RD_THREADS, 0, src, slice, d_nrid_local, d_nmask, nn, n, rid_base, L, Wd, WS,
-		                   ctx->prm.k, ctx->prm.diff_threshold, pbase, ctx->d_nread_rid.as<uint32_t>(), ctx->d_scr[1].as<uint8_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+		                   ctx->prm.k, mcb_ta_mul(ctx->prm.k), ctx->prm.diff_threshold, pbase, ctx->d_nread_rid.as<uint32_t>(), ctx->d_scr[1].as<uint8_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
 	} else if (n) {
 		if (!ctx->copy_stream) MCB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
 		const uint64_t CH = 1u << 21;                                   // reads per chunk: 64 MB at L = 100
@@ -1112,12 +1112,12 @@ static int for_reads_packed_impl(mcb_ctx *ctx, const uint64_t *rows, uint64_t n,
 			MCB_CUDA(cudaStreamWaitEvent(ctx->stream, ev[c], 0));
 			McbSpan sp(ctx->tm, "for_reads");
 			MCB_LAUNCH(ctx, "classify_sketch_packed", k_classify_sketch_packed, mcb_grid_for(cnt, RD_THREADS), RD_THREADS, 0, slice + off * WS, slice + off * WS, cnt, off, rid_base, L, Wd, WS,
-			           ctx->prm.k, ctx->prm.diff_threshold, pbase, bits, ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+			           ctx->prm.k, mcb_ta_mul(ctx->prm.k), ctx->prm.diff_threshold, pbase, bits, ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
 		}
 		if (nn) {
 			McbSpan sp(ctx->tm, "for_reads");
 			MCB_LAUNCH(ctx, "nreads_packed", k_nreads_packed, mcb_grid_for(nn, RD_THREADS), RD_THREADS, 0, slice, slice, d_nrid_local, d_nmask, nn, n, rid_base, L, Wd, WS,
-			           ctx->prm.k, ctx->prm.diff_threshold, pbase, ctx->d_nread_rid.as<uint32_t>(), ctx->d_scr[1].as<uint8_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
+			           ctx->prm.k, mcb_ta_mul(ctx->prm.k), ctx->prm.diff_threshold, pbase, ctx->d_nread_rid.as<uint32_t>(), ctx->d_scr[1].as<uint8_t>(), ctx->d_cls.as<uint8_t>(), ctx->d_elemA.as<ulonglong2>(), dc);
 		}
 		MCB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
 		MCB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1206,7 +1206,7 @@ extern "C" int mcb_debug_sketch_two(mcb_ctx *ctx, const uint32_t *rids, uint64_t
 	MCB_TRY(ctx->d_scr[0].ensure(n * 4)); MCB_TRY(ctx->d_scr[1].ensure(n * 16)); MCB_TRY(ctx->d_scr[2].ensure(n * 16));
 	MCB_CUDA(cudaMemcpyAsync(ctx->d_scr[0].p, rids, n * 4, cudaMemcpyHostToDevice, ctx->stream));
 	// note: positions are encoded against prm.k, decode with the same
-	MCB_LAUNCH(ctx, "resketch", k_resketch, mcb_grid_for(n, 128), 128, 0, ctx->d_packed.as<uint64_t>(), ctx->WS, ctx->L, ctx->prm.k, k,
+	MCB_LAUNCH(ctx, "resketch", k_resketch, mcb_grid_for(n, 128), 128, 0, ctx->d_packed.as<uint64_t>(), ctx->WS, ctx->L, ctx->prm.k, k, mcb_ta_mul(k),
 	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[0].as<uint32_t>(), n, ctx->d_scr[1].as<ulonglong2>(), ctx->d_counters.as<unsigned long long>());
 	MCB_LAUNCH(ctx, "elem_to_tuple", k_elem_to_tuple, mcb_grid_for(n, 256), 256, 0, ctx->d_scr[1].as<ulonglong2>(), n, ctx->L, ctx->prm.k,
 	           ctx->L + ctx->prm.max_rounds, ctx->d_scr[2].as<mcb_tuple>(), 0, (uint64_t)0);
@@ -1423,12 +1423,12 @@ int mcb_bucket_round_b_impl(mcb_ctx *ctx, uint64_t cid_first)
 			auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
 			if (lh2_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh2_smem));
 			MCB_LAUNCH(ctx, "sketch_lh", kern, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh2_smem, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
-			           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>(), (const uint64_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, 0);
+			           rw, k, mcb_ta_mul(k), m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>(), (const uint64_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, 0);
 		}
 		bs.tot_cl += n_cl_new; bs.tot_mem += n_mem_new; bs.tot_ref += n_ref_new; bs.tot_sg += n_sg_new;
 		// ---- rejected reads go to the next round with a shorter k-mer (kthread_bucket.c:205-212,488-496)
 		if (!is_last && n_resk) {
-			MCB_LAUNCH(ctx, "resketch", k_resketch, mcb_grid_for(n_resk, 128), 128, 0, ctx->d_packed.as<uint64_t>(), WS, L, k, kmer, pbase,
+			MCB_LAUNCH(ctx, "resketch", k_resketch, mcb_grid_for(n_resk, 128), 128, 0, ctx->d_packed.as<uint64_t>(), WS, L, k, kmer, mcb_ta_mul(kmer), pbase,
 			           B.b_rk.as<uint32_t>(), n_resk, bs.alt, dc);
 			ulonglong2 *t = bs.cur; bs.cur = bs.alt; bs.alt = t;
 			bs.tot_sk += n_resk;

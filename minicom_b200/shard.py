@@ -152,13 +152,21 @@ class ShardedFrontEnd:
 
     # ---- Stage 1: kt_for_reads + kt_for_bucket over the whole read set
     def stage1(self, rows_local, n_total: int, device_resident: bool = False, keep_mask: bool = False):
-        """rows_local: this rank's reads, (n_local, L) uint8 (numpy, or a CUDA tensor when device_resident).
+        """rows_local: this rank's reads: (n_local, L) uint8 ASCII rows (numpy, or a CUDA tensor when device_resident), an
+        api.ReadSet (packed on the host by the library's FASTQ reader), or a tuple (d_packed, d_nread_rid, d_nmask, n_nreads) of
+        device pointers to the same packed arrays.
         Returns (ReadsResult of the slice, Stage1Part of this rank).  keep_mask: the ownership bitmap of an earlier call on the
         same reads is still right (repeated runs of one job), do not rebuild it."""
         ctx = self.ctx
         lo, hi = rid_range(n_total, self.rank, self.world)
         ctx.shard_begin(n_total, lo)
-        rr = ctx.for_reads_device(rows_local.data_ptr(), hi - lo) if device_resident else ctx.for_reads(rows_local)
+        if isinstance(rows_local, tuple):
+            rr = ctx.for_reads_packed_device(rows_local[0], hi - lo, rows_local[1], rows_local[2], rows_local[3])
+        elif hasattr(rows_local, "view") and hasattr(rows_local, "add_rows"):
+            assert len(rows_local) == hi - lo
+            rr = ctx.for_reads_packed(rows_local)
+        else:
+            rr = ctx.for_reads_device(rows_local.data_ptr(), hi - lo) if device_resident else ctx.for_reads(rows_local)
         br, rounds = ctx.shard_for_bucket()
         if not (keep_mask and self.mask is not None):
             self.mask = owned_mask(n_total, br.sg)
