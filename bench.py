@@ -614,10 +614,13 @@ def bench_pipeline(args):
             "algorithmic_bytes_per_launch": step_bytes / launches_per_step if step_bytes else None, "launches_per_step": launches_per_step,
             "avg_launch_ms": dom_ms / max(1, dom_cnt), "share_of_device_time": round(dom_ms / max(1e-9, metric_ms(tm)), 4)}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and args.workload == "C2":
         with open(prof) as f:
-            roof["traffic"] = json.load(f).get(dom[2:])
-    roof["issue"] = issue_roofline(dom[2:], args.workload, avg_launch_s, torch.cuda.get_device_properties(local).multi_processor_count, clk.summary().get("sm_mhz"))
+            per_step = json.load(f).get(dom[2:])                       # DRAM bytes of all launches of the kernel in one step (committed ncu capture)
+        if per_step:
+            roof["traffic"] = per_step / max(1.0, launches_per_step)
+            roof["traffic_per_step"] = per_step
+            roof["algorithmic_bytes_per_step"] = step_bytes
     cpu = cpu_baseline(args.workload, 1, quiet=True) if not args.no_cpu_baseline else None
     value = n / (ms_dev / 1e3)
     line = {

@@ -14,6 +14,8 @@
  *                                               the caller between kt_for_bucket and realign_hash: SURVEY.md 8f, N1)
  *   mcb_realign         <- realign_hash        kthread_hash_realign.c:569 (singleRead2bitset bbhashdict.c:127,
  *                                               constructdictionary_realign :3, realign_hash_search :316)
+ *   mcb_readset_*       <- bseq_open/bseq_read bseq.c:19-96  (FASTQ -> 2-bit packed rows on the host)
+ *   mcb_dump_encode     <- print_encode        kthread_dump.c:33 (the per-read diff encoding only; SURVEY.md 8f, N2 first slice)
  *   mcb_sketch_lh_host  <- mm_sketch_lh_ori    sketch.c:116  (per-contig call made by the host contig merger,
  *                                               kthread_cb.c:234,365,418 — a boundary helper, not the batched path)
  *
@@ -273,6 +275,26 @@ int mcb_realign(mcb_ctx *ctx, const uint32_t *sg, uint64_t n_sg, const char *ref
                 uint64_t n_contigs, int threshold, int maxsearch, int ininumdict, mcb_realign_result *res);
 
 #define MCB_CLAIM_NONE 0x7F7F7F7F7F7F7F7Fll
+
+/* ------------------------------------------------------------------ */
+/* print_encode (kthread_dump.c:33-236), SURVEY.md 8f row N2: first slice */
+/* ------------------------------------------------------------------ */
+/* The per-read diff encoding of the dump stage (the loop at kthread_dump.c:66-118, shared by the ORDER, default and _PE
+ * variants): for every member of every contig the line print_encode writes to dif_char.txt — the read as it was before N
+ * replacement, reverse-complemented when dir, against its consensus window: runs of >= 2 equal characters as their decimal
+ * length, a run of 1 copied, every mismatching character copied, the trailing run dropped, "0" when nothing differs.
+ * members: y = rid<<32 | pos<<1 | dir, contig-major in the order the caller dumps them (after its qsort by cmpcluster2/3);
+ * member_off[n_contigs+1]; refs / ref_off as in mcb_realign (NULL, NULL: the contigs the context holds from the last
+ * mcb_combine / mcb_realign).  The reads are the ones mcb_for_reads* loaded.  enc holds the encodings back to back, no
+ * separators; member i occupies [enc_off[i], enc_off[i+1]).  Not yet bound by the drop-in shim: the rest of cluster_dump
+ * (position deltas, direction bits, packed consensus, the output files) is still the reference's host code. */
+typedef struct {
+	uint64_t n_members, n_bytes;
+	const uint64_t *enc_off;      /* [n_members+1] */
+	const char *enc;              /* [n_bytes] */
+} mcb_encode_result;
+int mcb_dump_encode(mcb_ctx *ctx, const uint64_t *members, const uint64_t *member_off, const char *refs, const uint64_t *ref_off, uint64_t n_contigs,
+                    mcb_encode_result *res);
 
 /* ------------------------------------------------------------------ */
 /* the same path over the GPUs of one box                */

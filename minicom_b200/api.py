@@ -38,6 +38,10 @@ class _ReadsetView(C.Structure):
                 ("nread_rid", C.c_void_p), ("nmask", C.c_void_p)]
 
 
+class _EncodeResult(C.Structure):
+    _fields_ = [("n_members", C.c_uint64), ("n_bytes", C.c_uint64), ("enc_off", C.c_void_p), ("enc", C.c_void_p)]
+
+
 class _BucketResult(C.Structure):
     _fields_ = [("n_clusters", C.c_uint64), ("cl_n", C.c_void_p), ("cl_a_off", C.c_void_p), ("cl_a", C.c_void_p),
                 ("cl_ref_off", C.c_void_p), ("cl_ref", C.c_void_p), ("n_sg", C.c_uint64), ("sg", C.c_void_p),
@@ -60,7 +64,7 @@ class _RealignResult(C.Structure):
 EXPORTS = [
     "mcb_resolve_params", "mcb_create", "mcb_destroy", "mcb_last_error", "mcb_version",
     "mcb_for_reads", "mcb_for_reads_ptrs", "mcb_for_reads_device", "mcb_for_reads_packed", "mcb_for_reads_packed_device",
-    "mcb_readset_create", "mcb_readset_destroy", "mcb_readset_add_fastq", "mcb_readset_add_fastq_buffer", "mcb_readset_add_rows", "mcb_readset_get",
+    "mcb_dump_encode", "mcb_readset_create", "mcb_readset_destroy", "mcb_readset_add_fastq", "mcb_readset_add_fastq_buffer", "mcb_readset_add_rows", "mcb_readset_get",
     "mcb_debug_read_tuples", "mcb_debug_sketch_two", "mcb_debug_unpack_reads",
     "mcb_for_bucket", "mcb_for_bucket_keep", "mcb_idx_build", "mcb_idx_build_scattered", "mcb_idx_get", "mcb_idx_destroy", "mcb_idx_stats", "mcb_idx_arrays",
     "mcb_combine", "mcb_realign", "mcb_sketch_lh_host", "mcb_sketch_two_host", "mcb_hash64",
@@ -108,6 +112,7 @@ def load_library() -> C.CDLL:
     lib.mcb_readset_add_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     lib.mcb_readset_get.argtypes = [C.c_void_p, C.POINTER(_ReadsetView)]
     lib.mcb_readset_get.restype = None
+    lib.mcb_dump_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_EncodeResult)]
     lib.mcb_debug_read_tuples.argtypes = [C.c_void_p, C.c_void_p]
     lib.mcb_debug_sketch_two.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     lib.mcb_debug_unpack_reads.argtypes = [C.c_void_p, C.c_void_p]
@@ -439,6 +444,20 @@ class Context:
         out = np.zeros((n, self.params.readlen), dtype=np.uint8)
         self._check(self.lib.mcb_debug_unpack_reads(self._h, out.ctypes.data))
         return out
+
+    # -- print_encode's per-read encoding (N2, first slice)
+    def dump_encode(self, members, member_off, refs=None, ref_off=None):
+        """(enc_off u64[n+1], enc bytes) for members y = rid<<32 | pos<<1 | dir given contig-major with member_off[n_contigs+1]"""
+        members = np.ascontiguousarray(members, dtype=np.uint64)
+        member_off = np.ascontiguousarray(member_off, dtype=np.uint64)
+        r = _EncodeResult()
+        if refs is None:
+            self._check(self.lib.mcb_dump_encode(self._h, members.ctypes.data, member_off.ctypes.data, None, None, len(member_off) - 1, C.byref(r)))
+        else:
+            refs = np.ascontiguousarray(refs, dtype=np.uint8)
+            ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
+            self._check(self.lib.mcb_dump_encode(self._h, members.ctypes.data, member_off.ctypes.data, refs.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1, C.byref(r)))
+        return _view(r.enc_off, r.n_members + 1, np.uint64), _view(r.enc, r.n_bytes, np.uint8).tobytes()
 
     # -- kt_for_bucket
     def for_bucket(self) -> BucketResult:

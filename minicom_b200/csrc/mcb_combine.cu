@@ -474,7 +474,7 @@ static int cb_sketch(mcb_ctx *ctx, CbSet &S, uint64_t n_items, uint32_t *cnt32, 
 	auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
 	if (smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	MCB_LAUNCH(ctx, "cb_sketch", kern, mcb_grid_for(n_items, LH_THREADS), LH_THREADS, smem, S.ref.as<char>(), S.roff.as<uint64_t>(), (uint64_t)0, n_items, (uint64_t)0,
-	           rw, k, mcb_ta_mul(k), INT_MAX, slots ? slots : off ? S.mins.as<mcb_tuple>() : (mcb_tuple*)nullptr, (uint8_t*)nullptr, off, cnt32, ch_contig, ch_start, ch_len, slots ? slot_cap : 0);
+	           rw, k, INT_MAX, slots ? slots : off ? S.mins.as<mcb_tuple>() : (mcb_tuple*)nullptr, (uint8_t*)nullptr, off, cnt32, ch_contig, ch_start, ch_len, slots ? slot_cap : 0);
 	return MCB_OK;
 }
 

@@ -28,7 +28,7 @@ struct LhRingSmem {
 template <bool WIDE>
 __global__ void __launch_bounds__(LH_THREADS)
 k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_ref_off, uint64_t cl_first, uint64_t cl_count, uint64_t cid_first,
-             int w, int k, McbTaMul TM, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ cnt32,
+             int w, int k, int m, mcb_tuple *__restrict__ mi, uint8_t *__restrict__ mi_cnt, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ cnt32,
              const uint32_t *__restrict__ ch_contig = nullptr, const uint32_t *__restrict__ ch_start = nullptr, int ch_len = 0, int slot_cap = 0)
 {
 	extern __shared__ __align__(16) unsigned char lh_smem[];
@@ -62,14 +62,16 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 	const int wlim = slot_cap ? slot_cap : m;
 	int n_out = 0;
 	const uint64_t mask = (1ull << (2 * k)) - 1, shift1 = 2 * (k - 1);
+	const uint32_t mh = (uint32_t)(mask >> 32);
+	const int s1 = WIDE ? 2 * (k - 1) - 32 : 0;
+	const uint32_t t3 = 3u << s1;
 	uint64_t fw = 0, rv = 0;
 	uint32_t flo = 0, fhi = 0, rlo = 0, rhi = 0;
 	uint64_t mn_x = ~0ull; uint32_t mn_p = ~0u;
 	uint64_t px = ~0ull; int pslot = 0; bool ptie = false;             // rightmost minimum of the slots written in this block
 	int l = b0, seen = 0, bp = 0, mp = 0;                               // l: bases since the last ambiguous one (= position here); seen: bases rolled into fw / rv
 	bool on = b0 >= start;
-	const int esh = WIDE ? TM.sh : 0;                                   // WIDE: hashes are kept top-aligned (mcb_hash64_ta), shifted down when emitted
-#define LH_EMIT(hx_, p_) do { if (on) { if (out && n_out < wlim) { mcb_tuple t_; t_.x = (hx_) >> esh; t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } } while (0)
+#define LH_EMIT(hx_, p_) do { if (on) { if (out && n_out < wlim) { mcb_tuple t_; t_.x = (hx_); t_.y = (uint64_t)rid << 32 | (uint64_t)(p_); out[n_out] = t_; } ++n_out; } } while (0)
 	for (int j = 0; j < w; ++j) { ring.set(j, ~0ull, ~0u); sst[j * LH_THREADS] = (uint8_t)(w - 1); }
 	for (int i = b0; i < end && n_out < m; ++i) {
 		const int ai = i + skew;
@@ -79,7 +81,8 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 		uint64_t ix = ~0ull; uint32_t ip = ~0u;
 		if (cc < 4) {
 			if (WIDE) {
-				MCB_TA_ROLL(cc, flo, fhi, rlo, rhi, TM);
+				fhi = __funnelshift_l(flo, fhi, 2) & mh; flo = flo * 4u + cc;
+				rlo = __funnelshift_r(rlo, rhi, 2); rhi = (rhi >> 2) | ((cc << s1) ^ t3);
 				fw = (uint64_t)fhi << 32 | flo; rv = (uint64_t)rhi << 32 | rlo;
 			} else {
 				fw = (fw << 2 | cc) & mask;
@@ -88,7 +91,7 @@ k_sketch_lh2(const char *__restrict__ cl_ref, const uint64_t *__restrict__ cl_re
 			if (fw == rv) continue;
 			const int z = fw < rv ? 0 : 1;
 			++l;
-			if (++seen >= k) { ix = WIDE ? mcb_hash64_ta(z ? rlo : flo, z ? rhi : fhi, TM) : mcb_hash64_hd(z ? rv : fw, mask); ip = (uint32_t)i << 1 | (uint32_t)z; }
+			if (++seen >= k) { ix = WIDE ? mcb_hash64_wide(z ? rv : fw, mh) : mcb_hash64_hd(z ? rv : fw, mask); ip = (uint32_t)i << 1 | (uint32_t)z; }
 		} else { l = 0; seen = 0; }
 		ring.set(bp, ix, ip);
 		{

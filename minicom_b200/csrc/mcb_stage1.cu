@@ -691,17 +691,27 @@ __device__ void cons_groups_bs(const ulonglong2 *__restrict__ el, uint32_t s, ui
 		unsigned long long refoff = 0;
 		int reflen2 = 0;
 		if (iscl) { sv = first_cov; reflen2 = last_cov + 1 - sv; }
-		if (iscl && lead) refoff = atomicAdd(&counters[CT_REFCURSOR], (unsigned long long)reflen2);
+		// The consensus goes to the scratch string buffer as whole 32-byte pieces: lane wq writes the characters of its 32 columns
+		// with two 16-byte stores into a 32-byte aligned slot of ceil(ncol/32) pieces, and the string proper (the covered span) is
+		// recorded as slot + sv.  (Byte stores, one column per lane and iteration, were 27 M store sectors for 1.1 M groups.)
+		const int npiece = (ncol + 31) >> 5;
+		if (iscl && lead) refoff = (atomicAdd(&counters[CT_REFCURSOR], (unsigned long long)(32 * npiece + 32)) + 31ull) & ~31ull;
 		refoff = __shfl_sync(FULL, refoff, lane & ~(GW - 1));
 		if (iscl) {
-			if (refoff + reflen2 > reftmp_cap) { if (lead) atomicAdd(&counters[CT_ERR], 1ull); }
-			else {
-				const int c0 = max(sv, 32 * wq), c1 = min(sv + reflen2, 32 * wq + 32);
-				for (int c = c0; c < c1; ++c) {
-					const int b = c - 32 * wq;
-					o.reftmp[refoff + (c - sv)] = "ACGT"[((conlo >> b) & 1u) | (((conhi >> b) & 1u) << 1)];
+			if (refoff + 32ull * npiece > reftmp_cap) { if (lead) atomicAdd(&counters[CT_ERR], 1ull); }
+			else if (wq < npiece) {
+				uint32_t wd[8];
+#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					const uint32_t l = (conlo >> (4 * j)) & 0xFu, h = (conhi >> (4 * j)) & 0xFu;
+					const uint32_t sel = ((l * 0x249u) & 0x1111u) | (((h * 0x249u) & 0x1111u) << 1);       // code of column 4j+i in nibble i
+					wd[j] = __byte_perm(0x54474341u, 0u, sel);                                             // "ACGT"[code]
 				}
+				uint4 *dst = (uint4*)(o.reftmp + refoff + 32ull * wq);
+				dst[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+				dst[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
 			}
+			refoff += (unsigned long long)sv;
 		}
 		if (have && lead) {
 			const uint32_t nout = iscl ? (uint32_t)nrej : cntm;
@@ -1286,7 +1296,8 @@ int mcb_bucket_round_a_impl(mcb_ctx *ctx, int r, int is_last)
 	const size_t cs_smem = cs_per_warp * CS_WARPS;
 	if (cs_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(k_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem));
 	// the ASCII buffer is dead after mcb_for_reads: reuse it for consensus strings before compaction
-	MCB_TRY(ctx->d_ascii.ensure((size_t)std::max<uint64_t>(bs.n_valid, ctx->n_local) * L + 16));
+	// (room for the 32-byte aligned slots of k_consensus_bs: a group of g reads takes at most g*L + 95 bytes)
+	MCB_TRY(ctx->d_ascii.ensure((size_t)std::max<uint64_t>(bs.n_valid, ctx->n_local) * (L + 48) + 256));
 	const uint64_t reftmp_cap = ctx->d_ascii.cap;
 	McbSpan sp(ctx->tm, "for_bucket");
 	// ---- K2: one stable sort; key = (bucket, minimizer, adjusted pos desc, rid asc)
@@ -1423,7 +1434,7 @@ int mcb_bucket_round_b_impl(mcb_ctx *ctx, uint64_t cid_first)
 			auto kern = (k > 16 && k < 32) ? k_sketch_lh2<true> : k_sketch_lh2<false>;
 			if (lh2_smem > 48 * 1024) MCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lh2_smem));
 			MCB_LAUNCH(ctx, "sketch_lh", kern, mcb_grid_for(n_cl_new, LH_THREADS), LH_THREADS, lh2_smem, B.d_cl_ref.as<char>(), B.d_cl_roff.as<uint64_t>(), tot_cl, n_cl_new, cid_first,
-			           rw, k, mcb_ta_mul(k), m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>(), (const uint64_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, 0);
+			           rw, k, m, B.d_mi.as<mcb_tuple>(), B.d_micnt.as<uint8_t>(), (const uint64_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0, 0);
 		}
 		bs.tot_cl += n_cl_new; bs.tot_mem += n_mem_new; bs.tot_ref += n_ref_new; bs.tot_sg += n_sg_new;
 		// ---- rejected reads go to the next round with a shorter k-mer (kthread_bucket.c:205-212,488-496)

@@ -999,3 +999,31 @@ int mco_pack_row(const char *s, int L, int WS, uint64_t *row, uint64_t *mask)
 	}
 	return hasn;
 }
+
+/* ------------------------------------------------------------------ N2: the per-read diff encoding of the dump stage */
+/* print_encode's inner loop (kthread_dump.c:66-118, identical in the ORDER, default and _PE variants): the read as it was before
+ * N replacement (N put back, :70-75), reverse-complemented when dir (preprocess.c:22-36: N stays N), compared with the consensus
+ * window; a run of >= 2 equal characters becomes its decimal length, a run of 1 is copied, every mismatching character is copied;
+ * the trailing run is dropped; no mismatch at all -> "0".  read: L characters (may hold N); ref_window: L consensus characters;
+ * out: at least L+1 bytes.  Returns the length (no terminator). */
+int mco_print_encode(const char *read, int dir, const char *ref_window, int L, char *out)
+{
+	char *tmp = (char*)malloc((size_t)L + 1);
+	if (dir) for (int i = L - 1, j = 0; i >= 0; --i, ++j) { char c = read[i]; tmp[j] = c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'G' ? 'C' : c == 'C' ? 'G' : 'N'; }
+	else memcpy(tmp, read, (size_t)L);
+	int n = 0, eq = 0;
+	for (int tj = 0; tj < L; ++tj) {
+		if (ref_window[tj] != tmp[tj]) {
+			if (eq > 1) {
+				char digits[12]; int nd = 0, v = eq;
+				while (v) { digits[nd++] = (char)('0' + v % 10); v /= 10; }
+				while (nd) out[n++] = digits[--nd];
+			} else for (int i = tj - eq; i < tj; ++i) out[n++] = tmp[i];
+			eq = 0;
+			out[n++] = tmp[tj];
+		} else ++eq;
+	}
+	if (n == 0) out[n++] = '0';
+	free(tmp);
+	return n;
+}

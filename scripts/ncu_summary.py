@@ -8,7 +8,7 @@ import json
 import re
 
 COLS = {"ms": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram__bytes_write.sum",
-        "dram_pct": "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram_pct": "dram__throughput.avg.pct_of_peak_sustained_elapsed", "rd_pct": "dram__bytes_read.sum.pct_of_peak_sustained_elapsed", "wr_pct": "dram__bytes_write.sum.pct_of_peak_sustained_elapsed", "sm_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "occ": "sm__warps_active.avg.pct_of_peak_sustained_active", "regs": "launch__registers_per_thread", "winst": "smsp__inst_executed.sum",
         "lanes": "smsp__thread_inst_executed_per_inst_executed.ratio", "issue": "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "l1hit": "l1tex__t_sector_hit_rate.pct"}
@@ -47,6 +47,8 @@ def main():
                     d[k] = float("nan")
             for k in COLS:
                 d.setdefault(k, float("nan"))
+            if d["dram_pct"] != d["dram_pct"]:                      # the section-prefixed column is empty in some exports: read % + write %
+                d["dram_pct"] = d["rd_pct"] + d["wr_pct"]
             rows.append(d)
     out = ["| # | kernel | grid | ms | DRAM MB (rd+wr) | DRAM % | SM % | issue % | lanes/inst | occupancy % | regs | M warp inst | L1 hit % |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for i, d in enumerate(rows):

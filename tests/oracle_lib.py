@@ -38,6 +38,7 @@ def lib():
         L.mco_kseq_all.restype = C.c_int64
         L.mco_kseq_all.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64]
         L.mco_pack_row.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mco_print_encode.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p]
         L.mco_stage1_run.restype = C.c_void_p
         L.mco_stage1_run.argtypes = [C.POINTER(Params), C.c_void_p, C.c_uint64]
         L.mco_stage1_free.argtypes = [C.c_void_p]
@@ -132,6 +133,13 @@ def pack_rows(rows: np.ndarray):
     for i in range(n):
         st[i] = f(rows[i].tobytes(), L, ws, packed[i].ctypes.data, mask[i].ctypes.data)
     return packed, mask, st
+
+
+def print_encode(read: bytes, direction: int, ref_window: bytes) -> bytes:
+    """the line print_encode writes to dif_char.txt for one member (kthread_dump.c:85-118)"""
+    out = C.create_string_buffer(len(read) + 2)
+    n = lib().mco_print_encode(read, direction, ref_window, len(read), out)
+    return out.raw[:n]
 
 
 def encode_byte_ok(read_oriented: bytes, ref_window: bytes):
