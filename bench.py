@@ -197,7 +197,7 @@ def issue_roofline(kernel, workload, avg_launch_s, sm_count, sm_mhz, path=None):
     peak = sm_count * 4 * (sm_mhz or 1965.0) * 1e6
     achieved = tab[kernel] / avg_launch_s
     return {"unit": "warp instructions/s", "achieved": round(achieved, 1), "peak": peak, "frac": round(achieved / peak, 4),
-            "warp_instructions_per_launch": tab[kernel], "source": "profiles/instructions.json (ncu smsp__inst_executed.sum, same workload) / live launch time"}
+            "warp_instructions": tab[kernel], "source": "profiles/instructions.json (ncu smsp__inst_executed.sum, same workload, per step or per launch as the caller's time is) / live device time"}
 
 
 def opts_text(ref_env):
@@ -621,6 +621,8 @@ def bench_pipeline(args):
             roof["traffic"] = per_step / max(1.0, launches_per_step)
             roof["traffic_per_step"] = per_step
             roof["algorithmic_bytes_per_step"] = step_bytes
+    # the same kernel against the instruction-issue roofline: warp instructions of its launches in one step (committed capture) / its live time per step
+    roof["issue"] = issue_roofline(dom[2:], args.workload, dom_ms / args.steps / 1e3, torch.cuda.get_device_properties(local).multi_processor_count, clk.summary().get("sm_mhz"))
     cpu = cpu_baseline(args.workload, 1, quiet=True) if not args.no_cpu_baseline else None
     value = n / (ms_dev / 1e3)
     line = {

@@ -703,8 +703,10 @@ __device__ void cons_groups_bs(const ulonglong2 *__restrict__ el, uint32_t s, ui
 				uint32_t wd[8];
 #pragma unroll
 				for (int j = 0; j < 8; ++j) {
-					const uint32_t l = (conlo >> (4 * j)) & 0xFu, h = (conhi >> (4 * j)) & 0xFu;
-					const uint32_t sel = ((l * 0x249u) & 0x1111u) | (((h * 0x249u) & 0x1111u) << 1);       // code of column 4j+i in nibble i
+					uint32_t l = (conlo >> (4 * j)) & 0xFu, h = (conhi >> (4 * j)) & 0xFu;
+					l = (l | (l << 6)) & 0x0303u; l = (l | (l << 3)) & 0x1111u;                             // bit i -> bit 4i (no carries)
+					h = (h | (h << 6)) & 0x0303u; h = (h | (h << 3)) & 0x1111u;
+					const uint32_t sel = l | (h << 1);                                                     // code of column 4j+i in nibble i
 					wd[j] = __byte_perm(0x54474341u, 0u, sel);                                             // "ACGT"[code]
 				}
 				uint4 *dst = (uint4*)(o.reftmp + refoff + 32ull * wq);

@@ -29,4 +29,4 @@ def test_issue_roofline_uses_the_committed_capture(tmp_path):
 def test_committed_instruction_table_is_for_the_bench_default():
     with open(os.path.join(ROOT, "profiles", "instructions.json")) as f:
         tab = json.load(f)
-    assert tab["workload"] == "C2" and tab["pack_classify_sketch"] > 1e9
+    assert tab["workload"] == "C2" and tab["classify_sketch_packed"] > 1e9 and tab["consensus"] > 5e8
