@@ -260,7 +260,7 @@ static int index_records(const char *buf, size_t len, int L, std::vector<uint64_
 }
 
 // the whole file in memory, through zlib like the reference (gzopen reads plain files too, bseq.c:23)
-static int slurp(const char *path, std::vector<char> &out)
+static int slurp(const char *path, char **out, size_t *out_len)
 {
 	gzFile f = gzopen(path, "r");
 	if (!f) { mcb_set_error("cannot open %s", path); return MCB_EINPUT; }
@@ -284,8 +284,7 @@ static int slurp(const char *path, std::vector<char> &out)
 		n += (size_t)got;
 	}
 	gzclose(f);
-	out.assign(p, p + n);            // one copy; keeps the interface simple (the file is read once per run)
-	free(p);
+	*out = p; *out_len = n;          // the caller frees it
 	return MCB_OK;
 }
 
@@ -294,9 +293,11 @@ extern "C" int mcb_readset_add_fastq(mcb_readset *rs, const char *path, int n_th
 	if (!rs || !path) { mcb_set_error("mcb_readset_add_fastq: null argument"); return MCB_EINVAL; }
 	if (ascii_out) *ascii_out = nullptr;
 	if (n_added) *n_added = 0;
-	std::vector<char> buf;
-	MCB_TRY(slurp(path, buf));
-	return mcb_readset_add_fastq_buffer(rs, buf.data(), buf.size(), n_threads, ascii_out, n_added);
+	char *buf = nullptr; size_t len = 0;
+	MCB_TRY(slurp(path, &buf, &len));
+	const int rc = mcb_readset_add_fastq_buffer(rs, buf, len, n_threads, ascii_out, n_added);
+	free(buf);
+	return rc;
 }
 
 extern "C" int mcb_readset_add_fastq_buffer(mcb_readset *rs, const char *buf, uint64_t len, int n_threads, char **ascii_out, uint64_t *n_added)
