@@ -31,6 +31,7 @@ CXXFLAGS="-O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -I$B -I$HERE -I$REF -I$ROO
 # bseq.o (the FASTQ reader) is replaced by the shim's packing reader (N3) unless MCB_KEEP_BSEQ=1
 KEPT="misc preprocess kthread_cb kthread_dump minicommain"
 if [ "${MCB_KEEP_BSEQ:-0}" = 1 ]; then KEPT="bseq $KEPT"; CXXFLAGS="$CXXFLAGS -DMCB_KEEP_BSEQ"; fi
+if [ "${MCB_KEEP_DUMP:-0}" = 1 ]; then CXXFLAGS="$CXXFLAGS -DMCB_KEEP_DUMP"; fi
 # minicompe links from an archive (src/Makefile:24-25,33-34): kthread_dump.o is never pulled in and clashes with kthread_dump_pe.o
 [ "$MODE" = pe ] && KEPT="${KEPT/kthread_dump /kthread_dump_pe }"
 pids=()
@@ -41,14 +42,28 @@ for p in "${pids[@]}"; do wait "$p"; done
 # is renamed so that the shim's combine_cluster (the GPU contig merge) is the one preprocess.o calls; the reference's own host
 # merge remains reachable as mcb_ref_combine_cluster (MCB_HOST_MERGE=1, and the multi-GPU path).
 objcopy --redefine-sym _Z15combine_clusteriP7reads_tPi=_Z23mcb_ref_combine_clusteriP7reads_tPi "$B/kthread_cb.o"
+# N2: kthread_dump[_pe].o stays linked for cluster_dump[_pe] (info.txt, the single-read and id files), but its per-contig worker
+# kt_dump_[pe_]for is WEAKENED so that the shim's definition (device encoding + dropin/mcb_dump_writer.h) is the one cluster_dump
+# calls; a second copy of the object with everything else made local keeps the reference's worker reachable as
+# mcb_ref_kt_dump_[pe_]for (MCB_HOST_DUMP=1).  MCB_KEEP_DUMP=1 at build time leaves the object alone.
+EXTRA=""
+if [ "${MCB_KEEP_DUMP:-0}" != 1 ]; then
+  DUMP=kthread_dump; SYM=_Z11kt_dump_foriP7reads_ti; NEW=_Z19mcb_ref_kt_dump_foriP7reads_ti
+  [ "$MODE" = pe ] && { DUMP=kthread_dump_pe; SYM=_Z14kt_dump_pe_foriP7reads_ti; NEW=_Z22mcb_ref_kt_dump_pe_foriP7reads_ti; }
+  NCALL=$(objdump -dr "$B/$DUMP.o" | grep -c "R_X86_64_PLT32[[:space:]]*$SYM" || true)
+  [ "$NCALL" -ge 1 ] || { echo "$DUMP.o does not call $SYM through its symbol: cannot interpose the dump worker" >&2; exit 4; }
+  objcopy --redefine-sym $SYM=$NEW -G $NEW "$B/$DUMP.o" "$B/${DUMP}_refworker.o"
+  objcopy --weaken-symbol=$SYM "$B/$DUMP.o"
+  EXTRA="$B/${DUMP}_refworker.o"
+fi
 ALL=""; for f in $KEPT; do ALL="$ALL $B/$f.o"; done
 LIBDIR=$ROOT/minicom_b200
-g++ -O3 -fopenmp $ALL "$B/mcb_dropin.o" -L"$LIBDIR" -lminicom_b200 -Wl,-rpath,'$ORIGIN/../../minicom_b200' -o "$HERE/_build/minicom_b200_L${L}_${MODE}" -lm -lz -lpthread
+g++ -O3 -fopenmp $ALL $EXTRA "$B/mcb_dropin.o" -L"$LIBDIR" -lminicom_b200 -Wl,-rpath,'$ORIGIN/../../minicom_b200' -o "$HERE/_build/minicom_b200_L${L}_${MODE}" -lm -lz -lpthread
 echo "built $HERE/_build/minicom_b200_L${L}_${MODE}"
 if [ "$WRAPPED" = wrap ]; then
   g++ $CXXFLAGS -c "$ROOT/oracle/ref/mcref_wrap.cpp" -o "$B/mcref_wrap.o"
   WRAP="-Wl,--wrap=_Z12kt_for_readsiP7reads_tl -Wl,--wrap=_Z13kt_for_bucketiP7reads_tl -Wl,--wrap=_Z17mm_idx_generationiP8mm_idx_t -Wl,--wrap=_Z15combine_clusteriP7reads_tPi -Wl,--wrap=_Z12realign_hashiP7reads_tii"
   mkdir -p "$ROOT/oracle/_ref"
-  g++ -O3 -fopenmp $ALL "$B/mcb_dropin.o" "$B/mcref_wrap.o" $WRAP -L"$LIBDIR" -lminicom_b200 -Wl,-rpath,'$ORIGIN/../../minicom_b200' -o "$ROOT/oracle/_ref/minicom_b200_L${L}_${MODE}_wrapped" -lm -lz -lpthread
+  g++ -O3 -fopenmp $ALL $EXTRA "$B/mcb_dropin.o" "$B/mcref_wrap.o" $WRAP -L"$LIBDIR" -lminicom_b200 -Wl,-rpath,'$ORIGIN/../../minicom_b200' -o "$ROOT/oracle/_ref/minicom_b200_L${L}_${MODE}_wrapped" -lm -lz -lpthread
   echo "built $ROOT/oracle/_ref/minicom_b200_L${L}_${MODE}_wrapped"
 fi

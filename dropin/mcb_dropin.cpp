@@ -6,9 +6,11 @@
 // bbhashdict.o) — SURVEY.md §8b:
 //     kt_for_reads  kt_for_bucket  mm_idx_init  mm_idx_generation  mm_idx_get  mm_idx_destroy  realign_hash
 //     mm_sketch_lh_ori  seq_nt4_table  invert_code_rule
-// plus combine_cluster (N1: the contig merge on the device, kthread_cb.o's own is kept under another name) and the five
+// plus combine_cluster (N1: the contig merge on the device, kthread_cb.o's own is kept under another name), the five
 // functions of bseq.o (N3: bseq_open bseq_read bseq_read_second bseq_close bseq_eof — the FASTQ reader, which here packs the
-// reads for the device while it parses; build with MCB_KEEP_BSEQ=1 to link the reference's bseq.o instead).
+// reads for the device while it parses; build with MCB_KEEP_BSEQ=1 to link the reference's bseq.o instead) and kt_dump_for /
+// kt_dump_pe_for (N2: the per-contig half of the dump stage — member sort, diff encoding of every read on the device, and the
+// per-thread-slot files; kthread_dump[_pe].o stays linked for cluster_dump[_pe], its own worker is weakened by build_dropin.sh).
 // It is compiled inside the reference tree against the reference's headers (breads.h, kvec.h and the generated
 // config.h), the way a maintainer would add it; it contains marshalling only — every computation is
 // a call into the C-ABI (include/minicom_b200.h).  Cluster placement equals the num_thr=1 layout of the reference
@@ -24,6 +26,7 @@ static inline void set_readlen(mcb_params *p, int v) { p->readlen = v; }
 #include "breads.h"
 #include "kvec.h"
 #include "config.h"
+#include "mcb_dump_writer.h"
 
 // ---- data symbols (sketch.c:8-25, kthread_bucket.c:64)
 unsigned char seq_nt4_table[256] = {
@@ -41,6 +44,7 @@ static mcb_group *g_grp = 0;    // MCB_DEVICES=0,1,...: the same calls over seve
 static double g_wall[4];      // for_reads, for_bucket, idx_build, realign (host wall seconds inside the entry points)
 static int g_calls[4];
 static double g_wall_combine = 0;   // combine_cluster (the contig merge)
+static double g_wall_dump = 0;      // kt_dump_for (the per-contig half of the dump stage)
 static bool g_contigs_on_device = false;   // the device merge handed its contigs to Stage 2: realign_hash need not ship them
 static std::string g_realign_detail;
 
@@ -142,9 +146,9 @@ struct McbAtExit {
 				dev += "}";
 				fprintf(f, "{\"n_reads\": %d, \"readlen\": %d, \"threads\": %d, \"kt_for_reads\": %.6f, \"kt_for_bucket\": %.6f, "
 				        "\"mm_idx_generation\": %.6f, \"n_idx\": %d, \"realign_hash\": %.6f, \"n_realign\": %d, \"realign_rounds\": [%s], "
-				        "\"kernel_launches\": %llu, \"combine_cluster\": %.6f, \"device_ms\": %s}\n",
+				        "\"kernel_launches\": %llu, \"combine_cluster\": %.6f, \"kt_dump_for\": %.6f, \"device_ms\": %s}\n",
 				        reads ? reads->n_seq : 0, reads ? reads->seq_len : 0, n_threads, g_wall[0], g_wall[1], g_wall[2], g_calls[2], g_wall[3], g_calls[3],
-				        g_realign_detail.c_str(), g_ctx ? (unsigned long long)mcb_kernel_launches(g_ctx) : 0ull, g_wall_combine, dev.c_str());     // (group: rank 0's launches, per-timer maximum over the ranks)
+				        g_realign_detail.c_str(), g_ctx ? (unsigned long long)mcb_kernel_launches(g_ctx) : 0ull, g_wall_combine, g_wall_dump, dev.c_str());     // (group: rank 0's launches, per-timer maximum over the ranks)
 				fclose(f);
 			}
 		}
@@ -421,3 +425,68 @@ void realign_hash(int n_threads_, reads_t *r, int index, int max_threshold)
 	g_realign_detail += buf;
 	g_wall[3] += dt; g_calls[3]++;
 }
+
+// ---- kt_dump_for (kthread_dump.c:333) / kt_dump_pe_for (kthread_dump_pe.c:180): N2.
+// The diff encoding of every member read (print_encode's loop) runs on the device, on the reads kt_for_reads left there; the
+// writer (mcb_dump_writer.h) lays the bytes out in the reference's files.  On several GPUs the reads are spread over the ranks,
+// so the encoding uses a context of its own on the first device, loaded from the packed read set.  MCB_HOST_DUMP=1 runs the
+// reference's own workers instead (linked as mcb_ref_kt_dump_[pe_]for by build_dropin.sh).
+#ifndef MCB_KEEP_DUMP
+struct DeviceEncoder : McbDumpEncoder {
+	mcb_ctx *ctx;
+	std::vector<uint64_t> off;
+	explicit DeviceEncoder(mcb_ctx *c) : ctx(c) {}
+	int encode(const uint64_t *members, const uint64_t *moff, const char *refs, const uint64_t *roff, uint64_t nc, const uint64_t **enc_off, const char **enc)
+	{
+		mcb_encode_result res;
+		int rc = mcb_dump_encode(ctx, members, moff, refs, roff, nc, &res);
+		if (rc) die("cluster_dump (mcb_dump_encode)", rc);
+		*enc_off = res.enc_off; *enc = res.enc;
+		return 0;
+	}
+};
+#ifdef _PE
+void mcb_ref_kt_dump_pe_for(int n_threads, reads_t *reads, int index);
+void kt_dump_pe_for(int n_threads_, reads_t *r, int index)
+#else
+void mcb_ref_kt_dump_for(int n_threads, reads_t *reads, int index);
+void kt_dump_for(int n_threads_, reads_t *r, int index)
+#endif
+{
+	if (getenv("MCB_HOST_DUMP")) {
+#ifdef _PE
+		mcb_ref_kt_dump_pe_for(n_threads_, r, index);
+#else
+		mcb_ref_kt_dump_for(n_threads_, r, index);
+#endif
+		return;
+	}
+	double t0 = realtime();
+	mcb_ctx *ctx = ctx_for(r);
+	mcb_ctx *own = 0;
+	if (g_grp) {                                                 // reads are spread over the ranks: a context of its own on the first device
+		mcb_params p;
+		memset(&p, 0, sizeof p);
+		set_readlen(&p, r->seq_len); p.k = r->k; p.b = r->b; p.rw = r->rw;
+		p.first_mininum = first_mininum; p.diff_threshold = diff_threshold; p.max_rounds = max_rounds;
+		p.device = 0;
+		if (const char *list = getenv("MCB_DEVICES")) p.device = atoi(list);
+		int rc = mcb_create(&p, &own);
+		if (rc) die("cluster_dump (mcb_create)", rc);
+		mcb_reads_result rr;
+		mcb_readset_view v;
+		memset(&v, 0, sizeof v);
+		if (g_rs) mcb_readset_get(g_rs, &v);
+		// the host strings carry the N replacement by now, the packed read set does not need it: both give the same table + N side table
+		rc = (g_rs && v.n_reads == (uint64_t)r->n_seq) ? mcb_for_reads_packed(own, v.packed, v.n_reads, v.nread_rid, v.nmask, v.n_nreads, &rr)
+		                                                : MCB_ESTATE;
+		if (rc == MCB_ESTATE) { fprintf(stderr, "minicom_b200: the dump stage on several GPUs needs the packed read set of the shim's FASTQ reader (or MCB_HOST_DUMP=1)\n"); exit(1); }
+		if (rc) die("cluster_dump (mcb_for_reads_packed)", rc);
+		ctx = own;
+	}
+	DeviceEncoder E(ctx);
+	mcb_dump_workers(n_threads_, r, index, E);
+	if (own) mcb_destroy(own);
+	g_wall_dump += realtime() - t0;
+}
+#endif

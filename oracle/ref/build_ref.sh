@@ -53,6 +53,20 @@ if [ ! -x "$OUT/decompress" ]; then
   g++ -O3 -std=c++11 -w -march=x86-64-v3 -fopenmp -include stdint.h -I$B -I$HERE -I$HERE/../../dropin -I$REF "$REF/decompress.c" -o "$OUT/decompress" -lm -lz -lpthread
 fi
 echo "built $OUT/minicom_ref_L${L}_${MODE}"
+# CPU check of the dump writer (dropin/mcb_dump_writer.h, N2): the reference with its kt_dump_[pe_]for weakened and replaced by the
+# writer + the oracle's print_encode (mcref_dumpcheck.cpp).  usage: build_ref.sh <readlen> <mode> dumpcheck
+if [ "${3:-}" = dumpcheck ]; then
+  DUMP=kthread_dump; SYM=_Z11kt_dump_foriP7reads_ti
+  [ "$MODE" = pe ] && { DUMP=kthread_dump_pe; SYM=_Z14kt_dump_pe_foriP7reads_ti; }
+  NCALL=$(objdump -dr "$B/$DUMP.o" | grep -c "R_X86_64_PLT32[[:space:]]*$SYM" || true)
+  [ "$NCALL" -ge 1 ] || { echo "$DUMP.o does not call $SYM through its symbol" >&2; exit 4; }
+  objcopy --weaken-symbol=$SYM "$B/$DUMP.o" "$B/${DUMP}_weak.o"
+  g++ $CXXFLAGS -c "$HERE/mcref_dumpcheck.cpp" -o "$B/mcref_dumpcheck.o"
+  gcc -O2 -std=c99 -c "$HERE/../mc_oracle.c" -o "$B/mc_oracle.o"
+  ALLW="${ALL/$B\/$DUMP.o/$B\/${DUMP}_weak.o}"
+  g++ -O3 -fopenmp $ALLW "$B/mcref_wrap.o" "$B/mcref_dumpcheck.o" "$B/mc_oracle.o" $WRAP -o "$OUT/minicom_ref_L${L}_${MODE}_dumpcheck" -lm -lz -lpthread
+  echo "built $OUT/minicom_ref_L${L}_${MODE}_dumpcheck"
+fi
 # unit-level entry points of the reference (hash64, mm_sketch_two, mm_sketch_lh_ori, radix_sort_128x, bseq_read) for ctypes tests
 if [ ! -f "$OUT/libmcref_units.so" ] || [ "$HERE/mcref_units.cpp" -nt "$OUT/libmcref_units.so" ] || [ "$HERE/mcref_units_bseq.cpp" -nt "$OUT/libmcref_units.so" ]; then
   g++ -O2 -std=c++11 -w -fPIC -shared -I$B -I$HERE -I$HERE/../../dropin -I$REF "$HERE/mcref_units.cpp" "$HERE/mcref_units_sort.cpp" "$HERE/mcref_units_bseq.cpp" "$REF/misc.c" "$REF/bseq.c" -o "$OUT/libmcref_units.so" -lz
