@@ -52,7 +52,11 @@ if [ "${MCB_KEEP_DUMP:-0}" != 1 ]; then
   [ "$MODE" = pe ] && { DUMP=kthread_dump_pe; SYM=_Z14kt_dump_pe_foriP7reads_ti; NEW=_Z22mcb_ref_kt_dump_pe_foriP7reads_ti; }
   NCALL=$(objdump -dr "$B/$DUMP.o" | grep -c "R_X86_64_PLT32[[:space:]]*$SYM" || true)
   [ "$NCALL" -ge 1 ] || { echo "$DUMP.o does not call $SYM through its symbol: cannot interpose the dump worker" >&2; exit 4; }
-  objcopy --redefine-sym $SYM=$NEW -G $NEW "$B/$DUMP.o" "$B/${DUMP}_refworker.o"
+  # (only the object's own strong definitions are made local: COMDAT / weak items such as DW.ref.__gxx_personality_v0 must stay
+  # as they are, pthread_exit in the reference's workers unwinds through them)
+  LARGS=""
+  for s in $(nm "$B/$DUMP.o" | awk '$2 ~ /^[TBDR]$/ {print $3}' | grep -v "^$SYM\$"); do LARGS="$LARGS --localize-symbol=$s"; done
+  objcopy --redefine-sym $SYM=$NEW $LARGS "$B/$DUMP.o" "$B/${DUMP}_refworker.o"
   objcopy --weaken-symbol=$SYM "$B/$DUMP.o"
   EXTRA="$B/${DUMP}_refworker.o"
 fi

@@ -66,3 +66,25 @@ def test_dropin_directory_matches_reference_manifest(name):
         rt = refdump.roundtrip(r["out"], wd, c["mode"], reads, reads2)
     print(f"{name}: {len(got)} files byte-identical to the reference (num_thr=1); round trip {rt}; {time.time() - t0:.0f}s; front end "
           f"{sum(r['timing'][k] for k in ('kt_for_reads', 'kt_for_bucket', 'mm_idx_generation', 'realign_hash')):.2f}s inside the entry points")
+
+
+@pytest.mark.parametrize("knob", [{"MCB_HOST_MERGE": "1"}, {"MCB_HOST_DUMP": "1"}, {"MCB_ASCII_READS": "1"}, {"MCB_HOST_MERGE": "1", "MCB_HOST_DUMP": "1", "MCB_ASCII_READS": "1"}],
+                         ids=["host_merge", "host_dump", "ascii_reads", "round1_paths"])
+def test_dropin_alternative_paths_write_the_same_directory(knob):
+    """The drop-in's switches between the device and the reference's host code for the stages next to the path (contig merge N1,
+    dump worker N2, FASTQ reader N3) must not change a byte: C1o (1 M reads, order-preserving) against the reference manifest with
+    each of them flipped.  (MCB_HOST_MERGE=1 is what the sharded bench's recording run uses.)"""
+    with open(os.path.join(GOLDEN, "manifest_C1o.json")) as f:
+        man = json.load(f)
+    c = man["config"]
+    exe = refdump.dropin_binary(c["L"], c["mode"])
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} not built")
+    import make_manifests
+    reads, reads2 = make_manifests.make_reads(c)
+    with tempfile.TemporaryDirectory() as wd:
+        r = refdump.run_reference(reads, wd, mode=c["mode"], env_opts=dict(c["env"], **knob), threads=1, dump=False, reads2=reads2, exe=exe)
+        got = {f: _sha(os.path.join(r["out"], f)) for f in sorted(os.listdir(r["out"]))}
+    assert sorted(got) == sorted(man["out"])
+    bad = [f for f in got if got[f] != man["out"][f]]
+    assert not bad, f"{knob}: files differ from the reference's: {bad}"
