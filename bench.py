@@ -520,7 +520,11 @@ def bench_pipeline(args):
         par.update({"manifest": os.path.relpath(path, ROOT), "against": "unmodified reference, num_thr=1, same seeded reads (tests/golden/make_manifests.py)",
                     "covers": "read classes, minimizer tuples, seed contigs, singles, index tuples, the first index (keys + posting order), the contigs after the device merge "
                               "(members, order, consensus), and per threshold round the singles, claims in append order, sg_flag and poly-A/T diversions"})
-    log(f"parity: {json.dumps(par)}")
+    else:
+        # no manifest committed for this workload (yet): the digests themselves go into the line, so that they can be compared with a
+        # reference manifest made later (tests/golden/make_manifests.py) without another GPU run
+        par.update({"note": "no reference manifest for this workload at run time; digest values included", "values": got})
+    log(f"parity: {json.dumps({k: v for k, v in par.items() if k != 'values'})}")
     del cr, got
     api.VIEW_COPY = False
     counters, wall = {}, {}
