@@ -176,3 +176,69 @@ def test_oracle_agrees_with_the_reference_on_the_adversarial_strings():
         cnt = R.ref_sketch_lh_ori(s, len(s), w, k, trial, buf.ctypes.data, 4096)
         got, n_got = O.sketch_lh(s, w, k, trial, cap=4096)
         assert n_got == cnt and np.array_equal(got, buf[:cnt]), (s, w, k)
+
+
+# ---------------------------------------------------------------- 3. top-aligned arithmetic (mcb_hash64_ta, MCB_TA_ROLL, mcb_common.cuh)
+# For 16 < k < 32 the device keeps k-mers and hashes in the TOP 2k bits of a pair of 32-bit halves (value << (64 - 2k)): hash64's
+# "& mask" after each multiplication becomes the wrap-around of 64-bit arithmetic, x ^= x >> s needs the shifted-in low bits
+# cleared, and some shifts are written as multiplications by powers of two (IMAD / IMAD.HI on the FMA pipe).  Restated here with
+# Python integers, 32 bits at a time exactly as the kernel does it, and compared with the oracle's hash64 / the plain roll.
+M32 = (1 << 32) - 1
+
+
+def _umulhi(a, b):
+    return ((a * b) >> 32) & M32
+
+
+def _madhi(a, b, c):
+    return (_umulhi(a, b) + c) & M32
+
+
+def hash64_top_aligned(lo, hi, k):
+    sh = 64 - 2 * k
+    lm = (~((1 << sh) - 1)) & M32
+    m24, m14, m28 = 1 << 8, 1 << 18, 1 << 4
+    sub = ((1 << 64) - (1 << sh)) & FULL
+    t = (lo * 0x1FFFFF + sub) & FULL
+    hi = (hi * 0x1FFFFF + (t >> 32)) & M32
+    lo = t & M32
+    fl, u = _madhi(lo, m24, (hi * m24) & M32), _umulhi(hi, m24)                  # x ^= x >> 24: funnel shift as IMAD + IMAD.HI
+    lo, hi = lo ^ (fl & lm), hi ^ u
+    t = lo * 265
+    hi = (hi * 265 + (t >> 32)) & M32
+    lo = t & M32
+    fl, u = (((hi << 32) | lo) >> 14) & M32, _umulhi(hi, m14)                    # x ^= x >> 14
+    lo, hi = lo ^ (fl & lm), hi ^ u
+    t = lo * 21
+    hi = (hi * 21 + (t >> 32)) & M32
+    lo = t & M32
+    fl, u = (((hi << 32) | lo) >> 28) & M32, _umulhi(hi, m28)                    # x ^= x >> 28
+    lo, hi = lo ^ (fl & lm), hi ^ u
+    t = lo * 0x80000001
+    hi = (hi * 0x80000001 + (t >> 32)) & M32
+    lo = t & M32
+    return (hi << 32) | lo
+
+
+@pytest.mark.parametrize("k", list(range(17, 32)))
+def test_top_aligned_hash_and_roll_equal_the_plain_arithmetic(k):
+    rng = np.random.default_rng(k)
+    mask, sh = (1 << (2 * k)) - 1, 64 - 2 * k
+    keys = [0, 1, mask, mask - 1, 1 << (2 * k - 1)] + [int(x) & mask for x in rng.integers(0, 1 << 62, size=3000)]
+    for key in keys:
+        kp = (key << sh) & FULL
+        got = hash64_top_aligned(kp & M32, kp >> 32, k)
+        assert got & ((1 << sh) - 1) == 0, "a top-aligned hash has empty low bits"
+        assert got >> sh == O.hash64(key, mask)
+    # the roll (sketch.c:257-259): f = (f << 2 | c) & mask, r = (r >> 2) | ((3 ^ c) << 2(k-1)), on the halves
+    lm, csh, p30, neg30 = (~((1 << sh) - 1)) & M32, 1 << sh, 1 << 30, (-(1 << 30)) & M32
+    f = r = 0
+    flo = fhi = rlo = rhi = 0
+    for c in rng.integers(0, 4, size=2000).tolist():
+        f = (f << 2 | c) & mask
+        r = (r >> 2) | ((3 ^ c) << (2 * (k - 1)))
+        fhi = ((fhi << 2) | (flo >> 30)) & M32
+        flo = (flo * 4 + c * csh) & M32
+        rlo = ((((rhi << 32) | rlo) >> 2) & M32) & lm
+        rhi = _madhi(rhi, p30, (c * neg30 + 0xC0000000) & M32)
+        assert ((fhi << 32) | flo) == (f << sh) and ((rhi << 32) | rlo) == (r << sh)
